@@ -1,0 +1,422 @@
+"""CPU oracle: NumPy restatement of JAX-Fluids' single-phase convective hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in `jaxfluids_b200/` may import this module;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs use it, and only as the checker / CPU baseline.
+
+Pinning: this restatement performs the reference's elementwise operations in
+the reference's order, so on NumPy it is BIT-IDENTICAL to the reference's own
+Python sources executed on the NumPy `jax` stand-in (oracle/refharness).  That
+identity is asserted by tests/test_oracle_pinning.py (in the build container,
+where /root/reference exists) and, everywhere, against the committed fixtures
+tests/golden/*.npz generated from the reference by oracle/refharness/make_goldens.py.
+The reference ships no tests/golden vectors of its own for this path.
+
+All file:line citations are relative to /root/reference/src/jaxfluids/.
+
+Layout: buffers are C-order (5, X, Y, Z); an active axis carries `nh` halo
+cells on both sides, an inactive axis has extent 1 (initialization/
+helper_functions.py:49).  Variables: prims (rho,u,v,w,p), cons (rho,rho u,rho v,
+rho w,E) (equation_information.py:92-110).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Sequence, Tuple
+
+import numpy as np
+
+EPS = float(np.finfo(np.float64).eps)          # config/precision.py:44-55 (eps, fp64)
+STENCIL_EPS = 1e-30                            # config/precision.py:53 (spatial stencil eps, fp64)
+FACES = ("east", "west", "north", "south", "top", "bottom")   # domain/__init__.py:5-7
+FACE_AXIS = {"east": 0, "west": 0, "north": 1, "south": 1, "top": 2, "bottom": 2}
+MINOR_AXES = ((2, 3), (3, 1), (1, 2))          # equation_information.py:110 (velocity_minor_axes)
+
+RK = {  # time_integration/{euler,RK2,RK3}.py
+    "EULER": dict(stages=1, dt_mult=(1.0,), blend=()),
+    "RK2": dict(stages=2, dt_mult=(1.0, 0.5), blend=((0.5, 0.5),)),
+    "RK3": dict(stages=3, dt_mult=(1.0, 0.25, 2.0 / 3.0), blend=((0.25, 0.75), (2.0 / 3.0, 1.0 / 3.0))),
+}
+
+
+@dataclass
+class Setup:
+    """The subset of case + numerical setup the path depends on."""
+    cells: Tuple[int, int, int]
+    domain: Tuple[Tuple[float, float], ...]      # ((xlo,xhi),(ylo,yhi),(zlo,zhi))
+    bc: Dict[str, str]                           # face -> PERIODIC|SYMMETRY|ZEROGRADIENT|INACTIVE
+    gamma: float
+    nh: int = 5
+    recon: str = "CHAR-PRIMITIVE"                # or PRIMITIVE
+    riemann: str = "HLLC"                        # or RUSANOV
+    integrator: str = "RK3"
+    cfl: float = 0.5
+    fixed_timestep: float | None = None
+    active: Tuple[int, ...] = field(init=False)
+
+    def __post_init__(self):
+        self.cells = tuple(int(c) for c in self.cells)
+        self.active = tuple(i for i in range(3) if self.cells[i] > 1)
+
+    # domain/mesh_creation/homogenous.py:13 ; domain_information.py:290
+    @property
+    def dx(self):
+        return tuple(np.float64((self.domain[i][1] - self.domain[i][0]) / self.cells[i]) for i in range(3))
+
+    @property
+    def inv_dx(self):
+        return tuple(np.float64(1.0) / d for d in self.dx)
+
+    @property
+    def dx_min(self):                            # domain_information.py:697-702
+        return min(self.dx[i] for i in self.active)
+
+    @property
+    def shape(self):                             # initialization/helper_functions.py:49
+        return (5,) + tuple(n + 2 * self.nh if n > 1 else 1 for n in self.cells)
+
+    @property
+    def interior(self):
+        nh = self.nh
+        return tuple(slice(nh, -nh) if self.cells[i] > 1 else slice(None) for i in range(3))
+
+    def cell_centers(self):                      # homogenous.py:14
+        out = []
+        for i in range(3):
+            lo, hi = self.domain[i]
+            d = (hi - lo) / self.cells[i]
+            out.append(np.linspace(lo + d / 2, hi - d / 2, self.cells[i]))
+        return out
+
+
+# --------------------------------------------------------------------------
+# equation of state / variable transforms
+# --------------------------------------------------------------------------
+def cons_from_prims(p, gamma):
+    """equation_manager.py:93-101 ; ideal_gas.py:85-88 ; math/sum_consistent.py:22-24."""
+    rho = p[0]
+    e = p[4] / (rho * (gamma - 1.0))
+    E = rho * (0.5 * (np.square(p[1]) + np.square(p[2]) + np.square(p[3])) + e)
+    return np.stack([rho, rho * p[1], rho * p[2], rho * p[3], E], axis=0)
+
+
+def prims_from_cons(c, gamma):
+    """equation_manager.py:164-171 ; ideal_gas.py:73-75."""
+    rho = c[0]
+    one_rho = 1.0 / rho
+    u, v, w = c[1] * one_rho, c[2] * one_rho, c[3] * one_rho
+    e = c[4] * one_rho - 0.5 * (np.square(u) + np.square(v) + np.square(w))
+    p = (gamma - 1.0) * e * rho
+    return np.stack([rho, u, v, w, p], axis=0)
+
+
+def speed_of_sound(p, rho, gamma):
+    """ideal_gas.py:69-71."""
+    return np.sqrt(gamma * p / rho)
+
+
+def physical_flux(p, c, axis):
+    """equation_manager.py:237-252."""
+    m = c[axis + 1]
+    f = [m, m * p[1], m * p[2], m * p[3], p[axis + 1] * (c[4] + p[4])]
+    f[axis + 1] = f[axis + 1] + p[4]
+    return np.stack(f, axis=0)
+
+
+# --------------------------------------------------------------------------
+# halo fill (outer boundaries)
+# --------------------------------------------------------------------------
+def halo_fill(prims, cons, s: Setup):
+    """halos/halo_manager.py:146-234 -> halos/outer/material.py:94-287, 868-894.
+
+    Source slices: halos/outer/boundary_condition.py:563-595; symmetry sign of the
+    face-normal velocity :698-731; faces in the order east..bottom; transverse
+    range = interior; mask = 1.0 so `halo*(1-mask) + new*mask`.
+    Returns new (prims, cons)."""
+    prims, cons = prims.copy(), cons.copy()
+    nh = s.nh
+    inter = s.interior
+    for face in FACES:
+        ax = FACE_AXIS[face]
+        kind = s.bc[face]
+        if ax not in s.active or kind == "INACTIVE":
+            continue
+        hi = face in ("east", "north", "top")
+        if kind == "PERIODIC":
+            src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
+        elif kind == "SYMMETRY":
+            src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
+        elif kind == "ZEROGRADIENT":
+            src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)
+        else:
+            raise NotImplementedError(kind)
+        dst = slice(-nh, None) if hi else slice(0, nh)
+        sl_src = [slice(None)] + list(inter)
+        sl_dst = [slice(None)] + list(inter)
+        sl_src[1 + ax] = src
+        sl_dst[1 + ax] = dst
+        hp = prims[tuple(sl_src)]
+        if kind == "SYMMETRY":
+            sign = np.ones((5, 1, 1, 1))
+            sign[1 + ax] *= -1.0
+            hp = hp * sign
+        hc = cons_from_prims(hp, s.gamma)
+        prims[tuple(sl_dst)] = prims[tuple(sl_dst)] * (1 - 1.0) + hp * 1.0
+        cons[tuple(sl_dst)] = cons[tuple(sl_dst)] * (1 - 1.0) + hc * 1.0
+    return prims, cons
+
+
+# --------------------------------------------------------------------------
+# WENO5-Z
+# --------------------------------------------------------------------------
+_DR = (1 / 10, 6 / 10, 3 / 10)
+_CR = ((1 / 3, -7 / 6, 11 / 6), (-1 / 6, 5 / 6, 1 / 3), (1 / 3, 5 / 6, -1 / 6))
+
+
+def weno5z(a, b, c, d, e):
+    """weno5_base.py:34-51 and weno/weno5_z.py:32-52 on the 5 cells (i-2..i+2) (j=0)
+    or their mirror (i+3..i-1) (j=1)."""
+    beta_0 = 13.0 / 12.0 * np.square(a - 2 * b + c) + 1.0 / 4.0 * np.square(a - 4 * b + 3 * c)
+    beta_1 = 13.0 / 12.0 * np.square(b - 2 * c + d) + 1.0 / 4.0 * np.square(b - d)
+    beta_2 = 13.0 / 12.0 * np.square(c - 2 * d + e) + 1.0 / 4.0 * np.square(3 * c - 4 * d + e)
+    tau_5 = np.abs(beta_0 - beta_2)
+    alpha_0 = _DR[0] * (1.0 + tau_5 / (beta_0 + STENCIL_EPS))
+    alpha_1 = _DR[1] * (1.0 + tau_5 / (beta_1 + STENCIL_EPS))
+    alpha_2 = _DR[2] * (1.0 + tau_5 / (beta_2 + STENCIL_EPS))
+    one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2)
+    omega_0, omega_1, omega_2 = alpha_0 * one_alpha, alpha_1 * one_alpha, alpha_2 * one_alpha
+    p_0 = _CR[0][0] * a + _CR[0][1] * b + _CR[0][2] * c
+    p_1 = _CR[1][0] * b + _CR[1][1] * c + _CR[1][2] * d
+    p_2 = _CR[2][0] * c + _CR[2][1] * d + _CR[2][2] * e
+    return omega_0 * p_0 + omega_1 * p_1 + omega_2 * p_2
+
+
+def _window(prims, axis, s: Setup):
+    """The six cells k=i-2..i+3 around every face f (cell i = nh-1+f), transverse interior.
+    eigendecomposition.py:75-95,117 ; stencils/spatial_stencil.py:45-113."""
+    nh, n = s.nh, s.cells[axis]
+    out = []
+    for k in range(6):
+        sl = [slice(None)] + list(s.interior)
+        lo = nh - 3 + k
+        sl[1 + axis] = slice(lo, lo + n + 1)
+        out.append(prims[tuple(sl)])
+    return out
+
+
+# --------------------------------------------------------------------------
+# reconstruction
+# --------------------------------------------------------------------------
+def reconstruct(prims, axis, s: Setup):
+    """high_order_godunov.py:233-419 (PRIMITIVE :267-280, CHAR-PRIMITIVE :298-316,:401-402).
+    Returns (prims_L, prims_R, cons_L, cons_R), each (5, faces...)."""
+    w = _window(prims, axis, s)
+    if s.recon == "PRIMITIVE":
+        pl = weno5z(w[0], w[1], w[2], w[3], w[4])
+        pr = weno5z(w[5], w[4], w[3], w[2], w[1])
+    elif s.recon == "CHAR-PRIMITIVE":
+        g = s.gamma
+        ua = 1 + axis
+        m0, m1 = MINOR_AXES[axis]
+        # rows the tangential velocities occupy in characteristic space
+        # (eigendecomposition.py:69-73): axis0 -> (2,3); axis1 -> (3,2); axis2 -> (2,3)
+        e0, e1 = ((2, 3), (3, 2), (2, 3))[axis]
+        # frozen state, arithmetic mean of cells i and i+1 (eigendecomposition.py:139-148, 215-231)
+        ave = 0.5 * (w[2] + w[3])
+        c_ave = np.sqrt(g * ave[4] / ave[0])
+        cc_ave = c_ave * c_ave
+        rho_ave = ave[0]
+        # to characteristic variables (eigendecomposition.py:425-431)
+        chars = []
+        for x in w:
+            o = [None] * 5
+            o[0] = -0.5 / c_ave * x[ua] + 0.5 / (cc_ave * rho_ave) * x[4]
+            o[1] = x[0] - 1.0 / cc_ave * x[4]
+            o[e0] = x[m0]
+            o[e1] = x[m1]
+            o[4] = 0.5 / c_ave * x[ua] + 0.5 / (cc_ave * rho_ave) * x[4]
+            chars.append(np.stack(o, axis=0))
+        cl = weno5z(chars[0], chars[1], chars[2], chars[3], chars[4])
+        cr = weno5z(chars[5], chars[4], chars[3], chars[2], chars[1])
+        # back to primitives (eigendecomposition.py:517-521)
+        res = []
+        for x in (cl, cr):
+            o = [None] * 5
+            o[0] = rho_ave * (x[0] + x[4]) + x[1]
+            o[ua] = c_ave * (-x[0] + x[4])
+            o[m0] = x[e0]
+            o[m1] = x[e1]
+            o[4] = cc_ave * rho_ave * (x[0] + x[4])
+            res.append(np.stack(o, axis=0))
+        pl, pr = res
+    else:
+        raise NotImplementedError(s.recon)
+    return pl, pr, cons_from_prims(pl, s.gamma), cons_from_prims(pr, s.gamma)
+
+
+# --------------------------------------------------------------------------
+# Riemann solvers
+# --------------------------------------------------------------------------
+def einfeldt(u_L, u_R, a_L, a_R, rho_L, rho_R):
+    """solvers/riemann_solvers/signal_speeds.py:109-133."""
+    sL, sR = np.sqrt(rho_L), np.sqrt(rho_R)
+    one_dens = 1.0 / (sL + sR)
+    eta2 = 0.5 * sL * sR * one_dens * one_dens
+    u_bar = (sL * u_L + sR * u_R) * one_dens
+    d_bar = np.sqrt((sL * a_L * a_L + sR * a_R * a_R) * one_dens + eta2 * np.square(u_R - u_L))
+    return np.minimum(u_bar - d_bar, u_L - a_L), np.maximum(u_bar + d_bar, u_R + a_R)
+
+
+def sstar(u_L, u_R, p_L, p_R, rho_L, rho_R, S_L, S_R):
+    """signal_speeds.py:159-199."""
+    dL = rho_L * (S_L - u_L)
+    dR = rho_R * (S_R - u_R)
+    return ((p_R - p_L) + (u_L * dL - u_R * dR)) / (dL - dR)
+
+
+def _hllc_star_flux(p, c, S_K, S_star, axis, left):
+    """HLLC.py:41-78."""
+    ua = 1 + axis
+    m0, m1 = MINOR_AXES[axis]
+    pre = (S_K - p[ua]) / (S_K - S_star) * p[0]
+    us = [pre, pre, pre, pre,
+          pre * (c[4] / c[0] + (S_star - p[ua]) * (S_star + p[4] / p[0] / (S_K - p[ua])))]
+    us[ua] = us[ua] * S_star
+    us[m0] = us[m0] * p[m0]
+    us[m1] = us[m1] * p[m1]
+    us = np.stack(us, axis=0)
+    f = physical_flux(p, c, axis)
+    S = np.minimum(S_K, 0.0) if left else np.maximum(S_K, 0.0)
+    return f + S * (us - c)
+
+
+def hllc(pl, pr, cl, cr, axis, gamma):
+    """HLLC.py:80-126."""
+    ua = 1 + axis
+    aL = speed_of_sound(pl[4], pl[0], gamma)
+    aR = speed_of_sound(pr[4], pr[0], gamma)
+    S_L, S_R = einfeldt(pl[ua], pr[ua], aL, aR, pl[0], pr[0])
+    S_s = sstar(pl[ua], pr[ua], pl[4], pr[4], pl[0], pr[0], S_L, S_R)
+    fL = _hllc_star_flux(pl, cl, S_L, S_s, axis, True)
+    fR = _hllc_star_flux(pr, cr, S_R, S_s, axis, False)
+    return 0.5 * (1 + np.sign(S_s)) * fL + 0.5 * (1 - np.sign(S_s)) * fR
+
+
+def rusanov(pl, pr, cl, cr, axis, gamma):
+    """Rusanov.py:25-47."""
+    ua = 1 + axis
+    aL = speed_of_sound(pl[4], pl[0], gamma)
+    aR = speed_of_sound(pr[4], pr[0], gamma)
+    alpha = np.maximum(np.abs(pl[ua]) + aL, np.abs(pr[ua]) + aR)
+    return 0.5 * (physical_flux(pl, cl, axis) + physical_flux(pr, cr, axis)) - 0.5 * alpha * (cr - cl)
+
+
+# --------------------------------------------------------------------------
+# right-hand side
+# --------------------------------------------------------------------------
+def face_flux(prims, axis, s: Setup):
+    """high_order_godunov.py:117-231: face fluxes (5, N_axis+1, transverse interior)."""
+    pl, pr, cl, cr = reconstruct(prims, axis, s)
+    if s.riemann == "HLLC":
+        return hllc(pl, pr, cl, cr, axis, s.gamma)
+    if s.riemann == "RUSANOV":
+        return rusanov(pl, pr, cl, cr, axis, s.gamma)
+    raise NotImplementedError(s.riemann)
+
+
+def rhs_axis(prims, axis, s: Setup):
+    """space_solver.py:456-674 (convective branch: :489, :517-543, :597-599)."""
+    fc = face_flux(prims, axis, s)
+    f = np.zeros_like(fc) + fc                                          # :517, :545
+    lo = [slice(None)] * 4
+    hi = [slice(None)] * 4
+    lo[1 + axis] = slice(None, -1)
+    hi[1 + axis] = slice(1, None)
+    out = np.zeros((5,) + s.cells)
+    out = out + s.inv_dx[axis] * (f[tuple(lo)] - f[tuple(hi)])
+    return out
+
+
+def compute_rhs(prims, s: Setup):
+    """space_solver.py:151-453 (single phase, convective only): 0.0 + rhs_x + rhs_y + rhs_z."""
+    rhs = 0.0
+    for axis in s.active:
+        rhs = rhs + rhs_axis(prims, axis, s)
+    return rhs
+
+
+# --------------------------------------------------------------------------
+# time step size, positivity info
+# --------------------------------------------------------------------------
+def time_step_size(prims, s: Setup):
+    """time_integration/time_step_size.py:15-157 (convective contribution only)."""
+    if s.fixed_timestep:
+        return float(s.fixed_timestep)
+    pi = prims[(slice(None),) + s.interior]
+    c = speed_of_sound(pi[4], pi[0], s.gamma)
+    acc = 0.0
+    for i in s.active:
+        acc = acc + (np.abs(pi[1 + i]) + c)
+    dt = s.dx_min / (np.max(acc) + EPS)
+    dt = dt * s.cfl
+    return float(dt)
+
+
+def positivity_info(prims, s: Setup):
+    """solvers/positivity/positivity_handler.py:245-254: (min rho, min p) over the interior."""
+    pi = prims[(slice(None),) + s.interior]
+    return float(np.min(pi[0])), float(np.min(pi[4]))
+
+
+# --------------------------------------------------------------------------
+# initialisation and the step
+# --------------------------------------------------------------------------
+def initialize(prims_interior, s: Setup, from_user_buffer=False):
+    """initialization/material_fields_initializer.py:590-690 (IC evaluated on the mesh)
+    or :148-210/:425-497 (user array).  `prims_interior` is (5,Nx,Ny,Nz); with
+    from_user_buffer=True it is (5-3+dim, ...) and inactive velocities keep the
+    eps fill of the buffer (helper_functions.py:21-60), as in the reference."""
+    buf = np.ones(s.shape) * EPS
+    sl = (slice(None),) + s.interior
+    if from_user_buffer:
+        idx = [0] + [1 + i for i in s.active] + [4]
+        buf[(idx,) + s.interior] = prims_interior
+    else:
+        buf[sl] = prims_interior
+    cons = cons_from_prims(buf, s.gamma)
+    return halo_fill(buf, cons, s)
+
+
+def stage(prims, cons, cons_n, dt, k, s: Setup):
+    """One RK stage: simulation_manager.py:770-1047 (single-phase branch).
+    Returns (prims, cons, rhs)."""
+    rk = RK[s.integrator]
+    rhs = compute_rhs(prims, s)                                         # :796
+    if k > 0:                                                           # RK3.py:49-50
+        a, b = rk["blend"][k - 1]
+        cons = a * cons + b * cons_n
+    step = dt * rk["dt_mult"][k]                                        # RK3.py:60
+    cons = cons.copy()
+    sl = (slice(None),) + s.interior
+    cons[sl] = cons[sl] + step * rhs                                    # time_integrator.py:57
+    prims = prims_from_cons(cons, s.gamma)                              # :943
+    prims, cons = halo_fill(prims, cons, s)                             # :963
+    return prims, cons, rhs
+
+
+def step(prims, cons, dt, s: Setup, record=None):
+    """One full time step; returns (prims, cons, dt_next)."""
+    cons_n = cons
+    with np.errstate(all="ignore"):     # untouched corner cells hold eps/garbage, as in the reference
+        for k in range(RK[s.integrator]["stages"]):
+            prims, cons, rhs = stage(prims, cons, cons_n, dt, k, s)
+            if record is not None:
+                record["rhs"].append(rhs)
+                record["prims"].append(prims)
+                record["cons"].append(cons)
+    return prims, cons, time_step_size(prims, s)                        # simulation_manager.py:612-628
+
+
+def totals(cons, s: Setup):
+    ci = cons[(slice(None),) + s.interior]
+    return np.array([ci[v].sum() for v in range(5)])

@@ -1,0 +1,1 @@
+def use(*a, **k): pass
