@@ -1,0 +1,168 @@
+/* jxf_b200.h -- C ABI of the B200-native (sm_100a) convective-RHS / SSP-RK path
+ * that stands in for JAX-Fluids' single-phase space solver.
+ *
+ * Every entry point is enqueue-only on the caller's stream (`stream` is a
+ * cudaStream_t passed as void*), never allocates, frees or retains caller
+ * memory, and returns 0 on success or a negative jxf_status; the message of the
+ * last failure on the calling thread is available from jxf_last_error().
+ * All device buffers are fp64, C-order (5, X, Y, Z) with `nh` halo cells on
+ * both sides of every active axis and extent 1 on inactive axes -- the
+ * reference's buffer layout (initialization/helper_functions.py:49).
+ * The rhs buffer is interior-only, (5, Nx, Ny, Nz) (space_solver.py:489).
+ *
+ * Citations "ref:" are file:line under /root/reference/src/jaxfluids/.
+ * The XLA-FFI binding a maintainer would add on the reference side is shown in
+ * INTEGRATION.md; it forwards to exactly these symbols.
+ */
+#ifndef JXF_B200_H
+#define JXF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum jxf_status {
+  JXF_OK = 0,
+  JXF_ERR_BAD_ARG = -1,
+  JXF_ERR_UNSUPPORTED = -2,   /* valid reference option that this path does not implement */
+  JXF_ERR_CUDA = -3
+} jxf_status;
+
+/* ref: stencils/__init__.py:15-19 + godunov.reconstruction_variable (read_conservatives.py:126-203) */
+enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
+/* ref: solvers/riemann_solvers/__init__.py:16-34 */
+enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1 };
+enum { JXF_SIGNAL_EINFELDT = 0 };
+/* ref: time_integration/__init__.py:6-11 */
+enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2 };
+/* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */
+enum { JXF_BC_INACTIVE = 0, JXF_BC_PERIODIC = 1, JXF_BC_SYMMETRY = 2, JXF_BC_ZEROGRADIENT = 3, JXF_BC_NEIGHBOR = 4 };
+/* face order of the reference: domain/__init__.py:5-7 */
+enum { JXF_EAST = 0, JXF_WEST = 1, JXF_NORTH = 2, JXF_SOUTH = 3, JXF_TOP = 4, JXF_BOTTOM = 5 };
+
+typedef struct jxf_config {
+  int32_t n[3];          /* interior cells of this block per axis (1 = inactive axis)            */
+  int32_t nh;            /* conservatives.halo_cells (>= 3, ref: weno5_base.py:18)               */
+  double  inv_dx[3];     /* 1/dx per axis, as the reference forms it (domain_information.py:290) */
+  double  dx_min;        /* min over active axes (domain_information.py:697-702)                 */
+  double  gamma;         /* IdealGas specific_heat_ratio                                         */
+  double  cfl;           /* time_integration.CFL                                                 */
+  double  fixed_dt;      /* time_integration.fixed_timestep, 0 = CFL based                       */
+  int32_t recon;         /* JXF_RECON_*     (stencil is WENO5-Z)                                 */
+  int32_t riemann;       /* JXF_RIEMANN_*                                                        */
+  int32_t signal_speed;  /* JXF_SIGNAL_*                                                         */
+  int32_t integrator;    /* JXF_INT_*                                                            */
+  int32_t bc[6];         /* JXF_BC_* per face, order east,west,north,south,top,bottom            */
+} jxf_config;
+
+typedef struct jxf_solver* jxf_handle;
+
+const char* jxf_last_error(void);
+int jxf_version(void);
+
+/* Builds the immutable launch plan for one block. Host-only; touches no device memory. */
+int jxf_create(const jxf_config* cfg, jxf_handle* out);
+int jxf_destroy(jxf_handle h);
+
+/* Number of fp64 elements of a halo'd (5,X,Y,Z) buffer / of the interior-only rhs buffer. */
+int64_t jxf_field_elems(jxf_handle h);
+int64_t jxf_rhs_elems(jxf_handle h);
+/* Number of RK stages of the configured integrator. */
+int jxf_num_stages(jxf_handle h);
+
+/* ref: SpaceSolver.compute_rhs (solvers/space_solver.py:151-453), convective single-phase branch:
+ * rhs = 0.0 + rhs_x + rhs_y + rhs_z over the active axes.  prims: in, rhs: out. */
+int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, void* stream);
+
+/* ref: SpaceSolver.compute_rhs_xi (space_solver.py:456-674): one axis.
+ * accumulate=0: rhs = 0.0 + rhs_axis ; accumulate=1: rhs += rhs_axis. */
+int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream);
+
+/* One fused RK stage = compute_rhs + TimeIntegrator.perform_stage_integration
+ * (time_integrator.py:108-227, RK3.py:27-62) + get_primitives_from_conservatives
+ * (equation_manager.py:164-171) + outer face halo fill (halo_manager.py:146-234).
+ *   prims_in   : primitives at stage entry (with halos)                  [in]
+ *   prims_out  : primitives after the stage, must not alias prims_in     [out]
+ *   cons_in    : conservatives at stage entry                            [in]
+ *   cons_n     : conservatives at step entry U^n (unused for stage 0)    [in]
+ *   cons_out   : conservatives after the stage; may alias cons_in/cons_n [out]
+ *   rhs_scratch: interior-only scratch for the partial sums of the first
+ *                sweeps (may be NULL with one active axis)               [scratch]
+ *   dt_dev     : device pointer to the step's dt                         [in]
+ *   red_dev    : device pointer to 3 doubles {max sum(|u_i|+c), min rho, min p};
+ *                updated (max/min-combined) when `reduce` != 0; caller resets via jxf_reduce_reset.
+ *   fill_halo  : 0 = leave halos to the caller (multi-GPU exchange), 1 = local BC fill. */
+int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out,
+              const double* cons_in, const double* cons_n, double* cons_out,
+              double* rhs_scratch, const double* dt_dev, double* red_dev,
+              int reduce, int fill_halo, void* stream);
+
+/* One whole time step on a single block (ref: SimulationManager._do_integration_step,
+ * simulation_manager.py:536-668, and do_runge_kutta_stages :670-1077): all RK stages with
+ * local halo fill, the reductions on the last stage, then jxf_finish_step.
+ * State at entry: (prims_a, cons_a).  cons ends in cons_a; prims end in prims_a if the
+ * return value is 0, in prims_b if it is 1.  Negative return = error.  No host sync. */
+int jxf_step_fused(jxf_handle h, double* prims_a, double* prims_b, double* cons_a, double* cons_b,
+                   double* rhs_scratch, double* dt_dev, double* time_dev, double* red_dev,
+                   double* info_dev, int fill_halo, void* stream);
+
+/* ref: HaloManager.perform_halo_update_material (halos/halo_manager.py:146-234) for
+ * PERIODIC / SYMMETRY / ZEROGRADIENT faces (halos/outer/material.py:868-894); cons halos are
+ * recomputed from prim halos (:248-250).  Faces marked JXF_BC_NEIGHBOR are skipped. In place. */
+int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream);
+
+/* ref: EquationManager.get_primitives_from_conservatives / get_conservatives_from_primitives
+ * (equation_manager.py:164-171, 93-101) over the whole halo'd buffer. */
+int jxf_prims_from_cons(jxf_handle h, const double* cons, double* prims, void* stream);
+int jxf_cons_from_prims(jxf_handle h, const double* prims, double* cons, void* stream);
+
+/* ref: compute_time_step_size (time_integration/time_step_size.py:15-157) and the min rho / min p
+ * logging reductions (solvers/positivity/positivity_handler.py:245-254).
+ * jxf_reduce      : red_dev <- combine(red_dev, reductions over the interior of prims)
+ * jxf_reduce_reset: red_dev <- {0, +inf, +inf}
+ * jxf_finish_step : dt_dev <- CFL*dx_min/(red[0]+eps) (or fixed_dt); time_dev += dt_used;
+ *                   info_dev[0..2] <- red; red_dev reset.  All on device, no host sync. */
+int jxf_reduce(jxf_handle h, const double* prims, double* red_dev, void* stream);
+int jxf_reduce_reset(jxf_handle h, double* red_dev, void* stream);
+int jxf_finish_step(jxf_handle h, double* red_dev, double* dt_dev, double* time_dev,
+                    double* info_dev, void* stream);
+
+/* Inter-block face exchange helpers (ref: halos/inner/material.py:30-93).
+ * pack  : copies the `nh` interior layers adjacent to `face` of prims into a dense slab
+ *         (5, nh, T1, T2) (transverse extents = interior), ready for ncclSend.
+ * unpack: writes a received slab into the halo layers of `face` of prims and recomputes the
+ *         conservatives there (:83-88). */
+int64_t jxf_face_slab_elems(jxf_handle h, int face);
+int jxf_pack_face(jxf_handle h, int face, const double* prims, double* slab, void* stream);
+int jxf_unpack_face(jxf_handle h, int face, const double* slab, double* prims, double* cons, void* stream);
+
+/* Launch accounting and optional per-kernel timing (bench / roofline evidence).
+ * Kinds: 0..2 = sweep along axis 0..2 writing rhs; 3..5 = sweep along axis 0..2 with the fused
+ * RK-stage epilogue; 6 = halo fill; 7 = other (transforms, reductions, pack/unpack).
+ * With profiling enabled every launch is bracketed by cudaEventRecord on the launch stream
+ * (up to 4096 launches between reads).  jxf_profile_read synchronises on the recorded events and
+ * returns, per kind, the summed device time in ms, the number of timed launches and the number of
+ * launches issued since the last reset. */
+#define JXF_PROFILE_KINDS 8
+#define JXF_PROFILE_HALO 6
+#define JXF_PROFILE_OTHER 7
+int jxf_profile_enable(jxf_handle h, int enable);
+int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* launches, int reset);
+
+/* Test hook: the per-face device function (reconstruction + Riemann flux,
+ * ref: HighOrderGodunov.compute_flux_xi, high_order_godunov.py:117-231) on caller-supplied
+ * 6-cell windows.  windows: (n, 5, 6) doubles, flux: (n, 5) doubles, both on the device. */
+int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n,
+                        double gamma, double* flux, void* stream);
+
+/* Device FP64 FMA throughput probe for the roofline denominator (bench only):
+ * runs `iters` dependent-chain DFMAs x 8 chains per thread on a full grid; returns the
+ * number of DFMA issued in *n_fma; time it with events around the call. */
+int jxf_fp64_probe(double* scratch, int iters, int64_t* n_fma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JXF_B200_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of the C ABI declared in include/jxf_b200.h.
+
+The shared library is built in-tree by `__graft_entry__.build()` (or
+`python -m jaxfluids_b200.build`).  There is NO fallback: if the library is
+missing, import of the compute path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libjxf_b200.so")
+
+# names declared in include/jxf_b200.h (kept in sync by tests/test_abi.py)
+EXPORTS = (
+    "jxf_last_error", "jxf_version", "jxf_create", "jxf_destroy", "jxf_field_elems", "jxf_rhs_elems",
+    "jxf_num_stages", "jxf_compute_rhs", "jxf_sweep", "jxf_stage", "jxf_halo_fill", "jxf_prims_from_cons",
+    "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
+    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux",
+)
+
+RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
+RIEMANN = {"HLLC": 0, "RUSANOV": 1}
+SIGNAL = {"EINFELDT": 0}
+INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
+BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4}
+FACES = ("east", "west", "north", "south", "top", "bottom")
+
+
+class JxfConfig(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32 * 3),
+        ("nh", C.c_int32),
+        ("inv_dx", C.c_double * 3),
+        ("dx_min", C.c_double),
+        ("gamma", C.c_double),
+        ("cfl", C.c_double),
+        ("fixed_dt", C.c_double),
+        ("recon", C.c_int32),
+        ("riemann", C.c_int32),
+        ("signal_speed", C.c_int32),
+        ("integrator", C.c_int32),
+        ("bc", C.c_int32 * 6),
+    ]
+
+
+class JxfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libjxf_b200.so and declare the prototypes. Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise JxfError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` at the repo root. There is no CPU fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, i32, i64 = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
+    lib.jxf_last_error.restype = C.c_char_p
+    lib.jxf_last_error.argtypes = []
+    lib.jxf_version.restype = i32
+    lib.jxf_create.restype = i32
+    lib.jxf_create.argtypes = [C.POINTER(JxfConfig), C.POINTER(vp)]
+    lib.jxf_destroy.restype = i32
+    lib.jxf_destroy.argtypes = [vp]
+    for name in ("jxf_field_elems", "jxf_rhs_elems"):
+        getattr(lib, name).restype = i64
+        getattr(lib, name).argtypes = [vp]
+    lib.jxf_num_stages.restype = i32
+    lib.jxf_num_stages.argtypes = [vp]
+    lib.jxf_compute_rhs.restype = i32
+    lib.jxf_compute_rhs.argtypes = [vp, dp, dp, vp]
+    lib.jxf_sweep.restype = i32
+    lib.jxf_sweep.argtypes = [vp, i32, dp, dp, i32, vp]
+    lib.jxf_stage.restype = i32
+    lib.jxf_stage.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, i32, i32, vp]
+    lib.jxf_halo_fill.restype = i32
+    lib.jxf_halo_fill.argtypes = [vp, dp, dp, vp]
+    lib.jxf_prims_from_cons.restype = i32
+    lib.jxf_prims_from_cons.argtypes = [vp, dp, dp, vp]
+    lib.jxf_cons_from_prims.restype = i32
+    lib.jxf_cons_from_prims.argtypes = [vp, dp, dp, vp]
+    lib.jxf_reduce.restype = i32
+    lib.jxf_reduce.argtypes = [vp, dp, dp, vp]
+    lib.jxf_reduce_reset.restype = i32
+    lib.jxf_reduce_reset.argtypes = [vp, dp, vp]
+    lib.jxf_finish_step.restype = i32
+    lib.jxf_finish_step.argtypes = [vp, dp, dp, dp, dp, vp]
+    lib.jxf_face_slab_elems.restype = i64
+    lib.jxf_face_slab_elems.argtypes = [vp, i32]
+    lib.jxf_pack_face.restype = i32
+    lib.jxf_pack_face.argtypes = [vp, i32, dp, dp, vp]
+    lib.jxf_unpack_face.restype = i32
+    lib.jxf_unpack_face.argtypes = [vp, i32, dp, dp, dp, vp]
+    lib.jxf_fp64_probe.restype = i32
+    lib.jxf_fp64_probe.argtypes = [dp, i32, C.POINTER(i64), vp]
+    lib.jxf_step_fused.restype = i32
+    lib.jxf_step_fused.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, i32, vp]
+    lib.jxf_profile_enable.restype = i32
+    lib.jxf_profile_enable.argtypes = [vp, i32]
+    lib.jxf_profile_read.restype = i32
+    lib.jxf_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64), i32]
+    lib.jxf_debug_face_flux.restype = i32
+    lib.jxf_debug_face_flux.argtypes = [i32, i32, i32, dp, i64, C.c_double, dp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().jxf_last_error().decode("utf-8", "replace")
+        raise JxfError(f"jxf error {rc}: {msg}")

@@ -1,0 +1,903 @@
+// jxf_b200.cu -- sm_100a kernels + C ABI (include/jxf_b200.h) of the convective path.
+//
+// Kernel family (one per sweep direction kind):
+//   sweep_strided<A,..>: sweep axis A is NOT the contiguous axis. Lanes run along the
+//       contiguous axis (coalesced), each thread marches along A with a rolling 6-cell
+//       register window and keeps the previous face flux, so every face flux is computed once.
+//   sweep_contig<A,..>:  sweep axis A IS the contiguous axis. Lanes = consecutive faces
+//       of the flattened (row, face) sequence; the left face flux comes from lane-1 by
+//       warp shuffle (lane 0: carry from the previous iteration).
+// EPI=0 writes/accumulates the axis contribution into the interior-only rhs buffer
+// (space_solver.py:597-599, :314); EPI=1 (last active axis of a stage) fuses the RK
+// stage combination (RK3.py:49-60, time_integrator.py:57), primitive recovery
+// (equation_manager.py:164-171) and the CFL / min-rho / min-p reductions
+// (time_step_size.py:103-109, positivity_handler.py:246-247).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+#include "../../include/jxf_b200.h"
+#include "numerics.cuh"
+
+namespace jxf {
+
+struct Geom {
+  int n[3];            // interior cells
+  int ext[3];          // buffer extents (n + 2nh, or 1)
+  int off[3];          // nh on active axes, 0 on inactive
+  int nh;
+  long long st[3];     // element strides of the halo'd buffers
+  long long vst;       // variable stride of the halo'd buffers
+  long long rst[3];    // element strides of the interior-only rhs buffer
+  long long rvst;
+};
+
+struct SweepArgs {
+  const double* prims;     // stage-entry primitives (halo'd)
+  double* rhs;             // interior-only accumulator
+  const double* cons_in;   // EPI only
+  const double* cons_n;    // EPI only, stage > 0
+  double* cons_out;        // EPI only
+  double* prims_out;       // EPI only
+  const double* dt;        // EPI only (device scalar)
+  double* red;             // EPI only, 3 doubles
+  double ca, cb;           // RK blend U = ca*U + cb*U^n
+  double dt_mult;          // RK stage dt multiplier
+  double gamma;
+  double inv_dx;
+  int blend;               // stage > 0
+  int has_prev;            // EPI: rhs holds earlier axes' sum
+  int accumulate;          // !EPI: rhs += (1) or rhs = 0.0 + (0)
+  int reduce;              // EPI: update red
+  int active_mask;         // bit i = axis i active
+  int chunk_len;           // strided: cells per chunk along A
+  int span;                // contig: faces per range
+};
+
+// ---------------------------------------------------------------------------
+// cell finalisation shared by both sweep kinds
+// ---------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void finalize_cell(const Geom& g, const SweepArgs& a, long long hidx, long long ridx,
+                                              const double (&r)[5], double step, Red& red) {
+  if (EPI == 0) {
+    if (a.accumulate) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] += r[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = 0.0 + r[v];
+    }
+  } else {
+    double U[5], tot[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) U[v] = a.cons_in[hidx + v * g.vst];
+    if (a.has_prev) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) tot[v] = a.rhs[ridx + v * g.rvst] + r[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) tot[v] = 0.0 + r[v];
+    }
+    if (a.blend) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) U[v] = a.ca * U[v] + a.cb * a.cons_n[hidx + v * g.vst];
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) U[v] = U[v] + step * tot[v];
+    double p[5];
+    prims_from_cons(U, a.gamma, p);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      a.cons_out[hidx + v * g.vst] = U[v];
+      a.prims_out[hidx + v * g.vst] = p[v];
+    }
+    if (a.reduce) red.add_cell(p, a.gamma, a.active_mask);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// strided sweep: thread = one (C,O) column, marching along A over one chunk
+// ---------------------------------------------------------------------------
+template <int A, int RECON, int RIEMANN, int EPI>
+__global__ void __launch_bounds__(128) sweep_strided(const Geom g, const SweepArgs a, const int C, const int O) {
+  const long long plane = (long long)g.n[C] * g.n[O];
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  Red red;
+  red.init();
+  if (p < plane) {
+    const int io = (int)(p / g.n[C]);
+    const int ic = (int)(p - (long long)io * g.n[C]);
+    const int f0 = blockIdx.y * a.chunk_len;
+    const int f1 = min(f0 + a.chunk_len, g.n[A]);
+    const long long sA = g.st[A];
+    const long long col_h = (long long)(io + g.off[O]) * g.st[O] + (long long)(ic + g.off[C]) * g.st[C];
+    const long long col_r = (long long)io * g.rst[O] + (long long)ic * g.rst[C];
+    const double* base = a.prims + col_h + (long long)(g.off[A] + f0 - 3) * sA;   // cell f0-3
+    const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
+    double w[5][6], nx[5], Fp[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) w[v][k] = base[v * g.vst + k * sA];
+      nx[v] = base[v * g.vst + 5 * sA];
+      Fp[v] = 0.0;
+    }
+    for (int f = f0; f <= f1; ++f) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) w[v][5] = nx[v];
+      if (f < f1) {   // prefetch cell f+3 (<= n+2 < n+nh since nh >= 3)
+        const double* nb = base + (long long)(f - f0 + 6) * sA;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) nx[v] = nb[v * g.vst];
+      }
+      double F[5];
+      face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+      if (f > f0) {
+        const int i = f - 1;
+        double r[5];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fp[v] - F[v]);
+        finalize_cell<EPI>(g, a, col_h + (long long)(g.off[A] + i) * sA, col_r + (long long)i * g.rst[A], r, step, red);
+      }
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        Fp[v] = F[v];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[v][k] = w[v][k + 1];
+      }
+    }
+  }
+  if (EPI) {
+    if (a.reduce) red_commit(red, a.red);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// contiguous sweep: lanes = consecutive faces of the flattened (row, face) sequence
+// ---------------------------------------------------------------------------
+template <int A, int RECON, int RIEMANN, int EPI>
+__global__ void __launch_bounds__(128) sweep_contig(const Geom g, const SweepArgs a, const int O1, const int O2,
+                                                    const long long total_faces) {
+  // rows are indexed row = i1 * n[O2] + i2 with O1 the slower of the two transverse axes
+  const int nf = g.n[A] + 1;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nranges = (total_faces + a.span - 1) / a.span;
+  const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
+  Red red;
+  red.init();
+  for (long long range = warp; range < nranges; range += nwarps) {
+    const long long gs = range * a.span;
+    const long long ge = min(gs + (long long)a.span, total_faces);
+    // one carry-in face unless the range starts a row
+    const long long gbeg = (gs % nf == 0) ? gs : gs - 1;
+    const int iters = (int)((ge - gbeg + 31) >> 5);
+    double carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    long long gf = gbeg + lane;
+    long long row = gf / nf;
+    int f = (int)(gf - row * nf);
+    for (int it = 0; it < iters; ++it) {
+      const bool act = gf < ge;
+      double F[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      long long col_h = 0, col_r = 0;
+      if (act) {
+        const int i1 = (int)(row / g.n[O2]);
+        const int i2 = (int)(row - (long long)i1 * g.n[O2]);
+        col_h = (long long)(i1 + g.off[O1]) * g.st[O1] + (long long)(i2 + g.off[O2]) * g.st[O2];
+        col_r = (long long)i1 * g.rst[O1] + (long long)i2 * g.rst[O2];
+        const double* base = a.prims + col_h + (long long)(g.off[A] + f - 3) * g.st[A];
+        double w[5][6];
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.st[A]];
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+      }
+      double Fl[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const double up = __shfl_up_sync(0xffffffffu, F[v], 1);
+        const double last = __shfl_sync(0xffffffffu, F[v], 31);
+        Fl[v] = (lane == 0) ? carry[v] : up;
+        carry[v] = last;
+      }
+      if (act && f > 0 && gf > gbeg) {
+        const int i = f - 1;
+        double r[5];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fl[v] - F[v]);
+        finalize_cell<EPI>(g, a, col_h + (long long)(g.off[A] + i) * g.st[A], col_r + (long long)i * g.rst[A], r, step, red);
+      }
+      gf += 32;
+      f += 32;
+      while (f >= nf) {
+        f -= nf;
+        ++row;
+      }
+    }
+  }
+  if (EPI) {
+    if (a.reduce) red_commit(red, a.red);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// halo fill: PERIODIC / SYMMETRY / ZEROGRADIENT face halos, cons recomputed
+// (halos/outer/material.py:868-894, boundary_condition.py:563-595, :698-731)
+// ---------------------------------------------------------------------------
+struct HaloArgs {
+  double* prims;
+  double* cons;
+  double gamma;
+  int bc[6];
+};
+
+__global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const HaloArgs a) {
+  const int face = blockIdx.y;
+  const int kind = a.bc[face];
+  if (kind != JXF_BC_PERIODIC && kind != JXF_BC_SYMMETRY && kind != JXF_BC_ZEROGRADIENT) return;
+  const int ax = face >> 1;
+  const bool hi = (face & 1) == 0;   // east, north, top
+  // transverse axes: t2 is the faster (larger index) one
+  const int t1 = (ax == 0) ? 1 : 0;
+  const int t2 = (ax == 2) ? 1 : 2;
+  const int n1 = g.n[t1], n2 = g.n[t2];
+  const long long total = (long long)g.nh * n1 * n2;
+  const int nh = g.nh, ext = g.ext[ax];
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int i2 = (int)(q % n2);
+    const long long q1 = q / n2;
+    const int i1 = (int)(q1 % n1);
+    const int l = (int)(q1 / n1);   // halo layer in increasing buffer index
+    const int dst = hi ? (ext - nh + l) : l;
+    int src;
+    if (kind == JXF_BC_PERIODIC) src = hi ? (nh + l) : (ext - 2 * nh + l);
+    else if (kind == JXF_BC_SYMMETRY) src = hi ? (ext - nh - 1 - l) : (2 * nh - 1 - l);
+    else src = hi ? (ext - nh - 1) : nh;
+    const long long tr = (long long)(i1 + g.off[t1]) * g.st[t1] + (long long)(i2 + g.off[t2]) * g.st[t2];
+    const long long is = tr + (long long)src * g.st[ax];
+    const long long id = tr + (long long)dst * g.st[ax];
+    double p[5], c[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) p[v] = a.prims[is + v * g.vst];
+    if (kind == JXF_BC_SYMMETRY) p[1 + ax] = p[1 + ax] * -1.0;
+    cons_from_prims(p, a.gamma, c);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      a.prims[id + v * g.vst] = p[v];
+      a.cons[id + v * g.vst] = c[v];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// whole-buffer transforms, reductions, finish-step, pack/unpack
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prims_from_cons_kernel(const double* __restrict__ cons, double* __restrict__ prims,
+                                                              long long vst, double gamma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vst; i += (long long)gridDim.x * blockDim.x) {
+    double c[5], p[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) c[v] = cons[i + v * vst];
+    prims_from_cons(c, gamma, p);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) prims[i + v * vst] = p[v];
+  }
+}
+
+__global__ void __launch_bounds__(256) cons_from_prims_kernel(const double* __restrict__ prims, double* __restrict__ cons,
+                                                              long long vst, double gamma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vst; i += (long long)gridDim.x * blockDim.x) {
+    double c[5], p[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) p[v] = prims[i + v * vst];
+    cons_from_prims(p, gamma, c);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) cons[i + v * vst] = c[v];
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_kernel(const Geom g, const double* __restrict__ prims, double* red,
+                                                     double gamma, int active_mask) {
+  const long long total = (long long)g.n[0] * g.n[1] * g.n[2];
+  Red r;
+  r.init();
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(q % g.n[2]);
+    const long long q1 = q / g.n[2];
+    const int j = (int)(q1 % g.n[1]);
+    const int i = (int)(q1 / g.n[1]);
+    const long long idx = (long long)(i + g.off[0]) * g.st[0] + (long long)(j + g.off[1]) * g.st[1] +
+                          (long long)(k + g.off[2]) * g.st[2];
+    double p[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) p[v] = prims[idx + v * g.vst];
+    r.add_cell(p, gamma, active_mask);
+  }
+  red_commit(r, red);
+}
+
+__global__ void reduce_reset_kernel(double* red) {
+  red[0] = 0.0;
+  red[1] = __longlong_as_double(0x7ff0000000000000LL);
+  red[2] = red[1];
+}
+
+// time_step_size.py:103-109,154-155: dt = dx_min / (max + eps); dt *= CFL
+__global__ void finish_step_kernel(double* red, double* dt, double* time, double* info, double dx_min, double cfl,
+                                   double fixed_dt) {
+  const double dt_used = *dt;
+  if (time) *time += dt_used;
+  if (info) {
+    info[0] = red[0];
+    info[1] = red[1];
+    info[2] = red[2];
+  }
+  if (fixed_dt > 0.0) {
+    *dt = fixed_dt;
+  } else {
+    double d = dx_min / (red[0] + kEps);
+    d *= cfl;
+    *dt = d;
+  }
+  red[0] = 0.0;
+  red[1] = __longlong_as_double(0x7ff0000000000000LL);
+  red[2] = red[1];
+}
+
+struct FaceArgs {
+  double* prims;
+  double* cons;
+  double* slab;
+  double gamma;
+  int face;
+  int unpack;
+};
+
+// slab layout (5, nh, n1, n2), layers in increasing buffer index along the face axis
+__global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const FaceArgs a) {
+  const int ax = a.face >> 1;
+  const bool hi = (a.face & 1) == 0;
+  const int t1 = (ax == 0) ? 1 : 0;
+  const int t2 = (ax == 2) ? 1 : 2;
+  const int n1 = g.n[t1], n2 = g.n[t2];
+  const long long total = (long long)g.nh * n1 * n2;
+  const int nh = g.nh, ext = g.ext[ax];
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int i2 = (int)(q % n2);
+    const long long q1 = q / n2;
+    const int i1 = (int)(q1 % n1);
+    const int l = (int)(q1 / n1);
+    const long long tr = (long long)(i1 + g.off[t1]) * g.st[t1] + (long long)(i2 + g.off[t2]) * g.st[t2];
+    if (!a.unpack) {
+      const int src = hi ? (ext - 2 * nh + l) : (nh + l);   // interior layers adjacent to the face
+      const long long is = tr + (long long)src * g.st[ax];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) a.slab[q + v * total] = a.prims[is + v * g.vst];
+    } else {
+      const int dst = hi ? (ext - nh + l) : l;
+      const long long id = tr + (long long)dst * g.st[ax];
+      double p[5], c[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) p[v] = a.slab[q + v * total];
+      cons_from_prims(p, a.gamma, c);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        a.prims[id + v * g.vst] = p[v];
+        a.cons[id + v * g.vst] = c[v];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+  double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.9999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// debug / test hook: the per-face device function on caller-supplied windows (n, 5, 6) -> (n, 5)
+template <int A, int RECON, int RIEMANN>
+__global__ void __launch_bounds__(128) face_flux_debug_kernel(const double* __restrict__ win, long long n, double gamma,
+                                                              double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double w[5][6], F[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[v][k] = win[(i * 5 + v) * 6 + k];
+  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) out[i * 5 + v] = F[v];
+}
+
+}  // namespace jxf
+
+// ===========================================================================
+// host side: plan + C ABI
+// ===========================================================================
+using namespace jxf;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JXF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return JXF_OK;
+}
+
+struct jxf_solver {
+  jxf_config cfg;
+  Geom g;
+  int active[3];
+  int n_active;
+  int active_mask;
+  int lane_axis;      // contiguous active axis
+  int num_sms;
+  int stages;
+  double dt_mult[3];
+  double blend[3][2];
+  // launch accounting / optional per-kernel event timing (jxf_profile_*)
+  long long launches[JXF_PROFILE_KINDS];
+  int prof_on;
+  int prof_n;
+  int prof_cap;
+  cudaEvent_t* prof_start;
+  cudaEvent_t* prof_stop;
+  unsigned char* prof_kind;
+};
+
+struct ProfScope {
+  jxf_solver* s;
+  cudaStream_t st;
+  int slot;
+  ProfScope(const jxf_solver* cs, int kind, cudaStream_t stream) : s(const_cast<jxf_solver*>(cs)), st(stream), slot(-1) {
+    s->launches[kind]++;
+    if (s->prof_on && s->prof_n < s->prof_cap) {
+      slot = s->prof_n++;
+      s->prof_kind[slot] = (unsigned char)kind;
+      cudaEventRecord(s->prof_start[slot], st);
+    }
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(s->prof_stop[slot], st);
+  }
+};
+
+extern "C" const char* jxf_last_error(void) { return g_err; }
+extern "C" int jxf_version(void) { return 100; }
+
+extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
+  if (!cfg || !out) return fail(JXF_ERR_BAD_ARG, "jxf_create: null argument");
+  if (cfg->nh < 3) return fail(JXF_ERR_BAD_ARG, "jxf_create: halo_cells=%d < 3 required by WENO5", cfg->nh);
+  for (int i = 0; i < 3; ++i)
+    if (cfg->n[i] < 1) return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d", i, cfg->n[i]);
+  if (cfg->recon != JXF_RECON_PRIMITIVE && cfg->recon != JXF_RECON_CHAR_PRIMITIVE)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
+  if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
+  if (cfg->signal_speed != JXF_SIGNAL_EINFELDT)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
+  if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
+  if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
+  jxf_solver* s = new (std::nothrow) jxf_solver;
+  if (!s) return fail(JXF_ERR_BAD_ARG, "jxf_create: out of host memory");
+  memset(s, 0, sizeof(*s));
+  s->cfg = *cfg;
+  Geom& g = s->g;
+  g.nh = cfg->nh;
+  s->n_active = 0;
+  s->lane_axis = -1;
+  for (int i = 0; i < 3; ++i) {
+    g.n[i] = cfg->n[i];
+    const bool act = cfg->n[i] > 1;
+    g.ext[i] = act ? cfg->n[i] + 2 * cfg->nh : 1;
+    g.off[i] = act ? cfg->nh : 0;
+    if (act) {
+      s->active[s->n_active++] = i;
+      s->active_mask |= 1 << i;
+      s->lane_axis = i;
+      if (cfg->n[i] < cfg->nh)
+        { delete s; return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d smaller than halo_cells", i, cfg->n[i]); }
+    }
+  }
+  if (s->n_active == 0) { delete s; return fail(JXF_ERR_BAD_ARG, "jxf_create: no active axis"); }
+  for (int f = 0; f < 6; ++f) {
+    const int ax = f >> 1;
+    const int b = cfg->bc[f];
+    const bool act = cfg->n[ax] > 1;
+    if (b < JXF_BC_INACTIVE || b > JXF_BC_NEIGHBOR) { delete s; return fail(JXF_ERR_UNSUPPORTED, "jxf_create: boundary type id %d at face %d not implemented on the B200 path", b, f); }
+    if (act && b == JXF_BC_INACTIVE) { delete s; return fail(JXF_ERR_BAD_ARG, "jxf_create: face %d of an active axis is INACTIVE", f); }
+  }
+  g.st[2] = 1;
+  g.st[1] = g.ext[2];
+  g.st[0] = (long long)g.ext[1] * g.ext[2];
+  g.vst = (long long)g.ext[0] * g.ext[1] * g.ext[2];
+  g.rst[2] = 1;
+  g.rst[1] = g.n[2];
+  g.rst[0] = (long long)g.n[1] * g.n[2];
+  g.rvst = (long long)g.n[0] * g.n[1] * g.n[2];
+  // RK tables: time_integration/euler.py, RK2.py:22-33, RK3.py:27-29
+  if (cfg->integrator == JXF_INT_EULER) {
+    s->stages = 1; s->dt_mult[0] = 1.0;
+  } else if (cfg->integrator == JXF_INT_RK2) {
+    s->stages = 2; s->dt_mult[0] = 1.0; s->dt_mult[1] = 0.5;
+    s->blend[1][0] = 0.5; s->blend[1][1] = 0.5;
+  } else {
+    s->stages = 3; s->dt_mult[0] = 1.0; s->dt_mult[1] = 0.25; s->dt_mult[2] = 2.0 / 3.0;
+    s->blend[1][0] = 0.25; s->blend[1][1] = 0.75;
+    s->blend[2][0] = 2.0 / 3.0; s->blend[2][1] = 1.0 / 3.0;
+  }
+  s->num_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) s->num_sms = sms;
+  }
+  (void)cudaGetLastError();
+  *out = s;
+  return JXF_OK;
+}
+
+static void prof_free(jxf_solver* s) {
+  if (s->prof_start) {
+    for (int i = 0; i < s->prof_cap; ++i) {
+      cudaEventDestroy(s->prof_start[i]);
+      cudaEventDestroy(s->prof_stop[i]);
+    }
+    delete[] s->prof_start;
+    delete[] s->prof_stop;
+    delete[] s->prof_kind;
+    s->prof_start = s->prof_stop = nullptr;
+    s->prof_kind = nullptr;
+    s->prof_cap = s->prof_n = 0;
+  }
+}
+
+extern "C" int jxf_destroy(jxf_handle h) {
+  if (h) prof_free(h);
+  delete h;
+  return JXF_OK;
+}
+
+extern "C" int jxf_profile_enable(jxf_handle h, int enable) {
+  if (!h) return fail(JXF_ERR_BAD_ARG, "jxf_profile_enable: null handle");
+  if (enable && !h->prof_start) {
+    const int cap = 4096;
+    h->prof_start = new (std::nothrow) cudaEvent_t[cap];
+    h->prof_stop = new (std::nothrow) cudaEvent_t[cap];
+    h->prof_kind = new (std::nothrow) unsigned char[cap];
+    if (!h->prof_start || !h->prof_stop || !h->prof_kind) return fail(JXF_ERR_BAD_ARG, "jxf_profile_enable: out of host memory");
+    for (int i = 0; i < cap; ++i) {
+      if (cudaEventCreate(&h->prof_start[i]) != cudaSuccess || cudaEventCreate(&h->prof_stop[i]) != cudaSuccess)
+        return fail(JXF_ERR_CUDA, "jxf_profile_enable: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    h->prof_cap = cap;
+  }
+  h->prof_on = enable ? 1 : 0;
+  return JXF_OK;
+}
+
+extern "C" int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* launches, int reset) {
+  if (!h) return fail(JXF_ERR_BAD_ARG, "jxf_profile_read: null handle");
+  for (int k = 0; k < JXF_PROFILE_KINDS; ++k) {
+    if (ms_sum) ms_sum[k] = 0.0;
+    if (timed) timed[k] = 0;
+    if (launches) launches[k] = h->launches[k];
+  }
+  for (int i = 0; i < h->prof_n; ++i) {
+    if (cudaEventSynchronize(h->prof_stop[i]) != cudaSuccess)
+      return fail(JXF_ERR_CUDA, "jxf_profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->prof_start[i], h->prof_stop[i]);
+    if (ms_sum) ms_sum[h->prof_kind[i]] += ms;
+    if (timed) timed[h->prof_kind[i]]++;
+  }
+  if (reset) {
+    h->prof_n = 0;
+    for (int k = 0; k < JXF_PROFILE_KINDS; ++k) h->launches[k] = 0;
+  }
+  return JXF_OK;
+}
+
+extern "C" int64_t jxf_field_elems(jxf_handle h) { return h ? 5 * h->g.vst : -1; }
+extern "C" int64_t jxf_rhs_elems(jxf_handle h) { return h ? 5 * h->g.rvst : -1; }
+extern "C" int jxf_num_stages(jxf_handle h) { return h ? h->stages : -1; }
+
+// ---------------------------------------------------------------------------
+// sweep dispatch
+// ---------------------------------------------------------------------------
+template <int A, int RECON, int RIEMANN, int EPI>
+static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
+  const Geom& g = s->g;
+  const int resident = s->num_sms * 4;   // ~4 CTAs of 128 threads per SM
+  if (A != s->lane_axis) {
+    const int C = s->lane_axis;
+    const int O = 3 - A - C;
+    const long long plane = (long long)g.n[C] * g.n[O];
+    const int bx = (int)((plane + 127) / 128);
+    // chunks along A: enough CTAs for ~4 waves, but chunks of >= 16 cells (<= 6% redundant faces)
+    int chunks = (int)std::min<long long>((4LL * resident + bx - 1) / bx, std::max(1, g.n[A] / 16));
+    chunks = std::max(1, std::min(chunks, 65535));
+    a.chunk_len = (g.n[A] + chunks - 1) / chunks;
+    chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
+    dim3 grid(bx, chunks);
+    ProfScope prof(s, A + 3 * EPI, st);
+    sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(g, a, C, O);
+  } else {
+    // the two transverse axes, O1 slower than O2
+    const int O1 = (A == 0) ? 1 : 0;
+    const int O2 = (A == 2) ? 1 : 2;
+    const long long rows = (long long)g.n[O1] * g.n[O2];
+    const int nf = g.n[A] + 1;
+    const long long total = rows * nf;
+    const long long target_warps = 4LL * resident * 4;   // ~4 waves of warps
+    long long span;
+    if (rows >= target_warps) {
+      span = (rows / target_warps) * nf;                 // whole rows per range, no carry-in face
+      span = std::min<long long>(span, 64LL * nf);
+    } else {
+      span = std::max<long long>(31, ((total / target_warps) / 32) * 32 - 1);
+      span = std::min<long long>(span, 32LL * 256 - 1);
+    }
+    if (span > 0x7fffffff) span = 0x7fffffff;
+    a.span = (int)span;
+    const long long nranges = (total + span - 1) / span;
+    const long long blocks = std::min<long long>((nranges + 3) / 4, (long long)resident * 4);
+    ProfScope prof(s, A + 3 * EPI, st);
+    sweep_contig<A, RECON, RIEMANN, EPI><<<(unsigned)std::max<long long>(1, blocks), 128, 0, st>>>(g, a, O1, O2, total);
+  }
+  return check_launch("sweep");
+}
+
+template <int A, int RECON, int RIEMANN>
+static int dispatch_epi(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  return epi ? launch_sweep<A, RECON, RIEMANN, 1>(s, a, st) : launch_sweep<A, RECON, RIEMANN, 0>(s, a, st);
+}
+template <int A, int RECON>
+static int dispatch_riemann(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  return s->cfg.riemann == JXF_RIEMANN_HLLC ? dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st)
+                                            : dispatch_epi<A, RECON, RIEMANN_RUSANOV>(s, a, epi, st);
+}
+template <int A>
+static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  return s->cfg.recon == JXF_RECON_PRIMITIVE ? dispatch_riemann<A, RECON_PRIMITIVE>(s, a, epi, st)
+                                             : dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
+}
+static int dispatch_axis(const jxf_solver* s, int axis, const SweepArgs& a, int epi, cudaStream_t st) {
+  switch (axis) {
+    case 0: return dispatch_recon<0>(s, a, epi, st);
+    case 1: return dispatch_recon<1>(s, a, epi, st);
+    default: return dispatch_recon<2>(s, a, epi, st);
+  }
+}
+
+static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, double* rhs) {
+  SweepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prims = prims;
+  a.rhs = rhs;
+  a.gamma = s->cfg.gamma;
+  a.inv_dx = s->cfg.inv_dx[axis];
+  a.active_mask = s->active_mask;
+  return a;
+}
+
+extern "C" int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream) {
+  if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: null argument");
+  if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: axis %d is not active", axis);
+  SweepArgs a = base_args(h, axis, prims, rhs);
+  a.accumulate = accumulate ? 1 : 0;
+  return dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+}
+
+extern "C" int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, void* stream) {
+  if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_compute_rhs: null argument");
+  for (int k = 0; k < h->n_active; ++k) {
+    int rc = jxf_sweep(h, h->active[k], prims, rhs, k > 0, stream);
+    if (rc) return rc;
+  }
+  return JXF_OK;
+}
+
+extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream) {
+  if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill: null argument");
+  HaloArgs a;
+  a.prims = prims;
+  a.cons = cons;
+  a.gamma = h->cfg.gamma;
+  long long maxcells = 0;
+  for (int f = 0; f < 6; ++f) {
+    a.bc[f] = h->cfg.bc[f];
+    const int ax = f >> 1;
+    if (h->g.n[ax] <= 1) a.bc[f] = JXF_BC_INACTIVE;
+    const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
+    if (a.bc[f] != JXF_BC_INACTIVE && a.bc[f] != JXF_BC_NEIGHBOR)
+      maxcells = std::max(maxcells, (long long)h->g.nh * h->g.n[t1] * h->g.n[t2]);
+  }
+  if (maxcells == 0) return JXF_OK;
+  const int bx = (int)std::min<long long>((maxcells + 127) / 128, 148 * 16);
+  ProfScope prof(h, JXF_PROFILE_HALO, (cudaStream_t)stream);
+  halo_fill_kernel<<<dim3(bx, 6), 128, 0, (cudaStream_t)stream>>>(h->g, a);
+  return check_launch("halo_fill");
+}
+
+extern "C" int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out, const double* cons_in,
+                         const double* cons_n, double* cons_out, double* rhs_scratch, const double* dt_dev,
+                         double* red_dev, int reduce, int fill_halo, void* stream) {
+  if (!h || !prims_in || !prims_out || !cons_in || !cons_out || !dt_dev)
+    return fail(JXF_ERR_BAD_ARG, "jxf_stage: null argument");
+  if (stage < 0 || stage >= h->stages) return fail(JXF_ERR_BAD_ARG, "jxf_stage: stage %d out of range", stage);
+  if (stage > 0 && !cons_n) return fail(JXF_ERR_BAD_ARG, "jxf_stage: cons_n required for stage > 0");
+  if (prims_in == prims_out) return fail(JXF_ERR_BAD_ARG, "jxf_stage: prims_out must not alias prims_in");
+  if (h->n_active > 1 && !rhs_scratch) return fail(JXF_ERR_BAD_ARG, "jxf_stage: rhs_scratch required");
+  if (reduce && !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage: red_dev required when reduce != 0");
+  for (int k = 0; k < h->n_active; ++k) {
+    const int axis = h->active[k];
+    const bool last = (k == h->n_active - 1);
+    SweepArgs a = base_args(h, axis, prims_in, rhs_scratch);
+    int rc;
+    if (!last) {
+      a.accumulate = k > 0;
+      rc = dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+    } else {
+      a.cons_in = cons_in;
+      a.cons_n = cons_n;
+      a.cons_out = cons_out;
+      a.prims_out = prims_out;
+      a.dt = dt_dev;
+      a.red = red_dev;
+      a.blend = stage > 0;
+      a.ca = h->blend[stage][0];
+      a.cb = h->blend[stage][1];
+      a.dt_mult = h->dt_mult[stage];
+      a.has_prev = k > 0;
+      a.reduce = reduce ? 1 : 0;
+      rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
+    }
+    if (rc) return rc;
+  }
+  if (fill_halo) return jxf_halo_fill(h, prims_out, cons_out, stream);
+  return JXF_OK;
+}
+
+extern "C" int jxf_step_fused(jxf_handle h, double* prims_a, double* prims_b, double* cons_a, double* cons_b,
+                              double* rhs_scratch, double* dt_dev, double* time_dev, double* red_dev,
+                              double* info_dev, int fill_halo, void* stream) {
+  if (!h || !prims_a || !prims_b || !cons_a || !cons_b || !dt_dev || !red_dev)
+    return fail(JXF_ERR_BAD_ARG, "jxf_step_fused: null argument");
+  double* pr[2] = {prims_a, prims_b};
+  int cur = 0;
+  for (int k = 0; k < h->stages; ++k) {
+    const bool last = (k == h->stages - 1);
+    const double* cin = (k == 0) ? cons_a : cons_b;
+    double* cout = last ? cons_a : cons_b;
+    int rc = jxf_stage(h, k, pr[cur], pr[cur ^ 1], cin, cons_a, cout, rhs_scratch, dt_dev, red_dev, last ? 1 : 0,
+                       fill_halo, stream);
+    if (rc) return rc;
+    cur ^= 1;
+  }
+  int rc = jxf_finish_step(h, red_dev, dt_dev, time_dev, info_dev, stream);
+  if (rc) return rc;
+  return cur;
+}
+
+extern "C" int jxf_prims_from_cons(jxf_handle h, const double* cons, double* prims, void* stream) {
+  if (!h || !cons || !prims) return fail(JXF_ERR_BAD_ARG, "jxf_prims_from_cons: null argument");
+  const int bx = (int)std::min<long long>((h->g.vst + 255) / 256, 148 * 8);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  prims_from_cons_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(cons, prims, h->g.vst, h->cfg.gamma);
+  return check_launch("prims_from_cons");
+}
+
+extern "C" int jxf_cons_from_prims(jxf_handle h, const double* prims, double* cons, void* stream) {
+  if (!h || !cons || !prims) return fail(JXF_ERR_BAD_ARG, "jxf_cons_from_prims: null argument");
+  const int bx = (int)std::min<long long>((h->g.vst + 255) / 256, 148 * 8);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  cons_from_prims_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(prims, cons, h->g.vst, h->cfg.gamma);
+  return check_launch("cons_from_prims");
+}
+
+extern "C" int jxf_reduce(jxf_handle h, const double* prims, double* red_dev, void* stream) {
+  if (!h || !prims || !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_reduce: null argument");
+  const long long total = h->g.rvst;
+  const int bx = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  reduce_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->g, prims, red_dev, h->cfg.gamma, h->active_mask);
+  return check_launch("reduce");
+}
+
+extern "C" int jxf_reduce_reset(jxf_handle h, double* red_dev, void* stream) {
+  if (!h || !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_reduce_reset: null argument");
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  reduce_reset_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(red_dev);
+  return check_launch("reduce_reset");
+}
+
+extern "C" int jxf_finish_step(jxf_handle h, double* red_dev, double* dt_dev, double* time_dev, double* info_dev,
+                               void* stream) {
+  if (!h || !red_dev || !dt_dev) return fail(JXF_ERR_BAD_ARG, "jxf_finish_step: null argument");
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  finish_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(red_dev, dt_dev, time_dev, info_dev, h->cfg.dx_min, h->cfg.cfl,
+                                                        h->cfg.fixed_dt);
+  return check_launch("finish_step");
+}
+
+extern "C" int64_t jxf_face_slab_elems(jxf_handle h, int face) {
+  if (!h || face < 0 || face > 5) return -1;
+  const int ax = face >> 1;
+  const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
+  return 5LL * h->g.nh * h->g.n[t1] * h->g.n[t2];
+}
+
+static int face_slab(jxf_handle h, int face, double* prims, double* cons, double* slab, int unpack, void* stream) {
+  if (!h || !prims || !slab || (unpack && !cons)) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: null argument");
+  if (face < 0 || face > 5 || h->g.n[face >> 1] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: face %d not active", face);
+  FaceArgs a;
+  a.prims = prims;
+  a.cons = cons;
+  a.slab = slab;
+  a.gamma = h->cfg.gamma;
+  a.face = face;
+  a.unpack = unpack;
+  const long long total = jxf_face_slab_elems(h, face) / 5;
+  const int bx = (int)std::min<long long>((total + 127) / 128, 148 * 16);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  face_slab_kernel<<<bx, 128, 0, (cudaStream_t)stream>>>(h->g, a);
+  return check_launch("face_slab");
+}
+
+extern "C" int jxf_pack_face(jxf_handle h, int face, const double* prims, double* slab, void* stream) {
+  return face_slab(h, face, const_cast<double*>(prims), nullptr, slab, 0, stream);
+}
+extern "C" int jxf_unpack_face(jxf_handle h, int face, const double* slab, double* prims, double* cons, void* stream) {
+  return face_slab(h, face, prims, cons, const_cast<double*>(slab), 1, stream);
+}
+
+extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n, double gamma,
+                                   double* flux, void* stream) {
+  if (!windows || !flux || n <= 0) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: bad argument");
+  const unsigned bx = (unsigned)((n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define JXF_DBG_CASE(A, R, S)                                                                     \
+  if (axis == A && recon == R && riemann == S) {                                                  \
+    face_flux_debug_kernel<A, R, S><<<bx, 128, 0, st>>>(windows, (long long)n, gamma, flux);       \
+    return check_launch("face_flux_debug");                                                       \
+  }
+  JXF_DBG_CASE(0, 0, 0) JXF_DBG_CASE(0, 0, 1) JXF_DBG_CASE(0, 1, 0) JXF_DBG_CASE(0, 1, 1)
+  JXF_DBG_CASE(1, 0, 0) JXF_DBG_CASE(1, 0, 1) JXF_DBG_CASE(1, 1, 0) JXF_DBG_CASE(1, 1, 1)
+  JXF_DBG_CASE(2, 0, 0) JXF_DBG_CASE(2, 0, 1) JXF_DBG_CASE(2, 1, 0) JXF_DBG_CASE(2, 1, 1)
+#undef JXF_DBG_CASE
+  return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
+}
+
+extern "C" int jxf_fp64_probe(double* scratch, int iters, int64_t* n_fma, void* stream) {
+  if (!scratch || iters <= 0) return fail(JXF_ERR_BAD_ARG, "jxf_fp64_probe: bad argument");
+  const int blocks = 148 * 8, threads = 256;
+  fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters);
+  if (n_fma) *n_fma = (int64_t)blocks * threads * 8LL * iters;
+  return check_launch("fp64_probe");
+}

@@ -1,0 +1,237 @@
+"""Device-side engine of one block: owns the fp64 buffers (torch CUDA tensors used
+purely as allocator/stream glue) and drives the C ABI (include/jxf_b200.h).
+
+There is no CPU path here: every method enqueues hand-written sm_100a kernels
+from libjxf_b200.so on the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FACES = _lib.FACES
+
+
+@dataclass
+class BlockConfig:
+    """What jxf_config needs, in the reference's vocabulary."""
+    cells: Tuple[int, int, int]                 # interior cells of this block
+    inv_dx: Tuple[float, float, float]          # 1/dx per axis (domain_information.py:290)
+    dx_min: float
+    gamma: float
+    bc: Dict[str, str]                          # face -> INACTIVE|PERIODIC|SYMMETRY|ZEROGRADIENT|NEIGHBOR
+    nh: int = 5
+    recon: str = "CHAR-PRIMITIVE"
+    riemann: str = "HLLC"
+    signal_speed: str = "EINFELDT"
+    integrator: str = "RK3"
+    cfl: float = 0.5
+    fixed_dt: float = 0.0
+
+    def to_c(self) -> _lib.JxfConfig:
+        def lookup(table, key, what):
+            if key not in table:
+                raise NotImplementedError(
+                    f"{what} '{key}' is a reference option that is not implemented on the B200 path "
+                    f"(available: {sorted(table)})")
+            return table[key]
+        c = _lib.JxfConfig()
+        for i in range(3):
+            c.n[i] = int(self.cells[i])
+            c.inv_dx[i] = float(self.inv_dx[i])
+        c.nh = int(self.nh)
+        c.dx_min = float(self.dx_min)
+        c.gamma = float(self.gamma)
+        c.cfl = float(self.cfl)
+        c.fixed_dt = float(self.fixed_dt or 0.0)
+        c.recon = lookup(_lib.RECON, self.recon, "reconstruction_variable")
+        c.riemann = lookup(_lib.RIEMANN, self.riemann, "riemann_solver")
+        c.signal_speed = lookup(_lib.SIGNAL, self.signal_speed, "signal_speed")
+        c.integrator = lookup(_lib.INTEGRATOR, self.integrator, "integrator")
+        for k, f in enumerate(FACES):
+            c.bc[k] = lookup(_lib.BC, self.bc[f], f"boundary condition type at {f}")
+        return c
+
+    @property
+    def shape(self):
+        return (5,) + tuple(n + 2 * self.nh if n > 1 else 1 for n in self.cells)
+
+    @property
+    def rhs_shape(self):
+        return (5,) + tuple(self.cells)
+
+    @property
+    def interior(self):
+        return tuple(slice(self.nh, -self.nh) if n > 1 else slice(None) for n in self.cells)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), "fp64 contiguous CUDA tensor required"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BlockSolver:
+    """Thin object wrapper over a jxf_handle."""
+
+    def __init__(self, cfg: BlockConfig, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise _lib.JxfError("jaxfluids_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.jxf_create(C.byref(cfg.to_c()), C.byref(self._h)))
+        self.stages = self.lib.jxf_num_stages(self._h)
+        self.active = tuple(i for i in range(3) if cfg.cells[i] > 1)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.jxf_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- buffers ----------------------------------------------------------
+    def new_field(self, fill: Optional[float] = None) -> torch.Tensor:
+        t = torch.empty(self.cfg.shape, dtype=torch.float64, device=self.device)
+        if fill is not None:
+            t.fill_(fill)
+        return t
+
+    def new_rhs(self) -> torch.Tensor:
+        return torch.empty(self.cfg.rhs_shape, dtype=torch.float64, device=self.device)
+
+    def new_scalars(self, n=1, value=0.0) -> torch.Tensor:
+        return torch.full((n,), value, dtype=torch.float64, device=self.device)
+
+    def new_red(self) -> torch.Tensor:
+        return torch.tensor([0.0, float("inf"), float("inf")], dtype=torch.float64, device=self.device)
+
+    # -- ABI calls (all enqueue-only on the current stream) ---------------
+    def compute_rhs(self, prims: torch.Tensor, rhs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        rhs = self.new_rhs() if rhs is None else rhs
+        _lib.check(self.lib.jxf_compute_rhs(self._h, _ptr(prims), _ptr(rhs), _stream()))
+        return rhs
+
+    def sweep(self, axis: int, prims, rhs, accumulate: bool):
+        _lib.check(self.lib.jxf_sweep(self._h, int(axis), _ptr(prims), _ptr(rhs), int(bool(accumulate)), _stream()))
+        return rhs
+
+    def stage(self, stage, prims_in, prims_out, cons_in, cons_n, cons_out, rhs, dt_dev, red_dev=None,
+              reduce=False, fill_halo=True):
+        _lib.check(self.lib.jxf_stage(self._h, int(stage), _ptr(prims_in), _ptr(prims_out), _ptr(cons_in),
+                                      _ptr(cons_n), _ptr(cons_out), _ptr(rhs), _ptr(dt_dev), _ptr(red_dev),
+                                      int(bool(reduce)), int(bool(fill_halo)), _stream()))
+
+    def step_fused(self, prims_a, prims_b, cons_a, cons_b, rhs, dt_dev, time_dev, red_dev, info_dev,
+                   fill_halo=True) -> int:
+        rc = self.lib.jxf_step_fused(self._h, _ptr(prims_a), _ptr(prims_b), _ptr(cons_a), _ptr(cons_b), _ptr(rhs),
+                                     _ptr(dt_dev), _ptr(time_dev), _ptr(red_dev), _ptr(info_dev),
+                                     int(bool(fill_halo)), _stream())
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
+    def halo_fill(self, prims, cons):
+        _lib.check(self.lib.jxf_halo_fill(self._h, _ptr(prims), _ptr(cons), _stream()))
+
+    def prims_from_cons(self, cons, prims):
+        _lib.check(self.lib.jxf_prims_from_cons(self._h, _ptr(cons), _ptr(prims), _stream()))
+
+    def cons_from_prims(self, prims, cons):
+        _lib.check(self.lib.jxf_cons_from_prims(self._h, _ptr(prims), _ptr(cons), _stream()))
+
+    def reduce(self, prims, red_dev):
+        _lib.check(self.lib.jxf_reduce(self._h, _ptr(prims), _ptr(red_dev), _stream()))
+
+    def reduce_reset(self, red_dev):
+        _lib.check(self.lib.jxf_reduce_reset(self._h, _ptr(red_dev), _stream()))
+
+    def finish_step(self, red_dev, dt_dev, time_dev=None, info_dev=None):
+        _lib.check(self.lib.jxf_finish_step(self._h, _ptr(red_dev), _ptr(dt_dev), _ptr(time_dev), _ptr(info_dev),
+                                            _stream()))
+
+    PROFILE_KINDS = ("sweep_x", "sweep_y", "sweep_z", "sweep_x_epilogue", "sweep_y_epilogue", "sweep_z_epilogue",
+                     "halo_fill", "other")
+
+    def profile_enable(self, on: bool = True):
+        _lib.check(self.lib.jxf_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, reset: bool = True):
+        """-> {kind: (ms_sum, timed_launches, launches)}; synchronises on the recorded events."""
+        n = len(self.PROFILE_KINDS)
+        ms = (C.c_double * n)()
+        timed = (C.c_int64 * n)()
+        launches = (C.c_int64 * n)()
+        _lib.check(self.lib.jxf_profile_read(self._h, ms, timed, launches, int(bool(reset))))
+        return {k: (ms[i], timed[i], launches[i]) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def face_slab_elems(self, face: int) -> int:
+        return int(self.lib.jxf_face_slab_elems(self._h, int(face)))
+
+    def pack_face(self, face: int, prims, slab):
+        _lib.check(self.lib.jxf_pack_face(self._h, int(face), _ptr(prims), _ptr(slab), _stream()))
+
+    def unpack_face(self, face: int, slab, prims, cons):
+        _lib.check(self.lib.jxf_unpack_face(self._h, int(face), _ptr(slab), _ptr(prims), _ptr(cons), _stream()))
+
+
+class BlockState:
+    """Ping-pong device state of one block + the no-sync single-block stepper."""
+
+    def __init__(self, solver: BlockSolver, prims_with_halos: np.ndarray | torch.Tensor,
+                 cons_with_halos: np.ndarray | torch.Tensor | None = None, dt: float | None = None, time: float = 0.0):
+        s = self.solver = solver
+        dev = s.device
+        self.prims = [torch.as_tensor(prims_with_halos, dtype=torch.float64).to(dev).contiguous(), s.new_field(1.0)]
+        self.cur = 0
+        self.cons_a = s.new_field(1.0)
+        self.cons_b = s.new_field(1.0)
+        if cons_with_halos is not None:
+            self.cons_a.copy_(torch.as_tensor(cons_with_halos, dtype=torch.float64))
+        else:
+            s.cons_from_prims(self.prims[0], self.cons_a)
+        self.rhs = s.new_rhs() if len(s.active) > 1 else None
+        self.red = s.new_red()
+        self.info = s.new_scalars(3)
+        self.time = s.new_scalars(1, time)
+        self.dt = s.new_scalars(1, 0.0)
+        if dt is None:
+            self.update_dt()
+        else:
+            self.dt.fill_(dt)
+
+    @property
+    def primitives(self) -> torch.Tensor:
+        return self.prims[self.cur]
+
+    @property
+    def conservatives(self) -> torch.Tensor:
+        return self.cons_a
+
+    def update_dt(self):
+        """dt from the current primitives (time_control_initializer.py:34-78)."""
+        s = self.solver
+        s.reduce_reset(self.red)
+        s.reduce(self.primitives, self.red)
+        s.finish_step(self.red, self.dt, None, self.info)
+
+    def step(self):
+        """One full RK step, enqueue-only."""
+        a, b = self.prims[self.cur], self.prims[self.cur ^ 1]
+        where = self.solver.step_fused(a, b, self.cons_a, self.cons_b, self.rhs, self.dt, self.time, self.red, self.info)
+        self.cur ^= where

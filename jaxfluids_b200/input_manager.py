@@ -1,0 +1,394 @@
+"""InputManager: reads a JAX-Fluids case setup and numerical setup (paths to .json
+files or dicts) and validates the keys the convective hot path uses.
+
+Mirrors input/input_manager.py:32-116 of the reference for the path's subset:
+the same JSON schema, the same defaults, the same option strings
+(registries.py).  Options outside the path raise NotImplementedError naming the
+JSON path; malformed values raise the reference's consistency AssertionError.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+from typing import Any, Callable, Dict, NamedTuple, Optional, Tuple, Union
+
+import numpy as np
+
+from . import registries as R
+from .domain_information import DomainInformation
+
+FACES = ("east", "west", "north", "south", "top", "bottom")          # domain/__init__.py:5-7
+FACE_AXIS = {"east": 0, "west": 0, "north": 1, "south": 1, "top": 2, "bottom": 2}
+AXES = ("x", "y", "z")
+
+
+def _assert(cond, msg, setup):
+    assert cond, f"Consistency error in {setup} setup file. {msg}"
+
+
+def read_json_setup(setup: Union[str, Dict], name: str) -> Dict:
+    """input/input_manager.py:341-366."""
+    if isinstance(setup, dict):
+        return copy.deepcopy(setup)
+    if isinstance(setup, (str, os.PathLike)):
+        path = os.fspath(setup)
+        assert os.path.isfile(path), f"Consistency error reading {name} file. {path} does not exist."
+        with open(path) as fh:
+            return json.load(fh)
+    raise AssertionError(f"Consistency error reading {name} file. {name} must be a path or a dictionary.")
+
+
+def get_setup_value(d: Dict, key: str, path: str, types, is_optional: bool, default_value: Any = None,
+                    possible_string_values=None, numerical_value_condition=None, setup="numerical"):
+    """input/setup_reader.py (_get_setup_value): same checks, same messages."""
+    def check(v):
+        _assert(isinstance(v, types), f"Key {path} must be of types {types}, but is of type {type(v)}.", setup)
+        if possible_string_values is not None and isinstance(v, str):
+            _assert(v in possible_string_values,
+                    f"Value of {path:s} must be in {possible_string_values} if value is of type str.", setup)
+        if numerical_value_condition is not None and isinstance(v, (int, float)):
+            op, ref = numerical_value_condition
+            ok = {">": v > ref, "<": v < ref, ">=": v >= ref, "<=": v <= ref}[op]
+            _assert(ok, f"Value of {path} must be {op:s} {str(ref):s}.", setup)
+    if key in d:
+        v = d[key]
+        if not is_optional:
+            check(v)
+        elif v is not None:
+            check(v)
+        else:
+            v = default_value
+        return v
+    if is_optional:
+        return default_value
+    _assert(False, f"Key {key:s} is not optional, but missing {path:s}.", setup)
+
+
+# ---------------------------------------------------------------------------
+# setup containers (names follow data_types/numerical_setup, data_types/case_setup)
+# ---------------------------------------------------------------------------
+class TimeIntegrationSetup(NamedTuple):
+    integrator: str
+    CFL: float
+    fixed_timestep: Any
+
+
+class HighOrderGodunovSetup(NamedTuple):
+    riemann_solver: str
+    signal_speed: str
+    reconstruction_stencil: str
+    reconstruction_variable: str
+    frozen_state: str
+
+
+class ConvectiveFluxesSetup(NamedTuple):
+    convective_solver: str
+    godunov: HighOrderGodunovSetup
+
+
+class ConservativesSetup(NamedTuple):
+    halo_cells: int
+    time_integration: TimeIntegrationSetup
+    convective_fluxes: ConvectiveFluxesSetup
+
+
+class ActivePhysicsSetup(NamedTuple):
+    is_convective_flux: bool = False
+    is_viscous_flux: bool = False
+    is_heat_flux: bool = False
+    is_volume_force: bool = False
+    is_surface_tension: bool = False
+    is_geometric_source: bool = False
+
+
+class PrecisionSetup(NamedTuple):
+    is_double_precision_compute: bool = True
+    is_double_precision_output: bool = True
+
+
+class LoggingSetup(NamedTuple):
+    level: str = "INFO"
+    frequency: int = 1
+    is_positivity: bool = True
+    is_only_last_stage: bool = True
+
+
+class OutputSetup(NamedTuple):
+    logging: LoggingSetup = LoggingSetup()
+
+
+class NumericalSetup(NamedTuple):
+    conservatives: ConservativesSetup
+    active_physics: ActivePhysicsSetup
+    precision: PrecisionSetup
+    output: OutputSetup
+
+
+class GeneralSetup(NamedTuple):
+    case_name: str
+    end_time: float
+    end_step: int
+    save_path: str
+    save_dt: Any
+
+
+class DomainSetup(NamedTuple):
+    cells: Tuple[int, int, int]
+    range: Tuple[Tuple[float, float], ...]
+    decomposition: Tuple[int, int, int]
+
+
+class MaterialSetup(NamedTuple):
+    model: str
+    specific_heat_ratio: float
+    specific_gas_constant: float
+
+
+class CaseSetup(NamedTuple):
+    general_setup: GeneralSetup
+    domain_setup: DomainSetup
+    boundary_condition_setup: Dict[str, str]
+    initial_condition_setup: Dict[str, Any]
+    material_setup: MaterialSetup
+
+
+def _np_namespace():
+    """`jnp` as seen by the lambda strings of a case file (setup_reader.py:171): NumPy."""
+    return np
+
+
+def make_ic_callable(value, labels: Tuple[str, ...], path: str) -> Callable:
+    """initial_condition entry -> callable on the mesh grid (setup_reader.py:125-218).
+    Floats broadcast over the grid; strings are Python lambdas eval'd with `jnp` (and `np`)
+    in scope, whose argument names must equal the active axis names."""
+    if isinstance(value, bool) or not isinstance(value, (float, int, str)) and not callable(value):
+        _assert(False, f"Value of {path} must be float or string that specifies a lambda function.", "case")
+    def full_shape(args):
+        return np.broadcast_shapes(*[np.shape(a) for a in args])
+    if isinstance(value, (float, int)):
+        v = float(value)
+        return lambda *args: np.broadcast_to(np.float64(v), full_shape(args))
+    if isinstance(value, str):
+        fn = eval(value, {"jnp": _np_namespace(), "np": np})   # noqa: S307 -- same contract as the reference
+        names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
+        _assert(tuple(names) == tuple(labels), f"Input argument labels of lambda for {path} must be {labels}.", "case")
+        # the mesh may be passed sparse (broadcastable 1-D axes): same values as the reference's dense
+        # meshgrid evaluation, without materialising three full-size coordinate arrays
+        return lambda *args: np.broadcast_to(np.asarray(fn(*args), dtype=np.float64), full_shape(args))
+    return value
+
+
+class EquationInformation:
+    """equation_information.py:92-110 for SINGLE-PHASE."""
+    equation_type = "SINGLE-PHASE"
+    no_primes = 5
+    primes_tuple = ("rho", "u", "v", "w", "p")
+    cons_tuple = ("rho", "rhou", "rhov", "rhow", "E")
+    ids_mass = 0
+    ids_velocity = (1, 2, 3)
+    ids_energy = 4
+    velocity_minor_axes = ((2, 3), (3, 1), (1, 2))
+    levelset_model = False
+    diffuse_interface_model = False
+    is_compute_temperature = False
+
+
+class InputManager:
+    def __init__(self, case_setup: Union[str, Dict], numerical_setup: Union[str, Dict], materials_setup=None) -> None:
+        self.case_setup_dict = read_json_setup(case_setup, "case setup")
+        self.numerical_setup_dict = read_json_setup(numerical_setup, "numerical setup")
+        if materials_setup:
+            raise NotImplementedError("materials_setup")          # input_manager.py:52-55 raises too
+        self._check_nondim(self.case_setup_dict)
+        self.numerical_setup = self._read_numerical(self.numerical_setup_dict)
+        self.case_setup = self._read_case(self.case_setup_dict)
+        self.equation_information = EquationInformation()
+        self.domain_information = DomainInformation(
+            cells=self.case_setup.domain_setup.cells,
+            domain_range=self.case_setup.domain_setup.range,
+            split=self.case_setup.domain_setup.decomposition,
+            nh=self.numerical_setup.conservatives.halo_cells)
+        self._sanity_check()
+
+    # -- numerical setup ---------------------------------------------------
+    def _read_numerical(self, d: Dict) -> NumericalSetup:
+        cons_d = get_setup_value(d, "conservatives", "conservatives", dict, False)
+        nh = get_setup_value(cons_d, "halo_cells", "conservatives/halo_cells", int, False,
+                             numerical_value_condition=(">", 0))
+        ti_d = get_setup_value(cons_d, "time_integration", "conservatives/time_integration", dict, False)
+        integ = get_setup_value(ti_d, "integrator", "conservatives/time_integration/integrator", str, False)
+        integ = R.select(integ, R.REFERENCE_TIME_INTEGRATORS, R.DICT_TIME_INTEGRATION,
+                         "conservatives/time_integration/integrator")
+        cfl = get_setup_value(ti_d, "CFL", "conservatives/time_integration/CFL", float, True, 0.5,
+                              numerical_value_condition=(">", 0.0))
+        fixed = get_setup_value(ti_d, "fixed_timestep", "conservatives/time_integration/fixed_timestep", float, True,
+                                False, numerical_value_condition=(">", 0.0))
+        cf_d = get_setup_value(cons_d, "convective_fluxes", "conservatives/convective_fluxes", dict, False)
+        solver = get_setup_value(cf_d, "convective_solver", "conservatives/convective_fluxes/convective_solver", str,
+                                 True, "GODUNOV")
+        solver = R.select(solver, R.REFERENCE_CONVECTIVE_SOLVERS, R.DICT_CONVECTIVE_SOLVER,
+                          "conservatives/convective_fluxes/convective_solver")
+        base = "conservatives/convective_fluxes/godunov"
+        g_d = get_setup_value(cf_d, "godunov", base, dict, False)
+        riemann = get_setup_value(g_d, "riemann_solver", base + "/riemann_solver", str, False)
+        riemann = R.select(riemann, R.REFERENCE_RIEMANN_SOLVERS, R.DICT_RIEMANN_SOLVER, base + "/riemann_solver")
+        sig = get_setup_value(g_d, "signal_speed", base + "/signal_speed", str, False)
+        sig = R.select(sig, R.REFERENCE_SIGNAL_SPEEDS, R.DICT_SIGNAL_SPEEDS, base + "/signal_speed")
+        rv = get_setup_value(g_d, "reconstruction_variable", base + "/reconstruction_variable", str, False)
+        rv = R.select(rv, R.REFERENCE_RECONSTRUCTION_VARIABLES, R.TUPLE_RECONSTRUCTION_VARIABLES,
+                      base + "/reconstruction_variable")
+        stencil = get_setup_value(g_d, "reconstruction_stencil", base + "/reconstruction_stencil", str, False)
+        stencil = R.select(stencil, R.REFERENCE_RECONSTRUCTION_STENCILS, R.DICT_SPATIAL_RECONSTRUCTION,
+                           base + "/reconstruction_stencil")
+        frozen = get_setup_value(g_d, "frozen_state", base + "/frozen_state", str, True, "ARITHMETIC")
+        frozen = R.select(frozen, R.REFERENCE_FROZEN_STATES, R.TUPLE_FROZEN_STATE, base + "/frozen_state")
+        # read_conservatives.py:361-365
+        req = R.REQUIRED_HALOS[stencil]
+        _assert(nh >= req, f"Reconstruction stencil {stencil} requires at least {req} halo cells, "
+                           f"but only {nh} are specified.", "numerical")
+        pos_d = cons_d.get("positivity", {}) or {}
+        for k, v in pos_d.items():
+            if k.startswith("is_") and v:
+                raise NotImplementedError(f"conservatives/positivity/{k} is not implemented on the B200 path")
+
+        ap_d = get_setup_value(d, "active_physics", "active_physics", dict, False)
+        ap = {}
+        for f in ActivePhysicsSetup._fields:
+            ap[f] = bool(get_setup_value(ap_d, f, f"active_physics/{f}", bool, True, False))
+        active_physics = ActivePhysicsSetup(**ap)
+        _assert(active_physics.is_convective_flux, "active_physics/is_convective_flux must be true "
+                "for the convective hot path.", "numerical")
+        for f in ActivePhysicsSetup._fields[1:]:
+            if getattr(active_physics, f):
+                raise NotImplementedError(f"active_physics/{f} is not implemented on the B200 path "
+                                          "(convective single-phase path only)")
+        for k in ("active_forcings",):
+            for kk, v in (d.get(k, {}) or {}).items():
+                if v:
+                    raise NotImplementedError(f"{k}/{kk} is not implemented on the B200 path")
+        for k in ("levelset", "diffuse_interface"):
+            if (d.get(k, {}) or {}).get("model"):
+                raise NotImplementedError(f"{k}/model is not implemented on the B200 path (single-phase only)")
+
+        pr_d = d.get("precision", {}) or {}
+        precision = PrecisionSetup(
+            bool(get_setup_value(pr_d, "is_double_precision_compute", "precision/is_double_precision_compute", bool, True, True)),
+            bool(get_setup_value(pr_d, "is_double_precision_output", "precision/is_double_precision_output", bool, True, True)))
+        if not precision.is_double_precision_compute:
+            raise NotImplementedError("precision/is_double_precision_compute = false is not implemented on the B200 "
+                                      "path (fp64 only)")
+        out_d = d.get("output", {}) or {}
+        log_d = out_d.get("logging", {}) or {}
+        logging_setup = LoggingSetup(
+            level=get_setup_value(log_d, "level", "output/logging/level", str, True, "INFO",
+                                  possible_string_values=("DEBUG", "INFO", "DEBUG_TO_FILE", "INFO_TO_FILE", "NONE")),
+            frequency=get_setup_value(log_d, "frequency", "output/logging/frequency", int, True, 1,
+                                      numerical_value_condition=(">", 0)),
+            is_positivity=bool(get_setup_value(log_d, "is_positivity", "output/logging/is_positivity", bool, True, True)),
+            is_only_last_stage=bool(get_setup_value(log_d, "is_only_last_stage", "output/logging/is_only_last_stage",
+                                                    bool, True, True)))
+        return NumericalSetup(
+            ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
+                               ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen))),
+            active_physics, precision, OutputSetup(logging_setup))
+
+    # -- case setup ----------------------------------------------------------
+    @staticmethod
+    def _check_nondim(d: Dict):
+        nd = d.get("nondimensionalization_parameters", {}) or {}
+        for k, v in nd.items():
+            if float(v) != 1.0:
+                raise NotImplementedError(f"nondimensionalization_parameters/{k} != 1.0 is not implemented on the "
+                                          "B200 path")
+
+    def _read_case(self, d: Dict) -> CaseSetup:
+        S = "case"
+        gen_d = get_setup_value(d, "general", "general", dict, False, setup=S)
+        case_name = get_setup_value(gen_d, "case_name", "general/case_name", str, False, setup=S)
+        end_time = get_setup_value(gen_d, "end_time", "general/end_time", float, True, False, None, (">=", 0.0), S)
+        end_step = get_setup_value(gen_d, "end_step", "general/end_step", int, True, False, None, (">=", 0), S)
+        _assert(isinstance(end_step, int) and not isinstance(end_step, bool) or isinstance(end_time, float),
+                "Either end_time or end_step must be given.", S)
+        if isinstance(end_time, bool):
+            end_time = float(np.finfo(np.float64).max)        # read_general.py:45-48
+        if isinstance(end_step, bool):
+            end_step = int(np.iinfo(np.int64).max)
+        save_path = get_setup_value(gen_d, "save_path", "general/save_path", str, True, "./results", setup=S)
+        save_dt = get_setup_value(gen_d, "save_dt", "general/save_dt", float, True, False, None, (">", 0.0), S)
+        general = GeneralSetup(case_name, end_time, end_step, save_path, save_dt)
+
+        if (d.get("restart", {}) or {}).get("is_restart"):
+            raise NotImplementedError("restart/is_restart is not implemented on the B200 path (needs h5py)")
+
+        dom_d = get_setup_value(d, "domain", "domain", dict, False, setup=S)
+        cells, rng = [], []
+        for ax in AXES:
+            a_d = get_setup_value(dom_d, ax, f"domain/{ax}", dict, False, setup=S)
+            n = get_setup_value(a_d, "cells", f"domain/{ax}/cells", int, False, None, None, (">", 0), S)
+            r = get_setup_value(a_d, "range", f"domain/{ax}/range", list, False, setup=S)
+            _assert(len(r) == 2 and r[1] > r[0], f"domain/{ax}/range must be [lower, upper] with upper > lower.", S)
+            st = a_d.get("stretching")
+            if st and (st.get("type") not in (None, False, "HOMOGENEOUS", "HOMOGENOUS")):
+                raise NotImplementedError(f"domain/{ax}/stretching is not implemented on the B200 path")
+            cells.append(int(n))
+            rng.append((float(r[0]), float(r[1])))
+        dec_d = dom_d.get("decomposition", {}) or {}
+        split = tuple(int(get_setup_value(dec_d, f"split_{ax}", f"domain/decomposition/split_{ax}", int, True, 1,
+                                          None, (">", 0), S)) for ax in AXES)
+        for i, ax in enumerate(AXES):
+            _assert(cells[i] % split[i] == 0, f"domain/{ax}/cells must be divisible by split_{ax}.", S)
+            _assert(not (cells[i] == 1 and split[i] > 1), f"Inactive axis {ax} cannot be split.", S)
+        domain = DomainSetup(tuple(cells), tuple(rng), split)
+
+        bc_d = get_setup_value(d, "boundary_conditions", "boundary_conditions", dict, False, setup=S)
+        bcs = {}
+        for f in FACES:
+            f_d = get_setup_value(bc_d, f, f"boundary_conditions/{f}", (dict, list), False, setup=S)
+            if isinstance(f_d, list):
+                raise NotImplementedError(f"boundary_conditions/{f}: multiple types per face are not implemented on "
+                                          "the B200 path")
+            t = get_setup_value(f_d, "type", f"boundary_conditions/{f}/type", str, False, setup=S)
+            t = R.select(t, R.REFERENCE_BOUNDARY_TYPES, R.TUPLE_BOUNDARY_TYPES, f"boundary_conditions/{f}/type", S)
+            active = cells[FACE_AXIS[f]] > 1
+            _assert((t == "INACTIVE") == (not active),
+                    f"boundary_conditions/{f}/type must be INACTIVE exactly for inactive axes.", S)
+            bcs[f] = t
+        for ax, (hi, lo) in enumerate((("east", "west"), ("north", "south"), ("top", "bottom"))):
+            _assert((bcs[hi] == "PERIODIC") == (bcs[lo] == "PERIODIC"),
+                    f"PERIODIC boundary conditions must be set at both {hi} and {lo}.", S)
+
+        ic_d = get_setup_value(d, "initial_condition", "initial_condition", dict, False, setup=S)
+        if "primitives" in ic_d:
+            ic_d = ic_d["primitives"]
+        labels = tuple(ax for i, ax in enumerate(AXES) if cells[i] > 1)
+        ic = {}
+        for name in ("rho", "u", "v", "w", "p"):
+            _assert(name in ic_d, f"Key {name} is not optional, but missing initial_condition/{name}.", S)
+            ic[name] = make_ic_callable(ic_d[name], labels, f"initial_condition/{name}")
+
+        mp_d = get_setup_value(d, "material_properties", "material_properties", dict, False, setup=S)
+        eos_d = get_setup_value(mp_d, "equation_of_state", "material_properties/equation_of_state", dict, False, setup=S)
+        model = get_setup_value(eos_d, "model", "material_properties/equation_of_state/model", str, False, setup=S)
+        model = R.select(model, R.REFERENCE_MATERIALS, R.DICT_MATERIAL, "material_properties/equation_of_state/model", S)
+        gamma = get_setup_value(eos_d, "specific_heat_ratio", "material_properties/equation_of_state/specific_heat_ratio",
+                                float, False, None, None, (">", 1.0), S)
+        Rgas = get_setup_value(eos_d, "specific_gas_constant",
+                               "material_properties/equation_of_state/specific_gas_constant", float, True, 1.0, None,
+                               (">", 0.0), S)
+        for k in ("forcings",):
+            if d.get(k):
+                raise NotImplementedError(f"{k} is not implemented on the B200 path")
+        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas)))
+
+    def _sanity_check(self):
+        di = self.domain_information
+        nh = self.numerical_setup.conservatives.halo_cells
+        for i in di.active_axes_indices:
+            _assert(di.device_number_of_cells[i] >= nh,
+                    f"domain/{AXES[i]}/cells per device must be >= halo_cells.", "case")
+
+    # -- helpers used by the other managers -----------------------------------
+    @property
+    def gamma(self) -> float:
+        return self.case_setup.material_setup.specific_heat_ratio

@@ -1,0 +1,59 @@
+"""Option names of the reference and which of them this path implements.
+
+The JSON strings of the reference select the new path unchanged.  A name the
+reference knows but this path does not implement raises NotImplementedError
+("... not implemented on the B200 path"); a name the reference does not know
+fails the same consistency assertion the reference raises.
+
+Name lists: solvers/convective_fluxes/__init__.py:7-12, solvers/riemann_solvers/
+__init__.py:16-34, stencils/reconstruction/**/__init__.py, time_integration/
+__init__.py:6-11, materials/single_materials/__init__.py:8-15, halos/outer/__init__.py:1-7.
+"""
+REFERENCE_CONVECTIVE_SOLVERS = ("GODUNOV", "FLUX-SPLITTING", "ALDM", "CENTRAL")
+REFERENCE_RIEMANN_SOLVERS = ("LAX-FRIEDRICHS", "HLL", "HLLC", "HLLC_SIMPLEALPHA", "HLLC-LM", "RUSANOV", "AUSMP", "CATUM")
+REFERENCE_SIGNAL_SPEEDS = ("ARITHMETIC", "RUSANOV", "DAVIS", "DAVIS2", "EINFELDT", "TORO")
+REFERENCE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE")
+REFERENCE_FROZEN_STATES = ("ARITHMETIC", "ROE")
+REFERENCE_RECONSTRUCTION_STENCILS = (
+    "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER", "KOREN-ADAP", "MC-ADAP", "MINMOD-ADAP",
+    "SUPERBEE-ADAP", "VANALBADA-ADAP", "VANLEER-ADAP", "MINMOD-AD", "MINMOD-AD-ADAP", "TENO5", "TENO5-A",
+    "TENO5-ADAP", "TENO6", "TENO6-ADAP", "TENO6-A", "TENO6-A-ADAP", "TENO8", "TENO8-A", "WENO1", "WENO3-JS",
+    "WENO3-N", "WENO3-NN-OPT1", "WENO3-NN-OPT2", "WENO3-Z", "WENO3-FP", "WENO5-JS", "WENO5-Z", "WENO6-CU",
+    "WENO6-CUM1", "WENO6-CUM2", "WENO7-JS", "WENO9-JS", "WENO3-JS-ADAP", "WENO3-Z-ADAP", "WENO5-JS-ADAP",
+    "WENO5-Z-ADAP", "WENO6-CU-ADAP", "CENTRAL2", "CENTRAL2-ADAP", "CENTRAL4", "CENTRAL4-ADAP", "CENTRAL6",
+    "CENTRAL6-ADAP", "CENTRAL8", "CENTRAL8-ADAP")
+REFERENCE_TIME_INTEGRATORS = ("EULER", "RK2", "RK3", "RK2_LS4")
+REFERENCE_MATERIALS = ("IdealGas", "SafeIdealGas", "StiffenedGas", "StiffenedGasComplete", "Tait",
+                       "BarotropicCavitationFluid")
+REFERENCE_BOUNDARY_TYPES = (
+    "ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "LINEAREXTRAPOLATION", "WALL", "ISOTHERMALWALL",
+    "MASSTRANSFERWALL", "MASSTRANSFERWALL_PARAMETERIZED", "ISOTHERMALMASSTRANSFERWALL", "DIRICHLET", "NEUMANN",
+    "SIMPLE_INFLOW", "SIMPLE_OUTFLOW", "DIRICHLET_PARAMETERIZED", "OPPOSITIONCONTROLWALL",
+    "ISOTHERMALOPPOSITIONCONTROLWALL")
+
+# what the sm_100a kernels implement
+DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov"}
+DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov"}
+DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt"}
+DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z"}
+TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
+TUPLE_FROZEN_STATE = ("ARITHMETIC",)
+DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3"}
+DICT_MATERIAL = {"IdealGas": "IdealGas"}
+TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE")
+
+REQUIRED_HALOS = {"WENO5-Z": 3}   # weno5_base.py:18
+
+
+def select(value, reference_names, implemented, path, setup="numerical"):
+    """Reference-style validation + 'not implemented on the B200 path'."""
+    assert isinstance(value, str), (
+        f"Consistency error in {setup} setup file. Key {path} must be of types {str}, but is of type {type(value)}.")
+    assert value in reference_names, (
+        f"Consistency error in {setup} setup file. Value of {path} must be in {tuple(reference_names)} "
+        "if value is of type str.")
+    if value not in implemented:
+        raise NotImplementedError(
+            f"{path} = '{value}' is a valid JAX-Fluids option that is not implemented on the B200 path "
+            f"(implemented: {tuple(implemented)}).")
+    return value

@@ -1,0 +1,174 @@
+"""BlockRuntime: the device state of this rank's block and the step/stage drivers
+that the API-level managers (InitializationManager, SimulationManager and its
+SpaceSolver / TimeIntegrator / HaloManager views) share.
+
+Memory plan per block (fp64): two primitive buffers (stage ping-pong: a sweep reads
+its neighbours' primitives, so a stage cannot update them in place), two
+conservative buffers (U and U^n swap roles, no per-step copy), one interior-only
+rhs accumulator, and one send + one recv slab per shared face.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .domain_information import FACES
+from .engine import BlockConfig, BlockSolver
+from .parallel import FACE_ID, ParallelContext
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+class BlockRuntime:
+    _cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+    @classmethod
+    def get(cls, input_manager, parallel: Optional[ParallelContext] = None) -> "BlockRuntime":
+        rt = cls._cache.get(input_manager)
+        if rt is None:
+            if parallel is None:
+                parallel = ParallelContext.from_environment(input_manager.domain_information)
+            rt = cls(input_manager, parallel)
+            cls._cache[input_manager] = rt
+        return rt
+
+    def __init__(self, input_manager, parallel: ParallelContext):
+        di = input_manager.domain_information
+        num = input_manager.numerical_setup
+        case = input_manager.case_setup
+        god = num.conservatives.convective_fluxes.godunov
+        ti = num.conservatives.time_integration
+        self.parallel = parallel
+        self.domain_information = di
+        self.bc_global = dict(case.boundary_condition_setup)
+        self.bc_block = parallel.block_boundary_types(self.bc_global)
+        self.neighbors = parallel.neighbors(self.bc_global)
+        self.cfg = BlockConfig(
+            cells=tuple(di.device_number_of_cells),
+            inv_dx=tuple(float(x) for x in di.one_cell_sizes),
+            dx_min=di.smallest_cell_size,
+            gamma=case.material_setup.specific_heat_ratio,
+            bc=self.bc_block,
+            nh=di.nh_conservatives,
+            recon=god.reconstruction_variable,
+            riemann=god.riemann_solver,
+            signal_speed=god.signal_speed,
+            integrator=ti.integrator,
+            cfl=ti.CFL,
+            fixed_dt=float(ti.fixed_timestep) if ti.fixed_timestep else 0.0,
+        )
+        self.solver = BlockSolver(self.cfg)
+        s = self.solver
+        self.device = s.device
+        self.stages = s.stages
+        self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
+        self.cons = [s.new_field(EPS), s.new_field(EPS)]        # cons[0] = U / U^n, cons[1] = stage scratch
+        self.cur = 0
+        self.rhs = s.new_rhs() if len(s.active) > 1 else None
+        self.red = s.new_red()
+        self.info = s.new_scalars(3)
+        self.time = s.new_scalars(1, 0.0)
+        self.dt = s.new_scalars(1, 0.0)
+        self._sign = torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=self.device)
+        self.send = {f: torch.empty(s.face_slab_elems(FACE_ID[f]), dtype=torch.float64, device=self.device)
+                     for f in self.neighbors}
+        self.recv = {f: torch.empty_like(self.send[f]) for f in self.neighbors}
+        self.kernel_launches = 0
+
+    # -- views ------------------------------------------------------------
+    @property
+    def primitives(self) -> torch.Tensor:
+        return self.prims[self.cur]
+
+    @property
+    def conservatives(self) -> torch.Tensor:
+        return self.cons[0]
+
+    def adopt(self, primitives: torch.Tensor, conservatives: torch.Tensor):
+        """Make externally supplied tensors the current state (copies unless they already are)."""
+        if primitives.data_ptr() != self.primitives.data_ptr():
+            self.primitives.copy_(primitives)
+        if conservatives.data_ptr() != self.conservatives.data_ptr():
+            self.conservatives.copy_(conservatives)
+
+    # -- initialisation -----------------------------------------------------
+    def upload_initial_primitives(self, host_interior: np.ndarray) -> Tuple[torch.Tensor, torch.Tensor]:
+        """material_fields_initializer.py:148-210 / :590-690: interior <- IC, cons = f(prims) on the
+        whole buffer, then the halo update."""
+        p = self.prims[self.cur]
+        p.fill_(EPS)
+        sl = (slice(None),) + self.cfg.interior
+        p[sl] = torch.as_tensor(np.ascontiguousarray(host_interior), dtype=torch.float64).to(self.device)
+        self.solver.cons_from_prims(p, self.cons[0])
+        self.halo_update(p, self.cons[0])
+        return p, self.cons[0]
+
+    def initial_time_step_and_positivity(self, prims: torch.Tensor):
+        s = self.solver
+        s.reduce_reset(self.red)
+        s.reduce(prims, self.red)
+        self._allreduce_red()
+        s.finish_step(self.red, self.dt, None, self.info)
+        info = self.info.cpu().numpy()
+        return float(self.dt.item()), float(info[1]), float(info[2])
+
+    # -- halo update ----------------------------------------------------------
+    def halo_update(self, prims: torch.Tensor, cons: torch.Tensor, local_done: bool = False):
+        """halo_manager.py:146-234: inter-block faces (inner/material.py:30-93) then outer BCs."""
+        s = self.solver
+        if self.neighbors:
+            for f in self.neighbors:
+                s.pack_face(FACE_ID[f], prims, self.send[f])
+            reqs = self.parallel.exchange(self.neighbors, self.send, self.recv)
+            for r in reqs:
+                r.wait()
+            for f in self.neighbors:
+                s.unpack_face(FACE_ID[f], self.recv[f], prims, cons)
+        if not local_done:
+            s.halo_fill(prims, cons)
+
+    def _allreduce_red(self):
+        if self.parallel.is_parallel:
+            buf = self.red * self._sign
+            self.parallel.allreduce_max(buf)
+            self.red.copy_(buf * self._sign)
+
+    # -- stepping ---------------------------------------------------------------
+    def set_time_control(self, time: float, dt: float):
+        self.time.fill_(float(time))
+        self.dt.fill_(float(dt))
+
+    def stage(self, k: int, reduce: bool):
+        """One RK stage on the current state (simulation_manager.py:770-1047)."""
+        s = self.solver
+        last = k == self.stages - 1
+        p_in, p_out = self.prims[self.cur], self.prims[self.cur ^ 1]
+        c_in = self.cons[0] if k == 0 else self.cons[1]
+        c_out = self.cons[0] if last else self.cons[1]
+        s.stage(k, p_in, p_out, c_in, self.cons[0], c_out, self.rhs, self.dt, self.red, reduce=reduce,
+                fill_halo=True)
+        if self.neighbors:
+            self.halo_update(p_out, c_out, local_done=True)
+        self.cur ^= 1
+
+    def step(self):
+        """One full time step, enqueue-only (no host sync)."""
+        if not self.parallel.is_parallel:
+            a, b = self.prims[self.cur], self.prims[self.cur ^ 1]
+            where = self.solver.step_fused(a, b, self.cons[0], self.cons[1], self.rhs, self.dt, self.time, self.red,
+                                           self.info)
+            self.cur ^= where
+            return
+        for k in range(self.stages):
+            self.stage(k, reduce=(k == self.stages - 1))
+        self._allreduce_red()
+        self.solver.finish_step(self.red, self.dt, self.time, self.info)
+
+    def read_step_scalars(self):
+        """(time, dt_next, max_speed_sum, min_rho, min_p) -- ONE device->host sync."""
+        v = torch.cat([self.time, self.dt, self.info]).cpu().numpy()
+        return float(v[0]), float(v[1]), float(v[2]), float(v[3]), float(v[4])

@@ -52,6 +52,7 @@ class Setup:
     integrator: str = "RK3"
     cfl: float = 0.5
     fixed_timestep: float | None = None
+    inv_dx_override: Tuple[float, float, float] | None = None   # sub-blocks of a larger grid (port_mt, multi-block tests)
     active: Tuple[int, ...] = field(init=False)
 
     def __post_init__(self):
@@ -65,6 +66,8 @@ class Setup:
 
     @property
     def inv_dx(self):
+        if self.inv_dx_override is not None:
+            return tuple(np.float64(v) for v in self.inv_dx_override)
         return tuple(np.float64(1.0) / d for d in self.dx)
 
     @property

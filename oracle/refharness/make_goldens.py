@@ -1,0 +1,83 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference sources (build container only).
+
+    python oracle/refharness/make_goldens.py
+
+Each fixture holds what the reference produced for one small case:
+  case_json / num_json : the exact setup dicts (so tests rebuild the same setup)
+  prims0               : initial primitives, interior (5,Nx,Ny,Nz)
+  dt0                  : initial time step
+  rhs_axis{a}          : per-axis rhs of the initial state (SpaceSolver.compute_rhs_xi)
+  rhs_s{k}             : total rhs at RK stage k of step 0
+  prims_s{k}, cons_s{k}: halo'd state after RK stage k of step 0
+  prims_n{N}, cons_n{N}: halo'd state after N steps
+  dt, time, totals, min_density, min_pressure : per-step sequences
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.refharness import run_reference as rr  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+FIXTURES = {
+    # name: (case, kwargs, nsteps, snapshots)
+    "sod200_char_hllc_rk3": ("sod", dict(cells=(200, None, None)), 100, (1, 10, 100)),
+    "sod100_prim_rusanov_rk2": ("sod", dict(cells=(100, None, None), recon="PRIMITIVE", riemann="RUSANOV",
+                                             integrator="RK2"), 10, (1, 10)),
+    "riemann2d_32x32_char_hllc_rk3": ("riemann2d", dict(cells=(32, 32, None)), 10, (1, 10)),
+    "riemann2d_24x40_prim_hllc_euler": ("riemann2d", dict(cells=(24, 40, None), recon="PRIMITIVE",
+                                                           integrator="EULER"), 5, (1, 5)),
+    "tgv16_sym_char_hllc_rk3": ("tgv", dict(cells=(16, 16, 16)), 5, (1, 5)),
+    "tgv_12x16x20_per_char_hllc_rk3": ("tgv", dict(cells=(12, 16, 20), bc="PERIODIC"), 3, (1, 3)),
+    "tgv16_per_char_rusanov_rk3": ("tgv", dict(cells=(16, 16, 16), bc="PERIODIC", riemann="RUSANOV"), 2, (2,)),
+}
+
+
+def make(name, case_name, kw, nsteps, snaps):
+    case, num = rr.customize(*rr.load_case(case_name), **kw)
+    run = rr.ReferenceRun(case, num)
+    d = {"case_json": np.array(json.dumps(case)), "num_json": np.array(json.dumps(num))}
+    d["prims0"] = run.interior(run.primitives).copy()
+    d["prims0_halo"] = run.primitives
+    d["cons0_halo"] = run.conservatives
+    d["dt0"] = np.float64(run.dt)
+    # per-axis rhs of the initial state
+    ss = run.sim.space_solver
+    mf = run.material_fields
+    for a in run.sim.domain_information.active_axes_indices:
+        out = ss.compute_rhs_xi(mf.conservatives, mf.primitives, None, a, 0.0, run.dt)
+        d[f"rhs_axis{a}"] = np.array(out[0].conservatives)
+    seq = {"dt": [], "time": [], "totals": [], "min_density": [], "min_pressure": []}
+    for n in range(1, nsteps + 1):
+        rec = run.step(record_stages=(n == 1))
+        if n == 1:
+            for k, (r, p, c) in enumerate(zip(rec["rhs"], rec["prims"], rec["cons"])):
+                d[f"rhs_s{k}"], d[f"prims_s{k}"], d[f"cons_s{k}"] = r, p, c
+        seq["dt"].append(rec["dt_next"])
+        seq["time"].append(rec["time"])
+        seq["totals"].append(rec["totals"])
+        seq["min_density"].append(rec["min_density"])
+        seq["min_pressure"].append(rec["min_pressure"])
+        if n in snaps:
+            d[f"prims_n{n}"], d[f"cons_n{n}"] = run.primitives, run.conservatives
+    for k, v in seq.items():
+        d[k] = np.array(v)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    for name, (case_name, kw, nsteps, snaps) in FIXTURES.items():
+        if only and name not in only:
+            continue
+        with np.errstate(all="ignore"):
+            make(name, case_name, kw, nsteps, snaps)

@@ -1,0 +1,127 @@
+"""Shared test helpers: setups, fixtures, error metrics."""
+import glob
+import json
+import os
+
+import numpy as np
+
+from oracle import port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star tolerances
+TOL_RHS = 1e-12        # per-stage RHS, relative L-inf
+TOL_PRIMS_100 = 1e-9   # primitives after 100 steps, relative L-inf
+TOL_TOTALS = 1e-12     # conserved totals
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    case = json.loads(str(g["case_json"]))
+    num = json.loads(str(g["num_json"]))
+    return g, case, num
+
+
+def setup_from_json(case, num) -> port.Setup:
+    d = case["domain"]
+    c = num["conservatives"]
+    g = c["convective_fluxes"]["godunov"]
+    return port.Setup(
+        cells=tuple(d[a]["cells"] for a in "xyz"),
+        domain=tuple(tuple(d[a]["range"]) for a in "xyz"),
+        bc={f: case["boundary_conditions"][f]["type"] for f in port.FACES},
+        gamma=case["material_properties"]["equation_of_state"]["specific_heat_ratio"],
+        nh=c["halo_cells"],
+        recon=g.get("reconstruction_variable", "PRIMITIVE"),
+        riemann=g.get("riemann_solver", "HLLC"),
+        integrator=c["time_integration"]["integrator"],
+        cfl=c["time_integration"].get("CFL", 0.5),
+    )
+
+
+def make_setup(cells, bc="PERIODIC", recon="CHAR-PRIMITIVE", riemann="HLLC", integrator="RK3", gamma=1.4,
+               length=1.0, nh=5):
+    cells = tuple(cells)
+    bcs = {}
+    for f in port.FACES:
+        ax = port.FACE_AXIS[f]
+        bcs[f] = (bc if isinstance(bc, str) else bc[f]) if cells[ax] > 1 else "INACTIVE"
+    return port.Setup(cells=cells, domain=((0.0, length),) * 3, bc=bcs, gamma=gamma, nh=nh, recon=recon,
+                      riemann=riemann, integrator=integrator)
+
+
+def smooth_ic(s: port.Setup, seed=0, amp=0.2):
+    """Deterministic smooth-but-generic periodic primitives (5, Nx, Ny, Nz), plus a steep feature."""
+    rng = np.random.default_rng(seed)
+    x, y, z = np.meshgrid(*s.cell_centers(), indexing="ij")
+    L = [s.domain[i][1] - s.domain[i][0] for i in range(3)]
+    ph = rng.uniform(0, 2 * np.pi, size=(5, 3))
+    k = 2 * np.pi
+
+    def wave(v):
+        out = 0.0
+        for i, (c, n) in enumerate(zip((x, y, z), s.cells)):
+            if n > 1:
+                out = out + np.sin(k * c / L[i] + ph[v, i]) * np.cos(2 * k * c / L[i] - ph[v, (i + 1) % 3])
+        return out
+    rho = 1.0 + amp * wave(0)
+    u = amp * 2 * wave(1)
+    v = amp * 2 * wave(2) if s.cells[1] > 1 else np.zeros_like(rho)
+    w = amp * 2 * wave(3) if s.cells[2] > 1 else np.zeros_like(rho)
+    p = 1.0 + amp * wave(4)
+    # a steep (but resolved-by-WENO) bump so the nonlinear weights are exercised
+    r2 = sum(((c - 0.5 * (s.domain[i][0] + s.domain[i][1])) / L[i]) ** 2
+             for i, (c, n) in enumerate(zip((x, y, z), s.cells)) if n > 1)
+    rho = rho + 0.5 * (r2 < 0.04)
+    p = p + 0.7 * (r2 < 0.04)
+    return np.stack([rho, u, v, w, p]).astype(np.float64)
+
+
+def field_scales(b, floor=1e-30):
+    """Per-field normalisation: max|b_v|, floored at 1e-3 of the largest field (fields that are
+    identically ~0 in the reference, e.g. w-momentum in TGV, cannot be normalised by themselves;
+    SURVEY 8c)."""
+    b = np.asarray(b)
+    scale_all = max(float(np.max(np.abs(b))), floor)
+    return np.array([max(float(np.max(np.abs(b[v]))), 1e-3 * scale_all) for v in range(b.shape[0])])
+
+
+def rhs_scales(prims, s):
+    """Per-field scale of a stage RHS: max over cells of sum_axes |rhs_axis| -- the size of the terms
+    the RHS is a sum of.  At low Mach the total is a cancellation of large axis contributions (TGV:
+    energy 169 + (-169) -> 0.3; mass 0.94 - 0.94 -> 1e-4), so normalising the error by the cancelled
+    total would measure the conditioning of the reference's own formula (the reference evaluated with
+    and without FMA contraction already differs by 1e-11 in that norm, tests/test_hostsim.py), not the
+    kernel.  The north-star bound 1e-12 is applied in this norm."""
+    tot = 0.0
+    for a in s.active:
+        tot = tot + np.abs(port.rhs_axis(prims, a, s))
+    return field_scales(tot)
+
+
+def rel_linf(a, b, scale=None):
+    """max_v max|a_v-b_v| / scale_v with scale_v = field_scales(b) unless given.  For a single
+    axis' contribution to the RHS pass the scales of the TOTAL stage RHS: the north-star bound is on
+    the stage RHS, and one axis can be ~0 (TGV: w = 0) while its fluxes are O(100)."""
+    a, b = np.asarray(a), np.asarray(b)
+    sc = field_scales(b) if scale is None else np.asarray(scale)
+    return max(float(np.max(np.abs(a[v] - b[v]))) / float(sc[v]) for v in range(b.shape[0]))
+
+
+def face_halo_mask(s: port.Setup):
+    """Boolean mask (X,Y,Z) of cells the path defines: interior + face halos (no edges/corners)."""
+    shape = s.shape[1:]
+    inter = [np.zeros(n, bool) for n in shape]
+    for i in range(3):
+        if s.cells[i] > 1:
+            inter[i][s.nh:-s.nh] = True
+        else:
+            inter[i][:] = True
+    ix, iy, iz = np.meshgrid(*inter, indexing="ij")
+    n_out = (~ix).astype(int) + (~iy).astype(int) + (~iz).astype(int)
+    return n_out <= 1

@@ -1,0 +1,43 @@
+"""Host simulation of the device numerics (see host_numerics.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libhost_numerics.so")
+SRC = os.path.join(HERE, "host_numerics.cpp")
+HDR = os.path.join(os.path.dirname(os.path.dirname(HERE)), "jaxfluids_b200", "csrc", "numerics.cuh")
+
+
+def load(fma=True):
+    so = SO if fma else SO.replace(".so", "_nofma.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        flags = ["-O2", "-mfma", "-ffp-contract=fast"] if fma else ["-O2", "-ffp-contract=off"]
+        subprocess.run(["g++", "-shared", "-fPIC", "-std=c++17", "-I/usr/local/cuda/include"] + flags +
+                       ["-o", so, SRC], check=True)
+    lib = C.CDLL(so)
+    lib.face_flux_host.restype = C.c_int
+    lib.face_flux_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_double, C.c_void_p]
+    return lib
+
+
+def rhs_axis(prims, axis, s, fma=True):
+    """Same contract as oracle.port.rhs_axis, computed with the device functions on the host."""
+    from oracle import port
+    lib = load(fma)
+    w = np.stack(port._window(prims, axis, s), axis=-1)          # (5, faces..., 6)
+    w = np.moveaxis(w, 0, -2)                                    # (faces..., 5, 6)
+    shp = w.shape[:-2]
+    w = np.ascontiguousarray(w.reshape(-1, 5, 6))
+    out = np.empty((w.shape[0], 5))
+    rc = lib.face_flux_host(axis, {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon], {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+                            w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data)
+    assert rc == 0
+    f = np.moveaxis(out.reshape(shp + (5,)), -1, 0)
+    lo = [slice(None)] * 4
+    hi = [slice(None)] * 4
+    lo[1 + axis] = slice(None, -1)
+    hi[1 + axis] = slice(1, None)
+    return s.inv_dx[axis] * (f[tuple(lo)] - f[tuple(hi)])

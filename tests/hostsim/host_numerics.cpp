@@ -1,0 +1,30 @@
+// Host build of jaxfluids_b200/csrc/numerics.cuh (TEST TOOL, not product): lets the CPU-only
+// container check the arithmetic of the device functions (with FMA contraction, like nvcc's
+// default -fmad=true) against the oracle before spending GPU time.
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#include <cmath>
+using std::fabs; using std::fmin; using std::fmax; using std::sqrt;
+#include "../../jaxfluids_b200/csrc/numerics.cuh"
+
+using namespace jxf;
+
+template <int A, int RECON, int RIEMANN>
+static void run(const double* win, long n, double gamma, double* out) {
+  for (long i = 0; i < n; ++i) {
+    double w[5][6], F[5];
+    for (int v = 0; v < 5; ++v) for (int k = 0; k < 6; ++k) w[v][k] = win[(i * 5 + v) * 6 + k];
+    face_flux<A, RECON, RIEMANN>(w, gamma, F);
+    for (int v = 0; v < 5; ++v) out[i * 5 + v] = F[v];
+  }
+}
+
+// windows: (n, 5, 6) doubles; out: (n, 5)
+extern "C" int face_flux_host(int axis, int recon, int riemann, const double* win, long n, double gamma, double* out) {
+#define CASE(A, R, S) if (axis == A && recon == R && riemann == S) { run<A, R, S>(win, n, gamma, out); return 0; }
+  CASE(0,0,0) CASE(0,0,1) CASE(0,1,0) CASE(0,1,1)
+  CASE(1,0,0) CASE(1,0,1) CASE(1,1,0) CASE(1,1,1)
+  CASE(2,0,0) CASE(2,0,1) CASE(2,1,0) CASE(2,1,1)
+  return -1;
+}

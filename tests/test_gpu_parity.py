@@ -1,0 +1,280 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI, against the CPU oracle
+(oracle/port.py, pinned bit-identically to the reference) and the reference's own fixtures.
+
+Tolerances are the north-star's: per-stage RHS rel L-inf <= 1e-12, primitives after 100 steps
+<= 1e-9, conserved totals <= 1e-12.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def make_solver(s: port.Setup, bc=None):
+    from jaxfluids_b200.engine import BlockConfig, BlockSolver
+    cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min),
+                      gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, riemann=s.riemann,
+                      integrator=s.integrator, cfl=s.cfl)
+    return BlockSolver(cfg)
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def test_library_is_loaded_and_native():
+    from jaxfluids_b200 import _lib
+    lib = _lib.load()
+    assert lib.jxf_version() >= 100
+
+
+VARIANTS = [("CHAR-PRIMITIVE", "HLLC"), ("PRIMITIVE", "HLLC"), ("CHAR-PRIMITIVE", "RUSANOV"), ("PRIMITIVE", "RUSANOV")]
+GRIDS = [(48, 1, 1), (1000, 1, 1), (40, 24, 1), (33, 47, 1), (24, 20, 28), (16, 33, 40), (37, 16, 19)]
+
+
+@pytest.mark.parametrize("recon,riemann", VARIANTS)
+@pytest.mark.parametrize("cells", GRIDS)
+def test_rhs_per_axis_and_total(cells, recon, riemann):
+    s = H.make_setup(cells, bc="PERIODIC", recon=recon, riemann=riemann)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=sum(cells)), s)
+    sol = make_solver(s)
+    p = dev(prims)
+    ref = port.compute_rhs(prims, s)
+    scales = H.rhs_scales(prims, s)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s), scale=scales) <= H.TOL_RHS, f"axis {a}"
+    got = host(sol.compute_rhs(p))
+    assert H.rel_linf(got, ref, scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("name", H.golden_names())
+def test_reference_fixture_rhs_and_stages(name):
+    """Against what the reference itself produced (tests/golden): per-axis rhs, stage rhs, stage states."""
+    g, case, num = H.load_golden(name)
+    s = H.setup_from_json(case, num)
+    sol = make_solver(s)
+    p0 = dev(g["prims0_halo"])
+    scales = H.rhs_scales(g["prims0_halo"], s)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p0, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), g[f"rhs_axis{a}"], scale=scales) <= H.TOL_RHS
+    mask = H.face_halo_mask(s)
+    nst = port.RK[s.integrator]["stages"]
+    for k in range(nst):
+        # stage rhs from the reference's stage-entry primitives
+        p_in = g["prims0_halo"] if k == 0 else g[f"prims_s{k-1}"]
+        p_in = np.nan_to_num(p_in, nan=1.0, posinf=1.0, neginf=1.0)
+        got = host(sol.compute_rhs(dev(p_in)))
+        assert H.rel_linf(got, g[f"rhs_s{k}"], scale=H.rhs_scales(p_in, s)) <= H.TOL_RHS, f"stage {k}"
+    # full first step through the fused stage kernels
+    from jaxfluids_b200.engine import BlockState
+    st = BlockState(sol, np.nan_to_num(g["prims0_halo"], nan=1.0, posinf=1.0, neginf=1.0),
+                    np.nan_to_num(g["cons0_halo"], nan=1.0, posinf=1.0, neginf=1.0))
+    assert abs(st.dt.item() - float(g["dt0"])) <= 1e-14 * float(g["dt0"])
+    st.step()
+    pr, co = host(st.primitives), host(st.conservatives)
+    ref_p, ref_c = g[f"prims_s{nst-1}"], g[f"cons_s{nst-1}"]
+    assert H.rel_linf(pr[:, mask], ref_p[:, mask]) <= 1e-12
+    assert H.rel_linf(co[:, mask], ref_c[:, mask]) <= 1e-12
+    assert abs(st.dt.item() - g["dt"][0]) <= 1e-12 * g["dt"][0]
+
+
+@pytest.mark.parametrize("name", H.golden_names())
+def test_reference_fixture_multi_step(name):
+    """dt sequence, totals, min rho / min p and the state after N steps against the reference."""
+    from jaxfluids_b200.engine import BlockState
+    g, case, num = H.load_golden(name)
+    s = H.setup_from_json(case, num)
+    sol = make_solver(s)
+    st = BlockState(sol, np.nan_to_num(g["prims0_halo"], nan=1.0, posinf=1.0, neginf=1.0),
+                    np.nan_to_num(g["cons0_halo"], nan=1.0, posinf=1.0, neginf=1.0))
+    mask = H.face_halo_mask(s)
+    n = len(g["dt"])
+    sl = (slice(None),) + s.interior
+    for i in range(1, n + 1):
+        st.step()
+        info = host(st.info)
+        assert abs(st.dt.item() - g["dt"][i - 1]) <= 1e-10 * g["dt"][i - 1]
+        assert abs(st.time.item() - g["time"][i - 1]) <= 1e-12 * g["time"][i - 1]
+        assert abs(info[1] - g["min_density"][i - 1]) <= 1e-10 * abs(g["min_density"][i - 1])
+        assert abs(info[2] - g["min_pressure"][i - 1]) <= 1e-10 * abs(g["min_pressure"][i - 1])
+        if f"prims_n{i}" in g:
+            pr, co = host(st.primitives), host(st.conservatives)
+            assert H.rel_linf(pr[:, mask], g[f"prims_n{i}"][:, mask]) <= H.TOL_PRIMS_100, f"step {i}"
+            tot = np.array([co[sl][v].sum() for v in range(5)])
+            ref = g["totals"][i - 1]
+            scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+            assert np.max(np.abs(tot - ref) / scale) <= H.TOL_TOTALS * max(1.0, np.sqrt(np.prod(s.cells)) / 10)
+
+
+@pytest.mark.parametrize("bc", ["PERIODIC", "SYMMETRY", "ZEROGRADIENT"])
+@pytest.mark.parametrize("cells", [(32, 1, 1), (20, 24, 1), (12, 16, 20)])
+def test_halo_fill(cells, bc):
+    s = H.make_setup(cells, bc=bc)
+    sol = make_solver(s)
+    rng = np.random.default_rng(1)
+    base = np.ones(s.shape) * port.EPS
+    base[(slice(None),) + s.interior] = H.smooth_ic(s, seed=3)
+    cons = port.cons_from_prims(base, s.gamma)
+    ref_p, ref_c = port.halo_fill(base, cons, s)
+    p, c = dev(base), dev(cons)
+    sol.halo_fill(p, c)
+    assert np.array_equal(host(p), ref_p)            # pure copies / sign flips: bit exact
+    mask = H.face_halo_mask(s)
+    assert H.rel_linf(host(c)[:, mask], ref_c[:, mask]) <= 1e-15
+
+
+@pytest.mark.parametrize("cells", [(64, 1, 1), (24, 20, 1), (12, 16, 20)])
+def test_whole_buffer_transforms(cells):
+    s = H.make_setup(cells)
+    sol = make_solver(s)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=5), s)
+    prims = np.nan_to_num(prims)
+    prims[prims == 0] = 1.0
+    c = sol.new_field()
+    sol.cons_from_prims(dev(prims), c)
+    ref_c = port.cons_from_prims(prims, s.gamma)
+    assert H.rel_linf(host(c), ref_c) <= 1e-15
+    p = sol.new_field()
+    sol.prims_from_cons(dev(ref_c), p)
+    assert H.rel_linf(host(p), port.prims_from_cons(ref_c, s.gamma)) <= 1e-14
+
+
+@pytest.mark.parametrize("integrator", ["EULER", "RK2", "RK3"])
+@pytest.mark.parametrize("cells,bc", [((96, 1, 1), "ZEROGRADIENT"), ((28, 36, 1), "SYMMETRY"), ((16, 12, 20), "PERIODIC")])
+def test_steps_against_oracle(cells, bc, integrator):
+    """10 steps: state, dt sequence, min rho/p, totals."""
+    from jaxfluids_b200.engine import BlockState
+    s = H.make_setup(cells, bc=bc, integrator=integrator)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=11, amp=0.1), s)
+    sol = make_solver(s)
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    assert abs(st.dt.item() - dt) <= 1e-14 * dt
+    mask = H.face_halo_mask(s)
+    for i in range(10):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    assert abs(st.dt.item() - dt) <= 1e-11 * dt
+    assert H.rel_linf(host(st.primitives)[:, mask], prims[:, mask]) <= 1e-11
+    assert H.rel_linf(host(st.conservatives)[:, mask], cons[:, mask]) <= 1e-11
+    mr, mp = port.positivity_info(prims, s)
+    info = host(st.info)
+    assert abs(info[1] - mr) <= 1e-11 * abs(mr) and abs(info[2] - mp) <= 1e-11 * abs(mp)
+
+
+def test_sod_100_steps_within_1e9():
+    """North-star bound: primitives rel L-inf <= 1e-9 after 100 steps (Sod, 1000 cells)."""
+    from jaxfluids_b200.engine import BlockState
+    s = H.make_setup((1000, 1, 1), bc="ZEROGRADIENT")
+    x = s.cell_centers()[0]
+    pr = np.zeros((5, 1000, 1, 1))
+    pr[0, :, 0, 0] = np.where(x <= 0.5, 1.0, 0.125)
+    pr[4, :, 0, 0] = np.where(x <= 0.5, 1.0, 0.1)
+    prims, cons = port.initialize(pr, s)
+    sol = make_solver(s)
+    st = BlockState(sol, prims, cons)
+    dt = port.time_step_size(prims, s)
+    for i in range(100):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    assert H.rel_linf(host(st.primitives), prims) <= H.TOL_PRIMS_100
+    tot = host(st.conservatives)[(slice(None),) + s.interior].sum(axis=(1, 2, 3))
+    ref = port.totals(cons, s)
+    assert abs(tot[0] - ref[0]) <= H.TOL_TOTALS * abs(ref[0]) * 10
+    assert abs(tot[4] - ref[4]) <= H.TOL_TOTALS * abs(ref[4]) * 10
+
+
+def test_tgv_32_100_steps_within_1e9():
+    """TGV 32^3 (the shipped case file's grid), SYMMETRY, 100 steps vs the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    g, case, num = H.load_golden("tgv16_sym_char_hllc_rk3")
+    case["domain"]["x"]["cells"] = case["domain"]["y"]["cells"] = case["domain"]["z"]["cells"] = 32
+    s = H.setup_from_json(case, num)
+    x, y, z = np.meshgrid(*s.cell_centers(), indexing="ij")
+    pr = np.stack([np.ones_like(x), np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z),
+                   np.zeros_like(x),
+                   1 / 1.4 / 0.1 ** 2 + 1 / 16.0 * ((np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2))])
+    prims, cons = port.initialize(pr, s)
+    sol = make_solver(s)
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    mask = H.face_halo_mask(s)
+    for i in range(100):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    assert H.rel_linf(host(st.primitives)[:, mask], prims[:, mask]) <= H.TOL_PRIMS_100
+    tot = host(st.conservatives)[(slice(None),) + s.interior].sum(axis=(1, 2, 3))
+    ref = port.totals(cons, s)
+    assert abs(tot[0] - ref[0]) <= H.TOL_TOTALS * abs(ref[0]) * 10
+    assert abs(tot[4] - ref[4]) <= H.TOL_TOTALS * abs(ref[4]) * 10
+
+
+def test_pack_unpack_faces_roundtrip():
+    """pack(face) of a periodic block + unpack on the opposite face == the PERIODIC halo fill."""
+    s = H.make_setup((12, 16, 20), bc="PERIODIC")
+    nb = {f: "NEIGHBOR" for f in port.FACES}
+    sol_n = make_solver(s, bc=nb)
+    base = np.ones(s.shape) * port.EPS
+    base[(slice(None),) + s.interior] = H.smooth_ic(s, seed=2)
+    cons = port.cons_from_prims(base, s.gamma)
+    ref_p, ref_c = port.halo_fill(base, cons, s)
+    p, c = dev(base), dev(cons)
+    sol_n.halo_fill(p, c)                       # all faces NEIGHBOR: must be a no-op
+    assert np.array_equal(host(p), base)
+    opp = {0: 1, 1: 0, 2: 3, 3: 2, 4: 5, 5: 4}
+    for face in range(6):
+        slab = torch.empty(sol_n.face_slab_elems(face), dtype=torch.float64, device="cuda")
+        sol_n.pack_face(face, p, slab)
+        sol_n.unpack_face(opp[face], slab, p, c)
+    assert np.array_equal(host(p), ref_p)
+    mask = H.face_halo_mask(s)
+    assert H.rel_linf(host(c)[:, mask], ref_c[:, mask]) <= 1e-15
+
+
+def test_full_size_properties_tgv256():
+    """BASELINE config 3 size (TGV 256^3): size-independent properties instead of the oracle --
+    (i) mass and energy conserved to 1e-12 under SYMMETRY BCs, (ii) the TGV mirror symmetries hold."""
+    from jaxfluids_b200.engine import BlockState
+    n = 256
+    s = H.make_setup((n, n, n), bc="SYMMETRY", gamma=5.0 / 3.0, length=2 * np.pi)
+    c = torch.as_tensor(s.cell_centers()[0], dtype=torch.float64, device="cuda")
+    x, y, z = c[:, None, None], c[None, :, None], c[None, None, :]
+    sol = make_solver(s)
+    p = sol.new_field(port.EPS)
+    nh = s.nh
+    it = p[:, nh:-nh, nh:-nh, nh:-nh]
+    it[0] = 1.0
+    it[1] = torch.sin(x) * torch.cos(y) * torch.cos(z)
+    it[2] = -torch.cos(x) * torch.sin(y) * torch.cos(z)
+    it[3] = 0.0
+    it[4] = 1 / 1.4 / 0.1 ** 2 + 1 / 16.0 * ((torch.cos(2 * x) + torch.cos(2 * y)) * (torch.cos(2 * z) + 2))
+    co = sol.new_field(port.EPS)
+    sol.cons_from_prims(p, co)
+    sol.halo_fill(p, co)
+    st = BlockState(sol, p, co)
+    tot0 = st.conservatives[:, nh:-nh, nh:-nh, nh:-nh].sum(dim=(1, 2, 3)).cpu().numpy()
+    for _ in range(3):
+        st.step()
+    ci = st.conservatives[:, nh:-nh, nh:-nh, nh:-nh]
+    tot = ci.sum(dim=(1, 2, 3)).cpu().numpy()
+    assert abs(tot[0] - tot0[0]) <= 1e-12 * abs(tot0[0])
+    assert abs(tot[4] - tot0[4]) <= 1e-12 * abs(tot0[4])
+    pi = st.primitives[:, nh:-nh, nh:-nh, nh:-nh]
+    # mirror symmetry about the domain centre planes: rho, p even; u odd in x; v odd in y
+    assert float((pi[0] - pi[0].flip(0)).abs().max()) <= 1e-12
+    assert float((pi[1] + pi[1].flip(0)).abs().max()) <= 1e-12
+    assert float((pi[2] + pi[2].flip(1)).abs().max()) <= 1e-12
+    assert float((pi[4] - pi[4].flip(2)).abs().max()) <= 1e-11 * float(pi[4].abs().max())
+    assert bool(torch.isfinite(pi).all())

@@ -1,0 +1,124 @@
+"""CPU: the reference's shipped case / numerical-setup JSON files select this path unchanged, and
+options outside the path fail loudly."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from jaxfluids_b200.input_manager import InputManager
+from jaxfluids_b200.domain_information import DomainInformation
+from tests import helpers as H
+
+
+def fixture_setups():
+    out = {}
+    for name in H.golden_names():
+        _, case, num = H.load_golden(name)
+        out[name] = (case, num)
+    return out
+
+
+SETUPS = fixture_setups()
+
+
+@pytest.mark.parametrize("name", sorted(SETUPS))
+def test_reference_json_parses(name, tmp_path):
+    case, num = SETUPS[name]
+    im = InputManager(case, num)
+    # also through files, like examples/*/run.py
+    pc, pn = tmp_path / "case.json", tmp_path / "num.json"
+    pc.write_text(json.dumps(case)); pn.write_text(json.dumps(num))
+    im2 = InputManager(str(pc), str(pn))
+    s = H.setup_from_json(case, num)
+    for m in (im, im2):
+        di = m.domain_information
+        assert di.global_number_of_cells == s.cells
+        assert di.device_shape_with_halos == s.shape
+        assert tuple(float(x) for x in di.one_cell_sizes) == tuple(float(x) for x in s.inv_dx)
+        assert di.smallest_cell_size == float(s.dx_min)
+        g = m.numerical_setup.conservatives.convective_fluxes.godunov
+        assert (g.reconstruction_variable, g.riemann_solver, g.reconstruction_stencil) == (s.recon, s.riemann, "WENO5-Z")
+        assert m.numerical_setup.conservatives.time_integration.integrator == s.integrator
+        assert m.case_setup.boundary_condition_setup == s.bc
+
+
+@pytest.mark.parametrize("name", sorted(SETUPS))
+def test_initial_condition_lambdas_match_reference(name):
+    g, case, num = H.load_golden(name)
+    im = InputManager(case, num)
+    mesh = im.domain_information.compute_device_mesh_grid(0)
+    ic = im.case_setup.initial_condition_setup
+    prims = np.stack([ic[k](*mesh) for k in ("rho", "u", "v", "w", "p")])
+    assert prims.shape == g["prims0"].shape
+    np.testing.assert_allclose(prims, g["prims0"], rtol=0, atol=1e-15)
+
+
+def _mod(d, path, value):
+    d = copy.deepcopy(d)
+    cur = d
+    for k in path[:-1]:
+        cur = cur.setdefault(k, {})
+    cur[path[-1]] = value
+    return d
+
+
+GOD = ("conservatives", "convective_fluxes", "godunov")
+
+
+@pytest.mark.parametrize("path,value", [
+    (GOD + ("riemann_solver",), "HLL"),
+    (GOD + ("signal_speed",), "DAVIS"),
+    (GOD + ("reconstruction_stencil",), "WENO5-JS"),
+    (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
+    (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
+    (("conservatives", "time_integration", "integrator"), "RK2_LS4"),
+    (("active_physics", "is_viscous_flux"), True),
+    (("precision", "is_double_precision_compute"), False),
+])
+def test_valid_reference_options_outside_the_path_raise_not_implemented(path, value):
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    with pytest.raises(NotImplementedError, match="B200 path"):
+        InputManager(case, _mod(num, path, value))
+
+
+@pytest.mark.parametrize("path,value", [
+    (GOD + ("riemann_solver",), "HLLD"),
+    (GOD + ("reconstruction_stencil",), "WENO5"),
+    (("conservatives", "time_integration", "CFL"), -0.5),
+    (("conservatives", "halo_cells"), 2),
+])
+def test_invalid_values_fail_the_reference_consistency_assertion(path, value):
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    with pytest.raises(AssertionError, match="Consistency error in numerical setup file"):
+        InputManager(case, _mod(num, path, value))
+
+
+def test_case_errors():
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    with pytest.raises(NotImplementedError):
+        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "WALL"), num)
+    with pytest.raises(AssertionError, match="case setup"):
+        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "PERIODIC"), num)   # west is SYMMETRY
+    with pytest.raises(AssertionError, match="argument labels"):
+        InputManager(_mod(case, ("initial_condition", "u"), "lambda x, y: x"), num)
+    with pytest.raises(NotImplementedError):
+        InputManager(_mod(case, ("material_properties", "equation_of_state", "model"), "StiffenedGas"), num)
+    bad = copy.deepcopy(case); del bad["general"]["end_time"]
+    with pytest.raises(AssertionError, match="end_time or end_step"):
+        InputManager(bad, num)
+
+
+def test_decomposition_bookkeeping():
+    di = DomainInformation((64, 32, 16), ((0, 1),) * 3, (2, 2, 2), 5)
+    assert di.device_number_of_cells == (32, 16, 8)
+    # rank = i*sy*sz + j*sz + k  (domain/helper_functions.py:155-169)
+    assert [di.block_index(r) for r in range(8)] == [(i, j, k) for i in range(2) for j in range(2) for k in range(2)]
+    assert di.neighbor(0, "east", periodic=False) == 4 and di.neighbor(0, "west", periodic=False) is None
+    assert di.neighbor(0, "west", periodic=True) == 4
+    assert di.neighbor(5, "north", periodic=False) == 7 and di.neighbor(5, "top", periodic=False) is None
+    assert di.neighbor(5, "bottom", periodic=False) == 4
+    assert di.block_slices(6) == (slice(32, 64), slice(16, 32), slice(0, 8))
+    di1 = DomainInformation((64, 1, 1), ((0, 1),) * 3, (1, 1, 1), 5)
+    assert di1.neighbor(0, "east", periodic=True) is None     # unsplit periodic axis is a local BC

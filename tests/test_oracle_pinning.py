@@ -1,0 +1,21 @@
+"""CPU, build container only: oracle/port.py is bit-identical to the reference's own sources run on
+the NumPy `jax` stand-in.  Skipped where /root/reference does not exist (the GPU box)."""
+import numpy as np
+import pytest
+
+from oracle.refharness import run_reference as rr
+
+pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference sources not present")
+
+
+@pytest.mark.parametrize("name,kw,nsteps", [
+    ("sod", dict(cells=(120, None, None)), 3),
+    ("sod", dict(cells=(64, None, None), recon="PRIMITIVE", riemann="RUSANOV", integrator="EULER"), 2),
+    ("riemann2d", dict(cells=(20, 28, None)), 2),
+    ("tgv", dict(cells=(12, 12, 12)), 1),
+    ("tgv", dict(cells=(10, 12, 14), bc="PERIODIC", recon="PRIMITIVE"), 1),
+])
+def test_port_is_bit_identical_to_reference(name, kw, nsteps):
+    from oracle.refharness import pin_check
+    with np.errstate(all="ignore"):
+        pin_check.check(name, nsteps=nsteps, **kw)
