@@ -57,11 +57,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = LIB_PATH
+    variant = os.environ.get("JXF_LIB_VARIANT")
+    if variant:
+        path = LIB_PATH.replace(".so", f"_{variant}.so")
+    if not os.path.exists(path):
         raise JxfError(
-            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"{path} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
             "g.build()'` at the repo root. There is no CPU fallback for this path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, dp, i32, i64 = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
     lib.jxf_last_error.restype = C.c_char_p
     lib.jxf_last_error.argtypes = []

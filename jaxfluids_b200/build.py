@@ -42,5 +42,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_variant(name: str, defines) -> str:
+    """Tuning builds (e.g. JXF_MIN_BLOCKS=4) next to the production library; selected at run time with
+    JXF_LIB_VARIANT=<name>.  Not used by tests or the default bench."""
+    out = OUT.replace(".so", f"_{name}.so")
+    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SRC
+    print("[jaxfluids_b200.build]", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -59,36 +59,68 @@ struct SweepArgs {
 };
 
 // ---------------------------------------------------------------------------
-// cell finalisation shared by both sweep kinds
+// sweep geometry in ROLES (filled on the host): A = sweep axis; T1/T2 = the two transverse axes
+// with T2 the faster one in memory.  Strided sweeps: T2 is the contiguous axis (lanes run along
+// it).  Contiguous sweeps: A itself is the contiguous axis and rows are indexed (i1, i2).
+// All offsets are relative to the first INTERIOR cell (h0 is folded into the base pointers).
 // ---------------------------------------------------------------------------
+struct SweepGeom {
+  int nA, n1, n2;
+  long long sA, s1, s2;      // strides in the halo'd buffers
+  long long rA, r1, r2;      // strides in the interior-only rhs buffer
+  long long vst, rvst;       // variable strides
+};
+
+#ifndef JXF_MIN_BLOCKS
+#define JXF_MIN_BLOCKS 3
+#endif
+
+// operands of the cell update that come from memory; loaded EARLY (before the flux arithmetic of
+// the iteration) so their latency hides behind ~700 FP64 instructions
 template <int EPI>
-__device__ __forceinline__ void finalize_cell(const Geom& g, const SweepArgs& a, long long hidx, long long ridx,
-                                              const double (&r)[5], double step, Red& red) {
+struct CellIn {
+  double rhs[5];   // EPI=0: accumulate target (if accumulate); EPI=1: earlier axes' sum (if has_prev)
+  double U[5];     // EPI=1
+  double Un[5];    // EPI=1, blend
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
+                                             CellIn<EPI>& in) {
   if (EPI == 0) {
     if (a.accumulate) {
 #pragma unroll
-      for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] += r[v];
-    } else {
-#pragma unroll
-      for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = 0.0 + r[v];
+      for (int v = 0; v < 5; ++v) in.rhs[v] = a.rhs[ridx + v * g.rvst];
     }
   } else {
-    double U[5], tot[5];
 #pragma unroll
-    for (int v = 0; v < 5; ++v) U[v] = a.cons_in[hidx + v * g.vst];
+    for (int v = 0; v < 5; ++v) in.U[v] = a.cons_in[hidx + v * g.vst];
     if (a.has_prev) {
 #pragma unroll
-      for (int v = 0; v < 5; ++v) tot[v] = a.rhs[ridx + v * g.rvst] + r[v];
-    } else {
-#pragma unroll
-      for (int v = 0; v < 5; ++v) tot[v] = 0.0 + r[v];
+      for (int v = 0; v < 5; ++v) in.rhs[v] = a.rhs[ridx + v * g.rvst];
     }
     if (a.blend) {
 #pragma unroll
-      for (int v = 0; v < 5; ++v) U[v] = a.ca * U[v] + a.cb * a.cons_n[hidx + v * g.vst];
+      for (int v = 0; v < 5; ++v) in.Un[v] = a.cons_n[hidx + v * g.vst];
     }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
+                                              const CellIn<EPI>& in, const double (&r)[5], double step, Red& red) {
+  if (EPI == 0) {
 #pragma unroll
-    for (int v = 0; v < 5; ++v) U[v] = U[v] + step * tot[v];
+    for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = (a.accumulate ? in.rhs[v] : 0.0) + r[v];
+  } else {
+    double U[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const double tot = (a.has_prev ? in.rhs[v] : 0.0) + r[v];
+      double u = in.U[v];
+      if (a.blend) u = a.ca * u + a.cb * in.Un[v];
+      U[v] = u + step * tot;
+    }
     double p[5];
     prims_from_cons(U, a.gamma, p);
 #pragma unroll
@@ -101,23 +133,24 @@ __device__ __forceinline__ void finalize_cell(const Geom& g, const SweepArgs& a,
 }
 
 // ---------------------------------------------------------------------------
-// strided sweep: thread = one (C,O) column, marching along A over one chunk
+// strided sweep: thread = one (i1, i2) column (i2 along the contiguous axis), marching along A
+// over one chunk with a rolling 6-cell register window; each face flux is computed once.
 // ---------------------------------------------------------------------------
 template <int A, int RECON, int RIEMANN, int EPI>
-__global__ void __launch_bounds__(128) sweep_strided(const Geom g, const SweepArgs a, const int C, const int O) {
-  const long long plane = (long long)g.n[C] * g.n[O];
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const SweepGeom g, const SweepArgs a) {
+  const long long plane = (long long)g.n1 * g.n2;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   Red red;
   red.init();
   if (p < plane) {
-    const int io = (int)(p / g.n[C]);
-    const int ic = (int)(p - (long long)io * g.n[C]);
+    const int i1 = (int)(p / g.n2);
+    const int i2 = (int)(p - (long long)i1 * g.n2);
     const int f0 = blockIdx.y * a.chunk_len;
-    const int f1 = min(f0 + a.chunk_len, g.n[A]);
-    const long long sA = g.st[A];
-    const long long col_h = (long long)(io + g.off[O]) * g.st[O] + (long long)(ic + g.off[C]) * g.st[C];
-    const long long col_r = (long long)io * g.rst[O] + (long long)ic * g.rst[C];
-    const double* base = a.prims + col_h + (long long)(g.off[A] + f0 - 3) * sA;   // cell f0-3
+    const int f1 = min(f0 + a.chunk_len, g.nA);
+    const long long sA = g.sA;
+    const long long col_h = i1 * g.s1 + i2 * g.s2;
+    const long long col_r = i1 * g.r1 + i2 * g.r2;
+    const double* base = a.prims + col_h + (long long)(f0 - 3) * sA;   // cell f0-3
     const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
     double w[5][6], nx[5], Fp[5];
 #pragma unroll
@@ -130,19 +163,22 @@ __global__ void __launch_bounds__(128) sweep_strided(const Geom g, const SweepAr
     for (int f = f0; f <= f1; ++f) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) w[v][5] = nx[v];
-      if (f < f1) {   // prefetch cell f+3 (<= n+2 < n+nh since nh >= 3)
+      if (f < f1) {   // prefetch cell f+3 (<= n+2 < n+nh since nh >= 3) for the next iteration
         const double* nb = base + (long long)(f - f0 + 6) * sA;
 #pragma unroll
         for (int v = 0; v < 5; ++v) nx[v] = nb[v * g.vst];
       }
+      const long long hidx = col_h + (long long)(f - 1) * sA;
+      const long long ridx = col_r + (long long)(f - 1) * g.rA;
+      CellIn<EPI> in;
+      if (f > f0) load_cell_in<EPI>(g, a, hidx, ridx, in);
       double F[5];
       face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
       if (f > f0) {
-        const int i = f - 1;
         double r[5];
 #pragma unroll
         for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fp[v] - F[v]);
-        finalize_cell<EPI>(g, a, col_h + (long long)(g.off[A] + i) * sA, col_r + (long long)i * g.rst[A], r, step, red);
+        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red);
       }
 #pragma unroll
       for (int v = 0; v < 5; ++v) {
@@ -158,13 +194,13 @@ __global__ void __launch_bounds__(128) sweep_strided(const Geom g, const SweepAr
 }
 
 // ---------------------------------------------------------------------------
-// contiguous sweep: lanes = consecutive faces of the flattened (row, face) sequence
+// contiguous sweep: lanes = consecutive faces of the flattened (row, face) sequence; the left
+// face flux comes from lane-1 by shuffle (lane 0: carry from the warp's previous iteration).
 // ---------------------------------------------------------------------------
 template <int A, int RECON, int RIEMANN, int EPI>
-__global__ void __launch_bounds__(128) sweep_contig(const Geom g, const SweepArgs a, const int O1, const int O2,
-                                                    const long long total_faces) {
-  // rows are indexed row = i1 * n[O2] + i2 with O1 the slower of the two transverse axes
-  const int nf = g.n[A] + 1;
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepGeom g, const SweepArgs a,
+                                                                    const long long total_faces) {
+  const int nf = g.nA + 1;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -184,19 +220,23 @@ __global__ void __launch_bounds__(128) sweep_contig(const Geom g, const SweepArg
     int f = (int)(gf - row * nf);
     for (int it = 0; it < iters; ++it) {
       const bool act = gf < ge;
+      const bool fin = act && f > 0 && gf > gbeg;
       double F[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      long long col_h = 0, col_r = 0;
+      long long hidx = 0, ridx = 0;
+      CellIn<EPI> in;
       if (act) {
-        const int i1 = (int)(row / g.n[O2]);
-        const int i2 = (int)(row - (long long)i1 * g.n[O2]);
-        col_h = (long long)(i1 + g.off[O1]) * g.st[O1] + (long long)(i2 + g.off[O2]) * g.st[O2];
-        col_r = (long long)i1 * g.rst[O1] + (long long)i2 * g.rst[O2];
-        const double* base = a.prims + col_h + (long long)(g.off[A] + f - 3) * g.st[A];
+        const int i1 = (int)(row / g.n2);
+        const int i2 = (int)(row - (long long)i1 * g.n2);
+        const long long col_h = i1 * g.s1 + i2 * g.s2;
+        hidx = col_h + (long long)(f - 1) * g.sA;
+        ridx = i1 * g.r1 + i2 * g.r2 + (long long)(f - 1) * g.rA;
+        const double* base = a.prims + col_h + (long long)(f - 3) * g.sA;
         double w[5][6];
 #pragma unroll
         for (int v = 0; v < 5; ++v)
 #pragma unroll
-          for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.st[A]];
+          for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.sA];
+        if (fin) load_cell_in<EPI>(g, a, hidx, ridx, in);
         face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
       }
       double Fl[5];
@@ -207,12 +247,11 @@ __global__ void __launch_bounds__(128) sweep_contig(const Geom g, const SweepArg
         Fl[v] = (lane == 0) ? carry[v] : up;
         carry[v] = last;
       }
-      if (act && f > 0 && gf > gbeg) {
-        const int i = f - 1;
+      if (fin) {
         double r[5];
 #pragma unroll
         for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fl[v] - F[v]);
-        finalize_cell<EPI>(g, a, col_h + (long long)(g.off[A] + i) * g.st[A], col_r + (long long)i * g.rst[A], r, step, red);
+        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red);
       }
       gf += 32;
       f += 32;
@@ -633,11 +672,29 @@ extern "C" int jxf_num_stages(jxf_handle h) { return h ? h->stages : -1; }
 template <int A, int RECON, int RIEMANN, int EPI>
 static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   const Geom& g = s->g;
-  const int resident = s->num_sms * 4;   // ~4 CTAs of 128 threads per SM
+  const int resident = s->num_sms * JXF_MIN_BLOCKS;   // CTAs of 128 threads resident on the device
+  // fold the interior origin into the base pointers
+  const long long h0 = g.off[0] * g.st[0] + g.off[1] * g.st[1] + g.off[2] * g.st[2];
+  a.prims += h0;
+  if (a.cons_in) a.cons_in += h0;
+  if (a.cons_n) a.cons_n += h0;
+  if (a.cons_out) a.cons_out += h0;
+  if (a.prims_out) a.prims_out += h0;
+  SweepGeom sg;
+  sg.nA = g.n[A];
+  sg.sA = g.st[A];
+  sg.rA = g.rst[A];
+  sg.vst = g.vst;
+  sg.rvst = g.rvst;
+  const int T1 = (A == 0) ? 1 : 0;       // slower transverse axis
+  const int T2 = (A == 2) ? 1 : 2;       // faster transverse axis
   if (A != s->lane_axis) {
+    // lanes along the contiguous axis C; the other transverse axis O is the slow one
     const int C = s->lane_axis;
     const int O = 3 - A - C;
-    const long long plane = (long long)g.n[C] * g.n[O];
+    sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
+    sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
+    const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
     // chunks along A: enough CTAs for ~4 waves, but chunks of >= 16 cells (<= 6% redundant faces)
     int chunks = (int)std::min<long long>((4LL * resident + bx - 1) / bx, std::max(1, g.n[A] / 16));
@@ -646,12 +703,11 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
     dim3 grid(bx, chunks);
     ProfScope prof(s, A + 3 * EPI, st);
-    sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(g, a, C, O);
+    sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
   } else {
-    // the two transverse axes, O1 slower than O2
-    const int O1 = (A == 0) ? 1 : 0;
-    const int O2 = (A == 2) ? 1 : 2;
-    const long long rows = (long long)g.n[O1] * g.n[O2];
+    sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
+    sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    const long long rows = (long long)sg.n1 * sg.n2;
     const int nf = g.n[A] + 1;
     const long long total = rows * nf;
     const long long target_warps = 4LL * resident * 4;   // ~4 waves of warps
@@ -668,7 +724,7 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     const long long nranges = (total + span - 1) / span;
     const long long blocks = std::min<long long>((nranges + 3) / 4, (long long)resident * 4);
     ProfScope prof(s, A + 3 * EPI, st);
-    sweep_contig<A, RECON, RIEMANN, EPI><<<(unsigned)std::max<long long>(1, blocks), 128, 0, st>>>(g, a, O1, O2, total);
+    sweep_contig<A, RECON, RIEMANN, EPI><<<(unsigned)std::max<long long>(1, blocks), 128, 0, st>>>(sg, a, total);
   }
   return check_launch("sweep");
 }

@@ -22,6 +22,27 @@ template <> struct AxisIds<0> { static constexpr int un = 1, t0 = 2, t1 = 3; };
 template <> struct AxisIds<1> { static constexpr int un = 2, t0 = 3, t1 = 1; };
 template <> struct AxisIds<2> { static constexpr int un = 3, t0 = 1, t1 = 2; };
 
+// ===========================================================================
+// Two evaluations of the same formulas:
+//   JXF_REFERENCE_ORDER : the reference's operations in the reference's order (IEEE div/sqrt).
+//                         Without FMA contraction this is bit-identical to the reference
+//                         (tests/test_hostsim.py); it documents WHAT is computed.
+//   default             : the production evaluation -- same formulas, re-associated so that
+//                         one face costs ~680 FP64-pipe instructions instead of ~1900:
+//                         * WENO5-Z on first differences, left+right share differences and
+//                           squares; the three nonlinear weights share ONE reciprocal
+//                           (omega_k = n_k / sum n with n_k = d_k (b_k+tau) prod_{j!=k} b_j,
+//                           b_k = beta_k + eps), betas carried with a common factor 12/13;
+//                         * the characteristic projection acts on the differences and the
+//                           face value is cell value + back-projected correction (R L = I);
+//                         * reciprocals / rsqrt by MUFU seed + Newton (no IEEE slow path),
+//                           1/rho, sqrt(rho), a^2 = gamma p / rho shared inside HLLC;
+//                         * only the HLLC star flux selected by sign(S*) is evaluated.
+//                         Deviation from the reference order is O(1e-15) relative
+//                         (tests/test_hostsim.py, tests/test_gpu_parity.py: <= 1e-12).
+// ===========================================================================
+#ifdef JXF_REFERENCE_ORDER
+
 // ---------------------------------------------------------------------------
 // WENO5-Z  (stencils/reconstruction/shock_capturing/weno5_base.py:34-51,
 //           weno/weno5_z.py:32-52).  (a,b,c,d,e) = cells i-2..i+2 for the left
@@ -194,6 +215,273 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     for (int v = 0; v < 5; ++v) F[v] = 0.5 * (fl[v] + fr[v]) - 0.5 * alpha * (cr[v] - cl[v]);
   }
 }
+
+#else  // production evaluation
+
+// ---------------------------------------------------------------------------
+// fast reciprocal / rsqrt / sqrt: MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 bits) + Newton.
+// Valid for normal, finite, positive-or-negative (rcp) / positive (rsqrt) arguments -- all
+// call sites divide by densities, sound speeds, wave-speed differences and WENO weight sums.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double rcp_fast(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_fast(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  // two Newton steps y <- y + y*(0.5*e) , e = 1 - a y^2
+  double h = 0.5 * y;
+  double e = fma(-a * y, y, 1.0);
+  y = fma(h, e, y);
+  h = 0.5 * y;
+  e = fma(-a * y, y, 1.0);
+  return fma(h, e, y);
+}
+#else
+__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
+__device__ __forceinline__ double rsqrt_fast(double a) { return 1.0 / sqrt(a); }
+#endif
+// sqrt(a) = a * rsqrt(a) with one residual correction (<= 1 ulp)
+__device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a) */) {
+  const double s = a * y;
+  const double r = fma(-s, s, a);
+  return fma(r, 0.5 * y, s);
+}
+
+// ---------------------------------------------------------------------------
+// WENO5-Z on the five first differences d_i = q_{i+1} - q_i of the 6-cell window
+// (weno5_base.py:34-51, weno/weno5_z.py:32-52).  Returns the corrections
+//   left  face value = q2 + cl   (cells i-2..i+2, centre i)
+//   right face value = q3 + cr   (mirror cells i+3..i-1, centre i+1)
+// beta~_k = (12/13) beta_k = e^2 + (3/13) t^2 ; tau, eps scale alike so tau/(beta+eps) is unchanged.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, double d3, double d4,
+                                            double& cl, double& cr) {
+  constexpr double k = 3.0 / 13.0;
+  constexpr double eps = kStencilEps * (12.0 / 13.0);
+  const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;      // second differences
+  const double s1 = e1 * e1, s2 = e2 * e2, s3 = e3 * e3, s4 = e4 * e4;
+  // left stencils:  (a-4b+3c) = 3 d1 - d0 ; (b-d) = -(d1+d2) ; (3c-4d+e) = d3 - 3 d2
+  const double tl0 = fma(3.0, d1, -d0), tl1 = d1 + d2, tl2 = fma(-3.0, d2, d3);
+  // right stencils (mirrored): d4 - 3 d3 ; d2 + d3 ; 3 d2 - d1
+  const double tr0 = fma(-3.0, d3, d4), tr1 = d2 + d3, tr2 = fma(3.0, d2, -d1);
+  const double bl0 = fma(k, tl0 * tl0, s1) + eps, bl1 = fma(k, tl1 * tl1, s2) + eps, bl2 = fma(k, tl2 * tl2, s3) + eps;
+  const double br0 = fma(k, tr0 * tr0, s4) + eps, br1 = fma(k, tr1 * tr1, s3) + eps, br2 = fma(k, tr2 * tr2, s2) + eps;
+  {
+    const double tau = fabs(bl0 - bl2);           // eps cancels in the difference
+    // n_k = d_k (b_k + tau) prod_{j != k} b_j with the common factor 1/10 dropped: d = (1, 6, 3)
+    const double n0 = (bl0 + tau) * (bl1 * bl2);
+    const double m1 = (bl1 + tau) * (bl0 * bl2);
+    const double m2 = (bl2 + tau) * (bl0 * bl1);
+    const double den = fma(6.0, m1, fma(3.0, m2, n0));
+    // p_k - c:  p0-c = 5/6 d1 - 1/3 d0 ; p1-c = 1/3 d2 + 1/6 d1 ; p2-c = 2/3 d2 - 1/6 d3   (x d_k)
+    const double q0 = fma(5.0 / 6.0, d1, (-1.0 / 3.0) * d0);
+    const double q1 = fma(2.0, d2, d1);                          // 6 (p1-c)
+    const double q2 = fma(2.0, d2, -0.5 * d3);                   // 3 (p2-c)
+    const double num = fma(m2, q2, fma(m1, q1, n0 * q0));
+    cl = num * rcp_fast(den);
+  }
+  {
+    const double tau = fabs(br0 - br2);
+    const double n0 = (br0 + tau) * (br1 * br2);
+    const double m1 = (br1 + tau) * (br0 * br2);
+    const double m2 = (br2 + tau) * (br0 * br1);
+    const double den = fma(6.0, m1, fma(3.0, m2, n0));
+    // mirrored differences d0'=-d4, d1'=-d3, d2'=-d2, d3'=-d1
+    const double q0 = fma(-5.0 / 6.0, d3, (1.0 / 3.0) * d4);
+    const double q1 = -fma(2.0, d2, d3);
+    const double q2 = fma(-2.0, d2, 0.5 * d1);
+    const double num = fma(m2, q2, fma(m1, q1, n0 * q0));
+    cr = num * rcp_fast(den);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// EOS / variable transforms (ideal_gas.py:69-88, equation_manager.py:93-101, 164-171, 237-252)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cons_from_prims(const double (&p)[5], double gamma, double (&c)[5]) {
+  const double e = p[4] / (p[0] * (gamma - 1.0));
+  c[0] = p[0];
+  c[1] = p[0] * p[1];
+  c[2] = p[0] * p[2];
+  c[3] = p[0] * p[3];
+  c[4] = p[0] * (0.5 * ((p[1] * p[1] + p[2] * p[2]) + p[3] * p[3]) + e);
+}
+
+// E = rho (u.u/2) + p/(gamma-1) with ig1 = 1/(gamma-1): no division
+__device__ __forceinline__ void cons_from_prims_fast(const double (&p)[5], double ig1, double (&c)[5]) {
+  const double q = fma(p[3], p[3], fma(p[2], p[2], p[1] * p[1]));
+  c[0] = p[0];
+  c[1] = p[0] * p[1];
+  c[2] = p[0] * p[2];
+  c[3] = p[0] * p[3];
+  c[4] = fma(p[0], 0.5 * q, p[4] * ig1);
+}
+
+__device__ __forceinline__ void prims_from_cons(const double (&c)[5], double gamma, double (&p)[5]) {
+  const double one_rho = rcp_fast(c[0]);
+  p[0] = c[0];
+  p[1] = c[1] * one_rho;
+  p[2] = c[2] * one_rho;
+  p[3] = c[3] * one_rho;
+  const double e = c[4] * one_rho - 0.5 * ((p[1] * p[1] + p[2] * p[2]) + p[3] * p[3]);
+  p[4] = (gamma - 1.0) * e * c[0];
+}
+
+// ---------------------------------------------------------------------------
+// Reconstruction (high_order_godunov.py:267-280 PRIMITIVE, :298-316 CHAR-PRIMITIVE with
+// eigendecomposition.py:139-148,215-231 frozen state, :425-431 projection, :517-521 back-projection)
+// ---------------------------------------------------------------------------
+template <int A, int RECON>
+__device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
+                                            double (&pl)[5], double (&pr)[5]) {
+  using Id = AxisIds<A>;
+  if (RECON == RECON_PRIMITIVE) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double cl, cr;
+      weno5z_corr(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3], w[v][5] - w[v][4], cl, cr);
+      pl[v] = w[v][2] + cl;
+      pr[v] = w[v][3] + cr;
+    }
+  } else {
+    double dr[5], du[5], dp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      dr[k] = w[0][k + 1] - w[0][k];
+      du[k] = w[Id::un][k + 1] - w[Id::un][k];
+      dp[k] = w[4][k + 1] - w[4][k];
+    }
+    // frozen state = arithmetic mean of cells i, i+1
+    const double rho_ave = fma(0.5, dr[2], w[0][2]);
+    const double p_ave = fma(0.5, dp[2], w[4][2]);
+    const double gp = gamma * p_ave;                  // = cc_ave * rho_ave
+    const double cc = gp * rcp_fast(rho_ave);
+    const double ic = rsqrt_fast(cc);                 // 1 / c_ave
+    const double c_ave = cc * ic;
+    const double k_u = 0.5 * ic;                      // 0.5 / c
+    const double k_cc = ic * ic;                      // 1 / cc
+    const double k_p = 0.5 * rcp_fast(gp);            // 0.5 / (cc rho)
+    double l0, r0, l1, r1, l4, r4;
+    {
+      double a[5], b[5], c[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double t = k_p * dp[k];
+        a[k] = fma(-k_u, du[k], t);                   // d W0
+        c[k] = fma(k_u, du[k], t);                    // d W4
+        b[k] = fma(-k_cc, dp[k], dr[k]);              // d W1
+      }
+      weno5z_corr(a[0], a[1], a[2], a[3], a[4], l0, r0);
+      weno5z_corr(b[0], b[1], b[2], b[3], b[4], l1, r1);
+      weno5z_corr(c[0], c[1], c[2], c[3], c[4], l4, r4);
+    }
+    double tl, tr;
+    weno5z_corr(w[Id::t0][1] - w[Id::t0][0], w[Id::t0][2] - w[Id::t0][1], w[Id::t0][3] - w[Id::t0][2],
+                w[Id::t0][4] - w[Id::t0][3], w[Id::t0][5] - w[Id::t0][4], tl, tr);
+    pl[Id::t0] = w[Id::t0][2] + tl;
+    pr[Id::t0] = w[Id::t0][3] + tr;
+    weno5z_corr(w[Id::t1][1] - w[Id::t1][0], w[Id::t1][2] - w[Id::t1][1], w[Id::t1][3] - w[Id::t1][2],
+                w[Id::t1][4] - w[Id::t1][3], w[Id::t1][5] - w[Id::t1][4], tl, tr);
+    pl[Id::t1] = w[Id::t1][2] + tl;
+    pr[Id::t1] = w[Id::t1][3] + tr;
+    // prims = cell value + R * correction
+    const double sl = l0 + l4, sr = r0 + r4;
+    pl[0] = w[0][2] + fma(rho_ave, sl, l1);
+    pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
+    pl[4] = fma(gp, sl, w[4][2]);
+    pr[0] = w[0][3] + fma(rho_ave, sr, r1);
+    pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
+    pr[4] = fma(gp, sr, w[4][3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Riemann solvers: HLLC + Einfeldt (HLLC.py:41-126, signal_speeds.py:109-133, :159-199),
+// Rusanov (Rusanov.py:25-47)
+// ---------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ void physical_flux(const double (&p)[5], const double (&c)[5], double (&f)[5]) {
+  const double m = c[1 + A];
+  f[0] = m;
+  f[1] = m * p[1];
+  f[2] = m * p[2];
+  f[3] = m * p[3];
+  f[1 + A] = fma(m, p[1 + A], p[4]);
+  f[4] = p[1 + A] * (c[4] + p[4]);
+}
+
+// F*_K = F_K + S_K^{-/+} (U*_K - U_K), Toro 10.72/10.73; dK = rho_K (S_K - u_K)
+template <int A>
+__device__ __forceinline__ void hllc_star_flux(const double (&p)[5], const double (&c)[5], double inv_rho,
+                                               double S_K, double S_lim, double dK, double S_star, double (&fs)[5]) {
+  using Id = AxisIds<A>;
+  const double pre = dK * rcp_fast(S_K - S_star);                  // (S_K-u_K)/(S_K-S*) rho_K
+  const double es = fma(S_star - p[Id::un], fma(p[4], rcp_fast(dK), S_star), c[4] * inv_rho);
+  double us[5];
+  us[0] = pre;
+  us[Id::un] = pre * S_star;
+  us[Id::t0] = pre * p[Id::t0];
+  us[Id::t1] = pre * p[Id::t1];
+  us[4] = pre * es;
+  double f[5];
+  physical_flux<A>(p, c, f);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) fs[v] = fma(S_lim, us[v] - c[v], f[v]);
+}
+
+template <int A, int RIEMANN>
+__device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double (&pr)[5],
+                                             double gamma, double (&F)[5]) {
+  using Id = AxisIds<A>;
+  const double ig1 = 1.0 / (gamma - 1.0);
+  double cl[5], cr[5];
+  cons_from_prims_fast(pl, ig1, cl);
+  cons_from_prims_fast(pr, ig1, cr);
+  const double uL = pl[Id::un], uR = pr[Id::un];
+  // y = 1/sqrt(rho): 1/rho = y^2, sqrt(rho) = rho y
+  const double yL = rsqrt_fast(pl[0]), yR = rsqrt_fast(pr[0]);
+  const double irL = yL * yL, irR = yR * yR;
+  const double a2L = gamma * pl[4] * irL, a2R = gamma * pr[4] * irR;       // a^2
+  const double aL = sqrt_fast(a2L, rsqrt_fast(a2L)), aR = sqrt_fast(a2R, rsqrt_fast(a2R));
+  if (RIEMANN == RIEMANN_HLLC) {
+    const double sL = pl[0] * yL, sR = pr[0] * yR;                         // sqrt(rho)
+    const double od = rcp_fast(sL + sR);
+    const double eta2 = 0.5 * sL * sR * od * od;
+    const double u_bar = fma(sL, uL, sR * uR) * od;
+    const double du = uR - uL;
+    const double x = fma(eta2, du * du, fma(sL, a2L, sR * a2R) * od);
+    const double d_bar = sqrt_fast(x, rsqrt_fast(x));
+    const double S_L = fmin(u_bar - d_bar, uL - aL);
+    const double S_R = fmax(u_bar + d_bar, uR + aR);
+    const double dL = pl[0] * (S_L - uL);
+    const double dR = pr[0] * (S_R - uR);
+    const double S_star = ((pr[4] - pl[4]) + fma(uL, dL, -(uR * dR))) * rcp_fast(dL - dR);
+    // F = 1/2 (1 + sign S*) F*_L + 1/2 (1 - sign S*) F*_R : only the selected side is evaluated
+    double fL[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, fR[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (S_star >= 0.0) hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
+    if (S_star <= 0.0) hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
+    const double wgt = (S_star == 0.0) ? 0.5 : 1.0;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = wgt * (fL[v] + fR[v]);
+  } else {
+    const double alpha = fmax(fabs(uL) + aL, fabs(uR) + aR);
+    double fl[5], fr[5];
+    physical_flux<A>(pl, cl, fl);
+    physical_flux<A>(pr, cr, fr);
+    const double ha = 0.5 * alpha;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = fma(-ha, cr[v] - cl[v], 0.5 * (fl[v] + fr[v]));
+  }
+}
+
+#endif  // JXF_REFERENCE_ORDER
 
 // window -> numerical flux at the face (high_order_godunov.py:117-231)
 template <int A, int RECON, int RIEMANN>

@@ -11,10 +11,14 @@ SRC = os.path.join(HERE, "host_numerics.cpp")
 HDR = os.path.join(os.path.dirname(os.path.dirname(HERE)), "jaxfluids_b200", "csrc", "numerics.cuh")
 
 
-def load(fma=True):
-    so = SO if fma else SO.replace(".so", "_nofma.so")
+def load(fma=True, reference_order=False):
+    """fma: contract a*b+c like nvcc does; reference_order: compile the JXF_REFERENCE_ORDER evaluation
+    (the reference's operation order) instead of the production evaluation."""
+    so = SO.replace(".so", f"_{'fma' if fma else 'nofma'}_{'ref' if reference_order else 'prod'}.so")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
         flags = ["-O2", "-mfma", "-ffp-contract=fast"] if fma else ["-O2", "-ffp-contract=off"]
+        if reference_order:
+            flags.append("-DJXF_REFERENCE_ORDER")
         subprocess.run(["g++", "-shared", "-fPIC", "-std=c++17", "-I/usr/local/cuda/include"] + flags +
                        ["-o", so, SRC], check=True)
     lib = C.CDLL(so)
@@ -23,10 +27,10 @@ def load(fma=True):
     return lib
 
 
-def rhs_axis(prims, axis, s, fma=True):
+def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     """Same contract as oracle.port.rhs_axis, computed with the device functions on the host."""
     from oracle import port
-    lib = load(fma)
+    lib = load(fma, reference_order)
     w = np.stack(port._window(prims, axis, s), axis=-1)          # (5, faces..., 6)
     w = np.moveaxis(w, 0, -2)                                    # (faces..., 5, 6)
     shp = w.shape[:-2]

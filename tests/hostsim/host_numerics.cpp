@@ -5,7 +5,7 @@
 #define __host__
 #define __forceinline__ inline
 #include <cmath>
-using std::fabs; using std::fmin; using std::fmax; using std::sqrt;
+using std::fabs; using std::fmin; using std::fmax; using std::sqrt; using std::fma;
 #include "../../jaxfluids_b200/csrc/numerics.cuh"
 
 using namespace jxf;
