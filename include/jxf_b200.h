@@ -93,7 +93,9 @@ int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accu
  *   dt_dev     : device pointer to the step's dt                         [in]
  *   red_dev    : device pointer to 3 doubles {max sum(|u_i|+c), min rho, min p};
  *                updated (max/min-combined) when `reduce` != 0; caller resets via jxf_reduce_reset.
- *   fill_halo  : 0 = leave halos to the caller (multi-GPU exchange), 1 = local BC fill. */
+ *   fill_halo  : 1 = the outer-BC face halos (PERIODIC/SYMMETRY/ZEROGRADIENT faces) of prims_out and
+ *                cons_out are written by the stage itself (fused into the last sweep's epilogue);
+ *                0 = halos are left untouched.  Faces marked JXF_BC_NEIGHBOR are never touched. */
 int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out,
               const double* cons_in, const double* cons_n, double* cons_out,
               double* rhs_scratch, const double* dt_dev, double* red_dev,
@@ -156,6 +158,10 @@ int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* laun
  * 6-cell windows.  windows: (n, 5, 6) doubles, flux: (n, 5) doubles, both on the device. */
 int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n,
                         double gamma, double* flux, void* stream);
+
+/* Test hook: accuracy of the reciprocal / rsqrt building blocks.  x: n positive doubles;
+ * out: (n, 4) = {MUFU rcp seed, MUFU rsqrt seed, rcp_fast(x), rsqrt_fast(x)}. */
+int jxf_debug_math(const double* x, int64_t n, double* out, void* stream);
 
 /* Device FP64 FMA throughput probe for the roofline denominator (bench only):
  * runs `iters` dependent-chain DFMAs x 8 chains per thread on a full grid; returns the

@@ -56,6 +56,9 @@ struct SweepArgs {
   int active_mask;         // bit i = axis i active
   int chunk_len;           // strided: cells per chunk along A
   int span;                // contig: faces per range
+  int fuse_halo;           // EPI: also write the outer-BC halo images of boundary-adjacent cells
+  int nh;
+  int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
 };
 
 // ---------------------------------------------------------------------------
@@ -65,6 +68,7 @@ struct SweepArgs {
 // All offsets are relative to the first INTERIOR cell (h0 is folded into the base pointers).
 // ---------------------------------------------------------------------------
 struct SweepGeom {
+  int axA, ax1, ax2;         // physical axis of each role
   int nA, n1, n2;
   long long sA, s1, s2;      // strides in the halo'd buffers
   long long rA, r1, r2;      // strides in the interior-only rhs buffer
@@ -74,6 +78,17 @@ struct SweepGeom {
 #ifndef JXF_MIN_BLOCKS
 #define JXF_MIN_BLOCKS 3
 #endif
+#ifndef JXF_PREFETCH
+#define JXF_PREFETCH 1
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const double* p) {
+#if JXF_PREFETCH == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 
 // operands of the cell update that come from memory; loaded EARLY (before the flux arithmetic of
 // the iteration) so their latency hides behind ~700 FP64 instructions
@@ -106,9 +121,54 @@ __device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs
   }
 }
 
+// Outer-BC halo images of one freshly updated interior cell (halos/outer/material.py:868-894,
+// boundary_condition.py:563-595, :698-731), fused into the stage epilogue: every face-halo cell of
+// PERIODIC / SYMMETRY / ZEROGRADIENT faces is the image of exactly one interior cell within nh of
+// that face, so the thread that produced the cell also writes its images (prims, and cons
+// recomputed from the image prims, :248-250).  i = interior index along the role axis.
+__device__ __forceinline__ void halo_image(const SweepArgs& a, long long vst, long long dst, const double (&p)[5],
+                                           int flip_var) {
+  double q[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) q[v] = (v == flip_var) ? p[v] * -1.0 : p[v];
+  double c[5];
+  cons_from_prims(q, a.gamma, c);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    a.prims_out[dst + v * vst] = q[v];
+    a.cons_out[dst + v * vst] = c[v];
+  }
+}
+
+__device__ __forceinline__ void halo_images_axis(const SweepArgs& a, long long vst, long long hidx, const double (&p)[5],
+                                                 int ax, int n, int i, long long stride) {
+  if (n <= 1) return;
+  const int nh = a.nh;
+  const int bhi = a.bc[2 * ax], blo = a.bc[2 * ax + 1];
+  // low side (west / south / bottom)
+  if (blo == JXF_BC_SYMMETRY) {
+    if (i < nh) halo_image(a, vst, hidx + (long long)(-1 - 2 * i) * stride, p, 1 + ax);
+  } else if (blo == JXF_BC_PERIODIC) {
+    if (i >= n - nh) halo_image(a, vst, hidx - (long long)n * stride, p, -1);
+  } else if (blo == JXF_BC_ZEROGRADIENT) {
+    if (i == 0)
+      for (int l = 1; l <= nh; ++l) halo_image(a, vst, hidx - (long long)l * stride, p, -1);
+  }
+  // high side (east / north / top)
+  if (bhi == JXF_BC_SYMMETRY) {
+    if (i >= n - nh) halo_image(a, vst, hidx + (long long)(2 * (n - i) - 1) * stride, p, 1 + ax);
+  } else if (bhi == JXF_BC_PERIODIC) {
+    if (i < nh) halo_image(a, vst, hidx + (long long)n * stride, p, -1);
+  } else if (bhi == JXF_BC_ZEROGRADIENT) {
+    if (i == n - 1)
+      for (int l = 1; l <= nh; ++l) halo_image(a, vst, hidx + (long long)l * stride, p, -1);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
-                                              const CellIn<EPI>& in, const double (&r)[5], double step, Red& red) {
+                                              const CellIn<EPI>& in, const double (&r)[5], double step, Red& red,
+                                              int iA, int i1, int i2) {
   if (EPI == 0) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = (a.accumulate ? in.rhs[v] : 0.0) + r[v];
@@ -129,6 +189,16 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
       a.prims_out[hidx + v * g.vst] = p[v];
     }
     if (a.reduce) red.add_cell(p, a.gamma, a.active_mask);
+    if (a.fuse_halo) {
+      // boundary-adjacent cells only (a thin shell); warp-divergent by construction
+      const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (i1 < a.nh) | (i1 >= g.n1 - a.nh) | (i2 < a.nh) |
+                        (i2 >= g.n2 - a.nh);
+      if (near) {
+        halo_images_axis(a, g.vst, hidx, p, g.axA, g.nA, iA, g.sA);
+        halo_images_axis(a, g.vst, hidx, p, g.ax1, g.n1, i1, g.s1);
+        halo_images_axis(a, g.vst, hidx, p, g.ax2, g.n2, i2, g.s2);
+      }
+    }
   }
 }
 
@@ -178,7 +248,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
         double r[5];
 #pragma unroll
         for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fp[v] - F[v]);
-        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red);
+        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red, f - 1, i1, i2);
       }
 #pragma unroll
       for (int v = 0; v < 5; ++v) {
@@ -223,14 +293,39 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepG
       const bool fin = act && f > 0 && gf > gbeg;
       double F[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       long long hidx = 0, ridx = 0;
+      int i1 = 0, i2 = 0;
       CellIn<EPI> in;
       if (act) {
-        const int i1 = (int)(row / g.n2);
-        const int i2 = (int)(row - (long long)i1 * g.n2);
+        i1 = (int)(row / g.n2);
+        i2 = (int)(row - (long long)i1 * g.n2);
         const long long col_h = i1 * g.s1 + i2 * g.s2;
         hidx = col_h + (long long)(f - 1) * g.sA;
         ridx = i1 * g.r1 + i2 * g.r2 + (long long)(f - 1) * g.rA;
         const double* base = a.prims + col_h + (long long)(f - 3) * g.sA;
+#if JXF_PREFETCH
+        if (it + 1 < iters) {
+          // pull the next iteration's lines (32 faces further along the flattened row sequence;
+          // rows are contiguous in memory up to the halo gap) towards the SM while this one computes
+          const long long nxt = 32 * g.sA;
+#pragma unroll
+          for (int v = 0; v < 5; ++v) prefetch_l2(base + v * g.vst + nxt + 3 * g.sA);
+          if (EPI) {
+#pragma unroll
+            for (int v = 0; v < 5; ++v) prefetch_l2(a.cons_in + hidx + v * g.vst + nxt);
+            if (a.has_prev) {
+#pragma unroll
+              for (int v = 0; v < 5; ++v) prefetch_l2(a.rhs + ridx + v * g.rvst + 32 * g.rA);
+            }
+            if (a.blend) {
+#pragma unroll
+              for (int v = 0; v < 5; ++v) prefetch_l2(a.cons_n + hidx + v * g.vst + nxt);
+            }
+          } else if (a.accumulate) {
+#pragma unroll
+            for (int v = 0; v < 5; ++v) prefetch_l2(a.rhs + ridx + v * g.rvst + 32 * g.rA);
+          }
+        }
+#endif
         double w[5][6];
 #pragma unroll
         for (int v = 0; v < 5; ++v)
@@ -251,7 +346,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepG
         double r[5];
 #pragma unroll
         for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fl[v] - F[v]);
-        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red);
+        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red, f - 1, i1, i2);
       }
       gf += 32;
       f += 32;
@@ -447,6 +542,22 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters)
   }
   out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
+
+#ifndef JXF_REFERENCE_ORDER
+// debug / test hook: accuracy of the MUFU seeds and of rcp_fast / rsqrt_fast: out = (n, 4)
+__global__ void __launch_bounds__(128) math_debug_kernel(const double* __restrict__ x, long long n, double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = x[i];
+  double r, q;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(a));
+  out[4 * i + 0] = r;
+  out[4 * i + 1] = q;
+  out[4 * i + 2] = rcp_fast(a);
+  out[4 * i + 3] = rsqrt_fast(a);
+}
+#endif
 
 // debug / test hook: the per-face device function on caller-supplied windows (n, 5, 6) -> (n, 5)
 template <int A, int RECON, int RIEMANN>
@@ -681,6 +792,7 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   if (a.cons_out) a.cons_out += h0;
   if (a.prims_out) a.prims_out += h0;
   SweepGeom sg;
+  sg.axA = A;
   sg.nA = g.n[A];
   sg.sA = g.st[A];
   sg.rA = g.rst[A];
@@ -692,8 +804,8 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     // lanes along the contiguous axis C; the other transverse axis O is the slow one
     const int C = s->lane_axis;
     const int O = 3 - A - C;
-    sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
-    sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
+    sg.ax1 = O; sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
+    sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
     const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
     // chunks along A: enough CTAs for ~4 waves, but chunks of >= 16 cells (<= 6% redundant faces)
@@ -705,8 +817,8 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     ProfScope prof(s, A + 3 * EPI, st);
     sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
   } else {
-    sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
-    sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
+    sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
     const long long rows = (long long)sg.n1 * sg.n2;
     const int nf = g.n[A] + 1;
     const long long total = rows * nf;
@@ -832,11 +944,13 @@ extern "C" int jxf_stage(jxf_handle h, int stage, const double* prims_in, double
       a.dt_mult = h->dt_mult[stage];
       a.has_prev = k > 0;
       a.reduce = reduce ? 1 : 0;
+      a.fuse_halo = fill_halo ? 1 : 0;      // outer-BC halo images written by the epilogue itself
+      a.nh = h->cfg.nh;
+      for (int f = 0; f < 6; ++f) a.bc[f] = (h->g.n[f >> 1] > 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
       rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
     }
     if (rc) return rc;
   }
-  if (fill_halo) return jxf_halo_fill(h, prims_out, cons_out, stream);
   return JXF_OK;
 }
 
@@ -948,6 +1062,16 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   JXF_DBG_CASE(2, 0, 0) JXF_DBG_CASE(2, 0, 1) JXF_DBG_CASE(2, 1, 0) JXF_DBG_CASE(2, 1, 1)
 #undef JXF_DBG_CASE
   return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
+}
+
+extern "C" int jxf_debug_math(const double* x, int64_t n, double* out, void* stream) {
+  if (!x || !out || n <= 0) return fail(JXF_ERR_BAD_ARG, "jxf_debug_math: bad argument");
+#ifndef JXF_REFERENCE_ORDER
+  math_debug_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, (long long)n, out);
+  return check_launch("math_debug");
+#else
+  return fail(JXF_ERR_UNSUPPORTED, "jxf_debug_math: built with JXF_REFERENCE_ORDER");
+#endif
 }
 
 extern "C" int jxf_fp64_probe(double* scratch, int iters, int64_t* n_fma, void* stream) {

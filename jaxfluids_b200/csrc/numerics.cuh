@@ -266,13 +266,14 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
   constexpr double k = 3.0 / 13.0;
   constexpr double eps = kStencilEps * (12.0 / 13.0);
   const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;      // second differences
-  const double s1 = e1 * e1, s2 = e2 * e2, s3 = e3 * e3, s4 = e4 * e4;
+  // eps is folded into the squared second differences: beta~_k + eps~ = k t^2 + (e^2 + eps~)
+  const double s1 = fma(e1, e1, eps), s2 = fma(e2, e2, eps), s3 = fma(e3, e3, eps), s4 = fma(e4, e4, eps);
   // left stencils:  (a-4b+3c) = 3 d1 - d0 ; (b-d) = -(d1+d2) ; (3c-4d+e) = d3 - 3 d2
   const double tl0 = fma(3.0, d1, -d0), tl1 = d1 + d2, tl2 = fma(-3.0, d2, d3);
   // right stencils (mirrored): d4 - 3 d3 ; d2 + d3 ; 3 d2 - d1
   const double tr0 = fma(-3.0, d3, d4), tr1 = d2 + d3, tr2 = fma(3.0, d2, -d1);
-  const double bl0 = fma(k, tl0 * tl0, s1) + eps, bl1 = fma(k, tl1 * tl1, s2) + eps, bl2 = fma(k, tl2 * tl2, s3) + eps;
-  const double br0 = fma(k, tr0 * tr0, s4) + eps, br1 = fma(k, tr1 * tr1, s3) + eps, br2 = fma(k, tr2 * tr2, s2) + eps;
+  const double bl0 = fma(k, tl0 * tl0, s1), bl1 = fma(k, tl1 * tl1, s2), bl2 = fma(k, tl2 * tl2, s3);
+  const double br0 = fma(k, tr0 * tr0, s4), br1 = fma(k, tr1 * tr1, s3), br2 = fma(k, tr2 * tr2, s2);
   {
     const double tau = fabs(bl0 - bl2);           // eps cancels in the difference
     // n_k = d_k (b_k + tau) prod_{j != k} b_j with the common factor 1/10 dropped: d = (1, 6, 3)
@@ -362,12 +363,13 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
     const double rho_ave = fma(0.5, dr[2], w[0][2]);
     const double p_ave = fma(0.5, dp[2], w[4][2]);
     const double gp = gamma * p_ave;                  // = cc_ave * rho_ave
-    const double cc = gp * rcp_fast(rho_ave);
-    const double ic = rsqrt_fast(cc);                 // 1 / c_ave
-    const double c_ave = cc * ic;
+    // z = 1/sqrt(gp rho): c = gp z, 1/c = rho z, 1/cc = (rho z)^2, 0.5/(cc rho) = 0.5 rho z^2
+    const double z = rsqrt_fast(gp * rho_ave);
+    const double ic = rho_ave * z;                    // 1 / c_ave
+    const double c_ave = gp * z;
     const double k_u = 0.5 * ic;                      // 0.5 / c
     const double k_cc = ic * ic;                      // 1 / cc
-    const double k_p = 0.5 * rcp_fast(gp);            // 0.5 / (cc rho)
+    const double k_p = k_u * z;                       // 0.5 / (cc rho)
     double l0, r0, l1, r1, l4, r4;
     {
       double a[5], b[5], c[5];

@@ -278,3 +278,24 @@ def test_full_size_properties_tgv256():
     assert float((pi[2] + pi[2].flip(1)).abs().max()) <= 1e-12
     assert float((pi[4] - pi[4].flip(2)).abs().max()) <= 1e-11 * float(pi[4].abs().max())
     assert bool(torch.isfinite(pi).all())
+
+
+def test_fast_reciprocal_and_rsqrt_accuracy():
+    """rcp_fast / rsqrt_fast (MUFU seed + Newton) are accurate to a few ulp over 40 decades."""
+    import ctypes as C
+    from jaxfluids_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-200, 200, 200000), rng.uniform(0.5, 2.0, 200000),
+                        10.0 ** rng.uniform(-30, 12, 200000)])
+    xd = dev(x)
+    out = torch.empty((x.size, 4), dtype=torch.float64, device="cuda")
+    _lib.check(lib.jxf_debug_math(C.c_void_p(xd.data_ptr()), x.size, C.c_void_p(out.data_ptr()), None))
+    o = host(out)
+    seed_rcp = np.max(np.abs(o[:, 0] * x - 1.0))
+    seed_rsq = np.max(np.abs(o[:, 1] * o[:, 1] * x - 1.0))
+    err_rcp = np.max(np.abs(o[:, 2] * x - 1.0))
+    err_rsq = np.max(np.abs(o[:, 3] * np.sqrt(x) - 1.0))
+    print(f"seed rcp {seed_rcp:.3e} seed rsqrt(y^2 x - 1) {seed_rsq:.3e} rcp_fast {err_rcp:.3e} rsqrt_fast {err_rsq:.3e}")
+    assert seed_rcp < 2.0 ** -18 and seed_rsq < 2.0 ** -17
+    assert err_rcp <= 4.5e-16 and err_rsq <= 4.5e-16
