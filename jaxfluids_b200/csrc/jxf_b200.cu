@@ -12,10 +12,12 @@
 // stage combination (RK3.py:49-60, time_integrator.py:57), primitive recovery
 // (equation_manager.py:164-171) and the CFL / min-rho / min-p reductions
 // (time_step_size.py:103-109, positivity_handler.py:246-247).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -79,7 +81,10 @@ struct SweepGeom {
 #define JXF_MIN_BLOCKS 3
 #endif
 #ifndef JXF_PREFETCH
-#define JXF_PREFETCH 1
+#define JXF_PREFETCH 0
+#endif
+#ifndef JXF_ROWS_KERNEL
+#define JXF_ROWS_KERNEL 1
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const double* p) {
@@ -362,6 +367,204 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepG
 }
 
 // ---------------------------------------------------------------------------
+// contiguous sweep, production form ("rows"): a warp owns groups of 32 rows.  Per row it walks
+// faces 1..nA in full 32-lane iterations (cell f-1 is finalised by the lane that computes face f;
+// lane 0 takes the previous iteration's last flux as carry), so every lane always has work; the
+// 32 row-opening faces f=0 of a group are computed first, one per lane.
+// Windows: the 37 cells [32 it - 2, 32 it + 34] of the row that one iteration touches are staged
+// into a per-warp shared-memory buffer ONE ITERATION AHEAD -- by a TMA tensor copy
+// (cp.async.bulk.tensor, box = 40 cells x 5 variables, completion on a per-buffer mbarrier) or,
+// when the buffer pitch is not 16-byte aligned (odd extents), by per-lane cp.async -- so the
+// DRAM latency of the next window hides behind the ~800 FP64 instructions of the current face.
+// ---------------------------------------------------------------------------
+constexpr int kWinSlots = 40;                  // cells per staged window (37 used)
+constexpr int kWinBytes = 5 * kWinSlots * 8;   // 1600 B moved per TMA op
+constexpr int kWinStride = 1664;               // buffer pitch, multiple of 128 B (TMA destination alignment)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 4-D tiled TMA load: coordinates (c0 = contiguous cell index, c1, c2, c3 = variable)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct RowsArgs {
+  int iters_per_row;      // ceil(nA / 32)
+  int group_rows;         // rows per warp work item (<= 32)
+  int shift;              // window slot 0 holds cell 32*it - shift; 2 or 3 so that the TMA start
+                          // coordinate (cA_off + 32*it - shift) is even: UTMALDG traps unless the
+                          // innermost coordinate * element size is a multiple of 16 B (measured on B200)
+  int c1_off, c2_off;     // halo offsets of the two transverse roles in TMA coordinates
+  int cA_off;             // halo offset of the sweep axis
+  int tma_dim1_is_role;   // which role (1 or 2) is TMA dimension 1 (the faster transverse axis): always role 2
+};
+
+template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
+sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
+  __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
+  __shared__ alignas(8) uint64_t bars[4 * 2];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long ngwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nrows = (long long)g.n1 * g.n2;
+  const int G = ra.group_rows;
+  const long long ngroups = (nrows + G - 1) / G;
+  const int ipr = ra.iters_per_row;
+  const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
+  unsigned char* const win0 = win_raw + wid * 2 * kWinStride;      // this warp's two window buffers
+  uint64_t* const bar0 = &bars[wid * 2];
+  uint32_t phase_bits = 0u;                                        // bit b = parity to wait for on buffer b
+  if (USE_TMA) {
+    if (lane == 0) {
+      mbar_init(bar0, 1);
+      mbar_init(bar0 + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  Red red;
+  red.init();
+
+  for (long long group = gwarp; group < ngroups; group += ngwarps) {
+    const long long row0 = group * G;
+    const int nr = (int)min((long long)G, nrows - row0);
+    // ---- the row-opening faces f = 0 of this group, one row per lane (direct loads) -------------
+    double F0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane < nr) {
+      const long long row = row0 + lane;
+      const int i1 = (int)(row / g.n2);
+      const int i2 = (int)(row - (long long)i1 * g.n2);
+      const double* base = a.prims + i1 * g.s1 + i2 * g.s2 - 3 * g.sA;
+      double w[5][6];
+#pragma unroll
+      for (int v = 0; v < 5; ++v)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.sA];
+      face_flux<A, RECON, RIEMANN>(w, a.gamma, F0);
+    }
+    // ---- main sequence: (row r, iteration it), windows staged one step ahead ---------------------
+    const int total = nr * ipr;
+    auto issue = [&](int j, int b) {
+      const int r = j / ipr;
+      const int it = j - r * ipr;
+      const long long row = row0 + r;
+      const int i1 = (int)(row / g.n2);
+      const int i2 = (int)(row - (long long)i1 * g.n2);
+      double* const wb = reinterpret_cast<double*>(win0 + b * kWinStride);
+      if (USE_TMA) {
+        if (lane == 0) {
+          mbar_expect_tx(bar0 + b, kWinBytes);
+          // TMA dims: (contiguous sweep axis, faster transverse (role 2), slower transverse (role 1), variable);
+          // cells past the end of the row are zero-filled by the TMA unit, no predication needed
+          tma_load_4d(wb, &tmap, bar0 + b, ra.cA_off + 32 * it - ra.shift, ra.c2_off + i2, ra.c1_off + i1, 0);
+        }
+      } else {
+        const double* src = a.prims + i1 * g.s1 + i2 * g.s2 + (long long)(32 * it - ra.shift) * g.sA;
+        const int cmax = g.nA + 2 - (32 * it - ra.shift);  // slots holding cells <= nA+2 are valid
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          if (lane <= cmax) cp_async8(wb + v * kWinSlots + lane, src + v * g.vst + lane);
+          if (lane < 6 && 32 + lane <= cmax) cp_async8(wb + v * kWinSlots + 32 + lane, src + v * g.vst + 32 + lane);
+        }
+        cp_async_commit();
+      }
+    };
+    issue(0, 0);
+    double carry[5];
+    int r = 0, it = 0;
+    for (int j = 0; j < total; ++j) {
+      const int b = j & 1;
+      if (j + 1 < total) issue(j + 1, b ^ 1);
+      const long long row = row0 + r;
+      const int i1 = (int)(row / g.n2);
+      const int i2 = (int)(row - (long long)i1 * g.n2);
+      const int f = 1 + 32 * it + lane;
+      const bool act = f <= g.nA;
+      const long long col_h = i1 * g.s1 + i2 * g.s2;
+      const long long hidx = col_h + (long long)(f - 1) * g.sA;
+      const long long ridx = i1 * g.r1 + i2 * g.r2 + (long long)(f - 1) * g.rA;
+      CellIn<EPI> in;
+      if (act) load_cell_in<EPI>(g, a, hidx, ridx, in);
+      if (it == 0) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) carry[v] = __shfl_sync(0xffffffffu, F0[v], r);
+      }
+      // wait for this iteration's window
+      const double* const wb = reinterpret_cast<const double*>(win0 + b * kWinStride);
+      if (USE_TMA) {
+        mbar_wait(bar0 + b, (phase_bits >> b) & 1u);
+        phase_bits ^= (1u << b);
+      } else {
+        if (j + 1 < total) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+      }
+      double F[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if (act) {
+        double w[5][6];
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) w[v][k] = wb[v * kWinSlots + (ra.shift - 2) + lane + k];
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+      }
+      double Fl[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const double up = __shfl_up_sync(0xffffffffu, F[v], 1);
+        const double last = __shfl_sync(0xffffffffu, F[v], 31);
+        Fl[v] = (lane == 0) ? carry[v] : up;
+        carry[v] = last;
+      }
+      if (act) {
+        double rr[5];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) rr[v] = a.inv_dx * (Fl[v] - F[v]);
+        finalize_cell<EPI>(g, a, hidx, ridx, in, rr, step, red, f - 1, i1, i2);
+      }
+      __syncwarp();          // all lanes are done with win[b] before it is refilled (issue(j+2))
+      if (++it == ipr) {
+        it = 0;
+        ++r;
+      }
+    }
+  }
+  if (EPI) {
+    if (a.reduce) red_commit(red, a.red);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // halo fill: PERIODIC / SYMMETRY / ZEROGRADIENT face halos, cons recomputed
 // (halos/outer/material.py:868-894, boundary_condition.py:563-595, :698-731)
 // ---------------------------------------------------------------------------
@@ -609,6 +812,12 @@ struct jxf_solver {
   int stages;
   double dt_mult[3];
   double blend[3][2];
+  // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
+  bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
+  bool tma_ok;
+  int n_maps;
+  const void* map_ptr[8];
+  CUtensorMap map[8];
   // launch accounting / optional per-kernel event timing (jxf_profile_*)
   long long launches[JXF_PROFILE_KINDS];
   int prof_on;
@@ -701,6 +910,9 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     s->blend[1][0] = 0.25; s->blend[1][1] = 0.75;
     s->blend[2][0] = 2.0 / 3.0; s->blend[2][1] = 1.0 / 3.0;
   }
+  s->tma_ok = !(getenv("JXF_NO_TMA") && atoi(getenv("JXF_NO_TMA")) != 0);
+  s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
+  s->n_maps = 0;
   s->num_sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -778,6 +990,55 @@ extern "C" int64_t jxf_rhs_elems(jxf_handle h) { return h ? 5 * h->g.rvst : -1; 
 extern "C" int jxf_num_stages(jxf_handle h) { return h ? h->stages : -1; }
 
 // ---------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched at run time: the library does not link libcuda)
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 4-D view (contiguous axis, faster transverse, slower transverse, variable) of a halo'd field buffer,
+// box = kWinSlots cells x 1 x 1 x 5 variables.  Returns nullptr when TMA cannot describe the buffer
+// (pitch not a multiple of 16 B, or no driver support) -- the cp.async loader is used instead.
+static const CUtensorMap* get_rows_map(jxf_solver* s, const double* base) {
+  if (!s->tma_ok) return nullptr;
+  for (int i = 0; i < s->n_maps; ++i)
+    if (s->map_ptr[i] == base) return &s->map[i];
+  PFN_encodeTiled enc = get_encode_fn();
+  const Geom& g = s->g;
+  if (!enc || (g.ext[2] * 8) % 16 != 0 || ((uintptr_t)base % 16) != 0) { s->tma_ok = false; return nullptr; }
+  // physical layout is (5, ext0, ext1, ext2); an inactive trailing axis has extent 1, which keeps the
+  // byte strides below valid; the contiguous ACTIVE axis may therefore be ext1 or ext0 with ext2 == 1.
+  if (s->lane_axis != 2) { s->tma_ok = false; return nullptr; }    // 1-D / 2-D grids: cp.async loader
+  cuuint64_t dims[4] = {(cuuint64_t)g.ext[2], (cuuint64_t)g.ext[1], (cuuint64_t)g.ext[0], 5};
+  cuuint64_t strides[3] = {(cuuint64_t)g.ext[2] * 8, (cuuint64_t)g.ext[1] * g.ext[2] * 8, (cuuint64_t)g.vst * 8};
+  cuuint32_t box[4] = {(cuuint32_t)kWinSlots, 1, 1, 5};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const int slot = s->n_maps < 8 ? s->n_maps : 7;
+  CUresult rc = enc(&s->map[slot], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { s->tma_ok = false; return nullptr; }
+  s->map_ptr[slot] = base;
+  if (s->n_maps < 8) s->n_maps++;
+  return &s->map[slot];
+}
+
+// ---------------------------------------------------------------------------
 // sweep dispatch
 // ---------------------------------------------------------------------------
 template <int A, int RECON, int RIEMANN, int EPI>
@@ -822,6 +1083,34 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     const long long rows = (long long)sg.n1 * sg.n2;
     const int nf = g.n[A] + 1;
     const long long total = rows * nf;
+#if JXF_ROWS_KERNEL
+    // production form whenever groups of >= 4 rows give every resident warp several work items
+    const long long warps_resident = 4LL * resident;
+    if ((s->force_rows || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
+      RowsArgs ra;
+      ra.iters_per_row = (g.n[A] + 31) / 32;
+      int G = 32;
+      while (G > 4 && rows / G < warps_resident * 8) G >>= 1;
+      ra.group_rows = G;
+      ra.shift = ((g.off[A] - 2) & 1) ? 3 : 2;
+      ra.cA_off = g.off[A];
+      ra.c1_off = g.off[T1];
+      ra.c2_off = g.off[T2];
+      ra.tma_dim1_is_role = 2;
+      const long long groups = (rows + G - 1) / G;
+      const long long blocks = std::min<long long>((groups + 3) / 4, (long long)resident);
+      const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0);
+      ProfScope prof(s, A + 3 * EPI, st);
+      if (map) {
+        sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map);
+      } else {
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy);
+      }
+      return check_launch("sweep_rows");
+    }
+#endif
     const long long target_warps = 4LL * resident * 4;   // ~4 waves of warps
     long long span;
     if (rows >= target_warps) {
