@@ -71,6 +71,7 @@ struct SweepArgs {
 // ---------------------------------------------------------------------------
 struct SweepGeom {
   int axA, ax1, ax2;         // physical axis of each role
+  int bcA_hi, bcA_lo, bc1_hi, bc1_lo, bc2_hi, bc2_lo;   // JXF_BC_* of the faces of each role (halo fusion)
   int nA, n1, n2;
   long long sA, s1, s2;      // strides in the halo'd buffers
   long long rA, r1, r2;      // strides in the interior-only rhs buffer
@@ -131,42 +132,52 @@ __device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs
 // PERIODIC / SYMMETRY / ZEROGRADIENT faces is the image of exactly one interior cell within nh of
 // that face, so the thread that produced the cell also writes its images (prims, and cons
 // recomputed from the image prims, :248-250).  i = interior index along the role axis.
-__device__ __forceinline__ void halo_image(const SweepArgs& a, long long vst, long long dst, const double (&p)[5],
-                                           int flip_var) {
-  double q[5];
+struct HaloOut {
+  double* prims;
+  double* cons;
+  long long vst;
+  double gamma;
+  int nh;
+};
+
+__device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, double p0, double p1, double p2, double p3,
+                                           double p4, int flip_var) {
+  double q[5] = {p0, p1, p2, p3, p4};
 #pragma unroll
-  for (int v = 0; v < 5; ++v) q[v] = (v == flip_var) ? p[v] * -1.0 : p[v];
+  for (int v = 1; v < 4; ++v) q[v] = (v == flip_var) ? q[v] * -1.0 : q[v];
   double c[5];
-  cons_from_prims(q, a.gamma, c);
+  cons_from_prims(q, h.gamma, c);
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
-    a.prims_out[dst + v * vst] = q[v];
-    a.cons_out[dst + v * vst] = c[v];
+    h.prims[dst + v * h.vst] = q[v];
+    h.cons[dst + v * h.vst] = c[v];
   }
 }
 
-__device__ __forceinline__ void halo_images_axis(const SweepArgs& a, long long vst, long long hidx, const double (&p)[5],
-                                                 int ax, int n, int i, long long stride) {
+// out of line on purpose: executed only by the thin shell of boundary-adjacent cells, and keeping it
+// out of the sweep loop keeps the hot loop inside the instruction cache
+__device__ __forceinline__ void halo_images_axis(double* prims_out, double* cons_out, long long vst, double gamma, int nh,
+                                              int bhi, int blo, long long hidx, double p0, double p1, double p2,
+                                              double p3, double p4, int ax, int n, int i, long long stride) {
   if (n <= 1) return;
-  const int nh = a.nh;
-  const int bhi = a.bc[2 * ax], blo = a.bc[2 * ax + 1];
+  HaloOut h{prims_out, cons_out, vst, gamma, nh};
   // low side (west / south / bottom)
   if (blo == JXF_BC_SYMMETRY) {
-    if (i < nh) halo_image(a, vst, hidx + (long long)(-1 - 2 * i) * stride, p, 1 + ax);
+    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p0, p1, p2, p3, p4, 1 + ax);
   } else if (blo == JXF_BC_PERIODIC) {
-    if (i >= n - nh) halo_image(a, vst, hidx - (long long)n * stride, p, -1);
+    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p0, p1, p2, p3, p4, -1);
   } else if (blo == JXF_BC_ZEROGRADIENT) {
     if (i == 0)
-      for (int l = 1; l <= nh; ++l) halo_image(a, vst, hidx - (long long)l * stride, p, -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p0, p1, p2, p3, p4, -1);
   }
   // high side (east / north / top)
   if (bhi == JXF_BC_SYMMETRY) {
-    if (i >= n - nh) halo_image(a, vst, hidx + (long long)(2 * (n - i) - 1) * stride, p, 1 + ax);
+    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p0, p1, p2, p3, p4, 1 + ax);
   } else if (bhi == JXF_BC_PERIODIC) {
-    if (i < nh) halo_image(a, vst, hidx + (long long)n * stride, p, -1);
+    if (i < nh) halo_image(h, hidx + (long long)n * stride, p0, p1, p2, p3, p4, -1);
   } else if (bhi == JXF_BC_ZEROGRADIENT) {
     if (i == n - 1)
-      for (int l = 1; l <= nh; ++l) halo_image(a, vst, hidx + (long long)l * stride, p, -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p0, p1, p2, p3, p4, -1);
   }
 }
 
@@ -199,9 +210,12 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
       const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (i1 < a.nh) | (i1 >= g.n1 - a.nh) | (i2 < a.nh) |
                         (i2 >= g.n2 - a.nh);
       if (near) {
-        halo_images_axis(a, g.vst, hidx, p, g.axA, g.nA, iA, g.sA);
-        halo_images_axis(a, g.vst, hidx, p, g.ax1, g.n1, i1, g.s1);
-        halo_images_axis(a, g.vst, hidx, p, g.ax2, g.n2, i2, g.s2);
+        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bcA_hi, g.bcA_lo, hidx,
+                         p[0], p[1], p[2], p[3], p[4], g.axA, g.nA, iA, g.sA);
+        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bc1_hi, g.bc1_lo, hidx,
+                         p[0], p[1], p[2], p[3], p[4], g.ax1, g.n1, i1, g.s1);
+        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bc2_hi, g.bc2_lo, hidx,
+                         p[0], p[1], p[2], p[3], p[4], g.ax2, g.n2, i2, g.s2);
       }
     }
   }
@@ -417,6 +431,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// out-of-line flux from a strided global window (rare paths only)
+template <int A, int RECON, int RIEMANN>
+__device__ __noinline__ void face_flux_from_global(const double* base, long long vst, long long sA, double gamma,
+                                                   double (&F)[5]) {
+  double w[5][6];
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[v][k] = base[v * vst + k * sA];
+  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+}
+
 struct RowsArgs {
   int iters_per_row;      // ceil(nA / 32)
   int group_rows;         // rows per warp work item (<= 32)
@@ -459,39 +485,33 @@ sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid
   for (long long group = gwarp; group < ngroups; group += ngwarps) {
     const long long row0 = group * G;
     const int nr = (int)min((long long)G, nrows - row0);
-    // ---- the row-opening faces f = 0 of this group, one row per lane (direct loads) -------------
+    // ---- the row-opening faces f = 0 of this group, one row per lane (direct strided loads; the flux
+    // code is called out of line here so the hot loop below holds the only inlined copy) -----------
     double F0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (lane < nr) {
       const long long row = row0 + lane;
-      const int i1 = (int)(row / g.n2);
-      const int i2 = (int)(row - (long long)i1 * g.n2);
-      const double* base = a.prims + i1 * g.s1 + i2 * g.s2 - 3 * g.sA;
-      double w[5][6];
-#pragma unroll
-      for (int v = 0; v < 5; ++v)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.sA];
-      face_flux<A, RECON, RIEMANN>(w, a.gamma, F0);
+      const int k1 = (int)(row / g.n2);
+      const int k2 = (int)(row - (long long)k1 * g.n2);
+      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0);
     }
     // ---- main sequence: (row r, iteration it), windows staged one step ahead ---------------------
+    // All index state is carried incrementally in 32-bit registers (no divisions in the loop):
+    // (r, it, i1, i2) for the iteration being computed, (rn, itn, i1n, i2n) for the one being staged.
     const int total = nr * ipr;
-    auto issue = [&](int j, int b) {
-      const int r = j / ipr;
-      const int it = j - r * ipr;
-      const long long row = row0 + r;
-      const int i1 = (int)(row / g.n2);
-      const int i2 = (int)(row - (long long)i1 * g.n2);
+    const int i1_0 = (int)(row0 / g.n2);
+    const int i2_0 = (int)(row0 - (long long)i1_0 * g.n2);
+    auto issue = [&](int b, int itn, int i1n, int i2n) {
       double* const wb = reinterpret_cast<double*>(win0 + b * kWinStride);
       if (USE_TMA) {
         if (lane == 0) {
           mbar_expect_tx(bar0 + b, kWinBytes);
           // TMA dims: (contiguous sweep axis, faster transverse (role 2), slower transverse (role 1), variable);
           // cells past the end of the row are zero-filled by the TMA unit, no predication needed
-          tma_load_4d(wb, &tmap, bar0 + b, ra.cA_off + 32 * it - ra.shift, ra.c2_off + i2, ra.c1_off + i1, 0);
+          tma_load_4d(wb, &tmap, bar0 + b, ra.cA_off + 32 * itn - ra.shift, ra.c2_off + i2n, ra.c1_off + i1n, 0);
         }
       } else {
-        const double* src = a.prims + i1 * g.s1 + i2 * g.s2 + (long long)(32 * it - ra.shift) * g.sA;
-        const int cmax = g.nA + 2 - (32 * it - ra.shift);  // slots holding cells <= nA+2 are valid
+        const double* src = a.prims + i1n * g.s1 + i2n * g.s2 + (long long)(32 * itn - ra.shift) * g.sA;
+        const int cmax = g.nA + 2 - (32 * itn - ra.shift);  // slots holding cells <= nA+2 are valid
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
           if (lane <= cmax) cp_async8(wb + v * kWinSlots + lane, src + v * g.vst + lane);
@@ -500,20 +520,27 @@ sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid
         cp_async_commit();
       }
     };
-    issue(0, 0);
+    issue(0, 0, i1_0, i2_0);
     double carry[5];
-    int r = 0, it = 0;
+    int r = 0, it = 0, i1 = i1_0, i2 = i2_0;
+    int itn = 0, i1n = i1_0, i2n = i2_0;
+    long long col_h = i1 * g.s1 + i2 * g.s2;
+    long long col_r = i1 * g.r1 + i2 * g.r2;
     for (int j = 0; j < total; ++j) {
       const int b = j & 1;
-      if (j + 1 < total) issue(j + 1, b ^ 1);
-      const long long row = row0 + r;
-      const int i1 = (int)(row / g.n2);
-      const int i2 = (int)(row - (long long)i1 * g.n2);
+      // advance the staged-iteration state and stage it
+      if (++itn == ipr) {
+        itn = 0;
+        if (++i2n == g.n2) {
+          i2n = 0;
+          ++i1n;
+        }
+      }
+      if (j + 1 < total) issue(b ^ 1, itn, i1n, i2n);
       const int f = 1 + 32 * it + lane;
       const bool act = f <= g.nA;
-      const long long col_h = i1 * g.s1 + i2 * g.s2;
       const long long hidx = col_h + (long long)(f - 1) * g.sA;
-      const long long ridx = i1 * g.r1 + i2 * g.r2 + (long long)(f - 1) * g.rA;
+      const long long ridx = col_r + (long long)(f - 1) * g.rA;
       CellIn<EPI> in;
       if (act) load_cell_in<EPI>(g, a, hidx, ridx, in);
       if (it == 0) {
@@ -532,10 +559,11 @@ sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid
       double F[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       if (act) {
         double w[5][6];
+        const double* wl = wb + (ra.shift - 2) + lane;
 #pragma unroll
         for (int v = 0; v < 5; ++v)
 #pragma unroll
-          for (int k = 0; k < 6; ++k) w[v][k] = wb[v * kWinSlots + (ra.shift - 2) + lane + k];
+          for (int k = 0; k < 6; ++k) w[v][k] = wl[v * kWinSlots + k];
         face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
       }
       double Fl[5];
@@ -552,10 +580,16 @@ sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid
         for (int v = 0; v < 5; ++v) rr[v] = a.inv_dx * (Fl[v] - F[v]);
         finalize_cell<EPI>(g, a, hidx, ridx, in, rr, step, red, f - 1, i1, i2);
       }
-      __syncwarp();          // all lanes are done with win[b] before it is refilled (issue(j+2))
+      __syncwarp();          // all lanes are done with win[b] before it is refilled two iterations later
       if (++it == ipr) {
         it = 0;
         ++r;
+        if (++i2 == g.n2) {
+          i2 = 0;
+          ++i1;
+        }
+        col_h = i1 * g.s1 + i2 * g.s2;
+        col_r = i1 * g.r1 + i2 * g.r2;
       }
     }
   }
@@ -1041,6 +1075,12 @@ static const CUtensorMap* get_rows_map(jxf_solver* s, const double* base) {
 // ---------------------------------------------------------------------------
 // sweep dispatch
 // ---------------------------------------------------------------------------
+static void set_role_bcs(SweepGeom& sg, const SweepArgs& a) {
+  sg.bcA_hi = a.bc[2 * sg.axA]; sg.bcA_lo = a.bc[2 * sg.axA + 1];
+  sg.bc1_hi = a.bc[2 * sg.ax1]; sg.bc1_lo = a.bc[2 * sg.ax1 + 1];
+  sg.bc2_hi = a.bc[2 * sg.ax2]; sg.bc2_lo = a.bc[2 * sg.ax2 + 1];
+}
+
 template <int A, int RECON, int RIEMANN, int EPI>
 static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   const Geom& g = s->g;
@@ -1075,11 +1115,13 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     a.chunk_len = (g.n[A] + chunks - 1) / chunks;
     chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
     dim3 grid(bx, chunks);
+    set_role_bcs(sg, a);
     ProfScope prof(s, A + 3 * EPI, st);
     sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
   } else {
     sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
     sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    set_role_bcs(sg, a);
     const long long rows = (long long)sg.n1 * sg.n2;
     const int nf = g.n[A] + 1;
     const long long total = rows * nf;

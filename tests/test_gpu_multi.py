@@ -1,0 +1,102 @@
+"""GPU, multi-rank: block decomposition with NCCL halo exchange against the single-block oracle.
+Launched as a subprocess with torchrun so that a plain `pytest -m gpu` covers it; skipped when fewer
+than 2 GPUs are visible."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = H.ROOT
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+WORKER = r'''
+import json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["JXF_ROOT"])
+from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+from oracle import port
+from tests import helpers as H
+
+split = tuple(int(v) for v in os.environ["JXF_SPLIT"].split(","))
+bc = os.environ["JXF_BC"]
+nsteps = int(os.environ["JXF_STEPS"])
+cells = tuple(int(v) for v in os.environ["JXF_CELLS"].split(","))
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+rank = dist.get_rank()
+s = H.make_setup(cells, bc=bc, gamma=1.4, length=1.0)
+prims0 = H.smooth_ic(s, seed=21, amp=0.1)
+case = {
+  "general": {"case_name": "mg", "end_step": nsteps, "save_path": "./results"},
+  "domain": {ax: {"cells": cells[i], "range": [0.0, 1.0]} for i, ax in enumerate("xyz")},
+  "boundary_conditions": {f: {"type": s.bc[f]} for f in port.FACES},
+  "initial_condition": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 1.0},
+  "material_properties": {"equation_of_state": {"model": "IdealGas", "specific_heat_ratio": 1.4, "specific_gas_constant": 1.0}},
+}
+case["domain"]["decomposition"] = {"split_x": split[0], "split_y": split[1], "split_z": split[2]}
+num = {"conservatives": {"halo_cells": 5, "time_integration": {"integrator": "RK3", "CFL": 0.5},
+       "convective_fluxes": {"convective_solver": "GODUNOV", "godunov": {"riemann_solver": "HLLC", "signal_speed": "EINFELDT",
+       "reconstruction_stencil": "WENO5-Z", "reconstruction_variable": "CHAR-PRIMITIVE"}}},
+       "active_physics": {"is_convective_flux": True}, "output": {"logging": {"level": "NONE"}}}
+im = InputManager(case, num)
+init = InitializationManager(im)
+active = [i for i in range(3) if cells[i] > 1]
+user = prims0[[0] + [1 + i for i in active] + [4]]
+buf = init.initialization(user_prime_init=user)
+sim = SimulationManager(im)
+sim.simulate(buf)
+out = sim.final_buffers
+di = im.domain_information
+nh = 5
+it = (slice(None),) + tuple(slice(nh, -nh) if cells[i] > 1 else slice(None) for i in range(3))
+mine = out.simulation_buffers.material_fields.primitives[it].cpu().numpy()
+# oracle on the global grid (single block), rank 0 gathers
+gathered = [None] * dist.get_world_size()
+dist.all_gather_object(gathered, (di.block_slices(rank), mine, out.time_control_variables.physical_timestep_size,
+                                  out.time_control_variables.physical_simulation_time))
+if rank == 0:
+    glob = np.empty((5,) + cells)
+    for sl, arr, _, _ in gathered:
+        glob[(slice(None),) + sl] = arr
+    p, c = port.initialize(user, s, from_user_buffer=True)
+    dt = port.time_step_size(p, s); t = 0.0
+    for _ in range(nsteps):
+        t += dt
+        p, c, dt = port.step(p, c, dt, s)
+    ref = p[(slice(None),) + s.interior]
+    err = H.rel_linf(glob, ref)
+    dts = [g[2] for g in gathered]
+    print("RESULT " + json.dumps({"err": err, "dt_err": max(abs(d - dt) / dt for d in dts), "t_err": abs(gathered[0][3] - t) / t}))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("split,cells,bc", [((2, 1, 1), (32, 20, 36), "PERIODIC"), ((1, 2, 1), (20, 32, 36), "SYMMETRY"),
+                                            ((1, 1, 2), (12, 16, 80), "PERIODIC"), ((2, 1, 1), (64, 24, 1), "ZEROGRADIENT")])
+def test_two_blocks_match_single_block_oracle(split, cells, bc, tmp_path):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = tmp_path / "worker.py"
+    worker.write_text(WORKER)
+    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="4",
+               JXF_CELLS=",".join(map(str, cells)))
+    port_no = 29500 + (os.getpid() % 200)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port_no), str(worker)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, out.stdout[-2000:] + out.stderr[-4000:]
+    res = json.loads(lines[-1][7:])
+    assert res["err"] <= 1e-12 and res["dt_err"] <= 1e-12 and res["t_err"] <= 1e-12, res
