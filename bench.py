@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -120,6 +120,8 @@ class ClockSampler:
             for n, v in zip(names, parts[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        if len(sm) > 2:                    # the first samples may precede the first kernel
+            sm, mx, pw = sm[1:], mx[1:], pw[1:]
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
@@ -244,13 +246,13 @@ def main():
     # ---- device-resident timed region ------------------------------------------------
     tcv = buffers.time_control_variables
     rt.set_time_control(tcv.physical_simulation_time, tcv.physical_timestep_size)
+    sampler = ClockSampler(dev)
+    sampler.start()                       # runs through warm-up + timed region (same workload throughout)
     for _ in range(args.warmup):
         rt.step()
     barrier()
     rt.solver.profile_read(reset=True)
     rt.solver.profile_enable(True)
-    sampler = ClockSampler(dev)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

@@ -272,10 +272,13 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
   const double br0 = fma(k, tr0 * tr0, s4), br1 = fma(k, tr1 * tr1, s3), br2 = fma(k, tr2 * tr2, s2);
   {
     const double tau = fabs(bl0 - bl2);           // eps cancels in the difference
-    // n_k = d_k (b_k + tau) prod_{j != k} b_j with the common factor 1/10 dropped: d = (1, 6, 3)
-    const double n0 = (bl0 + tau) * (bl1 * bl2);
-    const double m1 = (bl1 + tau) * (bl0 * bl2);
-    const double m2 = (bl2 + tau) * (bl0 * bl1);
+    // n_k = d_k (b_k + tau) prod_{j != k} b_j = d_k (P + tau prod_{j != k} b_j), P = b0 b1 b2, with the
+    // common factor 1/10 dropped: d = (1, 6, 3)
+    const double p12 = bl1 * bl2, p02 = bl0 * bl2, p01 = bl0 * bl1;
+    const double P = bl0 * p12;
+    const double n0 = fma(tau, p12, P);
+    const double m1 = fma(tau, p02, P);
+    const double m2 = fma(tau, p01, P);
     const double den = fma(6.0, m1, fma(3.0, m2, n0));
     // p_k - c:  p0-c = 5/6 d1 - 1/3 d0 ; p1-c = 1/3 d2 + 1/6 d1 ; p2-c = 2/3 d2 - 1/6 d3   (x d_k)
     const double q0 = fma(5.0 / 6.0, d1, (-1.0 / 3.0) * d0);
@@ -286,9 +289,11 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
   }
   {
     const double tau = fabs(br0 - br2);
-    const double n0 = (br0 + tau) * (br1 * br2);
-    const double m1 = (br1 + tau) * (br0 * br2);
-    const double m2 = (br2 + tau) * (br0 * br1);
+    const double p12 = br1 * br2, p02 = br0 * br2, p01 = br0 * br1;
+    const double P = br0 * p12;
+    const double n0 = fma(tau, p12, P);
+    const double m1 = fma(tau, p02, P);
+    const double m2 = fma(tau, p01, P);
     const double den = fma(6.0, m1, fma(3.0, m2, n0));
     // mirrored differences d0'=-d4, d1'=-d3, d2'=-d2, d3'=-d1
     const double q0 = fma(-5.0 / 6.0, d3, (1.0 / 3.0) * d4);
@@ -465,9 +470,9 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     double fL[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, fR[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (S_star >= 0.0) hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
     if (S_star <= 0.0) hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
-    const double wgt = (S_star == 0.0) ? 0.5 : 1.0;
+    // select, don't blend: S* > 0 -> F*_L, S* < 0 -> F*_R, S* = 0 -> the mean (sign(0) = 0 in the reference)
 #pragma unroll
-    for (int v = 0; v < 5; ++v) F[v] = wgt * (fL[v] + fR[v]);
+    for (int v = 0; v < 5; ++v) F[v] = (S_star > 0.0) ? fL[v] : ((S_star < 0.0) ? fR[v] : 0.5 * (fL[v] + fR[v]));
   } else {
     const double alpha = fmax(fabs(uL) + aL, fabs(uR) + aR);
     double fl[5], fr[5];
