@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <new>
 
 #include "../../include/jxf_b200.h"
@@ -1109,9 +1110,19 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
     const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
-    // chunks along A: enough CTAs for ~4 waves, but chunks of >= 16 cells (<= 6% redundant faces)
-    int chunks = (int)std::min<long long>((4LL * resident + bx - 1) / bx, std::max(1, g.n[A] / 16));
-    chunks = std::max(1, std::min(chunks, 65535));
+    // chunks along A: every chunk costs one redundant face (+ a 5-plane prologue), while few CTAs per
+    // resident slot leave a partial last wave; pick the chunk count that minimises
+    // (1 + 1.5/chunk_len) * ceil(waves)/waves over chunk lengths >= 16 cells
+    int chunks = 1;
+    double best = 1e30;
+    const int max_chunks = std::max(1, std::min(g.n[A] / 16, 65535));
+    for (int c = 1; c <= max_chunks; ++c) {
+      const int len = (g.n[A] + c - 1) / c;
+      const int cc = (g.n[A] + len - 1) / len;
+      const double waves = (double)bx * cc / resident;
+      const double cost = (1.0 + 1.5 / len) * (waves <= 1.0 ? 1.0 / waves : std::ceil(waves) / waves);
+      if (cost < best - 1e-12) { best = cost; chunks = cc; }
+    }
     a.chunk_len = (g.n[A] + chunks - 1) / chunks;
     chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
     dim3 grid(bx, chunks);
@@ -1131,8 +1142,10 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     if ((s->force_rows || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
       RowsArgs ra;
       ra.iters_per_row = (g.n[A] + 31) / 32;
-      int G = 32;
-      while (G > 4 && rows / G < warps_resident * 8) G >>= 1;
+      // one group per warp, 4 warps per CTA, many more CTAs than resident slots: the hardware block
+      // scheduler balances the tail (a static groups-per-warp split left ~8 % of the warps idle at the end)
+      int G = 8;
+      while (G > 4 && rows / G < warps_resident * 16) G >>= 1;
       ra.group_rows = G;
       ra.shift = ((g.off[A] - 2) & 1) ? 3 : 2;
       ra.cA_off = g.off[A];
@@ -1140,7 +1153,7 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       ra.c2_off = g.off[T2];
       ra.tma_dim1_is_role = 2;
       const long long groups = (rows + G - 1) / G;
-      const long long blocks = std::min<long long>((groups + 3) / 4, (long long)resident);
+      const long long blocks = std::min<long long>((groups + 3) / 4, 1LL << 30);
       const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0);
       ProfScope prof(s, A + 3 * EPI, st);
       if (map) {
