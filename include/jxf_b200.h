@@ -101,6 +101,21 @@ int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out
               double* rhs_scratch, const double* dt_dev, double* red_dev,
               int reduce, int fill_halo, void* stream);
 
+/* The same stage, starting at the `first_axis_index`-th ACTIVE axis (0 = whole stage).  With
+ * jxf_sweep_range this lets the host run the first sweep in pieces -- interior cells while the
+ * inter-block halo exchange of the previous stage is still in flight, the cells next to shared
+ * faces afterwards (ref: the halo update at simulation_manager.py:963 precedes the next
+ * compute_rhs at :796; only the sweep ALONG an axis reads that axis' halos). */
+int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, const double* prims_in, double* prims_out,
+                   const double* cons_in, const double* cons_n, double* cons_out,
+                   double* rhs_scratch, const double* dt_dev, double* red_dev,
+                   int reduce, int fill_halo, void* stream);
+
+/* jxf_sweep restricted to the cells [lo, hi) along `axis` (strided axes only; the contiguous
+ * axis accepts only the full range). */
+int jxf_sweep_range(jxf_handle h, int axis, int lo, int hi, const double* prims, double* rhs,
+                    int accumulate, void* stream);
+
 /* One whole time step on a single block (ref: SimulationManager._do_integration_step,
  * simulation_manager.py:536-668, and do_runge_kutta_stages :670-1077): all RK stages with
  * local halo fill, the reductions on the last stage, then jxf_finish_step.

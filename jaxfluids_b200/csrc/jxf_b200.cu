@@ -59,6 +59,7 @@ struct SweepArgs {
   int active_mask;         // bit i = axis i active
   int chunk_len;           // strided: cells per chunk along A
   int span;                // contig: faces per range
+  int range_lo, range_hi;  // strided: cells [range_lo, range_hi) along A are swept (default: all)
   int fuse_halo;           // EPI: also write the outer-BC halo images of boundary-adjacent cells
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
@@ -235,8 +236,8 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
   if (p < plane) {
     const int i1 = (int)(p / g.n2);
     const int i2 = (int)(p - (long long)i1 * g.n2);
-    const int f0 = blockIdx.y * a.chunk_len;
-    const int f1 = min(f0 + a.chunk_len, g.nA);
+    const int f0 = a.range_lo + blockIdx.y * a.chunk_len;
+    const int f1 = min(f0 + a.chunk_len, a.range_hi);
     const long long sA = g.sA;
     const long long col_h = i1 * g.s1 + i2 * g.s2;
     const long long col_r = i1 * g.r1 + i2 * g.r2;
@@ -1113,18 +1114,20 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     // chunks along A: every chunk costs one redundant face (+ a 5-plane prologue), while few CTAs per
     // resident slot leave a partial last wave; pick the chunk count that minimises
     // (1 + 1.5/chunk_len) * ceil(waves)/waves over chunk lengths >= 16 cells
+    if (a.range_hi <= a.range_lo) { a.range_lo = 0; a.range_hi = g.n[A]; }
+    const int nr = a.range_hi - a.range_lo;
     int chunks = 1;
     double best = 1e30;
-    const int max_chunks = std::max(1, std::min(g.n[A] / 16, 65535));
+    const int max_chunks = std::max(1, std::min(nr / 16, 65535));
     for (int c = 1; c <= max_chunks; ++c) {
-      const int len = (g.n[A] + c - 1) / c;
-      const int cc = (g.n[A] + len - 1) / len;
+      const int len = (nr + c - 1) / c;
+      const int cc = (nr + len - 1) / len;
       const double waves = (double)bx * cc / resident;
       const double cost = (1.0 + 1.5 / len) * (waves <= 1.0 ? 1.0 / waves : std::ceil(waves) / waves);
       if (cost < best - 1e-12) { best = cost; chunks = cc; }
     }
-    a.chunk_len = (g.n[A] + chunks - 1) / chunks;
-    chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
+    a.chunk_len = (nr + chunks - 1) / chunks;
+    chunks = (nr + a.chunk_len - 1) / a.chunk_len;
     dim3 grid(bx, chunks);
     set_role_bcs(sg, a);
     ProfScope prof(s, A + 3 * EPI, st);
@@ -1226,6 +1229,23 @@ extern "C" int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rh
   return dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
 }
 
+extern "C" int jxf_sweep_range(jxf_handle h, int axis, int lo, int hi, const double* prims, double* rhs, int accumulate,
+                               void* stream) {
+  if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: null argument");
+  if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: axis %d is not active", axis);
+  if (lo < 0 || hi > h->g.n[axis] || lo >= hi) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: bad range [%d, %d)", lo, hi);
+  if (axis == h->lane_axis) {
+    if (lo != 0 || hi != h->g.n[axis])
+      return fail(JXF_ERR_UNSUPPORTED, "jxf_sweep_range: partial ranges are not supported along the contiguous axis");
+    return jxf_sweep(h, axis, prims, rhs, accumulate, stream);
+  }
+  SweepArgs a = base_args(h, axis, prims, rhs);
+  a.accumulate = accumulate ? 1 : 0;
+  a.range_lo = lo;
+  a.range_hi = hi;
+  return dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+}
+
 extern "C" int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, void* stream) {
   if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_compute_rhs: null argument");
   for (int k = 0; k < h->n_active; ++k) {
@@ -1260,14 +1280,23 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
 extern "C" int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out, const double* cons_in,
                          const double* cons_n, double* cons_out, double* rhs_scratch, const double* dt_dev,
                          double* red_dev, int reduce, int fill_halo, void* stream) {
+  return jxf_stage_tail(h, stage, 0, prims_in, prims_out, cons_in, cons_n, cons_out, rhs_scratch, dt_dev, red_dev, reduce,
+                        fill_halo, stream);
+}
+
+extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, const double* prims_in, double* prims_out,
+                              const double* cons_in, const double* cons_n, double* cons_out, double* rhs_scratch,
+                              const double* dt_dev, double* red_dev, int reduce, int fill_halo, void* stream) {
   if (!h || !prims_in || !prims_out || !cons_in || !cons_out || !dt_dev)
     return fail(JXF_ERR_BAD_ARG, "jxf_stage: null argument");
+  if (first_axis_index < 0 || first_axis_index >= h->n_active)
+    return fail(JXF_ERR_BAD_ARG, "jxf_stage_tail: first_axis_index %d out of range", first_axis_index);
   if (stage < 0 || stage >= h->stages) return fail(JXF_ERR_BAD_ARG, "jxf_stage: stage %d out of range", stage);
   if (stage > 0 && !cons_n) return fail(JXF_ERR_BAD_ARG, "jxf_stage: cons_n required for stage > 0");
   if (prims_in == prims_out) return fail(JXF_ERR_BAD_ARG, "jxf_stage: prims_out must not alias prims_in");
   if (h->n_active > 1 && !rhs_scratch) return fail(JXF_ERR_BAD_ARG, "jxf_stage: rhs_scratch required");
   if (reduce && !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage: red_dev required when reduce != 0");
-  for (int k = 0; k < h->n_active; ++k) {
+  for (int k = first_axis_index; k < h->n_active; ++k) {
     const int axis = h->active[k];
     const bool last = (k == h->n_active - 1);
     SweepArgs a = base_args(h, axis, prims_in, rhs_scratch);

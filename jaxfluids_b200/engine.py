@@ -137,6 +137,16 @@ class BlockSolver:
                                       _ptr(cons_n), _ptr(cons_out), _ptr(rhs), _ptr(dt_dev), _ptr(red_dev),
                                       int(bool(reduce)), int(bool(fill_halo)), _stream()))
 
+    def sweep_range(self, axis: int, lo: int, hi: int, prims, rhs, accumulate: bool):
+        _lib.check(self.lib.jxf_sweep_range(self._h, int(axis), int(lo), int(hi), _ptr(prims), _ptr(rhs),
+                                            int(bool(accumulate)), _stream()))
+
+    def stage_tail(self, stage, first_axis_index, prims_in, prims_out, cons_in, cons_n, cons_out, rhs, dt_dev,
+                   red_dev=None, reduce=False, fill_halo=True):
+        _lib.check(self.lib.jxf_stage_tail(self._h, int(stage), int(first_axis_index), _ptr(prims_in), _ptr(prims_out),
+                                           _ptr(cons_in), _ptr(cons_n), _ptr(cons_out), _ptr(rhs), _ptr(dt_dev),
+                                           _ptr(red_dev), int(bool(reduce)), int(bool(fill_halo)), _stream()))
+
     def step_fused(self, prims_a, prims_b, cons_a, cons_b, rhs, dt_dev, time_dev, red_dev, info_dev,
                    fill_halo=True) -> int:
         rc = self.lib.jxf_step_fused(self._h, _ptr(prims_a), _ptr(prims_b), _ptr(cons_a), _ptr(cons_b), _ptr(rhs),

@@ -9,6 +9,7 @@ rhs accumulator, and one send + one recv slab per shared face.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -77,7 +78,14 @@ class BlockRuntime:
         self.send = {f: torch.empty(s.face_slab_elems(FACE_ID[f]), dtype=torch.float64, device=self.device)
                      for f in self.neighbors}
         self.recv = {f: torch.empty_like(self.send[f]) for f in self.neighbors}
-        self.kernel_launches = 0
+        # inter-block exchange runs on its own stream and overlaps the first sweep of the next stage
+        self.overlap = bool(self.neighbors) and os.environ.get("JXF_OVERLAP", "1") != "0"
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.neighbors else None
+        self._pending = None                      # event: halos of the current primitives are complete
+        first = s.active[0]
+        self._first_axis = first
+        self._first_strided = len(s.active) > 1   # the contiguous (last active) axis takes no partial ranges
+        self._first_split = any(f in self.neighbors for f in (FACES[2 * first], FACES[2 * first + 1]))
 
     # -- views ------------------------------------------------------------
     @property
@@ -90,6 +98,7 @@ class BlockRuntime:
 
     def adopt(self, primitives: torch.Tensor, conservatives: torch.Tensor):
         """Make externally supplied tensors the current state (copies unless they already are)."""
+        self.finish_pending()
         if primitives.data_ptr() != self.primitives.data_ptr():
             self.primitives.copy_(primitives)
         if conservatives.data_ptr() != self.conservatives.data_ptr():
@@ -142,17 +151,60 @@ class BlockRuntime:
         self.time.fill_(float(time))
         self.dt.fill_(float(dt))
 
+    # stencil reach: the rhs of a cell needs the fluxes of its two faces, whose windows span 3 cells
+    # on either side, so only cells within 3 of a shared face read exchanged halos
+    REACH = 3
+
+    def _start_exchange(self, prims: torch.Tensor, cons: torch.Tensor):
+        """Post the inter-block halo exchange of (prims, cons) on the communication stream."""
+        compute = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            self.halo_update(prims, cons, local_done=True)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self._pending = done
+
+    def finish_pending(self):
+        """Make the current stream wait for an in-flight halo exchange (before anyone reads halos)."""
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending)
+            self._pending = None
+
     def stage(self, k: int, reduce: bool):
-        """One RK stage on the current state (simulation_manager.py:770-1047)."""
+        """One RK stage on the current state (simulation_manager.py:770-1047).  With several blocks the
+        exchange of the previous stage's halos may still be in flight: only the sweep ALONG an axis reads
+        that axis' halos, so the first sweep runs on the interior cells (or entirely, when its axis is not
+        split) before waiting for the exchange."""
         s = self.solver
         last = k == self.stages - 1
         p_in, p_out = self.prims[self.cur], self.prims[self.cur ^ 1]
         c_in = self.cons[0] if k == 0 else self.cons[1]
         c_out = self.cons[0] if last else self.cons[1]
-        s.stage(k, p_in, p_out, c_in, self.cons[0], c_out, self.rhs, self.dt, self.red, reduce=reduce,
-                fill_halo=True)
+        args = (p_in, p_out, c_in, self.cons[0], c_out, self.rhs, self.dt, self.red)
+        if self._pending is not None and self.overlap and self._first_strided:
+            ax, n, w = self._first_axis, self.cfg.cells[self._first_axis], self.REACH
+            if self._first_split and n > 2 * w:
+                s.sweep_range(ax, w, n - w, p_in, self.rhs, accumulate=False)
+                self.finish_pending()
+                s.sweep_range(ax, 0, w, p_in, self.rhs, accumulate=False)
+                s.sweep_range(ax, n - w, n, p_in, self.rhs, accumulate=False)
+            else:
+                if self._first_split:
+                    self.finish_pending()
+                s.sweep_range(ax, 0, n, p_in, self.rhs, accumulate=False)
+                self.finish_pending()
+            s.stage_tail(k, 1, *args, reduce=reduce, fill_halo=True)
+        else:
+            self.finish_pending()
+            s.stage(k, *args, reduce=reduce, fill_halo=True)
         if self.neighbors:
-            self.halo_update(p_out, c_out, local_done=True)
+            if self.overlap:
+                self._start_exchange(p_out, c_out)
+            else:
+                self.halo_update(p_out, c_out, local_done=True)
         self.cur ^= 1
 
     def step(self):
@@ -170,5 +222,6 @@ class BlockRuntime:
 
     def read_step_scalars(self):
         """(time, dt_next, max_speed_sum, min_rho, min_p) -- ONE device->host sync."""
+        self.finish_pending()
         v = torch.cat([self.time, self.dt, self.info]).cpu().numpy()
         return float(v[0]), float(v[1]), float(v[2]), float(v[3]), float(v[4])

@@ -219,6 +219,7 @@ class SimulationManager:
         for k in range(rt.stages):
             rt.stage(k, reduce=(k == rt.stages - 1))
         rt._allreduce_red()
+        rt.finish_pending()
         red = rt.red.cpu().numpy()
         tcv = time_control_variables._replace(
             physical_simulation_time=time_control_variables.physical_simulation_time +
