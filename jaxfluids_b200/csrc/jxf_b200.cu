@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
       nx[v] = base[v * g.vst + 5 * sA];
       Fp[v] = 0.0;
     }
+    ReconCarry<RECON> cy;
+    recon_carry_init<A, RECON>(w, cy);        // weights of cell f0-1 (left stencil of the first face)
     for (int f = f0; f <= f1; ++f) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) w[v][5] = nx[v];
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
       CellIn<EPI> in;
       if (f > f0) load_cell_in<EPI>(g, a, hidx, ridx, in);
       double F[5];
-      face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy);
       if (f > f0) {
         double r[5];
 #pragma unroll

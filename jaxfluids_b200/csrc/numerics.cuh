@@ -243,12 +243,9 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
 __device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
 __device__ __forceinline__ double rsqrt_fast(double a) { return 1.0 / sqrt(a); }
 #endif
-// sqrt(a) = a * rsqrt(a) with one residual correction (<= 1 ulp)
-__device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a) */) {
-  const double s = a * y;
-  const double r = fma(-s, s, a);
-  return fma(r, 0.5 * y, s);
-}
+// sqrt(a) = a * rsqrt(a): y carries <= 2 ulp, the product <= 3 ulp -- these roots only feed wave-speed
+// estimates (a_K, d_bar), whose relative error enters the flux multiplied by the (small) jump
+__device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a) */) { return a * y; }
 
 // ---------------------------------------------------------------------------
 // WENO5-Z on the five first differences d_i = q_{i+1} - q_i of the 6-cell window
@@ -302,6 +299,53 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
     const double num = fma(m2, q2, fma(m1, q1, n0 * q0));
     cr = num * rcp_fast(den);
   }
+}
+
+// ---------------------------------------------------------------------------
+// The same scheme split at the cell: the five cells (i-2..i+2) around cell i feed BOTH the left
+// state of face i+1/2 and (mirrored) the right state of face i-1/2, with the same three smoothness
+// indicators and tau (beta_k^R = beta_{2-k}^L).  weno5z_g evaluates the d-free weight products
+// g_k = (b_k + tau) prod_{j!=k} b_j of that cell once from its four differences
+// (D0..D3 = differences of cells i-2..i+2); the two face values then cost one reciprocal each.
+// Used by the marching (strided) sweeps for fields that are reconstructed as they are (all five in
+// PRIMITIVE mode, the two tangential velocities in CHAR-PRIMITIVE mode): the weights computed for the
+// right state at one face are carried in registers to the left state of the next face.
+// ---------------------------------------------------------------------------
+struct WenoG {
+  double g0, g1, g2;
+};
+
+__device__ __forceinline__ WenoG weno5z_g(double D0, double D1, double D2, double D3) {
+  constexpr double k = 3.0 / 13.0;
+  constexpr double eps = kStencilEps * (12.0 / 13.0);
+  const double e1 = D1 - D0, e2 = D2 - D1, e3 = D3 - D2;
+  const double s1 = fma(e1, e1, eps), s2 = fma(e2, e2, eps), s3 = fma(e3, e3, eps);
+  const double t0 = fma(3.0, D1, -D0), t1 = D1 + D2, t2 = fma(-3.0, D2, D3);
+  const double b0 = fma(k, t0 * t0, s1), b1 = fma(k, t1 * t1, s2), b2 = fma(k, t2 * t2, s3);
+  const double tau = fabs(b0 - b2);
+  const double p12 = b1 * b2, p02 = b0 * b2, p01 = b0 * b1;
+  const double P = b0 * p12;
+  WenoG g;
+  g.g0 = fma(tau, p12, P);
+  g.g1 = fma(tau, p02, P);
+  g.g2 = fma(tau, p01, P);
+  return g;
+}
+// left state of the face to the right of the cell: cell value + this
+__device__ __forceinline__ double weno5z_left_corr(const WenoG& g, double D0, double D1, double D2, double D3) {
+  const double den = fma(6.0, g.g1, fma(3.0, g.g2, g.g0));
+  const double q0 = fma(5.0 / 6.0, D1, (-1.0 / 3.0) * D0);
+  const double q1 = fma(2.0, D2, D1);
+  const double q2 = fma(2.0, D2, -0.5 * D3);
+  return fma(g.g2, q2, fma(g.g1, q1, g.g0 * q0)) * rcp_fast(den);
+}
+// right state of the face to the left of the cell (mirror: sub-stencil k <-> 2-k): cell value + this
+__device__ __forceinline__ double weno5z_right_corr(const WenoG& g, double D0, double D1, double D2, double D3) {
+  const double den = fma(6.0, g.g1, fma(3.0, g.g0, g.g2));
+  const double q0 = fma(-5.0 / 6.0, D2, (1.0 / 3.0) * D3);
+  const double q1 = -fma(2.0, D1, D2);
+  const double q2 = fma(-2.0, D1, 0.5 * D0);
+  return fma(g.g0, q2, fma(g.g1, q1, g.g2 * q0)) * rcp_fast(den);
 }
 
 // ---------------------------------------------------------------------------
@@ -405,6 +449,82 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
   }
 }
 
+// Carry of the cell-centred weights between consecutive faces of a marching sweep.
+template <int RECON>
+struct ReconCarry {
+  static constexpr int N = (RECON == RECON_PRIMITIVE) ? 5 : 2;   // fields reconstructed as they are
+  WenoG g[N];
+};
+
+// weights of the cell that is the window's cell k=1..: prime the carry from the 5 cells w[.][0..4]
+// (= the cell-centred set of window cell 2, i.e. the left stencil of this face)
+template <int A, int RECON>
+__device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconCarry<RECON>& cy) {
+  using Id = AxisIds<A>;
+#pragma unroll
+  for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+    const int v = (RECON == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+    cy.g[j] = weno5z_g(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3]);
+  }
+}
+
+// reconstruct() for marching sweeps: `cy` holds, on entry, the weights of window cell 2 (left stencil
+// of this face); on exit those of window cell 3 (right stencil of this face = left stencil of the next)
+template <int A, int RECON>
+__device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
+                                                  double (&pr)[5], ReconCarry<RECON>& cy) {
+  using Id = AxisIds<A>;
+#pragma unroll
+  for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+    const int v = (RECON == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+    const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
+                 d4 = w[v][5] - w[v][4];
+    pl[v] = w[v][2] + weno5z_left_corr(cy.g[j], d0, d1, d2, d3);
+    const WenoG gn = weno5z_g(d1, d2, d3, d4);
+    pr[v] = w[v][3] + weno5z_right_corr(gn, d1, d2, d3, d4);
+    cy.g[j] = gn;
+  }
+  if (RECON != RECON_PRIMITIVE) {
+    double dr[5], du[5], dp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      dr[k] = w[0][k + 1] - w[0][k];
+      du[k] = w[Id::un][k + 1] - w[Id::un][k];
+      dp[k] = w[4][k + 1] - w[4][k];
+    }
+    const double rho_ave = fma(0.5, dr[2], w[0][2]);
+    const double p_ave = fma(0.5, dp[2], w[4][2]);
+    const double gp = gamma * p_ave;
+    const double z = rsqrt_fast(gp * rho_ave);
+    const double ic = rho_ave * z;
+    const double c_ave = gp * z;
+    const double k_u = 0.5 * ic;
+    const double k_cc = ic * ic;
+    const double k_p = k_u * z;
+    double l0, r0, l1, r1, l4, r4;
+    {
+      double a[5], b[5], c[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double t = k_p * dp[k];
+        a[k] = fma(-k_u, du[k], t);
+        c[k] = fma(k_u, du[k], t);
+        b[k] = fma(-k_cc, dp[k], dr[k]);
+      }
+      weno5z_corr(a[0], a[1], a[2], a[3], a[4], l0, r0);
+      weno5z_corr(b[0], b[1], b[2], b[3], b[4], l1, r1);
+      weno5z_corr(c[0], c[1], c[2], c[3], c[4], l4, r4);
+    }
+    const double sl = l0 + l4, sr = r0 + r4;
+    pl[0] = w[0][2] + fma(rho_ave, sl, l1);
+    pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
+    pl[4] = fma(gp, sl, w[4][2]);
+    pr[0] = w[0][3] + fma(rho_ave, sr, r1);
+    pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
+    pr[4] = fma(gp, sr, w[4][3]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Riemann solvers: HLLC + Einfeldt (HLLC.py:41-126, signal_speeds.py:109-133, :159-199),
 // Rusanov (Rusanov.py:25-47)
@@ -493,6 +613,26 @@ __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma,
   reconstruct<A, RECON>(w, gamma, pl, pr);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
 }
+
+#ifdef JXF_REFERENCE_ORDER
+template <int RECON>
+struct ReconCarry {};
+template <int A, int RECON>
+__device__ __forceinline__ void recon_carry_init(const double (&)[5][6], ReconCarry<RECON>&) {}
+template <int A, int RECON, int RIEMANN>
+__device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&) {
+  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+}
+#else
+// marching variant: shares the cell-centred weights of the as-is fields between consecutive faces
+template <int A, int RECON, int RIEMANN>
+__device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
+                                                ReconCarry<RECON>& cy) {
+  double pl[5], pr[5];
+  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
+  riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+}
+#endif
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------

@@ -27,6 +27,32 @@ def load(fma=True, reference_order=False):
     return lib
 
 
+def rhs_axis_march(prims, axis, s, fma=True):
+    """rhs_axis through the MARCHING variant of the device functions (weights of the as-is fields carried
+    from face to face along the sweep axis, as sweep_strided does)."""
+    from oracle import port
+    lib = load(fma, False)
+    lib.face_flux_march_host.restype = C.c_int
+    lib.face_flux_march_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_void_p]
+    w = np.stack(port._window(prims, axis, s), axis=-1)          # (5, X, Y, Z faces..., 6)
+    w = np.moveaxis(w, 0, -2)                                    # (fx, fy, fz, 5, 6)
+    w = np.moveaxis(w, axis, 2)                                  # sweep axis last of the three -> sequences
+    shp = w.shape[:3]
+    w = np.ascontiguousarray(w.reshape(-1, 5, 6))
+    out = np.empty((w.shape[0], 5))
+    rc = lib.face_flux_march_host(axis, {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon], {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+                                  w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data)
+    assert rc == 0
+    f = out.reshape(shp + (5,))
+    f = np.moveaxis(f, 2, axis)                                  # back to (fx, fy, fz, 5)
+    f = np.moveaxis(f, -1, 0)
+    lo = [slice(None)] * 4
+    hi = [slice(None)] * 4
+    lo[1 + axis] = slice(None, -1)
+    hi[1 + axis] = slice(1, None)
+    return s.inv_dx[axis] * (f[tuple(lo)] - f[tuple(hi)])
+
+
 def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     """Same contract as oracle.port.rhs_axis, computed with the device functions on the host."""
     from oracle import port

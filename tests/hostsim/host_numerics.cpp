@@ -20,6 +20,32 @@ static void run(const double* win, long n, double gamma, double* out) {
   }
 }
 
+// marching variant: `nseq` sequences of `len` consecutive faces each (windows laid out (nseq, len, 5, 6));
+// the carry is primed from the first window of each sequence, exactly as sweep_strided does
+template <int A, int RECON, int RIEMANN>
+static void run_march(const double* win, long nseq, long len, double gamma, double* out) {
+  for (long s = 0; s < nseq; ++s) {
+    ReconCarry<RECON> cy;
+    for (long i = 0; i < len; ++i) {
+      double w[5][6], F[5];
+      const double* p = win + ((s * len + i) * 5) * 6;
+      for (int v = 0; v < 5; ++v) for (int k = 0; k < 6; ++k) w[v][k] = p[v * 6 + k];
+      if (i == 0) recon_carry_init<A, RECON>(w, cy);
+      face_flux_carry<A, RECON, RIEMANN>(w, gamma, F, cy);
+      for (int v = 0; v < 5; ++v) out[(s * len + i) * 5 + v] = F[v];
+    }
+  }
+}
+
+extern "C" int face_flux_march_host(int axis, int recon, int riemann, const double* win, long nseq, long len, double gamma,
+                                    double* out) {
+#define MCASE(A, R, S) if (axis == A && recon == R && riemann == S) { run_march<A, R, S>(win, nseq, len, gamma, out); return 0; }
+  MCASE(0,0,0) MCASE(0,0,1) MCASE(0,1,0) MCASE(0,1,1)
+  MCASE(1,0,0) MCASE(1,0,1) MCASE(1,1,0) MCASE(1,1,1)
+  MCASE(2,0,0) MCASE(2,0,1) MCASE(2,1,0) MCASE(2,1,1)
+  return -1;
+}
+
 // windows: (n, 5, 6) doubles; out: (n, 5)
 extern "C" int face_flux_host(int axis, int recon, int riemann, const double* win, long n, double gamma, double* out) {
 #define CASE(A, R, S) if (axis == A && recon == R && riemann == S) { run<A, R, S>(win, n, gamma, out); return 0; }

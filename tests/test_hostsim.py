@@ -53,3 +53,16 @@ def test_cancelled_total_norm_measures_conditioning_not_implementation():
     b = total_rhs(g["prims0_halo"], s, fma=False, reference_order=True)
     assert H.rel_linf(a, b) > 1e-12
     assert H.rel_linf(a, b, scale=H.rhs_scales(g["prims0_halo"], s)) < 1e-12
+
+
+@pytest.mark.parametrize("name", H.golden_names())
+def test_marching_variant_with_carried_weights(name):
+    """sweep_strided's face_flux_carry (cell-centred weights of the as-is fields carried between
+    consecutive faces) against the reference fixtures, every axis."""
+    g, case, num = H.load_golden(name)
+    s = H.setup_from_json(case, num)
+    p_in = g["prims0_halo"]
+    scales = H.rhs_scales(p_in, s)
+    for a in s.active:
+        got = hostsim.rhs_axis_march(p_in, a, s, fma=True)
+        assert H.rel_linf(got, g[f"rhs_axis{a}"], scale=scales) <= H.TOL_RHS
