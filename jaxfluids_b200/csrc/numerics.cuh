@@ -218,6 +218,10 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 
 #else  // production evaluation
 
+#ifndef JXF_HLLC_BRANCH
+#define JXF_HLLC_BRANCH 1
+#endif
+
 // ---------------------------------------------------------------------------
 // fast reciprocal / rsqrt / sqrt: MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 bits) + Newton.
 // Valid for normal, finite, positive-or-negative (rcp) / positive (rsqrt) arguments -- all
@@ -587,12 +591,26 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     const double dR = pr[0] * (S_R - uR);
     const double S_star = ((pr[4] - pl[4]) + fma(uL, dL, -(uR * dR))) * rcp_fast(dL - dR);
     // F = 1/2 (1 + sign S*) F*_L + 1/2 (1 - sign S*) F*_R : only the selected side is evaluated
+    // (S* > 0 -> F*_L, S* < 0 -> F*_R, S* = 0 -> the mean, sign(0) = 0 in the reference)
+#if JXF_HLLC_BRANCH
+    if (S_star > 0.0) {
+      hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, F);
+    } else if (S_star < 0.0) {
+      hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, F);
+    } else {
+      double fL[5], fR[5];
+      hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
+      hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) F[v] = 0.5 * (fL[v] + fR[v]);
+    }
+#else
     double fL[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, fR[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (S_star >= 0.0) hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
     if (S_star <= 0.0) hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
-    // select, don't blend: S* > 0 -> F*_L, S* < 0 -> F*_R, S* = 0 -> the mean (sign(0) = 0 in the reference)
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = (S_star > 0.0) ? fL[v] : ((S_star < 0.0) ? fR[v] : 0.5 * (fL[v] + fR[v]));
+#endif
   } else {
     const double alpha = fmax(fabs(uL) + aL, fabs(uR) + aR);
     double fl[5], fr[5];
