@@ -146,6 +146,14 @@ int jxf_reduce_reset(jxf_handle h, double* red_dev, void* stream);
 int jxf_finish_step(jxf_handle h, double* red_dev, double* dt_dev, double* time_dev,
                     double* info_dev, void* stream);
 
+/* ref: TimeIntegrator.perform_stage_integration (time_integration/time_integrator.py:108-227) with
+ * prepare_buffer_for_integration / integrate of RungeKutta3 (RK3.py:49-60), RK2.py, euler.py:
+ * whole buffer  U <- a_s U + b_s U^n  (stage > 0), then interior  U += (dt m_s) rhs.
+ * Stand-alone form of what jxf_stage fuses into its last sweep; dt is a host scalar like the
+ * reference's physical_timestep_size.  cons_out may alias cons. */
+int jxf_integrate_stage(jxf_handle h, int stage, const double* cons, const double* cons_n, const double* rhs,
+                        double dt, double* cons_out, void* stream);
+
 /* Inter-block face exchange helpers (ref: halos/inner/material.py:30-93).
  * pack  : copies the `nh` interior layers adjacent to `face` of prims into a dense slab
  *         (5, nh, T1, T2) (transverse extents = interior), ready for ncclSend.

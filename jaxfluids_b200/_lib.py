@@ -17,7 +17,7 @@ EXPORTS = (
     "jxf_last_error", "jxf_version", "jxf_create", "jxf_destroy", "jxf_field_elems", "jxf_rhs_elems",
     "jxf_num_stages", "jxf_compute_rhs", "jxf_sweep", "jxf_stage", "jxf_halo_fill", "jxf_prims_from_cons",
     "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
-    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range",
+    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage",
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
@@ -115,6 +115,8 @@ def load():
     lib.jxf_stage_tail.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, i32, i32, vp]
     lib.jxf_sweep_range.restype = i32
     lib.jxf_sweep_range.argtypes = [vp, i32, i32, i32, dp, dp, i32, vp]
+    lib.jxf_integrate_stage.restype = i32
+    lib.jxf_integrate_stage.argtypes = [vp, i32, dp, dp, dp, C.c_double, dp, vp]
     lib.jxf_debug_math.restype = i32
     lib.jxf_debug_math.argtypes = [dp, i64, dp, vp]
     lib.jxf_debug_face_flux.restype = i32

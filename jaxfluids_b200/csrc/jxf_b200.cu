@@ -156,45 +156,50 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
   }
 }
 
-// out of line on purpose: executed only by the thin shell of boundary-adjacent cells, and keeping it
-// out of the sweep loop keeps the hot loop inside the instruction cache
-__device__ __forceinline__ void halo_images_axis(double* prims_out, double* cons_out, long long vst, double gamma, int nh,
-                                              int bhi, int blo, long long hidx, double p0, double p1, double p2,
-                                              double p3, double p4, int ax, int n, int i, long long stride) {
+// one role axis of the images of a cell
+__device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
+                                                 int ax, int n, int i, long long stride) {
   if (n <= 1) return;
-  HaloOut h{prims_out, cons_out, vst, gamma, nh};
+  const int nh = h.nh;
   // low side (west / south / bottom)
   if (blo == JXF_BC_SYMMETRY) {
-    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p0, p1, p2, p3, p4, 1 + ax);
+    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
   } else if (blo == JXF_BC_PERIODIC) {
-    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p0, p1, p2, p3, p4, -1);
+    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
   } else if (blo == JXF_BC_ZEROGRADIENT) {
     if (i == 0)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p0, p1, p2, p3, p4, -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
   }
   // high side (east / north / top)
   if (bhi == JXF_BC_SYMMETRY) {
-    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p0, p1, p2, p3, p4, 1 + ax);
+    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
   } else if (bhi == JXF_BC_PERIODIC) {
-    if (i < nh) halo_image(h, hidx + (long long)n * stride, p0, p1, p2, p3, p4, -1);
+    if (i < nh) halo_image(h, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
   } else if (bhi == JXF_BC_ZEROGRADIENT) {
     if (i == n - 1)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p0, p1, p2, p3, p4, -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
   }
 }
+
+// OUT OF LINE on purpose: executed only by the thin shell of boundary-adjacent cells; keeping it out of
+// the sweep loop keeps the hot loop short (instruction cache) and its register allocation free of this code
+__device__ __noinline__ void halo_images_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, double p0, double p1,
+                                              double p2, double p3, double p4, int iA, int i1, int i2);
 
 template <int EPI>
 __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
                                               const CellIn<EPI>& in, const double (&r)[5], double step, Red& red,
                                               int iA, int i1, int i2) {
+  // r = F_{i-1/2} - F_{i+1/2}; the axis contribution (1/dx) r (space_solver.py:597-599) is added to the
+  // earlier axes' sum with one fused multiply-add
   if (EPI == 0) {
 #pragma unroll
-    for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = (a.accumulate ? in.rhs[v] : 0.0) + r[v];
+    for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = a.accumulate ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
   } else {
     double U[5];
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
-      const double tot = (a.has_prev ? in.rhs[v] : 0.0) + r[v];
+      const double tot = a.has_prev ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
       double u = in.U[v];
       if (a.blend) u = a.ca * u + a.cb * in.Un[v];
       U[v] = u + step * tot;
@@ -211,16 +216,18 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
       // boundary-adjacent cells only (a thin shell); warp-divergent by construction
       const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (i1 < a.nh) | (i1 >= g.n1 - a.nh) | (i2 < a.nh) |
                         (i2 >= g.n2 - a.nh);
-      if (near) {
-        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bcA_hi, g.bcA_lo, hidx,
-                         p[0], p[1], p[2], p[3], p[4], g.axA, g.nA, iA, g.sA);
-        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bc1_hi, g.bc1_lo, hidx,
-                         p[0], p[1], p[2], p[3], p[4], g.ax1, g.n1, i1, g.s1);
-        halo_images_axis(a.prims_out, a.cons_out, g.vst, a.gamma, a.nh, g.bc2_hi, g.bc2_lo, hidx,
-                         p[0], p[1], p[2], p[3], p[4], g.ax2, g.n2, i2, g.s2);
-      }
+      if (near) halo_images_cell(g, a, hidx, p[0], p[1], p[2], p[3], p[4], iA, i1, i2);
     }
   }
+}
+
+__device__ __noinline__ void halo_images_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, double p0, double p1,
+                                              double p2, double p3, double p4, int iA, int i1, int i2) {
+  const HaloOut h{a.prims_out, a.cons_out, g.vst, a.gamma, a.nh};
+  const double p[5] = {p0, p1, p2, p3, p4};
+  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA);
+  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1);
+  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2);
 }
 
 // ---------------------------------------------------------------------------
@@ -228,7 +235,7 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
 // over one chunk with a rolling 6-cell register window; each face flux is computed once.
 // ---------------------------------------------------------------------------
 template <int A, int RECON, int RIEMANN, int EPI>
-__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const SweepGeom g, const SweepArgs a) {
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a) {
   const long long plane = (long long)g.n1 * g.n2;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   Red red;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
       if (f > f0) {
         double r[5];
 #pragma unroll
-        for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fp[v] - F[v]);
+        for (int v = 0; v < 5; ++v) r[v] = Fp[v] - F[v];
         finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red, f - 1, i1, i2);
       }
 #pragma unroll
@@ -287,11 +294,113 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const Sweep
 }
 
 // ---------------------------------------------------------------------------
+// strided sweep, production form ("march"): same thread mapping as sweep_strided, but the 6-cell
+// window lives in a per-thread column of a shared-memory RING of planes instead of registers.
+// Every iteration each thread posts ONE asynchronous copy (cp.async, 8 B x 5 variables, coalesced
+// across the warp) of the plane kRingAhead steps ahead of the window straight from global to shared
+// memory -- no staging registers, no window shift (the ring index rotates instead of the data) --
+// and reads the window values where the arithmetic needs them.  A thread only ever touches its own
+// column of the ring, so the pipeline needs no barrier: cp.async.wait_group orders a thread's own
+// copies.  Freed registers (~70 of 168) go to instruction-level parallelism of the FP64 arithmetic.
+// ---------------------------------------------------------------------------
+#ifndef JXF_MARCH_BLOCKS
+#define JXF_MARCH_BLOCKS 3
+#endif
+#ifndef JXF_MARCH_KERNEL
+#define JXF_MARCH_KERNEL 1
+#endif
+constexpr int kRingSlots = 8;                   // planes in the ring (power of two)
+constexpr int kRingAhead = kRingSlots - 6;      // planes in flight beyond the current window
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_copy8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ring_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ring_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int A, int RECON, int RIEMANN, int EPI>
+__global__ void __launch_bounds__(128, JXF_MARCH_BLOCKS)
+sweep_march(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a) {
+  __shared__ double ring[kRingSlots][5][128];
+  const int t = threadIdx.x;
+  const long long plane = (long long)g.n1 * g.n2;
+  const long long p = blockIdx.x * (long long)blockDim.x + t;
+  Red red;
+  red.init();
+  if (p < plane) {
+    const int i1 = (int)(p / g.n2);
+    const int i2 = (int)(p - (long long)i1 * g.n2);
+    const int f0 = a.range_lo + blockIdx.y * a.chunk_len;
+    const int f1 = min(f0 + a.chunk_len, a.range_hi);
+    const long long sA = g.sA;
+    const long long col_h = i1 * g.s1 + i2 * g.s2;
+    const long long col_r = i1 * g.r1 + i2 * g.r2;
+    const double* base = a.prims + col_h + (long long)(f0 - 3) * sA;   // ring cell 0 = cell f0-3
+    const int last_cell = f1 - f0 + 5;                                  // ring cell of cell f1+2 (< n+nh: nh >= 3)
+    const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
+    auto post = [&](int c) {
+      if (c <= last_cell) {
+        const double* src = base + (long long)c * sA;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) ring_copy8(&ring[c & (kRingSlots - 1)][v][t], src + v * g.vst);
+      }
+      ring_commit();
+    };
+#pragma unroll
+    for (int c = 0; c < 5 + kRingAhead; ++c) post(c);
+    ring_wait<kRingAhead>();                   // cells 0..4 have landed
+    ReconCarry<RECON> cy;
+    {
+      double w[5][6];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[v][k] = ring[k][v][t];
+        w[v][5] = 0.0;
+      }
+      recon_carry_init<A, RECON>(w, cy);       // weights of cell f0-1 (left stencil of the first face)
+    }
+    double Fp[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int nfaces = f1 - f0 + 1;
+    for (int j = 0; j < nfaces; ++j) {
+      post(j + 5 + kRingAhead);                // overwrites the slot of cell j-1, which no window needs any more
+      const int f = f0 + j;
+      const long long hidx = col_h + (long long)(f - 1) * sA;
+      const long long ridx = col_r + (long long)(f - 1) * g.rA;
+      CellIn<EPI> in;
+      if (j > 0) load_cell_in<EPI>(g, a, hidx, ridx, in);
+      ring_wait<kRingAhead>();                 // cells j..j+5 have landed
+      double w[5][6];
+#pragma unroll
+      for (int v = 0; v < 5; ++v)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[v][k] = ring[(j + k) & (kRingSlots - 1)][v][t];
+      double F[5];
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy);
+      if (j > 0) {
+        double r[5];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) r[v] = Fp[v] - F[v];
+        finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red, f - 1, i1, i2);
+      }
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Fp[v] = F[v];
+    }
+    ring_wait<0>();
+  }
+  if (EPI) {
+    if (a.reduce) red_commit(red, a.red);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // contiguous sweep: lanes = consecutive faces of the flattened (row, face) sequence; the left
 // face flux comes from lane-1 by shuffle (lane 0: carry from the warp's previous iteration).
 // ---------------------------------------------------------------------------
 template <int A, int RECON, int RIEMANN, int EPI>
-__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepGeom g, const SweepArgs a,
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a,
                                                                     const long long total_faces) {
   const int nf = g.nA + 1;
   const int lane = threadIdx.x & 31;
@@ -368,7 +477,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const SweepG
       if (fin) {
         double r[5];
 #pragma unroll
-        for (int v = 0; v < 5; ++v) r[v] = a.inv_dx * (Fl[v] - F[v]);
+        for (int v = 0; v < 5; ++v) r[v] = Fl[v] - F[v];
         finalize_cell<EPI>(g, a, hidx, ridx, in, r, step, red, f - 1, i1, i2);
       }
       gf += 32;
@@ -460,7 +569,7 @@ struct RowsArgs {
 
 template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
 __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
-sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
+sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
   __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
   __shared__ alignas(8) uint64_t bars[4 * 2];
   const int lane = threadIdx.x & 31;
@@ -581,7 +690,7 @@ sweep_rows(const SweepGeom g, const SweepArgs a, const RowsArgs ra, const __grid
       if (act) {
         double rr[5];
 #pragma unroll
-        for (int v = 0; v < 5; ++v) rr[v] = a.inv_dx * (Fl[v] - F[v]);
+        for (int v = 0; v < 5; ++v) rr[v] = Fl[v] - F[v];
         finalize_cell<EPI>(g, a, hidx, ridx, in, rr, step, red, f - 1, i1, i2);
       }
       __syncwarp();          // all lanes are done with win[b] before it is refilled two iterations later
@@ -697,6 +806,31 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Geom g, const double*
     r.add_cell(p, gamma, active_mask);
   }
   red_commit(r, red);
+}
+
+// stand-alone stage combination (time_integrator.py:108-227, RK3.py:49-60): whole buffer
+// U <- a U + b U^n (stage > 0), then interior U += (dt m) rhs.  out may alias cons.
+__global__ void __launch_bounds__(256) integrate_stage_kernel(const Geom g, const double* __restrict__ cons,
+                                                              const double* __restrict__ cons_n,
+                                                              const double* __restrict__ rhs, double* out, double ca,
+                                                              double cb, int blend, double step) {
+  const long long total = g.vst;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(q % g.ext[2]);
+    const long long q1 = q / g.ext[2];
+    const int j = (int)(q1 % g.ext[1]);
+    const int i = (int)(q1 / g.ext[1]);
+    const int ii = i - g.off[0], jj = j - g.off[1], kk = k - g.off[2];
+    const bool interior = ii >= 0 && ii < g.n[0] && jj >= 0 && jj < g.n[1] && kk >= 0 && kk < g.n[2];
+    const long long ridx = (long long)ii * g.rst[0] + (long long)jj * g.rst[1] + (long long)kk * g.rst[2];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double u = cons[q + v * g.vst];
+      if (blend) u = ca * u + cb * cons_n[q + v * g.vst];
+      if (interior) u = u + step * rhs[ridx + v * g.rvst];
+      out[q + v * g.vst] = u;
+    }
+  }
 }
 
 __global__ void reduce_reset_kernel(double* red) {
@@ -846,6 +980,7 @@ struct jxf_solver {
   int n_active;
   int active_mask;
   int lane_axis;      // contiguous active axis
+  int order[3];       // order[k] = axis of the k-th sweep of a stage; the LAST one carries the fused epilogue
   int num_sms;
   int stages;
   double dt_mult[3];
@@ -853,6 +988,7 @@ struct jxf_solver {
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
+  bool no_march;       // JXF_NO_MARCH=1: register-window strided kernel instead of the shared-memory ring (tests)
   int n_maps;
   const void* map_ptr[8];
   CUtensorMap map[8];
@@ -948,7 +1084,17 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     s->blend[1][0] = 0.25; s->blend[1][1] = 0.75;
     s->blend[2][0] = 2.0 / 3.0; s->blend[2][1] = 1.0 / 3.0;
   }
+  // Stage sweep order: the reference's x, y, z (space_solver.py:289-314), the fused epilogue on the last one.
+  // JXF_SWEEP_ORDER=xzy (3-D) puts the epilogue on the marching y sweep instead and leaves the contiguous
+  // z sweep a plain rhs accumulation; the sum (x + z) + y differs from (x + y) + z by rounding only.
+  // Measured equal within noise at 512^3, so the reference order is the default.
+  for (int k = 0; k < s->n_active; ++k) s->order[k] = s->active[k];
+  {
+    const char* so = getenv("JXF_SWEEP_ORDER");
+    if (s->n_active == 3 && so && strcmp(so, "xzy") == 0) { s->order[0] = 0; s->order[1] = 2; s->order[2] = 1; }
+  }
   s->tma_ok = !(getenv("JXF_NO_TMA") && atoi(getenv("JXF_NO_TMA")) != 0);
+  s->no_march = getenv("JXF_NO_MARCH") && atoi(getenv("JXF_NO_MARCH")) != 0;
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
   s->n_maps = 0;
   s->num_sms = 148;
@@ -1113,6 +1259,9 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
     const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
+#if JXF_MARCH_KERNEL
+    const int resident = s->num_sms * (s->no_march ? JXF_MIN_BLOCKS : JXF_MARCH_BLOCKS);
+#endif
     // chunks along A: every chunk costs one redundant face (+ a 5-plane prologue), while few CTAs per
     // resident slot leave a partial last wave; pick the chunk count that minimises
     // (1 + 1.5/chunk_len) * ceil(waves)/waves over chunk lengths >= 16 cells
@@ -1133,6 +1282,12 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     dim3 grid(bx, chunks);
     set_role_bcs(sg, a);
     ProfScope prof(s, A + 3 * EPI, st);
+#if JXF_MARCH_KERNEL
+    if (!s->no_march) {
+      sweep_march<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
+      return check_launch("sweep_march");
+    }
+#endif
     sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
   } else {
     sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
@@ -1196,13 +1351,23 @@ static int dispatch_epi(const jxf_solver* s, const SweepArgs& a, int epi, cudaSt
 }
 template <int A, int RECON>
 static int dispatch_riemann(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+#ifdef JXF_TUNE_ONLY   // tuning builds instantiate the bench variant only (CHAR-PRIMITIVE + HLLC)
+  if (s->cfg.riemann != JXF_RIEMANN_HLLC) return fail(JXF_ERR_UNSUPPORTED, "tuning build: HLLC only");
+  return dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st);
+#else
   return s->cfg.riemann == JXF_RIEMANN_HLLC ? dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st)
                                             : dispatch_epi<A, RECON, RIEMANN_RUSANOV>(s, a, epi, st);
+#endif
 }
 template <int A>
 static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+#ifdef JXF_TUNE_ONLY
+  if (s->cfg.recon != JXF_RECON_CHAR_PRIMITIVE) return fail(JXF_ERR_UNSUPPORTED, "tuning build: CHAR-PRIMITIVE only");
+  return dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
+#else
   return s->cfg.recon == JXF_RECON_PRIMITIVE ? dispatch_riemann<A, RECON_PRIMITIVE>(s, a, epi, st)
                                              : dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
+#endif
 }
 static int dispatch_axis(const jxf_solver* s, int axis, const SweepArgs& a, int epi, cudaStream_t st) {
   switch (axis) {
@@ -1299,7 +1464,7 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
   if (h->n_active > 1 && !rhs_scratch) return fail(JXF_ERR_BAD_ARG, "jxf_stage: rhs_scratch required");
   if (reduce && !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage: red_dev required when reduce != 0");
   for (int k = first_axis_index; k < h->n_active; ++k) {
-    const int axis = h->active[k];
+    const int axis = h->order[k];
     const bool last = (k == h->n_active - 1);
     SweepArgs a = base_args(h, axis, prims_in, rhs_scratch);
     int rc;
@@ -1391,6 +1556,18 @@ extern "C" int jxf_finish_step(jxf_handle h, double* red_dev, double* dt_dev, do
   return check_launch("finish_step");
 }
 
+extern "C" int jxf_integrate_stage(jxf_handle h, int stage, const double* cons, const double* cons_n, const double* rhs,
+                                   double dt, double* cons_out, void* stream) {
+  if (!h || !cons || !rhs || !cons_out) return fail(JXF_ERR_BAD_ARG, "jxf_integrate_stage: null argument");
+  if (stage < 0 || stage >= h->stages) return fail(JXF_ERR_BAD_ARG, "jxf_integrate_stage: stage %d out of range", stage);
+  if (stage > 0 && !cons_n) return fail(JXF_ERR_BAD_ARG, "jxf_integrate_stage: cons_n required for stage > 0");
+  const int bx = (int)std::min<long long>((h->g.vst + 255) / 256, 148 * 16);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  integrate_stage_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->g, cons, cons_n, rhs, cons_out, h->blend[stage][0],
+                                                               h->blend[stage][1], stage > 0, dt * h->dt_mult[stage]);
+  return check_launch("integrate_stage");
+}
+
 extern "C" int64_t jxf_face_slab_elems(jxf_handle h, int face) {
   if (!h || face < 0 || face > 5) return -1;
   const int ax = face >> 1;
@@ -1427,14 +1604,17 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   if (!windows || !flux || n <= 0) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: bad argument");
   const unsigned bx = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
+  (void)bx; (void)st; (void)axis; (void)recon; (void)riemann; (void)gamma;
 #define JXF_DBG_CASE(A, R, S)                                                                     \
   if (axis == A && recon == R && riemann == S) {                                                  \
     face_flux_debug_kernel<A, R, S><<<bx, 128, 0, st>>>(windows, (long long)n, gamma, flux);       \
     return check_launch("face_flux_debug");                                                       \
   }
+#ifndef JXF_TUNE_ONLY
   JXF_DBG_CASE(0, 0, 0) JXF_DBG_CASE(0, 0, 1) JXF_DBG_CASE(0, 1, 0) JXF_DBG_CASE(0, 1, 1)
   JXF_DBG_CASE(1, 0, 0) JXF_DBG_CASE(1, 0, 1) JXF_DBG_CASE(1, 1, 0) JXF_DBG_CASE(1, 1, 1)
   JXF_DBG_CASE(2, 0, 0) JXF_DBG_CASE(2, 0, 1) JXF_DBG_CASE(2, 1, 0) JXF_DBG_CASE(2, 1, 1)
+#endif
 #undef JXF_DBG_CASE
   return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
 }

@@ -221,6 +221,9 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 #ifndef JXF_HLLC_BRANCH
 #define JXF_HLLC_BRANCH 1
 #endif
+#ifndef JXF_RIEMANN_MAIN       // marching sweeps: 1 = branch-free short-chain Riemann solve + rare S* = 0 fix-up
+#define JXF_RIEMANN_MAIN 0
+#endif
 
 // ---------------------------------------------------------------------------
 // fast reciprocal / rsqrt / sqrt: MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 bits) + Newton.
@@ -544,11 +547,14 @@ __device__ __forceinline__ void physical_flux(const double (&p)[5], const double
   f[4] = p[1 + A] * (c[4] + p[4]);
 }
 
-// F*_K = F_K + S_K^{-/+} (U*_K - U_K), Toro 10.72/10.73; dK = rho_K (S_K - u_K)
+// F*_K = F_K + S_K^{-/+} (U*_K - U_K), Toro 10.72/10.73; dK = rho_K (S_K - u_K).  The conservative
+// state of side K is formed here, i.e. only for the side(s) that sign(S*) selects.
 template <int A>
-__device__ __forceinline__ void hllc_star_flux(const double (&p)[5], const double (&c)[5], double inv_rho,
-                                               double S_K, double S_lim, double dK, double S_star, double (&fs)[5]) {
+__device__ __forceinline__ void hllc_star_flux(const double (&p)[5], double ig1, double inv_rho, double S_K,
+                                               double S_lim, double dK, double S_star, double (&fs)[5]) {
   using Id = AxisIds<A>;
+  double c[5];
+  cons_from_prims_fast(p, ig1, c);
   const double pre = dK * rcp_fast(S_K - S_star);                  // (S_K-u_K)/(S_K-S*) rho_K
   const double es = fma(S_star - p[Id::un], fma(p[4], rcp_fast(dK), S_star), c[4] * inv_rho);
   double us[5];
@@ -568,9 +574,6 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
                                              double gamma, double (&F)[5]) {
   using Id = AxisIds<A>;
   const double ig1 = 1.0 / (gamma - 1.0);
-  double cl[5], cr[5];
-  cons_from_prims_fast(pl, ig1, cl);
-  cons_from_prims_fast(pr, ig1, cr);
   const double uL = pl[Id::un], uR = pr[Id::un];
   // y = 1/sqrt(rho): 1/rho = y^2, sqrt(rho) = rho y
   const double yL = rsqrt_fast(pl[0]), yR = rsqrt_fast(pr[0]);
@@ -594,24 +597,27 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     // (S* > 0 -> F*_L, S* < 0 -> F*_R, S* = 0 -> the mean, sign(0) = 0 in the reference)
 #if JXF_HLLC_BRANCH
     if (S_star > 0.0) {
-      hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, F);
+      hllc_star_flux<A>(pl, ig1, irL, S_L, fmin(S_L, 0.0), dL, S_star, F);
     } else if (S_star < 0.0) {
-      hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, F);
+      hllc_star_flux<A>(pr, ig1, irR, S_R, fmax(S_R, 0.0), dR, S_star, F);
     } else {
       double fL[5], fR[5];
-      hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
-      hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
+      hllc_star_flux<A>(pl, ig1, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
+      hllc_star_flux<A>(pr, ig1, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
 #pragma unroll
       for (int v = 0; v < 5; ++v) F[v] = 0.5 * (fL[v] + fR[v]);
     }
 #else
     double fL[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, fR[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (S_star >= 0.0) hllc_star_flux<A>(pl, cl, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
-    if (S_star <= 0.0) hllc_star_flux<A>(pr, cr, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
+    if (S_star >= 0.0) hllc_star_flux<A>(pl, ig1, irL, S_L, fmin(S_L, 0.0), dL, S_star, fL);
+    if (S_star <= 0.0) hllc_star_flux<A>(pr, ig1, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = (S_star > 0.0) ? fL[v] : ((S_star < 0.0) ? fR[v] : 0.5 * (fL[v] + fR[v]));
 #endif
   } else {
+    double cl[5], cr[5];
+    cons_from_prims_fast(pl, ig1, cl);
+    cons_from_prims_fast(pr, ig1, cr);
     const double alpha = fmax(fabs(uL) + aL, fabs(uR) + aR);
     double fl[5], fr[5];
     physical_flux<A>(pl, cl, fl);
@@ -620,6 +626,77 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = fma(-ha, cr[v] - cl[v], 0.5 * (fl[v] + fr[v]));
   }
+}
+
+// ---------------------------------------------------------------------------
+// riemann_flux_main / riemann_flux_exact: the form the software-pipelined sweeps use.  Same formulas as
+// riemann_flux, arranged for a SHORT DEPENDENCY CHAIN and NO BRANCH, so that the Riemann solve of face
+// j-1 and the reconstruction of face j interleave in one basic block:
+//   * a_K = sqrt(gamma p_K) / sqrt(rho_K): the two rsqrt run side by side instead of one after the other;
+//   * d_bar = sqrt(N) / (sL + sR) with N = (sL a_L^2 + sR a_R^2)(sL + sR) + sL sR (uR - uL)^2 / 2:
+//     rsqrt(N) does not wait for the reciprocal of (sL + sR);
+//   * S* = N* / D*, D* = dL - dR < 0 strictly (dL <= -rho_L a_L < 0 < rho_R a_R <= dR), so
+//     sign(S*) = -sign(N*) is known BEFORE the division and 1/(S_K - S*) = D* / (S_K D* - N*):
+//     the three reciprocals 1/D*, 1/(S_K D* - N*), 1/d_K run side by side;
+//   * the side K that sign(S*) selects is chosen by selecting the INPUTS of one star-flux evaluation.
+// S* = 0 exactly (sign(0) = 0 in the reference: the flux is the mean of both star fluxes -- every
+// face on a symmetry plane) is flagged in `zero`; the caller then replaces F by riemann_flux(), the
+// exact branchy form above, in a rarely taken branch at the end of its loop body.
+// ---------------------------------------------------------------------------
+template <int A, int RIEMANN>
+__device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const double (&pr)[5], double gamma,
+                                                  double (&F)[5], bool& zero) {
+  using Id = AxisIds<A>;
+  if (RIEMANN != RIEMANN_HLLC) {
+    riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+    zero = false;
+    return;
+  }
+  const double ig1 = 1.0 / (gamma - 1.0);
+  const double uL = pl[Id::un], uR = pr[Id::un];
+  const double gpL = gamma * pl[4], gpR = gamma * pr[4];
+  const double yL = rsqrt_fast(pl[0]), yR = rsqrt_fast(pr[0]);       // 1/sqrt(rho)
+  const double zL = rsqrt_fast(gpL), zR = rsqrt_fast(gpR);           // 1/sqrt(gamma p)
+  const double sL = pl[0] * yL, sR = pr[0] * yR;                     // sqrt(rho)
+  const double aL = (gpL * zL) * yL, aR = (gpR * zR) * yR;           // sound speeds
+  const double irL = yL * yL, irR = yR * yR;                         // 1/rho
+  const double a2L = gpL * irL, a2R = gpR * irR;
+  const double ss = sL + sR;
+  const double od = rcp_fast(ss);
+  const double du = uR - uL;
+  const double N = fma(0.5 * (sL * sR), du * du, fma(sL, a2L, sR * a2R) * ss);
+  const double d_bar = (N * rsqrt_fast(N)) * od;
+  const double u_bar = fma(sL, uL, sR * uR) * od;
+  const double S_L = fmin(u_bar - d_bar, uL - aL);
+  const double S_R = fmax(u_bar + d_bar, uR + aR);
+  const double dL = pl[0] * (S_L - uL);
+  const double dR = pr[0] * (S_R - uR);
+  const double Ns = (pr[4] - pl[4]) + fma(uL, dL, -(uR * dR));
+  const double Ds = dL - dR;                                          // < 0
+  const double S_star = Ns * rcp_fast(Ds);
+  zero = (Ns == 0.0);
+  const bool left = !(Ns > 0.0);                                      // S* >= 0 -> left star state
+  double p[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) p[v] = left ? pl[v] : pr[v];
+  const double S_K = left ? S_L : S_R;
+  const double dK = left ? dL : dR;
+  const double irK = left ? irL : irR;
+  const double S_lim = left ? fmin(S_L, 0.0) : fmax(S_R, 0.0);
+  double c[5];
+  cons_from_prims_fast(p, ig1, c);
+  const double pre = (dK * Ds) * rcp_fast(fma(S_K, Ds, -Ns));         // rho_K (S_K-u_K)/(S_K-S*)
+  const double es = fma(S_star - p[Id::un], fma(p[4], rcp_fast(dK), S_star), c[4] * irK);
+  double us[5];
+  us[0] = pre;
+  us[Id::un] = pre * S_star;
+  us[Id::t0] = pre * p[Id::t0];
+  us[Id::t1] = pre * p[Id::t1];
+  us[4] = pre * es;
+  double f[5];
+  physical_flux<A>(p, c, f);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) F[v] = fma(S_lim, us[v] - c[v], f[v]);
 }
 
 #endif  // JXF_REFERENCE_ORDER
@@ -633,10 +710,21 @@ __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma,
 }
 
 #ifdef JXF_REFERENCE_ORDER
+template <int A, int RIEMANN>
+__device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const double (&pr)[5], double gamma,
+                                                  double (&F)[5], bool& zero) {
+  riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+  zero = false;
+}
 template <int RECON>
 struct ReconCarry {};
 template <int A, int RECON>
 __device__ __forceinline__ void recon_carry_init(const double (&)[5][6], ReconCarry<RECON>&) {}
+template <int A, int RECON>
+__device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
+                                                  double (&pr)[5], ReconCarry<RECON>&) {
+  reconstruct<A, RECON>(w, gamma, pl, pr);
+}
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&) {
   face_flux<A, RECON, RIEMANN>(w, gamma, F);
@@ -648,7 +736,13 @@ __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double 
                                                 ReconCarry<RECON>& cy) {
   double pl[5], pr[5];
   reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
+#if JXF_RIEMANN_MAIN
+  bool zero;
+  riemann_flux_main<A, RIEMANN>(pl, pr, gamma, F, zero);
+  if (zero) riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+#else
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+#endif
 }
 #endif
 

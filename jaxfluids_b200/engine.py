@@ -156,6 +156,12 @@ class BlockSolver:
             _lib.check(rc)
         return rc
 
+    def integrate_stage(self, stage: int, cons, cons_n, rhs, dt: float, out=None):
+        out = torch.empty_like(cons) if out is None else out
+        _lib.check(self.lib.jxf_integrate_stage(self._h, int(stage), _ptr(cons), _ptr(cons_n), _ptr(rhs),
+                                                C.c_double(float(dt)), _ptr(out), _stream()))
+        return out
+
     def halo_fill(self, prims, cons):
         _lib.check(self.lib.jxf_halo_fill(self._h, _ptr(prims), _ptr(cons), _stream()))
 

@@ -82,13 +82,15 @@ class TimeIntegrator:
     def perform_stage_integration(self, integration_buffers: IntegrationBuffers, rhs_buffers: IntegrationBuffers,
                                   initial_stage_buffers: Optional[IntegrationBuffers], physical_timestep_size,
                                   stage: int, equation_information=None) -> IntegrationBuffers:
-        """Stand-alone stage combination on API tensors (the production path fuses this into the last
-        sweep kernel; this entry exists for callers that drive the pieces separately).  Uses the
-        fused-stage kernel with a zero-velocity trick is NOT possible, so the combination is done by
-        the axpy kernels of jxf (torch glue is not used for the arithmetic)."""
-        raise NotImplementedError(
-            "perform_stage_integration as a separate call is not exposed on the B200 path: the stage update is "
-            "fused into the last sweep kernel (use SimulationManager.do_runge_kutta_stages / do_integration_step)")
+        """time_integrator.py:108-227: stage > 0: U <- a U + b U^n on the whole buffer (RK3.py:49-50), then
+        interior U += (dt m_s) rhs (time_integrator.py:57).  Returns NEW buffers like the reference (the
+        production step fuses this into the last sweep kernel; this is the stand-alone entry)."""
+        cons = integration_buffers.euler_buffers.conservatives
+        cons_n = initial_stage_buffers.euler_buffers.conservatives if stage > 0 else None
+        rhs = rhs_buffers.euler_buffers.conservatives
+        out = self._rt.solver.integrate_stage(stage, cons.contiguous(), None if cons_n is None else cons_n.contiguous(),
+                                              rhs.contiguous(), float(physical_timestep_size))
+        return IntegrationBuffers(EulerIntegrationBuffers(out, None, None, None))
 
 
 class HaloManager:

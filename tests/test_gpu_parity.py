@@ -325,3 +325,66 @@ def test_rows_kernel_tma_and_cp_async(cells, bc, no_tma, monkeypatch):
     assert H.rel_linf(host(st.primitives)[:, mask], prims[:, mask]) <= 1e-12
     assert H.rel_linf(host(st.conservatives)[:, mask], cons[:, mask]) <= 1e-12
     assert abs(st.dt.item() - dt) <= 1e-12 * dt
+
+
+@pytest.mark.parametrize("no_march,order", [(0, "xzy"), (1, "xzy"), (0, "xyz"), (1, "xyz")])
+@pytest.mark.parametrize("cells,bc,recon,riemann", [
+    ((20, 16, 12), "PERIODIC", "CHAR-PRIMITIVE", "HLLC"), ((12, 36, 10), "SYMMETRY", "PRIMITIVE", "HLLC"),
+    ((40, 8, 9), "ZEROGRADIENT", "CHAR-PRIMITIVE", "RUSANOV"), ((33, 20, 1), "SYMMETRY", "CHAR-PRIMITIVE", "HLLC")])
+def test_strided_forms_and_sweep_orders(cells, bc, recon, riemann, no_march, order, monkeypatch):
+    """Both forms of the strided sweep (shared-memory ring `sweep_march`, register window `sweep_strided`)
+    and both stage sweep orders (epilogue on the marching y sweep, or on the contiguous z sweep): rhs and
+    3 full steps incl. fused epilogue / halo images, against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    monkeypatch.setenv("JXF_NO_MARCH", str(no_march))
+    monkeypatch.setenv("JXF_SWEEP_ORDER", order)
+    s = H.make_setup(cells, bc=bc, recon=recon, riemann=riemann)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=11, amp=0.1), s)
+    sol = make_solver(s)
+    prims_c = np.nan_to_num(prims, nan=1.0)
+    got = host(sol.compute_rhs(dev(prims_c)))
+    assert H.rel_linf(got, port.compute_rhs(prims, s), scale=H.rhs_scales(prims, s)) <= H.TOL_RHS
+    st = BlockState(sol, prims_c, np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    for _ in range(3):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    mask = H.face_halo_mask(s)
+    assert H.rel_linf(host(st.primitives)[:, mask], prims[:, mask]) <= 1e-12
+    assert H.rel_linf(host(st.conservatives)[:, mask], cons[:, mask]) <= 1e-12
+    assert abs(st.dt.item() - dt) <= 1e-12 * dt
+
+
+@pytest.mark.parametrize("cells,bc,integrator", [((20, 12, 16), "SYMMETRY", "RK3"), ((64, 1, 1), "ZEROGRADIENT", "RK2"),
+                                                 ((18, 22, 1), "PERIODIC", "EULER")])
+def test_step_from_separate_api_pieces(cells, bc, integrator):
+    """One full RK step driven piece by piece, as the reference's do_runge_kutta_stages does
+    (simulation_manager.py:796-963): compute_rhs -> perform_stage_integration (stand-alone
+    jxf_integrate_stage) -> get_primitives_from_conservatives -> halo update, vs the oracle stage by stage."""
+    s = H.make_setup(cells, bc=bc, integrator=integrator)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=3, amp=0.1), s)
+    sol = make_solver(s)
+    dt = port.time_step_size(prims, s)
+    p, c = dev(np.nan_to_num(prims, nan=1.0)), dev(np.nan_to_num(cons, nan=1.0))
+    c_n = c.clone()
+    cons_n = cons
+    mask = H.face_halo_mask(s)
+    for k in range(sol.stages):
+        rhs = sol.compute_rhs(p)
+        c_new = sol.integrate_stage(k, c, c_n if k > 0 else None, rhs, dt)
+        assert c_new.data_ptr() != c.data_ptr()                 # functional: new buffer, like the reference
+        p_new = torch.empty_like(c_new)
+        sol.prims_from_cons(c_new, p_new)
+        sol.halo_fill(p_new, c_new)
+        with np.errstate(all="ignore"):
+            prims, cons, rhs_ref = port.stage(prims, cons, cons_n, dt, k, s)
+        assert H.rel_linf(host(rhs), rhs_ref, scale=H.rhs_scales(np.nan_to_num(host(p), nan=1.0), s)) <= H.TOL_RHS
+        assert H.rel_linf(host(c_new)[:, mask], cons[:, mask]) <= 1e-13, f"stage {k}"
+        assert H.rel_linf(host(p_new)[:, mask], prims[:, mask]) <= 1e-13, f"stage {k}"
+        p, c = p_new, c_new
+    # in-place form (cons_out aliases cons) gives the same bits
+    c2 = c_n.clone()
+    rhs0 = sol.compute_rhs(dev(np.nan_to_num(port.initialize(H.smooth_ic(s, seed=3, amp=0.1), s)[0], nan=1.0)))
+    a = sol.integrate_stage(0, c_n, None, rhs0, dt)
+    sol.integrate_stage(0, c2, None, rhs0, dt, out=c2)
+    assert torch.equal(a, c2)
