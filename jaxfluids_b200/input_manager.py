@@ -87,10 +87,19 @@ class ConvectiveFluxesSetup(NamedTuple):
     godunov: HighOrderGodunovSetup
 
 
+class DissipativeFluxesSetup(NamedTuple):
+    """read_conservatives.py:374-440 (names; CENTRAL4 is what the sm_100a kernels implement)."""
+    reconstruction_stencil: str = "CENTRAL4"
+    derivative_stencil_center: str = "CENTRAL4"
+    derivative_stencil_face: str = "CENTRAL4"
+    is_laplacian: bool = False
+
+
 class ConservativesSetup(NamedTuple):
     halo_cells: int
     time_integration: TimeIntegrationSetup
     convective_fluxes: ConvectiveFluxesSetup
+    dissipative_fluxes: DissipativeFluxesSetup = DissipativeFluxesSetup()
 
 
 class ActivePhysicsSetup(NamedTuple):
@@ -100,6 +109,7 @@ class ActivePhysicsSetup(NamedTuple):
     is_volume_force: bool = False
     is_surface_tension: bool = False
     is_geometric_source: bool = False
+    is_viscous_heat_production: bool = True      # read_active_physics default
 
 
 class PrecisionSetup(NamedTuple):
@@ -139,10 +149,22 @@ class DomainSetup(NamedTuple):
     decomposition: Tuple[int, int, int]
 
 
+class TransportSetup(NamedTuple):
+    """material_properties/transport (read_material_manager.py:200-330): the CUSTOM float values and the
+    PRANDTL conductivity model are implemented; non-dimensionalisation references are 1."""
+    dynamic_viscosity_model: str = "CUSTOM"
+    dynamic_viscosity: float = 0.0
+    bulk_viscosity: float = 0.0
+    thermal_conductivity_model: str = "CUSTOM"
+    thermal_conductivity: float = 0.0
+    prandtl_number: float = 1.0
+
+
 class MaterialSetup(NamedTuple):
     model: str
     specific_heat_ratio: float
     specific_gas_constant: float
+    transport: TransportSetup = TransportSetup()
 
 
 class CaseSetup(NamedTuple):
@@ -255,14 +277,32 @@ class InputManager:
         ap_d = get_setup_value(d, "active_physics", "active_physics", dict, False)
         ap = {}
         for f in ActivePhysicsSetup._fields:
-            ap[f] = bool(get_setup_value(ap_d, f, f"active_physics/{f}", bool, True, False))
+            default = ActivePhysicsSetup._field_defaults[f]
+            ap[f] = bool(get_setup_value(ap_d, f, f"active_physics/{f}", bool, True, default))
         active_physics = ActivePhysicsSetup(**ap)
         _assert(active_physics.is_convective_flux, "active_physics/is_convective_flux must be true "
                 "for the convective hot path.", "numerical")
-        for f in ActivePhysicsSetup._fields[1:]:
+        for f in ("is_volume_force", "is_surface_tension", "is_geometric_source"):
             if getattr(active_physics, f):
                 raise NotImplementedError(f"active_physics/{f} is not implemented on the B200 path "
-                                          "(convective single-phase path only)")
+                                          "(single-phase convective + viscous + heat flux only)")
+        # read_conservatives.py:374-440
+        is_diss = active_physics.is_viscous_flux or active_physics.is_heat_flux
+        df_d = get_setup_value(cons_d, "dissipative_fluxes", "conservatives/dissipative_fluxes", dict, not is_diss, {})
+        df = {}
+        for key, optional in (("derivative_stencil_face", not is_diss),
+                              ("reconstruction_stencil", not active_physics.is_viscous_flux),
+                              ("derivative_stencil_center", not active_physics.is_viscous_flux)):
+            v = get_setup_value(df_d, key, f"conservatives/dissipative_fluxes/{key}", str, optional, "CENTRAL4")
+            if is_diss:
+                v = R.select(v, R.REFERENCE_CENTRAL_STENCILS, R.TUPLE_DISSIPATIVE_STENCILS,
+                             f"conservatives/dissipative_fluxes/{key}")
+            df[key] = v
+        df["is_laplacian"] = bool(get_setup_value(df_d, "is_laplacian", "conservatives/dissipative_fluxes/is_laplacian",
+                                                  bool, True, False))
+        if is_diss and df["is_laplacian"]:
+            raise NotImplementedError("conservatives/dissipative_fluxes/is_laplacian is not implemented on the B200 path")
+        dissipative = DissipativeFluxesSetup(**df)
         for k in ("active_forcings",):
             for kk, v in (d.get(k, {}) or {}).items():
                 if v:
@@ -290,7 +330,8 @@ class InputManager:
                                                     bool, True, True)))
         return NumericalSetup(
             ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
-                               ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen))),
+                               ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen)),
+                               dissipative),
             active_physics, precision, OutputSetup(logging_setup))
 
     # -- case setup ----------------------------------------------------------
@@ -379,7 +420,50 @@ class InputManager:
         for k in ("forcings",):
             if d.get(k):
                 raise NotImplementedError(f"{k} is not implemented on the B200 path")
-        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas)))
+        transport = self._read_transport(mp_d)
+        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport))
+
+    def _read_transport(self, mp_d: Dict) -> TransportSetup:
+        """read_material_manager.py:200-330: required exactly when the flux that needs them is active."""
+        S = "case"
+        ap = self.numerical_setup.active_physics
+        base = "material_properties/transport"
+        if not (ap.is_viscous_flux or ap.is_heat_flux):
+            return TransportSetup()
+        tr_d = get_setup_value(mp_d, "transport", base, dict, False, setup=S)
+
+        def custom_float(dd, key, path):
+            v = get_setup_value(dd, key, path, (float, str), False, setup=S)
+            if isinstance(v, str):
+                raise NotImplementedError(f"{path} given as a lambda string is not implemented on the B200 path "
+                                          "(constant CUSTOM values only)")
+            return float(v)
+        mu_model, mu, bulk = "CUSTOM", 0.0, 0.0
+        need_mu = ap.is_viscous_flux or (tr_d.get("thermal_conductivity", {}) or {}).get("model") == "PRANDTL"
+        if need_mu:
+            mu_d = get_setup_value(tr_d, "dynamic_viscosity", base + "/dynamic_viscosity", dict, False, setup=S)
+            mu_model = get_setup_value(mu_d, "model", base + "/dynamic_viscosity/model", str, False,
+                                       possible_string_values=("CUSTOM", "SUTHERLAND"), setup=S)
+            if mu_model != "CUSTOM":
+                raise NotImplementedError(f"{base}/dynamic_viscosity/model = '{mu_model}' is a valid JAX-Fluids option "
+                                          "that is not implemented on the B200 path (implemented: ('CUSTOM',))")
+            mu = custom_float(mu_d, "value", base + "/dynamic_viscosity/value")
+            bulk = float(get_setup_value(tr_d, "bulk_viscosity", base + "/bulk_viscosity", float, False, setup=S))
+        tc_model, tc, prandtl = "CUSTOM", 0.0, 1.0
+        if ap.is_heat_flux:
+            tc_d = get_setup_value(tr_d, "thermal_conductivity", base + "/thermal_conductivity", dict, False, setup=S)
+            tc_model = get_setup_value(tc_d, "model", base + "/thermal_conductivity/model", str, False,
+                                       possible_string_values=("CUSTOM", "PRANDTL", "SUTHERLAND"), setup=S)
+            if tc_model == "CUSTOM":
+                tc = custom_float(tc_d, "value", base + "/thermal_conductivity/value")
+            elif tc_model == "PRANDTL":
+                prandtl = float(get_setup_value(tc_d, "prandtl_number", base + "/thermal_conductivity/prandtl_number",
+                                                float, False, numerical_value_condition=(">", 0.0), setup=S))
+            else:
+                raise NotImplementedError(f"{base}/thermal_conductivity/model = '{tc_model}' is a valid JAX-Fluids "
+                                          "option that is not implemented on the B200 path "
+                                          "(implemented: ('CUSTOM', 'PRANDTL'))")
+        return TransportSetup(mu_model, mu, bulk, tc_model, tc, prandtl)
 
     def _sanity_check(self):
         di = self.domain_information

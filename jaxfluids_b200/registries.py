@@ -22,6 +22,8 @@ REFERENCE_RECONSTRUCTION_STENCILS = (
     "WENO6-CUM1", "WENO6-CUM2", "WENO7-JS", "WENO9-JS", "WENO3-JS-ADAP", "WENO3-Z-ADAP", "WENO5-JS-ADAP",
     "WENO5-Z-ADAP", "WENO6-CU-ADAP", "CENTRAL2", "CENTRAL2-ADAP", "CENTRAL4", "CENTRAL4-ADAP", "CENTRAL6",
     "CENTRAL6-ADAP", "CENTRAL8", "CENTRAL8-ADAP")
+REFERENCE_CENTRAL_STENCILS = ("CENTRAL2", "CENTRAL4", "CENTRAL6", "CENTRAL8", "CENTRAL2-ADAP", "CENTRAL4-ADAP",
+                              "CENTRAL6-ADAP", "CENTRAL8-ADAP")
 REFERENCE_TIME_INTEGRATORS = ("EULER", "RK2", "RK3", "RK2_LS4")
 REFERENCE_MATERIALS = ("IdealGas", "SafeIdealGas", "StiffenedGas", "StiffenedGasComplete", "Tait",
                        "BarotropicCavitationFluid")
@@ -38,6 +40,7 @@ DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt"}
 DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z"}
 TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
 TUPLE_FROZEN_STATE = ("ARITHMETIC",)
+TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
 DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
 TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE")

@@ -53,6 +53,16 @@ class Setup:
     cfl: float = 0.5
     fixed_timestep: float | None = None
     inv_dx_override: Tuple[float, float, float] | None = None   # sub-blocks of a larger grid (port_mt, multi-block tests)
+    # dissipative fluxes (active_physics + material_properties/transport); CENTRAL4 stencils
+    is_viscous_flux: bool = False
+    is_heat_flux: bool = False
+    is_viscous_heat_production: bool = True      # numerical_setup/active_physics default
+    dynamic_viscosity: float = 0.0               # transport/dynamic_viscosity, model CUSTOM (float)
+    bulk_viscosity: float = 0.0
+    thermal_conductivity_model: str = "CUSTOM"   # CUSTOM (float value) | PRANDTL
+    thermal_conductivity: float = 0.0
+    prandtl_number: float = 1.0
+    gas_constant: float = 1.0                    # equation_of_state/specific_gas_constant
     active: Tuple[int, ...] = field(init=False)
 
     def __post_init__(self):
@@ -82,6 +92,14 @@ class Setup:
     def interior(self):
         nh = self.nh
         return tuple(slice(nh, -nh) if self.cells[i] > 1 else slice(None) for i in range(3))
+
+    @property
+    def is_dissipative(self):
+        return self.is_viscous_flux or self.is_heat_flux
+
+    @property
+    def cp(self):                                # ideal_gas.py:33
+        return self.gamma / (self.gamma - 1.0) * self.gas_constant
 
     def cell_centers(self):                      # homogenous.py:14
         out = []
@@ -166,6 +184,76 @@ def halo_fill(prims, cons, s: Setup):
         hc = cons_from_prims(hp, s.gamma)
         prims[tuple(sl_dst)] = prims[tuple(sl_dst)] * (1 - 1.0) + hp * 1.0
         cons[tuple(sl_dst)] = cons[tuple(sl_dst)] * (1 - 1.0) + hc * 1.0
+    if s.is_dissipative and len(s.active) > 1:       # halo_manager.py:119-129, :193-199
+        prims, cons = edge_halo_fill(prims, cons, s)
+    return prims, cons
+
+
+# domain/__init__.py:9-15 (order matters only for documentation: edge regions are disjoint and no edge
+# reads another edge's region)
+EDGES = ("west_south", "west_north", "east_north", "east_south", "south_bottom", "north_bottom",
+         "south_top", "north_top", "east_bottom", "west_bottom", "east_top", "west_top")
+OPPOSITE = {"east": "west", "west": "east", "north": "south", "south": "north", "top": "bottom", "bottom": "top"}
+
+
+def _edge_range(face, code, nh):
+    """halos/halo_slices.py:98-147: index range along the axis of `face` for the edge region itself
+    (code None), or with this face's range moved to the nh interior layers next to it (code '1')."""
+    hi = face in ("east", "north", "top")
+    if code == "1":
+        return slice(-2 * nh, -nh) if hi else slice(nh, 2 * nh)
+    return slice(-nh, None) if hi else slice(0, nh)
+
+
+def edge_halo_fill(prims, cons, s: Setup):
+    """halos/outer/material.py:289-383 (edge_halo_update / compute_edge_halos) with the type combination of
+    boundary_condition.py:128-179 and the retrieve table :607-655: the FIRST face of the edge that is
+    PERIODIC or SYMMETRY decides (PERIODIC: copy from the opposite side, SYMMETRY: mirror + negate that
+    face's normal velocity); otherwise the mean of the two adjacent halo regions.  cons recomputed."""
+    prims, cons = prims.copy(), cons.copy()
+    nh = s.nh
+    for edge in EDGES:
+        fa, fb = edge.split("_")
+        axa, axb = FACE_AXIS[fa], FACE_AXIS[fb]
+        if axa not in s.active or axb not in s.active:
+            continue
+        types = []
+        decided = False
+        for f in (fa, fb):
+            if not decided and s.bc[f] in ("PERIODIC", "SYMMETRY"):
+                types.append(s.bc[f])
+                decided = True
+            else:
+                types.append("ANY")
+
+        def region(face_a, code_a, face_b, code_b):
+            sl = [slice(None)] + list(s.interior)
+            sl[1 + axa] = _edge_range(face_a, code_a, nh)
+            sl[1 + axb] = _edge_range(face_b, code_b, nh)
+            return tuple(sl)
+
+        if types == ["ANY", "ANY"]:
+            hp = 0.5 * (prims[region(fa, "1", fb, None)] + prims[region(fa, None, fb, "1")])
+        else:
+            k = 0 if types[0] != "ANY" else 1
+            faces = [fa, fb]
+            codes = [None, None]
+            codes[k] = "1"
+            if types[k] == "PERIODIC":
+                faces[k] = OPPOSITE[faces[k]]
+            hp = prims[region(faces[0], codes[0], faces[1], codes[1])]
+            if types[k] == "SYMMETRY":
+                ax = (axa, axb)[k]
+                flip = [slice(None)] * 4
+                flip[1 + ax] = slice(None, None, -1)
+                hp = hp[tuple(flip)]
+                sign = np.ones((5, 1, 1, 1))
+                sign[1 + ax] *= -1.0
+                hp = hp * sign
+        hc = cons_from_prims(hp, s.gamma)
+        dst = region(fa, None, fb, None)
+        prims[dst] = prims[dst] * (1 - 1) + hp * 1
+        cons[dst] = cons[dst] * (1 - 1) + hc * 1
     return prims, cons
 
 
@@ -315,6 +403,138 @@ def rusanov(pl, pr, cl, cr, axis, gamma):
 
 
 # --------------------------------------------------------------------------
+# dissipative fluxes (CENTRAL4 stencils): solvers/source_term_solver.py
+# --------------------------------------------------------------------------
+def temperature(prims, s: Setup):
+    """ideal_gas.py:64-65: T = p / (rho R), on whatever region is passed."""
+    return prims[4] / (prims[0] * s.gas_constant)
+
+
+def _sl(s: Setup, axis, lo, hi, ext):
+    """[..., transverse = interior widened by `ext`, axis = lo:hi]."""
+    nh = s.nh
+    out = [Ellipsis]
+    for i in range(3):
+        if i == axis:
+            out.append(slice(lo, hi if hi != 0 else None))
+        elif s.cells[i] > 1:
+            out.append(slice(nh - ext, -(nh - ext)))
+        else:
+            out.append(slice(None))
+    return tuple(out)
+
+
+def central4_reconstruct(buf, axis, s: Setup, n=None):
+    """stencils/reconstruction/central/central_4.py:32-47 with spatial_stencil.py:99-111: faces f = 0..N of
+    `axis`, cells n-2+f .. n+1+f, transverse range [n:-n] (n = the buffer's halo width)."""
+    n = s.nh if n is None else n
+    ext = s.nh - n            # only used with buffers that carry s.nh halos
+    b = [buf[_sl(s, axis, n + k, -n + k + 1, ext)] for k in (-2, -1, 0, 1)]
+    c0, c1 = -1.0 / 16.0, 9.0 / 16.0
+    return c0 * (b[0] + b[3]) + c1 * (b[1] + b[2])
+
+
+def deriv4_face(buf, dxi, axis, s: Setup):
+    """stencils/derivative/deriv_face_4.py: 1/dx * (1/24 (u_{i-1} - u_{i+2}) + 27/24 (u_{i+1} - u_i))."""
+    n = s.nh
+    b = [buf[_sl(s, axis, n + k, -n + k + 1, 0)] for k in (-2, -1, 0, 1)]
+    c0, c1 = 1.0 / 24.0, 27.0 / 24.0
+    return 1.0 / dxi * (c0 * (b[0] - b[3]) + c1 * (b[2] - b[1]))
+
+
+def deriv4_center_offset2(buf, dxi, axis, s: Setup):
+    """stencils/derivative/deriv_center_4.py with nh = s.nh, offset = 2 (source_term_solver.py:63-70):
+    cell-centre derivative on the interior widened by 2 cells in every active axis."""
+    n = s.nh - 2
+    b = [buf[_sl(s, axis, n + k, -n + k, 2)] for k in (-2, -1, 1, 2)]
+    c0, c1 = 1.0 / 12.0, 8.0 / 12.0
+    return 1.0 / dxi * (c0 * (b[0] - b[3]) + c1 * (b[2] - b[1]))
+
+
+def _reconstruct_offset2(buf2, axis, s: Setup):
+    """central_4 on a buffer that carries 2 halo cells (reconstruct_stencil_duidxi, source_term_solver.py:75-80)."""
+    def sl(lo, hi):
+        out = [Ellipsis]
+        for i in range(3):
+            if i == axis:
+                out.append(slice(lo, hi if hi != 0 else None))
+            elif s.cells[i] > 1:
+                out.append(slice(2, -2))
+            else:
+                out.append(slice(None))
+        return tuple(out)
+    b = [buf2[sl(2 + k, -2 + k + 1)] for k in (-2, -1, 0, 1)]
+    c0, c1 = -1.0 / 16.0, 9.0 / 16.0
+    return c0 * (b[0] + b[3]) + c1 * (b[1] + b[2])
+
+
+def _flux_shape(axis, s: Setup):
+    return tuple(s.cells[i] + (1 if i == axis else 0) for i in range(3))
+
+
+def _temperature_at_face(T, axis, s: Setup):
+    T_cf = central4_reconstruct(T, axis, s)
+    return np.where(T_cf <= 0.0, EPS, T_cf)                              # source_term_solver.py:289-292
+
+
+def _dynamic_viscosity(T, s: Setup):
+    """material.py:91-92 with the CUSTOM float wrapper (input/setup_reader.py:203-216): ones_like(T) * value,
+    non-dimensionalised by rho_ref u_ref L_ref = 1."""
+    return np.ones_like(T) * s.dynamic_viscosity
+
+
+def _thermal_conductivity(T, s: Setup):
+    if s.thermal_conductivity_model == "CUSTOM":
+        return np.ones_like(T) * s.thermal_conductivity
+    if s.thermal_conductivity_model == "PRANDTL":                        # material.py:115-116
+        return s.cp * _dynamic_viscosity(T, s) / s.prandtl_number
+    raise NotImplementedError(s.thermal_conductivity_model)
+
+
+def viscous_flux_axis(prims, T, axis, s: Setup):
+    """source_term_solver.py:258-345 (+ :405-470 velocity gradient, :503-533 tau, :535-582 derivatives):
+    (4, faces) = (tau_axis0, tau_axis1, tau_axis2, u.tau)."""
+    T_cf = _temperature_at_face(T, axis, s)
+    mu_1 = _dynamic_viscosity(T_cf, s)
+    mu_2 = s.bulk_viscosity - 2.0 / 3.0 * mu_1
+    vel = prims[1:4]
+    shape = _flux_shape(axis, s)
+    grad = []                                  # grad[i] = d(vel)/dx_i at the faces of `axis`, (3, faces)
+    for i in range(3):
+        if i in s.active:
+            if i == axis:
+                g = deriv4_face(vel, s.dx[i], i, s)
+            else:
+                g = _reconstruct_offset2(deriv4_center_offset2(vel, s.dx[i], i, s), axis, s)
+        else:
+            g = np.zeros((3,) + shape)
+        grad.append(g)
+    vg = np.stack(grad, axis=1)                # vg[c, i] = d u_c / d x_i
+    tau = []
+    for k in range(3):
+        if axis in s.active and k in s.active:
+            tau.append(mu_1 * (vg[axis, k] + vg[k, axis]))
+        else:
+            tau.append(np.zeros(shape))
+    tau[axis] = tau[axis] + mu_2 * sum([vg[k, k] for k in s.active])
+    vel_cf = central4_reconstruct(vel, axis, s)
+    if s.is_viscous_heat_production:
+        vt = 0.0
+        for k in s.active:
+            vt = vt + tau[k] * vel_cf[k]
+    else:
+        vt = np.zeros_like(tau[0])
+    return np.stack([*tau, vt])
+
+
+def heat_flux_axis(prims, T, axis, s: Setup):
+    """source_term_solver.py:188-250: q = -lambda(T_face) dT/dx_axis."""
+    T_cf = _temperature_at_face(T, axis, s)
+    lam = _thermal_conductivity(T_cf, s)
+    return -lam * deriv4_face(T, s.dx[axis], axis, s)
+
+
+# --------------------------------------------------------------------------
 # right-hand side
 # --------------------------------------------------------------------------
 def face_flux(prims, axis, s: Setup):
@@ -331,6 +551,14 @@ def rhs_axis(prims, axis, s: Setup):
     """space_solver.py:456-674 (convective branch: :489, :517-543, :597-599)."""
     fc = face_flux(prims, axis, s)
     f = np.zeros_like(fc) + fc                                          # :517, :545
+    if s.is_dissipative:
+        T = temperature(prims, s)
+        if s.is_viscous_flux:                                           # :567-573
+            f = f.copy()
+            f[1:5] = f[1:5] + (-viscous_flux_axis(prims, T, axis, s))
+        if s.is_heat_flux:                                              # :576-584
+            f = f.copy()
+            f[4] = f[4] + heat_flux_axis(prims, T, axis, s)
     lo = [slice(None)] * 4
     hi = [slice(None)] * 4
     lo[1 + axis] = slice(None, -1)
@@ -361,6 +589,15 @@ def time_step_size(prims, s: Setup):
     for i in s.active:
         acc = acc + (np.abs(pi[1 + i]) + c)
     dt = s.dx_min / (np.max(acc) + EPS)
+    if s.is_dissipative:
+        T = temperature(pi, s)
+        dx2 = s.dx_min * s.dx_min
+        if s.is_viscous_flux:                                           # time_step_size.py:111-121
+            nu = _dynamic_viscosity(T, s) / pi[0]
+            dt = np.minimum(dt, 3.0 / 14.0 * dx2 / (np.max(nu) + EPS))
+        if s.is_heat_flux:                                              # :123-135
+            alpha = _thermal_conductivity(T, s) / (pi[0] * s.cp)
+            dt = np.minimum(dt, 0.1 * dx2 / (np.max(alpha) + EPS))
     dt = dt * s.cfl
     return float(dt)
 

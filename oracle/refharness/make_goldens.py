@@ -36,11 +36,22 @@ FIXTURES = {
     "tgv16_sym_char_hllc_rk3": ("tgv", dict(cells=(16, 16, 16)), 5, (1, 5)),
     "tgv_12x16x20_per_char_hllc_rk3": ("tgv", dict(cells=(12, 16, 20), bc="PERIODIC"), 3, (1, 3)),
     "tgv16_per_char_rusanov_rk3": ("tgv", dict(cells=(16, 16, 16), bc="PERIODIC", riemann="RUSANOV"), 2, (2,)),
+    # viscous + heat flux (CENTRAL4 dissipative stencils, edge halos): kwargs carry a `dissipation` entry
+    "tgv12_sym_visc_prandtl_rk3": ("tgv", dict(cells=(12, 12, 12), dissipation=dict(mu=1 / 160, prandtl=0.71)), 3, (1, 3)),
+    "tgv_10x12x14_per_visc_bulk_kappa_rk3": ("tgv", dict(cells=(10, 12, 14), bc="PERIODIC",
+                                                         dissipation=dict(mu=1 / 100, bulk=0.002, kappa=0.05)), 2, (2,)),
+    "riemann2d_20x24_visc_rk3": ("riemann2d", dict(cells=(20, 24, None), dissipation=dict(mu=1e-3)), 3, (3,)),
+    "sod80_visc_prandtl_rk3": ("sod", dict(cells=(80, None, None), dissipation=dict(mu=2e-3, prandtl=0.7)), 5, (5,)),
 }
 
 
 def make(name, case_name, kw, nsteps, snaps):
+    kw = dict(kw)
+    dissipation = kw.pop("dissipation", None)
     case, num = rr.customize(*rr.load_case(case_name), **kw)
+    if dissipation:
+        from oracle.refharness import pin_check
+        case, num = pin_check.with_dissipation(case, num, **dissipation)
     run = rr.ReferenceRun(case, num)
     d = {"case_json": np.array(json.dumps(case)), "num_json": np.array(json.dumps(num))}
     d["prims0"] = run.interior(run.primitives).copy()
@@ -51,7 +62,8 @@ def make(name, case_name, kw, nsteps, snaps):
     ss = run.sim.space_solver
     mf = run.material_fields
     for a in run.sim.domain_information.active_axes_indices:
-        out = ss.compute_rhs_xi(mf.conservatives, mf.primitives, None, a, 0.0, run.dt)
+        out = ss.compute_rhs_xi(mf.conservatives, mf.primitives, mf.temperature, a, 0.0, run.dt,
+                                ml_setup=run.default_ml_setup())
         d[f"rhs_axis{a}"] = np.array(out[0].conservatives)
     seq = {"dt": [], "time": [], "totals": [], "min_density": [], "min_pressure": []}
     for n in range(1, nsteps + 1):

@@ -1,5 +1,5 @@
 """Pin oracle/port.py against the reference executed on the stand-in (build container only)."""
-import os, sys, time
+import json, os, sys, time
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -8,23 +8,34 @@ from oracle.refharness import run_reference as rr
 
 
 def setup_from_case(case, num):
-    d = case["domain"]
-    g = num["conservatives"]["convective_fluxes"]["godunov"]
-    return port.Setup(
-        cells=tuple(d[a]["cells"] for a in "xyz"),
-        domain=tuple(tuple(d[a]["range"]) for a in "xyz"),
-        bc={f: case["boundary_conditions"][f]["type"] for f in port.FACES},
-        gamma=case["material_properties"]["equation_of_state"]["specific_heat_ratio"],
-        nh=num["conservatives"]["halo_cells"],
-        recon=g.get("reconstruction_variable", "PRIMITIVE"),
-        riemann=g.get("riemann_solver", "HLLC"),
-        integrator=num["conservatives"]["time_integration"]["integrator"],
-        cfl=num["conservatives"]["time_integration"].get("CFL", 0.5),
-    )
+    from tests import helpers
+    return helpers.setup_from_json(case, num)
 
 
-def check(name, nsteps=3, **kw):
+def with_dissipation(case, num, mu=None, bulk=0.0, kappa=None, prandtl=None):
+    """Switch the viscous / heat flux of a shipped case on (active_physics + transport block)."""
+    case, num = json.loads(json.dumps(case)), json.loads(json.dumps(num))
+    tr = case["material_properties"].setdefault("transport", {})
+    if mu is not None:
+        num["active_physics"]["is_viscous_flux"] = True
+        tr["dynamic_viscosity"] = {"model": "CUSTOM", "value": float(mu)}
+        tr["bulk_viscosity"] = float(bulk)
+    if kappa is not None or prandtl is not None:
+        num["active_physics"]["is_heat_flux"] = True
+        tr.setdefault("dynamic_viscosity", {"model": "CUSTOM", "value": 0.0})
+        tr.setdefault("bulk_viscosity", 0.0)
+        tr["thermal_conductivity"] = ({"model": "PRANDTL", "prandtl_number": float(prandtl)} if prandtl is not None
+                                      else {"model": "CUSTOM", "value": float(kappa)})
+    num["conservatives"].setdefault("dissipative_fluxes", {"reconstruction_stencil": "CENTRAL4",
+                                                          "derivative_stencil_center": "CENTRAL4",
+                                                          "derivative_stencil_face": "CENTRAL4"})
+    return case, num
+
+
+def check(name, nsteps=3, dissipation=None, **kw):
     case, num = rr.customize(*rr.load_case(name), **kw)
+    if dissipation:
+        case, num = with_dissipation(case, num, **dissipation)
     t0 = time.time()
     ref = rr.ReferenceRun(case, num)
     s = setup_from_case(case, num)
@@ -48,7 +59,7 @@ def check(name, nsteps=3, **kw):
         mr, mp = port.positivity_info(prims, s)
         assert mr == rec["min_density"] and mp == rec["min_pressure"]
         assert np.array_equal(port.totals(cons, s), rec["totals"])
-    print(f"PIN OK  {name:10s} {kw}  ({time.time()-t0:.1f}s)")
+    print(f"PIN OK  {name:10s} {kw} {dissipation or ''}  ({time.time()-t0:.1f}s)")
 
 
 if __name__ == "__main__":
@@ -60,3 +71,7 @@ if __name__ == "__main__":
     check("tgv", cells=(16, 16, 16), nsteps=2)
     check("tgv", cells=(12, 16, 20), bc="PERIODIC", nsteps=2)
     check("tgv", cells=(16, 16, 16), bc="PERIODIC", recon="PRIMITIVE", riemann="RUSANOV", nsteps=2)
+    check("tgv", cells=(12, 12, 12), nsteps=2, dissipation=dict(mu=1 / 160, prandtl=0.71))
+    check("tgv", cells=(10, 12, 14), bc="PERIODIC", nsteps=2, dissipation=dict(mu=1 / 100, bulk=0.002, kappa=0.05))
+    check("riemann2d", cells=(20, 24, None), nsteps=2, dissipation=dict(mu=1e-3))
+    check("sod", cells=(80, None, None), nsteps=2, dissipation=dict(mu=2e-3, prandtl=0.7))

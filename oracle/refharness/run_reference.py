@@ -151,13 +151,20 @@ class ReferenceRun:
         nhx, nhy, nhz = di.domain_slices_conservatives
         return a[..., nhx, nhy, nhz]
 
+    def default_ml_setup(self):
+        """The (empty) MachineLearningSetup the reference builds from simulate()'s defaults
+        (simulation_manager.py:189-190, :582)."""
+        from jaxfluids.data_types.ml_buffers import CallablesSetup, ParametersSetup, combine_callables_and_params
+        return combine_callables_and_params(CallablesSetup(), ParametersSetup())
+
     def compute_rhs(self, prims=None, cons=None):
         """One SpaceSolver.compute_rhs evaluation on the current (or given) state."""
         mf = self.material_fields
         prims = mf.primitives if prims is None else prims
         cons = mf.conservatives if cons is None else cons
         save, self._cur = self._cur, None
-        out = self.sim.space_solver.compute_rhs(cons, prims, None, 0.0, self.dt)
+        out = self.sim.space_solver.compute_rhs(cons, prims, mf.temperature, 0.0, self.dt,
+                                                ml_setup=self.default_ml_setup())
         self._cur = save
         return self.np.array(out[0].euler_buffers.conservatives)
 
@@ -167,7 +174,9 @@ class ReferenceRun:
         rec = {"dt_used": float(tcv.physical_timestep_size), "rhs": [], "prims": [], "cons": []}
         self._cur = rec
         cfp = self.sim.compute_control_flow_params(tcv, self.buffers.step_information)
-        self.buffers, _ = self.sim._do_integration_step(self.buffers, cfp, None, None)
+        # the defaults SimulationManager.simulate passes (simulation_manager.py:189-190)
+        from jaxfluids.data_types.ml_buffers import CallablesSetup, ParametersSetup
+        self.buffers, _ = self.sim._do_integration_step(self.buffers, cfp, ParametersSetup(), CallablesSetup())
         self._cur = None
         tcv = self.buffers.time_control_variables
         rec["dt_next"] = float(tcv.physical_timestep_size)

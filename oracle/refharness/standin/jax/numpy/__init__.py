@@ -81,6 +81,16 @@ class ndarray(_np.ndarray):
     def __setitem__(self, k, v):
         raise TypeError("stand-in jax arrays are immutable; use .at[].set()")
 
+    # `array != None` / `array == None` are plain identity tests for a jax.Array (the reference uses them,
+    # e.g. halos/outer/material.py:305); NumPy would broadcast them elementwise
+    def __ne__(self, o):
+        return True if o is None else _np.ndarray.__ne__(self, o)
+
+    def __eq__(self, o):
+        return False if o is None else _np.ndarray.__eq__(self, o)
+
+    __hash__ = None
+
 
 def _wrap(x):
     if isinstance(x, _np.ndarray) and not isinstance(x, ndarray):

@@ -16,8 +16,12 @@ TOL_PRIMS_100 = 1e-9   # primitives after 100 steps, relative L-inf
 TOL_TOTALS = 1e-12     # conserved totals
 
 
-def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+def golden_names(dissipative=None):
+    """All fixtures; dissipative=False/True keeps only the convective-only / the viscous+heat ones."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    if dissipative is None:
+        return names
+    return [n for n in names if ("visc" in n) == bool(dissipative)]
 
 
 def load_golden(name):
@@ -25,6 +29,23 @@ def load_golden(name):
     case = json.loads(str(g["case_json"]))
     num = json.loads(str(g["num_json"]))
     return g, case, num
+
+
+def dissipation_from_json(case, num) -> dict:
+    """active_physics + material_properties/transport -> the oracle Setup's dissipative-flux fields."""
+    ap = num.get("active_physics", {})
+    if not (ap.get("is_viscous_flux") or ap.get("is_heat_flux")):
+        return {}
+    tr = case["material_properties"].get("transport", {}) or {}
+    mu = tr.get("dynamic_viscosity", {}) or {}
+    tc = tr.get("thermal_conductivity", {}) or {}
+    return dict(is_viscous_flux=bool(ap.get("is_viscous_flux")), is_heat_flux=bool(ap.get("is_heat_flux")),
+                is_viscous_heat_production=bool(ap.get("is_viscous_heat_production", True)),
+                dynamic_viscosity=float(mu.get("value", 0.0)), bulk_viscosity=float(tr.get("bulk_viscosity", 0.0)),
+                thermal_conductivity_model=tc.get("model", "CUSTOM"),
+                thermal_conductivity=float(tc.get("value", 0.0) or 0.0),
+                prandtl_number=float(tc.get("prandtl_number", 1.0) or 1.0),
+                gas_constant=float(case["material_properties"]["equation_of_state"]["specific_gas_constant"]))
 
 
 def setup_from_json(case, num) -> port.Setup:
@@ -41,6 +62,7 @@ def setup_from_json(case, num) -> port.Setup:
         riemann=g.get("riemann_solver", "HLLC"),
         integrator=c["time_integration"]["integrator"],
         cfl=c["time_integration"].get("CFL", 0.5),
+        **dissipation_from_json(case, num),
     )
 
 

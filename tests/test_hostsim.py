@@ -21,7 +21,7 @@ def total_rhs(prims, s, fma, reference_order=False):
     return tot
 
 
-@pytest.mark.parametrize("name", H.golden_names())
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
 def test_device_functions_without_fma_are_bit_identical_to_reference(name):
     g, case, num = H.load_golden(name)
     s = H.setup_from_json(case, num)
@@ -31,7 +31,7 @@ def test_device_functions_without_fma_are_bit_identical_to_reference(name):
 
 
 @pytest.mark.parametrize("reference_order", [True, False])
-@pytest.mark.parametrize("name", H.golden_names())
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
 def test_device_functions_with_fma_within_tolerance(name, reference_order):
     """Both evaluations (reference order / production re-association), FMA-contracted, every stage of
     the first step of every reference fixture."""
@@ -55,7 +55,7 @@ def test_cancelled_total_norm_measures_conditioning_not_implementation():
     assert H.rel_linf(a, b, scale=H.rhs_scales(g["prims0_halo"], s)) < 1e-12
 
 
-@pytest.mark.parametrize("name", H.golden_names())
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
 def test_marching_variant_with_carried_weights(name):
     """sweep_strided's face_flux_carry (cell-centred weights of the as-is fields carried between
     consecutive faces) against the reference fixtures, every axis."""

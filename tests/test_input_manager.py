@@ -74,7 +74,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
     (("conservatives", "time_integration", "integrator"), "RK2_LS4"),
-    (("active_physics", "is_viscous_flux"), True),
+    (("active_physics", "is_volume_force"), True),
     (("precision", "is_double_precision_compute"), False),
 ])
 def test_valid_reference_options_outside_the_path_raise_not_implemented(path, value):
@@ -93,6 +93,32 @@ def test_invalid_values_fail_the_reference_consistency_assertion(path, value):
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     with pytest.raises(AssertionError, match="Consistency error in numerical setup file"):
         InputManager(case, _mod(num, path, value))
+
+
+def test_dissipative_setup_is_read_like_the_reference():
+    """active_physics + dissipative_fluxes + material_properties/transport (read_conservatives.py:374-440,
+    read_material_manager.py:200-330)."""
+    case, num = SETUPS["tgv12_sym_visc_prandtl_rk3"]
+    im = InputManager(case, num)
+    ap = im.numerical_setup.active_physics
+    assert ap.is_viscous_flux and ap.is_heat_flux and ap.is_viscous_heat_production
+    df = im.numerical_setup.conservatives.dissipative_fluxes
+    assert (df.reconstruction_stencil, df.derivative_stencil_center, df.derivative_stencil_face) == ("CENTRAL4",) * 3
+    tr = im.case_setup.material_setup.transport
+    assert tr.dynamic_viscosity == 1 / 160 and tr.thermal_conductivity_model == "PRANDTL" and tr.prandtl_number == 0.71
+    # valid reference options this path does not implement
+    with pytest.raises(NotImplementedError, match="B200 path"):
+        InputManager(case, _mod(num, ("conservatives", "dissipative_fluxes", "reconstruction_stencil"), "CENTRAL6"))
+    with pytest.raises(NotImplementedError, match="B200 path"):
+        InputManager(case, _mod(num, ("conservatives", "dissipative_fluxes", "is_laplacian"), True))
+    with pytest.raises(NotImplementedError, match="B200 path"):
+        InputManager(_mod(case, ("material_properties", "transport", "dynamic_viscosity"),
+                          {"model": "SUTHERLAND", "sutherland_parameters": [1.7e-5, 273.0, 110.4]}), num)
+    # missing transport block with the viscous flux on: the reference's "not optional" assertion
+    bad = copy.deepcopy(case)
+    del bad["material_properties"]["transport"]
+    with pytest.raises(AssertionError, match="Consistency error in case setup file"):
+        InputManager(bad, num)
 
 
 def test_case_errors():

@@ -14,6 +14,11 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("riemann2d", dict(cells=(20, 28, None)), 2),
     ("tgv", dict(cells=(12, 12, 12)), 1),
     ("tgv", dict(cells=(10, 12, 14), bc="PERIODIC", recon="PRIMITIVE"), 1),
+    # viscous + heat flux, edge halos (SYMMETRY mirror / PERIODIC copy / ANY_ANY mean)
+    ("tgv", dict(cells=(10, 10, 12), dissipation=dict(mu=1 / 160, prandtl=0.71)), 1),
+    ("tgv", dict(cells=(8, 10, 12), bc="PERIODIC", dissipation=dict(mu=0.01, bulk=0.002, kappa=0.05)), 1),
+    ("riemann2d", dict(cells=(16, 20, None), dissipation=dict(mu=1e-3, kappa=1e-3)), 2),
+    ("sod", dict(cells=(64, None, None), dissipation=dict(mu=2e-3, prandtl=0.7)), 2),
 ])
 def test_port_is_bit_identical_to_reference(name, kw, nsteps):
     from oracle.refharness import pin_check
