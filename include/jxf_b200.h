@@ -55,6 +55,16 @@ typedef struct jxf_config {
   int32_t signal_speed;  /* JXF_SIGNAL_*                                                         */
   int32_t integrator;    /* JXF_INT_*                                                            */
   int32_t bc[6];         /* JXF_BC_* per face, order east,west,north,south,top,bottom            */
+  /* dissipative fluxes (ref: active_physics is_viscous_flux / is_heat_flux / is_viscous_heat_production,
+   * conservatives/dissipative_fluxes = CENTRAL4 x3, material_properties/transport; source_term_solver.py:188-345) */
+  int32_t viscous_flux;             /* 0/1                                                        */
+  int32_t heat_flux;                /* 0/1                                                        */
+  int32_t viscous_heat_production;  /* 0/1: u.tau in the energy flux (default 1)                  */
+  int32_t reserved0;
+  double  dynamic_viscosity;        /* transport/dynamic_viscosity, model CUSTOM (constant)       */
+  double  bulk_viscosity;           /* transport/bulk_viscosity                                   */
+  double  thermal_conductivity;     /* constant lambda: CUSTOM value, or cp*mu/Pr for PRANDTL     */
+  double  gas_constant;             /* equation_of_state/specific_gas_constant (T = p/(rho R))    */
 } jxf_config;
 
 typedef struct jxf_solver* jxf_handle;
@@ -127,8 +137,28 @@ int jxf_step_fused(jxf_handle h, double* prims_a, double* prims_b, double* cons_
 
 /* ref: HaloManager.perform_halo_update_material (halos/halo_manager.py:146-234) for
  * PERIODIC / SYMMETRY / ZEROGRADIENT faces (halos/outer/material.py:868-894); cons halos are
- * recomputed from prim halos (:248-250).  Faces marked JXF_BC_NEIGHBOR are skipped. In place. */
+ * recomputed from prim halos (:248-250).  Faces marked JXF_BC_NEIGHBOR are skipped. In place.
+ * With the viscous or heat flux active the EDGE halos are filled too (halo_manager.py:119-129,
+ * :193-199 -> jxf_halo_fill_edges). */
 int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream);
+
+/* ref: BoundaryConditionMaterial.edge_halo_update / compute_edge_halos (halos/outer/material.py:289-383)
+ * with the type combination of boundary_condition.py:128-179 and the retrieve table :607-655: per edge
+ * (pair of faces) the FIRST face that is PERIODIC or SYMMETRY decides -- PERIODIC: copy across the
+ * domain, SYMMETRY: mirror and negate that face's normal velocity -- otherwise the mean of the two
+ * adjacent halo regions; cons recomputed.  Needs the face halos filled.  In place. */
+int jxf_halo_fill_edges(jxf_handle h, double* prims, double* cons, void* stream);
+
+/* ref: SourceTermSolver.compute_viscous_flux_xi + compute_heat_flux_xi (solvers/source_term_solver.py:188-345,
+ * :405-470, :503-582; CENTRAL4 stencils/derivative/deriv_face_4.py, deriv_center_4.py,
+ * stencils/reconstruction/central/central_4.py) folded into the flux divergence as
+ * space_solver.py:567-599 does: rhs (+)= (1/dx) (Fd_{i-1/2} - Fd_{i+1/2}), Fd = (0, -tau, -u.tau + q).
+ * accumulate=0 writes (mass row = 0), accumulate=1 adds.  Needs face AND edge halos of prims. */
+int jxf_dissipative_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream);
+
+/* ref: MaterialManager.get_temperature -> IdealGas.get_temperature (ideal_gas.py:64-65): T = p/(rho R) on
+ * the whole halo'd buffer; temperature: (X, Y, Z) doubles. */
+int jxf_temperature(jxf_handle h, const double* prims, double* temperature, void* stream);
 
 /* ref: EquationManager.get_primitives_from_conservatives / get_conservatives_from_primitives
  * (equation_manager.py:164-171, 93-101) over the whole halo'd buffer. */
@@ -139,7 +169,9 @@ int jxf_cons_from_prims(jxf_handle h, const double* prims, double* cons, void* s
  * logging reductions (solvers/positivity/positivity_handler.py:245-254).
  * jxf_reduce      : red_dev <- combine(red_dev, reductions over the interior of prims)
  * jxf_reduce_reset: red_dev <- {0, +inf, +inf}
- * jxf_finish_step : dt_dev <- CFL*dx_min/(red[0]+eps) (or fixed_dt); time_dev += dt_used;
+ * jxf_finish_step : dt_dev <- CFL*min(dx_min/(red[0]+eps), 3/14 dx^2/(max nu+eps), 0.1 dx^2/(max alpha+eps))
+ *                   (diffusive limits only with the viscous / heat flux, time_step_size.py:111-135; or
+ *                   fixed_dt); time_dev += dt_used;
  *                   info_dev[0..2] <- red; red_dev reset.  All on device, no host sync. */
 int jxf_reduce(jxf_handle h, const double* prims, double* red_dev, void* stream);
 int jxf_reduce_reset(jxf_handle h, double* red_dev, void* stream);
@@ -165,14 +197,16 @@ int jxf_unpack_face(jxf_handle h, int face, const double* slab, double* prims, d
 
 /* Launch accounting and optional per-kernel timing (bench / roofline evidence).
  * Kinds: 0..2 = sweep along axis 0..2 writing rhs; 3..5 = sweep along axis 0..2 with the fused
- * RK-stage epilogue; 6 = halo fill; 7 = other (transforms, reductions, pack/unpack).
+ * RK-stage epilogue; 6 = halo fill; 7 = other (transforms, reductions, pack/unpack); 8 = dissipative
+ * (viscous + heat flux) sweeps.
  * With profiling enabled every launch is bracketed by cudaEventRecord on the launch stream
  * (up to 4096 launches between reads).  jxf_profile_read synchronises on the recorded events and
  * returns, per kind, the summed device time in ms, the number of timed launches and the number of
  * launches issued since the last reset. */
-#define JXF_PROFILE_KINDS 8
+#define JXF_PROFILE_KINDS 9
 #define JXF_PROFILE_HALO 6
 #define JXF_PROFILE_OTHER 7
+#define JXF_PROFILE_DISSIPATIVE 8
 int jxf_profile_enable(jxf_handle h, int enable);
 int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* launches, int reset);
 

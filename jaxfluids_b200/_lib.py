@@ -17,7 +17,7 @@ EXPORTS = (
     "jxf_last_error", "jxf_version", "jxf_create", "jxf_destroy", "jxf_field_elems", "jxf_rhs_elems",
     "jxf_num_stages", "jxf_compute_rhs", "jxf_sweep", "jxf_stage", "jxf_halo_fill", "jxf_prims_from_cons",
     "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
-    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage",
+    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature",
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
@@ -42,6 +42,14 @@ class JxfConfig(C.Structure):
         ("signal_speed", C.c_int32),
         ("integrator", C.c_int32),
         ("bc", C.c_int32 * 6),
+        ("viscous_flux", C.c_int32),
+        ("heat_flux", C.c_int32),
+        ("viscous_heat_production", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("dynamic_viscosity", C.c_double),
+        ("bulk_viscosity", C.c_double),
+        ("thermal_conductivity", C.c_double),
+        ("gas_constant", C.c_double),
     ]
 
 
@@ -117,6 +125,12 @@ def load():
     lib.jxf_sweep_range.argtypes = [vp, i32, i32, i32, dp, dp, i32, vp]
     lib.jxf_integrate_stage.restype = i32
     lib.jxf_integrate_stage.argtypes = [vp, i32, dp, dp, dp, C.c_double, dp, vp]
+    lib.jxf_halo_fill_edges.restype = i32
+    lib.jxf_halo_fill_edges.argtypes = [vp, dp, dp, vp]
+    lib.jxf_dissipative_sweep.restype = i32
+    lib.jxf_dissipative_sweep.argtypes = [vp, i32, dp, dp, i32, vp]
+    lib.jxf_temperature.restype = i32
+    lib.jxf_temperature.argtypes = [vp, dp, dp, vp]
     lib.jxf_debug_math.restype = i32
     lib.jxf_debug_math.argtypes = [dp, i64, dp, vp]
     lib.jxf_debug_face_flux.restype = i32

@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "jxf_b200.cu")]
-DEPS = [os.path.join(HERE, "csrc", "numerics.cuh"), os.path.join(os.path.dirname(HERE), "include", "jxf_b200.h")]
+DEPS = [os.path.join(HERE, "csrc", "numerics.cuh"), os.path.join(HERE, "csrc", "dissipative.cuh"), os.path.join(os.path.dirname(HERE), "include", "jxf_b200.h")]
 OUT = os.path.join(HERE, "lib", "libjxf_b200.so")
 
 NVCC_FLAGS = [

@@ -1,0 +1,326 @@
+// dissipative.cuh -- viscous + heat flux of the single-phase path (included by jxf_b200.cu).
+//
+// ref (file:line under /root/reference/src/jaxfluids/):
+//   solvers/source_term_solver.py:188-250 (heat flux), :258-345 (viscous flux), :405-470 (velocity
+//   gradient at faces), :503-533 (tau), :535-582 (d/dx_i at the faces of axis j);
+//   stencils/derivative/deriv_face_4.py, deriv_center_4.py, stencils/reconstruction/central/central_4.py;
+//   solvers/space_solver.py:567-599 (folded into the face flux before the divergence);
+//   halos/outer/material.py:289-383 + boundary_condition.py:128-179, :607-655 (edge halos).
+//
+// Face flux of axis A between cells i and i+1, from the four cells i-1..i+2 along A:
+//   d u_c / d x_A        : 1/dx (1/24 (u_{i-1} - u_{i+2}) + 27/24 (u_{i+1} - u_i))          (face derivative)
+//   d u_c / d x_t, t != A: central_4 reconstruction along A of the CELL-CENTRE derivative
+//                          1/dx_t (1/12 (u_{-2} - u_{+2}) + 8/12 (u_{+1} - u_{-1})) taken along t
+//   tau_k = mu (du_A/dx_k + du_k/dx_A),  tau_A += (bulk - 2/3 mu) div u,  u.tau with central_4 face velocities,
+//   q = -lambda dT/dx_A (face derivative), T = p / (rho R).
+// mu, bulk, lambda are constants here (transport model CUSTOM with float values, PRANDTL with a CUSTOM
+// viscosity), so the reference's T-at-face reconstruction only feeds constants and is not evaluated.
+//
+// Two kernels, the same split as the convective sweeps:
+//   visc_march<A>: A is NOT the contiguous axis.  Thread = one column, lanes along the contiguous axis,
+//       marching along A with a rolling 4-cell window of {u, v, w, T, six transverse cell-centre
+//       derivatives}; every cell's derivatives and every face flux are computed once.
+//   visc_rows<A>:  A IS the contiguous axis.  CTA = one row segment, thread = one cell: each thread forms
+//       its cell's data, the four-cell stencils and the flux differences go through shared memory.
+// Both are streaming kernels bound by HBM: 40 B/cell of primitives in + 32 B/cell rhs in/out.
+#pragma once
+
+namespace jxf {
+
+#ifdef JXF_REFERENCE_ORDER
+__device__ __forceinline__ double visc_rcp(double a) { return 1.0 / a; }
+#else
+__device__ __forceinline__ double visc_rcp(double a) { return rcp_fast(a); }
+#endif
+
+struct ViscArgs {
+  const double* prims;
+  double* rhs;
+  double mu1, mu2;          // mu, bulk - 2/3 mu
+  double lambda;            // thermal conductivity
+  double gas_constant;
+  double inv_dxA, inv_dx1, inv_dx2;   // 1/dx of the three ROLE axes (A, 1, 2)
+  int visc, heat, heat_prod;
+  int active_mask;          // bit i = physical axis i active
+  int accumulate;
+  int chunk_len;            // march: cells per chunk along A
+  int seg_len;              // rows: cells per CTA along A
+};
+
+struct VCell {
+  double u[3];
+  double T;
+  double d1[3];             // d u_c / d x_(role 1) at the cell centre
+  double d2[3];             // d u_c / d x_(role 2)
+};
+
+// cell-centre data of the cell at element offset `idx` (relative to the interior origin)
+__device__ __forceinline__ void load_vcell(const SweepGeom& g, const ViscArgs& a, long long idx, VCell& c) {
+  const double* p = a.prims + idx;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.u[k] = p[(1 + k) * g.vst];
+  c.T = 0.0;
+  if (a.heat) c.T = p[4 * g.vst] * visc_rcp(p[0] * a.gas_constant);
+  constexpr double c0 = 1.0 / 12.0, c1 = 8.0 / 12.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    c.d1[k] = 0.0;
+    c.d2[k] = 0.0;
+  }
+  if (a.visc) {
+    if (g.n1 > 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double* q = p + (1 + k) * g.vst;
+        c.d1[k] = a.inv_dx1 * fma(c1, q[g.s1] - q[-g.s1], c0 * (q[-2 * g.s1] - q[2 * g.s1]));
+      }
+    }
+    if (g.n2 > 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double* q = p + (1 + k) * g.vst;
+        c.d2[k] = a.inv_dx2 * fma(c1, q[g.s2] - q[-g.s2], c0 * (q[-2 * g.s2] - q[2 * g.s2]));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double central4(double a, double b, double c, double d) {
+  return fma(9.0 / 16.0, b + c, (-1.0 / 16.0) * (a + d));
+}
+__device__ __forceinline__ double dface4(double a, double b, double c, double d) {
+  return fma(27.0 / 24.0, c - b, (1.0 / 24.0) * (a - d));
+}
+
+// dissipative part of the face flux, components (momentum x, y, z, energy), sign as it enters the
+// convective flux: Fd = (-tau, -u.tau + q)
+template <int A>
+__device__ __forceinline__ void dissipative_face_flux(const SweepGeom& g, const ViscArgs& a, const VCell& c0,
+                                                      const VCell& c1, const VCell& c2, const VCell& c3,
+                                                      double (&F)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) F[k] = 0.0;
+  if (a.visc) {
+    // vg[c][i] = d u_c / d x_i at the face; i indexes PHYSICAL axes
+    double vg[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) vg[k][i] = 0.0;
+      vg[k][A] = a.inv_dxA * dface4(c0.u[k], c1.u[k], c2.u[k], c3.u[k]);
+      const double t1 = central4(c0.d1[k], c1.d1[k], c2.d1[k], c3.d1[k]);
+      const double t2 = central4(c0.d2[k], c1.d2[k], c2.d2[k], c3.d2[k]);
+      // roles -> physical axes are compile-time for a given A and lane axis layout, but the role table
+      // is in g: ax1/ax2 are uniform, so these selects are cheap
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i != A) vg[k][i] = (i == g.ax1) ? t1 : ((i == g.ax2) ? t2 : 0.0);
+      }
+    }
+    const bool act[3] = {(a.active_mask & 1) != 0, (a.active_mask & 2) != 0, (a.active_mask & 4) != 0};
+    double tau[3];
+    double div = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tau[k] = act[k] ? a.mu1 * (vg[A][k] + vg[k][A]) : 0.0;
+      if (act[k]) div += vg[k][k];
+    }
+    tau[A] = fma(a.mu2, div, tau[A]);
+    double vt = 0.0;
+    if (a.heat_prod) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (act[k]) vt = fma(tau[k], central4(c0.u[k], c1.u[k], c2.u[k], c3.u[k]), vt);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) F[k] = -tau[k];
+    F[3] = -vt;
+  }
+  if (a.heat) F[3] = fma(-a.lambda, a.inv_dxA * dface4(c0.T, c1.T, c2.T, c3.T), F[3]);
+}
+
+__device__ __forceinline__ void dissipative_update(const SweepGeom& g, const ViscArgs& a, long long ridx,
+                                                   const double (&Flo)[4], const double (&Fhi)[4]) {
+  if (!a.accumulate) a.rhs[ridx] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double* r = a.rhs + ridx + (1 + k) * g.rvst;
+    const double d = Flo[k] - Fhi[k];
+    *r = a.accumulate ? fma(a.inv_dxA, d, *r) : a.inv_dxA * d;
+  }
+}
+
+template <int A>
+__global__ void __launch_bounds__(128) visc_march(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
+  const long long plane = (long long)g.n1 * g.n2;
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= plane) return;
+  const int i1 = (int)(p / g.n2);
+  const int i2 = (int)(p - (long long)i1 * g.n2);
+  const int f0 = blockIdx.y * a.chunk_len;
+  const int f1 = min(f0 + a.chunk_len, g.nA);
+  const long long col_h = i1 * g.s1 + i2 * g.s2;
+  const long long col_r = i1 * g.r1 + i2 * g.r2;
+  VCell c0, c1, c2, c3;
+  load_vcell(g, a, col_h + (long long)(f0 - 2) * g.sA, c0);
+  load_vcell(g, a, col_h + (long long)(f0 - 1) * g.sA, c1);
+  load_vcell(g, a, col_h + (long long)f0 * g.sA, c2);
+  double Fp[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int f = f0; f <= f1; ++f) {
+    load_vcell(g, a, col_h + (long long)(f + 1) * g.sA, c3);      // cell f+1 <= n+1 < n+nh
+    double F[4];
+    dissipative_face_flux<A>(g, a, c0, c1, c2, c3, F);
+    if (f > f0) dissipative_update(g, a, col_r + (long long)(f - 1) * g.rA, Fp, F);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Fp[k] = F[k];
+    c0 = c1;
+    c1 = c2;
+    c2 = c3;
+  }
+}
+
+// shared layout: 10 cell quantities + 4 flux components, each blockDim doubles
+template <int A>
+__global__ void __launch_bounds__(1024) visc_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
+  extern __shared__ double vs[];
+  const int B = blockDim.x;
+  const int tid = threadIdx.x;
+  const long long row = blockIdx.x;
+  const int i1 = (int)(row / g.n2);
+  const int i2 = (int)(row - (long long)i1 * g.n2);
+  const int s0 = blockIdx.y * a.seg_len;                 // first cell of this segment
+  const int L = min(a.seg_len, g.nA - s0);               // cells in this segment
+  const long long col_h = i1 * g.s1 + i2 * g.s2;
+  const long long col_r = i1 * g.r1 + i2 * g.r2;
+  const int k = s0 - 2 + tid;                            // this thread's cell
+  if (tid < L + 4) {
+    VCell c;
+    load_vcell(g, a, col_h + (long long)k * g.sA, c);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      vs[q * B + tid] = c.u[q];
+      vs[(4 + q) * B + tid] = c.d1[q];
+      vs[(7 + q) * B + tid] = c.d2[q];
+    }
+    vs[3 * B + tid] = c.T;
+  }
+  __syncthreads();
+  double* fl = vs + 10 * B;
+  if (tid >= 1 && tid <= L + 1) {                        // face between cells k and k+1
+    VCell c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = tid - 1 + j;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        c[j].u[q] = vs[q * B + t];
+        c[j].d1[q] = vs[(4 + q) * B + t];
+        c[j].d2[q] = vs[(7 + q) * B + t];
+      }
+      c[j].T = vs[3 * B + t];
+    }
+    double F[4];
+    dissipative_face_flux<A>(g, a, c[0], c[1], c[2], c[3], F);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fl[q * B + tid] = F[q];
+  }
+  __syncthreads();
+  if (tid >= 2 && tid <= L + 1) {                        // cell k = s0 + tid - 2: faces computed by tid-1 (low) and tid (high)
+    double Flo[4], Fhi[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Flo[q] = fl[q * B + tid - 1];
+      Fhi[q] = fl[q * B + tid];
+    }
+    dissipative_update(g, a, col_r + (long long)k * g.rA, Flo, Fhi);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// edge halos (halos/outer/material.py:289-383)
+// ---------------------------------------------------------------------------
+struct EdgeArgs {
+  double* prims;
+  double* cons;
+  double gamma;
+  int bc[6];
+};
+
+// faces of the 12 edges in the reference's order (domain/__init__.py:9-15), as face ids
+// (east 0, west 1, north 2, south 3, top 4, bottom 5)
+__constant__ int kEdgeFaces[12][2] = {{1, 3}, {1, 2}, {0, 2}, {0, 3}, {3, 5}, {2, 5},
+                                      {3, 4}, {2, 4}, {0, 5}, {1, 5}, {0, 4}, {1, 4}};
+
+__device__ __forceinline__ int edge_src_index(int kind, bool hi, int l, int nh, int ext) {
+  // buffer index along one axis of the edge for halo layer l (in increasing buffer index):
+  //   kind 0: the halo itself; 1: adjacent interior layers, same order ("_1" slices, halo_slices.py:98-147);
+  //   2: PERIODIC, the interior layers next to the OPPOSITE face; 3: SYMMETRY, adjacent layers mirrored
+  switch (kind) {
+    case 0: return hi ? ext - nh + l : l;
+    case 1: return hi ? ext - 2 * nh + l : nh + l;
+    case 2: return hi ? nh + l : ext - 2 * nh + l;
+    default: return hi ? ext - nh - 1 - l : 2 * nh - 1 - l;
+  }
+}
+
+__global__ void __launch_bounds__(128) halo_fill_edges_kernel(const Geom g, const EdgeArgs a) {
+  const int e = blockIdx.y;
+  const int fa = kEdgeFaces[e][0], fb = kEdgeFaces[e][1];
+  const int axa = fa >> 1, axb = fb >> 1;
+  if (g.n[axa] <= 1 || g.n[axb] <= 1) return;
+  const int ta = a.bc[fa], tb = a.bc[fb];
+  if (ta == JXF_BC_NEIGHBOR || tb == JXF_BC_NEIGHBOR) return;      // inter-block edges: not handled here
+  const int axr = 3 - axa - axb;                                     // running axis
+  const int nr = g.n[axr], nh = g.nh;
+  const bool hia = (fa & 1) == 0, hib = (fb & 1) == 0;
+  // boundary_condition.py:128-179: the first PERIODIC / SYMMETRY face decides
+  int which = -1;   // 0: face a decides, 1: face b decides, -1: ANY_ANY
+  if (ta == JXF_BC_PERIODIC || ta == JXF_BC_SYMMETRY) which = 0;
+  else if (tb == JXF_BC_PERIODIC || tb == JXF_BC_SYMMETRY) which = 1;
+  const int tdec = which == 0 ? ta : tb;
+  const long long total = (long long)nh * nh * nr;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int ir = (int)(q % nr);
+    const long long q1 = q / nr;
+    const int lb = (int)(q1 % nh);
+    const int la = (int)(q1 / nh);
+    const long long run = (long long)(ir + g.off[axr]) * g.st[axr];
+    const long long dst = run + (long long)edge_src_index(0, hia, la, nh, g.ext[axa]) * g.st[axa] +
+                          (long long)edge_src_index(0, hib, lb, nh, g.ext[axb]) * g.st[axb];
+    double p[5];
+    if (which < 0) {
+      const long long s1 = run + (long long)edge_src_index(1, hia, la, nh, g.ext[axa]) * g.st[axa] +
+                           (long long)edge_src_index(0, hib, lb, nh, g.ext[axb]) * g.st[axb];
+      const long long s2 = run + (long long)edge_src_index(0, hia, la, nh, g.ext[axa]) * g.st[axa] +
+                           (long long)edge_src_index(1, hib, lb, nh, g.ext[axb]) * g.st[axb];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) p[v] = 0.5 * (a.prims[s1 + v * g.vst] + a.prims[s2 + v * g.vst]);
+    } else {
+      const int kind = (tdec == JXF_BC_PERIODIC) ? 2 : 3;
+      const int ka = which == 0 ? kind : 0, kb = which == 1 ? kind : 0;
+      const long long s = run + (long long)edge_src_index(ka, hia, la, nh, g.ext[axa]) * g.st[axa] +
+                          (long long)edge_src_index(kb, hib, lb, nh, g.ext[axb]) * g.st[axb];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) p[v] = a.prims[s + v * g.vst];
+      if (tdec == JXF_BC_SYMMETRY) {
+        const int ax = which == 0 ? axa : axb;
+        p[1 + ax] = p[1 + ax] * -1.0;
+      }
+    }
+    double c[5];
+    cons_from_prims(p, a.gamma, c);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      a.prims[dst + v * g.vst] = p[v];
+      if (a.cons) a.cons[dst + v * g.vst] = c[v];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) temperature_kernel(const double* __restrict__ prims, double* __restrict__ T,
+                                                          long long vst, double gas_constant) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vst; i += (long long)gridDim.x * blockDim.x)
+    T[i] = prims[i + 4 * vst] / (prims[i] * gas_constant);
+}
+
+}  // namespace jxf

@@ -839,9 +839,17 @@ __global__ void reduce_reset_kernel(double* red) {
   red[2] = red[1];
 }
 
-// time_step_size.py:103-109,154-155: dt = dx_min / (max + eps); dt *= CFL
+// time_step_size.py:103-109,154-155: dt = dx_min / (max + eps); dt *= CFL.  With the viscous / heat flux
+// (:111-135): dt = min(dt, 3/14 dx^2 / (max nu + eps), 0.1 dx^2 / (max alpha + eps)), nu = mu / rho,
+// alpha = lambda / (rho cp).  mu and lambda are constants on this path and x -> fl(mu / x), x -> fl(lambda /
+// fl(x cp)) are monotone, so the maxima over the cells are attained at the minimum density red[1], bit for bit.
+struct DtLimits {
+  int visc, heat;
+  double mu, lambda, cp;
+};
+
 __global__ void finish_step_kernel(double* red, double* dt, double* time, double* info, double dx_min, double cfl,
-                                   double fixed_dt) {
+                                   double fixed_dt, DtLimits lim) {
   const double dt_used = *dt;
   if (time) *time += dt_used;
   if (info) {
@@ -853,6 +861,9 @@ __global__ void finish_step_kernel(double* red, double* dt, double* time, double
     *dt = fixed_dt;
   } else {
     double d = dx_min / (red[0] + kEps);
+    const double dx2 = dx_min * dx_min;
+    if (lim.visc) d = fmin(d, (3.0 / 14.0) * dx2 / (lim.mu / red[1] + kEps));
+    if (lim.heat) d = fmin(d, 0.1 * dx2 / (lim.lambda / (red[1] * lim.cp) + kEps));
     d *= cfl;
     *dt = d;
   }
@@ -952,6 +963,8 @@ __global__ void __launch_bounds__(128) face_flux_debug_kernel(const double* __re
 
 }  // namespace jxf
 
+#include "dissipative.cuh"
+
 // ===========================================================================
 // host side: plan + C ABI
 // ===========================================================================
@@ -1020,7 +1033,7 @@ struct ProfScope {
 };
 
 extern "C" const char* jxf_last_error(void) { return g_err; }
-extern "C" int jxf_version(void) { return 100; }
+extern "C" int jxf_version(void) { return 110; }
 
 extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   if (!cfg || !out) return fail(JXF_ERR_BAD_ARG, "jxf_create: null argument");
@@ -1036,6 +1049,12 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
   if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
+  if (cfg->viscous_flux || cfg->heat_flux) {
+    if (!(cfg->gas_constant > 0.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gas_constant=%g", cfg->gas_constant);
+    if (cfg->dynamic_viscosity < 0.0 || cfg->thermal_conductivity < 0.0)
+      return fail(JXF_ERR_BAD_ARG, "jxf_create: negative transport coefficient");
+    if (cfg->nh < 4) return fail(JXF_ERR_BAD_ARG, "jxf_create: the dissipative fluxes need halo_cells >= 4 (2 + 2)");
+  }
   jxf_solver* s = new (std::nothrow) jxf_solver;
   if (!s) return fail(JXF_ERR_BAD_ARG, "jxf_create: out of host memory");
   memset(s, 0, sizeof(*s));
@@ -1388,12 +1407,114 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   return a;
 }
 
+// ---------------------------------------------------------------------------
+// dissipative sweeps (dissipative.cuh)
+// ---------------------------------------------------------------------------
+static bool dissipative(const jxf_solver* s) { return s->cfg.viscous_flux || s->cfg.heat_flux; }
+
+template <int A>
+static int launch_dissipative(const jxf_solver* s, const double* prims, double* rhs, int accumulate, cudaStream_t st) {
+  const Geom& g = s->g;
+  const long long h0 = g.off[0] * g.st[0] + g.off[1] * g.st[1] + g.off[2] * g.st[2];
+  SweepGeom sg;
+  memset(&sg, 0, sizeof(sg));
+  sg.axA = A; sg.nA = g.n[A]; sg.sA = g.st[A]; sg.rA = g.rst[A];
+  sg.vst = g.vst; sg.rvst = g.rvst;
+  ViscArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prims = prims + h0;
+  a.rhs = rhs;
+  a.mu1 = s->cfg.dynamic_viscosity;
+  a.mu2 = s->cfg.bulk_viscosity - 2.0 / 3.0 * s->cfg.dynamic_viscosity;     // source_term_solver.py:524
+  a.lambda = s->cfg.thermal_conductivity;
+  a.gas_constant = s->cfg.gas_constant;
+  a.visc = s->cfg.viscous_flux;
+  a.heat = s->cfg.heat_flux;
+  a.heat_prod = s->cfg.viscous_heat_production;
+  a.active_mask = s->active_mask;
+  a.accumulate = accumulate ? 1 : 0;
+  a.inv_dxA = s->cfg.inv_dx[A];
+  ProfScope prof(s, JXF_PROFILE_DISSIPATIVE, st);
+  if (A != s->lane_axis) {
+    const int C = s->lane_axis, O = 3 - A - C;
+    sg.ax1 = O; sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
+    sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
+    a.inv_dx1 = s->cfg.inv_dx[O];
+    a.inv_dx2 = s->cfg.inv_dx[C];
+    const long long plane = (long long)sg.n1 * sg.n2;
+    const int bx = (int)((plane + 127) / 128);
+    // enough CTAs for ~8 per SM; every chunk re-reads a 3-cell prologue
+    int chunks = (int)std::min<long long>(std::max<long long>(1, (8LL * s->num_sms + bx - 1) / bx), std::max(1, g.n[A] / 16));
+    a.chunk_len = (g.n[A] + chunks - 1) / chunks;
+    chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
+    visc_march<A><<<dim3(bx, chunks), 128, 0, st>>>(sg, a);
+  } else {
+    const int T1 = (A == 0) ? 1 : 0, T2 = (A == 2) ? 1 : 2;
+    sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
+    sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    a.inv_dx1 = s->cfg.inv_dx[T1];
+    a.inv_dx2 = s->cfg.inv_dx[T2];
+    // one CTA per row segment of up to 1020 cells (+4 stencil cells = 1024 threads)
+    const int nseg = (g.n[A] + 1019) / 1020;
+    a.seg_len = (g.n[A] + nseg - 1) / nseg;
+    const int threads = ((a.seg_len + 4 + 31) / 32) * 32;
+    const long long rows = (long long)sg.n1 * sg.n2;
+    if (rows > 0x7fffffffLL) return fail(JXF_ERR_UNSUPPORTED, "dissipative sweep: too many rows");
+    visc_rows<A><<<dim3((unsigned)rows, nseg), threads, (size_t)threads * 14 * sizeof(double), st>>>(sg, a);
+  }
+  return check_launch("dissipative sweep");
+}
+
+static int dissipative_sweep(const jxf_solver* s, int axis, const double* prims, double* rhs, int accumulate, cudaStream_t st) {
+  switch (axis) {
+    case 0: return launch_dissipative<0>(s, prims, rhs, accumulate, st);
+    case 1: return launch_dissipative<1>(s, prims, rhs, accumulate, st);
+    default: return launch_dissipative<2>(s, prims, rhs, accumulate, st);
+  }
+}
+
+extern "C" int jxf_dissipative_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream) {
+  if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_dissipative_sweep: null argument");
+  if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_dissipative_sweep: axis %d is not active", axis);
+  if (!dissipative(h)) return fail(JXF_ERR_BAD_ARG, "jxf_dissipative_sweep: neither viscous nor heat flux is configured");
+  return dissipative_sweep(h, axis, prims, rhs, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int jxf_halo_fill_edges(jxf_handle h, double* prims, double* cons, void* stream) {
+  if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill_edges: null argument");
+  if (h->n_active < 2) return JXF_OK;
+  EdgeArgs a;
+  a.prims = prims;
+  a.cons = cons;
+  a.gamma = h->cfg.gamma;
+  int nmax = 1;
+  for (int f = 0; f < 6; ++f) a.bc[f] = (h->g.n[f >> 1] > 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
+  for (int i = 0; i < 3; ++i) nmax = std::max(nmax, h->g.n[i]);
+  const long long cells = (long long)h->g.nh * h->g.nh * nmax;
+  const int bx = (int)std::min<long long>((cells + 127) / 128, 148 * 4);
+  ProfScope prof(h, JXF_PROFILE_HALO, (cudaStream_t)stream);
+  halo_fill_edges_kernel<<<dim3(bx, 12), 128, 0, (cudaStream_t)stream>>>(h->g, a);
+  return check_launch("halo_fill_edges");
+}
+
+extern "C" int jxf_temperature(jxf_handle h, const double* prims, double* temperature, void* stream) {
+  if (!h || !prims || !temperature) return fail(JXF_ERR_BAD_ARG, "jxf_temperature: null argument");
+  if (!(h->cfg.gas_constant > 0.0)) return fail(JXF_ERR_BAD_ARG, "jxf_temperature: gas_constant not configured");
+  const int bx = (int)std::min<long long>((h->g.vst + 255) / 256, 148 * 8);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  temperature_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(prims, temperature, h->g.vst, h->cfg.gas_constant);
+  return check_launch("temperature");
+}
+
 extern "C" int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream) {
   if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: null argument");
   if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: axis %d is not active", axis);
   SweepArgs a = base_args(h, axis, prims, rhs);
   a.accumulate = accumulate ? 1 : 0;
-  return dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+  int rc = dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+  // compute_rhs_xi folds the axis' viscous / heat flux into the same divergence (space_solver.py:567-599)
+  if (rc == JXF_OK && dissipative(h)) rc = dissipative_sweep(h, axis, prims, rhs, 1, (cudaStream_t)stream);
+  return rc;
 }
 
 extern "C" int jxf_sweep_range(jxf_handle h, int axis, int lo, int hi, const double* prims, double* rhs, int accumulate,
@@ -1401,6 +1522,7 @@ extern "C" int jxf_sweep_range(jxf_handle h, int axis, int lo, int hi, const dou
   if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: null argument");
   if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: axis %d is not active", axis);
   if (lo < 0 || hi > h->g.n[axis] || lo >= hi) return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: bad range [%d, %d)", lo, hi);
+  if (dissipative(h)) return fail(JXF_ERR_UNSUPPORTED, "jxf_sweep_range: not available with the viscous / heat flux");
   if (axis == h->lane_axis) {
     if (lo != 0 || hi != h->g.n[axis])
       return fail(JXF_ERR_UNSUPPORTED, "jxf_sweep_range: partial ranges are not supported along the contiguous axis");
@@ -1437,11 +1559,15 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
     if (a.bc[f] != JXF_BC_INACTIVE && a.bc[f] != JXF_BC_NEIGHBOR)
       maxcells = std::max(maxcells, (long long)h->g.nh * h->g.n[t1] * h->g.n[t2]);
   }
-  if (maxcells == 0) return JXF_OK;
-  const int bx = (int)std::min<long long>((maxcells + 127) / 128, 148 * 16);
-  ProfScope prof(h, JXF_PROFILE_HALO, (cudaStream_t)stream);
-  halo_fill_kernel<<<dim3(bx, 6), 128, 0, (cudaStream_t)stream>>>(h->g, a);
-  return check_launch("halo_fill");
+  if (maxcells > 0) {
+    const int bx = (int)std::min<long long>((maxcells + 127) / 128, 148 * 16);
+    ProfScope prof(h, JXF_PROFILE_HALO, (cudaStream_t)stream);
+    halo_fill_kernel<<<dim3(bx, 6), 128, 0, (cudaStream_t)stream>>>(h->g, a);
+    int rc = check_launch("halo_fill");
+    if (rc) return rc;
+  }
+  if (dissipative(h)) return jxf_halo_fill_edges(h, prims, cons, stream);
+  return JXF_OK;
 }
 
 extern "C" int jxf_stage(jxf_handle h, int stage, const double* prims_in, double* prims_out, const double* cons_in,
@@ -1461,15 +1587,24 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
   if (stage < 0 || stage >= h->stages) return fail(JXF_ERR_BAD_ARG, "jxf_stage: stage %d out of range", stage);
   if (stage > 0 && !cons_n) return fail(JXF_ERR_BAD_ARG, "jxf_stage: cons_n required for stage > 0");
   if (prims_in == prims_out) return fail(JXF_ERR_BAD_ARG, "jxf_stage: prims_out must not alias prims_in");
-  if (h->n_active > 1 && !rhs_scratch) return fail(JXF_ERR_BAD_ARG, "jxf_stage: rhs_scratch required");
+  const bool diss = dissipative(h);
+  if ((h->n_active > 1 || diss) && !rhs_scratch) return fail(JXF_ERR_BAD_ARG, "jxf_stage: rhs_scratch required");
   if (reduce && !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage: red_dev required when reduce != 0");
+  if (diss) {
+    // viscous + heat flux divergence of all axes first: rhs = D_x + D_y + D_z, the convective sweeps add to it
+    if (first_axis_index != 0) return fail(JXF_ERR_UNSUPPORTED, "jxf_stage_tail: partial stages are not available with the viscous / heat flux");
+    for (int k = 0; k < h->n_active; ++k) {
+      int rc = dissipative_sweep(h, h->active[k], prims_in, rhs_scratch, k > 0, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  }
   for (int k = first_axis_index; k < h->n_active; ++k) {
     const int axis = h->order[k];
     const bool last = (k == h->n_active - 1);
     SweepArgs a = base_args(h, axis, prims_in, rhs_scratch);
     int rc;
     if (!last) {
-      a.accumulate = k > 0;
+      a.accumulate = k > 0 || diss;
       rc = dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
     } else {
       a.cons_in = cons_in;
@@ -1482,7 +1617,7 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       a.ca = h->blend[stage][0];
       a.cb = h->blend[stage][1];
       a.dt_mult = h->dt_mult[stage];
-      a.has_prev = k > 0;
+      a.has_prev = k > 0 || diss;
       a.reduce = reduce ? 1 : 0;
       a.fuse_halo = fill_halo ? 1 : 0;      // outer-BC halo images written by the epilogue itself
       a.nh = h->cfg.nh;
@@ -1491,6 +1626,8 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
     }
     if (rc) return rc;
   }
+  // the next stage's dissipative stencils read edge halos (halo_manager.py:119-129)
+  if (diss && fill_halo) return jxf_halo_fill_edges(h, prims_out, cons_out, stream);
   return JXF_OK;
 }
 
@@ -1551,8 +1688,14 @@ extern "C" int jxf_finish_step(jxf_handle h, double* red_dev, double* dt_dev, do
                                void* stream) {
   if (!h || !red_dev || !dt_dev) return fail(JXF_ERR_BAD_ARG, "jxf_finish_step: null argument");
   ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  DtLimits lim;
+  lim.visc = h->cfg.viscous_flux;
+  lim.heat = h->cfg.heat_flux;
+  lim.mu = h->cfg.dynamic_viscosity;
+  lim.lambda = h->cfg.thermal_conductivity;
+  lim.cp = h->cfg.gamma / (h->cfg.gamma - 1.0) * h->cfg.gas_constant;      // ideal_gas.py:33
   finish_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(red_dev, dt_dev, time_dev, info_dev, h->cfg.dx_min, h->cfg.cfl,
-                                                        h->cfg.fixed_dt);
+                                                        h->cfg.fixed_dt, lim);
   return check_launch("finish_step");
 }
 

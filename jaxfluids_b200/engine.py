@@ -33,6 +33,31 @@ class BlockConfig:
     integrator: str = "RK3"
     cfl: float = 0.5
     fixed_dt: float = 0.0
+    # dissipative fluxes (active_physics + material_properties/transport); constants only on this path
+    is_viscous_flux: bool = False
+    is_heat_flux: bool = False
+    is_viscous_heat_production: bool = True
+    dynamic_viscosity: float = 0.0
+    bulk_viscosity: float = 0.0
+    thermal_conductivity_model: str = "CUSTOM"        # CUSTOM | PRANDTL
+    thermal_conductivity: float = 0.0
+    prandtl_number: float = 1.0
+    gas_constant: float = 1.0
+
+    @property
+    def is_dissipative(self) -> bool:
+        return bool(self.is_viscous_flux or self.is_heat_flux)
+
+    def thermal_conductivity_value(self) -> float:
+        """material.py:112-116: CUSTOM value, or PRANDTL cp mu / Pr with cp = gamma/(gamma-1) R (ideal_gas.py:33),
+        evaluated in the reference's operation order."""
+        if self.thermal_conductivity_model == "CUSTOM":
+            return float(self.thermal_conductivity)
+        if self.thermal_conductivity_model == "PRANDTL":
+            cp = self.gamma / (self.gamma - 1.0) * self.gas_constant
+            return cp * float(self.dynamic_viscosity) / float(self.prandtl_number)
+        raise NotImplementedError(f"thermal_conductivity model '{self.thermal_conductivity_model}' is not implemented "
+                                  "on the B200 path (implemented: CUSTOM, PRANDTL)")
 
     def to_c(self) -> _lib.JxfConfig:
         def lookup(table, key, what):
@@ -56,6 +81,13 @@ class BlockConfig:
         c.integrator = lookup(_lib.INTEGRATOR, self.integrator, "integrator")
         for k, f in enumerate(FACES):
             c.bc[k] = lookup(_lib.BC, self.bc[f], f"boundary condition type at {f}")
+        c.viscous_flux = int(bool(self.is_viscous_flux))
+        c.heat_flux = int(bool(self.is_heat_flux))
+        c.viscous_heat_production = int(bool(self.is_viscous_heat_production))
+        c.dynamic_viscosity = float(self.dynamic_viscosity)
+        c.bulk_viscosity = float(self.bulk_viscosity)
+        c.thermal_conductivity = self.thermal_conductivity_value() if self.is_heat_flux else 0.0
+        c.gas_constant = float(self.gas_constant)
         return c
 
     @property
@@ -162,6 +194,19 @@ class BlockSolver:
                                                 C.c_double(float(dt)), _ptr(out), _stream()))
         return out
 
+    def dissipative_sweep(self, axis: int, prims, rhs, accumulate: bool):
+        _lib.check(self.lib.jxf_dissipative_sweep(self._h, int(axis), _ptr(prims), _ptr(rhs), int(bool(accumulate)),
+                                                  _stream()))
+        return rhs
+
+    def halo_fill_edges(self, prims, cons):
+        _lib.check(self.lib.jxf_halo_fill_edges(self._h, _ptr(prims), _ptr(cons), _stream()))
+
+    def temperature(self, prims, out=None):
+        out = torch.empty(tuple(prims.shape[1:]), dtype=torch.float64, device=prims.device) if out is None else out
+        _lib.check(self.lib.jxf_temperature(self._h, _ptr(prims), _ptr(out), _stream()))
+        return out
+
     def halo_fill(self, prims, cons):
         _lib.check(self.lib.jxf_halo_fill(self._h, _ptr(prims), _ptr(cons), _stream()))
 
@@ -182,7 +227,7 @@ class BlockSolver:
                                             _stream()))
 
     PROFILE_KINDS = ("sweep_x", "sweep_y", "sweep_z", "sweep_x_epilogue", "sweep_y_epilogue", "sweep_z_epilogue",
-                     "halo_fill", "other")
+                     "halo_fill", "other", "dissipative")
 
     def profile_enable(self, on: bool = True):
         _lib.check(self.lib.jxf_profile_enable(self._h, int(bool(on))))
@@ -221,7 +266,7 @@ class BlockState:
             self.cons_a.copy_(torch.as_tensor(cons_with_halos, dtype=torch.float64))
         else:
             s.cons_from_prims(self.prims[0], self.cons_a)
-        self.rhs = s.new_rhs() if len(s.active) > 1 else None
+        self.rhs = s.new_rhs() if (len(s.active) > 1 or s.cfg.is_dissipative) else None
         self.red = s.new_red()
         self.info = s.new_scalars(3)
         self.time = s.new_scalars(1, time)

@@ -61,7 +61,19 @@ class BlockRuntime:
             integrator=ti.integrator,
             cfl=ti.CFL,
             fixed_dt=float(ti.fixed_timestep) if ti.fixed_timestep else 0.0,
+            is_viscous_flux=num.active_physics.is_viscous_flux,
+            is_heat_flux=num.active_physics.is_heat_flux,
+            is_viscous_heat_production=num.active_physics.is_viscous_heat_production,
+            dynamic_viscosity=case.material_setup.transport.dynamic_viscosity,
+            bulk_viscosity=case.material_setup.transport.bulk_viscosity,
+            thermal_conductivity_model=case.material_setup.transport.thermal_conductivity_model,
+            thermal_conductivity=case.material_setup.transport.thermal_conductivity,
+            prandtl_number=case.material_setup.transport.prandtl_number,
+            gas_constant=case.material_setup.specific_gas_constant,
         )
+        if self.cfg.is_dissipative and parallel.is_parallel:
+            raise NotImplementedError("the viscous / heat flux with a domain decomposition (inter-block edge halo "
+                                      "exchange) is not implemented on the B200 path yet")
         self.solver = BlockSolver(self.cfg)
         s = self.solver
         self.device = s.device
@@ -69,7 +81,7 @@ class BlockRuntime:
         self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
         self.cons = [s.new_field(EPS), s.new_field(EPS)]        # cons[0] = U / U^n, cons[1] = stage scratch
         self.cur = 0
-        self.rhs = s.new_rhs() if len(s.active) > 1 else None
+        self.rhs = s.new_rhs() if (len(s.active) > 1 or self.cfg.is_dissipative) else None
         self.red = s.new_red()
         self.info = s.new_scalars(3)
         self.time = s.new_scalars(1, 0.0)

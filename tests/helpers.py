@@ -147,3 +147,17 @@ def face_halo_mask(s: port.Setup):
     ix, iy, iz = np.meshgrid(*inter, indexing="ij")
     n_out = (~ix).astype(int) + (~iy).astype(int) + (~iz).astype(int)
     return n_out <= 1
+
+
+def defined_mask(s: port.Setup):
+    """Cells the path defines: interior + face halos, + edge halos with the viscous / heat flux."""
+    shape = s.shape[1:]
+    inter = [np.zeros(n, bool) for n in shape]
+    for i in range(3):
+        if s.cells[i] > 1:
+            inter[i][s.nh:-s.nh] = True
+        else:
+            inter[i][:] = True
+    ix, iy, iz = np.meshgrid(*inter, indexing="ij")
+    n_out = (~ix).astype(int) + (~iy).astype(int) + (~iz).astype(int)
+    return n_out <= (2 if s.is_dissipative else 1)

@@ -18,7 +18,12 @@ def make_solver(s: port.Setup, bc=None):
     from jaxfluids_b200.engine import BlockConfig, BlockSolver
     cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min),
                       gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, riemann=s.riemann,
-                      integrator=s.integrator, cfl=s.cfl)
+                      integrator=s.integrator, cfl=s.cfl,
+                      is_viscous_flux=s.is_viscous_flux, is_heat_flux=s.is_heat_flux,
+                      is_viscous_heat_production=s.is_viscous_heat_production, dynamic_viscosity=s.dynamic_viscosity,
+                      bulk_viscosity=s.bulk_viscosity, thermal_conductivity_model=s.thermal_conductivity_model,
+                      thermal_conductivity=s.thermal_conductivity, prandtl_number=s.prandtl_number,
+                      gas_constant=s.gas_constant)
     return BlockSolver(cfg)
 
 
@@ -388,3 +393,100 @@ def test_step_from_separate_api_pieces(cells, bc, integrator):
     a = sol.integrate_stage(0, c_n, None, rhs0, dt)
     sol.integrate_stage(0, c2, None, rhs0, dt, out=c2)
     assert torch.equal(a, c2)
+
+
+# ---------------------------------------------------------------------------
+# viscous + heat flux (CENTRAL4), edge halos, diffusive dt limits
+# ---------------------------------------------------------------------------
+DISS = [dict(is_viscous_flux=True, dynamic_viscosity=2e-3, bulk_viscosity=5e-4),
+        dict(is_viscous_flux=True, is_heat_flux=True, dynamic_viscosity=1e-3, thermal_conductivity_model="PRANDTL",
+             prandtl_number=0.71, gas_constant=1.3),
+        dict(is_heat_flux=True, thermal_conductivity=3e-3, gas_constant=0.8),
+        dict(is_viscous_flux=True, is_viscous_heat_production=False, dynamic_viscosity=1e-3)]
+
+
+def diss_setup(cells, bc, extra, **kw):
+    s = H.make_setup(cells, bc=bc, **kw)
+    for k, v in extra.items():
+        setattr(s, k, v)
+    return s
+
+
+@pytest.mark.parametrize("bc", ["PERIODIC", "SYMMETRY", "ZEROGRADIENT"])
+@pytest.mark.parametrize("cells", [(14, 12, 16), (18, 22, 1), (40, 1, 1)])
+def test_edge_halo_fill_is_bit_exact(cells, bc):
+    """jxf_halo_fill with the dissipative fluxes on = face halos + edge halos
+    (halos/outer/material.py:289-383): bit-identical to the oracle on every face and edge cell."""
+    s = diss_setup(cells, bc, DISS[0])
+    prims, cons = port.initialize(H.smooth_ic(s, seed=5), s)            # oracle: faces + edges
+    s0 = H.make_setup(cells, bc=bc)
+    p0, c0 = port.initialize(H.smooth_ic(s, seed=5), s0)                # faces only
+    sol = make_solver(s)
+    p, c = dev(np.nan_to_num(p0, nan=7.0)), dev(np.nan_to_num(c0, nan=7.0))
+    if len(s.active) > 1:                                               # scramble the edge regions first
+        nh = s.nh
+        p[:, :nh, :nh] = 3.0
+    sol.halo_fill(p, c)
+    m = H.defined_mask(s)                                               # interior + faces + edges
+    assert np.array_equal(host(p)[:, m], prims[:, m])              # copies / sign flips / 0.5 (a + b): bit exact
+    assert H.rel_linf(host(c)[:, m], cons[:, m]) <= 1e-15           # recomputed (FMA contraction on the device)
+
+
+@pytest.mark.parametrize("extra", DISS)
+@pytest.mark.parametrize("cells,bc", [((20, 16, 24), "PERIODIC"), ((12, 18, 40), "SYMMETRY"), ((16, 12, 10), "ZEROGRADIENT"),
+                                      ((30, 26, 1), "SYMMETRY"), ((24, 33, 1), "ZEROGRADIENT"), ((64, 1, 1), "ZEROGRADIENT")])
+def test_dissipative_rhs_per_axis_and_total(cells, bc, extra):
+    """Per-axis and total rhs with the viscous / heat flux folded in (space_solver.py:567-599), and the
+    stand-alone dissipative sweep against (oracle with) - (oracle without)."""
+    s = diss_setup(cells, bc, extra)
+    s_conv = H.make_setup(cells, bc=bc)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=sum(cells), amp=0.1), s)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    scales = H.rhs_scales(prims, s_conv)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s), scale=scales) <= H.TOL_RHS, f"axis {a}"
+        d = sol.new_rhs()
+        sol.dissipative_sweep(a, p, d, accumulate=False)
+        ref_d = port.rhs_axis(prims, a, s) - port.rhs_axis(prims, a, s_conv)
+        dscale = np.maximum(np.abs(ref_d).max(axis=(1, 2, 3)), 1e-300)
+        err = np.abs(host(d) - ref_d).max(axis=(1, 2, 3))
+        # the reference forms (conv - visc) before differencing: its own rounding is ~1e-16 of the CONVECTIVE terms
+        assert np.all(err <= 1e-12 * np.maximum(dscale, scales.reshape(-1))), (a, err, dscale)
+        assert np.all(host(d)[0] == 0.0)
+    got = host(sol.compute_rhs(p))
+    assert H.rel_linf(got, port.compute_rhs(prims, s), scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("extra", DISS[:3])
+@pytest.mark.parametrize("cells,bc,integrator", [((16, 12, 20), "SYMMETRY", "RK3"), ((14, 16, 12), "PERIODIC", "RK2"),
+                                                 ((22, 18, 1), "ZEROGRADIENT", "RK3"), ((48, 1, 1), "ZEROGRADIENT", "EULER")])
+def test_dissipative_steps_against_oracle(cells, bc, integrator, extra):
+    """5 full steps with viscous / heat flux: state, dt sequence (incl. the diffusive dt limits) and the
+    temperature buffer."""
+    from jaxfluids_b200.engine import BlockState
+    extra = dict(extra)
+    if extra.get("dynamic_viscosity"):
+        extra["dynamic_viscosity"] = 0.05                                # large enough for the viscous dt limit to bind
+    s = diss_setup(cells, bc, extra, integrator=integrator)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=9, amp=0.1), s)
+    sol = make_solver(s)
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    assert abs(st.dt.item() - dt) <= 1e-14 * dt
+    conv_dt = port.time_step_size(prims, H.make_setup(cells, bc=bc, integrator=integrator))
+    if extra.get("dynamic_viscosity"):
+        assert dt < conv_dt                                              # the diffusive limit is the active one
+    m = H.defined_mask(s)
+    for _ in range(5):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+        assert abs(st.dt.item() - dt) <= 1e-12 * dt
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+    assert H.rel_linf(host(st.conservatives)[:, m], cons[:, m]) <= 1e-12
+    gp = host(st.primitives)
+    T = host(sol.temperature(st.primitives))                          # ideal_gas.py:64-65 on the same bits: exact
+    assert np.array_equal(T[m], port.temperature(gp, s)[m])
+    assert np.allclose(T[m], port.temperature(prims, s)[m], rtol=1e-11, atol=0)
