@@ -37,10 +37,12 @@ ALG_FLOPS_PER_CELL_STEP = 9.7e3      # CHAR-PRIMITIVE + HLLC + EINF
 # compulsory bytes per cell of ONE launch of each kernel kind (DESIGN.md "kernels"):
 KERNEL_BYTES = {"sweep_x": 80.0, "sweep_y": 120.0, "sweep_z": 120.0,
                 # prims in + rhs in + U in + U^n in (2 of 3 stages) + U out + prims out
-                "sweep_x_epilogue": 226.7, "sweep_y_epilogue": 226.7, "sweep_z_epilogue": 226.7}
+                "sweep_x_epilogue": 226.7, "sweep_y_epilogue": 226.7, "sweep_z_epilogue": 226.7,
+                # dissipative sweep: prims in (40) + 4 rhs rows in/out (64) (+8 for the mass row of the first)
+                "dissipative": 106.7}
 
 
-def tgv_case(cells_per_gpu: int, split, end_step: int):
+def tgv_case(cells_per_gpu: int, split, end_step: int, viscous: bool = False):
     sx, sy, sz = split
     dom = {}
     for ax, s in zip("xyz", split):
@@ -70,6 +72,15 @@ def tgv_case(cells_per_gpu: int, split, end_step: int):
         "precision": {"is_double_precision_compute": True, "is_double_precision_output": True},
         "output": {"logging": {"level": "NONE"}},
     }
+    if viscous:
+        # the TGV at Re = 1600, Pr = 0.71: viscous + heat flux with the CENTRAL4 stencils
+        num["active_physics"].update(is_viscous_flux=True, is_heat_flux=True)
+        num["conservatives"]["dissipative_fluxes"] = {"reconstruction_stencil": "CENTRAL4",
+                                                      "derivative_stencil_center": "CENTRAL4",
+                                                      "derivative_stencil_face": "CENTRAL4"}
+        case["material_properties"]["transport"] = {
+            "dynamic_viscosity": {"model": "CUSTOM", "value": 1.0 / 1600.0}, "bulk_viscosity": 0.0,
+            "thermal_conductivity": {"model": "PRANDTL", "prandtl_number": 0.71}}
     return case, num
 
 
@@ -187,6 +198,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--viscous", action="store_true",
+                    help="widened workload (not the BASELINE line): TGV Re=1600 with viscous + heat flux")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -200,6 +213,8 @@ def main():
               "cells_per_gpu": args.cells ** 3, "global_cells": args.cells ** 3 * n_gpus,
               "decomposition": list(split), "dx_fixed": True,
               "l2": "inputs larger than L2 (5.7 GB per field buffer at 512^3), no flush needed"}
+    if args.viscous:
+        config["workload"] += " + viscous and heat flux (CENTRAL4), Re 1600, Pr 0.71 [widened workload]"
 
     if args.impl == "reference":
         if rank != 0:
@@ -230,7 +245,7 @@ def main():
     from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
     dev = torch.cuda.current_device()
 
-    case, num = tgv_case(args.cells, split, end_step=10 ** 9)
+    case, num = tgv_case(args.cells, split, end_step=10 ** 9, viscous=args.viscous)
     im = InputManager(case, num)
     init = InitializationManager(im)
     buffers = init.initialization()
@@ -319,6 +334,11 @@ def main():
             "frac_of_roof": (mcups / n_gpus) / (1e-6 / max(t_hbm, t_fp64)),
             "hbm_frac_step": (mcups / n_gpus) * 1e6 * ALG_BYTES_PER_CELL_STEP / (hbm_peak * 1e9)},
     }
+    if args.viscous and prof.get("dissipative", (0, 0, 0))[1]:
+        d_ms = prof["dissipative"][0] / prof["dissipative"][1]
+        d_gbs = cells_local * KERNEL_BYTES["dissipative"] / (d_ms * 1e-3) / 1e9
+        roofline["dissipative_sweep"] = {"bound": "hbm", "launch_ms": d_ms, "bytes_per_cell_launch": KERNEL_BYTES["dissipative"],
+                                         "achieved": d_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": d_gbs / hbm_peak}
     launches = int(sum(v[2] for v in prof.values()))
 
     # ---- end-to-end through the public API with HOST buffers ---------------------------------

@@ -54,35 +54,68 @@ struct VCell {
   double d2[3];             // d u_c / d x_(role 2)
 };
 
-// cell-centre data of the cell at element offset `idx` (relative to the interior origin)
-__device__ __forceinline__ void load_vcell(const SweepGeom& g, const ViscArgs& a, long long idx, VCell& c) {
+// raw operands of one cell: own (rho, u, v, w, p) and the +-1, +-2 neighbours of the velocities along the two
+// transverse role axes.  Loading (vraw_load) and reducing (vcell_from_raw) are separate so that the marching
+// kernel can post the loads of the NEXT cell before it works on the current face (software pipeline).
+struct VRaw {
+  double own[5];
+  double n1[3][4];          // velocity k at -2, -1, +1, +2 along role 1
+  double n2[3][4];
+};
+
+__device__ __forceinline__ void vraw_load(const SweepGeom& g, const ViscArgs& a, long long idx, VRaw& r) {
   const double* p = a.prims + idx;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) c.u[k] = p[(1 + k) * g.vst];
-  c.T = 0.0;
-  if (a.heat) c.T = p[4 * g.vst] * visc_rcp(p[0] * a.gas_constant);
-  constexpr double c0 = 1.0 / 12.0, c1 = 8.0 / 12.0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    c.d1[k] = 0.0;
-    c.d2[k] = 0.0;
+  r.own[0] = r.own[4] = 1.0;
+  if (a.heat) {
+    r.own[0] = p[0];
+    r.own[4] = p[4 * g.vst];
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r.own[1 + k] = p[(1 + k) * g.vst];
   if (a.visc) {
     if (g.n1 > 1) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const double* q = p + (1 + k) * g.vst;
-        c.d1[k] = a.inv_dx1 * fma(c1, q[g.s1] - q[-g.s1], c0 * (q[-2 * g.s1] - q[2 * g.s1]));
+        r.n1[k][0] = q[-2 * g.s1]; r.n1[k][1] = q[-g.s1]; r.n1[k][2] = q[g.s1]; r.n1[k][3] = q[2 * g.s1];
       }
     }
     if (g.n2 > 1) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const double* q = p + (1 + k) * g.vst;
-        c.d2[k] = a.inv_dx2 * fma(c1, q[g.s2] - q[-g.s2], c0 * (q[-2 * g.s2] - q[2 * g.s2]));
+        r.n2[k][0] = q[-2 * g.s2]; r.n2[k][1] = q[-g.s2]; r.n2[k][2] = q[g.s2]; r.n2[k][3] = q[2 * g.s2];
       }
     }
   }
+}
+
+__device__ __forceinline__ void vcell_from_raw(const SweepGeom& g, const ViscArgs& a, const VRaw& r, VCell& c) {
+  constexpr double c0 = 1.0 / 12.0, c1 = 8.0 / 12.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    c.u[k] = r.own[1 + k];
+    c.d1[k] = 0.0;
+    c.d2[k] = 0.0;
+  }
+  c.T = a.heat ? r.own[4] * visc_rcp(r.own[0] * a.gas_constant) : 0.0;
+  if (a.visc) {
+    if (g.n1 > 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c.d1[k] = a.inv_dx1 * fma(c1, r.n1[k][2] - r.n1[k][1], c0 * (r.n1[k][0] - r.n1[k][3]));
+    }
+    if (g.n2 > 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c.d2[k] = a.inv_dx2 * fma(c1, r.n2[k][2] - r.n2[k][1], c0 * (r.n2[k][0] - r.n2[k][3]));
+    }
+  }
+}
+
+// cell-centre data of the cell at element offset `idx` (relative to the interior origin)
+__device__ __forceinline__ void load_vcell(const SweepGeom& g, const ViscArgs& a, long long idx, VCell& c) {
+  VRaw r;
+  vraw_load(g, a, idx, r);
+  vcell_from_raw(g, a, r, c);
 }
 
 __device__ __forceinline__ double central4(double a, double b, double c, double d) {
@@ -150,14 +183,14 @@ __device__ __forceinline__ void dissipative_update(const SweepGeom& g, const Vis
   }
 }
 
+// CTA = 32 lanes along the contiguous axis x 4 columns along the other transverse axis: the +-1, +-2
+// neighbours a cell-centre derivative reads along that axis are mostly the CTA's own columns (L1 hits)
 template <int A>
-__global__ void __launch_bounds__(128) visc_march(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
-  const long long plane = (long long)g.n1 * g.n2;
-  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (p >= plane) return;
-  const int i1 = (int)(p / g.n2);
-  const int i2 = (int)(p - (long long)i1 * g.n2);
-  const int f0 = blockIdx.y * a.chunk_len;
+__global__ void __launch_bounds__(128, 3) visc_march(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
+  const int i2 = blockIdx.x * 32 + threadIdx.x;
+  const int i1 = blockIdx.y * 4 + threadIdx.y;
+  if (i1 >= g.n1 || i2 >= g.n2) return;
+  const int f0 = blockIdx.z * a.chunk_len;
   const int f1 = min(f0 + a.chunk_len, g.nA);
   const long long col_h = i1 * g.s1 + i2 * g.s2;
   const long long col_r = i1 * g.r1 + i2 * g.r2;
@@ -165,12 +198,26 @@ __global__ void __launch_bounds__(128) visc_march(const __grid_constant__ SweepG
   load_vcell(g, a, col_h + (long long)(f0 - 2) * g.sA, c0);
   load_vcell(g, a, col_h + (long long)(f0 - 1) * g.sA, c1);
   load_vcell(g, a, col_h + (long long)f0 * g.sA, c2);
+  VRaw nx;
+  vraw_load(g, a, col_h + (long long)(f0 + 1) * g.sA, nx);        // cell f0+1, consumed by the first iteration
   double Fp[4] = {0.0, 0.0, 0.0, 0.0};
   for (int f = f0; f <= f1; ++f) {
-    load_vcell(g, a, col_h + (long long)(f + 1) * g.sA, c3);      // cell f+1 <= n+1 < n+nh
+    vcell_from_raw(g, a, nx, c3);                                  // cell f+1 <= n+1 < n+nh
+    // post the next cell's loads and this cell's rhs loads now; they are consumed one face of arithmetic later
+    if (f < f1) vraw_load(g, a, col_h + (long long)(f + 2) * g.sA, nx);
+    const long long ridx = col_r + (long long)(f - 1) * g.rA;
+    double r_old[4] = {0.0, 0.0, 0.0, 0.0};
+    if (f > f0 && a.accumulate) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r_old[k] = a.rhs[ridx + (1 + k) * g.rvst];
+    }
     double F[4];
     dissipative_face_flux<A>(g, a, c0, c1, c2, c3, F);
-    if (f > f0) dissipative_update(g, a, col_r + (long long)(f - 1) * g.rA, Fp, F);
+    if (f > f0) {
+      if (!a.accumulate) a.rhs[ridx] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a.rhs[ridx + (1 + k) * g.rvst] = fma(a.inv_dxA, Fp[k] - F[k], r_old[k]);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) Fp[k] = F[k];
     c0 = c1;
@@ -179,21 +226,33 @@ __global__ void __launch_bounds__(128) visc_march(const __grid_constant__ SweepG
   }
 }
 
-// shared layout: 10 cell quantities + 4 flux components, each blockDim doubles
+// shared layout per row of the CTA: 10 cell quantities + 4 flux components, each blockDim.x doubles.
+// CTA = blockDim.y consecutive rows x one segment of the contiguous axis (neighbouring rows share the lines
+// their transverse derivatives read)
 template <int A>
-__global__ void __launch_bounds__(1024) visc_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
-  extern __shared__ double vs[];
+__global__ void __launch_bounds__(256) visc_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
+  extern __shared__ double vs_all[];
   const int B = blockDim.x;
   const int tid = threadIdx.x;
-  const long long row = blockIdx.x;
-  const int i1 = (int)(row / g.n2);
-  const int i2 = (int)(row - (long long)i1 * g.n2);
+  double* const vs = vs_all + (size_t)threadIdx.y * 14 * B;
+  const long long nrows = (long long)g.n1 * g.n2;
+  const long long row = blockIdx.x * (long long)blockDim.y + threadIdx.y;
+  const bool live = row < nrows;
+  const int i1 = live ? (int)(row / g.n2) : 0;
+  const int i2 = live ? (int)(row - (long long)i1 * g.n2) : 0;
   const int s0 = blockIdx.y * a.seg_len;                 // first cell of this segment
   const int L = min(a.seg_len, g.nA - s0);               // cells in this segment
   const long long col_h = i1 * g.s1 + i2 * g.s2;
   const long long col_r = i1 * g.r1 + i2 * g.r2;
   const int k = s0 - 2 + tid;                            // this thread's cell
-  if (tid < L + 4) {
+  const bool owns = live && tid >= 2 && tid <= L + 1;    // cell k is updated by this thread
+  const long long ridx = col_r + (long long)k * g.rA;
+  double r_old[4] = {0.0, 0.0, 0.0, 0.0};
+  if (owns && a.accumulate) {                            // posted with the stencil loads, consumed after both barriers
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r_old[q] = a.rhs[ridx + (1 + q) * g.rvst];
+  }
+  if (live && tid < L + 4) {
     VCell c;
     load_vcell(g, a, col_h + (long long)k * g.sA, c);
 #pragma unroll
@@ -206,7 +265,7 @@ __global__ void __launch_bounds__(1024) visc_rows(const __grid_constant__ SweepG
   }
   __syncthreads();
   double* fl = vs + 10 * B;
-  if (tid >= 1 && tid <= L + 1) {                        // face between cells k and k+1
+  if (live && tid >= 1 && tid <= L + 1) {                // face between cells k and k+1
     VCell c[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -225,14 +284,11 @@ __global__ void __launch_bounds__(1024) visc_rows(const __grid_constant__ SweepG
     for (int q = 0; q < 4; ++q) fl[q * B + tid] = F[q];
   }
   __syncthreads();
-  if (tid >= 2 && tid <= L + 1) {                        // cell k = s0 + tid - 2: faces computed by tid-1 (low) and tid (high)
-    double Flo[4], Fhi[4];
+  if (owns) {                                            // faces computed by tid-1 (low) and tid (high)
+    if (!a.accumulate) a.rhs[ridx] = 0.0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      Flo[q] = fl[q * B + tid - 1];
-      Fhi[q] = fl[q * B + tid];
-    }
-    dissipative_update(g, a, col_r + (long long)k * g.rA, Flo, Fhi);
+    for (int q = 0; q < 4; ++q)
+      a.rhs[ridx + (1 + q) * g.rvst] = fma(a.inv_dxA, fl[q * B + tid - 1] - fl[q * B + tid], r_old[q]);
   }
 }
 

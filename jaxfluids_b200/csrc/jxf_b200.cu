@@ -1441,26 +1441,40 @@ static int launch_dissipative(const jxf_solver* s, const double* prims, double* 
     sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
     a.inv_dx1 = s->cfg.inv_dx[O];
     a.inv_dx2 = s->cfg.inv_dx[C];
-    const long long plane = (long long)sg.n1 * sg.n2;
-    const int bx = (int)((plane + 127) / 128);
+    const int bx = (sg.n2 + 31) / 32, by = (sg.n1 + 3) / 4;
+    if (by > 65535) return fail(JXF_ERR_UNSUPPORTED, "dissipative sweep: transverse extent too large");
     // enough CTAs for ~8 per SM; every chunk re-reads a 3-cell prologue
-    int chunks = (int)std::min<long long>(std::max<long long>(1, (8LL * s->num_sms + bx - 1) / bx), std::max(1, g.n[A] / 16));
+    const long long tiles = (long long)bx * by;
+    int chunks = (int)std::min<long long>(std::max<long long>(1, (8LL * s->num_sms + tiles - 1) / tiles),
+                                          std::max(1, std::min(g.n[A] / 16, 65535)));
     a.chunk_len = (g.n[A] + chunks - 1) / chunks;
     chunks = (g.n[A] + a.chunk_len - 1) / a.chunk_len;
-    visc_march<A><<<dim3(bx, chunks), 128, 0, st>>>(sg, a);
+    visc_march<A><<<dim3(bx, by, chunks), dim3(32, 4), 0, st>>>(sg, a);
   } else {
     const int T1 = (A == 0) ? 1 : 0, T2 = (A == 2) ? 1 : 2;
     sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
     sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
     a.inv_dx1 = s->cfg.inv_dx[T1];
     a.inv_dx2 = s->cfg.inv_dx[T2];
-    // one CTA per row segment of up to 1020 cells (+4 stencil cells = 1024 threads)
-    const int nseg = (g.n[A] + 1019) / 1020;
+    // CTA = R consecutive rows x one segment of <= 252 cells (+4 stencil cells)
+    int seg_max = 252;
+    if (getenv("JXF_VISC_SEG")) seg_max = std::max(28, std::min(252, atoi(getenv("JXF_VISC_SEG"))));
+    const int nseg = (g.n[A] + seg_max - 1) / seg_max;
     a.seg_len = (g.n[A] + nseg - 1) / nseg;
     const int threads = ((a.seg_len + 4 + 31) / 32) * 32;
+    int R = 1;      // measured at 512^3: 1 row per CTA 6.7 ms, 2 rows 8.6 ms, 4 rows 10.1 ms (more CTAs overlap the phases)
+    if (getenv("JXF_VISC_ROWS_R")) R = std::max(1, std::min(256 / threads, atoi(getenv("JXF_VISC_ROWS_R"))));
     const long long rows = (long long)sg.n1 * sg.n2;
-    if (rows > 0x7fffffffLL) return fail(JXF_ERR_UNSUPPORTED, "dissipative sweep: too many rows");
-    visc_rows<A><<<dim3((unsigned)rows, nseg), threads, (size_t)threads * 14 * sizeof(double), st>>>(sg, a);
+    const long long groups = (rows + R - 1) / R;
+    if (groups > 0x7fffffffLL || nseg > 65535) return fail(JXF_ERR_UNSUPPORTED, "dissipative sweep: grid too large");
+    const size_t smem = (size_t)R * threads * 14 * sizeof(double);     // <= 28 KB
+    static bool attr_set = false;                                       // per instantiation (per axis)
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(visc_rows<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 14 * (int)sizeof(double)) != cudaSuccess)
+        return fail(JXF_ERR_CUDA, "dissipative sweep: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+      attr_set = true;
+    }
+    visc_rows<A><<<dim3((unsigned)groups, nseg), dim3(threads, R), smem, st>>>(sg, a);
   }
   return check_launch("dissipative sweep");
 }

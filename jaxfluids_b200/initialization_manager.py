@@ -86,7 +86,9 @@ class InitializationManager:
         tcv = TimeControlVariables(
             physical_simulation_time=time0, simulation_step=0, physical_timestep_size=dt,
             fixed_time_step_size=fixed, end_time=gs.end_time, end_step=gs.end_step)
-        material_fields = MaterialFieldBuffers(conservatives=cons, primitives=prims, temperature=None)
+        # equation_information.is_compute_temperature: the temperature buffer exists with the viscous / heat flux
+        temperature = rt.temperature(prims)
+        material_fields = MaterialFieldBuffers(conservatives=cons, primitives=prims, temperature=temperature)
         sim = SimulationBuffers(material_fields, LevelsetFieldBuffers(), SolidFieldBuffers())
         step_info = StepInformation(positivity=(PositivityStateInformation(min_pressure=min_p, min_density=min_rho),))
         return JaxFluidsBuffers(sim, tcv, ForcingParameters(), step_info)

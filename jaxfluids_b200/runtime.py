@@ -108,6 +108,13 @@ class BlockRuntime:
     def conservatives(self) -> torch.Tensor:
         return self.cons[0]
 
+    def temperature(self, prims: torch.Tensor) -> Optional[torch.Tensor]:
+        """material_manager.get_temperature on the halo'd buffer (simulation_manager.py:971-974); None unless the
+        viscous / heat flux is active (equation_information.is_compute_temperature)."""
+        if not self.cfg.is_dissipative:
+            return None
+        return self.solver.temperature(prims)
+
     def adopt(self, primitives: torch.Tensor, conservatives: torch.Tensor):
         """Make externally supplied tensors the current state (copies unless they already are)."""
         self.finish_pending()

@@ -98,16 +98,23 @@ class HaloManager:
 
     def __init__(self, runtime: BlockRuntime):
         self._rt = runtime
-        self.fill_edge_halos_material = False      # halo_manager.py:119-143: only with viscous/heat flux
-        self.fill_vertex_halos_material = False
+        self.fill_edge_halos_material = runtime.cfg.is_dissipative      # halo_manager.py:119-129
+        self.fill_vertex_halos_material = False                         # :131-143: level-set models only
 
     def perform_halo_update_material(self, primitives, physical_simulation_time=0.0, fill_edge_halos=False,
                                      fill_vertex_halos=False, conservatives=None, fill_face_halos=True,
                                      ml_setup=None):
-        assert not fill_edge_halos and not fill_vertex_halos, "edge/vertex halos are not on the convective path"
+        assert not fill_vertex_halos, "vertex halos are not on this path (level-set models only)"
         cons = conservatives if conservatives is not None else torch.empty_like(primitives)
-        self._rt.halo_update(primitives, cons)
+        self._rt.halo_update(primitives, cons)                 # faces; + edges when the dissipative fluxes are on
+        if fill_edge_halos and not self._rt.cfg.is_dissipative:
+            self._rt.solver.halo_fill_edges(primitives, cons)
         return (primitives, cons) if conservatives is not None else primitives
+
+    def perform_outer_halo_update_temperature(self, temperature, physical_simulation_time=0.0):
+        """halo_manager.py:236-253.  For PERIODIC / SYMMETRY / ZEROGRADIENT faces the temperature halos equal the
+        temperature of the halo primitives, which `get_temperature` on the halo'd buffer already produced."""
+        return temperature
 
 
 def compute_time_step_size(primitives, runtime: BlockRuntime) -> float:
@@ -203,7 +210,7 @@ class SimulationManager:
         t, dt_next, _, min_rho, min_p = rt.read_step_scalars()
         tcv = tcv._replace(physical_simulation_time=t, simulation_step=tcv.simulation_step + 1,
                            physical_timestep_size=dt_next)
-        material_fields = MaterialFieldBuffers(rt.conservatives, rt.primitives, None)
+        material_fields = MaterialFieldBuffers(rt.conservatives, rt.primitives, rt.temperature(rt.primitives))
         sim = SimulationBuffers(material_fields, jxf_buffers.simulation_buffers.levelset_fields,
                                 jxf_buffers.simulation_buffers.solid_fields)
         info = StepInformation(positivity=(PositivityStateInformation(min_pressure=min_p, min_density=min_rho),))
@@ -229,4 +236,5 @@ class SimulationManager:
             simulation_step=time_control_variables.simulation_step + 1)
         info = StepInformation(positivity=(PositivityStateInformation(min_pressure=float(red[2]),
                                                                       min_density=float(red[1])),))
-        return (MaterialFieldBuffers(rt.conservatives, rt.primitives, None), tcv, levelset_fields, solid_fields, info)
+        return (MaterialFieldBuffers(rt.conservatives, rt.primitives, rt.temperature(rt.primitives)), tcv,
+                levelset_fields, solid_fields, info)
