@@ -84,19 +84,71 @@ def tgv_case(cells_per_gpu: int, split, end_step: int, viscous: bool = False):
     return case, num
 
 
+# DRAM traffic per launch at 512^3 (dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture,
+# profiles/r01b_ncu_full_sweeps.txt): equals the compulsory bytes above to within 3 % -- no wasted re-reads
+# (the z+epilogue capture is stage 0, which does not read U^n: 210.7 B/cell against 186.7 compulsory + halo images)
+NCU_TRAFFIC_512 = {"sweep_x": 5.668472e9 + 5.328012e9, "sweep_y": 11.035736e9 + 5.328945e9,
+                   "sweep_z_epilogue": 16.883604e9 + 11.400052e9, "dissipative": 10.118630e9 + 4.270035e9}
+
+
 # ---------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / power / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line).
+    NVML in a thread (nvidia_ml_py; ~1 ms per sample, works on 8-GPU boxes where one `nvidia-smi` query takes
+    hundreds of ms), falling back to an `nvidia-smi -lms` child process."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.samples, self.thread, self._stop, self.nvml = [], None, threading.Event(), None
+        self.t_mark = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            R = pynvml
+            bits = {"hw_slowdown": getattr(R, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(R, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+
+            def reasons_of(h):
+                try:
+                    return pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    return pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+
+            def pump():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        mask = reasons_of(h)
+                        self.samples.append((time.perf_counter(), mhz, pw, {k for k, b in bits.items() if mask & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -106,11 +158,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Start of the timed region: only samples taken after this count (NVML path)."""
+        self.t_mark = time.perf_counter()
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            sel = [x for x in self.samples if self.t_mark is None or x[0] >= self.t_mark]
+            if not sel:
+                sel = self.samples
+            if not sel:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            reasons = set()
+            for x in sel:
+                reasons |= x[3]
+            return {"sm_mhz": statistics.median(x[1] for x in sel), "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(x[2] for x in sel), "samples": len(sel), "reasons": sorted(reasons),
+                    "source": "nvml, 10 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -136,7 +206,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvidia-smi -lms 50"}
 
 
 # ---------------------------------------------------------------------------
@@ -270,6 +340,7 @@ def main():
     rt.solver.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         rt.step()
@@ -323,7 +394,10 @@ def main():
     t_fp64 = ALG_FLOPS_PER_CELL_STEP / (fp64_tflops * 1e12)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / hbm_peak,
+        "traffic": (NCU_TRAFFIC_512.get(dom) if args.cells == 512 else None),
+        "traffic_source": "profiles/r01b_ncu_full_sweeps.txt (ncu --set full, one launch, bytes)",
+        "peak_source": peak_src,
         "bytes_per_cell_launch": KERNEL_BYTES[dom], "launch_ms": dom_ms,
         "note": "the path is FP64-pipe bound (AI ~22 flop/B): see step_roofline for the binding bound",
         "kernel_ms": kernel_ms, "kernel_share_of_step": share,

@@ -195,6 +195,17 @@ int64_t jxf_face_slab_elems(jxf_handle h, int face);
 int jxf_pack_face(jxf_handle h, int face, const double* prims, double* slab, void* stream);
 int jxf_unpack_face(jxf_handle h, int face, const double* slab, double* prims, double* cons, void* stream);
 
+/* The same with the transverse range widened over the nh halo cells of a transverse axis (ref: the inter-block
+ * EDGE halo update, halos/inner/halo_communication.py edge tables, needed by the dissipative fluxes).
+ * ext_mask: bit 0 / 1 = low / high side of the slower transverse axis, bit 2 / 3 = of the faster one.
+ * Exchanging the faces axis by axis -- x faces widened over the PHYSICAL y/z face halos, y faces over all x
+ * halos and the physical z halos, z faces over all x and y halos -- fills every edge halo next to a shared
+ * face with what a single-block halo update would put there. */
+int64_t jxf_face_slab_elems_ext(jxf_handle h, int face, int ext_mask);
+int jxf_pack_face_ext(jxf_handle h, int face, int ext_mask, const double* prims, double* slab, void* stream);
+int jxf_unpack_face_ext(jxf_handle h, int face, int ext_mask, const double* slab, double* prims, double* cons,
+                        void* stream);
+
 /* Launch accounting and optional per-kernel timing (bench / roofline evidence).
  * Kinds: 0..2 = sweep along axis 0..2 writing rhs; 3..5 = sweep along axis 0..2 with the fused
  * RK-stage epilogue; 6 = halo fill; 7 = other (transforms, reductions, pack/unpack); 8 = dissipative

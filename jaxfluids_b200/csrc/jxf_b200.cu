@@ -879,15 +879,17 @@ struct FaceArgs {
   double gamma;
   int face;
   int unpack;
+  int lo1, n1, lo2, n2;   // transverse ranges in BUFFER coordinates: [lo, lo + n) along the two transverse axes
 };
 
-// slab layout (5, nh, n1, n2), layers in increasing buffer index along the face axis
+// slab layout (5, nh, n1, n2), layers in increasing buffer index along the face axis; the transverse ranges are
+// the interior, optionally widened over the halo cells of a transverse axis (edge halos of the dissipative path)
 __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const FaceArgs a) {
   const int ax = a.face >> 1;
   const bool hi = (a.face & 1) == 0;
   const int t1 = (ax == 0) ? 1 : 0;
   const int t2 = (ax == 2) ? 1 : 2;
-  const int n1 = g.n[t1], n2 = g.n[t2];
+  const int n1 = a.n1, n2 = a.n2;
   const long long total = (long long)g.nh * n1 * n2;
   const int nh = g.nh, ext = g.ext[ax];
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const Face
     const long long q1 = q / n2;
     const int i1 = (int)(q1 % n1);
     const int l = (int)(q1 / n1);
-    const long long tr = (long long)(i1 + g.off[t1]) * g.st[t1] + (long long)(i2 + g.off[t2]) * g.st[t2];
+    const long long tr = (long long)(i1 + a.lo1) * g.st[t1] + (long long)(i2 + a.lo2) * g.st[t2];
     if (!a.unpack) {
       const int src = hi ? (ext - 2 * nh + l) : (nh + l);   // interior layers adjacent to the face
       const long long is = tr + (long long)src * g.st[ax];
@@ -1725,16 +1727,37 @@ extern "C" int jxf_integrate_stage(jxf_handle h, int stage, const double* cons, 
   return check_launch("integrate_stage");
 }
 
-extern "C" int64_t jxf_face_slab_elems(jxf_handle h, int face) {
-  if (!h || face < 0 || face > 5) return -1;
+// transverse range of a face slab: interior, widened by the nh halo cells on the sides named in ext_mask
+// (bit 0: low side of the slower transverse axis, bit 1: its high side, bit 2 / 3: the faster transverse axis)
+static void slab_ranges(const jxf_solver* h, int face, int ext_mask, int& lo1, int& n1, int& lo2, int& n2) {
   const int ax = face >> 1;
   const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
-  return 5LL * h->g.nh * h->g.n[t1] * h->g.n[t2];
+  const Geom& g = h->g;
+  lo1 = g.off[t1]; n1 = g.n[t1];
+  lo2 = g.off[t2]; n2 = g.n[t2];
+  if (g.n[t1] > 1) {
+    if (ext_mask & 1) { lo1 -= g.nh; n1 += g.nh; }
+    if (ext_mask & 2) n1 += g.nh;
+  }
+  if (g.n[t2] > 1) {
+    if (ext_mask & 4) { lo2 -= g.nh; n2 += g.nh; }
+    if (ext_mask & 8) n2 += g.nh;
+  }
 }
 
-static int face_slab(jxf_handle h, int face, double* prims, double* cons, double* slab, int unpack, void* stream) {
+extern "C" int64_t jxf_face_slab_elems_ext(jxf_handle h, int face, int ext_mask) {
+  if (!h || face < 0 || face > 5) return -1;
+  int lo1, n1, lo2, n2;
+  slab_ranges(h, face, ext_mask, lo1, n1, lo2, n2);
+  return 5LL * h->g.nh * n1 * n2;
+}
+
+extern "C" int64_t jxf_face_slab_elems(jxf_handle h, int face) { return jxf_face_slab_elems_ext(h, face, 0); }
+
+static int face_slab(jxf_handle h, int face, int ext_mask, double* prims, double* cons, double* slab, int unpack, void* stream) {
   if (!h || !prims || !slab || (unpack && !cons)) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: null argument");
   if (face < 0 || face > 5 || h->g.n[face >> 1] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: face %d not active", face);
+  if (ext_mask < 0 || ext_mask > 15) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: ext_mask %d", ext_mask);
   FaceArgs a;
   a.prims = prims;
   a.cons = cons;
@@ -1742,7 +1765,8 @@ static int face_slab(jxf_handle h, int face, double* prims, double* cons, double
   a.gamma = h->cfg.gamma;
   a.face = face;
   a.unpack = unpack;
-  const long long total = jxf_face_slab_elems(h, face) / 5;
+  slab_ranges(h, face, ext_mask, a.lo1, a.n1, a.lo2, a.n2);
+  const long long total = (long long)h->g.nh * a.n1 * a.n2;
   const int bx = (int)std::min<long long>((total + 127) / 128, 148 * 16);
   ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
   face_slab_kernel<<<bx, 128, 0, (cudaStream_t)stream>>>(h->g, a);
@@ -1750,10 +1774,17 @@ static int face_slab(jxf_handle h, int face, double* prims, double* cons, double
 }
 
 extern "C" int jxf_pack_face(jxf_handle h, int face, const double* prims, double* slab, void* stream) {
-  return face_slab(h, face, const_cast<double*>(prims), nullptr, slab, 0, stream);
+  return face_slab(h, face, 0, const_cast<double*>(prims), nullptr, slab, 0, stream);
 }
 extern "C" int jxf_unpack_face(jxf_handle h, int face, const double* slab, double* prims, double* cons, void* stream) {
-  return face_slab(h, face, prims, cons, const_cast<double*>(slab), 1, stream);
+  return face_slab(h, face, 0, prims, cons, const_cast<double*>(slab), 1, stream);
+}
+extern "C" int jxf_pack_face_ext(jxf_handle h, int face, int ext_mask, const double* prims, double* slab, void* stream) {
+  return face_slab(h, face, ext_mask, const_cast<double*>(prims), nullptr, slab, 0, stream);
+}
+extern "C" int jxf_unpack_face_ext(jxf_handle h, int face, int ext_mask, const double* slab, double* prims, double* cons,
+                                   void* stream) {
+  return face_slab(h, face, ext_mask, prims, cons, const_cast<double*>(slab), 1, stream);
 }
 
 extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n, double gamma,

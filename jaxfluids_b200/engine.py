@@ -241,14 +241,15 @@ class BlockSolver:
         _lib.check(self.lib.jxf_profile_read(self._h, ms, timed, launches, int(bool(reset))))
         return {k: (ms[i], timed[i], launches[i]) for i, k in enumerate(self.PROFILE_KINDS)}
 
-    def face_slab_elems(self, face: int) -> int:
-        return int(self.lib.jxf_face_slab_elems(self._h, int(face)))
+    def face_slab_elems(self, face: int, ext_mask: int = 0) -> int:
+        return int(self.lib.jxf_face_slab_elems_ext(self._h, int(face), int(ext_mask)))
 
-    def pack_face(self, face: int, prims, slab):
-        _lib.check(self.lib.jxf_pack_face(self._h, int(face), _ptr(prims), _ptr(slab), _stream()))
+    def pack_face(self, face: int, prims, slab, ext_mask: int = 0):
+        _lib.check(self.lib.jxf_pack_face_ext(self._h, int(face), int(ext_mask), _ptr(prims), _ptr(slab), _stream()))
 
-    def unpack_face(self, face: int, slab, prims, cons):
-        _lib.check(self.lib.jxf_unpack_face(self._h, int(face), _ptr(slab), _ptr(prims), _ptr(cons), _stream()))
+    def unpack_face(self, face: int, slab, prims, cons, ext_mask: int = 0):
+        _lib.check(self.lib.jxf_unpack_face_ext(self._h, int(face), int(ext_mask), _ptr(slab), _ptr(prims), _ptr(cons),
+                                                _stream()))
 
 
 class BlockState:

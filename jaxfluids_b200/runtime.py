@@ -71,9 +71,7 @@ class BlockRuntime:
             prandtl_number=case.material_setup.transport.prandtl_number,
             gas_constant=case.material_setup.specific_gas_constant,
         )
-        if self.cfg.is_dissipative and parallel.is_parallel:
-            raise NotImplementedError("the viscous / heat flux with a domain decomposition (inter-block edge halo "
-                                      "exchange) is not implemented on the B200 path yet")
+
         self.solver = BlockSolver(self.cfg)
         s = self.solver
         self.device = s.device
@@ -87,11 +85,15 @@ class BlockRuntime:
         self.time = s.new_scalars(1, 0.0)
         self.dt = s.new_scalars(1, 0.0)
         self._sign = torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=self.device)
-        self.send = {f: torch.empty(s.face_slab_elems(FACE_ID[f]), dtype=torch.float64, device=self.device)
-                     for f in self.neighbors}
+        # With the dissipative fluxes the exchange also carries EDGE halos: faces go axis by axis, each slab widened
+        # over the transverse halos that are already complete (ext_mask, see jxf_pack_face_ext)
+        self.ext_mask = {f: (self._edge_ext_mask(f) if self.cfg.is_dissipative else 0) for f in self.neighbors}
+        self.send = {f: torch.empty(s.face_slab_elems(FACE_ID[f], self.ext_mask[f]), dtype=torch.float64,
+                                    device=self.device) for f in self.neighbors}
         self.recv = {f: torch.empty_like(self.send[f]) for f in self.neighbors}
         # inter-block exchange runs on its own stream and overlaps the first sweep of the next stage
-        self.overlap = bool(self.neighbors) and os.environ.get("JXF_OVERLAP", "1") != "0"
+        self.overlap = (bool(self.neighbors) and os.environ.get("JXF_OVERLAP", "1") != "0"
+                        and not self.cfg.is_dissipative)
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.neighbors else None
         self._pending = None                      # event: halos of the current primitives are complete
         first = s.active[0]
@@ -145,9 +147,44 @@ class BlockRuntime:
         return float(self.dt.item()), float(info[1]), float(info[2])
 
     # -- halo update ----------------------------------------------------------
+    def _edge_ext_mask(self, face: str) -> int:
+        """Transverse widening of the slab of a shared face: over ALL halos of the axes exchanged before this one
+        (lower axis index), and over the PHYSICAL-boundary halos of the axes exchanged after it."""
+        ax = FACE_ID[face] >> 1
+        t1 = 1 if ax == 0 else 0
+        t2 = 1 if ax == 2 else 2
+        mask = 0
+        for bit, t in ((0, t1), (2, t2)):
+            if self.cfg.cells[t] <= 1:
+                continue
+            for side, f in ((0, FACES[2 * t + 1]), (1, FACES[2 * t])):      # low side face, high side face
+                physical = self.bc_block[f] not in ("NEIGHBOR", "INACTIVE")
+                if t < ax or physical:
+                    mask |= 1 << (bit + side)
+        return mask
+
+    def _halo_update_with_edges(self, prims: torch.Tensor, cons: torch.Tensor, local_done: bool):
+        """Dissipative path on several blocks: physical faces + physical edges locally, then the shared faces
+        axis by axis with widened slabs (inter-block edge halos; halos/inner/halo_communication.py)."""
+        s = self.solver
+        if not local_done:
+            s.halo_fill(prims, cons)                     # physical faces, then edges between two physical faces
+        for ax in range(3):
+            faces = {f: nb for f, nb in self.neighbors.items() if FACE_ID[f] >> 1 == ax}
+            if not faces:
+                continue
+            for f in faces:
+                s.pack_face(FACE_ID[f], prims, self.send[f], self.ext_mask[f])
+            for r in self.parallel.exchange(faces, self.send, self.recv):
+                r.wait()
+            for f in faces:
+                s.unpack_face(FACE_ID[f], self.recv[f], prims, cons, self.ext_mask[f])
+
     def halo_update(self, prims: torch.Tensor, cons: torch.Tensor, local_done: bool = False):
         """halo_manager.py:146-234: inter-block faces (inner/material.py:30-93) then outer BCs."""
         s = self.solver
+        if self.neighbors and self.cfg.is_dissipative:
+            return self._halo_update_with_edges(prims, cons, local_done)
         if self.neighbors:
             for f in self.neighbors:
                 s.pack_face(FACE_ID[f], prims, self.send[f])

@@ -36,6 +36,11 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl")
 rank = dist.get_rank()
 s = H.make_setup(cells, bc=bc, gamma=1.4, length=1.0)
+visc = os.environ.get("JXF_VISC", "0") == "1"
+if visc:
+    s.is_viscous_flux = s.is_heat_flux = True
+    s.dynamic_viscosity, s.bulk_viscosity = 0.02, 0.003
+    s.thermal_conductivity_model, s.prandtl_number, s.gas_constant = "PRANDTL", 0.71, 1.0
 prims0 = H.smooth_ic(s, seed=21, amp=0.1)
 case = {
   "general": {"case_name": "mg", "end_step": nsteps, "save_path": "./results"},
@@ -49,6 +54,12 @@ num = {"conservatives": {"halo_cells": 5, "time_integration": {"integrator": "RK
        "convective_fluxes": {"convective_solver": "GODUNOV", "godunov": {"riemann_solver": "HLLC", "signal_speed": "EINFELDT",
        "reconstruction_stencil": "WENO5-Z", "reconstruction_variable": "CHAR-PRIMITIVE"}}},
        "active_physics": {"is_convective_flux": True}, "output": {"logging": {"level": "NONE"}}}
+if visc:
+    num["active_physics"].update(is_viscous_flux=True, is_heat_flux=True)
+    num["conservatives"]["dissipative_fluxes"] = {"reconstruction_stencil": "CENTRAL4", "derivative_stencil_center": "CENTRAL4",
+                                                  "derivative_stencil_face": "CENTRAL4"}
+    case["material_properties"]["transport"] = {"dynamic_viscosity": {"model": "CUSTOM", "value": 0.02}, "bulk_viscosity": 0.003,
+                                                "thermal_conductivity": {"model": "PRANDTL", "prandtl_number": 0.71}}
 im = InputManager(case, num)
 init = InitializationManager(im)
 active = [i for i in range(3) if cells[i] > 1]
@@ -83,15 +94,18 @@ dist.destroy_process_group()
 '''
 
 
+@pytest.mark.parametrize("visc", [0, 1])
 @pytest.mark.parametrize("split,cells,bc", [((2, 1, 1), (32, 20, 36), "PERIODIC"), ((1, 2, 1), (20, 32, 36), "SYMMETRY"),
-                                            ((1, 1, 2), (12, 16, 80), "PERIODIC"), ((2, 1, 1), (64, 24, 1), "ZEROGRADIENT")])
-def test_two_blocks_match_single_block_oracle(split, cells, bc, tmp_path):
+                                            ((1, 1, 2), (12, 16, 80), "PERIODIC"), ((2, 1, 1), (64, 24, 1), "ZEROGRADIENT"),
+                                            ((1, 2, 1), (24, 40, 20), "ZEROGRADIENT")])
+def test_two_blocks_match_single_block_oracle(split, cells, bc, visc, tmp_path):
+    """visc=1: viscous + heat flux, i.e. the inter-block EDGE halos ride on the widened face slabs."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     worker = tmp_path / "worker.py"
     worker.write_text(WORKER)
     env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="4",
-               JXF_CELLS=",".join(map(str, cells)))
+               JXF_CELLS=",".join(map(str, cells)), JXF_VISC=str(visc))
     port_no = 29500 + (os.getpid() % 200)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port_no), str(worker)],

@@ -87,3 +87,26 @@ def test_two_rank_exchange_routing(split, cells, bc):
             inner = hi_face if rank == 0 else lo_face
             outer = lo_face if rank == 0 else hi_face
             assert types[inner] == "NEIGHBOR" and types[outer] == bc and len(nbrs) == 1
+
+
+def test_edge_widening_masks_of_shared_faces():
+    """Which transverse halos a shared face's slab is widened over on the dissipative path (runtime.
+    BlockRuntime._edge_ext_mask): all halos of the axes exchanged earlier, the PHYSICAL halos of the later ones.
+    bit 0/1 = low/high side of the slower transverse axis, bit 2/3 = of the faster one."""
+    from types import SimpleNamespace
+    from jaxfluids_b200.runtime import BlockRuntime
+    # block (0,0,0) of a (2,2,1) split, SYMMETRY walls: east + north shared, west/south/top/bottom physical
+    rt = SimpleNamespace(cfg=SimpleNamespace(cells=(16, 16, 16)),
+                         bc_block={"east": "NEIGHBOR", "west": "SYMMETRY", "north": "NEIGHBOR", "south": "SYMMETRY",
+                                   "top": "SYMMETRY", "bottom": "SYMMETRY"})
+    m = lambda f: BlockRuntime._edge_ext_mask(rt, f)
+    # x face: transverse (y, z) are exchanged later -> only their physical sides: south (y low), bottom, top
+    assert m("east") == (1 << 0) | (1 << 2) | (1 << 3)
+    # y face: transverse (x, z): x was exchanged earlier -> both sides; z physical on both sides
+    assert m("north") == 0b1111
+    # 2-D block (z inactive): y face widened over both x sides only
+    rt2 = SimpleNamespace(cfg=SimpleNamespace(cells=(16, 16, 1)),
+                          bc_block={"east": "ZEROGRADIENT", "west": "NEIGHBOR", "north": "NEIGHBOR", "south": "NEIGHBOR",
+                                    "top": "INACTIVE", "bottom": "INACTIVE"})
+    assert BlockRuntime._edge_ext_mask(rt2, "north") == 0b0011
+    assert BlockRuntime._edge_ext_mask(rt2, "west") == 0           # y sides are shared and exchanged later
