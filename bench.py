@@ -305,7 +305,7 @@ def main():
     if world > 1:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
-        dist.init_process_group(backend="nccl")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         if rank == 0:
             entry.build()
         dist.barrier()
