@@ -32,6 +32,8 @@ typedef enum jxf_status {
 
 /* ref: stencils/__init__.py:15-19 + godunov.reconstruction_variable (read_conservatives.py:126-203) */
 enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
+/* ref: stencils/reconstruction/shock_capturing/weno/weno5_z.py, weno5_js.py (DICT_SPATIAL_RECONSTRUCTION) */
+enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1 };
 /* ref: solvers/riemann_solvers/__init__.py:16-34 */
 enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1 };
 enum { JXF_SIGNAL_EINFELDT = 0 };
@@ -50,7 +52,7 @@ typedef struct jxf_config {
   double  gamma;         /* IdealGas specific_heat_ratio                                         */
   double  cfl;           /* time_integration.CFL                                                 */
   double  fixed_dt;      /* time_integration.fixed_timestep, 0 = CFL based                       */
-  int32_t recon;         /* JXF_RECON_*     (stencil is WENO5-Z)                                 */
+  int32_t recon;         /* JXF_RECON_*     (the stencil is `stencil` below)                     */
   int32_t riemann;       /* JXF_RIEMANN_*                                                        */
   int32_t signal_speed;  /* JXF_SIGNAL_*                                                         */
   int32_t integrator;    /* JXF_INT_*                                                            */
@@ -60,7 +62,7 @@ typedef struct jxf_config {
   int32_t viscous_flux;             /* 0/1                                                        */
   int32_t heat_flux;                /* 0/1                                                        */
   int32_t viscous_heat_production;  /* 0/1: u.tau in the energy flux (default 1)                  */
-  int32_t reserved0;
+  int32_t stencil;                  /* JXF_STENCIL_*: godunov.reconstruction_stencil (0 = WENO5-Z)    */
   double  dynamic_viscosity;        /* transport/dynamic_viscosity, model CUSTOM (constant)       */
   double  bulk_viscosity;           /* transport/bulk_viscosity                                   */
   double  thermal_conductivity;     /* constant lambda: CUSTOM value, or cp*mu/Pr for PRANDTL     */
@@ -223,7 +225,8 @@ int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* laun
 
 /* Test hook: the per-face device function (reconstruction + Riemann flux,
  * ref: HighOrderGodunov.compute_flux_xi, high_order_godunov.py:117-231) on caller-supplied
- * 6-cell windows.  windows: (n, 5, 6) doubles, flux: (n, 5) doubles, both on the device. */
+ * 6-cell windows.  windows: (n, 5, 6) doubles, flux: (n, 5) doubles, both on the device.
+ * `recon` = JXF_RECON_* + 2 * JXF_STENCIL_*. */
 int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n,
                         double gamma, double* flux, void* stream);
 

@@ -21,6 +21,7 @@ EXPORTS = (
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
+STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1}
 RIEMANN = {"HLLC": 0, "RUSANOV": 1}
 SIGNAL = {"EINFELDT": 0}
 INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
@@ -45,7 +46,7 @@ class JxfConfig(C.Structure):
         ("viscous_flux", C.c_int32),
         ("heat_flux", C.c_int32),
         ("viscous_heat_production", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("stencil", C.c_int32),
         ("dynamic_viscosity", C.c_double),
         ("bulk_viscosity", C.c_double),
         ("thermal_conductivity", C.c_double),

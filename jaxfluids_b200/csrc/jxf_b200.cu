@@ -1044,6 +1044,8 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     if (cfg->n[i] < 1) return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d", i, cfg->n[i]);
   if (cfg->recon != JXF_RECON_PRIMITIVE && cfg->recon != JXF_RECON_CHAR_PRIMITIVE)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
+  if (cfg->stencil != JXF_STENCIL_WENO5Z && cfg->stencil != JXF_STENCIL_WENO5JS)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
   if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
   if (cfg->signal_speed != JXF_SIGNAL_EINFELDT)
@@ -1382,12 +1384,18 @@ static int dispatch_riemann(const jxf_solver* s, const SweepArgs& a, int epi, cu
 }
 template <int A>
 static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  // kernels' RECON parameter = reconstruction variable + 2 * stencil (numerics.cuh)
 #ifdef JXF_TUNE_ONLY
-  if (s->cfg.recon != JXF_RECON_CHAR_PRIMITIVE) return fail(JXF_ERR_UNSUPPORTED, "tuning build: CHAR-PRIMITIVE only");
+  if (s->cfg.recon != JXF_RECON_CHAR_PRIMITIVE || s->cfg.stencil != JXF_STENCIL_WENO5Z)
+    return fail(JXF_ERR_UNSUPPORTED, "tuning build: WENO5-Z CHAR-PRIMITIVE only");
   return dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
 #else
-  return s->cfg.recon == JXF_RECON_PRIMITIVE ? dispatch_riemann<A, RECON_PRIMITIVE>(s, a, epi, st)
-                                             : dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
+  switch (s->cfg.recon + 2 * s->cfg.stencil) {
+    case 0: return dispatch_riemann<A, 0>(s, a, epi, st);
+    case 1: return dispatch_riemann<A, 1>(s, a, epi, st);
+    case 2: return dispatch_riemann<A, 2>(s, a, epi, st);
+    default: return dispatch_riemann<A, 3>(s, a, epi, st);
+  }
 #endif
 }
 static int dispatch_axis(const jxf_solver* s, int axis, const SweepArgs& a, int epi, cudaStream_t st) {
@@ -1802,6 +1810,8 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   JXF_DBG_CASE(0, 0, 0) JXF_DBG_CASE(0, 0, 1) JXF_DBG_CASE(0, 1, 0) JXF_DBG_CASE(0, 1, 1)
   JXF_DBG_CASE(1, 0, 0) JXF_DBG_CASE(1, 0, 1) JXF_DBG_CASE(1, 1, 0) JXF_DBG_CASE(1, 1, 1)
   JXF_DBG_CASE(2, 0, 0) JXF_DBG_CASE(2, 0, 1) JXF_DBG_CASE(2, 1, 0) JXF_DBG_CASE(2, 1, 1)
+  JXF_DBG_CASE(0, 2, 0) JXF_DBG_CASE(0, 3, 0) JXF_DBG_CASE(1, 2, 0) JXF_DBG_CASE(1, 3, 0)
+  JXF_DBG_CASE(2, 2, 0) JXF_DBG_CASE(2, 3, 0)
 #endif
 #undef JXF_DBG_CASE
   return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");

@@ -13,7 +13,9 @@ namespace jxf {
 constexpr double kStencilEps = 1e-30;                 // config/precision.py:53
 constexpr double kEps = 2.220446049250313e-16;        // config/precision.py:44-55
 
-enum { RECON_PRIMITIVE = 0, RECON_CHAR_PRIMITIVE = 1 };
+enum { RECON_PRIMITIVE = 0, RECON_CHAR_PRIMITIVE = 1 };   // reconstruction variable = RECON & 1
+enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1 };          // reconstruction stencil  = RECON >> 1
+// The kernels' RECON template parameter carries both: RECON = variable + 2 * stencil.
 enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
 
 // velocity_minor_axes, equation_information.py:110
@@ -48,7 +50,8 @@ template <> struct AxisIds<2> { static constexpr int un = 3, t0 = 1, t1 = 2; };
 //           weno/weno5_z.py:32-52).  (a,b,c,d,e) = cells i-2..i+2 for the left
 //           state, mirrored (i+3..i-1) for the right state.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
+template <int ST>
+__device__ __forceinline__ double weno5(double a, double b, double c, double d, double e) {
   const double s0 = a - 2.0 * b + c;
   const double q0 = a - 4.0 * b + 3.0 * c;
   const double s1 = b - 2.0 * c + d;
@@ -58,10 +61,17 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
   const double beta0 = (13.0 / 12.0) * (s0 * s0) + 0.25 * (q0 * q0);
   const double beta1 = (13.0 / 12.0) * (s1 * s1) + 0.25 * (q1 * q1);
   const double beta2 = (13.0 / 12.0) * (s2 * s2) + 0.25 * (q2 * q2);
-  const double tau5 = fabs(beta0 - beta2);
-  const double alpha0 = 0.1 * (1.0 + tau5 / (beta0 + kStencilEps));
-  const double alpha1 = 0.6 * (1.0 + tau5 / (beta1 + kStencilEps));
-  const double alpha2 = 0.3 * (1.0 + tau5 / (beta2 + kStencilEps));
+  double alpha0, alpha1, alpha2;
+  if (ST == STENCIL_WENO5Z) {
+    const double tau5 = fabs(beta0 - beta2);
+    alpha0 = 0.1 * (1.0 + tau5 / (beta0 + kStencilEps));
+    alpha1 = 0.6 * (1.0 + tau5 / (beta1 + kStencilEps));
+    alpha2 = 0.3 * (1.0 + tau5 / (beta2 + kStencilEps));
+  } else {   // WENO5-JS, weno/weno5_js.py:36-43
+    alpha0 = 0.1 * (1.0 / (beta0 * beta0 + kStencilEps));
+    alpha1 = 0.6 * (1.0 / (beta1 * beta1 + kStencilEps));
+    alpha2 = 0.3 * (1.0 / (beta2 * beta2 + kStencilEps));
+  }
   const double inv = 1.0 / (alpha0 + alpha1 + alpha2);
   const double p0 = (1.0 / 3.0) * a + (-7.0 / 6.0) * b + (11.0 / 6.0) * c;
   const double p1 = (-1.0 / 6.0) * b + (5.0 / 6.0) * c + (1.0 / 3.0) * d;
@@ -69,9 +79,10 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
   return (alpha0 * inv) * p0 + (alpha1 * inv) * p1 + (alpha2 * inv) * p2;
 }
 
+template <int ST>
 __device__ __forceinline__ void weno5z_lr(const double (&q)[6], double& left, double& right) {
-  left = weno5z(q[0], q[1], q[2], q[3], q[4]);
-  right = weno5z(q[5], q[4], q[3], q[2], q[1]);
+  left = weno5<ST>(q[0], q[1], q[2], q[3], q[4]);
+  right = weno5<ST>(q[5], q[4], q[3], q[2], q[1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -119,9 +130,9 @@ template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
                                             double (&pl)[5], double (&pr)[5]) {
   using Id = AxisIds<A>;
-  if (RECON == RECON_PRIMITIVE) {
+  if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
-    for (int v = 0; v < 5; ++v) weno5z_lr(w[v], pl[v], pr[v]);
+    for (int v = 0; v < 5; ++v) weno5z_lr<(RECON >> 1)>(w[v], pl[v], pr[v]);
   } else {
     const double rho_ave = 0.5 * (w[0][2] + w[0][3]);
     const double p_ave = 0.5 * (w[4][2] + w[4][3]);
@@ -133,15 +144,15 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
     double q[6], l0, r0, l1, r1, l4, r4;
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = -k_u * w[Id::un][k] + k_p * w[4][k];
-    weno5z_lr(q, l0, r0);
+    weno5z_lr<(RECON >> 1)>(q, l0, r0);
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = w[0][k] - k_cc * w[4][k];
-    weno5z_lr(q, l1, r1);
+    weno5z_lr<(RECON >> 1)>(q, l1, r1);
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = k_u * w[Id::un][k] + k_p * w[4][k];
-    weno5z_lr(q, l4, r4);
-    weno5z_lr(w[Id::t0], pl[Id::t0], pr[Id::t0]);
-    weno5z_lr(w[Id::t1], pl[Id::t1], pr[Id::t1]);
+    weno5z_lr<(RECON >> 1)>(q, l4, r4);
+    weno5z_lr<(RECON >> 1)>(w[Id::t0], pl[Id::t0], pr[Id::t0]);
+    weno5z_lr<(RECON >> 1)>(w[Id::t1], pl[Id::t1], pr[Id::t1]);
     const double ccr = cc_ave * rho_ave;
     pl[0] = rho_ave * (l0 + l4) + l1;
     pl[Id::un] = c_ave * (-l0 + l4);
@@ -261,10 +272,15 @@ __device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a
 //   right face value = q3 + cr   (mirror cells i+3..i-1, centre i+1)
 // beta~_k = (12/13) beta_k = e^2 + (3/13) t^2 ; tau, eps scale alike so tau/(beta+eps) is unchanged.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, double d3, double d4,
-                                            double& cl, double& cr) {
+// WENO5-JS (weno/weno5_js.py:32-50): alpha_k = d_k / (beta_k^2 + eps); with B_k = beta~_k^2 + eps~^2 (the same
+// common-factor scaling, (12/13)^2 on both terms) omega_k = d_k prod_{j!=k} B_j / sum -- the same one-reciprocal
+// form with tau = 0 and b_k replaced by B_k.
+template <int ST>
+__device__ __forceinline__ void weno5_corr(double d0, double d1, double d2, double d3, double d4,
+                                           double& cl, double& cr) {
   constexpr double k = 3.0 / 13.0;
-  constexpr double eps = kStencilEps * (12.0 / 13.0);
+  constexpr double eps = (ST == STENCIL_WENO5Z) ? kStencilEps * (12.0 / 13.0) : 0.0;
+  constexpr double eps_js = kStencilEps * (12.0 / 13.0) * (12.0 / 13.0);
   const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;      // second differences
   // eps is folded into the squared second differences: beta~_k + eps~ = k t^2 + (e^2 + eps~)
   const double s1 = fma(e1, e1, eps), s2 = fma(e2, e2, eps), s3 = fma(e3, e3, eps), s4 = fma(e4, e4, eps);
@@ -272,17 +288,22 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
   const double tl0 = fma(3.0, d1, -d0), tl1 = d1 + d2, tl2 = fma(-3.0, d2, d3);
   // right stencils (mirrored): d4 - 3 d3 ; d2 + d3 ; 3 d2 - d1
   const double tr0 = fma(-3.0, d3, d4), tr1 = d2 + d3, tr2 = fma(3.0, d2, -d1);
-  const double bl0 = fma(k, tl0 * tl0, s1), bl1 = fma(k, tl1 * tl1, s2), bl2 = fma(k, tl2 * tl2, s3);
-  const double br0 = fma(k, tr0 * tr0, s4), br1 = fma(k, tr1 * tr1, s3), br2 = fma(k, tr2 * tr2, s2);
+  double bl0 = fma(k, tl0 * tl0, s1), bl1 = fma(k, tl1 * tl1, s2), bl2 = fma(k, tl2 * tl2, s3);
+  double br0 = fma(k, tr0 * tr0, s4), br1 = fma(k, tr1 * tr1, s3), br2 = fma(k, tr2 * tr2, s2);
+  if (ST == STENCIL_WENO5JS) {
+    bl0 = fma(bl0, bl0, eps_js); bl1 = fma(bl1, bl1, eps_js); bl2 = fma(bl2, bl2, eps_js);
+    br0 = fma(br0, br0, eps_js); br1 = fma(br1, br1, eps_js); br2 = fma(br2, br2, eps_js);
+  }
   {
-    const double tau = fabs(bl0 - bl2);           // eps cancels in the difference
+    const double tau = (ST == STENCIL_WENO5Z) ? fabs(bl0 - bl2) : 0.0;           // eps cancels in the difference
     // n_k = d_k (b_k + tau) prod_{j != k} b_j = d_k (P + tau prod_{j != k} b_j), P = b0 b1 b2, with the
     // common factor 1/10 dropped: d = (1, 6, 3)
     const double p12 = bl1 * bl2, p02 = bl0 * bl2, p01 = bl0 * bl1;
     const double P = bl0 * p12;
-    const double n0 = fma(tau, p12, P);
-    const double m1 = fma(tau, p02, P);
-    const double m2 = fma(tau, p01, P);
+    // Z: (b_k + tau) prod_{j != k} b_j ; JS: prod_{j != k} B_j
+    const double n0 = (ST == STENCIL_WENO5Z) ? fma(tau, p12, P) : p12;
+    const double m1 = (ST == STENCIL_WENO5Z) ? fma(tau, p02, P) : p02;
+    const double m2 = (ST == STENCIL_WENO5Z) ? fma(tau, p01, P) : p01;
     const double den = fma(6.0, m1, fma(3.0, m2, n0));
     // p_k - c:  p0-c = 5/6 d1 - 1/3 d0 ; p1-c = 1/3 d2 + 1/6 d1 ; p2-c = 2/3 d2 - 1/6 d3   (x d_k)
     const double q0 = fma(5.0 / 6.0, d1, (-1.0 / 3.0) * d0);
@@ -292,12 +313,12 @@ __device__ __forceinline__ void weno5z_corr(double d0, double d1, double d2, dou
     cl = num * rcp_fast(den);
   }
   {
-    const double tau = fabs(br0 - br2);
+    const double tau = (ST == STENCIL_WENO5Z) ? fabs(br0 - br2) : 0.0;
     const double p12 = br1 * br2, p02 = br0 * br2, p01 = br0 * br1;
     const double P = br0 * p12;
-    const double n0 = fma(tau, p12, P);
-    const double m1 = fma(tau, p02, P);
-    const double m2 = fma(tau, p01, P);
+    const double n0 = (ST == STENCIL_WENO5Z) ? fma(tau, p12, P) : p12;
+    const double m1 = (ST == STENCIL_WENO5Z) ? fma(tau, p02, P) : p02;
+    const double m2 = (ST == STENCIL_WENO5Z) ? fma(tau, p01, P) : p01;
     const double den = fma(6.0, m1, fma(3.0, m2, n0));
     // mirrored differences d0'=-d4, d1'=-d3, d2'=-d2, d3'=-d1
     const double q0 = fma(-5.0 / 6.0, d3, (1.0 / 3.0) * d4);
@@ -322,20 +343,25 @@ struct WenoG {
   double g0, g1, g2;
 };
 
+template <int ST>
 __device__ __forceinline__ WenoG weno5z_g(double D0, double D1, double D2, double D3) {
   constexpr double k = 3.0 / 13.0;
-  constexpr double eps = kStencilEps * (12.0 / 13.0);
+  constexpr double eps = (ST == STENCIL_WENO5Z) ? kStencilEps * (12.0 / 13.0) : 0.0;
+  constexpr double eps_js = kStencilEps * (12.0 / 13.0) * (12.0 / 13.0);
   const double e1 = D1 - D0, e2 = D2 - D1, e3 = D3 - D2;
   const double s1 = fma(e1, e1, eps), s2 = fma(e2, e2, eps), s3 = fma(e3, e3, eps);
   const double t0 = fma(3.0, D1, -D0), t1 = D1 + D2, t2 = fma(-3.0, D2, D3);
-  const double b0 = fma(k, t0 * t0, s1), b1 = fma(k, t1 * t1, s2), b2 = fma(k, t2 * t2, s3);
-  const double tau = fabs(b0 - b2);
+  double b0 = fma(k, t0 * t0, s1), b1 = fma(k, t1 * t1, s2), b2 = fma(k, t2 * t2, s3);
+  if (ST == STENCIL_WENO5JS) {
+    b0 = fma(b0, b0, eps_js); b1 = fma(b1, b1, eps_js); b2 = fma(b2, b2, eps_js);
+  }
+  const double tau = (ST == STENCIL_WENO5Z) ? fabs(b0 - b2) : 0.0;
   const double p12 = b1 * b2, p02 = b0 * b2, p01 = b0 * b1;
   const double P = b0 * p12;
   WenoG g;
-  g.g0 = fma(tau, p12, P);
-  g.g1 = fma(tau, p02, P);
-  g.g2 = fma(tau, p01, P);
+  g.g0 = (ST == STENCIL_WENO5Z) ? fma(tau, p12, P) : p12;
+  g.g1 = (ST == STENCIL_WENO5Z) ? fma(tau, p02, P) : p02;
+  g.g2 = (ST == STENCIL_WENO5Z) ? fma(tau, p01, P) : p01;
   return g;
 }
 // left state of the face to the right of the cell: cell value + this
@@ -395,11 +421,11 @@ template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
                                             double (&pl)[5], double (&pr)[5]) {
   using Id = AxisIds<A>;
-  if (RECON == RECON_PRIMITIVE) {
+  if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
       double cl, cr;
-      weno5z_corr(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3], w[v][5] - w[v][4], cl, cr);
+      weno5_corr<(RECON >> 1)>(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3], w[v][5] - w[v][4], cl, cr);
       pl[v] = w[v][2] + cl;
       pr[v] = w[v][3] + cr;
     }
@@ -432,16 +458,16 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
         c[k] = fma(k_u, du[k], t);                    // d W4
         b[k] = fma(-k_cc, dp[k], dr[k]);              // d W1
       }
-      weno5z_corr(a[0], a[1], a[2], a[3], a[4], l0, r0);
-      weno5z_corr(b[0], b[1], b[2], b[3], b[4], l1, r1);
-      weno5z_corr(c[0], c[1], c[2], c[3], c[4], l4, r4);
+      weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
+      weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
+      weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
     }
     double tl, tr;
-    weno5z_corr(w[Id::t0][1] - w[Id::t0][0], w[Id::t0][2] - w[Id::t0][1], w[Id::t0][3] - w[Id::t0][2],
+    weno5_corr<(RECON >> 1)>(w[Id::t0][1] - w[Id::t0][0], w[Id::t0][2] - w[Id::t0][1], w[Id::t0][3] - w[Id::t0][2],
                 w[Id::t0][4] - w[Id::t0][3], w[Id::t0][5] - w[Id::t0][4], tl, tr);
     pl[Id::t0] = w[Id::t0][2] + tl;
     pr[Id::t0] = w[Id::t0][3] + tr;
-    weno5z_corr(w[Id::t1][1] - w[Id::t1][0], w[Id::t1][2] - w[Id::t1][1], w[Id::t1][3] - w[Id::t1][2],
+    weno5_corr<(RECON >> 1)>(w[Id::t1][1] - w[Id::t1][0], w[Id::t1][2] - w[Id::t1][1], w[Id::t1][3] - w[Id::t1][2],
                 w[Id::t1][4] - w[Id::t1][3], w[Id::t1][5] - w[Id::t1][4], tl, tr);
     pl[Id::t1] = w[Id::t1][2] + tl;
     pr[Id::t1] = w[Id::t1][3] + tr;
@@ -459,7 +485,7 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
 // Carry of the cell-centred weights between consecutive faces of a marching sweep.
 template <int RECON>
 struct ReconCarry {
-  static constexpr int N = (RECON == RECON_PRIMITIVE) ? 5 : 2;   // fields reconstructed as they are
+  static constexpr int N = ((RECON & 1) == RECON_PRIMITIVE) ? 5 : 2;   // fields reconstructed as they are
   WenoG g[N];
 };
 
@@ -470,8 +496,8 @@ __device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconC
   using Id = AxisIds<A>;
 #pragma unroll
   for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
-    const int v = (RECON == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
-    cy.g[j] = weno5z_g(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3]);
+    const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+    cy.g[j] = weno5z_g<(RECON >> 1)>(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3]);
   }
 }
 
@@ -483,15 +509,15 @@ __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], doubl
   using Id = AxisIds<A>;
 #pragma unroll
   for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
-    const int v = (RECON == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+    const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
     const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
                  d4 = w[v][5] - w[v][4];
     pl[v] = w[v][2] + weno5z_left_corr(cy.g[j], d0, d1, d2, d3);
-    const WenoG gn = weno5z_g(d1, d2, d3, d4);
+    const WenoG gn = weno5z_g<(RECON >> 1)>(d1, d2, d3, d4);
     pr[v] = w[v][3] + weno5z_right_corr(gn, d1, d2, d3, d4);
     cy.g[j] = gn;
   }
-  if (RECON != RECON_PRIMITIVE) {
+  if ((RECON & 1) != RECON_PRIMITIVE) {
     double dr[5], du[5], dp[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -518,9 +544,9 @@ __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], doubl
         c[k] = fma(k_u, du[k], t);
         b[k] = fma(-k_cc, dp[k], dr[k]);
       }
-      weno5z_corr(a[0], a[1], a[2], a[3], a[4], l0, r0);
-      weno5z_corr(b[0], b[1], b[2], b[3], b[4], l1, r1);
-      weno5z_corr(c[0], c[1], c[2], c[3], c[4], l4, r4);
+      weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
+      weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
+      weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
     }
     const double sl = l0 + l4, sr = r0 + r4;
     pl[0] = w[0][2] + fma(rho_ave, sl, l1);

@@ -28,6 +28,7 @@ class BlockConfig:
     bc: Dict[str, str]                          # face -> INACTIVE|PERIODIC|SYMMETRY|ZEROGRADIENT|NEIGHBOR
     nh: int = 5
     recon: str = "CHAR-PRIMITIVE"
+    stencil: str = "WENO5-Z"
     riemann: str = "HLLC"
     signal_speed: str = "EINFELDT"
     integrator: str = "RK3"
@@ -76,6 +77,7 @@ class BlockConfig:
         c.cfl = float(self.cfl)
         c.fixed_dt = float(self.fixed_dt or 0.0)
         c.recon = lookup(_lib.RECON, self.recon, "reconstruction_variable")
+        c.stencil = lookup(_lib.STENCIL, self.stencil, "reconstruction_stencil")
         c.riemann = lookup(_lib.RIEMANN, self.riemann, "riemann_solver")
         c.signal_speed = lookup(_lib.SIGNAL, self.signal_speed, "signal_speed")
         c.integrator = lookup(_lib.INTEGRATOR, self.integrator, "integrator")

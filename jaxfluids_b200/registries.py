@@ -37,7 +37,7 @@ REFERENCE_BOUNDARY_TYPES = (
 DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov"}
 DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov"}
 DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt"}
-DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z"}
+DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS"}
 TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
 TUPLE_FROZEN_STATE = ("ARITHMETIC",)
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
@@ -45,7 +45,7 @@ DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKu
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
 TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE")
 
-REQUIRED_HALOS = {"WENO5-Z": 3}   # weno5_base.py:18
+REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3}   # weno5_base.py:18
 
 
 def select(value, reference_names, implemented, path, setup="numerical"):

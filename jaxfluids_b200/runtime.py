@@ -56,6 +56,7 @@ class BlockRuntime:
             bc=self.bc_block,
             nh=di.nh_conservatives,
             recon=god.reconstruction_variable,
+            stencil=god.reconstruction_stencil,
             riemann=god.riemann_solver,
             signal_speed=god.signal_speed,
             integrator=ti.integrator,

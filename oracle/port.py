@@ -48,6 +48,7 @@ class Setup:
     gamma: float
     nh: int = 5
     recon: str = "CHAR-PRIMITIVE"                # or PRIMITIVE
+    stencil: str = "WENO5-Z"                     # or WENO5-JS (godunov.reconstruction_stencil)
     riemann: str = "HLLC"                        # or RUSANOV
     integrator: str = "RK3"
     cfl: float = 0.5
@@ -282,6 +283,28 @@ def weno5z(a, b, c, d, e):
     return omega_0 * p_0 + omega_1 * p_1 + omega_2 * p_2
 
 
+def weno5js(a, b, c, d, e):
+    """weno5_base.py:34-51 and weno/weno5_js.py:32-50."""
+    beta_0 = 13.0 / 12.0 * np.square(a - 2 * b + c) + 1.0 / 4.0 * np.square(a - 4 * b + 3 * c)
+    beta_1 = 13.0 / 12.0 * np.square(b - 2 * c + d) + 1.0 / 4.0 * np.square(b - d)
+    beta_2 = 13.0 / 12.0 * np.square(c - 2 * d + e) + 1.0 / 4.0 * np.square(3 * c - 4 * d + e)
+    one_beta_0_sq = 1.0 / (beta_0 * beta_0 + STENCIL_EPS)
+    one_beta_1_sq = 1.0 / (beta_1 * beta_1 + STENCIL_EPS)
+    one_beta_2_sq = 1.0 / (beta_2 * beta_2 + STENCIL_EPS)
+    alpha_0 = _DR[0] * one_beta_0_sq
+    alpha_1 = _DR[1] * one_beta_1_sq
+    alpha_2 = _DR[2] * one_beta_2_sq
+    one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2)
+    omega_0, omega_1, omega_2 = alpha_0 * one_alpha, alpha_1 * one_alpha, alpha_2 * one_alpha
+    p_0 = _CR[0][0] * a + _CR[0][1] * b + _CR[0][2] * c
+    p_1 = _CR[1][0] * b + _CR[1][1] * c + _CR[1][2] * d
+    p_2 = _CR[2][0] * c + _CR[2][1] * d + _CR[2][2] * e
+    return omega_0 * p_0 + omega_1 * p_1 + omega_2 * p_2
+
+
+STENCILS = {"WENO5-Z": weno5z, "WENO5-JS": weno5js}
+
+
 def _window(prims, axis, s: Setup):
     """The six cells k=i-2..i+3 around every face f (cell i = nh-1+f), transverse interior.
     eigendecomposition.py:75-95,117 ; stencils/spatial_stencil.py:45-113."""
@@ -302,6 +325,7 @@ def reconstruct(prims, axis, s: Setup):
     """high_order_godunov.py:233-419 (PRIMITIVE :267-280, CHAR-PRIMITIVE :298-316,:401-402).
     Returns (prims_L, prims_R, cons_L, cons_R), each (5, faces...)."""
     w = _window(prims, axis, s)
+    weno5z = STENCILS[s.stencil]                 # the stencil the JSON names (local name kept for brevity)
     if s.recon == "PRIMITIVE":
         pl = weno5z(w[0], w[1], w[2], w[3], w[4])
         pr = weno5z(w[5], w[4], w[3], w[2], w[1])

@@ -42,6 +42,11 @@ FIXTURES = {
                                                          dissipation=dict(mu=1 / 100, bulk=0.002, kappa=0.05)), 2, (2,)),
     "riemann2d_20x24_visc_rk3": ("riemann2d", dict(cells=(20, 24, None), dissipation=dict(mu=1e-3)), 3, (3,)),
     "sod80_visc_prandtl_rk3": ("sod", dict(cells=(80, None, None), dissipation=dict(mu=2e-3, prandtl=0.7)), 5, (5,)),
+    # WENO5-JS
+    "sod100_js_char_hllc_rk3": ("sod", dict(cells=(100, None, None), stencil="WENO5-JS"), 20, (1, 20)),
+    "riemann2d_24x28_js_prim_hllc_rk3": ("riemann2d", dict(cells=(24, 28, None), stencil="WENO5-JS", recon="PRIMITIVE"), 5, (5,)),
+    "tgv_10x12x10_per_js_prim_visc_rk3": ("tgv", dict(cells=(10, 12, 10), bc="PERIODIC", stencil="WENO5-JS", recon="PRIMITIVE",
+                                                      dissipation=dict(mu=1e-2)), 2, (2,)),
 }
 
 

@@ -59,7 +59,7 @@ def load_case(name: str):
     return case, num
 
 
-def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None):
+def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -74,6 +74,8 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         g["reconstruction_variable"] = recon
     if riemann is not None:
         g["riemann_solver"] = riemann
+    if stencil is not None:
+        g["reconstruction_stencil"] = stencil
     if integrator is not None:
         num["conservatives"]["time_integration"]["integrator"] = integrator
     # keep the reference from writing anything / printing the banner

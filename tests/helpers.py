@@ -59,6 +59,7 @@ def setup_from_json(case, num) -> port.Setup:
         gamma=case["material_properties"]["equation_of_state"]["specific_heat_ratio"],
         nh=c["halo_cells"],
         recon=g.get("reconstruction_variable", "PRIMITIVE"),
+        stencil=g.get("reconstruction_stencil", "WENO5-Z"),
         riemann=g.get("riemann_solver", "HLLC"),
         integrator=c["time_integration"]["integrator"],
         cfl=c["time_integration"].get("CFL", 0.5),
@@ -67,14 +68,14 @@ def setup_from_json(case, num) -> port.Setup:
 
 
 def make_setup(cells, bc="PERIODIC", recon="CHAR-PRIMITIVE", riemann="HLLC", integrator="RK3", gamma=1.4,
-               length=1.0, nh=5):
+               length=1.0, nh=5, stencil="WENO5-Z"):
     cells = tuple(cells)
     bcs = {}
     for f in port.FACES:
         ax = port.FACE_AXIS[f]
         bcs[f] = (bc if isinstance(bc, str) else bc[f]) if cells[ax] > 1 else "INACTIVE"
     return port.Setup(cells=cells, domain=((0.0, length),) * 3, bc=bcs, gamma=gamma, nh=nh, recon=recon,
-                      riemann=riemann, integrator=integrator)
+                      riemann=riemann, integrator=integrator, stencil=stencil)
 
 
 def smooth_ic(s: port.Setup, seed=0, amp=0.2):

@@ -40,7 +40,7 @@ def rhs_axis_march(prims, axis, s, fma=True):
     shp = w.shape[:3]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_march_host(axis, {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon], {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+    rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
                                   w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data)
     assert rc == 0
     f = out.reshape(shp + (5,))
@@ -62,7 +62,7 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     shp = w.shape[:-2]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_host(axis, {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon], {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+    rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
                             w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data)
     assert rc == 0
     f = np.moveaxis(out.reshape(shp + (5,)), -1, 0)

@@ -40,17 +40,17 @@ static void run_march(const double* win, long nseq, long len, double gamma, doub
 extern "C" int face_flux_march_host(int axis, int recon, int riemann, const double* win, long nseq, long len, double gamma,
                                     double* out) {
 #define MCASE(A, R, S) if (axis == A && recon == R && riemann == S) { run_march<A, R, S>(win, nseq, len, gamma, out); return 0; }
-  MCASE(0,0,0) MCASE(0,0,1) MCASE(0,1,0) MCASE(0,1,1)
-  MCASE(1,0,0) MCASE(1,0,1) MCASE(1,1,0) MCASE(1,1,1)
-  MCASE(2,0,0) MCASE(2,0,1) MCASE(2,1,0) MCASE(2,1,1)
+  MCASE(0,0,0) MCASE(0,0,1) MCASE(0,1,0) MCASE(0,1,1) MCASE(0,2,0) MCASE(0,2,1) MCASE(0,3,0) MCASE(0,3,1)
+  MCASE(1,0,0) MCASE(1,0,1) MCASE(1,1,0) MCASE(1,1,1) MCASE(1,2,0) MCASE(1,2,1) MCASE(1,3,0) MCASE(1,3,1)
+  MCASE(2,0,0) MCASE(2,0,1) MCASE(2,1,0) MCASE(2,1,1) MCASE(2,2,0) MCASE(2,2,1) MCASE(2,3,0) MCASE(2,3,1)
   return -1;
 }
 
 // windows: (n, 5, 6) doubles; out: (n, 5)
 extern "C" int face_flux_host(int axis, int recon, int riemann, const double* win, long n, double gamma, double* out) {
 #define CASE(A, R, S) if (axis == A && recon == R && riemann == S) { run<A, R, S>(win, n, gamma, out); return 0; }
-  CASE(0,0,0) CASE(0,0,1) CASE(0,1,0) CASE(0,1,1)
-  CASE(1,0,0) CASE(1,0,1) CASE(1,1,0) CASE(1,1,1)
-  CASE(2,0,0) CASE(2,0,1) CASE(2,1,0) CASE(2,1,1)
+  CASE(0,0,0) CASE(0,0,1) CASE(0,1,0) CASE(0,1,1) CASE(0,2,0) CASE(0,2,1) CASE(0,3,0) CASE(0,3,1)
+  CASE(1,0,0) CASE(1,0,1) CASE(1,1,0) CASE(1,1,1) CASE(1,2,0) CASE(1,2,1) CASE(1,3,0) CASE(1,3,1)
+  CASE(2,0,0) CASE(2,0,1) CASE(2,1,0) CASE(2,1,1) CASE(2,2,0) CASE(2,2,1) CASE(2,3,0) CASE(2,3,1)
   return -1;
 }

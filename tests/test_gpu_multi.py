@@ -106,11 +106,30 @@ def test_two_blocks_match_single_block_oracle(split, cells, bc, visc, tmp_path):
     worker.write_text(WORKER)
     env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="4",
                JXF_CELLS=",".join(map(str, cells)), JXF_VISC=str(visc))
+    _run_worker(worker, env, 2)
+
+
+def _run_worker(worker, env, nproc):
     port_no = 29500 + (os.getpid() % 200)
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port_no), str(worker)],
                          env=env, capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
     assert lines, out.stdout[-2000:] + out.stderr[-4000:]
     res = json.loads(lines[-1][7:])
     assert res["err"] <= 1e-12 and res["dt_err"] <= 1e-12 and res["t_err"] <= 1e-12, res
+
+
+@pytest.mark.parametrize("visc", [0, 1])
+@pytest.mark.parametrize("split,cells,bc,nproc", [((2, 2, 1), (32, 28, 20), "SYMMETRY", 4), ((2, 2, 1), (24, 32, 16), "PERIODIC", 4),
+                                                  ((1, 2, 2), (12, 24, 40), "ZEROGRADIENT", 4), ((2, 2, 2), (24, 20, 28), "SYMMETRY", 8)])
+def test_pencil_and_block_decompositions(split, cells, bc, nproc, visc, tmp_path):
+    """4 and 8 blocks: edges shared by two split axes (neighbour x neighbour), neighbour x physical edges, and
+    with visc=1 the edge halos the dissipative stencils read there."""
+    if _ngpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    worker = tmp_path / "worker.py"
+    worker.write_text(WORKER)
+    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="3",
+               JXF_CELLS=",".join(map(str, cells)), JXF_VISC=str(visc))
+    _run_worker(worker, env, nproc)

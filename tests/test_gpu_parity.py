@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def make_solver(s: port.Setup, bc=None):
     from jaxfluids_b200.engine import BlockConfig, BlockSolver
     cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min),
-                      gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, riemann=s.riemann,
+                      gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, stencil=s.stencil, riemann=s.riemann,
                       integrator=s.integrator, cfl=s.cfl,
                       is_viscous_flux=s.is_viscous_flux, is_heat_flux=s.is_heat_flux,
                       is_viscous_heat_production=s.is_viscous_heat_production, dynamic_viscosity=s.dynamic_viscosity,
@@ -524,3 +524,28 @@ def test_public_api_runs_reference_case_files(name):
                 gp = host(mf.primitives)
                 assert np.array_equal(host(mf.temperature)[m], port.temperature(gp, s)[m])
     assert tcv.simulation_step == n
+
+
+@pytest.mark.parametrize("recon,riemann", VARIANTS)
+@pytest.mark.parametrize("cells,bc", [((96, 1, 1), "ZEROGRADIENT"), ((36, 28, 1), "PERIODIC"), ((20, 16, 40), "SYMMETRY")])
+def test_weno5js_rhs_and_steps(cells, bc, recon, riemann):
+    """godunov.reconstruction_stencil = WENO5-JS (weno/weno5_js.py): per-axis rhs and 3 steps, all kernels
+    (marching with carried weights, rows with TMA windows, small-grid contiguous)."""
+    from jaxfluids_b200.engine import BlockState
+    s = H.make_setup(cells, bc=bc, recon=recon, riemann=riemann, stencil="WENO5-JS")
+    prims, cons = port.initialize(H.smooth_ic(s, seed=2, amp=0.15), s)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    scales = H.rhs_scales(prims, s)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s), scale=scales) <= H.TOL_RHS, f"axis {a}"
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    for _ in range(3):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    m = H.defined_mask(s)
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+    assert abs(st.dt.item() - dt) <= 1e-12 * dt

@@ -39,7 +39,7 @@ def test_reference_json_parses(name, tmp_path):
         assert tuple(float(x) for x in di.one_cell_sizes) == tuple(float(x) for x in s.inv_dx)
         assert di.smallest_cell_size == float(s.dx_min)
         g = m.numerical_setup.conservatives.convective_fluxes.godunov
-        assert (g.reconstruction_variable, g.riemann_solver, g.reconstruction_stencil) == (s.recon, s.riemann, "WENO5-Z")
+        assert (g.reconstruction_variable, g.riemann_solver, g.reconstruction_stencil) == (s.recon, s.riemann, s.stencil)
         assert m.numerical_setup.conservatives.time_integration.integrator == s.integrator
         assert m.case_setup.boundary_condition_setup == s.bc
 
@@ -70,7 +70,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
 @pytest.mark.parametrize("path,value", [
     (GOD + ("riemann_solver",), "HLL"),
     (GOD + ("signal_speed",), "DAVIS"),
-    (GOD + ("reconstruction_stencil",), "WENO5-JS"),
+    (GOD + ("reconstruction_stencil",), "TENO5"),
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
     (("conservatives", "time_integration", "integrator"), "RK2_LS4"),

@@ -19,6 +19,9 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("tgv", dict(cells=(8, 10, 12), bc="PERIODIC", dissipation=dict(mu=0.01, bulk=0.002, kappa=0.05)), 1),
     ("riemann2d", dict(cells=(16, 20, None), dissipation=dict(mu=1e-3, kappa=1e-3)), 2),
     ("sod", dict(cells=(64, None, None), dissipation=dict(mu=2e-3, prandtl=0.7)), 2),
+    # WENO5-JS
+    ("sod", dict(cells=(80, None, None), stencil="WENO5-JS"), 2),
+    ("tgv", dict(cells=(10, 10, 10), stencil="WENO5-JS", recon="PRIMITIVE", bc="PERIODIC"), 1),
 ])
 def test_port_is_bit_identical_to_reference(name, kw, nsteps):
     from oracle.refharness import pin_check
