@@ -40,7 +40,8 @@ enum { JXF_SIGNAL_EINFELDT = 0 };
 /* ref: time_integration/__init__.py:6-11 */
 enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2 };
 /* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */
-enum { JXF_BC_INACTIVE = 0, JXF_BC_PERIODIC = 1, JXF_BC_SYMMETRY = 2, JXF_BC_ZEROGRADIENT = 3, JXF_BC_NEIGHBOR = 4 };
+enum { JXF_BC_INACTIVE = 0, JXF_BC_PERIODIC = 1, JXF_BC_SYMMETRY = 2, JXF_BC_ZEROGRADIENT = 3, JXF_BC_NEIGHBOR = 4,
+       JXF_BC_WALL = 5 /* ref: halos/outer/material.py:473-520, constant wall_velocity_callable */ };
 /* face order of the reference: domain/__init__.py:5-7 */
 enum { JXF_EAST = 0, JXF_WEST = 1, JXF_NORTH = 2, JXF_SOUTH = 3, JXF_TOP = 4, JXF_BOTTOM = 5 };
 
@@ -67,6 +68,11 @@ typedef struct jxf_config {
   double  bulk_viscosity;           /* transport/bulk_viscosity                                   */
   double  thermal_conductivity;     /* constant lambda: CUSTOM value, or cp*mu/Pr for PRANDTL     */
   double  gas_constant;             /* equation_of_state/specific_gas_constant (T = p/(rho R))    */
+  /* ref: conservatives/positivity (solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE branch):
+   * reconstructed states with density < 1e-12 or pressure < 1e-10 fall back to the first-order state */
+  int32_t interpolation_limiter;    /* 0/1: positivity/is_interpolation_limiter                   */
+  int32_t limit_velocity;           /* 0/1: positivity/limit_velocity (all primitives, not just rho, p) */
+  double  wall_velocity[6][3];      /* (u, v, w) of the wall at each JXF_BC_WALL face             */
 } jxf_config;
 
 typedef struct jxf_solver* jxf_handle;

@@ -63,6 +63,8 @@ struct SweepArgs {
   int fuse_halo;           // EPI: also write the outer-BC halo images of boundary-adjacent cells
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
+  int limiter;             // interpolation limiter: 0 off, 1 density + pressure, 2 all primitives
+  double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
 };
 
 // ---------------------------------------------------------------------------
@@ -142,11 +144,18 @@ struct HaloOut {
   int nh;
 };
 
+// wall = nullptr: copy, negating velocity component flip_var (1..3; -1 = none).  wall != nullptr: no-slip wall
+// moving with (u, v, w) = wall[0..2]: every velocity component becomes 2 u_wall - u (halos/outer/material.py:510-512)
 __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, double p0, double p1, double p2, double p3,
-                                           double p4, int flip_var) {
+                                           double p4, int flip_var, const double* wall = nullptr) {
   double q[5] = {p0, p1, p2, p3, p4};
+  if (wall) {
 #pragma unroll
-  for (int v = 1; v < 4; ++v) q[v] = (v == flip_var) ? q[v] * -1.0 : q[v];
+    for (int v = 1; v < 4; ++v) q[v] = 2 * wall[v - 1] - q[v];
+  } else {
+#pragma unroll
+    for (int v = 1; v < 4; ++v) q[v] = (v == flip_var) ? q[v] * -1.0 : q[v];
+  }
   double c[5];
   cons_from_prims(q, h.gamma, c);
 #pragma unroll
@@ -156,14 +165,17 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
   }
 }
 
-// one role axis of the images of a cell
+// one role axis of the images of a cell; wall_hi / wall_lo: wall velocities of the two faces of this axis
 __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
-                                                 int ax, int n, int i, long long stride) {
+                                                 int ax, int n, int i, long long stride, const double* wall_hi,
+                                                 const double* wall_lo) {
   if (n <= 1) return;
   const int nh = h.nh;
   // low side (west / south / bottom)
   if (blo == JXF_BC_SYMMETRY) {
     if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
+  } else if (blo == JXF_BC_WALL) {
+    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_lo);
   } else if (blo == JXF_BC_PERIODIC) {
     if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
   } else if (blo == JXF_BC_ZEROGRADIENT) {
@@ -173,6 +185,8 @@ __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int 
   // high side (east / north / top)
   if (bhi == JXF_BC_SYMMETRY) {
     if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
+  } else if (bhi == JXF_BC_WALL) {
+    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_hi);
   } else if (bhi == JXF_BC_PERIODIC) {
     if (i < nh) halo_image(h, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
   } else if (bhi == JXF_BC_ZEROGRADIENT) {
@@ -225,9 +239,9 @@ __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const SweepArg
                                               double p2, double p3, double p4, int iA, int i1, int i2) {
   const HaloOut h{a.prims_out, a.cons_out, g.vst, a.gamma, a.nh};
   const double p[5] = {p0, p1, p2, p3, p4};
-  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA);
-  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1);
-  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2);
+  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1]);
+  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1]);
+  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const __gri
       CellIn<EPI> in;
       if (f > f0) load_cell_in<EPI>(g, a, hidx, ridx, in);
       double F[5];
-      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy);
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter);
       if (f > f0) {
         double r[5];
 #pragma unroll
@@ -378,7 +392,7 @@ sweep_march(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepAr
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[v][k] = ring[(j + k) & (kRingSlots - 1)][v][t];
       double F[5];
-      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy);
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter);
       if (j > 0) {
         double r[5];
 #pragma unroll
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const __grid
 #pragma unroll
           for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.sA];
         if (fin) load_cell_in<EPI>(g, a, hidx, ridx, in);
-        face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter);
       }
       double Fl[5];
 #pragma unroll
@@ -547,13 +561,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // out-of-line flux from a strided global window (rare paths only)
 template <int A, int RECON, int RIEMANN>
 __device__ __noinline__ void face_flux_from_global(const double* base, long long vst, long long sA, double gamma,
-                                                   double (&F)[5]) {
+                                                   double (&F)[5], int lim) {
   double w[5][6];
 #pragma unroll
   for (int v = 0; v < 5; ++v)
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[v][k] = base[v * vst + k * sA];
-  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, lim);
 }
 
 struct RowsArgs {
@@ -605,7 +619,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
       const long long row = row0 + lane;
       const int k1 = (int)(row / g.n2);
       const int k2 = (int)(row - (long long)k1 * g.n2);
-      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0);
+      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0, a.limiter);
     }
     // ---- main sequence: (row r, iteration it), windows staged one step ahead ---------------------
     // All index state is carried incrementally in 32-bit registers (no divisions in the loop):
@@ -677,7 +691,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
         for (int v = 0; v < 5; ++v)
 #pragma unroll
           for (int k = 0; k < 6; ++k) w[v][k] = wl[v * kWinSlots + k];
-        face_flux<A, RECON, RIEMANN>(w, a.gamma, F);
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter);
       }
       double Fl[5];
 #pragma unroll
@@ -720,12 +734,13 @@ struct HaloArgs {
   double* cons;
   double gamma;
   int bc[6];
+  double wall[6][3];
 };
 
 __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const HaloArgs a) {
   const int face = blockIdx.y;
   const int kind = a.bc[face];
-  if (kind != JXF_BC_PERIODIC && kind != JXF_BC_SYMMETRY && kind != JXF_BC_ZEROGRADIENT) return;
+  if (kind != JXF_BC_PERIODIC && kind != JXF_BC_SYMMETRY && kind != JXF_BC_ZEROGRADIENT && kind != JXF_BC_WALL) return;
   const int ax = face >> 1;
   const bool hi = (face & 1) == 0;   // east, north, top
   // transverse axes: t2 is the faster (larger index) one
@@ -743,7 +758,7 @@ __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const Halo
     const int dst = hi ? (ext - nh + l) : l;
     int src;
     if (kind == JXF_BC_PERIODIC) src = hi ? (nh + l) : (ext - 2 * nh + l);
-    else if (kind == JXF_BC_SYMMETRY) src = hi ? (ext - nh - 1 - l) : (2 * nh - 1 - l);
+    else if (kind == JXF_BC_SYMMETRY || kind == JXF_BC_WALL) src = hi ? (ext - nh - 1 - l) : (2 * nh - 1 - l);
     else src = hi ? (ext - nh - 1) : nh;
     const long long tr = (long long)(i1 + g.off[t1]) * g.st[t1] + (long long)(i2 + g.off[t2]) * g.st[t2];
     const long long is = tr + (long long)src * g.st[ax];
@@ -752,6 +767,10 @@ __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const Halo
 #pragma unroll
     for (int v = 0; v < 5; ++v) p[v] = a.prims[is + v * g.vst];
     if (kind == JXF_BC_SYMMETRY) p[1 + ax] = p[1 + ax] * -1.0;
+    if (kind == JXF_BC_WALL) {
+#pragma unroll
+      for (int v = 1; v < 4; ++v) p[v] = 2 * a.wall[face][v - 1] - p[v];
+    }
     cons_from_prims(p, a.gamma, c);
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -1085,7 +1104,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     const int ax = f >> 1;
     const int b = cfg->bc[f];
     const bool act = cfg->n[ax] > 1;
-    if (b < JXF_BC_INACTIVE || b > JXF_BC_NEIGHBOR) { delete s; return fail(JXF_ERR_UNSUPPORTED, "jxf_create: boundary type id %d at face %d not implemented on the B200 path", b, f); }
+    if (b < JXF_BC_INACTIVE || b > JXF_BC_WALL) { delete s; return fail(JXF_ERR_UNSUPPORTED, "jxf_create: boundary type id %d at face %d not implemented on the B200 path", b, f); }
     if (act && b == JXF_BC_INACTIVE) { delete s; return fail(JXF_ERR_BAD_ARG, "jxf_create: face %d of an active axis is INACTIVE", f); }
   }
   g.st[2] = 1;
@@ -1414,6 +1433,7 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   a.gamma = s->cfg.gamma;
   a.inv_dx = s->cfg.inv_dx[axis];
   a.active_mask = s->active_mask;
+  a.limiter = s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0;
   return a;
 }
 
@@ -1577,6 +1597,7 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
   long long maxcells = 0;
   for (int f = 0; f < 6; ++f) {
     a.bc[f] = h->cfg.bc[f];
+    for (int k = 0; k < 3; ++k) a.wall[f][k] = h->cfg.wall_velocity[f][k];
     const int ax = f >> 1;
     if (h->g.n[ax] <= 1) a.bc[f] = JXF_BC_INACTIVE;
     const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
@@ -1645,7 +1666,10 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       a.reduce = reduce ? 1 : 0;
       a.fuse_halo = fill_halo ? 1 : 0;      // outer-BC halo images written by the epilogue itself
       a.nh = h->cfg.nh;
-      for (int f = 0; f < 6; ++f) a.bc[f] = (h->g.n[f >> 1] > 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
+      for (int f = 0; f < 6; ++f) {
+        a.bc[f] = (h->g.n[f >> 1] > 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
+        for (int q = 0; q < 3; ++q) a.wall[f][q] = h->cfg.wall_velocity[f][q];
+      }
       rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
     }
     if (rc) return rc;

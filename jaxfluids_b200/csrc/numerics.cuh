@@ -727,11 +727,32 @@ __device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const d
 
 #endif  // JXF_REFERENCE_ORDER
 
+// Interpolation limiter (solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE; eps from
+// config/precision.py:54): a reconstructed state whose density is < 1e-12, or whose pressure then is < 1e-10,
+// falls back to the first-order state (the adjacent cell: window index 2 for the left, 3 for the right state) --
+// density and pressure only (lim = 1) or all primitives (lim = 2, positivity/limit_velocity).  lim = 0: off.
+__device__ __forceinline__ void limit_interpolation(double (&p)[5], const double (&w)[5][6], int k, int lim) {
+  if (lim == 0) return;
+  const bool m1 = p[0] < 1e-12;
+  const double p4 = m1 ? w[4][k] : p[4];
+  if (m1 || p4 < 1e-10) {
+    p[0] = w[0][k];
+    p[4] = w[4][k];
+    if (lim == 2) {
+      p[1] = w[1][k];
+      p[2] = w[2][k];
+      p[3] = w[3][k];
+    }
+  }
+}
+
 // window -> numerical flux at the face (high_order_godunov.py:117-231)
 template <int A, int RECON, int RIEMANN>
-__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5]) {
+__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int lim = 0) {
   double pl[5], pr[5];
   reconstruct<A, RECON>(w, gamma, pl, pr);
+  limit_interpolation(pl, w, 2, lim);
+  limit_interpolation(pr, w, 3, lim);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
 }
 
@@ -752,16 +773,19 @@ __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], doubl
   reconstruct<A, RECON>(w, gamma, pl, pr);
 }
 template <int A, int RECON, int RIEMANN>
-__device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&) {
-  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+__device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&,
+                                                int lim = 0) {
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, lim);
 }
 #else
 // marching variant: shares the cell-centred weights of the as-is fields between consecutive faces
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
-                                                ReconCarry<RECON>& cy) {
+                                                ReconCarry<RECON>& cy, int lim = 0) {
   double pl[5], pr[5];
   reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
+  limit_interpolation(pl, w, 2, lim);
+  limit_interpolation(pr, w, 3, lim);
 #if JXF_RIEMANN_MAIN
   bool zero;
   riemann_flux_main<A, RIEMANN>(pl, pr, gamma, F, zero);

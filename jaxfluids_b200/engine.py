@@ -44,6 +44,10 @@ class BlockConfig:
     thermal_conductivity: float = 0.0
     prandtl_number: float = 1.0
     gas_constant: float = 1.0
+    # conservatives/positivity and WALL boundaries
+    is_interpolation_limiter: bool = False
+    limit_velocity: bool = False
+    wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> constant (u, v, w)
 
     @property
     def is_dissipative(self) -> bool:
@@ -90,6 +94,12 @@ class BlockConfig:
         c.bulk_viscosity = float(self.bulk_viscosity)
         c.thermal_conductivity = self.thermal_conductivity_value() if self.is_heat_flux else 0.0
         c.gas_constant = float(self.gas_constant)
+        c.interpolation_limiter = int(bool(self.is_interpolation_limiter))
+        c.limit_velocity = int(bool(self.limit_velocity))
+        for k, f in enumerate(FACES):
+            uvw = self.wall_velocity.get(f, (0.0, 0.0, 0.0))
+            for q in range(3):
+                c.wall_velocity[k][q] = float(uvw[q])
         return c
 
     @property

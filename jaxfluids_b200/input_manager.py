@@ -95,11 +95,18 @@ class DissipativeFluxesSetup(NamedTuple):
     is_laplacian: bool = False
 
 
+class PositivitySetup(NamedTuple):
+    """read_positivity.py: the interpolation limiter is what this path implements."""
+    is_interpolation_limiter: bool = False
+    limit_velocity: bool = False
+
+
 class ConservativesSetup(NamedTuple):
     halo_cells: int
     time_integration: TimeIntegrationSetup
     convective_fluxes: ConvectiveFluxesSetup
     dissipative_fluxes: DissipativeFluxesSetup = DissipativeFluxesSetup()
+    positivity: PositivitySetup = PositivitySetup()
 
 
 class ActivePhysicsSetup(NamedTuple):
@@ -173,6 +180,7 @@ class CaseSetup(NamedTuple):
     boundary_condition_setup: Dict[str, str]
     initial_condition_setup: Dict[str, Any]
     material_setup: MaterialSetup
+    wall_velocity_setup: Dict[str, Tuple[float, float, float]] = {}      # WALL faces: constant (u, v, w)
 
 
 def _np_namespace():
@@ -271,8 +279,13 @@ class InputManager:
                            f"but only {nh} are specified.", "numerical")
         pos_d = cons_d.get("positivity", {}) or {}
         for k, v in pos_d.items():
-            if k.startswith("is_") and v:
-                raise NotImplementedError(f"conservatives/positivity/{k} is not implemented on the B200 path")
+            if k.startswith("is_") and v and k != "is_interpolation_limiter":
+                raise NotImplementedError(f"conservatives/positivity/{k} is not implemented on the B200 path "
+                                          "(implemented: is_interpolation_limiter)")
+        positivity = PositivitySetup(
+            bool(get_setup_value(pos_d, "is_interpolation_limiter", "conservatives/positivity/is_interpolation_limiter",
+                                 bool, True, False)),
+            bool(get_setup_value(pos_d, "limit_velocity", "conservatives/positivity/limit_velocity", bool, True, False)))
 
         ap_d = get_setup_value(d, "active_physics", "active_physics", dict, False)
         ap = {}
@@ -331,7 +344,7 @@ class InputManager:
         return NumericalSetup(
             ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
                                ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen)),
-                               dissipative),
+                               dissipative, positivity),
             active_physics, precision, OutputSetup(logging_setup))
 
     # -- case setup ----------------------------------------------------------
@@ -384,6 +397,7 @@ class InputManager:
 
         bc_d = get_setup_value(d, "boundary_conditions", "boundary_conditions", dict, False, setup=S)
         bcs = {}
+        walls = {}
         for f in FACES:
             f_d = get_setup_value(bc_d, f, f"boundary_conditions/{f}", (dict, list), False, setup=S)
             if isinstance(f_d, list):
@@ -395,6 +409,19 @@ class InputManager:
             _assert((t == "INACTIVE") == (not active),
                     f"boundary_conditions/{f}/type must be INACTIVE exactly for inactive axes.", S)
             bcs[f] = t
+            if t == "WALL":
+                # read_boundary_conditions: wall_velocity_callable {u, v, w}, floats or lambdas of (coords, t)
+                wv_d = get_setup_value(f_d, "wall_velocity_callable", f"boundary_conditions/{f}/wall_velocity_callable",
+                                       dict, False, setup=S)
+                uvw = []
+                for k in ("u", "v", "w"):
+                    v = get_setup_value(wv_d, k, f"boundary_conditions/{f}/wall_velocity_callable/{k}", (float, str),
+                                        False, setup=S)
+                    if isinstance(v, str):
+                        raise NotImplementedError(f"boundary_conditions/{f}/wall_velocity_callable/{k} given as a lambda "
+                                                  "string is not implemented on the B200 path (constant wall velocity only)")
+                    uvw.append(float(v))
+                walls[f] = tuple(uvw)
         for ax, (hi, lo) in enumerate((("east", "west"), ("north", "south"), ("top", "bottom"))):
             _assert((bcs[hi] == "PERIODIC") == (bcs[lo] == "PERIODIC"),
                     f"PERIODIC boundary conditions must be set at both {hi} and {lo}.", S)
@@ -421,7 +448,7 @@ class InputManager:
             if d.get(k):
                 raise NotImplementedError(f"{k} is not implemented on the B200 path")
         transport = self._read_transport(mp_d)
-        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport))
+        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport), walls)
 
     def _read_transport(self, mp_d: Dict) -> TransportSetup:
         """read_material_manager.py:200-330: required exactly when the flux that needs them is active."""

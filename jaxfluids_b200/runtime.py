@@ -71,6 +71,9 @@ class BlockRuntime:
             thermal_conductivity=case.material_setup.transport.thermal_conductivity,
             prandtl_number=case.material_setup.transport.prandtl_number,
             gas_constant=case.material_setup.specific_gas_constant,
+            is_interpolation_limiter=num.conservatives.positivity.is_interpolation_limiter,
+            limit_velocity=num.conservatives.positivity.limit_velocity,
+            wall_velocity=dict(case.wall_velocity_setup),
         )
 
         self.solver = BlockSolver(self.cfg)

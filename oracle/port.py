@@ -64,6 +64,10 @@ class Setup:
     thermal_conductivity: float = 0.0
     prandtl_number: float = 1.0
     gas_constant: float = 1.0                    # equation_of_state/specific_gas_constant
+    # conservatives/positivity (limiter_interpolation.py) and WALL boundaries (halos/outer/material.py:473-520)
+    is_interpolation_limiter: bool = False
+    limit_velocity: bool = False
+    wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> (u, v, w), constants
     active: Tuple[int, ...] = field(init=False)
 
     def __post_init__(self):
@@ -166,7 +170,7 @@ def halo_fill(prims, cons, s: Setup):
         hi = face in ("east", "north", "top")
         if kind == "PERIODIC":
             src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
-        elif kind == "SYMMETRY":
+        elif kind in ("SYMMETRY", "WALL"):
             src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
         elif kind == "ZEROGRADIENT":
             src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)
@@ -182,6 +186,9 @@ def halo_fill(prims, cons, s: Setup):
             sign = np.ones((5, 1, 1, 1))
             sign[1 + ax] *= -1.0
             hp = hp * sign
+        if kind == "WALL":                       # halos/outer/material.py:473-520: u_halo = 2 u_wall - u_mirror
+            uw = s.wall_velocity.get(face, (0.0, 0.0, 0.0))
+            hp = np.stack([hp[0]] + [2 * (np.ones_like(hp[0]) * uw[k]) - hp[1 + k] for k in range(3)] + [hp[4]], axis=0)
         hc = cons_from_prims(hp, s.gamma)
         prims[tuple(sl_dst)] = prims[tuple(sl_dst)] * (1 - 1.0) + hp * 1.0
         cons[tuple(sl_dst)] = cons[tuple(sl_dst)] * (1 - 1.0) + hc * 1.0
@@ -366,7 +373,29 @@ def reconstruct(prims, axis, s: Setup):
         pl, pr = res
     else:
         raise NotImplementedError(s.recon)
+    if s.is_interpolation_limiter:               # high_order_godunov.py:163-174
+        pl = _limit_interpolation(pl, w[2], s)   # WENO1 left state = cell i
+        pr = _limit_interpolation(pr, w[3], s)   # WENO1 right state = cell i+1
     return pl, pr, cons_from_prims(pl, s.gamma), cons_from_prims(pr, s.gamma)
+
+
+INTERPOLATION_LIMITER_EPS = (1e-12, 1e-10)       # config/precision.py:54 (density, pressure), fp64
+
+
+def _limit_interpolation(p, p_first_order, s: Setup):
+    """solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE branch: where the reconstructed density
+    is below eps (then where the pressure is), fall back to the first-order state -- density and pressure only,
+    or all primitives with positivity/limit_velocity."""
+    ids = [0, 1, 2, 3, 4] if s.limit_velocity else [0, 4]
+
+    def apply(mask, p):
+        p = p.copy()
+        for v in ids:
+            p[v] = p[v] * (1 - mask) + p_first_order[v] * mask
+        return p
+    p = apply(np.where(p[0] < INTERPOLATION_LIMITER_EPS[0], 1, 0), p)
+    p = apply(np.where(p[4] + 0.0 < INTERPOLATION_LIMITER_EPS[1], 1, 0), p)
+    return p
 
 
 # --------------------------------------------------------------------------

@@ -47,7 +47,33 @@ FIXTURES = {
     "riemann2d_24x28_js_prim_hllc_rk3": ("riemann2d", dict(cells=(24, 28, None), stencil="WENO5-JS", recon="PRIMITIVE"), 5, (5,)),
     "tgv_10x12x10_per_js_prim_visc_rk3": ("tgv", dict(cells=(10, 12, 10), bc="PERIODIC", stencil="WENO5-JS", recon="PRIMITIVE",
                                                       dissipation=dict(mu=1e-2)), 2, (2,)),
+    # the shipped lid-driven cavity example, shrunk: WALL on four faces (moving lid), WENO5-JS PRIMITIVE, viscous,
+    # interpolation limiter on, halo_cells 4
+    "cavity_24x20_wall_js_visc_rk3": ("cavity", dict(cells=(24, 20, None)), 5, (5,)),
 }
+
+
+def make_limiter_fixture():
+    """rhs of a state on which the interpolation limiter (limiter_interpolation.py:77-209) fires thousands of
+    times (density ~3e-13 / pressure ~4e-11 regions), for both settings of positivity/limit_velocity."""
+    d = {}
+    for lv in (False, True):
+        case, num = rr.customize(*rr.load_case("riemann2d"), cells=(20, 24, None), recon="CHAR-PRIMITIVE")
+        num["conservatives"]["positivity"] = {"is_interpolation_limiter": True, "limit_velocity": lv}
+        x, y = np.meshgrid(np.linspace(0, 1, 20), np.linspace(0, 1, 24), indexing="ij")
+        rho = np.where(x < 0.5, 1.0 + 0.1 * np.sin(7 * y), 3e-13 * (1 + 0.5 * np.sin(9 * y + 3 * x)))
+        p = np.where(y < 0.5, 1.0 + 0.2 * np.cos(5 * x), 4e-11 * (1 + 0.5 * np.cos(11 * x + y)))
+        user = np.stack([rho, 0.3 * np.sin(3 * x), 0.2 * np.cos(4 * y), p])[..., None]
+        run = rr.ReferenceRun(case, num, user_prime_init=user)
+        tag = "lv1" if lv else "lv0"
+        d[f"case_json_{tag}"], d[f"num_json_{tag}"] = np.array(json.dumps(case)), np.array(json.dumps(num))
+        d["user"] = user
+        d[f"prims_halo_{tag}"] = run.primitives
+        d[f"rhs_{tag}"] = run.compute_rhs()
+    os.makedirs(os.path.join(OUT, "special"), exist_ok=True)
+    path = os.path.join(OUT, "special", "limiter_riemann2d_20x24.npz")
+    np.savez_compressed(path, **d)
+    print(f"special/limiter_riemann2d_20x24: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
 def make(name, case_name, kw, nsteps, snaps):
@@ -98,3 +124,6 @@ if __name__ == "__main__":
             continue
         with np.errstate(all="ignore"):
             make(name, case_name, kw, nsteps, snaps)
+    if not only or "limiter" in only:
+        with np.errstate(all="ignore"):
+            make_limiter_fixture()

@@ -46,6 +46,7 @@ CASES = {
     "sod": ("examples_1D/02_sod_shock_tube", "sod.json"),
     "riemann2d": ("examples_2D/07_riemann_problem", "riemann2D.json"),
     "tgv": ("examples_3D/01_tgv", "tgv.json"),
+    "cavity": ("examples_2D/03_lid_driven_cavity", "lid_driven_cavity.json"),   # WALL x4, WENO5-JS, viscous, limiter, nh 4
 }
 
 

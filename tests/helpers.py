@@ -63,6 +63,11 @@ def setup_from_json(case, num) -> port.Setup:
         riemann=g.get("riemann_solver", "HLLC"),
         integrator=c["time_integration"]["integrator"],
         cfl=c["time_integration"].get("CFL", 0.5),
+        is_interpolation_limiter=bool((c.get("positivity", {}) or {}).get("is_interpolation_limiter", False)),
+        limit_velocity=bool((c.get("positivity", {}) or {}).get("limit_velocity", False)),
+        wall_velocity={f: tuple(float(case["boundary_conditions"][f].get("wall_velocity_callable", {}).get(k, 0.0))
+                                for k in "uvw")
+                       for f in port.FACES if case["boundary_conditions"][f]["type"] == "WALL"},
         **dissipation_from_json(case, num),
     )
 

@@ -23,7 +23,8 @@ def make_solver(s: port.Setup, bc=None):
                       is_viscous_heat_production=s.is_viscous_heat_production, dynamic_viscosity=s.dynamic_viscosity,
                       bulk_viscosity=s.bulk_viscosity, thermal_conductivity_model=s.thermal_conductivity_model,
                       thermal_conductivity=s.thermal_conductivity, prandtl_number=s.prandtl_number,
-                      gas_constant=s.gas_constant)
+                      gas_constant=s.gas_constant, is_interpolation_limiter=s.is_interpolation_limiter,
+                      limit_velocity=s.limit_velocity, wall_velocity=dict(s.wall_velocity))
     return BlockSolver(cfg)
 
 
@@ -492,7 +493,8 @@ def test_dissipative_steps_against_oracle(cells, bc, integrator, extra):
     assert np.allclose(T[m], port.temperature(prims, s)[m], rtol=1e-11, atol=0)
 
 
-@pytest.mark.parametrize("name", ["tgv12_sym_visc_prandtl_rk3", "riemann2d_20x24_visc_rk3", "tgv16_sym_char_hllc_rk3"])
+@pytest.mark.parametrize("name", ["tgv12_sym_visc_prandtl_rk3", "riemann2d_20x24_visc_rk3", "tgv16_sym_char_hllc_rk3",
+                                  "cavity_24x20_wall_js_visc_rk3", "sod100_js_char_hllc_rk3"])
 def test_public_api_runs_reference_case_files(name):
     """The reference's JSON setups through InputManager -> InitializationManager -> SimulationManager
     (do_integration_step), compared with what the reference itself produced for them: dt sequence, state after
@@ -549,3 +551,58 @@ def test_weno5js_rhs_and_steps(cells, bc, recon, riemann):
     m = H.defined_mask(s)
     assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
     assert abs(st.dt.item() - dt) <= 1e-12 * dt
+
+
+@pytest.mark.parametrize("tag", ["lv0", "lv1"])
+def test_interpolation_limiter_fixture_rhs(tag):
+    """positivity/is_interpolation_limiter (limiter_interpolation.py:77-209) on the reference's fixture where it
+    fires thousands of times (near-vacuum regions): rhs against the reference, all kernels."""
+    import json, os
+    g = np.load(os.path.join(H.GOLDEN, "special", "limiter_riemann2d_20x24.npz"))
+    case, num = json.loads(str(g[f"case_json_{tag}"])), json.loads(str(g[f"num_json_{tag}"]))
+    s = H.setup_from_json(case, num)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(g[f"prims_halo_{tag}"], nan=1.0, posinf=1.0, neginf=1.0))
+    ref = g[f"rhs_{tag}"]
+    with np.errstate(all="ignore"):
+        scales = H.rhs_scales(g[f"prims_halo_{tag}"], s)
+    got = host(sol.compute_rhs(p))
+    assert np.isfinite(got).all()
+    assert H.rel_linf(got, ref, scale=scales) <= H.TOL_RHS
+    # and the limiter matters: without it the result differs
+    import copy
+    s0 = copy.copy(s)
+    s0.is_interpolation_limiter = False
+    got0 = host(make_solver(s0).compute_rhs(p))
+    assert not np.allclose(got0, got, rtol=1e-6, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("cells,walls", [
+    ((28, 24, 1), {"east": (0, 0, 0), "west": (0, 0, 0), "north": (0.5, 0, 0), "south": (0, 0, 0)}),
+    ((12, 16, 20), {"north": (0.1, 0.0, -0.2), "south": (0, 0, 0)})])
+def test_wall_boundaries_viscous_steps(cells, walls):
+    """WALL faces with constant wall velocity (halos/outer/material.py:473-520: u_halo = 2 u_wall - u_mirror), the
+    other active faces PERIODIC; viscous; halo fill bit-exact, 4 steps against the oracle (lid-driven-cavity and
+    Couette-like setups)."""
+    from jaxfluids_b200.engine import BlockState
+    bc = {f: ("WALL" if f in walls else "PERIODIC") for f in port.FACES}
+    s = H.make_setup(cells, bc=bc, recon="PRIMITIVE", stencil="WENO5-JS", nh=4)
+    s.wall_velocity = {f: tuple(float(x) for x in v) for f, v in walls.items()}
+    s.is_viscous_flux, s.is_viscous_heat_production, s.dynamic_viscosity = True, False, 5e-3
+    s.is_interpolation_limiter = True
+    prims, cons = port.initialize(H.smooth_ic(s, seed=13, amp=0.05), s)
+    sol = make_solver(s)
+    # stand-alone halo fill from interior-only data: copies / 2 u_w - u: bit exact
+    s_raw = H.make_setup(cells, bc={f: ("ZEROGRADIENT" if s.bc[f] != "INACTIVE" else "INACTIVE") for f in port.FACES}, nh=4)
+    p_raw, c_raw = port.initialize(H.smooth_ic(s, seed=13, amp=0.05), s_raw)
+    p, c = dev(p_raw), dev(c_raw)
+    sol.halo_fill(p, c)
+    m = H.defined_mask(s)
+    assert np.array_equal(host(p)[:, m], prims[:, m])
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    for _ in range(4):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+        assert abs(st.dt.item() - dt) <= 1e-12 * dt
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12

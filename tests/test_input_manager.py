@@ -124,7 +124,15 @@ def test_dissipative_setup_is_read_like_the_reference():
 def test_case_errors():
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     with pytest.raises(NotImplementedError):
+        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "DIRICHLET"), num)
+    # WALL: constant wall_velocity_callable is read; a missing one is the reference's consistency error; a lambda
+    # string is a valid option this path does not implement
+    with pytest.raises(AssertionError, match="wall_velocity_callable"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "WALL"), num)
+    wall = _mod(case, ("boundary_conditions", "east"), {"type": "WALL", "wall_velocity_callable": {"u": 0.0, "v": 0.5, "w": 0.0}})
+    assert InputManager(wall, num).case_setup.wall_velocity_setup == {"east": (0.0, 0.5, 0.0)}
+    with pytest.raises(NotImplementedError, match="B200 path"):
+        InputManager(_mod(wall, ("boundary_conditions", "east", "wall_velocity_callable", "v"), "lambda y, z, t: 0.5"), num)
     with pytest.raises(AssertionError, match="case setup"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "PERIODIC"), num)   # west is SYMMETRY
     with pytest.raises(AssertionError, match="argument labels"):

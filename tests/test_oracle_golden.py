@@ -60,3 +60,23 @@ def test_sod_physics_against_exact_solution():
     mid_R = (x > x_contact + 0.03) & (x < 0.5 + 1.7521557320301779 * 0.2 - 0.03)
     assert np.max(np.abs(rho_num[mid_L] - rho_star_L)) < 5e-3
     assert np.max(np.abs(rho_num[mid_R] - rho_star_R)) < 5e-3
+
+
+@pytest.mark.parametrize("tag", ["lv0", "lv1"])
+def test_interpolation_limiter_fixture(tag):
+    """positivity/is_interpolation_limiter on a state where it fires thousands of times (fixture generated from
+    the reference, oracle/refharness/make_goldens.py:make_limiter_fixture)."""
+    import json, copy, os
+    g = np.load(os.path.join(H.GOLDEN, "special", "limiter_riemann2d_20x24.npz"))
+    case, num = json.loads(str(g[f"case_json_{tag}"])), json.loads(str(g[f"num_json_{tag}"]))
+    s = H.setup_from_json(case, num)
+    assert s.is_interpolation_limiter and s.limit_velocity == (tag == "lv1")
+    with np.errstate(all="ignore"):
+        prims, cons = port.initialize(g["user"], s, from_user_buffer=True)
+        assert np.array_equal(prims, g[f"prims_halo_{tag}"])
+        s0 = copy.copy(s)
+        s0.is_interpolation_limiter = False
+        changed = sum(int((a != b).sum()) for ax in s.active
+                      for a, b in zip(port.reconstruct(prims, ax, s0)[:2], port.reconstruct(prims, ax, s)[:2]))
+        assert changed > 1000                                  # the limiter really acts on this state
+        assert np.array_equal(port.compute_rhs(prims, s), g[f"rhs_{tag}"], equal_nan=True)
