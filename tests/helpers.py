@@ -129,7 +129,15 @@ def rhs_scales(prims, s):
     tot = 0.0
     for a in s.active:
         tot = tot + np.abs(port.rhs_axis(prims, a, s))
-    return field_scales(tot)
+    sc = np.asarray(field_scales(tot), dtype=float)
+    # Floor: 1 % of the largest face-flux term (1/dx) max|F_v|.  Each axis contribution is itself a difference of
+    # two face fluxes; for a fluid (nearly) at rest with uniform pressure (lid-driven cavity at t = 0) those are
+    # equal O(p/dx) numbers, so the rounding floor of the rhs is eps * p/dx however small the rhs itself is.
+    fl = np.zeros(5)
+    for a in s.active:
+        f = np.abs(np.nan_to_num(port.face_flux(prims, a, s)))
+        fl = np.maximum(fl, f.reshape(5, -1).max(axis=1) * float(s.inv_dx[a]))
+    return np.maximum(sc, 1e-2 * fl)
 
 
 def rel_linf(a, b, scale=None):
