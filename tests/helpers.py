@@ -130,13 +130,18 @@ def rhs_scales(prims, s):
     for a in s.active:
         tot = tot + np.abs(port.rhs_axis(prims, a, s))
     sc = np.asarray(field_scales(tot), dtype=float)
-    # Floor: 1 % of the largest face-flux term (1/dx) max|F_v|.  Each axis contribution is itself a difference of
-    # two face fluxes; for a fluid (nearly) at rest with uniform pressure (lid-driven cavity at t = 0) those are
-    # equal O(p/dx) numbers, so the rounding floor of the rhs is eps * p/dx however small the rhs itself is.
+    # Floor: 1 % of the largest term the numerical flux is built from, per field: (1/dx) max(|F_v|, (|u_n| + c) |U_v|)
+    # (HLLC = physical flux + S_K (U*_K - U_K)).  Each axis contribution is itself a difference of two face fluxes;
+    # for a fluid (nearly) at rest with uniform pressure (lid-driven cavity at t = 0) those are equal O(p/dx),
+    # O(rho c/dx) numbers, so the rounding floor of the rhs is eps * rho c/dx however small the rhs itself is.
     fl = np.zeros(5)
+    pi = np.nan_to_num(prims[(slice(None),) + s.interior], nan=1.0)
+    ci = np.abs(port.cons_from_prims(pi, s.gamma))
+    c = port.speed_of_sound(pi[4], pi[0], s.gamma)
     for a in s.active:
         f = np.abs(np.nan_to_num(port.face_flux(prims, a, s)))
-        fl = np.maximum(fl, f.reshape(5, -1).max(axis=1) * float(s.inv_dx[a]))
+        wave = (np.abs(pi[1 + a]) + c)[None] * ci
+        fl = np.maximum(fl, np.maximum(f.reshape(5, -1).max(axis=1), wave.reshape(5, -1).max(axis=1)) * float(s.inv_dx[a]))
     return np.maximum(sc, 1e-2 * fl)
 
 
