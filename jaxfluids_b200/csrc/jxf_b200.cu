@@ -913,10 +913,21 @@ __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const Face
   const int nh = g.nh, ext = g.ext[ax];
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
        q += (long long)gridDim.x * blockDim.x) {
-    const int i2 = (int)(q % n2);
-    const long long q1 = q / n2;
-    const int i1 = (int)(q1 % n1);
-    const int l = (int)(q1 / n1);
+    // slab order: layers slowest, except for faces of the CONTIGUOUS axis, whose nh layers are adjacent in memory:
+    // there the layer index runs fastest so that a row's nh cells are one 8 nh-byte access (both ends of an
+    // exchange run this kernel, so the order is private to it)
+    int i1, i2, l;
+    if (g.st[ax] == 1) {
+      l = (int)(q % nh);
+      const long long q1 = q / nh;
+      i2 = (int)(q1 % n2);
+      i1 = (int)(q1 / n2);
+    } else {
+      i2 = (int)(q % n2);
+      const long long q1 = q / n2;
+      i1 = (int)(q1 % n1);
+      l = (int)(q1 / n1);
+    }
     const long long tr = (long long)(i1 + a.lo1) * g.st[t1] + (long long)(i2 + a.lo2) * g.st[t2];
     if (!a.unpack) {
       const int src = hi ? (ext - 2 * nh + l) : (nh + l);   // interior layers adjacent to the face
