@@ -44,11 +44,14 @@ def riemann2d(n):
     return c
 
 
-def run(name, case, steps, warmup):
+def run(name, case, steps, warmup, graph=False):
     im = InputManager(case, NUM)
     buf = InitializationManager(im).initialization()
     sim = SimulationManager(im)
     rt = sim.runtime
+    if graph:
+        rt.use_cuda_graph(True)
+        name += " [CUDA graph]"
     tcv = buf.time_control_variables
     rt.set_time_control(tcv.physical_simulation_time, tcv.physical_timestep_size)
     for _ in range(warmup):
@@ -69,5 +72,7 @@ def run(name, case, steps, warmup):
 
 if __name__ == "__main__":
     run("Sod 1000 cells", sod(1000), 200, 20)
+    run("Sod 1000 cells", sod(1000), 200, 20, graph=True)
     run("2-D Riemann 1024^2", riemann2d(1024), 50, 5)
+    run("2-D Riemann 1024^2", riemann2d(1024), 50, 5, graph=True)
     run("TGV 256^3", bench.tgv_case(256, (1, 1, 1), 10 ** 9)[0], 10, 3)

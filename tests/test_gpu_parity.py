@@ -606,3 +606,39 @@ def test_wall_boundaries_viscous_steps(cells, walls):
         st.step()
         assert abs(st.dt.item() - dt) <= 1e-12 * dt
     assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+
+
+@pytest.mark.parametrize("cells,bc,integrator", [((200, 1, 1), "ZEROGRADIENT", "RK3"), ((48, 40, 1), "PERIODIC", "RK2"),
+                                                 ((20, 16, 36), "SYMMETRY", "RK3")])
+def test_cuda_graph_step_is_bit_identical(cells, bc, integrator):
+    """BlockRuntime.use_cuda_graph: the replayed step (one graph per ping-pong parity) gives the same bits as the
+    launched step, including dt / t carried on the device."""
+    from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+    s = H.make_setup(cells, bc=bc, integrator=integrator)
+    case = {"general": {"case_name": "g", "end_step": 10, "save_path": "./r"},
+            "domain": {ax: {"cells": cells[i], "range": [0.0, 1.0]} for i, ax in enumerate("xyz")},
+            "boundary_conditions": {f: {"type": s.bc[f]} for f in port.FACES},
+            "initial_condition": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 1.0},
+            "material_properties": {"equation_of_state": {"model": "IdealGas", "specific_heat_ratio": 1.4,
+                                                          "specific_gas_constant": 1.0}}}
+    num = {"conservatives": {"halo_cells": 5, "time_integration": {"integrator": integrator, "CFL": 0.5},
+           "convective_fluxes": {"convective_solver": "GODUNOV", "godunov": {"riemann_solver": "HLLC", "signal_speed": "EINFELDT",
+           "reconstruction_stencil": "WENO5-Z", "reconstruction_variable": "CHAR-PRIMITIVE"}}},
+           "active_physics": {"is_convective_flux": True}, "output": {"logging": {"level": "NONE"}}}
+    user = H.smooth_ic(s, seed=17, amp=0.1)[[0] + [1 + i for i in s.active] + [4]]
+    outs = []
+    for graph in (False, True):
+        im = InputManager(case, num)
+        buf = InitializationManager(im).initialization(user_prime_init=user)
+        rt = SimulationManager(im).runtime
+        tcv = buf.time_control_variables
+        rt.set_time_control(tcv.physical_simulation_time, tcv.physical_timestep_size)
+        if graph:
+            rt.use_cuda_graph(True)
+        for _ in range(5):
+            rt.step()
+        outs.append((host(rt.primitives).copy(), host(rt.conservatives).copy(), rt.read_step_scalars()))
+    m = H.face_halo_mask(s)
+    assert np.array_equal(outs[0][0][:, m], outs[1][0][:, m])
+    assert np.array_equal(outs[0][1][:, m], outs[1][1][:, m])
+    assert outs[0][2] == outs[1][2]
