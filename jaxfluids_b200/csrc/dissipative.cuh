@@ -229,8 +229,11 @@ __global__ void __launch_bounds__(128, 3) visc_march(const __grid_constant__ Swe
 // shared layout per row of the CTA: 10 cell quantities + 4 flux components, each blockDim.x doubles.
 // CTA = blockDim.y consecutive rows x one segment of the contiguous axis (neighbouring rows share the lines
 // their transverse derivatives read)
+#ifndef JXF_VISC_ROWS_MINB
+#define JXF_VISC_ROWS_MINB 1
+#endif
 template <int A>
-__global__ void __launch_bounds__(256) visc_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
+__global__ void __launch_bounds__(256, JXF_VISC_ROWS_MINB) visc_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ ViscArgs a) {
   extern __shared__ double vs_all[];
   const int B = blockDim.x;
   const int tid = threadIdx.x;

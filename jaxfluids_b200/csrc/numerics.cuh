@@ -621,7 +621,20 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     const double S_star = ((pr[4] - pl[4]) + fma(uL, dL, -(uR * dR))) * rcp_fast(dL - dR);
     // F = 1/2 (1 + sign S*) F*_L + 1/2 (1 - sign S*) F*_R : only the selected side is evaluated
     // (S* > 0 -> F*_L, S* < 0 -> F*_R, S* = 0 -> the mean, sign(0) = 0 in the reference)
-#if JXF_HLLC_BRANCH
+#if JXF_HLLC_BRANCH == 2
+    // two inlined copies of the star flux instead of four (instruction-cache footprint of the hot loops):
+    // S* >= 0 evaluates the left one, S* <= 0 the right one, S* = 0 both and their mean
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = 0.0;
+    if (S_star >= 0.0) hllc_star_flux<A>(pl, ig1, irL, S_L, fmin(S_L, 0.0), dL, S_star, F);
+    if (S_star <= 0.0) {
+      double fR[5];
+      hllc_star_flux<A>(pr, ig1, irR, S_R, fmax(S_R, 0.0), dR, S_star, fR);
+      const bool both = (S_star == 0.0);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) F[v] = both ? 0.5 * (F[v] + fR[v]) : fR[v];
+    }
+#elif JXF_HLLC_BRANCH
     if (S_star > 0.0) {
       hllc_star_flux<A>(pl, ig1, irL, S_L, fmin(S_L, 0.0), dL, S_star, F);
     } else if (S_star < 0.0) {

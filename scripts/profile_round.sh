@@ -13,7 +13,9 @@ ncu --set full --clock-control none --import-source on -k regex:sweep_ -s 27 -c 
 ncu -i /tmp/prof_$tag.ncu-rep --page raw --csv > $out/prof_${tag}_raw.csv 2>/dev/null
 python profiles/ncu_summary.py $out/prof_${tag}_raw.csv > $out/ncu_full_${tag}_summary.txt
 for k in sweep_rows sweep_march; do
-  ncu -i /tmp/prof_$tag.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | python scripts/ncu_source_mix.py 4194304 > $out/mix_${tag}_$k.txt
+  ncu -i /tmp/prof_$tag.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null > /tmp/src_$k.csv
+  python scripts/ncu_source_mix.py 4194304 < /tmp/src_$k.csv > $out/mix_${tag}_$k.txt
+  python scripts/ncu_source_stalls.py 60 < /tmp/src_$k.csv > $out/stalls_${tag}_$k.txt
 done
 # (3) dissipative sweeps (x, z) at 512^3
 ncu --set full --clock-control none -k regex:visc_ -s 6 -c 1 -o /tmp/prof_${tag}_viscx -f \
