@@ -41,7 +41,8 @@ enum { JXF_SIGNAL_EINFELDT = 0 };
 enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2 };
 /* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */
 enum { JXF_BC_INACTIVE = 0, JXF_BC_PERIODIC = 1, JXF_BC_SYMMETRY = 2, JXF_BC_ZEROGRADIENT = 3, JXF_BC_NEIGHBOR = 4,
-       JXF_BC_WALL = 5 /* ref: halos/outer/material.py:473-520, constant wall_velocity_callable */ };
+       JXF_BC_WALL = 5      /* ref: halos/outer/material.py:473-520, constant wall_velocity_callable */,
+       JXF_BC_DIRICHLET = 6 /* ref: halos/outer/material.py:732-798, constant primitives_callable   */ };
 /* face order of the reference: domain/__init__.py:5-7 */
 enum { JXF_EAST = 0, JXF_WEST = 1, JXF_NORTH = 2, JXF_SOUTH = 3, JXF_TOP = 4, JXF_BOTTOM = 5 };
 
@@ -73,6 +74,12 @@ typedef struct jxf_config {
   int32_t interpolation_limiter;    /* 0/1: positivity/is_interpolation_limiter                   */
   int32_t limit_velocity;           /* 0/1: positivity/limit_velocity (all primitives, not just rho, p) */
   double  wall_velocity[6][3];      /* (u, v, w) of the wall at each JXF_BC_WALL face             */
+  double  dirichlet[6][5];          /* (rho, u, v, w, p) prescribed at each JXF_BC_DIRICHLET face */
+  /* ref: active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186, space_solver.py:378-384):
+   * rhs(rho u_i) += g_i rho, rhs(E) += g . (rho u), from the stage's conservatives */
+  int32_t volume_force;             /* 0/1                                                        */
+  int32_t reserved1;
+  double  gravity[3];
 } jxf_config;
 
 typedef struct jxf_solver* jxf_handle;

@@ -25,7 +25,7 @@ STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1}
 RIEMANN = {"HLLC": 0, "RUSANOV": 1}
 SIGNAL = {"EINFELDT": 0}
 INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
-BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4, "WALL": 5}
+BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4, "WALL": 5, "DIRICHLET": 6}
 FACES = ("east", "west", "north", "south", "top", "bottom")
 
 
@@ -54,6 +54,10 @@ class JxfConfig(C.Structure):
         ("interpolation_limiter", C.c_int32),
         ("limit_velocity", C.c_int32),
         ("wall_velocity", (C.c_double * 3) * 6),
+        ("dirichlet", (C.c_double * 5) * 6),
+        ("volume_force", C.c_int32),
+        ("reserved1", C.c_int32),
+        ("gravity", C.c_double * 3),
     ]
 
 

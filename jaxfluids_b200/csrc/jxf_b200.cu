@@ -64,7 +64,10 @@ struct SweepArgs {
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
   int limiter;             // interpolation limiter: 0 off, 1 density + pressure, 2 all primitives
+  int volume_force;        // EPI: add the gravity source (g_i rho, g . rho u) of the stage's conservatives
+  double gravity[3];
   double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
+  double dirichlet[6][5];  // prescribed primitives per JXF_BC_DIRICHLET face
 };
 
 // ---------------------------------------------------------------------------
@@ -168,7 +171,7 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
 // one role axis of the images of a cell; wall_hi / wall_lo: wall velocities of the two faces of this axis
 __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
                                                  int ax, int n, int i, long long stride, const double* wall_hi,
-                                                 const double* wall_lo) {
+                                                 const double* wall_lo, const double* dir_hi, const double* dir_lo) {
   if (n <= 1) return;
   const int nh = h.nh;
   // low side (west / south / bottom)
@@ -181,6 +184,10 @@ __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int 
   } else if (blo == JXF_BC_ZEROGRADIENT) {
     if (i == 0)
       for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
+  } else if (blo == JXF_BC_DIRICHLET) {       // constants: written by the thread of the boundary-adjacent cell
+    if (i == 0)
+      for (int l = 1; l <= nh; ++l)
+        halo_image(h, hidx - (long long)l * stride, dir_lo[0], dir_lo[1], dir_lo[2], dir_lo[3], dir_lo[4], -1);
   }
   // high side (east / north / top)
   if (bhi == JXF_BC_SYMMETRY) {
@@ -192,6 +199,10 @@ __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int 
   } else if (bhi == JXF_BC_ZEROGRADIENT) {
     if (i == n - 1)
       for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
+  } else if (bhi == JXF_BC_DIRICHLET) {
+    if (i == n - 1)
+      for (int l = 1; l <= nh; ++l)
+        halo_image(h, hidx + (long long)l * stride, dir_hi[0], dir_hi[1], dir_hi[2], dir_hi[3], dir_hi[4], -1);
   }
 }
 
@@ -213,7 +224,11 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
     double U[5];
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
-      const double tot = a.has_prev ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
+      double tot = a.has_prev ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
+      if (a.volume_force) {     // space_solver.py:378-384 with the einsums of source_term_solver.py:180-182
+        if (v >= 1 && v <= 3) tot += a.gravity[v - 1] * in.U[0];
+        if (v == 4) tot += (a.gravity[0] * in.U[1] + a.gravity[1] * in.U[2]) + a.gravity[2] * in.U[3];
+      }
       double u = in.U[v];
       if (a.blend) u = a.ca * u + a.cb * in.Un[v];
       U[v] = u + step * tot;
@@ -239,9 +254,12 @@ __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const SweepArg
                                               double p2, double p3, double p4, int iA, int i1, int i2) {
   const HaloOut h{a.prims_out, a.cons_out, g.vst, a.gamma, a.nh};
   const double p[5] = {p0, p1, p2, p3, p4};
-  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1]);
-  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1]);
-  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1]);
+  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1],
+                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1]);
+  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
+                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1]);
+  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1],
+                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -735,12 +753,14 @@ struct HaloArgs {
   double gamma;
   int bc[6];
   double wall[6][3];
+  double dirichlet[6][5];
 };
 
 __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const HaloArgs a) {
   const int face = blockIdx.y;
   const int kind = a.bc[face];
-  if (kind != JXF_BC_PERIODIC && kind != JXF_BC_SYMMETRY && kind != JXF_BC_ZEROGRADIENT && kind != JXF_BC_WALL) return;
+  if (kind != JXF_BC_PERIODIC && kind != JXF_BC_SYMMETRY && kind != JXF_BC_ZEROGRADIENT && kind != JXF_BC_WALL &&
+      kind != JXF_BC_DIRICHLET) return;
   const int ax = face >> 1;
   const bool hi = (face & 1) == 0;   // east, north, top
   // transverse axes: t2 is the faster (larger index) one
@@ -770,6 +790,10 @@ __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const Halo
     if (kind == JXF_BC_WALL) {
 #pragma unroll
       for (int v = 1; v < 4; ++v) p[v] = 2 * a.wall[face][v - 1] - p[v];
+    }
+    if (kind == JXF_BC_DIRICHLET) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) p[v] = a.dirichlet[face][v];
     }
     cons_from_prims(p, a.gamma, c);
 #pragma unroll
@@ -849,6 +873,27 @@ __global__ void __launch_bounds__(256) integrate_stage_kernel(const Geom g, cons
       if (interior) u = u + step * rhs[ridx + v * g.rvst];
       out[q + v * g.vst] = u;
     }
+  }
+}
+
+// volume forces for the stand-alone rhs entry points (jxf_compute_rhs): the stage path adds them in its epilogue
+// from the stage's conservatives; here rho u is re-formed from the primitives (differs by rounding only)
+__global__ void __launch_bounds__(256) gravity_rhs_kernel(const Geom g, const double* __restrict__ prims, double* rhs,
+                                                          double g0, double g1, double g2) {
+  const long long total = (long long)g.n[0] * g.n[1] * g.n[2];
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(q % g.n[2]);
+    const long long q1 = q / g.n[2];
+    const int j = (int)(q1 % g.n[1]);
+    const int i = (int)(q1 / g.n[1]);
+    const long long idx = (long long)(i + g.off[0]) * g.st[0] + (long long)(j + g.off[1]) * g.st[1] +
+                          (long long)(k + g.off[2]) * g.st[2];
+    const double rho = prims[idx];
+    const double m0 = rho * prims[idx + g.vst], m1 = rho * prims[idx + 2 * g.vst], m2 = rho * prims[idx + 3 * g.vst];
+    rhs[q + 1 * g.rvst] += g0 * rho;
+    rhs[q + 2 * g.rvst] += g1 * rho;
+    rhs[q + 3 * g.rvst] += g2 * rho;
+    rhs[q + 4 * g.rvst] += (g0 * m0 + g1 * m1) + g2 * m2;
   }
 }
 
@@ -1115,7 +1160,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     const int ax = f >> 1;
     const int b = cfg->bc[f];
     const bool act = cfg->n[ax] > 1;
-    if (b < JXF_BC_INACTIVE || b > JXF_BC_WALL) { delete s; return fail(JXF_ERR_UNSUPPORTED, "jxf_create: boundary type id %d at face %d not implemented on the B200 path", b, f); }
+    if (b < JXF_BC_INACTIVE || b > JXF_BC_DIRICHLET) { delete s; return fail(JXF_ERR_UNSUPPORTED, "jxf_create: boundary type id %d at face %d not implemented on the B200 path", b, f); }
     if (act && b == JXF_BC_INACTIVE) { delete s; return fail(JXF_ERR_BAD_ARG, "jxf_create: face %d of an active axis is INACTIVE", f); }
   }
   g.st[2] = 1;
@@ -1596,6 +1641,13 @@ extern "C" int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, v
     int rc = jxf_sweep(h, h->active[k], prims, rhs, k > 0, stream);
     if (rc) return rc;
   }
+  if (h->cfg.volume_force) {
+    const int bx = (int)std::min<long long>((h->g.rvst + 255) / 256, 148 * 8);
+    ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+    gravity_rhs_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->g, prims, rhs, h->cfg.gravity[0], h->cfg.gravity[1],
+                                                            h->cfg.gravity[2]);
+    return check_launch("gravity_rhs");
+  }
   return JXF_OK;
 }
 
@@ -1609,6 +1661,7 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
   for (int f = 0; f < 6; ++f) {
     a.bc[f] = h->cfg.bc[f];
     for (int k = 0; k < 3; ++k) a.wall[f][k] = h->cfg.wall_velocity[f][k];
+    for (int k = 0; k < 5; ++k) a.dirichlet[f][k] = h->cfg.dirichlet[f][k];
     const int ax = f >> 1;
     if (h->g.n[ax] <= 1) a.bc[f] = JXF_BC_INACTIVE;
     const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
@@ -1680,7 +1733,10 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       for (int f = 0; f < 6; ++f) {
         a.bc[f] = (h->g.n[f >> 1] > 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
         for (int q = 0; q < 3; ++q) a.wall[f][q] = h->cfg.wall_velocity[f][q];
+        for (int q = 0; q < 5; ++q) a.dirichlet[f][q] = h->cfg.dirichlet[f][q];
       }
+      a.volume_force = h->cfg.volume_force;
+      for (int q = 0; q < 3; ++q) a.gravity[q] = h->cfg.gravity[q];
       rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
     }
     if (rc) return rc;

@@ -48,6 +48,9 @@ class BlockConfig:
     is_interpolation_limiter: bool = False
     limit_velocity: bool = False
     wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> constant (u, v, w)
+    dirichlet: Dict[str, Tuple[float, ...]] = field(default_factory=dict)               # face -> constant (rho,u,v,w,p)
+    is_volume_force: bool = False
+    gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
 
     @property
     def is_dissipative(self) -> bool:
@@ -100,6 +103,12 @@ class BlockConfig:
             uvw = self.wall_velocity.get(f, (0.0, 0.0, 0.0))
             for q in range(3):
                 c.wall_velocity[k][q] = float(uvw[q])
+            vals = self.dirichlet.get(f, (1.0, 0.0, 0.0, 0.0, 1.0))
+            for q in range(5):
+                c.dirichlet[k][q] = float(vals[q])
+        c.volume_force = int(bool(self.is_volume_force))
+        for q in range(3):
+            c.gravity[q] = float(self.gravity[q])
         return c
 
     @property

@@ -181,6 +181,8 @@ class CaseSetup(NamedTuple):
     initial_condition_setup: Dict[str, Any]
     material_setup: MaterialSetup
     wall_velocity_setup: Dict[str, Tuple[float, float, float]] = {}      # WALL faces: constant (u, v, w)
+    dirichlet_setup: Dict[str, Tuple[float, float, float, float, float]] = {}   # DIRICHLET faces: constant prims
+    gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)               # forcings/gravity
 
 
 def _np_namespace():
@@ -295,10 +297,10 @@ class InputManager:
         active_physics = ActivePhysicsSetup(**ap)
         _assert(active_physics.is_convective_flux, "active_physics/is_convective_flux must be true "
                 "for the convective hot path.", "numerical")
-        for f in ("is_volume_force", "is_surface_tension", "is_geometric_source"):
+        for f in ("is_surface_tension", "is_geometric_source"):
             if getattr(active_physics, f):
                 raise NotImplementedError(f"active_physics/{f} is not implemented on the B200 path "
-                                          "(single-phase convective + viscous + heat flux only)")
+                                          "(single-phase convective + viscous + heat flux + gravity only)")
         # read_conservatives.py:374-440
         is_diss = active_physics.is_viscous_flux or active_physics.is_heat_flux
         df_d = get_setup_value(cons_d, "dissipative_fluxes", "conservatives/dissipative_fluxes", dict, not is_diss, {})
@@ -398,6 +400,7 @@ class InputManager:
         bc_d = get_setup_value(d, "boundary_conditions", "boundary_conditions", dict, False, setup=S)
         bcs = {}
         walls = {}
+        dirichlets = {}
         for f in FACES:
             f_d = get_setup_value(bc_d, f, f"boundary_conditions/{f}", (dict, list), False, setup=S)
             if isinstance(f_d, list):
@@ -422,6 +425,19 @@ class InputManager:
                                                   "string is not implemented on the B200 path (constant wall velocity only)")
                     uvw.append(float(v))
                 walls[f] = tuple(uvw)
+            if t == "DIRICHLET":
+                # read_boundary_conditions: primitives_callable {rho, u, v, w, p}, floats or lambdas of (coords, t)
+                pc_d = get_setup_value(f_d, "primitives_callable", f"boundary_conditions/{f}/primitives_callable",
+                                       dict, False, setup=S)
+                vals = []
+                for k in ("rho", "u", "v", "w", "p"):
+                    v = get_setup_value(pc_d, k, f"boundary_conditions/{f}/primitives_callable/{k}", (float, str),
+                                        False, setup=S)
+                    if isinstance(v, str):
+                        raise NotImplementedError(f"boundary_conditions/{f}/primitives_callable/{k} given as a lambda "
+                                                  "string is not implemented on the B200 path (constant values only)")
+                    vals.append(float(v))
+                dirichlets[f] = tuple(vals)
         for ax, (hi, lo) in enumerate((("east", "west"), ("north", "south"), ("top", "bottom"))):
             _assert((bcs[hi] == "PERIODIC") == (bcs[lo] == "PERIODIC"),
                     f"PERIODIC boundary conditions must be set at both {hi} and {lo}.", S)
@@ -444,11 +460,20 @@ class InputManager:
         Rgas = get_setup_value(eos_d, "specific_gas_constant",
                                "material_properties/equation_of_state/specific_gas_constant", float, True, 1.0, None,
                                (">", 0.0), S)
-        for k in ("forcings",):
-            if d.get(k):
-                raise NotImplementedError(f"{k} is not implemented on the B200 path")
+        # forcings: gravity (read_forcings; used with active_physics/is_volume_force) is what this path implements
+        gravity = (0.0, 0.0, 0.0)
+        fo_d = d.get("forcings", {}) or {}
+        for k, v in fo_d.items():
+            if k != "gravity" and v:
+                raise NotImplementedError(f"forcings/{k} is not implemented on the B200 path (implemented: gravity)")
+        if self.numerical_setup.active_physics.is_volume_force:
+            gv = get_setup_value(fo_d, "gravity", "forcings/gravity", list, False, setup=S)
+            _assert(len(gv) == 3 and all(isinstance(x, (int, float)) for x in gv),
+                    "forcings/gravity must be a list of three numbers.", S)
+            gravity = tuple(float(x) for x in gv)
         transport = self._read_transport(mp_d)
-        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport), walls)
+        return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport), walls,
+                         dirichlets, gravity)
 
     def _read_transport(self, mp_d: Dict) -> TransportSetup:
         """read_material_manager.py:200-330: required exactly when the flux that needs them is active."""

@@ -43,7 +43,7 @@ TUPLE_FROZEN_STATE = ("ARITHMETIC",)
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
 DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
-TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL")
+TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL", "DIRICHLET")
 
 REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3}   # weno5_base.py:18
 

@@ -74,6 +74,9 @@ class BlockRuntime:
             is_interpolation_limiter=num.conservatives.positivity.is_interpolation_limiter,
             limit_velocity=num.conservatives.positivity.limit_velocity,
             wall_velocity=dict(case.wall_velocity_setup),
+            dirichlet=dict(case.dirichlet_setup),
+            is_volume_force=num.active_physics.is_volume_force,
+            gravity=tuple(case.gravity),
         )
 
         self.solver = BlockSolver(self.cfg)

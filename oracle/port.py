@@ -68,6 +68,10 @@ class Setup:
     is_interpolation_limiter: bool = False
     limit_velocity: bool = False
     wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> (u, v, w), constants
+    dirichlet: Dict[str, Tuple[float, float, float, float, float]] = field(default_factory=dict)  # face -> constant prims
+    # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
+    is_volume_force: bool = False
+    gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     active: Tuple[int, ...] = field(init=False)
 
     def __post_init__(self):
@@ -172,7 +176,7 @@ def halo_fill(prims, cons, s: Setup):
             src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
         elif kind in ("SYMMETRY", "WALL"):
             src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
-        elif kind == "ZEROGRADIENT":
+        elif kind in ("ZEROGRADIENT", "DIRICHLET"):
             src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)
         else:
             raise NotImplementedError(kind)
@@ -182,6 +186,9 @@ def halo_fill(prims, cons, s: Setup):
         sl_src[1 + ax] = src
         sl_dst[1 + ax] = dst
         hp = prims[tuple(sl_src)]
+        if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: constant primitives_callable
+            vals = s.dirichlet[face]
+            hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(5)], axis=0)
         if kind == "SYMMETRY":
             sign = np.ones((5, 1, 1, 1))
             sign[1 + ax] *= -1.0
@@ -621,11 +628,27 @@ def rhs_axis(prims, axis, s: Setup):
     return out
 
 
-def compute_rhs(prims, s: Setup):
-    """space_solver.py:151-453 (single phase, convective only): 0.0 + rhs_x + rhs_y + rhs_z."""
+def gravity_forces(cons, s: Setup):
+    """source_term_solver.py:163-186: (4, ...) = (g_i rho, g . (rho u)) on the interior, with the reference's einsums."""
+    ci = cons[(slice(None),) + s.interior]
+    g = np.array(s.gravity, dtype=np.float64)
+    density = np.expand_dims(ci[0], axis=0)
+    momentum = ci[1:4]
+    mom = np.einsum("ij..., jk...->ik...", g.reshape(3, 1), density)
+    ene = np.einsum("ij..., jk...->ik...", g.reshape(1, 3), momentum)
+    return np.concatenate([mom, ene], axis=0)
+
+
+def compute_rhs(prims, s: Setup, cons=None):
+    """space_solver.py:151-453 (single phase): 0.0 + rhs_x + rhs_y + rhs_z (+ volume forces, :378-384, which
+    read the conservatives)."""
     rhs = 0.0
     for axis in s.active:
         rhs = rhs + rhs_axis(prims, axis, s)
+    if s.is_volume_force:
+        cons = cons_from_prims(prims, s.gamma) if cons is None else cons
+        rhs = rhs.copy()
+        rhs[1:5] = rhs[1:5] + gravity_forces(cons, s)
     return rhs
 
 
@@ -684,7 +707,7 @@ def stage(prims, cons, cons_n, dt, k, s: Setup):
     """One RK stage: simulation_manager.py:770-1047 (single-phase branch).
     Returns (prims, cons, rhs)."""
     rk = RK[s.integrator]
-    rhs = compute_rhs(prims, s)                                         # :796
+    rhs = compute_rhs(prims, s, cons)                                   # :796
     if k > 0:                                                           # RK3.py:49-50
         a, b = rk["blend"][k - 1]
         cons = a * cons + b * cons_n

@@ -50,6 +50,8 @@ FIXTURES = {
     # the shipped lid-driven cavity example, shrunk: WALL on four faces (moving lid), WENO5-JS PRIMITIVE, viscous,
     # interpolation limiter on, halo_cells 4
     "cavity_24x20_wall_js_visc_rk3": ("cavity", dict(cells=(24, 20, None)), 5, (5,)),
+    # the shipped Rayleigh-Taylor example, shrunk: DIRICHLET north/south, SYMMETRY east/west, gravity, limiter
+    "rti_16x48_dirichlet_gravity_rk3": ("rti", dict(cells=(16, 48, None)), 5, (5,)),
 }
 
 

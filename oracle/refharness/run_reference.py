@@ -47,6 +47,7 @@ CASES = {
     "riemann2d": ("examples_2D/07_riemann_problem", "riemann2D.json"),
     "tgv": ("examples_3D/01_tgv", "tgv.json"),
     "cavity": ("examples_2D/03_lid_driven_cavity", "lid_driven_cavity.json"),   # WALL x4, WENO5-JS, viscous, limiter, nh 4
+    "rti": ("examples_2D/04_rayleigh_taylor_instability", "rti.json"),           # DIRICHLET N/S, gravity, limiter
 }
 
 
@@ -68,7 +69,7 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
                 case["domain"][ax]["cells"] = int(n)
     if bc is not None:
         for face in ("east", "west", "north", "south", "top", "bottom"):
-            if case["boundary_conditions"][face]["type"] != "INACTIVE":
+            if case["boundary_conditions"][face]["type"] not in ("INACTIVE", "DIRICHLET", "WALL"):
                 case["boundary_conditions"][face] = {"type": bc}
     g = num["conservatives"]["convective_fluxes"]["godunov"]
     if recon is not None:

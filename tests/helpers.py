@@ -21,7 +21,8 @@ def golden_names(dissipative=None):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
     if dissipative is None:
         return names
-    return [n for n in names if ("visc" in n) == bool(dissipative)]
+    # "dissipative" = anything beyond the convective face flux in the rhs (viscous / heat flux, gravity)
+    return [n for n in names if ("visc" in n or "gravity" in n) == bool(dissipative)]
 
 
 def load_golden(name):
@@ -68,6 +69,10 @@ def setup_from_json(case, num) -> port.Setup:
         wall_velocity={f: tuple(float(case["boundary_conditions"][f].get("wall_velocity_callable", {}).get(k, 0.0))
                                 for k in "uvw")
                        for f in port.FACES if case["boundary_conditions"][f]["type"] == "WALL"},
+        dirichlet={f: tuple(float(case["boundary_conditions"][f]["primitives_callable"][k]) for k in ("rho", "u", "v", "w", "p"))
+                   for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
+        is_volume_force=bool(num.get("active_physics", {}).get("is_volume_force", False)),
+        gravity=tuple(float(x) for x in (case.get("forcings", {}) or {}).get("gravity", (0.0, 0.0, 0.0))),
         **dissipation_from_json(case, num),
     )
 

@@ -24,7 +24,8 @@ def make_solver(s: port.Setup, bc=None):
                       bulk_viscosity=s.bulk_viscosity, thermal_conductivity_model=s.thermal_conductivity_model,
                       thermal_conductivity=s.thermal_conductivity, prandtl_number=s.prandtl_number,
                       gas_constant=s.gas_constant, is_interpolation_limiter=s.is_interpolation_limiter,
-                      limit_velocity=s.limit_velocity, wall_velocity=dict(s.wall_velocity))
+                      limit_velocity=s.limit_velocity, wall_velocity=dict(s.wall_velocity),
+                      dirichlet=dict(s.dirichlet), is_volume_force=s.is_volume_force, gravity=tuple(s.gravity))
     return BlockSolver(cfg)
 
 
@@ -494,7 +495,7 @@ def test_dissipative_steps_against_oracle(cells, bc, integrator, extra):
 
 
 @pytest.mark.parametrize("name", ["tgv12_sym_visc_prandtl_rk3", "riemann2d_20x24_visc_rk3", "tgv16_sym_char_hllc_rk3",
-                                  "cavity_24x20_wall_js_visc_rk3", "sod100_js_char_hllc_rk3"])
+                                  "cavity_24x20_wall_js_visc_rk3", "sod100_js_char_hllc_rk3", "rti_16x48_dirichlet_gravity_rk3"])
 def test_public_api_runs_reference_case_files(name):
     """The reference's JSON setups through InputManager -> InitializationManager -> SimulationManager
     (do_integration_step), compared with what the reference itself produced for them: dt sequence, state after
@@ -642,3 +643,42 @@ def test_cuda_graph_step_is_bit_identical(cells, bc, integrator):
     assert np.array_equal(outs[0][0][:, m], outs[1][0][:, m])
     assert np.array_equal(outs[0][1][:, m], outs[1][1][:, m])
     assert outs[0][2] == outs[1][2]
+
+
+@pytest.mark.parametrize("cells,gravity,visc", [((16, 40, 1), (0.0, 1.0, 0.0), False), ((12, 14, 24), (0.3, -0.2, 1.0), True),
+                                                ((80, 1, 1), (-0.7, 0.0, 0.0), False)])
+def test_dirichlet_and_gravity_steps(cells, gravity, visc):
+    """DIRICHLET faces with constant primitives (halos/outer/material.py:732-798) on the last active axis, the other
+    faces SYMMETRY, plus the gravity source (source_term_solver.py:163-186): rhs incl. volume forces, halo fill
+    bit-exact, 4 steps against the oracle (Rayleigh-Taylor-like setups)."""
+    from jaxfluids_b200.engine import BlockState
+    act = [i for i in range(3) if cells[i] > 1]
+    last = act[-1]
+    bc = {f: ("DIRICHLET" if port.FACE_AXIS[f] == last else "SYMMETRY") for f in port.FACES}
+    s = H.make_setup(cells, bc=bc, recon="PRIMITIVE")
+    hi_f, lo_f = port.FACES[2 * last], port.FACES[2 * last + 1]
+    s.dirichlet = {hi_f: (1.0, 0.0, 0.0, 0.0, 2.5), lo_f: (2.0, 0.01, -0.02, 0.0, 1.0)}
+    s.is_volume_force, s.gravity = True, tuple(gravity)
+    s.is_interpolation_limiter = True
+    if visc:
+        s.is_viscous_flux, s.is_heat_flux, s.dynamic_viscosity = True, True, 5e-3
+        s.thermal_conductivity_model, s.prandtl_number = "PRANDTL", 0.72
+    prims, cons = port.initialize(H.smooth_ic(s, seed=23, amp=0.05), s)
+    sol = make_solver(s)
+    p, c = dev(np.nan_to_num(prims, nan=1.0)), dev(np.nan_to_num(cons, nan=1.0))
+    scales = H.rhs_scales(prims, s)
+    got = host(sol.compute_rhs(p))
+    assert H.rel_linf(got, port.compute_rhs(prims, s, cons), scale=scales) <= H.TOL_RHS
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    m = H.defined_mask(s)
+    for _ in range(4):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+        assert abs(st.dt.item() - dt) <= 1e-12 * dt
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+    # the DIRICHLET halos hold exactly the prescribed constants
+    gp = host(st.primitives)
+    sl = [slice(None)] + list(s.interior)
+    sl[1 + last] = slice(0, s.nh)
+    assert np.array_equal(gp[tuple(sl)], np.broadcast_to(np.array(s.dirichlet[lo_f]).reshape(5, 1, 1, 1), gp[tuple(sl)].shape))

@@ -74,7 +74,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
     (("conservatives", "time_integration", "integrator"), "RK2_LS4"),
-    (("active_physics", "is_volume_force"), True),
+    (("active_physics", "is_geometric_source"), True),
     (("precision", "is_double_precision_compute"), False),
 ])
 def test_valid_reference_options_outside_the_path_raise_not_implemented(path, value):
@@ -124,7 +124,18 @@ def test_dissipative_setup_is_read_like_the_reference():
 def test_case_errors():
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     with pytest.raises(NotImplementedError):
+        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "NEUMANN"), num)
+    # DIRICHLET: constant primitives_callable
+    with pytest.raises(AssertionError, match="primitives_callable"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "DIRICHLET"), num)
+    dirich = _mod(case, ("boundary_conditions", "east"),
+                  {"type": "DIRICHLET", "primitives_callable": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 2.5}})
+    assert InputManager(dirich, num).case_setup.dirichlet_setup == {"east": (1.0, 0.0, 0.0, 0.0, 2.5)}
+    # gravity needs forcings/gravity when is_volume_force is on
+    with pytest.raises(AssertionError, match="gravity"):
+        InputManager(case, _mod(num, ("active_physics", "is_volume_force"), True))
+    grav = _mod(case, ("forcings",), {"gravity": [0.0, 1.0, 0.0]})
+    assert InputManager(grav, _mod(num, ("active_physics", "is_volume_force"), True)).case_setup.gravity == (0.0, 1.0, 0.0)
     # WALL: constant wall_velocity_callable is read; a missing one is the reference's consistency error; a lambda
     # string is a valid option this path does not implement
     with pytest.raises(AssertionError, match="wall_velocity_callable"):
