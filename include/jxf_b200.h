@@ -78,7 +78,8 @@ typedef struct jxf_config {
   /* ref: active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186, space_solver.py:378-384):
    * rhs(rho u_i) += g_i rho, rhs(E) += g . (rho u), from the stage's conservatives */
   int32_t volume_force;             /* 0/1                                                        */
-  int32_t reserved1;
+  int32_t no_convective_flux;       /* 1: active_physics/is_convective_flux = false (dissipative fluxes only,
+                                       space_solver.py:517-545); the stage then runs unfused              */
   double  gravity[3];
 } jxf_config;
 

@@ -56,7 +56,7 @@ class JxfConfig(C.Structure):
         ("wall_velocity", (C.c_double * 3) * 6),
         ("dirichlet", (C.c_double * 5) * 6),
         ("volume_force", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("no_convective_flux", C.c_int32),
         ("gravity", C.c_double * 3),
     ]
 

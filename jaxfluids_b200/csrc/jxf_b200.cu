@@ -897,6 +897,58 @@ __global__ void __launch_bounds__(256) gravity_rhs_kernel(const Geom g, const do
   }
 }
 
+// unfused stage update (no convective sweep to carry the epilogue: is_convective_flux = false): interior cells
+// U <- a U + b U^n + (dt m) (rhs [+ gravity]), primitives recovered, reductions on the last stage; halos by jxf_halo_fill
+struct UpdateArgs {
+  const double* cons_in;
+  const double* cons_n;
+  const double* rhs;
+  double* cons_out;
+  double* prims_out;
+  const double* dt;
+  double* red;
+  double ca, cb, dt_mult, gamma;
+  double gravity[3];
+  int blend, reduce, active_mask, volume_force;
+};
+
+__global__ void __launch_bounds__(256) update_stage_kernel(const Geom g, const UpdateArgs a) {
+  const long long total = (long long)g.n[0] * g.n[1] * g.n[2];
+  const double step = (*a.dt) * a.dt_mult;
+  Red red;
+  red.init();
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(q % g.n[2]);
+    const long long q1 = q / g.n[2];
+    const int j = (int)(q1 % g.n[1]);
+    const int i = (int)(q1 / g.n[1]);
+    const long long idx = (long long)(i + g.off[0]) * g.st[0] + (long long)(j + g.off[1]) * g.st[1] +
+                          (long long)(k + g.off[2]) * g.st[2];
+    double U0[5], U[5], p[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) U0[v] = a.cons_in[idx + v * g.vst];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double tot = a.rhs[q + v * g.rvst];
+      if (a.volume_force) {
+        if (v >= 1 && v <= 3) tot += a.gravity[v - 1] * U0[0];
+        if (v == 4) tot += (a.gravity[0] * U0[1] + a.gravity[1] * U0[2]) + a.gravity[2] * U0[3];
+      }
+      double u = U0[v];
+      if (a.blend) u = a.ca * u + a.cb * a.cons_n[idx + v * g.vst];
+      U[v] = u + step * tot;
+    }
+    prims_from_cons(U, a.gamma, p);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      a.cons_out[idx + v * g.vst] = U[v];
+      a.prims_out[idx + v * g.vst] = p[v];
+    }
+    if (a.reduce) red.add_cell(p, a.gamma, a.active_mask);
+  }
+  if (a.reduce) red_commit(red, a.red);
+}
+
 __global__ void reduce_reset_kernel(double* red) {
   red[0] = 0.0;
   red[1] = __longlong_as_double(0x7ff0000000000000LL);
@@ -1128,6 +1180,8 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
   if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
+  if (cfg->no_convective_flux && !(cfg->viscous_flux || cfg->heat_flux))
+    return fail(JXF_ERR_BAD_ARG, "jxf_create: no flux is active");
   if (cfg->viscous_flux || cfg->heat_flux) {
     if (!(cfg->gas_constant > 0.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gas_constant=%g", cfg->gas_constant);
     if (cfg->dynamic_viscosity < 0.0 || cfg->thermal_conductivity < 0.0)
@@ -1609,6 +1663,8 @@ extern "C" int jxf_temperature(jxf_handle h, const double* prims, double* temper
 extern "C" int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rhs, int accumulate, void* stream) {
   if (!h || !prims || !rhs) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: null argument");
   if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: axis %d is not active", axis);
+  if (h->cfg.no_convective_flux)      // flux_xi = 0 + dissipative part only (space_solver.py:517-584)
+    return dissipative_sweep(h, axis, prims, rhs, accumulate, (cudaStream_t)stream);
   SweepArgs a = base_args(h, axis, prims, rhs);
   a.accumulate = accumulate ? 1 : 0;
   int rc = dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
@@ -1706,6 +1762,23 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       int rc = dissipative_sweep(h, h->active[k], prims_in, rhs_scratch, k > 0, (cudaStream_t)stream);
       if (rc) return rc;
     }
+  }
+  if (h->cfg.no_convective_flux) {
+    // no sweep to carry the fused epilogue: plain update kernel, then the halo kernels
+    UpdateArgs u;
+    u.cons_in = cons_in; u.cons_n = cons_n; u.rhs = rhs_scratch; u.cons_out = cons_out; u.prims_out = prims_out;
+    u.dt = dt_dev; u.red = red_dev;
+    u.ca = h->blend[stage][0]; u.cb = h->blend[stage][1]; u.dt_mult = h->dt_mult[stage]; u.gamma = h->cfg.gamma;
+    for (int q = 0; q < 3; ++q) u.gravity[q] = h->cfg.gravity[q];
+    u.blend = stage > 0; u.reduce = reduce ? 1 : 0; u.active_mask = h->active_mask; u.volume_force = h->cfg.volume_force;
+    const int bx = (int)std::min<long long>((h->g.rvst + 255) / 256, 148 * 8);
+    {
+      ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+      update_stage_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->g, u);
+    }
+    int rc = check_launch("update_stage");
+    if (rc) return rc;
+    return fill_halo ? jxf_halo_fill(h, prims_out, cons_out, stream) : JXF_OK;
   }
   for (int k = first_axis_index; k < h->n_active; ++k) {
     const int axis = h->order[k];

@@ -51,6 +51,7 @@ class BlockConfig:
     dirichlet: Dict[str, Tuple[float, ...]] = field(default_factory=dict)               # face -> constant (rho,u,v,w,p)
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    is_convective_flux: bool = True
 
     @property
     def is_dissipative(self) -> bool:
@@ -107,6 +108,7 @@ class BlockConfig:
             for q in range(5):
                 c.dirichlet[k][q] = float(vals[q])
         c.volume_force = int(bool(self.is_volume_force))
+        c.no_convective_flux = int(not self.is_convective_flux)
         for q in range(3):
             c.gravity[q] = float(self.gravity[q])
         return c

@@ -295,8 +295,9 @@ class InputManager:
             default = ActivePhysicsSetup._field_defaults[f]
             ap[f] = bool(get_setup_value(ap_d, f, f"active_physics/{f}", bool, True, default))
         active_physics = ActivePhysicsSetup(**ap)
-        _assert(active_physics.is_convective_flux, "active_physics/is_convective_flux must be true "
-                "for the convective hot path.", "numerical")
+        _assert(active_physics.is_convective_flux or active_physics.is_viscous_flux or active_physics.is_heat_flux,
+                "active_physics: at least one of is_convective_flux, is_viscous_flux, is_heat_flux must be true.",
+                "numerical")
         for f in ("is_surface_tension", "is_geometric_source"):
             if getattr(active_physics, f):
                 raise NotImplementedError(f"active_physics/{f} is not implemented on the B200 path "

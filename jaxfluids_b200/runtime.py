@@ -76,6 +76,7 @@ class BlockRuntime:
             wall_velocity=dict(case.wall_velocity_setup),
             dirichlet=dict(case.dirichlet_setup),
             is_volume_force=num.active_physics.is_volume_force,
+            is_convective_flux=num.active_physics.is_convective_flux,
             gravity=tuple(case.gravity),
         )
 

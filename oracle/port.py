@@ -72,6 +72,7 @@ class Setup:
     # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    is_convective_flux: bool = True              # active_physics/is_convective_flux (false: heat-equation examples)
     active: Tuple[int, ...] = field(init=False)
 
     def __post_init__(self):
@@ -609,8 +610,11 @@ def face_flux(prims, axis, s: Setup):
 
 def rhs_axis(prims, axis, s: Setup):
     """space_solver.py:456-674 (convective branch: :489, :517-543, :597-599)."""
-    fc = face_flux(prims, axis, s)
-    f = np.zeros_like(fc) + fc                                          # :517, :545
+    if s.is_convective_flux:
+        fc = face_flux(prims, axis, s)
+        f = np.zeros_like(fc) + fc                                      # :517, :545
+    else:
+        f = np.zeros((5,) + _flux_shape(axis, s))                       # :517 only
     if s.is_dissipative:
         T = temperature(prims, s)
         if s.is_viscous_flux:                                           # :567-573

@@ -52,6 +52,8 @@ FIXTURES = {
     "cavity_24x20_wall_js_visc_rk3": ("cavity", dict(cells=(24, 20, None)), 5, (5,)),
     # the shipped Rayleigh-Taylor example, shrunk: DIRICHLET north/south, SYMMETRY east/west, gravity, limiter
     "rti_16x48_dirichlet_gravity_rk3": ("rti", dict(cells=(16, 48, None)), 5, (5,)),
+    # the shipped 1-D heat equation example, shrunk: heat flux only (is_convective_flux false), DIRICHLET E/W, nh 4
+    "heat1d_40_dirichlet_noconv_rk3": ("heat1d", dict(cells=(40, None, None)), 6, (6,)),
 }
 
 

@@ -48,6 +48,7 @@ CASES = {
     "tgv": ("examples_3D/01_tgv", "tgv.json"),
     "cavity": ("examples_2D/03_lid_driven_cavity", "lid_driven_cavity.json"),   # WALL x4, WENO5-JS, viscous, limiter, nh 4
     "rti": ("examples_2D/04_rayleigh_taylor_instability", "rti.json"),           # DIRICHLET N/S, gravity, limiter
+    "heat1d": ("examples_1D/08_heat_equation", "heat_equation.json"),            # heat flux only (no convective flux)
 }
 
 

@@ -22,7 +22,7 @@ def golden_names(dissipative=None):
     if dissipative is None:
         return names
     # "dissipative" = anything beyond the convective face flux in the rhs (viscous / heat flux, gravity)
-    return [n for n in names if ("visc" in n or "gravity" in n) == bool(dissipative)]
+    return [n for n in names if ("visc" in n or "gravity" in n or "noconv" in n) == bool(dissipative)]
 
 
 def load_golden(name):
@@ -72,6 +72,7 @@ def setup_from_json(case, num) -> port.Setup:
         dirichlet={f: tuple(float(case["boundary_conditions"][f]["primitives_callable"][k]) for k in ("rho", "u", "v", "w", "p"))
                    for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
         is_volume_force=bool(num.get("active_physics", {}).get("is_volume_force", False)),
+        is_convective_flux=bool(num.get("active_physics", {}).get("is_convective_flux", True)),
         gravity=tuple(float(x) for x in (case.get("forcings", {}) or {}).get("gravity", (0.0, 0.0, 0.0))),
         **dissipation_from_json(case, num),
     )
@@ -144,6 +145,8 @@ def rhs_scales(prims, s):
     ci = np.abs(port.cons_from_prims(pi, s.gamma))
     c = port.speed_of_sound(pi[4], pi[0], s.gamma)
     for a in s.active:
+        if not s.is_convective_flux:
+            continue
         f = np.abs(np.nan_to_num(port.face_flux(prims, a, s)))
         wave = (np.abs(pi[1 + a]) + c)[None] * ci
         fl = np.maximum(fl, np.maximum(f.reshape(5, -1).max(axis=1), wave.reshape(5, -1).max(axis=1)) * float(s.inv_dx[a]))

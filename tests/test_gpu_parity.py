@@ -25,7 +25,8 @@ def make_solver(s: port.Setup, bc=None):
                       thermal_conductivity=s.thermal_conductivity, prandtl_number=s.prandtl_number,
                       gas_constant=s.gas_constant, is_interpolation_limiter=s.is_interpolation_limiter,
                       limit_velocity=s.limit_velocity, wall_velocity=dict(s.wall_velocity),
-                      dirichlet=dict(s.dirichlet), is_volume_force=s.is_volume_force, gravity=tuple(s.gravity))
+                      dirichlet=dict(s.dirichlet), is_volume_force=s.is_volume_force, gravity=tuple(s.gravity),
+                      is_convective_flux=s.is_convective_flux)
     return BlockSolver(cfg)
 
 
@@ -495,7 +496,8 @@ def test_dissipative_steps_against_oracle(cells, bc, integrator, extra):
 
 
 @pytest.mark.parametrize("name", ["tgv12_sym_visc_prandtl_rk3", "riemann2d_20x24_visc_rk3", "tgv16_sym_char_hllc_rk3",
-                                  "cavity_24x20_wall_js_visc_rk3", "sod100_js_char_hllc_rk3", "rti_16x48_dirichlet_gravity_rk3"])
+                                  "cavity_24x20_wall_js_visc_rk3", "sod100_js_char_hllc_rk3", "rti_16x48_dirichlet_gravity_rk3",
+                                  "heat1d_40_dirichlet_noconv_rk3"])
 def test_public_api_runs_reference_case_files(name):
     """The reference's JSON setups through InputManager -> InitializationManager -> SimulationManager
     (do_integration_step), compared with what the reference itself produced for them: dt sequence, state after
@@ -682,3 +684,28 @@ def test_dirichlet_and_gravity_steps(cells, gravity, visc):
     sl = [slice(None)] + list(s.interior)
     sl[1 + last] = slice(0, s.nh)
     assert np.array_equal(gp[tuple(sl)], np.broadcast_to(np.array(s.dirichlet[lo_f]).reshape(5, 1, 1, 1), gp[tuple(sl)].shape))
+
+
+@pytest.mark.parametrize("cells,bc", [((60, 1, 1), "ZEROGRADIENT"), ((20, 24, 1), "PERIODIC"), ((12, 10, 16), "SYMMETRY")])
+def test_dissipative_only_steps(cells, bc):
+    """active_physics/is_convective_flux = false (the heat-equation examples): rhs = dissipative fluxes only, stage
+    runs unfused (update kernel + halo kernels); 4 steps incl. dt against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    s = diss_setup(cells, bc, DISS[1])
+    s.is_convective_flux = False
+    prims, cons = port.initialize(H.smooth_ic(s, seed=31, amp=0.1), s)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    ref = port.compute_rhs(prims, s)
+    got = host(sol.compute_rhs(p))
+    sc = np.maximum(np.abs(ref).reshape(5, -1).max(axis=1), 1e-3 * np.abs(ref).max())
+    assert max(np.abs(got[v] - ref[v]).max() / sc[v] for v in range(5)) <= 1e-12
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    m = H.defined_mask(s)
+    for _ in range(4):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+        assert abs(st.dt.item() - dt) <= 1e-12 * dt
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+    assert H.rel_linf(host(st.conservatives)[:, m], cons[:, m]) <= 1e-12
