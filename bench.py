@@ -305,7 +305,13 @@ def main():
     if world > 1:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        opts = None
+        if os.environ.get("JXF_COMM_PRIORITY", "1") != "0":
+            try:                      # NCCL kernels on a high-priority stream: they overlap a sweep that fills the SMs
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:
+                opts = None
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local), pg_options=opts)
         if rank == 0:
             entry.build()
         dist.barrier()

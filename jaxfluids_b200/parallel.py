@@ -44,7 +44,13 @@ class ParallelContext:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
                 if torch.cuda.is_available():
                     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-                dist.init_process_group(backend=backend)
+                opts = None
+                if backend == "nccl":
+                    try:              # NCCL kernels overlap sweeps that fill the SMs: high-priority stream
+                        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                    except Exception:
+                        opts = None
+                dist.init_process_group(backend=backend, pg_options=opts)
                 return cls(domain_information, dist.get_rank(), dist.get_world_size())
         return cls(domain_information, 0, 1)
 

@@ -102,7 +102,10 @@ class BlockRuntime:
         # inter-block exchange runs on its own stream and overlaps the first sweep of the next stage
         self.overlap = (bool(self.neighbors) and os.environ.get("JXF_OVERLAP", "1") != "0"
                         and not self.cfg.is_dissipative)
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.neighbors else None
+        # high priority: the pack / unpack kernels of the exchange share the SMs with the overlapped sweep (which
+        # fills every SM); with a high-priority stream their CTAs take the slots that free up first
+        prio = -1 if os.environ.get("JXF_COMM_PRIORITY", "1") != "0" else 0
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=prio) if self.neighbors else None
         self._pending = None                      # event: halos of the current primitives are complete
         first = s.active[0]
         self._first_axis = first

@@ -33,8 +33,8 @@ bc = os.environ["JXF_BC"]
 nsteps = int(os.environ["JXF_STEPS"])
 cells = tuple(int(v) for v in os.environ["JXF_CELLS"].split(","))
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-dist.init_process_group("nccl")
-rank = dist.get_rank()
+# no explicit init_process_group: the package creates the NCCL group itself from the torchrun environment
+# (ParallelContext.from_environment) when the first manager needs the block runtime
 s = H.make_setup(cells, bc=bc, gamma=1.4, length=1.0)
 visc = os.environ.get("JXF_VISC", "0") == "1"
 if visc:
@@ -62,6 +62,8 @@ if visc:
                                                 "thermal_conductivity": {"model": "PRANDTL", "prandtl_number": 0.71}}
 im = InputManager(case, num)
 init = InitializationManager(im)
+assert dist.is_initialized()
+rank = dist.get_rank()
 active = [i for i in range(3) if cells[i] > 1]
 user = prims0[[0] + [1 + i for i in active] + [4]]
 buf = init.initialization(user_prime_init=user)
