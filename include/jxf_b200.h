@@ -36,7 +36,8 @@ enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
 enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1 };
 /* ref: solvers/riemann_solvers/__init__.py:16-34 */
 enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1 };
-enum { JXF_SIGNAL_EINFELDT = 0 };
+/* ref: solvers/riemann_solvers/signal_speeds.py (DICT_SIGNAL_SPEEDS); DAVIS2 is marked not working upstream */
+enum { JXF_SIGNAL_EINFELDT = 0, JXF_SIGNAL_ARITHMETIC = 1, JXF_SIGNAL_RUSANOV = 2, JXF_SIGNAL_DAVIS = 3, JXF_SIGNAL_TORO = 4 };
 /* ref: time_integration/__init__.py:6-11 */
 enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2 };
 /* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */

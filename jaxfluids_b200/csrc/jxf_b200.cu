@@ -63,7 +63,8 @@ struct SweepArgs {
   int fuse_halo;           // EPI: also write the outer-BC halo images of boundary-adjacent cells
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
-  int limiter;             // interpolation limiter: 0 off, 1 density + pressure, 2 all primitives
+  int limiter;             // face-flux options: interpolation limiter (0 off, 1 density + pressure, 2 all primitives)
+                           // | HLLC signal speed (JXF_SIGNAL_*) << 4
   int volume_force;        // EPI: add the gravity source (g_i rho, g . rho u) of the stage's conservatives
   double gravity[3];
   double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
@@ -1175,7 +1176,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
   if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
-  if (cfg->signal_speed != JXF_SIGNAL_EINFELDT)
+  if (cfg->signal_speed < JXF_SIGNAL_EINFELDT || cfg->signal_speed > JXF_SIGNAL_TORO)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
   if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
@@ -1543,7 +1544,8 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   a.gamma = s->cfg.gamma;
   a.inv_dx = s->cfg.inv_dx[axis];
   a.active_mask = s->active_mask;
-  a.limiter = s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0;
+  // packed face-flux options (numerics.cuh face_flux `opt`): limiter mode | signal speed << 4
+  a.limiter = (s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0) | (s->cfg.signal_speed << 4);
   return a;
 }
 

@@ -17,6 +17,36 @@ enum { RECON_PRIMITIVE = 0, RECON_CHAR_PRIMITIVE = 1 };   // reconstruction vari
 enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1 };          // reconstruction stencil  = RECON >> 1
 // The kernels' RECON template parameter carries both: RECON = variable + 2 * stencil.
 enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
+// HLLC wave-speed estimate (signal_speeds.py): a run-time option `sig` of riemann_flux (uniform branch), packed
+// with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4)
+enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG_TORO = 4 };
+
+// signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order
+__device__ __forceinline__ void simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
+                                                     double rhoR, double pL, double pR, double gamma, double& S_L,
+                                                     double& S_R) {
+  if (sig == SIG_ARITHMETIC) {
+    const double u_mean = 0.5 * (uL + uR), a_mean = 0.5 * (aL + aR);
+    S_L = fmin(u_mean - a_mean, uL - aL);
+    S_R = fmax(u_mean + a_mean, uR + aR);
+  } else if (sig == SIG_RUSANOV) {
+    const double S_plus = fmax(fabs(uL) + aL, fabs(uR) + aR);
+    S_L = -S_plus;
+    S_R = S_plus;
+  } else if (sig == SIG_DAVIS) {
+    S_L = fmin(uL - aL, uR - aR);
+    S_R = fmax(uL + aL, uR + aR);
+  } else {   // SIG_TORO
+    const double rho_bar = 0.5 * (rhoL + rhoR), a_bar = 0.5 * (aL + aR);
+    const double p_pvrs = 0.5 * (pL + pR) - 0.5 * (uR - uL) * rho_bar * a_bar;
+    const double p_star = fmax(0.0, p_pvrs);
+    const double g_ = (gamma + 1) * 0.5 / gamma;
+    const double qL = (p_star <= pL) ? 1.0 : sqrt(1 + g_ * (p_star / pL - 1));
+    const double qR = (p_star <= pR) ? 1.0 : sqrt(1 + g_ * (p_star / pR - 1));
+    S_L = uL - aL * qL;
+    S_R = uR + aR * qR;
+  }
+}
 
 // velocity_minor_axes, equation_information.py:110
 template <int A> struct AxisIds;
@@ -189,7 +219,7 @@ __device__ __forceinline__ void hllc_star_flux(const double (&p)[5], const doubl
 
 template <int A, int RIEMANN>
 __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double (&pr)[5],
-                                             double gamma, double (&F)[5]) {
+                                             double gamma, double (&F)[5], int sig = SIG_EINFELDT) {
   using Id = AxisIds<A>;
   double cl[5], cr[5];
   cons_from_prims(pl, gamma, cl);
@@ -198,14 +228,19 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
   const double aR = sqrt(gamma * pr[4] / pr[0]);
   const double uL = pl[Id::un], uR = pr[Id::un];
   if (RIEMANN == RIEMANN_HLLC) {
-    const double sL = sqrt(pl[0]), sR = sqrt(pr[0]);
-    const double one_dens = 1.0 / (sL + sR);
-    const double eta2 = 0.5 * sL * sR * one_dens * one_dens;
-    const double u_bar = (sL * uL + sR * uR) * one_dens;
-    const double du = uR - uL;
-    const double d_bar = sqrt((sL * aL * aL + sR * aR * aR) * one_dens + eta2 * (du * du));
-    const double S_L = fmin(u_bar - d_bar, uL - aL);
-    const double S_R = fmax(u_bar + d_bar, uR + aR);
+    double S_L, S_R;
+    if (sig == SIG_EINFELDT) {
+      const double sL = sqrt(pl[0]), sR = sqrt(pr[0]);
+      const double one_dens = 1.0 / (sL + sR);
+      const double eta2 = 0.5 * sL * sR * one_dens * one_dens;
+      const double u_bar = (sL * uL + sR * uR) * one_dens;
+      const double du = uR - uL;
+      const double d_bar = sqrt((sL * aL * aL + sR * aR * aR) * one_dens + eta2 * (du * du));
+      S_L = fmin(u_bar - d_bar, uL - aL);
+      S_R = fmax(u_bar + d_bar, uR + aR);
+    } else {
+      simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma, S_L, S_R);
+    }
     const double dL = pl[0] * (S_L - uL);
     const double dR = pr[0] * (S_R - uR);
     const double S_star = ((pr[4] - pl[4]) + (uL * dL - uR * dR)) / (dL - dR);
@@ -597,7 +632,7 @@ __device__ __forceinline__ void hllc_star_flux(const double (&p)[5], double ig1,
 
 template <int A, int RIEMANN>
 __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double (&pr)[5],
-                                             double gamma, double (&F)[5]) {
+                                             double gamma, double (&F)[5], int sig = SIG_EINFELDT) {
   using Id = AxisIds<A>;
   const double ig1 = 1.0 / (gamma - 1.0);
   const double uL = pl[Id::un], uR = pr[Id::un];
@@ -607,15 +642,20 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
   const double a2L = gamma * pl[4] * irL, a2R = gamma * pr[4] * irR;       // a^2
   const double aL = sqrt_fast(a2L, rsqrt_fast(a2L)), aR = sqrt_fast(a2R, rsqrt_fast(a2R));
   if (RIEMANN == RIEMANN_HLLC) {
-    const double sL = pl[0] * yL, sR = pr[0] * yR;                         // sqrt(rho)
-    const double od = rcp_fast(sL + sR);
-    const double eta2 = 0.5 * sL * sR * od * od;
-    const double u_bar = fma(sL, uL, sR * uR) * od;
-    const double du = uR - uL;
-    const double x = fma(eta2, du * du, fma(sL, a2L, sR * a2R) * od);
-    const double d_bar = sqrt_fast(x, rsqrt_fast(x));
-    const double S_L = fmin(u_bar - d_bar, uL - aL);
-    const double S_R = fmax(u_bar + d_bar, uR + aR);
+    double S_L, S_R;
+    if (sig == SIG_EINFELDT) {
+      const double sL = pl[0] * yL, sR = pr[0] * yR;                       // sqrt(rho)
+      const double od = rcp_fast(sL + sR);
+      const double eta2 = 0.5 * sL * sR * od * od;
+      const double u_bar = fma(sL, uL, sR * uR) * od;
+      const double du = uR - uL;
+      const double x = fma(eta2, du * du, fma(sL, a2L, sR * a2R) * od);
+      const double d_bar = sqrt_fast(x, rsqrt_fast(x));
+      S_L = fmin(u_bar - d_bar, uL - aL);
+      S_R = fmax(u_bar + d_bar, uR + aR);
+    } else {      // the simple estimates (uniform branch; not the tuned path)
+      simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma, S_L, S_R);
+    }
     const double dL = pl[0] * (S_L - uL);
     const double dR = pr[0] * (S_R - uR);
     const double S_star = ((pr[4] - pl[4]) + fma(uL, dL, -(uR * dR))) * rcp_fast(dL - dR);
@@ -684,10 +724,10 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 // ---------------------------------------------------------------------------
 template <int A, int RIEMANN>
 __device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const double (&pr)[5], double gamma,
-                                                  double (&F)[5], bool& zero) {
+                                                  double (&F)[5], bool& zero, int sig = SIG_EINFELDT) {
   using Id = AxisIds<A>;
-  if (RIEMANN != RIEMANN_HLLC) {
-    riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+  if (RIEMANN != RIEMANN_HLLC || sig != SIG_EINFELDT) {
+    riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
     zero = false;
     return;
   }
@@ -761,19 +801,20 @@ __device__ __forceinline__ void limit_interpolation(double (&p)[5], const double
 
 // window -> numerical flux at the face (high_order_godunov.py:117-231)
 template <int A, int RECON, int RIEMANN>
-__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int lim = 0) {
+__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int opt = 0) {
+  const int lim = opt & 15, sig = opt >> 4;
   double pl[5], pr[5];
   reconstruct<A, RECON>(w, gamma, pl, pr);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
-  riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+  riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
 }
 
 #ifdef JXF_REFERENCE_ORDER
 template <int A, int RIEMANN>
 __device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const double (&pr)[5], double gamma,
-                                                  double (&F)[5], bool& zero) {
-  riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+                                                  double (&F)[5], bool& zero, int sig = SIG_EINFELDT) {
+  riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
   zero = false;
 }
 template <int RECON>
@@ -787,24 +828,25 @@ __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], doubl
 }
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&,
-                                                int lim = 0) {
-  face_flux<A, RECON, RIEMANN>(w, gamma, F, lim);
+                                                int opt = 0) {
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, opt);
 }
 #else
 // marching variant: shares the cell-centred weights of the as-is fields between consecutive faces
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
-                                                ReconCarry<RECON>& cy, int lim = 0) {
+                                                ReconCarry<RECON>& cy, int opt = 0) {
+  const int lim = opt & 15, sig = opt >> 4;
   double pl[5], pr[5];
   reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
 #if JXF_RIEMANN_MAIN
   bool zero;
-  riemann_flux_main<A, RIEMANN>(pl, pr, gamma, F, zero);
-  if (zero) riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+  riemann_flux_main<A, RIEMANN>(pl, pr, gamma, F, zero, sig);
+  if (zero) riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
 #else
-  riemann_flux<A, RIEMANN>(pl, pr, gamma, F);
+  riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
 #endif
 }
 #endif

@@ -50,6 +50,7 @@ class Setup:
     recon: str = "CHAR-PRIMITIVE"                # or PRIMITIVE
     stencil: str = "WENO5-Z"                     # or WENO5-JS (godunov.reconstruction_stencil)
     riemann: str = "HLLC"                        # or RUSANOV
+    signal_speed: str = "EINFELDT"               # HLLC wave-speed estimate: EINFELDT | ARITHMETIC | RUSANOV | DAVIS | TORO
     integrator: str = "RK3"
     cfl: float = 0.5
     fixed_timestep: float | None = None
@@ -419,6 +420,31 @@ def einfeldt(u_L, u_R, a_L, a_R, rho_L, rho_R):
     return np.minimum(u_bar - d_bar, u_L - a_L), np.maximum(u_bar + d_bar, u_R + a_R)
 
 
+def signal_speeds(name, u_L, u_R, a_L, a_R, rho_L, rho_R, p_L, p_R, gamma):
+    """solvers/riemann_solvers/signal_speeds.py:10-69, :109-157 (+ estimate_pressure :201-214)."""
+    if name == "EINFELDT":
+        return einfeldt(u_L, u_R, a_L, a_R, rho_L, rho_R)
+    if name == "ARITHMETIC":
+        u_mean = 0.5 * (u_L + u_R)
+        a_mean = 0.5 * (a_L + a_R)
+        return np.minimum(u_mean - a_mean, u_L - a_L), np.maximum(u_mean + a_mean, u_R + a_R)
+    if name == "RUSANOV":
+        S_plus = np.maximum(np.abs(u_L) + a_L, np.abs(u_R) + a_R)
+        return -S_plus, S_plus
+    if name == "DAVIS":
+        return np.minimum(u_L - a_L, u_R - a_R), np.maximum(u_L + a_L, u_R + a_R)
+    if name == "TORO":
+        rho_bar = 0.5 * (rho_L + rho_R)
+        a_bar = 0.5 * (a_L + a_R)
+        p_pvrs = 0.5 * (p_L + p_R) - 0.5 * (u_R - u_L) * rho_bar * a_bar
+        p_star = np.maximum(0.0, p_pvrs)
+        gamma_ = (gamma + 1) * 0.5 / gamma
+        q_L = 1.0 * (p_star <= p_L) + np.sqrt(1 + gamma_ * (p_star / p_L - 1)) * (p_star > p_L)
+        q_R = 1.0 * (p_star <= p_R) + np.sqrt(1 + gamma_ * (p_star / p_R - 1)) * (p_star > p_R)
+        return u_L - a_L * q_L, u_R + a_R * q_R
+    raise NotImplementedError(name)
+
+
 def sstar(u_L, u_R, p_L, p_R, rho_L, rho_R, S_L, S_R):
     """signal_speeds.py:159-199."""
     dL = rho_L * (S_L - u_L)
@@ -442,12 +468,12 @@ def _hllc_star_flux(p, c, S_K, S_star, axis, left):
     return f + S * (us - c)
 
 
-def hllc(pl, pr, cl, cr, axis, gamma):
+def hllc(pl, pr, cl, cr, axis, gamma, signal_speed="EINFELDT"):
     """HLLC.py:80-126."""
     ua = 1 + axis
     aL = speed_of_sound(pl[4], pl[0], gamma)
     aR = speed_of_sound(pr[4], pr[0], gamma)
-    S_L, S_R = einfeldt(pl[ua], pr[ua], aL, aR, pl[0], pr[0])
+    S_L, S_R = signal_speeds(signal_speed, pl[ua], pr[ua], aL, aR, pl[0], pr[0], pl[4], pr[4], gamma)
     S_s = sstar(pl[ua], pr[ua], pl[4], pr[4], pl[0], pr[0], S_L, S_R)
     fL = _hllc_star_flux(pl, cl, S_L, S_s, axis, True)
     fR = _hllc_star_flux(pr, cr, S_R, S_s, axis, False)
@@ -602,7 +628,7 @@ def face_flux(prims, axis, s: Setup):
     """high_order_godunov.py:117-231: face fluxes (5, N_axis+1, transverse interior)."""
     pl, pr, cl, cr = reconstruct(prims, axis, s)
     if s.riemann == "HLLC":
-        return hllc(pl, pr, cl, cr, axis, s.gamma)
+        return hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
     if s.riemann == "RUSANOV":
         return rusanov(pl, pr, cl, cr, axis, s.gamma)
     raise NotImplementedError(s.riemann)

@@ -62,7 +62,8 @@ def load_case(name: str):
     return case, num
 
 
-def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None):
+def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None,
+              signal_speed=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -79,6 +80,8 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         g["riemann_solver"] = riemann
     if stencil is not None:
         g["reconstruction_stencil"] = stencil
+    if signal_speed is not None:
+        g["signal_speed"] = signal_speed
     if integrator is not None:
         num["conservatives"]["time_integration"]["integrator"] = integrator
     # keep the reference from writing anything / printing the banner

@@ -62,6 +62,7 @@ def setup_from_json(case, num) -> port.Setup:
         recon=g.get("reconstruction_variable", "PRIMITIVE"),
         stencil=g.get("reconstruction_stencil", "WENO5-Z"),
         riemann=g.get("riemann_solver", "HLLC"),
+        signal_speed=g.get("signal_speed", "EINFELDT"),
         integrator=c["time_integration"]["integrator"],
         cfl=c["time_integration"].get("CFL", 0.5),
         is_interpolation_limiter=bool((c.get("positivity", {}) or {}).get("is_interpolation_limiter", False)),

@@ -23,8 +23,15 @@ def load(fma=True, reference_order=False):
                        ["-o", so, SRC], check=True)
     lib = C.CDLL(so)
     lib.face_flux_host.restype = C.c_int
-    lib.face_flux_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_double, C.c_void_p]
+    lib.face_flux_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_int]
     return lib
+
+
+def _opt(s):
+    """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4."""
+    lim = (2 if s.limit_velocity else 1) if s.is_interpolation_limiter else 0
+    sig = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}[s.signal_speed]
+    return lim | (sig << 4)
 
 
 def rhs_axis_march(prims, axis, s, fma=True):
@@ -33,7 +40,8 @@ def rhs_axis_march(prims, axis, s, fma=True):
     from oracle import port
     lib = load(fma, False)
     lib.face_flux_march_host.restype = C.c_int
-    lib.face_flux_march_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_void_p]
+    lib.face_flux_march_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_void_p,
+                                         C.c_int]
     w = np.stack(port._window(prims, axis, s), axis=-1)          # (5, X, Y, Z faces..., 6)
     w = np.moveaxis(w, 0, -2)                                    # (fx, fy, fz, 5, 6)
     w = np.moveaxis(w, axis, 2)                                  # sweep axis last of the three -> sequences
@@ -41,7 +49,7 @@ def rhs_axis_march(prims, axis, s, fma=True):
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
     rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
-                                  w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data)
+                                  w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s))
     assert rc == 0
     f = out.reshape(shp + (5,))
     f = np.moveaxis(f, 2, axis)                                  # back to (fx, fy, fz, 5)
@@ -63,7 +71,7 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
     rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
-                            w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data)
+                            w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s))
     assert rc == 0
     f = np.moveaxis(out.reshape(shp + (5,)), -1, 0)
     lo = [slice(None)] * 4

@@ -69,7 +69,7 @@ def test_create_destroy_and_sizes(built_library):
     (dict(nh=2), -1, "halo_cells"),
     (dict(recon=3), -2, "reconstruction_variable"),
     (dict(riemann=5), -2, "riemann_solver"),
-    (dict(sig=2), -2, "signal_speed"),
+    (dict(sig=9), -2, "signal_speed"),
     (dict(integ=3), -2, "integrator"),
     (dict(bc=[7] * 6), -2, "boundary type"),
     (dict(gamma=0.9), -1, "gamma"),

@@ -18,6 +18,7 @@ def make_solver(s: port.Setup, bc=None):
     from jaxfluids_b200.engine import BlockConfig, BlockSolver
     cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min),
                       gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, stencil=s.stencil, riemann=s.riemann,
+                      signal_speed=s.signal_speed,
                       integrator=s.integrator, cfl=s.cfl,
                       is_viscous_flux=s.is_viscous_flux, is_heat_flux=s.is_heat_flux,
                       is_viscous_heat_production=s.is_viscous_heat_production, dynamic_viscosity=s.dynamic_viscosity,
@@ -709,3 +710,28 @@ def test_dissipative_only_steps(cells, bc):
         assert abs(st.dt.item() - dt) <= 1e-12 * dt
     assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
     assert H.rel_linf(host(st.conservatives)[:, m], cons[:, m]) <= 1e-12
+
+
+@pytest.mark.parametrize("sig", ["ARITHMETIC", "RUSANOV", "DAVIS", "TORO"])
+@pytest.mark.parametrize("cells,bc,recon", [((120, 1, 1), "ZEROGRADIENT", "CHAR-PRIMITIVE"), ((32, 36, 1), "PERIODIC", "PRIMITIVE"),
+                                            ((16, 20, 40), "SYMMETRY", "CHAR-PRIMITIVE")])
+def test_hllc_signal_speed_estimates(cells, bc, recon, sig):
+    """godunov.signal_speed (signal_speeds.py:10-69, :135-157): per-axis rhs and 3 steps against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    s = H.make_setup(cells, bc=bc, recon=recon)
+    s.signal_speed = sig
+    prims, cons = port.initialize(H.smooth_ic(s, seed=6, amp=0.2), s)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    scales = H.rhs_scales(prims, s)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s), scale=scales) <= H.TOL_RHS, f"axis {a}"
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    for _ in range(3):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    m = H.defined_mask(s)
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12

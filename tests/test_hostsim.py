@@ -66,3 +66,41 @@ def test_marching_variant_with_carried_weights(name):
     for a in s.active:
         got = hostsim.rhs_axis_march(p_in, a, s, fma=True)
         assert H.rel_linf(got, g[f"rhs_axis{a}"], scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("stencil", ["WENO5-Z", "WENO5-JS"])
+@pytest.mark.parametrize("sig", ["EINFELDT", "ARITHMETIC", "RUSANOV", "DAVIS", "TORO"])
+def test_signal_speeds_and_stencils_host_simulated(sig, stencil):
+    """godunov.signal_speed x reconstruction_stencil: the device functions compiled for the host -- production
+    evaluation (with FMA) and its marching form within 1e-12 of the pinned oracle, the reference-order evaluation
+    (no FMA) bit-identical to it."""
+    for cells, recon, bc in [((48, 1, 1), "CHAR-PRIMITIVE", "ZEROGRADIENT"), ((14, 18, 1), "PRIMITIVE", "PERIODIC"),
+                             ((8, 10, 12), "CHAR-PRIMITIVE", "SYMMETRY")]:
+        s = H.make_setup(cells, bc=bc, recon=recon, stencil=stencil)
+        s.signal_speed = sig
+        prims, cons = port.initialize(H.smooth_ic(s, seed=4, amp=0.2), s)
+        scales = H.rhs_scales(prims, s)
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s)
+            assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)
+
+
+@pytest.mark.parametrize("tag", ["lv0", "lv1"])
+def test_interpolation_limiter_host_simulated(tag):
+    """limit_interpolation (numerics.cuh) on the reference's near-vacuum fixture, where it fires thousands of times."""
+    import json, os
+    g = np.load(os.path.join(H.GOLDEN, "special", "limiter_riemann2d_20x24.npz"))
+    case, num = json.loads(str(g[f"case_json_{tag}"])), json.loads(str(g[f"num_json_{tag}"]))
+    s = H.setup_from_json(case, num)
+    with np.errstate(all="ignore"):
+        p = g[f"prims_halo_{tag}"]
+        tot = 0.0
+        for a in s.active:
+            tot = tot + hostsim.rhs_axis(p, a, s, fma=True)
+        assert H.rel_linf(tot, g[f"rhs_{tag}"], scale=H.rhs_scales(p, s)) <= H.TOL_RHS
+        tot0 = 0.0
+        for a in s.active:
+            tot0 = tot0 + hostsim.rhs_axis(p, a, s, fma=False, reference_order=True)
+        assert np.array_equal(tot0, g[f"rhs_{tag}"], equal_nan=True)

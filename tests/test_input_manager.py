@@ -69,7 +69,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
 
 @pytest.mark.parametrize("path,value", [
     (GOD + ("riemann_solver",), "HLL"),
-    (GOD + ("signal_speed",), "DAVIS"),
+    (GOD + ("signal_speed",), "DAVIS2"),
     (GOD + ("reconstruction_stencil",), "TENO5"),
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),

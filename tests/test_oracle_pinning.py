@@ -22,6 +22,16 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     # WENO5-JS
     ("sod", dict(cells=(80, None, None), stencil="WENO5-JS"), 2),
     ("tgv", dict(cells=(10, 10, 10), stencil="WENO5-JS", recon="PRIMITIVE", bc="PERIODIC"), 1),
+    # HLLC signal speed estimates
+    ("sod", dict(cells=(64, None, None), signal_speed="TORO"), 2),
+    ("sod", dict(cells=(64, None, None), signal_speed="ARITHMETIC"), 2),
+    ("riemann2d", dict(cells=(16, 16, None), signal_speed="DAVIS"), 1),
+    ("riemann2d", dict(cells=(16, 16, None), signal_speed="RUSANOV"), 1),
+    # the shipped lid-driven cavity / Rayleigh-Taylor / heat-equation examples (WALL, DIRICHLET, gravity, limiter,
+    # WENO5-JS, viscous, heat flux only)
+    ("cavity", dict(cells=(16, 14, None)), 2),
+    ("rti", dict(cells=(12, 32, None)), 2),
+    ("heat1d", dict(cells=(32, None, None)), 2),
 ])
 def test_port_is_bit_identical_to_reference(name, kw, nsteps):
     from oracle.refharness import pin_check
