@@ -21,10 +21,19 @@ enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
 // with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4)
 enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG_TORO = 4 };
 
-// signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order
-__device__ __forceinline__ void simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
-                                                     double rhoR, double pL, double pR, double gamma, double& S_L,
-                                                     double& S_R) {
+// signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order.
+// OUT OF LINE: the tuned path is EINFELDT; keeping these (IEEE sqrt / divisions) out of the sweep loops keeps the
+// hot loops' size and register allocation what they are without them.
+#ifndef JXF_NOINLINE
+#ifdef __CUDACC__
+#define JXF_NOINLINE __noinline__
+#else
+#define JXF_NOINLINE
+#endif
+#endif
+__device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
+                                                    double rhoR, double pL, double pR, double gamma) {
+  double S_L, S_R;
   if (sig == SIG_ARITHMETIC) {
     const double u_mean = 0.5 * (uL + uR), a_mean = 0.5 * (aL + aR);
     S_L = fmin(u_mean - a_mean, uL - aL);
@@ -46,6 +55,10 @@ __device__ __forceinline__ void simple_signal_speeds(int sig, double uL, double 
     S_L = uL - aL * qL;
     S_R = uR + aR * qR;
   }
+  double2 r;
+  r.x = S_L;
+  r.y = S_R;
+  return r;
 }
 
 // velocity_minor_axes, equation_information.py:110
@@ -239,7 +252,9 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
       S_L = fmin(u_bar - d_bar, uL - aL);
       S_R = fmax(u_bar + d_bar, uR + aR);
     } else {
-      simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma, S_L, S_R);
+      const double2 ss = simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+      S_L = ss.x;
+      S_R = ss.y;
     }
     const double dL = pl[0] * (S_L - uL);
     const double dR = pr[0] * (S_R - uR);
@@ -654,7 +669,9 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
       S_L = fmin(u_bar - d_bar, uL - aL);
       S_R = fmax(u_bar + d_bar, uR + aR);
     } else {      // the simple estimates (uniform branch; not the tuned path)
-      simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma, S_L, S_R);
+      const double2 ss = simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+      S_L = ss.x;
+      S_R = ss.y;
     }
     const double dL = pl[0] * (S_L - uL);
     const double dR = pr[0] * (S_R - uR);
