@@ -457,7 +457,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_reference_run(steps=3, warmup=1, budget_s=float(os.environ.get("JXF_CPU_BUDGET_S", "40")))
+        cpu_baseline, _ = cpu_reference_run(steps=3, warmup=1, budget_s=float(os.environ.get("JXF_CPU_BUDGET_S", "100")))
 
     if rank == 0:
         line = {"metric": "cell-updates/sec (MCUPS) per RK3 step, 3D TGV fp64", "value": mcups, "unit": "MCUPS",
