@@ -263,6 +263,7 @@ __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const SweepArg
                    a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1]);
 }
 
+#ifdef JXF_WITH_STRIDED   // the register-window predecessor of sweep_march: A/B builds only (-DJXF_WITH_STRIDED)
 // ---------------------------------------------------------------------------
 // strided sweep: thread = one (i1, i2) column (i2 along the contiguous axis), marching along A
 // over one chunk with a rolling 6-cell register window; each face flux is computed once.
@@ -325,6 +326,8 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const __gri
     if (a.reduce) red_commit(red, a.red);
   }
 }
+
+#endif  // JXF_WITH_STRIDED
 
 // ---------------------------------------------------------------------------
 // strided sweep, production form ("march"): same thread mapping as sweep_strided, but the 6-cell
@@ -1131,7 +1134,7 @@ struct jxf_solver {
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
-  bool no_march;       // JXF_NO_MARCH=1: register-window strided kernel instead of the shared-memory ring (tests)
+  bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
   int n_maps;
   const void* map_ptr[8];
   CUtensorMap map[8];
@@ -1247,7 +1250,10 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     if (s->n_active == 3 && so && strcmp(so, "xzy") == 0) { s->order[0] = 0; s->order[1] = 2; s->order[2] = 1; }
   }
   s->tma_ok = !(getenv("JXF_NO_TMA") && atoi(getenv("JXF_NO_TMA")) != 0);
+  s->no_march = false;
+#ifdef JXF_WITH_STRIDED
   s->no_march = getenv("JXF_NO_MARCH") && atoi(getenv("JXF_NO_MARCH")) != 0;
+#endif
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
   s->n_maps = 0;
   s->num_sms = 148;
@@ -1412,9 +1418,7 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
     const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
-#if JXF_MARCH_KERNEL
     const int resident = s->num_sms * (s->no_march ? JXF_MIN_BLOCKS : JXF_MARCH_BLOCKS);
-#endif
     // chunks along A: every chunk costs one redundant face (+ a 5-plane prologue), while few CTAs per
     // resident slot leave a partial last wave; pick the chunk count that minimises
     // (1 + 1.5/chunk_len) * ceil(waves)/waves over chunk lengths >= 16 cells
@@ -1435,13 +1439,13 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     dim3 grid(bx, chunks);
     set_role_bcs(sg, a);
     ProfScope prof(s, A + 3 * EPI, st);
-#if JXF_MARCH_KERNEL
-    if (!s->no_march) {
-      sweep_march<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
-      return check_launch("sweep_march");
+#ifdef JXF_WITH_STRIDED
+    if (s->no_march) {
+      sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
+      return check_launch("sweep_strided");
     }
 #endif
-    sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
+    sweep_march<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
   } else {
     sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
     sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];

@@ -336,13 +336,13 @@ def test_rows_kernel_tma_and_cp_async(cells, bc, no_tma, monkeypatch):
     assert abs(st.dt.item() - dt) <= 1e-12 * dt
 
 
-@pytest.mark.parametrize("no_march,order", [(0, "xzy"), (1, "xzy"), (0, "xyz"), (1, "xyz")])
+@pytest.mark.parametrize("no_march,order", [(0, "xzy"), (0, "xyz")])
 @pytest.mark.parametrize("cells,bc,recon,riemann", [
     ((20, 16, 12), "PERIODIC", "CHAR-PRIMITIVE", "HLLC"), ((12, 36, 10), "SYMMETRY", "PRIMITIVE", "HLLC"),
     ((40, 8, 9), "ZEROGRADIENT", "CHAR-PRIMITIVE", "RUSANOV"), ((33, 20, 1), "SYMMETRY", "CHAR-PRIMITIVE", "HLLC")])
 def test_strided_forms_and_sweep_orders(cells, bc, recon, riemann, no_march, order, monkeypatch):
-    """Both forms of the strided sweep (shared-memory ring `sweep_march`, register window `sweep_strided`)
-    and both stage sweep orders (epilogue on the marching y sweep, or on the contiguous z sweep): rhs and
+    """The marching sweep (shared-memory ring `sweep_march`; its register-window predecessor `sweep_strided` is
+    compiled only with -DJXF_WITH_STRIDED) and both stage sweep orders (epilogue on the marching y sweep, or on the contiguous z sweep): rhs and
     3 full steps incl. fused epilogue / halo images, against the oracle."""
     from jaxfluids_b200.engine import BlockState
     monkeypatch.setenv("JXF_NO_MARCH", str(no_march))
