@@ -284,6 +284,9 @@ class InputManager:
             if k.startswith("is_") and v and k != "is_interpolation_limiter":
                 raise NotImplementedError(f"conservatives/positivity/{k} is not implemented on the B200 path "
                                           "(implemented: is_interpolation_limiter)")
+        if pos_d.get("flux_limiter") not in (None, False):
+            raise NotImplementedError(f"conservatives/positivity/flux_limiter = '{pos_d['flux_limiter']}' is not "
+                                      "implemented on the B200 path (implemented: is_interpolation_limiter)")
         positivity = PositivitySetup(
             bool(get_setup_value(pos_d, "is_interpolation_limiter", "conservatives/positivity/is_interpolation_limiter",
                                  bool, True, False)),
