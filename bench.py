@@ -256,6 +256,87 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, threads: int | N
                       f"reference sources run on the NumPy jax stand-in"}, el / steps * 1e3
 
 
+def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, world, barrier):
+    """End to end through the public API with HOST buffers."""
+    import torch
+    import torch.distributed as dist
+    k_e2e = args.e2e_steps or max(2, min(args.steps, 5))
+    host_state = torch.empty(tuple(rt.primitives.shape), dtype=torch.float64, pin_memory=True)
+    host_state.copy_(rt.primitives)
+    jb = buffers._replace(time_control_variables=tcv._replace(physical_simulation_time=time_now,
+                                                              physical_timestep_size=dt_now))
+    def one_step(jb_):
+        rt.solver.cons_from_prims(rt.primitives, rt.conservatives)
+        mf = jb_.simulation_buffers.material_fields._replace(primitives=rt.primitives, conservatives=rt.conservatives)
+        jb_ = jb_._replace(simulation_buffers=jb_.simulation_buffers._replace(material_fields=mf))
+        return sim.do_integration_step(jb_)[0]          # public API; reads (t, dt, min rho, min p) back = D2H
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    # (1) serial: upload, then step, then read back -- nothing overlaps
+    def serial():
+        nonlocal jb
+        for _ in range(k_e2e):
+            # H2D: the step's input state (the block's halo'd primitive buffer) from pinned host memory;
+            # the conservatives are rebuilt from it on the device
+            rt.primitives.copy_(host_state, non_blocking=True)
+            jb = one_step(jb)
+    ms_serial = timed(serial)
+
+    # (2) pipelined: the upload of step k+1's host input (copy stream, device staging buffer) overlaps step k;
+    # every step still uploads its own input from pinned host memory and reads its result back inside the
+    # timed region, and the first upload is not overlapped with anything
+    k_pipe = max(k_e2e, args.steps)
+    stagebuf = [torch.empty_like(rt.primitives) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    up = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i % 2])
+            stagebuf[i % 2].copy_(host_state, non_blocking=True)
+            up[i % 2].record(copy_stream)
+
+    def pipelined():
+        nonlocal jb
+        cur = torch.cuda.current_stream()
+        for ev in free:
+            ev.record(cur)
+        upload(0)
+        for k in range(k_pipe):
+            if k + 1 < k_pipe:
+                upload(k + 1)
+            cur.wait_event(up[k % 2])
+            rt.primitives.copy_(stagebuf[k % 2], non_blocking=True)
+            free[k % 2].record(cur)
+            jb = one_step(jb)
+    ms_pipe = timed(pipelined)
+    del stagebuf
+    e2e = {"value": cells_global * k_pipe / (ms_pipe * 1e-3) / 1e6, "unit": "MCUPS",
+           "h2d_bytes_per_step": int(host_state.numel() * 8), "d2h_bytes_per_step": 40,
+           "steps": k_pipe, "ms_per_step": ms_pipe / k_pipe,
+           "what": "per step: H2D of the block's halo'd primitive buffer from pinned host memory (copy stream, "
+                   "device staging buffer; the upload of step k+1 overlaps step k, the first upload overlaps "
+                   "nothing), device copy into the state, prim->cons on the device, "
+                   "SimulationManager.do_integration_step, D2H of (t, dt, max speed, min rho, min p); "
+                   "PCIe-bound (5.7 GB per step)",
+           "serial": {"value": cells_global * k_e2e / (ms_serial * 1e-3) / 1e6, "steps": k_e2e,
+                      "ms_per_step": ms_serial / k_e2e, "what": "same without any overlap (upload, then step)"}}
+
+    return e2e
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -424,79 +505,12 @@ def main():
     # ---- end-to-end through the public API with HOST buffers ---------------------------------
     e2e = None
     if not args.no_e2e:
-        k_e2e = args.e2e_steps or max(2, min(args.steps, 5))
-        host_state = torch.empty(tuple(rt.primitives.shape), dtype=torch.float64, pin_memory=True)
-        host_state.copy_(rt.primitives)
-        jb = buffers._replace(time_control_variables=tcv._replace(physical_simulation_time=time_now,
-                                                                  physical_timestep_size=dt_now))
-        def one_step(jb_):
-            rt.solver.cons_from_prims(rt.primitives, rt.conservatives)
-            mf = jb_.simulation_buffers.material_fields._replace(primitives=rt.primitives, conservatives=rt.conservatives)
-            jb_ = jb_._replace(simulation_buffers=jb_.simulation_buffers._replace(material_fields=mf))
-            return sim.do_integration_step(jb_)[0]          # public API; reads (t, dt, min rho, min p) back = D2H
-
-        def timed(fn):
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            barrier()
-            te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        try:
+            e2e = measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, world, barrier)
+        except Exception as exc:                      # never lose the device-resident line to the host-buffer leg
             if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            return float(te.item())
-
-        # (1) serial: upload, then step, then read back -- nothing overlaps
-        def serial():
-            nonlocal jb
-            for _ in range(k_e2e):
-                # H2D: the step's input state (the block's halo'd primitive buffer) from pinned host memory;
-                # the conservatives are rebuilt from it on the device
-                rt.primitives.copy_(host_state, non_blocking=True)
-                jb = one_step(jb)
-        ms_serial = timed(serial)
-
-        # (2) pipelined: the upload of step k+1's host input (copy stream, device staging buffer) overlaps step k;
-        # every step still uploads its own input from pinned host memory and reads its result back inside the
-        # timed region, and the first upload is not overlapped with anything
-        k_pipe = max(k_e2e, args.steps)
-        stagebuf = [torch.empty_like(rt.primitives) for _ in range(2)]
-        copy_stream = torch.cuda.Stream()
-        up = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-
-        def upload(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[i % 2])
-                stagebuf[i % 2].copy_(host_state, non_blocking=True)
-                up[i % 2].record(copy_stream)
-
-        def pipelined():
-            nonlocal jb
-            cur = torch.cuda.current_stream()
-            for ev in free:
-                ev.record(cur)
-            upload(0)
-            for k in range(k_pipe):
-                if k + 1 < k_pipe:
-                    upload(k + 1)
-                cur.wait_event(up[k % 2])
-                rt.primitives.copy_(stagebuf[k % 2], non_blocking=True)
-                free[k % 2].record(cur)
-                jb = one_step(jb)
-        ms_pipe = timed(pipelined)
-        del stagebuf
-        e2e = {"value": cells_global * k_pipe / (ms_pipe * 1e-3) / 1e6, "unit": "MCUPS",
-               "h2d_bytes_per_step": int(host_state.numel() * 8), "d2h_bytes_per_step": 40,
-               "steps": k_pipe, "ms_per_step": ms_pipe / k_pipe,
-               "what": "per step: H2D of the block's halo'd primitive buffer from pinned host memory (copy stream, "
-                       "device staging buffer; the upload of step k+1 overlaps step k, the first upload overlaps "
-                       "nothing), device copy into the state, prim->cons on the device, "
-                       "SimulationManager.do_integration_step, D2H of (t, dt, max speed, min rho, min p); "
-                       "PCIe-bound (5.7 GB per step)",
-               "serial": {"value": cells_global * k_e2e / (ms_serial * 1e-3) / 1e6, "steps": k_e2e,
-                          "ms_per_step": ms_serial / k_e2e, "what": "same without any overlap (upload, then step)"}}
+                raise                                 # ranks must stay in step: fail loudly instead of hanging
+            e2e = {"value": None, "unit": "MCUPS", "error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu_baseline = None
