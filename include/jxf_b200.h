@@ -35,7 +35,7 @@ enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
 /* ref: stencils/reconstruction/shock_capturing/weno/weno5_z.py, weno5_js.py (DICT_SPATIAL_RECONSTRUCTION) */
 enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1 };
 /* ref: solvers/riemann_solvers/__init__.py:16-34 */
-enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1 };
+enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1, JXF_RIEMANN_HLL = 2 /* HLL.py; uses jxf_config.signal_speed */ };
 /* ref: solvers/riemann_solvers/signal_speeds.py (DICT_SIGNAL_SPEEDS); DAVIS2 is marked not working upstream */
 enum { JXF_SIGNAL_EINFELDT = 0, JXF_SIGNAL_ARITHMETIC = 1, JXF_SIGNAL_RUSANOV = 2, JXF_SIGNAL_DAVIS = 3, JXF_SIGNAL_TORO = 4 };
 /* ref: time_integration/__init__.py:6-11 */

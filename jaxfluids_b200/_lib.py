@@ -22,7 +22,7 @@ EXPORTS = (
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
 STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1}
-RIEMANN = {"HLLC": 0, "RUSANOV": 1}
+RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2}
 SIGNAL = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}
 INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
 BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4, "WALL": 5, "DIRICHLET": 6}

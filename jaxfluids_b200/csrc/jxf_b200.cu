@@ -64,7 +64,7 @@ struct SweepArgs {
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
   int limiter;             // face-flux options: interpolation limiter (0 off, 1 density + pressure, 2 all primitives)
-                           // | HLLC signal speed (JXF_SIGNAL_*) << 4
+                           // | signal speed (JXF_SIGNAL_*) << 4 | HLL solver << 8
   int volume_force;        // EPI: add the gravity source (g_i rho, g . rho u) of the stage's conservatives
   double gravity[3];
   double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
@@ -1177,7 +1177,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
   if (cfg->stencil != JXF_STENCIL_WENO5Z && cfg->stencil != JXF_STENCIL_WENO5JS)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
-  if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV)
+  if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV && cfg->riemann != JXF_RIEMANN_HLL)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
   if (cfg->signal_speed < JXF_SIGNAL_EINFELDT || cfg->signal_speed > JXF_SIGNAL_TORO)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
@@ -1549,7 +1549,8 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   a.inv_dx = s->cfg.inv_dx[axis];
   a.active_mask = s->active_mask;
   // packed face-flux options (numerics.cuh face_flux `opt`): limiter mode | signal speed << 4
-  a.limiter = (s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0) | (s->cfg.signal_speed << 4);
+  a.limiter = (s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0) | (s->cfg.signal_speed << 4) |
+              ((s->cfg.riemann == JXF_RIEMANN_HLL ? 1 : 0) << 8);      // HLL rides on the RUSANOV instantiations
   return a;
 }
 

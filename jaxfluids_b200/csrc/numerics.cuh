@@ -18,7 +18,8 @@ enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1 };          // reconstruction ste
 // The kernels' RECON template parameter carries both: RECON = variable + 2 * stencil.
 enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
 // HLLC wave-speed estimate (signal_speeds.py): a run-time option `sig` of riemann_flux (uniform branch), packed
-// with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4)
+// with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4) | (HLL << 8), HLL = the HLL
+// Riemann solver (HLL.py) riding on the RIEMANN_RUSANOV kernel instantiations
 enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG_TORO = 4 };
 
 // signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order.
@@ -58,6 +59,22 @@ __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double 
   double2 r;
   r.x = S_L;
   r.y = S_R;
+  return r;
+}
+
+// signal_speeds.py:109-133 in the reference's order (IEEE sqrt / division) -- for the HLL solver, which is not a
+// tuned path (the HLLC kernels carry their own fast evaluation of the same formula)
+__device__ JXF_NOINLINE double2 einfeldt_signal_speeds(double uL, double uR, double aL, double aR, double rhoL,
+                                                      double rhoR) {
+  const double sL = sqrt(rhoL), sR = sqrt(rhoR);
+  const double one_dens = 1.0 / (sL + sR);
+  const double eta2 = 0.5 * sL * sR * one_dens * one_dens;
+  const double u_bar = (sL * uL + sR * uR) * one_dens;
+  const double du = uR - uL;
+  const double d_bar = sqrt((sL * aL * aL + sR * aR * aR) * one_dens + eta2 * (du * du));
+  double2 r;
+  r.x = fmin(u_bar - d_bar, uL - aL);
+  r.y = fmax(u_bar + d_bar, uR + aR);
   return r;
 }
 
@@ -242,7 +259,7 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
   const double uL = pl[Id::un], uR = pr[Id::un];
   if (RIEMANN == RIEMANN_HLLC) {
     double S_L, S_R;
-    if (sig == SIG_EINFELDT) {
+    if ((sig & 15) == SIG_EINFELDT) {
       const double sL = sqrt(pl[0]), sR = sqrt(pr[0]);
       const double one_dens = 1.0 / (sL + sR);
       const double eta2 = 0.5 * sL * sR * one_dens * one_dens;
@@ -252,7 +269,7 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
       S_L = fmin(u_bar - d_bar, uL - aL);
       S_R = fmax(u_bar + d_bar, uR + aR);
     } else {
-      const double2 ss = simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+      const double2 ss = simple_signal_speeds(sig & 15, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
       S_L = ss.x;
       S_R = ss.y;
     }
@@ -266,6 +283,18 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     const double wl = 0.5 * (1.0 + sgn), wr = 0.5 * (1.0 - sgn);
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = wl * fL[v] + wr * fR[v];
+  } else if ((sig >> 4) & 1) {
+    // HLL: solvers/riemann_solvers/HLL.py (the kernels' RIEMANN_RUSANOV instantiation with the HLL bit of `sig`)
+    const int sp = sig & 15;
+    const double2 ss = (sp == SIG_EINFELDT) ? einfeldt_signal_speeds(uL, uR, aL, aR, pl[0], pr[0])
+                                            : simple_signal_speeds(sp, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+    const double wL = fmin(ss.x, 0.0), wR = fmax(ss.y, 0.0);
+    double fl[5], fr[5];
+    physical_flux<A>(pl, cl, fl);
+    physical_flux<A>(pr, cr, fr);
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+      F[v] = (wR * fl[v] - wL * fr[v] + wL * wR * (cr[v] - cl[v])) / (wR - wL + kEps);
   } else {
     // Rusanov: solvers/riemann_solvers/Rusanov.py:25-47
     const double alpha = fmax(fabs(uL) + aL, fabs(uR) + aR);
@@ -658,7 +687,7 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
   const double aL = sqrt_fast(a2L, rsqrt_fast(a2L)), aR = sqrt_fast(a2R, rsqrt_fast(a2R));
   if (RIEMANN == RIEMANN_HLLC) {
     double S_L, S_R;
-    if (sig == SIG_EINFELDT) {
+    if ((sig & 15) == SIG_EINFELDT) {
       const double sL = pl[0] * yL, sR = pr[0] * yR;                       // sqrt(rho)
       const double od = rcp_fast(sL + sR);
       const double eta2 = 0.5 * sL * sR * od * od;
@@ -669,7 +698,7 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
       S_L = fmin(u_bar - d_bar, uL - aL);
       S_R = fmax(u_bar + d_bar, uR + aR);
     } else {      // the simple estimates (uniform branch; not the tuned path)
-      const double2 ss = simple_signal_speeds(sig, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+      const double2 ss = simple_signal_speeds(sig & 15, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
       S_L = ss.x;
       S_R = ss.y;
     }
@@ -710,6 +739,20 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = (S_star > 0.0) ? fL[v] : ((S_star < 0.0) ? fR[v] : 0.5 * (fL[v] + fR[v]));
 #endif
+  } else if ((sig >> 4) & 1) {
+    // HLL (HLL.py): F = (S_R+ F_L - S_L- F_R + S_L- S_R+ (U_R - U_L)) / (S_R+ - S_L- + eps)
+    const int sp = sig & 15;
+    const double2 ss = (sp == SIG_EINFELDT) ? einfeldt_signal_speeds(uL, uR, aL, aR, pl[0], pr[0])
+                                            : simple_signal_speeds(sp, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+    const double wL = fmin(ss.x, 0.0), wR = fmax(ss.y, 0.0);
+    double cl[5], cr[5], fl[5], fr[5];
+    cons_from_prims_fast(pl, ig1, cl);
+    cons_from_prims_fast(pr, ig1, cr);
+    physical_flux<A>(pl, cl, fl);
+    physical_flux<A>(pr, cr, fr);
+    const double inv = rcp_fast(wR - wL + kEps), ww = wL * wR;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = fma(ww, cr[v] - cl[v], fma(wR, fl[v], -(wL * fr[v]))) * inv;
   } else {
     double cl[5], cr[5];
     cons_from_prims_fast(pl, ig1, cl);
@@ -743,7 +786,7 @@ template <int A, int RIEMANN>
 __device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const double (&pr)[5], double gamma,
                                                   double (&F)[5], bool& zero, int sig = SIG_EINFELDT) {
   using Id = AxisIds<A>;
-  if (RIEMANN != RIEMANN_HLLC || sig != SIG_EINFELDT) {
+  if (RIEMANN != RIEMANN_HLLC || (sig & 15) != SIG_EINFELDT) {
     riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
     zero = false;
     return;

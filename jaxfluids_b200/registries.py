@@ -35,7 +35,7 @@ REFERENCE_BOUNDARY_TYPES = (
 
 # what the sm_100a kernels implement
 DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov"}
-DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov"}
+DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov", "HLL": "HLL"}
 DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt", "ARITHMETIC": "signal_speed_Arithmetic",
                       "RUSANOV": "signal_speed_Rusanov", "DAVIS": "signal_speed_Davis", "TORO": "signal_speed_Toro"}
 DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS"}

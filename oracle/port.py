@@ -480,6 +480,19 @@ def hllc(pl, pr, cl, cr, axis, gamma, signal_speed="EINFELDT"):
     return 0.5 * (1 + np.sign(S_s)) * fL + 0.5 * (1 - np.sign(S_s)) * fR
 
 
+def hll(pl, pr, cl, cr, axis, gamma, signal_speed="EINFELDT"):
+    """solvers/riemann_solvers/HLL.py (single phase)."""
+    ua = 1 + axis
+    aL = speed_of_sound(pl[4], pl[0], gamma)
+    aR = speed_of_sound(pr[4], pr[0], gamma)
+    S_L, S_R = signal_speeds(signal_speed, pl[ua], pr[ua], aL, aR, pl[0], pr[0], pl[4], pr[4], gamma)
+    wL = np.minimum(S_L, 0.0)
+    wR = np.maximum(S_R, 0.0)
+    fL = physical_flux(pl, cl, axis)
+    fR = physical_flux(pr, cr, axis)
+    return (wR * fL - wL * fR + wL * wR * (cr - cl)) / (wR - wL + EPS)
+
+
 def rusanov(pl, pr, cl, cr, axis, gamma):
     """Rusanov.py:25-47."""
     ua = 1 + axis
@@ -631,6 +644,8 @@ def face_flux(prims, axis, s: Setup):
         return hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
     if s.riemann == "RUSANOV":
         return rusanov(pl, pr, cl, cr, axis, s.gamma)
+    if s.riemann == "HLL":
+        return hll(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
     raise NotImplementedError(s.riemann)
 
 

@@ -47,6 +47,10 @@ FIXTURES = {
     "riemann2d_24x28_js_prim_hllc_rk3": ("riemann2d", dict(cells=(24, 28, None), stencil="WENO5-JS", recon="PRIMITIVE"), 5, (5,)),
     "tgv_10x12x10_per_js_prim_visc_rk3": ("tgv", dict(cells=(10, 12, 10), bc="PERIODIC", stencil="WENO5-JS", recon="PRIMITIVE",
                                                       dissipation=dict(mu=1e-2)), 2, (2,)),
+    # HLL Riemann solver (solvers/riemann_solvers/HLL.py)
+    "sod100_char_hll_rk3": ("sod", dict(cells=(100, None, None), riemann="HLL"), 10, (10,)),
+    "riemann2d_20x24_prim_hll_davis_rk3": ("riemann2d", dict(cells=(20, 24, None), recon="PRIMITIVE", riemann="HLL",
+                                                               signal_speed="DAVIS"), 3, (3,)),
     # the shipped lid-driven cavity example, shrunk: WALL on four faces (moving lid), WENO5-JS PRIMITIVE, viscous,
     # interpolation limiter on, halo_cells 4
     "cavity_24x20_wall_js_visc_rk3": ("cavity", dict(cells=(24, 20, None)), 5, (5,)),

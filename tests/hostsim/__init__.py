@@ -31,7 +31,7 @@ def _opt(s):
     """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4."""
     lim = (2 if s.limit_velocity else 1) if s.is_interpolation_limiter else 0
     sig = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}[s.signal_speed]
-    return lim | (sig << 4)
+    return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8)
 
 
 def rhs_axis_march(prims, axis, s, fma=True):
@@ -48,7 +48,7 @@ def rhs_axis_march(prims, axis, s, fma=True):
     shp = w.shape[:3]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+    rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
                                   w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s))
     assert rc == 0
     f = out.reshape(shp + (5,))
@@ -70,7 +70,7 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     shp = w.shape[:-2]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1}[s.riemann],
+    rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
                             w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s))
     assert rc == 0
     f = np.moveaxis(out.reshape(shp + (5,)), -1, 0)

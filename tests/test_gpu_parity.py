@@ -735,3 +735,28 @@ def test_hllc_signal_speed_estimates(cells, bc, recon, sig):
         st.step()
     m = H.defined_mask(s)
     assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+
+
+@pytest.mark.parametrize("sig", ["EINFELDT", "TORO"])
+@pytest.mark.parametrize("cells,bc,recon", [((120, 1, 1), "ZEROGRADIENT", "CHAR-PRIMITIVE"), ((32, 36, 1), "PERIODIC", "PRIMITIVE"),
+                                            ((16, 20, 40), "SYMMETRY", "CHAR-PRIMITIVE")])
+def test_hll_riemann_solver(cells, bc, recon, sig):
+    """riemann_solver = HLL (solvers/riemann_solvers/HLL.py): per-axis rhs and 3 steps against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    s = H.make_setup(cells, bc=bc, recon=recon, riemann="HLL")
+    s.signal_speed = sig
+    prims, cons = port.initialize(H.smooth_ic(s, seed=6, amp=0.2), s)
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    scales = H.rhs_scales(prims, s)
+    for a in s.active:
+        rhs = sol.new_rhs()
+        sol.sweep(a, p, rhs, accumulate=False)
+        assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s), scale=scales) <= H.TOL_RHS, f"axis {a}"
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    dt = port.time_step_size(prims, s)
+    for _ in range(3):
+        prims, cons, dt = port.step(prims, cons, dt, s)
+        st.step()
+    m = H.defined_mask(s)
+    assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12

@@ -104,3 +104,20 @@ def test_interpolation_limiter_host_simulated(tag):
         for a in s.active:
             tot0 = tot0 + hostsim.rhs_axis(p, a, s, fma=False, reference_order=True)
         assert np.array_equal(tot0, g[f"rhs_{tag}"], equal_nan=True)
+
+
+@pytest.mark.parametrize("sig", ["EINFELDT", "ARITHMETIC", "RUSANOV", "DAVIS", "TORO"])
+def test_hll_host_simulated(sig):
+    """riemann_solver = HLL (HLL.py) with every signal speed: production evaluation within 1e-12 of the pinned
+    oracle, reference-order evaluation bit-identical."""
+    for cells, recon, bc in [((48, 1, 1), "CHAR-PRIMITIVE", "ZEROGRADIENT"), ((14, 18, 1), "PRIMITIVE", "PERIODIC"),
+                             ((8, 10, 12), "CHAR-PRIMITIVE", "SYMMETRY")]:
+        s = H.make_setup(cells, bc=bc, recon=recon, riemann="HLL")
+        s.signal_speed = sig
+        prims, cons = port.initialize(H.smooth_ic(s, seed=8, amp=0.2), s)
+        scales = H.rhs_scales(prims, s)
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s)
+            assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)

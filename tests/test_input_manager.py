@@ -68,7 +68,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
 
 
 @pytest.mark.parametrize("path,value", [
-    (GOD + ("riemann_solver",), "HLL"),
+    (GOD + ("riemann_solver",), "HLLC-LM"),
     (GOD + ("signal_speed",), "DAVIS2"),
     (GOD + ("reconstruction_stencil",), "TENO5"),
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),

@@ -27,6 +27,9 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("sod", dict(cells=(64, None, None), signal_speed="ARITHMETIC"), 2),
     ("riemann2d", dict(cells=(16, 16, None), signal_speed="DAVIS"), 1),
     ("riemann2d", dict(cells=(16, 16, None), signal_speed="RUSANOV"), 1),
+    # HLL Riemann solver
+    ("sod", dict(cells=(64, None, None), riemann="HLL"), 2),
+    ("riemann2d", dict(cells=(16, 16, None), riemann="HLL", signal_speed="DAVIS"), 1),
     # the shipped lid-driven cavity / Rayleigh-Taylor / heat-equation examples (WALL, DIRICHLET, gravity, limiter,
     # WENO5-JS, viscous, heat flux only)
     ("cavity", dict(cells=(16, 14, None)), 2),
