@@ -82,7 +82,16 @@ typedef struct jxf_config {
   int32_t no_convective_flux;       /* 1: active_physics/is_convective_flux = false (dissipative fluxes only,
                                        space_solver.py:517-545); the stage then runs unfused              */
   double  gravity[3];
+  /* ref: conservatives/positivity/flux_limiter + flux_partition (solvers/positivity/limiter_flux.py:146-330,
+   * space_solver.py:532-543): faces whose flux would drive a neighbour cell's density / pressure below eps under the
+   * pseudo-integration with the physical time step fall back to the first-order HLLC flux. The sweeps read the time
+   * step from the device scalar of jxf_stage / jxf_step_fused; jxf_sweep / jxf_compute_rhs use jxf_bind_timestep. */
+  int32_t flux_limiter;             /* JXF_FLUXLIM_*                                              */
+  int32_t flux_partition;           /* JXF_PARTITION_*                                            */
 } jxf_config;
+
+enum { JXF_FLUXLIM_NONE = 0, JXF_FLUXLIM_SIMPLE = 1, JXF_FLUXLIM_NASA = 2 };
+enum { JXF_PARTITION_UNIFORM = 0, JXF_PARTITION_CELLSIZE = 1 };
 
 typedef struct jxf_solver* jxf_handle;
 
@@ -102,6 +111,11 @@ int jxf_num_stages(jxf_handle h);
 /* ref: SpaceSolver.compute_rhs (solvers/space_solver.py:151-453), convective single-phase branch:
  * rhs = 0.0 + rhs_x + rhs_y + rhs_z over the active axes.  prims: in, rhs: out. */
 int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, void* stream);
+
+/* The device scalar holding the physical time step size that jxf_sweep / jxf_sweep_range / jxf_compute_rhs hand to
+ * the positivity flux limiter (ref: the physical_timestep_size argument of SpaceSolver.compute_rhs,
+ * space_solver.py:151-164). Only needed when jxf_config.flux_limiter is set; the pointer is stored, not read. */
+int jxf_bind_timestep(jxf_handle h, const double* dt);
 
 /* ref: SpaceSolver.compute_rhs_xi (space_solver.py:456-674): one axis.
  * accumulate=0: rhs = 0.0 + rhs_axis ; accumulate=1: rhs += rhs_axis. */

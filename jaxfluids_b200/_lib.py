@@ -17,11 +17,13 @@ EXPORTS = (
     "jxf_last_error", "jxf_version", "jxf_create", "jxf_destroy", "jxf_field_elems", "jxf_rhs_elems",
     "jxf_num_stages", "jxf_compute_rhs", "jxf_sweep", "jxf_stage", "jxf_halo_fill", "jxf_prims_from_cons",
     "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
-    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature", "jxf_face_slab_elems_ext", "jxf_pack_face_ext", "jxf_unpack_face_ext",
+    "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature", "jxf_face_slab_elems_ext", "jxf_pack_face_ext", "jxf_unpack_face_ext", "jxf_bind_timestep",
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
 STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1}
+FLUX_LIMITER = {None: 0, False: 0, "SIMPLE": 1, "NASA": 2}
+FLUX_PARTITION = {"UNIFORM": 0, "CELLSIZE": 1}
 RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2}
 SIGNAL = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}
 INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
@@ -58,6 +60,8 @@ class JxfConfig(C.Structure):
         ("volume_force", C.c_int32),
         ("no_convective_flux", C.c_int32),
         ("gravity", C.c_double * 3),
+        ("flux_limiter", C.c_int32),
+        ("flux_partition", C.c_int32),
     ]
 
 
@@ -97,6 +101,8 @@ def load():
     lib.jxf_num_stages.argtypes = [vp]
     lib.jxf_compute_rhs.restype = i32
     lib.jxf_compute_rhs.argtypes = [vp, dp, dp, vp]
+    lib.jxf_bind_timestep.restype = i32
+    lib.jxf_bind_timestep.argtypes = [vp, dp]
     lib.jxf_sweep.restype = i32
     lib.jxf_sweep.argtypes = [vp, i32, dp, dp, i32, vp]
     lib.jxf_stage.restype = i32

@@ -64,7 +64,8 @@ struct SweepArgs {
   int nh;
   int bc[6];               // JXF_BC_* per physical face (east,west,north,south,top,bottom)
   int limiter;             // face-flux options: interpolation limiter (0 off, 1 density + pressure, 2 all primitives)
-                           // | signal speed (JXF_SIGNAL_*) << 4 | HLL solver << 8
+                           // | signal speed (JXF_SIGNAL_*) << 4 | HLL solver << 8 | flux limiter (1 SIMPLE, 2 NASA) << 9
+  FluxLimArgs fl;          // positivity flux limiter: dt pointer, 1/dx of the axis, flux partition
   int volume_force;        // EPI: add the gravity source (g_i rho, g . rho u) of the stage's conservatives
   double gravity[3];
   double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const __gri
       CellIn<EPI> in;
       if (f > f0) load_cell_in<EPI>(g, a, hidx, ridx, in);
       double F[5];
-      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter);
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter, a.fl);
       if (f > f0) {
         double r[5];
 #pragma unroll
@@ -414,7 +415,7 @@ sweep_march(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepAr
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[v][k] = ring[(j + k) & (kRingSlots - 1)][v][t];
       double F[5];
-      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter);
+      face_flux_carry<A, RECON, RIEMANN>(w, a.gamma, F, cy, a.limiter, a.fl);
       if (j > 0) {
         double r[5];
 #pragma unroll
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const __grid
 #pragma unroll
           for (int k = 0; k < 6; ++k) w[v][k] = base[v * g.vst + k * g.sA];
         if (fin) load_cell_in<EPI>(g, a, hidx, ridx, in);
-        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter);
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter, a.fl);
       }
       double Fl[5];
 #pragma unroll
@@ -583,13 +584,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // out-of-line flux from a strided global window (rare paths only)
 template <int A, int RECON, int RIEMANN>
 __device__ __noinline__ void face_flux_from_global(const double* base, long long vst, long long sA, double gamma,
-                                                   double (&F)[5], int lim) {
+                                                   double (&F)[5], int lim, const FluxLimArgs fl) {
   double w[5][6];
 #pragma unroll
   for (int v = 0; v < 5; ++v)
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[v][k] = base[v * vst + k * sA];
-  face_flux<A, RECON, RIEMANN>(w, gamma, F, lim);
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, lim, fl);
 }
 
 struct RowsArgs {
@@ -641,7 +642,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
       const long long row = row0 + lane;
       const int k1 = (int)(row / g.n2);
       const int k2 = (int)(row - (long long)k1 * g.n2);
-      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0, a.limiter);
+      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0, a.limiter, a.fl);
     }
     // ---- main sequence: (row r, iteration it), windows staged one step ahead ---------------------
     // All index state is carried incrementally in 32-bit registers (no divisions in the loop):
@@ -713,7 +714,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
         for (int v = 0; v < 5; ++v)
 #pragma unroll
           for (int k = 0; k < 6; ++k) w[v][k] = wl[v * kWinSlots + k];
-        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter);
+        face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter, a.fl);
       }
       double Fl[5];
 #pragma unroll
@@ -1089,7 +1090,8 @@ __global__ void __launch_bounds__(128) face_flux_debug_kernel(const double* __re
   for (int v = 0; v < 5; ++v)
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[v][k] = win[(i * 5 + v) * 6 + k];
-  face_flux<A, RECON, RIEMANN>(w, gamma, F);
+  const FluxLimArgs nofl = {nullptr, 0.0, 0.0};
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, 0, nofl);
 #pragma unroll
   for (int v = 0; v < 5; ++v) out[i * 5 + v] = F[v];
 }
@@ -1127,6 +1129,7 @@ struct jxf_solver {
   int active_mask;
   int lane_axis;      // contiguous active axis
   int order[3];       // order[k] = axis of the k-th sweep of a stage; the LAST one carries the fused epilogue
+  const double* dt_bound;   // jxf_bind_timestep: time step for the flux limiter outside jxf_stage
   int num_sms;
   int stages;
   double dt_mult[3];
@@ -1184,6 +1187,10 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
   if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
+  if (cfg->flux_limiter < JXF_FLUXLIM_NONE || cfg->flux_limiter > JXF_FLUXLIM_NASA)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: flux_limiter id %d not implemented on the B200 path", cfg->flux_limiter);
+  if (cfg->flux_partition < JXF_PARTITION_UNIFORM || cfg->flux_partition > JXF_PARTITION_CELLSIZE)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: flux_partition id %d not implemented on the B200 path", cfg->flux_partition);
   if (cfg->no_convective_flux && !(cfg->viscous_flux || cfg->heat_flux))
     return fail(JXF_ERR_BAD_ARG, "jxf_create: no flux is active");
   if (cfg->viscous_flux || cfg->heat_flux) {
@@ -1550,7 +1557,17 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   a.active_mask = s->active_mask;
   // packed face-flux options (numerics.cuh face_flux `opt`): limiter mode | signal speed << 4
   a.limiter = (s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0) | (s->cfg.signal_speed << 4) |
-              ((s->cfg.riemann == JXF_RIEMANN_HLL ? 1 : 0) << 8);      // HLL rides on the RUSANOV instantiations
+              ((s->cfg.riemann == JXF_RIEMANN_HLL ? 1 : 0) << 8) |     // HLL rides on the RUSANOV instantiations
+              (s->cfg.flux_limiter << 9);
+  // positivity flux limiter: lambda = dt / dx * sigma (limiter_flux.py:202-205, compute_partition :681-720)
+  a.fl.dt = s->dt_bound;
+  a.fl.inv_dx = s->cfg.inv_dx[axis];
+  a.fl.sigma = (double)s->n_active;
+  if (s->cfg.flux_partition == JXF_PARTITION_CELLSIZE) {
+    double sum = 0.0;
+    for (int k = 0; k < s->n_active; ++k) sum += s->cfg.inv_dx[s->active[k]];
+    a.fl.sigma = sum / s->cfg.inv_dx[axis];
+  }
   return a;
 }
 
@@ -1672,6 +1689,8 @@ extern "C" int jxf_sweep(jxf_handle h, int axis, const double* prims, double* rh
   if (axis < 0 || axis > 2 || h->g.n[axis] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_sweep: axis %d is not active", axis);
   if (h->cfg.no_convective_flux)      // flux_xi = 0 + dissipative part only (space_solver.py:517-584)
     return dissipative_sweep(h, axis, prims, rhs, accumulate, (cudaStream_t)stream);
+  if (h->cfg.flux_limiter && !h->dt_bound)
+    return fail(JXF_ERR_BAD_ARG, "jxf_sweep: the flux limiter needs the time step (jxf_bind_timestep)");
   SweepArgs a = base_args(h, axis, prims, rhs);
   a.accumulate = accumulate ? 1 : 0;
   int rc = dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
@@ -1691,11 +1710,19 @@ extern "C" int jxf_sweep_range(jxf_handle h, int axis, int lo, int hi, const dou
       return fail(JXF_ERR_UNSUPPORTED, "jxf_sweep_range: partial ranges are not supported along the contiguous axis");
     return jxf_sweep(h, axis, prims, rhs, accumulate, stream);
   }
+  if (h->cfg.flux_limiter && !h->dt_bound)
+    return fail(JXF_ERR_BAD_ARG, "jxf_sweep_range: the flux limiter needs the time step (jxf_bind_timestep)");
   SweepArgs a = base_args(h, axis, prims, rhs);
   a.accumulate = accumulate ? 1 : 0;
   a.range_lo = lo;
   a.range_hi = hi;
   return dispatch_axis(h, axis, a, 0, (cudaStream_t)stream);
+}
+
+extern "C" int jxf_bind_timestep(jxf_handle h, const double* dt) {
+  if (!h) return fail(JXF_ERR_BAD_ARG, "jxf_bind_timestep: null handle");
+  h->dt_bound = dt;
+  return JXF_OK;
 }
 
 extern "C" int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, void* stream) {
@@ -1791,6 +1818,7 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
     const int axis = h->order[k];
     const bool last = (k == h->n_active - 1);
     SweepArgs a = base_args(h, axis, prims_in, rhs_scratch);
+    a.fl.dt = dt_dev;
     int rc;
     if (!last) {
       a.accumulate = k > 0 || diss;

@@ -859,15 +859,85 @@ __device__ __forceinline__ void limit_interpolation(double (&p)[5], const double
   }
 }
 
-// window -> numerical flux at the face (high_order_godunov.py:117-231)
+// Positivity-preserving flux limiter (solvers/positivity/limiter_flux.py:146-330, SINGLE-PHASE, flux_limiter
+// SIMPLE (mode 1) | NASA (mode 2); eps from config/precision.py:55).  Purely per face: with lambda = dt / dx * sigma
+// (sigma = the flux partition of the axis, compute_partition :681-720) the two cells of the face are pseudo-
+// integrated, U_minus = U_{i+1} + 2 lambda (F - Fs_{i+1}), U_plus = U_i - 2 lambda (F - Fs_i) (Fs = 0 for SIMPLE,
+// the cell's physical flux for NASA); if min density < 1e-12 the face takes the first-order flux (WENO1 states =
+// the two cells, HLLC + Einfeldt, :58-99); then the same test on the pressures of the re-integrated states (< 1e-10).
+// Out of line and by value: the hot loops only gain a uniform branch on bits 9-10 of the option word.
+struct FluxLimArgs {
+  const double* dt;     // physical time step size (device scalar; host pointer in the host simulation)
+  double inv_dx;        // 1 / dx of the sweep axis
+  double sigma;         // flux partition: dim (UNIFORM) or sum_a(1/dx_a) / (1/dx_axis) (CELLSIZE)
+};
+struct Vec5 {
+  double v[5];
+};
+__device__ __forceinline__ bool below_eps(double a, double b, double eps) {   // jnp.minimum(a, b) < eps (NaN -> false)
+  return !(a != a || b != b) && (a < eps || b < eps);
+}
+template <int A>
+__device__ JXF_NOINLINE Vec5 flux_limiter_fix(Vec5 Fin, Vec5 cellL, Vec5 cellR, double gamma, double lam2, int mode) {
+  double cL[5], cR[5], Fp[5], F[5], fsL[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, fsR[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int v = 0; v < 5; ++v) F[v] = Fin.v[v];
+  cons_from_prims(cellL.v, gamma, cL);
+  cons_from_prims(cellR.v, gamma, cR);
+  riemann_flux<A, RIEMANN_HLLC>(cellL.v, cellR.v, gamma, Fp, SIG_EINFELDT);
+  if (mode == 2) {
+    physical_flux<A>(cellL.v, cL, fsL);
+    physical_flux<A>(cellR.v, cR, fsR);
+  }
+  // first integration check: density
+  if (below_eps(cR[0] + lam2 * (F[0] - fsR[0]), cL[0] - lam2 * (F[0] - fsL[0]), 1e-12)) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = Fp[v];
+  }
+  // second integration check: pressure of the re-integrated states
+  double um[5], up[5], wm[5], wp[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    um[v] = cR[v] + lam2 * (F[v] - fsR[v]);
+    up[v] = cL[v] - lam2 * (F[v] - fsL[v]);
+  }
+  prims_from_cons(um, gamma, wm);
+  prims_from_cons(up, gamma, wp);
+  const bool sw = below_eps(wm[4], wp[4], 1e-10);
+  Vec5 out;
+#pragma unroll
+  for (int v = 0; v < 5; ++v) out.v[v] = sw ? Fp[v] : F[v];
+  return out;
+}
+template <int A>
+__device__ __forceinline__ void apply_flux_limiter(const double (&w)[5][6], double gamma, double (&F)[5], int opt,
+                                                   const FluxLimArgs& fl) {
+  const int mode = (opt >> 9) & 3;
+  if (mode == 0) return;
+  const double lam2 = 2.0 * (((*fl.dt) * fl.inv_dx) * fl.sigma);
+  Vec5 Fin, cl, cr;
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    Fin.v[v] = F[v];
+    cl.v[v] = w[v][2];
+    cr.v[v] = w[v][3];
+  }
+  const Vec5 out = flux_limiter_fix<A>(Fin, cl, cr, gamma, lam2, mode);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) F[v] = out.v[v];
+}
+
+// window -> numerical flux at the face (high_order_godunov.py:117-231; flux limiter: space_solver.py:532-543)
 template <int A, int RECON, int RIEMANN>
-__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int opt = 0) {
+__device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int opt,
+                                          const FluxLimArgs& fl) {
   const int lim = opt & 15, sig = opt >> 4;
   double pl[5], pr[5];
   reconstruct<A, RECON>(w, gamma, pl, pr);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
+  apply_flux_limiter<A>(w, gamma, F, opt, fl);
 }
 
 #ifdef JXF_REFERENCE_ORDER
@@ -888,14 +958,14 @@ __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], doubl
 }
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&,
-                                                int opt = 0) {
-  face_flux<A, RECON, RIEMANN>(w, gamma, F, opt);
+                                                int opt, const FluxLimArgs& fl) {
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, opt, fl);
 }
 #else
 // marching variant: shares the cell-centred weights of the as-is fields between consecutive faces
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
-                                                ReconCarry<RECON>& cy, int opt = 0) {
+                                                ReconCarry<RECON>& cy, int opt, const FluxLimArgs& fl) {
   const int lim = opt & 15, sig = opt >> 4;
   double pl[5], pr[5];
   reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
@@ -908,6 +978,7 @@ __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double 
 #else
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
 #endif
+  apply_flux_limiter<A>(w, gamma, F, opt, fl);
 }
 #endif
 

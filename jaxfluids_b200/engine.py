@@ -47,6 +47,8 @@ class BlockConfig:
     # conservatives/positivity and WALL boundaries
     is_interpolation_limiter: bool = False
     limit_velocity: bool = False
+    flux_limiter: Optional[str] = None                 # positivity/flux_limiter: SIMPLE | NASA
+    flux_partition: str = "UNIFORM"                    # positivity/flux_partition: UNIFORM | CELLSIZE
     wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> constant (u, v, w)
     dirichlet: Dict[str, Tuple[float, ...]] = field(default_factory=dict)               # face -> constant (rho,u,v,w,p)
     is_volume_force: bool = False
@@ -100,6 +102,11 @@ class BlockConfig:
         c.gas_constant = float(self.gas_constant)
         c.interpolation_limiter = int(bool(self.is_interpolation_limiter))
         c.limit_velocity = int(bool(self.limit_velocity))
+        if self.flux_limiter not in _lib.FLUX_LIMITER or self.flux_partition not in _lib.FLUX_PARTITION:
+            raise NotImplementedError(f"positivity flux_limiter={self.flux_limiter!r} / flux_partition="
+                                      f"{self.flux_partition!r} is not implemented on the B200 path")
+        c.flux_limiter = _lib.FLUX_LIMITER[self.flux_limiter]
+        c.flux_partition = _lib.FLUX_PARTITION[self.flux_partition]
         for k, f in enumerate(FACES):
             uvw = self.wall_velocity.get(f, (0.0, 0.0, 0.0))
             for q in range(3):
@@ -181,6 +188,12 @@ class BlockSolver:
         rhs = self.new_rhs() if rhs is None else rhs
         _lib.check(self.lib.jxf_compute_rhs(self._h, _ptr(prims), _ptr(rhs), _stream()))
         return rhs
+
+    def bind_timestep(self, dt_dev: Optional[torch.Tensor]):
+        """Device scalar with the physical time step size that compute_rhs / sweep / sweep_range hand to the positivity
+        flux limiter (the physical_timestep_size argument of SpaceSolver.compute_rhs, space_solver.py:151-164)."""
+        self._dt_bound = dt_dev            # keep the tensor alive: the library stores the pointer only
+        _lib.check(self.lib.jxf_bind_timestep(self._h, _ptr(dt_dev)))
 
     def sweep(self, axis: int, prims, rhs, accumulate: bool):
         _lib.check(self.lib.jxf_sweep(self._h, int(axis), _ptr(prims), _ptr(rhs), int(bool(accumulate)), _stream()))
@@ -295,6 +308,8 @@ class BlockState:
         self.info = s.new_scalars(3)
         self.time = s.new_scalars(1, time)
         self.dt = s.new_scalars(1, 0.0)
+        if s.cfg.flux_limiter:              # sweeps issued outside jxf_stage (overlap pieces, compute_rhs) read this dt
+            s.bind_timestep(self.dt)
         if dt is None:
             self.update_dt()
         else:

@@ -96,9 +96,11 @@ class DissipativeFluxesSetup(NamedTuple):
 
 
 class PositivitySetup(NamedTuple):
-    """read_positivity.py: the interpolation limiter is what this path implements."""
+    """read_positivity.py: the interpolation limiter and the SIMPLE / NASA flux limiters are what this path implements."""
     is_interpolation_limiter: bool = False
     limit_velocity: bool = False
+    flux_limiter: Optional[str] = None
+    flux_partition: str = "UNIFORM"
 
 
 class ConservativesSetup(NamedTuple):
@@ -284,13 +286,22 @@ class InputManager:
             if k.startswith("is_") and v and k != "is_interpolation_limiter":
                 raise NotImplementedError(f"conservatives/positivity/{k} is not implemented on the B200 path "
                                           "(implemented: is_interpolation_limiter)")
-        if pos_d.get("flux_limiter") not in (None, False):
-            raise NotImplementedError(f"conservatives/positivity/flux_limiter = '{pos_d['flux_limiter']}' is not "
-                                      "implemented on the B200 path (implemented: is_interpolation_limiter)")
+        # read_positivity.py:20-30 (flux_limiter: one of TUPLE_POSITIVITY_FIXES or absent / false)
+        flux_limiter = pos_d.get("flux_limiter", False)
+        if flux_limiter not in (None, False):
+            flux_limiter = R.select(flux_limiter, R.REFERENCE_POSITIVITY_FIXES, R.TUPLE_POSITIVITY_FIXES,
+                                    "conservatives/positivity/flux_limiter")
+        else:
+            flux_limiter = None
+        flux_partition = R.select(get_setup_value(pos_d, "flux_partition", "conservatives/positivity/flux_partition",
+                                                  str, True, "UNIFORM"),
+                                  R.REFERENCE_POSITIVITY_PARTITIONS, R.TUPLE_POSITIVITY_PARTITIONS,
+                                  "conservatives/positivity/flux_partition")
         positivity = PositivitySetup(
             bool(get_setup_value(pos_d, "is_interpolation_limiter", "conservatives/positivity/is_interpolation_limiter",
                                  bool, True, False)),
-            bool(get_setup_value(pos_d, "limit_velocity", "conservatives/positivity/limit_velocity", bool, True, False)))
+            bool(get_setup_value(pos_d, "limit_velocity", "conservatives/positivity/limit_velocity", bool, True, False)),
+            flux_limiter, flux_partition)
 
         ap_d = get_setup_value(d, "active_physics", "active_physics", dict, False)
         ap = {}

@@ -14,6 +14,8 @@ REFERENCE_RIEMANN_SOLVERS = ("LAX-FRIEDRICHS", "HLL", "HLLC", "HLLC_SIMPLEALPHA"
 REFERENCE_SIGNAL_SPEEDS = ("ARITHMETIC", "RUSANOV", "DAVIS", "DAVIS2", "EINFELDT", "TORO")
 REFERENCE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE")
 REFERENCE_FROZEN_STATES = ("ARITHMETIC", "ROE")
+REFERENCE_POSITIVITY_FIXES = ("SIMPLE", "NASA", "HAS")               # solvers/positivity/__init__.py:1-3
+REFERENCE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE", "WAVESPEED")   # :5-7
 REFERENCE_RECONSTRUCTION_STENCILS = (
     "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER", "KOREN-ADAP", "MC-ADAP", "MINMOD-ADAP",
     "SUPERBEE-ADAP", "VANALBADA-ADAP", "VANLEER-ADAP", "MINMOD-AD", "MINMOD-AD-ADAP", "TENO5", "TENO5-A",
@@ -41,6 +43,8 @@ DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt", "ARITHMETIC": "signal
 DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS"}
 TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
 TUPLE_FROZEN_STATE = ("ARITHMETIC",)
+TUPLE_POSITIVITY_FIXES = ("SIMPLE", "NASA")          # HAS is marked "TODO NEEDS UPDATE" upstream (limiter_flux.py:211)
+TUPLE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE")   # WAVESPEED needs a global max per axis before every sweep
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
 DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}

@@ -73,6 +73,8 @@ class BlockRuntime:
             gas_constant=case.material_setup.specific_gas_constant,
             is_interpolation_limiter=num.conservatives.positivity.is_interpolation_limiter,
             limit_velocity=num.conservatives.positivity.limit_velocity,
+            flux_limiter=num.conservatives.positivity.flux_limiter,
+            flux_partition=num.conservatives.positivity.flux_partition,
             wall_velocity=dict(case.wall_velocity_setup),
             dirichlet=dict(case.dirichlet_setup),
             is_volume_force=num.active_physics.is_volume_force,

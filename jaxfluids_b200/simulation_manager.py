@@ -10,6 +10,7 @@ log line, as the reference's host loop does (simulation_manager.py:325-397).
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import time as _time
 from typing import Dict, List, Optional, Tuple
@@ -55,14 +56,36 @@ class SpaceSolver:
                     interface_velocity=None, interface_pressure=None, solid_velocity=None, solid_temperature=None,
                     interface_cells=None, forcing_buffers=None, ml_setup=None, is_feed_forward=False
                     ) -> Tuple[IntegrationBuffers, PositivityCounter, DiscretizationCounter]:
-        rhs = self._rt.solver.compute_rhs(primitives)
+        with self._timestep(physical_timestep_size):
+            rhs = self._rt.solver.compute_rhs(primitives)
         return (IntegrationBuffers(EulerIntegrationBuffers(rhs, None, None, None)), PositivityCounter(),
                 DiscretizationCounter())
 
-    def compute_rhs_xi(self, conservatives, primitives, temperature, axis, *args, **kwargs):
+    def compute_rhs_xi(self, conservatives, primitives, temperature, axis, physical_simulation_time=0.0,
+                       physical_timestep_size=0.0, *args, **kwargs):
         rhs = self._rt.solver.new_rhs()
-        self._rt.solver.sweep(axis, primitives, rhs, accumulate=False)
+        with self._timestep(physical_timestep_size):
+            self._rt.solver.sweep(axis, primitives, rhs, accumulate=False)
         return EulerIntegrationBuffers(rhs, None, None, None), PositivityCounter(), DiscretizationCounter()
+
+    @contextlib.contextmanager
+    def _timestep(self, physical_timestep_size):
+        """The positivity flux limiter scales with the physical time step size (space_solver.py:532-543): bind the
+        caller's value for the duration of the call, then the stepper's own device scalar again."""
+        solver = self._rt.solver
+        if not solver.cfg.flux_limiter:
+            yield
+            return
+        if torch.is_tensor(physical_timestep_size):
+            dt = physical_timestep_size.to(device=solver.device, dtype=torch.float64).reshape(1).contiguous()
+        else:
+            dt = solver.new_scalars(1, float(physical_timestep_size))
+        previous = getattr(solver, "_dt_bound", None)
+        solver.bind_timestep(dt)
+        try:
+            yield
+        finally:
+            solver.bind_timestep(previous)     # (the scratch scalar is freed stream-ordered, after the sweeps read it)
 
 
 class TimeIntegrator:

@@ -68,6 +68,8 @@ class Setup:
     # conservatives/positivity (limiter_interpolation.py) and WALL boundaries (halos/outer/material.py:473-520)
     is_interpolation_limiter: bool = False
     limit_velocity: bool = False
+    flux_limiter: str | None = None              # positivity/flux_limiter: SIMPLE | NASA (limiter_flux.py)
+    flux_partition: str = "UNIFORM"              # positivity/flux_partition: UNIFORM | CELLSIZE
     wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> (u, v, w), constants
     dirichlet: Dict[str, Tuple[float, float, float, float, float]] = field(default_factory=dict)  # face -> constant prims
     # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
@@ -637,22 +639,74 @@ def heat_flux_axis(prims, T, axis, s: Setup):
 # --------------------------------------------------------------------------
 # right-hand side
 # --------------------------------------------------------------------------
-def face_flux(prims, axis, s: Setup):
-    """high_order_godunov.py:117-231: face fluxes (5, N_axis+1, transverse interior)."""
+def flux_limiter(F, prims, cons, dt, axis, s: Setup):
+    """limiter_flux.py:146-330 (SINGLE-PHASE, flux_limiter SIMPLE | NASA): a face whose high-order flux would drive
+    the density (first check) or then the pressure (second check) of one of its two cells below eps under the
+    pseudo-integration U -/+ 2 lambda F falls back to the first-order HLLC / Einfeldt flux (binary switch)."""
+    eps_density, eps_pressure = 1e-12, 1e-10                            # config/precision.py:55
+    nh, n = s.nh, s.cells[axis]
+
+    def cells(buf, lo):                                                 # cons_positivity_slices, :134-138
+        sl = [slice(None)] + list(s.interior)
+        sl[1 + axis] = slice(lo, lo + n + 1)
+        return buf[tuple(sl)]
+
+    if s.flux_partition == "UNIFORM":                                   # compute_partition, :681-720
+        one_sigma = len(s.active)
+    elif s.flux_partition == "CELLSIZE":
+        one_sigma = sum(s.inv_dx[a] for a in s.active) / s.inv_dx[axis]
+    else:
+        raise NotImplementedError(s.flux_partition)
+    lam = dt * s.inv_dx[axis] * one_sigma                               # :205
+    # first-order flux: WENO1 in PRIMITIVE variables + HLLC + Einfeldt (:58-99)
+    pL, pR = cells(prims, nh - 1), cells(prims, nh)
+    F_pos = hllc(pL, pR, cons_from_prims(pL, s.gamma), cons_from_prims(pR, s.gamma), axis, s.gamma, "EINFELDT")
+    c_plus, c_minus = cells(cons, nh - 1), cells(cons, nh)              # cell i (+), cell i+1 (-)
+    if s.flux_limiter == "NASA":
+        fs = physical_flux(prims, cons, axis)                           # equation_manager.get_fluxes_xi
+        fs_plus, fs_minus = cells(fs, nh - 1), cells(fs, nh)
+
+    def integrate(F):                                                   # integrate_positivity, :471-560
+        if s.flux_limiter == "SIMPLE":
+            return c_minus + 2.0 * lam * F, c_plus - 2.0 * lam * F
+        if s.flux_limiter == "NASA":
+            return c_minus + 2.0 * lam * (F - fs_minus), c_plus - 2.0 * lam * (F - fs_plus)
+        raise NotImplementedError(s.flux_limiter)
+
+    U_minus, U_plus = integrate(F)
+    theta = np.where(np.minimum(U_minus[0], U_plus[0]) < eps_density, 1, 0)            # :571-575
+    F = theta * F_pos + (1 - theta) * F                                                # :766
+    U_minus, U_plus = integrate(F)
+    W_minus, W_plus = prims_from_cons(U_minus, s.gamma), prims_from_cons(U_plus, s.gamma)
+    theta = np.where(np.minimum(W_minus[4] + 0.0, W_plus[4] + 0.0) < eps_pressure, 1, 0)   # :620-628 (pb = 0)
+    return theta * F_pos + (1 - theta) * F
+
+
+def face_flux(prims, axis, s: Setup, cons=None, dt=None):
+    """high_order_godunov.py:117-231: face fluxes (5, N_axis+1, transverse interior); with positivity/flux_limiter
+    the positivity-preserving switch of space_solver.py:532-543 follows."""
     pl, pr, cl, cr = reconstruct(prims, axis, s)
     if s.riemann == "HLLC":
-        return hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
-    if s.riemann == "RUSANOV":
-        return rusanov(pl, pr, cl, cr, axis, s.gamma)
-    if s.riemann == "HLL":
-        return hll(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
-    raise NotImplementedError(s.riemann)
+        F = hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
+    elif s.riemann == "RUSANOV":
+        F = rusanov(pl, pr, cl, cr, axis, s.gamma)
+    elif s.riemann == "HLL":
+        F = hll(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
+    else:
+        raise NotImplementedError(s.riemann)
+    if s.flux_limiter:
+        if dt is None:
+            raise ValueError("positivity/flux_limiter needs the physical time step size")
+        cons = cons_from_prims(prims, s.gamma) if cons is None else cons
+        with np.errstate(all="ignore"):
+            F = flux_limiter(F, prims, cons, dt, axis, s)
+    return F
 
 
-def rhs_axis(prims, axis, s: Setup):
+def rhs_axis(prims, axis, s: Setup, cons=None, dt=None):
     """space_solver.py:456-674 (convective branch: :489, :517-543, :597-599)."""
     if s.is_convective_flux:
-        fc = face_flux(prims, axis, s)
+        fc = face_flux(prims, axis, s, cons, dt)
         f = np.zeros_like(fc) + fc                                      # :517, :545
     else:
         f = np.zeros((5,) + _flux_shape(axis, s))                       # :517 only
@@ -684,12 +738,12 @@ def gravity_forces(cons, s: Setup):
     return np.concatenate([mom, ene], axis=0)
 
 
-def compute_rhs(prims, s: Setup, cons=None):
+def compute_rhs(prims, s: Setup, cons=None, dt=None):
     """space_solver.py:151-453 (single phase): 0.0 + rhs_x + rhs_y + rhs_z (+ volume forces, :378-384, which
     read the conservatives)."""
     rhs = 0.0
     for axis in s.active:
-        rhs = rhs + rhs_axis(prims, axis, s)
+        rhs = rhs + rhs_axis(prims, axis, s, cons, dt)
     if s.is_volume_force:
         cons = cons_from_prims(prims, s.gamma) if cons is None else cons
         rhs = rhs.copy()
@@ -752,7 +806,7 @@ def stage(prims, cons, cons_n, dt, k, s: Setup):
     """One RK stage: simulation_manager.py:770-1047 (single-phase branch).
     Returns (prims, cons, rhs)."""
     rk = RK[s.integrator]
-    rhs = compute_rhs(prims, s, cons)                                   # :796
+    rhs = compute_rhs(prims, s, cons, dt)                               # :796 (dt: the flux limiter's lambda)
     if k > 0:                                                           # RK3.py:49-50
         a, b = rk["blend"][k - 1]
         cons = a * cons + b * cons_n

@@ -51,6 +51,13 @@ FIXTURES = {
     "sod100_char_hll_rk3": ("sod", dict(cells=(100, None, None), riemann="HLL"), 10, (10,)),
     "riemann2d_20x24_prim_hll_davis_rk3": ("riemann2d", dict(cells=(20, 24, None), recon="PRIMITIVE", riemann="HLL",
                                                                signal_speed="DAVIS"), 3, (3,)),
+    # the shipped double-rarefaction example, shrunk: flux limiter SIMPLE + interpolation limiter, WENO5-JS, nh 4
+    "rarefaction100_fluxlim_simple_rk3": ("rarefaction", dict(cells=(100, None, None)), 30, (30,)),
+    # ... and a stronger one (Mach 9.4 apart): ~500 face fluxes replaced over the 40 steps
+    "rarefaction100_strong_fluxlim_simple_rk3": ("rarefaction", dict(cells=(100, None, None), initial_condition={
+        "u": "lambda x: -2.5*(x <= 0.5) + 2.5*(x > 0.5)", "p": 0.05}), 40, (40,)),
+    "riemann2d_16x20_fluxlim_nasa_cellsize_rk3": ("riemann2d", dict(cells=(16, 20, None), positivity={
+        "flux_limiter": "NASA", "flux_partition": "CELLSIZE"}), 3, (3,)),
     # the shipped lid-driven cavity example, shrunk: WALL on four faces (moving lid), WENO5-JS PRIMITIVE, viscous,
     # interpolation limiter on, halo_cells 4
     "cavity_24x20_wall_js_visc_rk3": ("cavity", dict(cells=(24, 20, None)), 5, (5,)),
@@ -82,6 +89,31 @@ def make_limiter_fixture():
     path = os.path.join(OUT, "special", "limiter_riemann2d_20x24.npz")
     np.savez_compressed(path, **d)
     print(f"special/limiter_riemann2d_20x24: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def make_flux_limiter_fixture():
+    """rhs of a near-vacuum, fast-moving state on which the positivity flux limiter (limiter_flux.py:146-330) replaces
+    hundreds of face fluxes by the first-order flux -- per variant (SIMPLE / NASA, UNIFORM / CELLSIZE partition)."""
+    d = {}
+    x, y = np.meshgrid(np.linspace(0, 1, 20), np.linspace(0, 1, 24), indexing="ij")
+    rho = np.where(x < 0.5, 1.0 + 0.1 * np.sin(7 * y), 2e-3 * (1 + 0.5 * np.sin(9 * y + 3 * x)))
+    p = np.where(y < 0.5, 1.0 + 0.2 * np.cos(5 * x), 1e-3 * (1 + 0.5 * np.cos(11 * x + y)))
+    user = np.stack([rho, 3.0 * np.sin(3 * x + 2 * y), 2.0 * np.cos(4 * y - x), p])[..., None]
+    d["user"] = user
+    for tag, pos in (("simple", {"flux_limiter": "SIMPLE"}), ("nasa", {"flux_limiter": "NASA"}),
+                     ("simple_cellsize", {"flux_limiter": "SIMPLE", "flux_partition": "CELLSIZE"}),
+                     ("nasa_interp", {"flux_limiter": "NASA", "is_interpolation_limiter": True})):
+        case, num = rr.customize(*rr.load_case("riemann2d"), cells=(20, 24, None), positivity=pos)
+        case["domain"]["y"]["range"] = [0.0, 1.7]                # dx != dy: the partitions differ
+        run = rr.ReferenceRun(case, num, user_prime_init=user)
+        d[f"case_json_{tag}"], d[f"num_json_{tag}"] = np.array(json.dumps(case)), np.array(json.dumps(num))
+        d[f"prims_halo_{tag}"], d[f"cons_halo_{tag}"] = run.primitives, run.conservatives
+        # a time step 6x the CFL one makes the pseudo-integration overshoot on many faces
+        d[f"dt_{tag}"] = np.float64(6.0 * run.dt)
+        d[f"rhs_{tag}"] = run.compute_rhs(dt=6.0 * run.dt)
+    path = os.path.join(OUT, "special", "flux_limiter_riemann2d_20x24.npz")
+    np.savez_compressed(path, **d)
+    print(f"special/flux_limiter_riemann2d_20x24: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
 def make(name, case_name, kw, nsteps, snaps):
@@ -135,3 +167,6 @@ if __name__ == "__main__":
     if not only or "limiter" in only:
         with np.errstate(all="ignore"):
             make_limiter_fixture()
+    if not only or "flux_limiter" in only:
+        with np.errstate(all="ignore"):
+            make_flux_limiter_fixture()

@@ -49,6 +49,7 @@ CASES = {
     "cavity": ("examples_2D/03_lid_driven_cavity", "lid_driven_cavity.json"),   # WALL x4, WENO5-JS, viscous, limiter, nh 4
     "rti": ("examples_2D/04_rayleigh_taylor_instability", "rti.json"),           # DIRICHLET N/S, gravity, limiter
     "heat1d": ("examples_1D/08_heat_equation", "heat_equation.json"),            # heat flux only (no convective flux)
+    "rarefaction": ("examples_1D/04_double_rarefaction", "double_rarefaction.json"),  # flux limiter SIMPLE + interp. limiter
 }
 
 
@@ -63,7 +64,7 @@ def load_case(name: str):
 
 
 def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None,
-              signal_speed=None):
+              signal_speed=None, positivity=None, initial_condition=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -84,6 +85,10 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         g["signal_speed"] = signal_speed
     if integrator is not None:
         num["conservatives"]["time_integration"]["integrator"] = integrator
+    if positivity is not None:
+        num["conservatives"]["positivity"] = dict(positivity)
+    if initial_condition is not None:
+        case["initial_condition"].update(initial_condition)
     # keep the reference from writing anything / printing the banner
     num.setdefault("output", {})
     num["output"].setdefault("logging", {})
@@ -165,13 +170,14 @@ class ReferenceRun:
         from jaxfluids.data_types.ml_buffers import CallablesSetup, ParametersSetup, combine_callables_and_params
         return combine_callables_and_params(CallablesSetup(), ParametersSetup())
 
-    def compute_rhs(self, prims=None, cons=None):
-        """One SpaceSolver.compute_rhs evaluation on the current (or given) state."""
+    def compute_rhs(self, prims=None, cons=None, dt=None):
+        """One SpaceSolver.compute_rhs evaluation on the current (or given) state (dt: the physical time step
+        size handed to the positivity flux limiter; default: the current one)."""
         mf = self.material_fields
         prims = mf.primitives if prims is None else prims
         cons = mf.conservatives if cons is None else cons
         save, self._cur = self._cur, None
-        out = self.sim.space_solver.compute_rhs(cons, prims, mf.temperature, 0.0, self.dt,
+        out = self.sim.space_solver.compute_rhs(cons, prims, mf.temperature, 0.0, self.dt if dt is None else dt,
                                                 ml_setup=self.default_ml_setup())
         self._cur = save
         return self.np.array(out[0].euler_buffers.conservatives)

@@ -23,7 +23,8 @@ def load(fma=True, reference_order=False):
                        ["-o", so, SRC], check=True)
     lib = C.CDLL(so)
     lib.face_flux_host.restype = C.c_int
-    lib.face_flux_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_int]
+    lib.face_flux_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_int,
+                                   C.c_double, C.c_double, C.c_double]
     return lib
 
 
@@ -31,17 +32,28 @@ def _opt(s):
     """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4."""
     lim = (2 if s.limit_velocity else 1) if s.is_interpolation_limiter else 0
     sig = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}[s.signal_speed]
-    return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8)
+    fl = {None: 0, "SIMPLE": 1, "NASA": 2}[s.flux_limiter]
+    return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9)
 
 
-def rhs_axis_march(prims, axis, s, fma=True):
+def _flux_limiter_args(s, axis, dt):
+    """(dt, 1/dx, sigma) of numerics.cuh FluxLimArgs, as base_args (jxf_b200.cu) fills them."""
+    sigma = float(len(s.active))
+    if s.flux_partition == "CELLSIZE":
+        sigma = sum(s.inv_dx[a] for a in s.active) / s.inv_dx[axis]
+    if s.flux_limiter and dt is None:
+        raise ValueError("flux limiter: dt required")
+    return float(dt or 0.0), float(s.inv_dx[axis]), sigma
+
+
+def rhs_axis_march(prims, axis, s, fma=True, dt=None):
     """rhs_axis through the MARCHING variant of the device functions (weights of the as-is fields carried
     from face to face along the sweep axis, as sweep_strided does)."""
     from oracle import port
     lib = load(fma, False)
     lib.face_flux_march_host.restype = C.c_int
     lib.face_flux_march_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_void_p,
-                                         C.c_int]
+                                         C.c_int, C.c_double, C.c_double, C.c_double]
     w = np.stack(port._window(prims, axis, s), axis=-1)          # (5, X, Y, Z faces..., 6)
     w = np.moveaxis(w, 0, -2)                                    # (fx, fy, fz, 5, 6)
     w = np.moveaxis(w, axis, 2)                                  # sweep axis last of the three -> sequences
@@ -49,7 +61,8 @@ def rhs_axis_march(prims, axis, s, fma=True):
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
     rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
-                                  w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s))
+                                  w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s),
+                                  *_flux_limiter_args(s, axis, dt))
     assert rc == 0
     f = out.reshape(shp + (5,))
     f = np.moveaxis(f, 2, axis)                                  # back to (fx, fy, fz, 5)
@@ -61,7 +74,7 @@ def rhs_axis_march(prims, axis, s, fma=True):
     return s.inv_dx[axis] * (f[tuple(lo)] - f[tuple(hi)])
 
 
-def rhs_axis(prims, axis, s, fma=True, reference_order=False):
+def rhs_axis(prims, axis, s, fma=True, reference_order=False, dt=None):
     """Same contract as oracle.port.rhs_axis, computed with the device functions on the host."""
     from oracle import port
     lib = load(fma, reference_order)
@@ -71,7 +84,8 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False):
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
     rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
-                            w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s))
+                            w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s),
+                            *_flux_limiter_args(s, axis, dt))
     assert rc == 0
     f = np.moveaxis(out.reshape(shp + (5,)), -1, 0)
     lo = [slice(None)] * 4

@@ -11,11 +11,11 @@ using std::fabs; using std::fmin; using std::fmax; using std::sqrt; using std::f
 using namespace jxf;
 
 template <int A, int RECON, int RIEMANN>
-static void run(const double* win, long n, double gamma, double* out, int opt) {
+static void run(const double* win, long n, double gamma, double* out, int opt, const FluxLimArgs& fl) {
   for (long i = 0; i < n; ++i) {
     double w[5][6], F[5];
     for (int v = 0; v < 5; ++v) for (int k = 0; k < 6; ++k) w[v][k] = win[(i * 5 + v) * 6 + k];
-    face_flux<A, RECON, RIEMANN>(w, gamma, F, opt);
+    face_flux<A, RECON, RIEMANN>(w, gamma, F, opt, fl);
     for (int v = 0; v < 5; ++v) out[i * 5 + v] = F[v];
   }
 }
@@ -23,7 +23,8 @@ static void run(const double* win, long n, double gamma, double* out, int opt) {
 // marching variant: `nseq` sequences of `len` consecutive faces each (windows laid out (nseq, len, 5, 6));
 // the carry is primed from the first window of each sequence, exactly as sweep_strided does
 template <int A, int RECON, int RIEMANN>
-static void run_march(const double* win, long nseq, long len, double gamma, double* out, int opt) {
+static void run_march(const double* win, long nseq, long len, double gamma, double* out, int opt,
+                      const FluxLimArgs& fl) {
   for (long s = 0; s < nseq; ++s) {
     ReconCarry<RECON> cy;
     for (long i = 0; i < len; ++i) {
@@ -31,15 +32,16 @@ static void run_march(const double* win, long nseq, long len, double gamma, doub
       const double* p = win + ((s * len + i) * 5) * 6;
       for (int v = 0; v < 5; ++v) for (int k = 0; k < 6; ++k) w[v][k] = p[v * 6 + k];
       if (i == 0) recon_carry_init<A, RECON>(w, cy);
-      face_flux_carry<A, RECON, RIEMANN>(w, gamma, F, cy, opt);
+      face_flux_carry<A, RECON, RIEMANN>(w, gamma, F, cy, opt, fl);
       for (int v = 0; v < 5; ++v) out[(s * len + i) * 5 + v] = F[v];
     }
   }
 }
 
 extern "C" int face_flux_march_host(int axis, int recon, int riemann, const double* win, long nseq, long len, double gamma,
-                                    double* out, int opt) {
-#define MCASE(A, R, S) if (axis == A && recon == R && riemann == S) { run_march<A, R, S>(win, nseq, len, gamma, out, opt); return 0; }
+                                    double* out, int opt, double dt, double inv_dx, double sigma) {
+  const FluxLimArgs fl = {&dt, inv_dx, sigma};
+#define MCASE(A, R, S) if (axis == A && recon == R && riemann == S) { run_march<A, R, S>(win, nseq, len, gamma, out, opt, fl); return 0; }
   MCASE(0,0,0) MCASE(0,0,1) MCASE(0,1,0) MCASE(0,1,1) MCASE(0,2,0) MCASE(0,2,1) MCASE(0,3,0) MCASE(0,3,1)
   MCASE(1,0,0) MCASE(1,0,1) MCASE(1,1,0) MCASE(1,1,1) MCASE(1,2,0) MCASE(1,2,1) MCASE(1,3,0) MCASE(1,3,1)
   MCASE(2,0,0) MCASE(2,0,1) MCASE(2,1,0) MCASE(2,1,1) MCASE(2,2,0) MCASE(2,2,1) MCASE(2,3,0) MCASE(2,3,1)
@@ -47,8 +49,10 @@ extern "C" int face_flux_march_host(int axis, int recon, int riemann, const doub
 }
 
 // windows: (n, 5, 6) doubles; out: (n, 5)
-extern "C" int face_flux_host(int axis, int recon, int riemann, const double* win, long n, double gamma, double* out, int opt) {
-#define CASE(A, R, S) if (axis == A && recon == R && riemann == S) { run<A, R, S>(win, n, gamma, out, opt); return 0; }
+extern "C" int face_flux_host(int axis, int recon, int riemann, const double* win, long n, double gamma, double* out, int opt,
+                              double dt, double inv_dx, double sigma) {
+  const FluxLimArgs fl = {&dt, inv_dx, sigma};
+#define CASE(A, R, S) if (axis == A && recon == R && riemann == S) { run<A, R, S>(win, n, gamma, out, opt, fl); return 0; }
   CASE(0,0,0) CASE(0,0,1) CASE(0,1,0) CASE(0,1,1) CASE(0,2,0) CASE(0,2,1) CASE(0,3,0) CASE(0,3,1)
   CASE(1,0,0) CASE(1,0,1) CASE(1,1,0) CASE(1,1,1) CASE(1,2,0) CASE(1,2,1) CASE(1,3,0) CASE(1,3,1)
   CASE(2,0,0) CASE(2,0,1) CASE(2,1,0) CASE(2,1,1) CASE(2,2,0) CASE(2,2,1) CASE(2,3,0) CASE(2,3,1)

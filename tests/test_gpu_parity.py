@@ -4,6 +4,8 @@
 Tolerances are the north-star's: per-stage RHS rel L-inf <= 1e-12, primitives after 100 steps
 <= 1e-9, conserved totals <= 1e-12.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -25,7 +27,8 @@ def make_solver(s: port.Setup, bc=None):
                       bulk_viscosity=s.bulk_viscosity, thermal_conductivity_model=s.thermal_conductivity_model,
                       thermal_conductivity=s.thermal_conductivity, prandtl_number=s.prandtl_number,
                       gas_constant=s.gas_constant, is_interpolation_limiter=s.is_interpolation_limiter,
-                      limit_velocity=s.limit_velocity, wall_velocity=dict(s.wall_velocity),
+                      limit_velocity=s.limit_velocity, flux_limiter=s.flux_limiter, flux_partition=s.flux_partition,
+                      wall_velocity=dict(s.wall_velocity),
                       dirichlet=dict(s.dirichlet), is_volume_force=s.is_volume_force, gravity=tuple(s.gravity),
                       is_convective_flux=s.is_convective_flux)
     return BlockSolver(cfg)
@@ -74,6 +77,8 @@ def test_reference_fixture_rhs_and_stages(name):
     sol = make_solver(s)
     p0 = dev(g["prims0_halo"])
     scales = H.rhs_scales(g["prims0_halo"], s)
+    if s.flux_limiter:          # the fixture's rhs were taken with the step's physical time step size
+        sol.bind_timestep(dev(np.array([float(g["dt0"])])))
     for a in s.active:
         rhs = sol.new_rhs()
         sol.sweep(a, p0, rhs, accumulate=False)
@@ -760,3 +765,77 @@ def test_hll_riemann_solver(cells, bc, recon, sig):
         st.step()
     m = H.defined_mask(s)
     assert H.rel_linf(host(st.primitives)[:, m], prims[:, m]) <= 1e-12
+
+
+@pytest.mark.parametrize("tag", ["simple", "nasa", "simple_cellsize", "nasa_interp"])
+def test_flux_limiter_fixture_rhs(tag):
+    """positivity/flux_limiter SIMPLE | NASA (limiter_flux.py:146-330) on the reference's fixture where hundreds of
+    faces fall back to the first-order flux (a face switched differently would be an O(1) error): per-axis sweeps,
+    compute_rhs, and the public SpaceSolver.compute_rhs with physical_timestep_size."""
+    import copy, json
+    g = np.load(os.path.join(H.GOLDEN, "special", "flux_limiter_riemann2d_20x24.npz"))
+    s = H.setup_from_json(json.loads(str(g[f"case_json_{tag}"])), json.loads(str(g[f"num_json_{tag}"])))
+    prims, cons, dt = g[f"prims_halo_{tag}"], g[f"cons_halo_{tag}"], float(g[f"dt_{tag}"])
+    sol = make_solver(s)
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    scales = H.rhs_scales(prims, s)
+    with pytest.raises(Exception):                      # no time step bound yet: must fail loudly, not guess
+        sol.sweep(s.active[0], p, sol.new_rhs(), accumulate=False)
+    sol.bind_timestep(dev(np.array([dt])))
+    with np.errstate(all="ignore"):
+        for a in s.active:
+            rhs = sol.new_rhs()
+            sol.sweep(a, p, rhs, accumulate=False)
+            assert H.rel_linf(host(rhs), port.rhs_axis(prims, a, s, cons, dt), scale=scales) <= H.TOL_RHS, f"axis {a}"
+    got = host(sol.compute_rhs(p))
+    assert H.rel_linf(got, g[f"rhs_{tag}"], scale=scales) <= H.TOL_RHS
+    # and the limiter matters on this state
+    s0 = copy.copy(s)
+    s0.flux_limiter = None
+    assert H.rel_linf(host(make_solver(s0).compute_rhs(p)), g[f"rhs_{tag}"], scale=scales) > 1e-3
+    # a different time step switches a different set of faces
+    sol.bind_timestep(dev(np.array([0.5 * dt])))
+    with np.errstate(all="ignore"):
+        ref_half = port.compute_rhs(prims, s, cons, 0.5 * dt)
+    assert H.rel_linf(host(sol.compute_rhs(p)), ref_half, scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("force_rows", [False, True])
+def test_flux_limiter_3d_all_kernels(force_rows, monkeypatch):
+    """The limiter through every sweep kernel (march x / y, rows or contig z, fused epilogue) on a 3-D near-vacuum
+    state: one stage rhs and 2 steps against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    if force_rows:
+        monkeypatch.setenv("JXF_FORCE_ROWS", "1")
+    s = H.make_setup((20, 18, 40), bc="PERIODIC", recon="CHAR-PRIMITIVE")
+    s.flux_limiter = "SIMPLE"
+    rng = np.random.default_rng(5)
+    ic = H.smooth_ic(s, seed=9, amp=0.3)
+    x, y, z = s.cell_centers()
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    ic[0] = np.where(np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Z) > 0.3, 4e-3, ic[0])        # near-vacuum pockets
+    ic[1:4] *= 6.0
+    prims, cons = port.initialize(ic, s)
+    dt = 3.0 * port.time_step_size(prims, s)
+    sol = make_solver(s)
+    sol.bind_timestep(dev(np.array([dt])))
+    p = dev(prims)
+    scales = H.rhs_scales(prims, s)
+    import copy
+    s0 = copy.copy(s)
+    s0.flux_limiter = None
+    with np.errstate(all="ignore"):
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s, cons, dt)
+            assert np.abs(ref - port.rhs_axis(prims, a, s0)).max() > 0, "limiter inactive on this axis"
+            rhs = sol.new_rhs()
+            sol.sweep(a, p, rhs, accumulate=False)
+            assert H.rel_linf(host(rhs), ref, scale=scales) <= H.TOL_RHS, f"axis {a}"
+    # fused stages: one step at this (over-CFL) dt, checked where the oracle's result is finite
+    st = BlockState(sol, prims, cons, dt=dt)
+    with np.errstate(all="ignore"):
+        rp, rc, _ = port.step(prims, cons, dt, s)
+    st.step()
+    m = H.defined_mask(s) & np.isfinite(rp).all(axis=0)
+    assert m.sum() > 0.5 * np.prod(s.cells)
+    assert H.rel_linf(host(st.primitives)[:, m], rp[:, m]) <= 1e-11

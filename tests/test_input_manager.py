@@ -75,7 +75,8 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
     (("conservatives", "time_integration", "integrator"), "RK2_LS4"),
     (("active_physics", "is_geometric_source"), True),
-    (("conservatives", "positivity", "flux_limiter"), "SIMPLE"),
+    (("conservatives", "positivity", "flux_limiter"), "HAS"),
+    (("conservatives", "positivity", "flux_partition"), "WAVESPEED"),
     (("conservatives", "positivity", "is_thinc_interpolation_limiter"), True),
     (("precision", "is_double_precision_compute"), False),
 ])

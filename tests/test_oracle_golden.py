@@ -16,7 +16,7 @@ def test_port_reproduces_reference_fixture(name):
     dt = port.time_step_size(prims, s)
     assert dt == float(g["dt0"])
     for a in s.active:
-        assert np.array_equal(port.rhs_axis(prims, a, s), g[f"rhs_axis{a}"])
+        assert np.array_equal(port.rhs_axis(prims, a, s, cons, dt), g[f"rhs_axis{a}"])
     nsteps = len(g["dt"])
     for n in range(1, nsteps + 1):
         rec = {"rhs": [], "prims": [], "cons": []} if n == 1 else None
@@ -80,3 +80,20 @@ def test_interpolation_limiter_fixture(tag):
                       for a, b in zip(port.reconstruct(prims, ax, s0)[:2], port.reconstruct(prims, ax, s)[:2]))
         assert changed > 1000                                  # the limiter really acts on this state
         assert np.array_equal(port.compute_rhs(prims, s), g[f"rhs_{tag}"], equal_nan=True)
+
+
+@pytest.mark.parametrize("tag", ["simple", "nasa", "simple_cellsize", "nasa_interp"])
+def test_flux_limiter_fixture(tag):
+    """positivity/flux_limiter on a state where hundreds of faces fall back to the first-order flux (fixture from the
+    reference, oracle/refharness/make_goldens.py:make_flux_limiter_fixture)."""
+    import copy, json, os
+    g = np.load(os.path.join(H.GOLDEN, "special", "flux_limiter_riemann2d_20x24.npz"))
+    s = H.setup_from_json(json.loads(str(g[f"case_json_{tag}"])), json.loads(str(g[f"num_json_{tag}"])))
+    prims, cons, dt = g[f"prims_halo_{tag}"], g[f"cons_halo_{tag}"], float(g[f"dt_{tag}"])
+    with np.errstate(all="ignore"):
+        assert np.array_equal(port.compute_rhs(prims, s, cons, dt), g[f"rhs_{tag}"])
+        s0 = copy.copy(s)
+        s0.flux_limiter = None
+        switched = sum(int((port.face_flux(prims, a, s, cons, dt) != port.face_flux(prims, a, s0)).any(axis=0).sum())
+                       for a in s.active)
+    assert switched > 80                                   # the limiter really acts on this state
