@@ -809,12 +809,12 @@ def test_flux_limiter_3d_all_kernels(force_rows, monkeypatch):
         monkeypatch.setenv("JXF_FORCE_ROWS", "1")
     s = H.make_setup((20, 18, 40), bc="PERIODIC", recon="CHAR-PRIMITIVE")
     s.flux_limiter = "SIMPLE"
-    rng = np.random.default_rng(5)
+    s.is_interpolation_limiter = True          # keeps the reconstructed states of this state admissible
     ic = H.smooth_ic(s, seed=9, amp=0.3)
     x, y, z = s.cell_centers()
     X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
-    ic[0] = np.where(np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Z) > 0.3, 4e-3, ic[0])        # near-vacuum pockets
-    ic[1:4] *= 6.0
+    ic[0] = np.where(np.sin(2 * np.pi * (X + Y)) * np.cos(2 * np.pi * (Z - Y)) > 0.3, 2e-2, ic[0])   # rarefied pockets
+    ic[1:4] *= 4.0                             # (host-simulated: 45 / 265 / 2141 faces switch on x / y / z)
     prims, cons = port.initialize(ic, s)
     dt = 3.0 * port.time_step_size(prims, s)
     sol = make_solver(s)
