@@ -1,6 +1,7 @@
 """In-tree build of libjxf_b200.so (nvcc, sm_100a only)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -10,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "jxf_b200.cu")]
 DEPS = [os.path.join(HERE, "csrc", "numerics.cuh"), os.path.join(HERE, "csrc", "dissipative.cuh"), os.path.join(os.path.dirname(HERE), "include", "jxf_b200.h")]
 OUT = os.path.join(HERE, "lib", "libjxf_b200.so")
+STAMP = OUT + ".srchash"          # written after a successful build; travels with the .so
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,11 +27,25 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, flags)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in SRC + DEPS:
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
+    """Content-based, not mtime-based: a copy of the tree (the GPU box snapshot, a git checkout, a stash/pop) changes
+    mtimes but must never trigger a multi-minute nvcc run inside a test or a bench."""
     if not os.path.exists(OUT):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(p) <= t for p in SRC + DEPS + [os.path.abspath(__file__)])
+    if not os.path.exists(STAMP):      # a library built before the stamp existed: fall back to modification times
+        t = os.path.getmtime(OUT)
+        return all(os.path.getmtime(p) <= t for p in SRC + DEPS)
+    with open(STAMP) as fh:
+        return fh.read().strip() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -38,7 +54,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     print("[jaxfluids_b200.build]", " ".join(cmd), flush=True)
+    digest = source_hash()             # before the compile: an edit during the build must not be stamped as built
+    if os.path.exists(STAMP):
+        os.remove(STAMP)
     subprocess.run(cmd, check=True)
+    with open(STAMP, "w") as fh:
+        fh.write(digest + "\n")
     return OUT
 
 

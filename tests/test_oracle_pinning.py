@@ -30,6 +30,13 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     # HLL Riemann solver
     ("sod", dict(cells=(64, None, None), riemann="HLL"), 2),
     ("riemann2d", dict(cells=(16, 16, None), riemann="HLL", signal_speed="DAVIS"), 1),
+    # positivity flux limiter (the shipped double-rarefaction example; a stronger one where it fires every step;
+    # NASA / CELLSIZE variants)
+    ("rarefaction", dict(cells=(100, None, None)), 12),
+    ("rarefaction", dict(cells=(80, None, None), initial_condition={
+        "u": "lambda x: -2.5*(x <= 0.5) + 2.5*(x > 0.5)", "p": 0.05}), 12),
+    ("riemann2d", dict(cells=(16, 20, None), positivity={"flux_limiter": "NASA", "flux_partition": "CELLSIZE"}), 2),
+    ("tgv", dict(cells=(8, 10, 12), positivity={"flux_limiter": "SIMPLE", "flux_partition": "CELLSIZE"}), 1),
     # the shipped lid-driven cavity / Rayleigh-Taylor / heat-equation examples (WALL, DIRICHLET, gravity, limiter,
     # WENO5-JS, viscous, heat flux only)
     ("cavity", dict(cells=(16, 14, None)), 2),
