@@ -94,6 +94,8 @@ class BlockRuntime:
         self.info = s.new_scalars(3)
         self.time = s.new_scalars(1, 0.0)
         self.dt = s.new_scalars(1, 0.0)
+        if self.cfg.flux_limiter:           # sweeps issued outside jxf_stage (overlap pieces, compute_rhs) read this dt
+            s.bind_timestep(self.dt)
         self._sign = torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=self.device)
         # With the dissipative fluxes the exchange also carries EDGE halos: faces go axis by axis, each slab widened
         # over the transverse halos that are already complete (ext_mask, see jxf_pack_face_ext)
