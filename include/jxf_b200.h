@@ -32,14 +32,23 @@ typedef enum jxf_status {
 
 /* ref: stencils/__init__.py:15-19 + godunov.reconstruction_variable (read_conservatives.py:126-203) */
 enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
-/* ref: stencils/reconstruction/shock_capturing/weno/weno5_z.py, weno5_js.py (DICT_SPATIAL_RECONSTRUCTION) */
-enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1 };
+/* ref: stencils/reconstruction/shock_capturing/weno/weno5_z.py, weno5_js.py (DICT_SPATIAL_RECONSTRUCTION): the two
+ * tuned forms.  Ids >= 2: the other stencils of the reference that fit the kernels' 6-cell window, evaluated in
+ * the reference's operation order by one generic set of kernel instantiations (weno/weno1_js.py, weno3_js.py,
+ * weno3_z.py, weno3_n.py, teno/teno5.py, teno/teno6.py, weno/weno6_cu.py, muscl/muscl3.py with stencils/limiter.py,
+ * reconstruction/central/central_2.py). */
+enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1, JXF_STENCIL_WENO1 = 2, JXF_STENCIL_WENO3JS = 3,
+       JXF_STENCIL_WENO3Z = 4, JXF_STENCIL_TENO5 = 5, JXF_STENCIL_WENO6CU = 6, JXF_STENCIL_KOREN = 7, JXF_STENCIL_MC = 8,
+       JXF_STENCIL_MINMOD = 9, JXF_STENCIL_SUPERBEE = 10, JXF_STENCIL_VANALBADA = 11, JXF_STENCIL_VANLEER = 12,
+       JXF_STENCIL_WENO3N = 13, JXF_STENCIL_CENTRAL2 = 14, JXF_STENCIL_TENO6 = 15 };
 /* ref: solvers/riemann_solvers/__init__.py:16-34 */
-enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1, JXF_RIEMANN_HLL = 2 /* HLL.py; uses jxf_config.signal_speed */ };
+enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1, JXF_RIEMANN_HLL = 2 /* HLL.py; uses jxf_config.signal_speed */,
+       JXF_RIEMANN_HLLCLM = 3 /* HLLCLM.py (low-Mach HLLC, Fleischmann et al. 2020); uses jxf_config.signal_speed */,
+       JXF_RIEMANN_AUSMP = 4 /* AUSMP.py (AUSM+) */ };
 /* ref: solvers/riemann_solvers/signal_speeds.py (DICT_SIGNAL_SPEEDS); DAVIS2 is marked not working upstream */
 enum { JXF_SIGNAL_EINFELDT = 0, JXF_SIGNAL_ARITHMETIC = 1, JXF_SIGNAL_RUSANOV = 2, JXF_SIGNAL_DAVIS = 3, JXF_SIGNAL_TORO = 4 };
 /* ref: time_integration/__init__.py:6-11 */
-enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2 };
+enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2, JXF_INT_RK2_LS4 = 3 /* RK2_LS4.py: 4 stages */ };
 /* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */
 enum { JXF_BC_INACTIVE = 0, JXF_BC_PERIODIC = 1, JXF_BC_SYMMETRY = 2, JXF_BC_ZEROGRADIENT = 3, JXF_BC_NEIGHBOR = 4,
        JXF_BC_WALL = 5      /* ref: halos/outer/material.py:473-520, constant wall_velocity_callable */,

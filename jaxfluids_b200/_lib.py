@@ -21,12 +21,15 @@ EXPORTS = (
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
-STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1}
+# ids = include/jxf_b200.h JXF_STENCIL_*; >= 2: the generic (reference-order) kernel instantiations
+STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z": 4, "TENO5": 5, "WENO6-CU": 6,
+           "KOREN": 7, "MC": 8, "MINMOD": 9, "SUPERBEE": 10, "VANALBADA": 11, "VANLEER": 12, "WENO3-N": 13,
+           "CENTRAL2": 14, "TENO6": 15}
 FLUX_LIMITER = {None: 0, False: 0, "SIMPLE": 1, "NASA": 2}
 FLUX_PARTITION = {"UNIFORM": 0, "CELLSIZE": 1}
-RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2}
+RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2, "HLLC-LM": 3, "AUSMP": 4}
 SIGNAL = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}
-INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2}
+INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2, "RK2_LS4": 3}
 BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4, "WALL": 5, "DIRICHLET": 6}
 FACES = ("east", "west", "north", "south", "top", "bottom")
 

@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(128) math_debug_kernel(const double* __restric
 // debug / test hook: the per-face device function on caller-supplied windows (n, 5, 6) -> (n, 5)
 template <int A, int RECON, int RIEMANN>
 __global__ void __launch_bounds__(128) face_flux_debug_kernel(const double* __restrict__ win, long long n, double gamma,
-                                                              double* __restrict__ out) {
+                                                              double* __restrict__ out, int opt) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double w[5][6], F[5];
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(128) face_flux_debug_kernel(const double* __re
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[v][k] = win[(i * 5 + v) * 6 + k];
   const FluxLimArgs nofl = {nullptr, 0.0, 0.0};
-  face_flux<A, RECON, RIEMANN>(w, gamma, F, 0, nofl);
+  face_flux<A, RECON, RIEMANN>(w, gamma, F, opt, nofl);
 #pragma unroll
   for (int v = 0; v < 5; ++v) out[i * 5 + v] = F[v];
 }
@@ -1132,8 +1132,8 @@ struct jxf_solver {
   const double* dt_bound;   // jxf_bind_timestep: time step for the flux limiter outside jxf_stage
   int num_sms;
   int stages;
-  double dt_mult[3];
-  double blend[3][2];
+  double dt_mult[4];
+  double blend[4][2];
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
@@ -1178,13 +1178,13 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     if (cfg->n[i] < 1) return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d", i, cfg->n[i]);
   if (cfg->recon != JXF_RECON_PRIMITIVE && cfg->recon != JXF_RECON_CHAR_PRIMITIVE)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
-  if (cfg->stencil != JXF_STENCIL_WENO5Z && cfg->stencil != JXF_STENCIL_WENO5JS)
+  if (cfg->stencil < JXF_STENCIL_WENO5Z || cfg->stencil > JXF_STENCIL_TENO6)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
-  if (cfg->riemann != JXF_RIEMANN_HLLC && cfg->riemann != JXF_RIEMANN_RUSANOV && cfg->riemann != JXF_RIEMANN_HLL)
+  if (cfg->riemann < JXF_RIEMANN_HLLC || cfg->riemann > JXF_RIEMANN_AUSMP)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
   if (cfg->signal_speed < JXF_SIGNAL_EINFELDT || cfg->signal_speed > JXF_SIGNAL_TORO)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
-  if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK3)
+  if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK2_LS4)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
   if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
   if (cfg->flux_limiter < JXF_FLUXLIM_NONE || cfg->flux_limiter > JXF_FLUXLIM_NASA)
@@ -1236,9 +1236,13 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   g.rst[1] = g.n[2];
   g.rst[0] = (long long)g.n[1] * g.n[2];
   g.rvst = (long long)g.n[0] * g.n[1] * g.n[2];
-  // RK tables: time_integration/euler.py, RK2.py:22-33, RK3.py:27-29
+  // RK tables: time_integration/euler.py, RK2.py:22-33, RK3.py:27-29, RK2_LS4.py:27-30
   if (cfg->integrator == JXF_INT_EULER) {
     s->stages = 1; s->dt_mult[0] = 1.0;
+  } else if (cfg->integrator == JXF_INT_RK2_LS4) {
+    // low-storage 4-stage scheme: every later stage restarts from U^n (blend (0, 1)): u^k = u^n + m_k dt L(u^{k-1})
+    s->stages = 4; s->dt_mult[0] = 0.11; s->dt_mult[1] = 0.2766; s->dt_mult[2] = 0.5; s->dt_mult[3] = 1.0;
+    for (int k = 1; k < 4; ++k) { s->blend[k][0] = 0.0; s->blend[k][1] = 1.0; }
   } else if (cfg->integrator == JXF_INT_RK2) {
     s->stages = 2; s->dt_mult[0] = 1.0; s->dt_mult[1] = 0.5;
     s->blend[1][0] = 0.5; s->blend[1][1] = 0.5;
@@ -1531,11 +1535,15 @@ static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cuda
     return fail(JXF_ERR_UNSUPPORTED, "tuning build: WENO5-Z CHAR-PRIMITIVE only");
   return dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
 #else
-  switch (s->cfg.recon + 2 * s->cfg.stencil) {
+  // every stencil other than the two tuned WENO5 forms runs in the STENCIL_GENERIC instantiations (RECON 4 / 5),
+  // selected at run time by bits 11-14 of the option word (base_args)
+  switch (s->cfg.recon + 2 * std::min(s->cfg.stencil, (int)STENCIL_GENERIC)) {
     case 0: return dispatch_riemann<A, 0>(s, a, epi, st);
     case 1: return dispatch_riemann<A, 1>(s, a, epi, st);
     case 2: return dispatch_riemann<A, 2>(s, a, epi, st);
-    default: return dispatch_riemann<A, 3>(s, a, epi, st);
+    case 3: return dispatch_riemann<A, 3>(s, a, epi, st);
+    case 4: return dispatch_riemann<A, 4>(s, a, epi, st);
+    default: return dispatch_riemann<A, 5>(s, a, epi, st);
   }
 #endif
 }
@@ -1558,7 +1566,10 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
   // packed face-flux options (numerics.cuh face_flux `opt`): limiter mode | signal speed << 4
   a.limiter = (s->cfg.interpolation_limiter ? (s->cfg.limit_velocity ? 2 : 1) : 0) | (s->cfg.signal_speed << 4) |
               ((s->cfg.riemann == JXF_RIEMANN_HLL ? 1 : 0) << 8) |     // HLL rides on the RUSANOV instantiations
-              (s->cfg.flux_limiter << 9);
+              ((s->cfg.riemann == JXF_RIEMANN_HLLCLM ? RIEMANN_ALT_HLLCLM                 // ... and so do HLLC-LM, AUSM+
+                : s->cfg.riemann == JXF_RIEMANN_AUSMP ? RIEMANN_ALT_AUSMP : 0) << 15) |
+              (s->cfg.flux_limiter << 9) |
+              ((s->cfg.stencil >= JXF_STENCIL_WENO1 ? s->cfg.stencil : 0) << 11);   // generic stencil id (numerics.cuh ALT_*)
   // positivity flux limiter: lambda = dt / dx * sigma (limiter_flux.py:202-205, compute_partition :681-720)
   a.fl.dt = s->dt_bound;
   a.fl.inv_dx = s->cfg.inv_dx[axis];
@@ -1999,10 +2010,16 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   if (!windows || !flux || n <= 0) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: bad argument");
   const unsigned bx = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  (void)bx; (void)st; (void)axis; (void)recon; (void)riemann; (void)gamma;
+  (void)bx; (void)st; (void)axis; (void)riemann; (void)gamma;
+  // stencils other than the two WENO5 forms: the generic instantiations + the stencil id in the option word
+  const int stencil = recon >> 1;
+  if (recon < 0 || stencil > JXF_STENCIL_TENO6) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
+  const int opt = (stencil >= JXF_STENCIL_WENO1 ? stencil : 0) << 11;
+  recon = (recon & 1) + 2 * std::min(stencil, (int)STENCIL_GENERIC);
+  (void)opt;
 #define JXF_DBG_CASE(A, R, S)                                                                     \
   if (axis == A && recon == R && riemann == S) {                                                  \
-    face_flux_debug_kernel<A, R, S><<<bx, 128, 0, st>>>(windows, (long long)n, gamma, flux);       \
+    face_flux_debug_kernel<A, R, S><<<bx, 128, 0, st>>>(windows, (long long)n, gamma, flux, opt);  \
     return check_launch("face_flux_debug");                                                       \
   }
 #ifndef JXF_TUNE_ONLY
@@ -2011,6 +2028,8 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   JXF_DBG_CASE(2, 0, 0) JXF_DBG_CASE(2, 0, 1) JXF_DBG_CASE(2, 1, 0) JXF_DBG_CASE(2, 1, 1)
   JXF_DBG_CASE(0, 2, 0) JXF_DBG_CASE(0, 3, 0) JXF_DBG_CASE(1, 2, 0) JXF_DBG_CASE(1, 3, 0)
   JXF_DBG_CASE(2, 2, 0) JXF_DBG_CASE(2, 3, 0)
+  JXF_DBG_CASE(0, 4, 0) JXF_DBG_CASE(0, 5, 0) JXF_DBG_CASE(1, 4, 0) JXF_DBG_CASE(1, 5, 0)
+  JXF_DBG_CASE(2, 4, 0) JXF_DBG_CASE(2, 5, 0)
 #endif
 #undef JXF_DBG_CASE
   return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");

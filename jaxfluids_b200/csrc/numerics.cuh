@@ -14,13 +14,23 @@ constexpr double kStencilEps = 1e-30;                 // config/precision.py:53
 constexpr double kEps = 2.220446049250313e-16;        // config/precision.py:44-55
 
 enum { RECON_PRIMITIVE = 0, RECON_CHAR_PRIMITIVE = 1 };   // reconstruction variable = RECON & 1
-enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1 };          // reconstruction stencil  = RECON >> 1
+enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1, STENCIL_GENERIC = 2 };   // reconstruction stencil = RECON >> 1
 // The kernels' RECON template parameter carries both: RECON = variable + 2 * stencil.
+// STENCIL_GENERIC: the other reconstruction stencils of the reference that fit the 6-cell window, selected at run
+// time by `alt` (bits 11-14 of the face-flux option word) inside ONE extra set of kernel instantiations -- plain
+// reference-order arithmetic in an out-of-line function, not a tuned path.  The ids are the C ABI's JXF_STENCIL_*.
+enum { ALT_WENO5Z = 0, ALT_WENO5JS = 1,   // reference-order forms of the two tuned stencils (flux-splitting path only)
+       ALT_WENO1 = 2, ALT_WENO3JS = 3, ALT_WENO3Z = 4, ALT_TENO5 = 5, ALT_WENO6CU = 6, ALT_KOREN = 7, ALT_MC = 8,
+       ALT_MINMOD = 9, ALT_SUPERBEE = 10, ALT_VANALBADA = 11, ALT_VANLEER = 12, ALT_WENO3N = 13, ALT_CENTRAL2 = 14,
+       ALT_TENO6 = 15 };
 enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
 // HLLC wave-speed estimate (signal_speeds.py): a run-time option `sig` of riemann_flux (uniform branch), packed
 // with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4) | (HLL << 8), HLL = the HLL
 // Riemann solver (HLL.py) riding on the RIEMANN_RUSANOV kernel instantiations
 enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG_TORO = 4 };
+// Further per-face Riemann solvers of the reference, bits 15-16 of the option word (= bits 11-12 of `sig`), riding on
+// the RIEMANN_RUSANOV kernel instantiations like HLL: plain reference-order arithmetic in an out-of-line function.
+enum { RIEMANN_ALT_NONE = 0, RIEMANN_ALT_HLLCLM = 1 /* HLLCLM.py */, RIEMANN_ALT_AUSMP = 2 /* AUSMP.py */ };
 
 // signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order.
 // OUT OF LINE: the tuned path is EINFELDT; keeping these (IEEE sqrt / divisions) out of the sweep loops keeps the
@@ -32,6 +42,19 @@ enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG
 #define JXF_NOINLINE
 #endif
 #endif
+struct Vec5 {
+  double v[5];
+};
+template <int A>
+__device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR, double gamma);   // defined below
+// convective_solver = FLUX-SPLITTING (flux_splitting_scheme.py): bits 17-18 of the option word select the eigenvalue
+// choice; only the STENCIL_GENERIC kernel instantiations carry the branch
+enum { FS_NONE = 0, FS_ROE = 1, FS_CLLF = 2, FS_LLF = 3 };
+struct Win6 {
+  double w[5][6];
+};
+template <int A>
+__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs);             // defined below
 __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
                                                     double rhoR, double pL, double pR, double gamma) {
   double S_L, S_R;
@@ -83,6 +106,182 @@ template <int A> struct AxisIds;
 template <> struct AxisIds<0> { static constexpr int un = 1, t0 = 2, t1 = 3; };
 template <> struct AxisIds<1> { static constexpr int un = 2, t0 = 3, t1 = 1; };
 template <> struct AxisIds<2> { static constexpr int un = 3, t0 = 1, t1 = 2; };
+
+// ---------------------------------------------------------------------------
+// Generic reconstruction stencils (STENCIL_GENERIC).  q0..q5 = the six cells around the face in upwind-biased
+// order (the face lies between q2 and q3): cells i-2..i+3 for the left state (j = 0), their mirror i+3..i-2 for
+// the right state (j = 1) -- stencils/spatial_stencil.py:45-113.  Reference order, IEEE division.
+//   WENO1            weno/weno1_js.py:24-29
+//   WENO3-JS / -Z / -N  weno3_base.py:33-49, weno/weno3_js.py:15-43, weno/weno3_z.py:23-43, weno/weno3_n.py:22-41
+//   CENTRAL2         reconstruction/central/central_2.py:38-47 (the same mean on both sides)
+//   TENO5            teno/teno5.py:32-71 (C = 1, q = 6, C_T = 1e-5, d = (0.05, 0.55, 0.40)), weno5_base.py:34-51
+//   WENO6-CU         weno6_base.py:32-58, weno/weno6_cu.py:36-63 (C = 20)
+//   TENO6            teno6_base.py:32-62, teno/teno6.py:42-73 (C = 1, q = 6, C_T = 1e-7, d = (.05, .45, .3, .2))
+//   KOREN .. VANLEER muscl/muscl3.py:39-77 with stencils/limiter.py:6-22 (the two sides are not mirror images of
+//                    one formula, hence `j`)
+// ---------------------------------------------------------------------------
+__device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
+                                               double q5) {
+  const double eps = kStencilEps;
+  if (id == ALT_WENO1) return q2;
+  if (id == ALT_CENTRAL2) return 0.5 * ((j == 0) ? (q2 + q3) : (q3 + q2));    // buffer[i] + buffer[i+1] on both sides
+  if (id == ALT_WENO3JS || id == ALT_WENO3Z || id == ALT_WENO3N) {
+    const double d0 = q2 - q1, d1 = q3 - q2;
+    const double beta_0 = d0 * d0, beta_1 = d1 * d1;
+    double alpha_0, alpha_1;
+    if (id == ALT_WENO3JS) {
+      alpha_0 = (1.0 / 3.0) * (1.0 / (beta_0 * beta_0 + eps));
+      alpha_1 = (2.0 / 3.0) * (1.0 / (beta_1 * beta_1 + eps));
+    } else {
+      double tau_3 = fabs(beta_0 - beta_1);
+      if (id == ALT_WENO3N) {
+        const double s = q1 - 2.0 * q2 + q3, t = q1 - q3;
+        const double beta_3 = (13.0 / 12.0) * (s * s) + 0.25 * (t * t);
+        tau_3 = fabs(0.5 * (beta_0 + beta_1) - beta_3);
+      }
+      alpha_0 = (1.0 / 3.0) * (1.0 + tau_3 / (beta_0 + eps));
+      alpha_1 = (2.0 / 3.0) * (1.0 + tau_3 / (beta_1 + eps));
+    }
+    const double one_alpha = 1.0 / (alpha_0 + alpha_1);
+    const double p_0 = -0.5 * q1 + 1.5 * q2;
+    const double p_1 = 0.5 * q2 + 0.5 * q3;
+    return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1;
+  }
+  if (id == ALT_TENO5 || id == ALT_WENO6CU || id == ALT_TENO6 || id == ALT_WENO5Z || id == ALT_WENO5JS) {
+    const double s0 = q0 - 2.0 * q1 + q2, t0 = q0 - 4.0 * q1 + 3.0 * q2;
+    const double s1 = q1 - 2.0 * q2 + q3, t1 = q1 - q3;
+    const double s2 = q2 - 2.0 * q3 + q4, t2 = 3.0 * q2 - 4.0 * q3 + q4;
+    const double beta_0 = (13.0 / 12.0) * (s0 * s0) + 0.25 * (t0 * t0);
+    const double beta_1 = (13.0 / 12.0) * (s1 * s1) + 0.25 * (t1 * t1);
+    const double beta_2 = (13.0 / 12.0) * (s2 * s2) + 0.25 * (t2 * t2);
+    const double p_0 = (1.0 / 3.0) * q0 + (-7.0 / 6.0) * q1 + (11.0 / 6.0) * q2;
+    const double p_1 = (-1.0 / 6.0) * q1 + (5.0 / 6.0) * q2 + (1.0 / 3.0) * q3;
+    const double p_2 = (1.0 / 3.0) * q2 + (5.0 / 6.0) * q3 + (-1.0 / 6.0) * q4;
+    if (id == ALT_WENO5Z || id == ALT_WENO5JS) {   // weno/weno5_z.py:32-52, weno/weno5_js.py:32-50
+      double alpha_0, alpha_1, alpha_2;
+      if (id == ALT_WENO5Z) {
+        const double tau_5 = fabs(beta_0 - beta_2);
+        alpha_0 = 0.1 * (1.0 + tau_5 / (beta_0 + eps));
+        alpha_1 = 0.6 * (1.0 + tau_5 / (beta_1 + eps));
+        alpha_2 = 0.3 * (1.0 + tau_5 / (beta_2 + eps));
+      } else {
+        alpha_0 = 0.1 * (1.0 / (beta_0 * beta_0 + eps));
+        alpha_1 = 0.6 * (1.0 / (beta_1 * beta_1 + eps));
+        alpha_2 = 0.3 * (1.0 / (beta_2 * beta_2 + eps));
+      }
+      const double one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2);
+      return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2;
+    }
+    if (id == ALT_TENO5) {
+      const double tau_5 = fabs(beta_0 - beta_2);
+      // jnp.power(x, 6): the value only feeds the cut-off comparison below
+      const double x0 = 1.0 + tau_5 / (beta_0 + eps), x1 = 1.0 + tau_5 / (beta_1 + eps), x2 = 1.0 + tau_5 / (beta_2 + eps);
+      const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2;
+      const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2;
+      const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2);
+      const double w0 = 0.05 * ((gamma_0 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
+      const double w1 = 0.55 * ((gamma_1 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
+      const double w2 = 0.40 * ((gamma_2 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
+      const double one_dk = 1.0 / (w0 + w1 + w2 + eps);
+      return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2;
+    }
+    const double beta_6 = 1.0 / 10080 / 12 * (
+        271779 * q0 * q0 +
+        q0 * (-2380800 * q1 + 4086352 * q2 - 3462252 * q3 + 1458762 * q4 - 245620 * q5) +
+        q1 * (5653317 * q1 - 20427884 * q2 + 17905032 * q3 - 7727988 * q4 + 1325006 * q5) +
+        q2 * (19510972 * q2 - 35817664 * q3 + 15929912 * q4 - 2792660 * q5) +
+        q3 * (17195652 * q3 - 15880404 * q4 + 2863984 * q5) +
+        q4 * (3824847 * q4 - 1429976 * q5) +
+        139633 * q5 * q5);
+    if (id == ALT_TENO6) {
+      const double beta_3 = 1.0 / 240.0 * (
+          q2 * (2107 * q2 - 9402 * q3 + 7042 * q4 - 1854 * q5)
+          + q3 * (11003 * q3 - 17246 * q4 + 4642 * q5)
+          + q4 * (7043 * q4 - 3882 * q5)
+          + 547 * q5 * q5);
+      const double p_3 = (3.0 / 12.0) * q2 + (13.0 / 12.0) * q3 + (-5.0 / 12.0) * q4 + (1.0 / 12.0) * q5;
+      const double tau_6 = fabs(beta_6 - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2));
+      const double x0 = 1.0 + tau_6 / (beta_0 + eps), x1 = 1.0 + tau_6 / (beta_1 + eps);
+      const double x2 = 1.0 + tau_6 / (beta_2 + eps), x3 = 1.0 + tau_6 / (beta_3 + eps);
+      const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2, c3 = x3 * x3 * x3;
+      const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2, gamma_3 = c3 * c3;
+      const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2 + gamma_3);
+      const double w0 = 0.050 * ((gamma_0 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
+      const double w1 = 0.450 * ((gamma_1 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
+      const double w2 = 0.300 * ((gamma_2 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
+      const double w3 = 0.200 * ((gamma_3 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
+      const double one_dk = 1.0 / (w0 + w1 + w2 + w3 + eps);
+      return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3;
+    }
+    const double beta_3 = beta_6;       // weno6_base.py calls the six-point indicator beta_3
+    const double p_3 = (11.0 / 6.0) * q3 + (-7.0 / 6.0) * q4 + (1.0 / 3.0) * q5;
+    const double tau_6 = beta_3 - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2);
+    const double alpha_0 = (1.0 / 20.0) * (20.0 + tau_6 / (beta_0 + eps));
+    const double alpha_1 = (9.0 / 20.0) * (20.0 + tau_6 / (beta_1 + eps));
+    const double alpha_2 = (9.0 / 20.0) * (20.0 + tau_6 / (beta_2 + eps));
+    const double alpha_3 = (1.0 / 20.0) * (20.0 + tau_6 / (beta_3 + eps));
+    const double one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2 + alpha_3);
+    return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2 +
+           (alpha_3 * one_alpha) * p_3;
+  }
+  // MUSCL3 with a slope limiter
+  const double delta_central = (j == 0) ? (q3 - q2) : (q2 - q3);
+  const double delta_upwind = (j == 0) ? (q2 - q1) : (q1 - q2);
+  const double r = (delta_upwind >= eps) ? delta_central / (delta_upwind + 1e-10)
+                                         : (delta_central + eps) / (delta_upwind + eps);
+  double lim;
+  if (id == ALT_KOREN) lim = fmax(0.0, fmin(2.0 * r, fmin((1.0 + 2.0 * r) / 3.0, 2.0)));
+  else if (id == ALT_MC) lim = fmax(0.0, fmin(2.0 * r, fmin((1.0 + r) / 2.0, 2.0)));
+  else if (id == ALT_MINMOD) lim = fmax(0.0, fmin(1.0, r));
+  else if (id == ALT_SUPERBEE) lim = fmax(0.0, fmax(fmin(1.0, 2.0 * r), fmin(2.0, r)));
+  else if (id == ALT_VANALBADA) lim = fmax(0.0, r) * (1.0 + r) / (1.0 + r * r);
+  else lim = fmax(0.0, 2.0 * r) / (1.0 + fabs(r));   // ALT_VANLEER
+  return (j == 0) ? q2 + 0.5 * lim * delta_upwind : q2 - 0.5 * lim * delta_upwind;
+}
+
+__device__ __forceinline__ void stencil_generic_lr(int id, const double (&q)[6], double& left, double& right) {
+  left = stencil_generic(id, 0, q[0], q[1], q[2], q[3], q[4], q[5]);
+  right = stencil_generic(id, 1, q[5], q[4], q[3], q[2], q[1], q[0]);
+}
+
+// reconstruct() of the generic stencils: PRIMITIVE (high_order_godunov.py:267-280) or CHAR-PRIMITIVE (:298-316 with
+// eigendecomposition.py:139-148, 215-231, 425-431, 517-521), reference order.
+template <int A, bool CHAR>
+__device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], double gamma, double (&pl)[5],
+                                                    double (&pr)[5], int id) {
+  using Id = AxisIds<A>;
+  if (!CHAR) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) stencil_generic_lr(id, w[v], pl[v], pr[v]);
+  } else {
+    const double rho_ave = 0.5 * (w[0][2] + w[0][3]);
+    const double p_ave = 0.5 * (w[4][2] + w[4][3]);
+    const double c_ave = sqrt(gamma * p_ave / rho_ave);
+    const double cc_ave = c_ave * c_ave;
+    const double k_u = 0.5 / c_ave;
+    const double k_p = 0.5 / (cc_ave * rho_ave);
+    const double k_cc = 1.0 / cc_ave;
+    double q[6], l0, r0, l1, r1, l4, r4;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = -k_u * w[Id::un][k] + k_p * w[4][k];
+    stencil_generic_lr(id, q, l0, r0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = w[0][k] - k_cc * w[4][k];
+    stencil_generic_lr(id, q, l1, r1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = k_u * w[Id::un][k] + k_p * w[4][k];
+    stencil_generic_lr(id, q, l4, r4);
+    stencil_generic_lr(id, w[Id::t0], pl[Id::t0], pr[Id::t0]);
+    stencil_generic_lr(id, w[Id::t1], pl[Id::t1], pr[Id::t1]);
+    const double ccr = cc_ave * rho_ave;
+    pl[0] = rho_ave * (l0 + l4) + l1;
+    pl[Id::un] = c_ave * (-l0 + l4);
+    pl[4] = ccr * (l0 + l4);
+    pr[0] = rho_ave * (r0 + r4) + r1;
+    pr[Id::un] = c_ave * (-r0 + r4);
+    pr[4] = ccr * (r0 + r4);
+  }
+}
 
 // ===========================================================================
 // Two evaluations of the same formulas:
@@ -188,9 +387,11 @@ __device__ __forceinline__ void physical_flux(const double (&p)[5], const double
 // ---------------------------------------------------------------------------
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
-                                            double (&pl)[5], double (&pr)[5]) {
+                                            double (&pl)[5], double (&pr)[5], int alt = 0) {
   using Id = AxisIds<A>;
-  if ((RECON & 1) == RECON_PRIMITIVE) {
+  if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
+    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt);
+  } else if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) weno5z_lr<(RECON >> 1)>(w[v], pl[v], pr[v]);
   } else {
@@ -283,6 +484,13 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
     const double wl = 0.5 * (1.0 + sgn), wr = 0.5 * (1.0 - sgn);
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = wl * fL[v] + wr * fR[v];
+  } else if ((sig >> 11) & 3) {
+    Vec5 a, b;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) { a.v[v] = pl[v]; b.v[v] = pr[v]; }
+    const Vec5 o = riemann_other<A>((sig >> 11) & 3, sig & 15, a, b, gamma);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = o.v[v];
   } else if ((sig >> 4) & 1) {
     // HLL: solvers/riemann_solvers/HLL.py (the kernels' RIEMANN_RUSANOV instantiation with the HLL bit of `sig`)
     const int sp = sig & 15;
@@ -498,9 +706,11 @@ __device__ __forceinline__ void prims_from_cons(const double (&c)[5], double gam
 // ---------------------------------------------------------------------------
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
-                                            double (&pl)[5], double (&pr)[5]) {
+                                            double (&pl)[5], double (&pr)[5], int alt = 0) {
   using Id = AxisIds<A>;
-  if ((RECON & 1) == RECON_PRIMITIVE) {
+  if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
+    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt);
+  } else if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
       double cl, cr;
@@ -564,8 +774,9 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
 // Carry of the cell-centred weights between consecutive faces of a marching sweep.
 template <int RECON>
 struct ReconCarry {
-  static constexpr int N = ((RECON & 1) == RECON_PRIMITIVE) ? 5 : 2;   // fields reconstructed as they are
-  WenoG g[N];
+  // fields reconstructed as they are (none for the generic stencils: nothing is carried)
+  static constexpr int N = ((RECON >> 1) == STENCIL_GENERIC) ? 0 : (((RECON & 1) == RECON_PRIMITIVE) ? 5 : 2);
+  WenoG g[N > 0 ? N : 1];
 };
 
 // weights of the cell that is the window's cell k=1..: prime the carry from the 5 cells w[.][0..4]
@@ -573,10 +784,12 @@ struct ReconCarry {
 template <int A, int RECON>
 __device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconCarry<RECON>& cy) {
   using Id = AxisIds<A>;
+  if constexpr ((RECON >> 1) != STENCIL_GENERIC) {
 #pragma unroll
-  for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
-    const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
-    cy.g[j] = weno5z_g<(RECON >> 1)>(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3]);
+    for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+      const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+      cy.g[j] = weno5z_g<(RECON >> 1)>(w[v][1] - w[v][0], w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3]);
+    }
   }
 }
 
@@ -584,56 +797,60 @@ __device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconC
 // of this face); on exit those of window cell 3 (right stencil of this face = left stencil of the next)
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                  double (&pr)[5], ReconCarry<RECON>& cy) {
+                                                  double (&pr)[5], ReconCarry<RECON>& cy, int alt = 0) {
   using Id = AxisIds<A>;
+  if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
+    reconstruct<A, RECON>(w, gamma, pl, pr, alt);
+  } else {
 #pragma unroll
-  for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
-    const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
-    const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
-                 d4 = w[v][5] - w[v][4];
-    pl[v] = w[v][2] + weno5z_left_corr(cy.g[j], d0, d1, d2, d3);
-    const WenoG gn = weno5z_g<(RECON >> 1)>(d1, d2, d3, d4);
-    pr[v] = w[v][3] + weno5z_right_corr(gn, d1, d2, d3, d4);
-    cy.g[j] = gn;
-  }
-  if ((RECON & 1) != RECON_PRIMITIVE) {
-    double dr[5], du[5], dp[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      dr[k] = w[0][k + 1] - w[0][k];
-      du[k] = w[Id::un][k + 1] - w[Id::un][k];
-      dp[k] = w[4][k + 1] - w[4][k];
+    for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+      const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+      const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
+                   d4 = w[v][5] - w[v][4];
+      pl[v] = w[v][2] + weno5z_left_corr(cy.g[j], d0, d1, d2, d3);
+      const WenoG gn = weno5z_g<(RECON >> 1)>(d1, d2, d3, d4);
+      pr[v] = w[v][3] + weno5z_right_corr(gn, d1, d2, d3, d4);
+      cy.g[j] = gn;
     }
-    const double rho_ave = fma(0.5, dr[2], w[0][2]);
-    const double p_ave = fma(0.5, dp[2], w[4][2]);
-    const double gp = gamma * p_ave;
-    const double z = rsqrt_fast(gp * rho_ave);
-    const double ic = rho_ave * z;
-    const double c_ave = gp * z;
-    const double k_u = 0.5 * ic;
-    const double k_cc = ic * ic;
-    const double k_p = k_u * z;
-    double l0, r0, l1, r1, l4, r4;
-    {
-      double a[5], b[5], c[5];
+    if ((RECON & 1) != RECON_PRIMITIVE) {
+      double dr[5], du[5], dp[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double t = k_p * dp[k];
-        a[k] = fma(-k_u, du[k], t);
-        c[k] = fma(k_u, du[k], t);
-        b[k] = fma(-k_cc, dp[k], dr[k]);
+        dr[k] = w[0][k + 1] - w[0][k];
+        du[k] = w[Id::un][k + 1] - w[Id::un][k];
+        dp[k] = w[4][k + 1] - w[4][k];
       }
-      weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
-      weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
-      weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
+      const double rho_ave = fma(0.5, dr[2], w[0][2]);
+      const double p_ave = fma(0.5, dp[2], w[4][2]);
+      const double gp = gamma * p_ave;
+      const double z = rsqrt_fast(gp * rho_ave);
+      const double ic = rho_ave * z;
+      const double c_ave = gp * z;
+      const double k_u = 0.5 * ic;
+      const double k_cc = ic * ic;
+      const double k_p = k_u * z;
+      double l0, r0, l1, r1, l4, r4;
+      {
+        double a[5], b[5], c[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double t = k_p * dp[k];
+          a[k] = fma(-k_u, du[k], t);
+          c[k] = fma(k_u, du[k], t);
+          b[k] = fma(-k_cc, dp[k], dr[k]);
+        }
+        weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
+        weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
+        weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
+      }
+      const double sl = l0 + l4, sr = r0 + r4;
+      pl[0] = w[0][2] + fma(rho_ave, sl, l1);
+      pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
+      pl[4] = fma(gp, sl, w[4][2]);
+      pr[0] = w[0][3] + fma(rho_ave, sr, r1);
+      pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
+      pr[4] = fma(gp, sr, w[4][3]);
     }
-    const double sl = l0 + l4, sr = r0 + r4;
-    pl[0] = w[0][2] + fma(rho_ave, sl, l1);
-    pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
-    pl[4] = fma(gp, sl, w[4][2]);
-    pr[0] = w[0][3] + fma(rho_ave, sr, r1);
-    pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
-    pr[4] = fma(gp, sr, w[4][3]);
   }
 }
 
@@ -739,6 +956,13 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 #pragma unroll
     for (int v = 0; v < 5; ++v) F[v] = (S_star > 0.0) ? fL[v] : ((S_star < 0.0) ? fR[v] : 0.5 * (fL[v] + fR[v]));
 #endif
+  } else if ((sig >> 11) & 3) {      // HLLC-LM / AUSM+ (out of line, reference order)
+    Vec5 a, b;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) { a.v[v] = pl[v]; b.v[v] = pr[v]; }
+    const Vec5 o = riemann_other<A>((sig >> 11) & 3, sig & 15, a, b, gamma);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) F[v] = o.v[v];
   } else if ((sig >> 4) & 1) {
     // HLL (HLL.py): F = (S_R+ F_L - S_L- F_R + S_L- S_R+ (U_R - U_L)) / (S_R+ - S_L- + eps)
     const int sp = sig & 15;
@@ -840,6 +1064,231 @@ __device__ __forceinline__ void riemann_flux_main(const double (&pl)[5], const d
 
 #endif  // JXF_REFERENCE_ORDER
 
+// ---------------------------------------------------------------------------
+// HLLC-LM (HLLCLM.py:30-135: HLLC with the low-Mach wave-speed limiter of Fleischmann et al. 2020, Ma_limit = 0.1)
+// and AUSM+ (AUSMP.py:29-95: interface speed of sound ARITHMETIC, alpha = 3/16, beta = 1/8), reference order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double sign_ref(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0); }   // jnp.sign
+
+template <int A>
+__device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR, double gamma) {
+  using Id = AxisIds<A>;
+  const double (&pl)[5] = PL.v;
+  const double (&pr)[5] = PR.v;
+  double cl[5], cr[5];
+  cons_from_prims(pl, gamma, cl);
+  cons_from_prims(pr, gamma, cr);
+  const double aL = sqrt(gamma * pl[4] / pl[0]);
+  const double aR = sqrt(gamma * pr[4] / pr[0]);
+  const double uL = pl[Id::un], uR = pr[Id::un];
+  Vec5 out;
+  if (variant == RIEMANN_ALT_HLLCLM) {
+    const double2 ss = (sp == SIG_EINFELDT) ? einfeldt_signal_speeds(uL, uR, aL, aR, pl[0], pr[0])
+                                            : simple_signal_speeds(sp, uL, uR, aL, aR, pl[0], pr[0], pl[4], pr[4], gamma);
+    const double S_L = ss.x, S_R = ss.y;
+    const double dL = pl[0] * (S_L - uL);
+    const double dR = pr[0] * (S_R - uR);
+    const double S_s = ((pr[4] - pl[4]) + (uL * dL - uR * dR)) / (dL - dR);
+    double usL[5], usR[5];
+    {
+      const double pre = (S_L - uL) / (S_L - S_s) * pl[0];
+      usL[0] = pre;
+      usL[Id::un] = pre * S_s;
+      usL[Id::t0] = pre * pl[Id::t0];
+      usL[Id::t1] = pre * pl[Id::t1];
+      usL[4] = pre * (cl[4] / cl[0] + (S_s - uL) * (S_s + pl[4] / pl[0] / (S_L - uL)));
+    }
+    {
+      const double pre = (S_R - uR) / (S_R - S_s) * pr[0];
+      usR[0] = pre;
+      usR[Id::un] = pre * S_s;
+      usR[Id::t0] = pre * pr[Id::t0];
+      usR[Id::t1] = pre * pr[Id::t1];
+      usR[4] = pre * (cr[4] / cr[0] + (S_s - uR) * (S_s + pr[4] / pr[0] / (S_R - uR)));
+    }
+    const double Ma_local = fmax(fabs(uL / aL), fabs(uR / aR));
+    const double phi = sin(fmin(1.0, Ma_local / 0.1) * 3.141592653589793 * 0.5);
+    const double wL = phi * S_L, wR = phi * S_R;
+    double fL[5], fR[5];
+    physical_flux<A>(pl, cl, fL);
+    physical_flux<A>(pr, cr, fR);
+    const double kL = 0.5 * (1.0 + sign_ref(S_L)), kR = 0.5 * (1.0 - sign_ref(S_R));
+    const double kS = 0.25 * (1.0 - sign_ref(S_L)) * (1.0 + sign_ref(S_R));
+    const double abs_s = fabs(S_s);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const double flux_star = 0.5 * (fL[v] + fR[v]) +
+                               0.5 * (wL * (usL[v] - cl[v]) + abs_s * (usL[v] - usR[v]) + wR * (usR[v] - cr[v]));
+      out.v[v] = kL * fL[v] + kR * fR[v] + kS * flux_star;
+    }
+  } else {   // RIEMANN_ALT_AUSMP
+    const double alpha = 3.0 / 16.0, beta = 1.0 / 8.0;
+    const double a = 0.5 * (aL + aR);
+    const double M_l = uL / a, M_r = uR / a;
+    const double ql = M_l * M_l - 1.0, qr = M_r * M_r - 1.0;
+    const double M_plus = (fabs(M_l) >= 1.0) ? 0.5 * (M_l + fabs(M_l))
+                                             : 0.25 * ((M_l + 1.0) * (M_l + 1.0)) + beta * (ql * ql);
+    const double M_minus = (fabs(M_r) >= 1.0) ? 0.5 * (M_r - fabs(M_r))
+                                              : -0.25 * ((M_r - 1.0) * (M_r - 1.0)) - beta * (qr * qr);
+    const double M_ausm = M_plus + M_minus;
+    const double M_ausm_plus = 0.5 * (M_ausm + fabs(M_ausm));
+    const double M_ausm_minus = 0.5 * (M_ausm - fabs(M_ausm));
+    const double P_plus = (fabs(M_l) >= 1.0) ? 0.5 * (1.0 + sign_ref(M_l))
+                                             : 0.25 * ((M_l + 1.0) * (M_l + 1.0)) * (2.0 - M_l) + alpha * M_l * (ql * ql);
+    const double P_minus = (fabs(M_r) >= 1.0) ? 0.5 * (1.0 - sign_ref(M_r))
+                                              : 0.25 * ((M_r - 1.0) * (M_r - 1.0)) * (2.0 + M_r) - alpha * M_r * (qr * qr);
+    const double pressure_ausm = P_plus * pl[4] + P_minus * pr[4];
+    double phiL[5], phiR[5];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { phiL[v] = cl[v]; phiR[v] = cr[v]; }
+    phiL[4] = cl[4] + pl[4];
+    phiR[4] = cr[4] + pr[4];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) out.v[v] = a * (M_ausm_plus * phiL[v] + M_ausm_minus * phiR[v]);
+    out.v[Id::un] = out.v[Id::un] + pressure_ausm;
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// Flux-splitting scheme (solvers/convective_fluxes/flux_splitting_scheme.py:62-111) with the conservative
+// eigendecomposition of Fedkiw et al. 1999 at the ARITHMETIC frozen state (eigendecomposition.py:146-231, 576-715):
+// conservatives U_k and physical fluxes F_k of the six window cells in the characteristic space of the face,
+// F+- = (L F_k +- |lambda| L U_k) / 2, F+ reconstructed from the left (j = 0), F- from the right (j = 1), summed and
+// transformed back with R.  Eigenvalue magnitudes: ROE :668-671, CLLF :674-681, LLF :684-689.  The conservatives
+// of the window cells are formed from the primitives (equation_manager.py:93-101).  Reference order; the matrix
+// products run over all five entries in order, zeros included, like the reference's einsum.
+// ---------------------------------------------------------------------------
+template <int A>
+__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs) {
+  using Id = AxisIds<A>;
+  const double (&w)[5][6] = W.w;
+  double ave[5], pL[5], pR[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    pL[v] = w[v][2];
+    pR[v] = w[v][3];
+    ave[v] = 0.5 * (pL[v] + pR[v]);
+  }
+  const double G = gamma - 1.0;
+  const double q2 = (ave[1] * ave[1] + ave[2] * ave[2]) + ave[3] * ave[3];
+  const double E = ave[4] / (gamma - 1.0) + 0.5 * ave[0] * q2;
+  const double H = (E + ave[4]) / ave[0];
+  const double c = sqrt(gamma * ave[4] / ave[0]);
+  const double cc = c * c;
+  const double one_cc = 1.0 / cc, one_rho = 1.0 / ave[0];
+  const int ua = Id::un, m0 = Id::t0, m1 = Id::t1;
+  double R[5][5], L[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { R[i][k] = 0.0; L[i][k] = 0.0; }
+  R[0][0] = 1.0;
+  R[ua][0] = ave[ua] - c;
+  R[m0][0] = ave[m0];
+  R[m1][0] = ave[m1];
+  R[4][0] = H - ave[ua] * c;
+  R[0][ua] = G;
+  R[1][ua] = G * ave[1];
+  R[2][ua] = G * ave[2];
+  R[3][ua] = G * ave[3];
+  R[4][ua] = G * H - cc;
+  R[m0][m0] = -ave[0];
+  R[4][m0] = -ave[0] * ave[m0];
+  R[m1][m1] = ave[0];
+  R[4][m1] = ave[0] * ave[m1];
+  R[0][4] = 1.0;
+  R[ua][4] = ave[ua] + c;
+  R[m0][4] = ave[m0];
+  R[m1][4] = ave[m1];
+  R[4][4] = H + ave[ua] * c;
+  L[0][0] = 0.5 * one_cc * (G * q2 - G * H + (ave[ua] + c) * c);
+  L[0][ua] = 0.5 * one_cc * (-ave[ua] * G - c);
+  L[0][m0] = 0.5 * one_cc * (-ave[m0] * G);
+  L[0][m1] = 0.5 * one_cc * (-ave[m1] * G);
+  L[0][4] = 0.5 * one_cc * G;
+  L[ua][0] = one_cc * (H - q2);
+  L[ua][1] = ave[1] * one_cc;
+  L[ua][2] = ave[2] * one_cc;
+  L[ua][3] = ave[3] * one_cc;
+  L[ua][4] = -one_cc;
+  L[m0][0] = ave[m0] * one_rho;
+  L[m0][m0] = -one_rho;
+  L[m1][0] = -ave[m1] * one_rho;
+  L[m1][m1] = one_rho;
+  L[4][0] = 0.5 * one_cc * (G * q2 - G * H - (ave[ua] - c) * c);
+  L[4][ua] = 0.5 * one_cc * (-ave[ua] * G + c);
+  L[4][m0] = 0.5 * one_cc * (-ave[m0] * G);
+  L[4][m1] = 0.5 * one_cc * (-ave[m1] * G);
+  L[4][4] = 0.5 * one_cc * G;
+  double lam[5];
+  if (fs == FS_ROE) {
+    lam[0] = fabs(ave[ua] - c);
+    lam[1] = fabs(ave[ua]);
+    lam[4] = fabs(ave[ua] + c);
+  } else {
+    const double cL = sqrt(gamma * pL[4] / pL[0]), cR = sqrt(gamma * pR[4] / pR[0]);
+    if (fs == FS_CLLF) {
+      lam[0] = fmax(fabs(pL[ua] - cL), fabs(pR[ua] - cR));
+      lam[1] = fmax(fabs(pL[ua]), fabs(pR[ua]));
+      lam[4] = fmax(fabs(pL[ua] + cL), fabs(pR[ua] + cR));
+    } else {   // FS_LLF
+      lam[0] = lam[1] = lam[4] = fmax(fabs(pL[ua]) + cL, fabs(pR[ua]) + cR);
+    }
+  }
+  lam[2] = lam[1];
+  lam[3] = lam[1];
+  double pos[5][6], neg[5][6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double p[5], u[5], f[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) p[v] = w[v][k];
+    cons_from_prims(p, gamma, u);
+    physical_flux<A>(p, u, f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double ch = L[i][0] * u[0], cf = L[i][0] * f[0];
+#pragma unroll
+      for (int v = 1; v < 5; ++v) {
+        ch = ch + L[i][v] * u[v];
+        cf = cf + L[i][v] * f[v];
+      }
+      const double lc = lam[i] * ch;
+      pos[i][k] = 0.5 * (cf + lc);
+      neg[i][k] = 0.5 * (cf - lc);
+    }
+  }
+  double xi[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double l = stencil_generic(id, 0, pos[i][0], pos[i][1], pos[i][2], pos[i][3], pos[i][4], pos[i][5]);
+    const double r = stencil_generic(id, 1, neg[i][5], neg[i][4], neg[i][3], neg[i][2], neg[i][1], neg[i][0]);
+    xi[i] = l + r;
+  }
+  Vec5 out;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double acc = R[i][0] * xi[0];
+#pragma unroll
+    for (int v = 1; v < 5; ++v) acc = acc + R[i][v] * xi[v];
+    out.v[i] = acc;
+  }
+  return out;
+}
+
+template <int A>
+__device__ __forceinline__ void flux_splitting_face(const double (&w)[5][6], double gamma, double (&F)[5], int id, int fs) {
+  Win6 W;
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) W.w[v][k] = w[v][k];
+  const Vec5 o = flux_splitting_flux<A>(W, gamma, id, fs);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) F[v] = o.v[v];
+}
+
 // Interpolation limiter (solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE; eps from
 // config/precision.py:54): a reconstructed state whose density is < 1e-12, or whose pressure then is < 1e-10,
 // falls back to the first-order state (the adjacent cell: window index 2 for the left, 3 for the right state) --
@@ -870,9 +1319,6 @@ struct FluxLimArgs {
   const double* dt;     // physical time step size (device scalar; host pointer in the host simulation)
   double inv_dx;        // 1 / dx of the sweep axis
   double sigma;         // flux partition: dim (UNIFORM) or sum_a(1/dx_a) / (1/dx_axis) (CELLSIZE)
-};
-struct Vec5 {
-  double v[5];
 };
 __device__ __forceinline__ bool below_eps(double a, double b, double eps) {   // jnp.minimum(a, b) < eps (NaN -> false)
   return !(a != a || b != b) && (a < eps || b < eps);
@@ -932,8 +1378,14 @@ template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int opt,
                                           const FluxLimArgs& fl) {
   const int lim = opt & 15, sig = opt >> 4;
+  if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
+    if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
+      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3);
+      return;
+    }
+  }
   double pl[5], pr[5];
-  reconstruct<A, RECON>(w, gamma, pl, pr);
+  reconstruct<A, RECON>(w, gamma, pl, pr, (opt >> 11) & 15);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
@@ -953,8 +1405,8 @@ template <int A, int RECON>
 __device__ __forceinline__ void recon_carry_init(const double (&)[5][6], ReconCarry<RECON>&) {}
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                  double (&pr)[5], ReconCarry<RECON>&) {
-  reconstruct<A, RECON>(w, gamma, pl, pr);
+                                                  double (&pr)[5], ReconCarry<RECON>&, int alt = 0) {
+  reconstruct<A, RECON>(w, gamma, pl, pr, alt);
 }
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&,
@@ -967,8 +1419,14 @@ template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
                                                 ReconCarry<RECON>& cy, int opt, const FluxLimArgs& fl) {
   const int lim = opt & 15, sig = opt >> 4;
+  if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
+    if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
+      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3);
+      return;
+    }
+  }
   double pl[5], pr[5];
-  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
+  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy, (opt >> 11) & 15);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
 #if JXF_RIEMANN_MAIN

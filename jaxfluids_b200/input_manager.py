@@ -281,6 +281,10 @@ class InputManager:
         req = R.REQUIRED_HALOS[stencil]
         _assert(nh >= req, f"Reconstruction stencil {stencil} requires at least {req} halo cells, "
                            f"but only {nh} are specified.", "numerical")
+        if nh < R.KERNEL_HALOS:
+            raise NotImplementedError(f"conservatives/halo_cells = {nh} is valid for {stencil} in JAX-Fluids, but the "
+                                      f"B200 sweep kernels stage {R.KERNEL_HALOS} cells on either side of a face: "
+                                      f"halo_cells >= {R.KERNEL_HALOS} is required on the B200 path")
         pos_d = cons_d.get("positivity", {}) or {}
         for k, v in pos_d.items():
             if k.startswith("is_") and v and k != "is_interpolation_limiter":

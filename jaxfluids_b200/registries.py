@@ -37,20 +37,33 @@ REFERENCE_BOUNDARY_TYPES = (
 
 # what the sm_100a kernels implement
 DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov"}
-DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov", "HLL": "HLL"}
+# HLLC is the tuned kernel; the others ride on the RUSANOV kernel instantiations (run-time variants).  Not
+# implemented: LAX-FRIEDRICHS (a global max over all faces before every sweep), CATUM, HLLC_SIMPLEALPHA (its
+# single-phase branch raises NotImplementedError in the reference itself)
+DICT_RIEMANN_SOLVER = {"HLLC": "HLLC", "RUSANOV": "Rusanov", "HLL": "HLL", "HLLC-LM": "HLLCLM", "AUSMP": "AUSMP"}
 DICT_SIGNAL_SPEEDS = {"EINFELDT": "signal_speed_Einfeldt", "ARITHMETIC": "signal_speed_Arithmetic",
                       "RUSANOV": "signal_speed_Rusanov", "DAVIS": "signal_speed_Davis", "TORO": "signal_speed_Toro"}
-DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS"}
+# WENO5-Z / WENO5-JS are the tuned kernels; the others run in the generic (reference-order) instantiations
+DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS", "WENO1": "WENO1", "WENO3-JS": "WENO3JS",
+                               "WENO3-Z": "WENO3Z", "TENO5": "TENO5", "WENO6-CU": "WENO6CU", "KOREN": "KOREN",
+                               "MC": "MC", "MINMOD": "MINMOD", "SUPERBEE": "SUPERBEE", "VANALBADA": "VANALBADA",
+                               "VANLEER": "VANLEER", "WENO3-N": "WENO3N",
+                               "CENTRAL2": "CentralSecondOrderReconstruction", "TENO6": "TENO6"}
 TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
 TUPLE_FROZEN_STATE = ("ARITHMETIC",)
 TUPLE_POSITIVITY_FIXES = ("SIMPLE", "NASA")          # HAS is marked "TODO NEEDS UPDATE" upstream (limiter_flux.py:211)
 TUPLE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE")   # WAVESPEED needs a global max per axis before every sweep
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
-DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3"}
+DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3", "RK2_LS4": "RungeKutta2_LS4"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
 TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL", "DIRICHLET")
 
-REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3}   # weno5_base.py:18
+# required_halos of the reference classes (weno5_base.py:18, weno3_base.py:18, weno6_base.py:17, muscl3.py:20,
+# weno1_js.py: 1, central_2.py:21, teno6_base.py:16)
+REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3, "WENO1": 1, "WENO3-JS": 2, "WENO3-Z": 2, "TENO5": 3, "WENO6-CU": 3,
+                  "KOREN": 2, "MC": 2, "MINMOD": 2, "SUPERBEE": 2, "VANALBADA": 2, "VANLEER": 2, "WENO3-N": 2,
+                  "CENTRAL2": 1, "TENO6": 3}
+KERNEL_HALOS = 3          # the sweep kernels always stage 3 cells on either side of a face
 
 
 def select(value, reference_names, implemented, path, setup="numerical"):

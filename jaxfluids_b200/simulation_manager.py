@@ -89,11 +89,12 @@ class SpaceSolver:
 
 
 class TimeIntegrator:
-    """time_integration/time_integrator.py + RK3.py / RK2.py / euler.py tables."""
+    """time_integration/time_integrator.py + RK3.py / RK2.py / euler.py / RK2_LS4.py tables."""
     TABLES = {
         "EULER": (1, (1.0,), (1.0,), ()),
         "RK2": (2, (1.0, 0.5), (1.0, 1.0), ((0.5, 0.5),)),
         "RK3": (3, (1.0, 0.25, 2.0 / 3.0), (1.0, 0.5, 1.0), ((0.25, 0.75), (2.0 / 3.0, 1.0 / 3.0))),
+        "RK2_LS4": (4, (0.11, 0.2766, 0.5, 1.0), (0.11, 0.2766, 0.5, 1.0), ((0.0, 1.0), (0.0, 1.0), (0.0, 1.0))),
     }
 
     def __init__(self, runtime: BlockRuntime, name: str):

@@ -32,8 +32,10 @@ FACES = ("east", "west", "north", "south", "top", "bottom")   # domain/__init__.
 FACE_AXIS = {"east": 0, "west": 0, "north": 1, "south": 1, "top": 2, "bottom": 2}
 MINOR_AXES = ((2, 3), (3, 1), (1, 2))          # equation_information.py:110 (velocity_minor_axes)
 
-RK = {  # time_integration/{euler,RK2,RK3}.py
+RK = {  # time_integration/{euler,RK2,RK3,RK2_LS4}.py
     "EULER": dict(stages=1, dt_mult=(1.0,), blend=()),
+    # RK2_LS4.py:27-30 (the blend table there has three (0, 1) entries: every later stage restarts from U^n)
+    "RK2_LS4": dict(stages=4, dt_mult=(0.11, 0.2766, 0.5, 1.0), blend=((0.0, 1.0), (0.0, 1.0), (0.0, 1.0))),
     "RK2": dict(stages=2, dt_mult=(1.0, 0.5), blend=((0.5, 0.5),)),
     "RK3": dict(stages=3, dt_mult=(1.0, 0.25, 2.0 / 3.0), blend=((0.25, 0.75), (2.0 / 3.0, 1.0 / 3.0))),
 }
@@ -52,6 +54,8 @@ class Setup:
     riemann: str = "HLLC"                        # or RUSANOV
     signal_speed: str = "EINFELDT"               # HLLC wave-speed estimate: EINFELDT | ARITHMETIC | RUSANOV | DAVIS | TORO
     integrator: str = "RK3"
+    convective_solver: str = "GODUNOV"           # or FLUX-SPLITTING (convective_fluxes/flux_splitting block)
+    flux_splitting: str = "ROE"                  # flux_splitting/flux_splitting: ROE | CLLF | LLF (eigenvalue choice)
     cfl: float = 0.5
     fixed_timestep: float | None = None
     inv_dx_override: Tuple[float, float, float] | None = None   # sub-blocks of a larger grid (port_mt, multi-block tests)
@@ -320,7 +324,196 @@ def weno5js(a, b, c, d, e):
     return omega_0 * p_0 + omega_1 * p_1 + omega_2 * p_2
 
 
-STENCILS = {"WENO5-Z": weno5z, "WENO5-JS": weno5js}
+def weno1(q, j):
+    """weno/weno1_js.py:24-29: the upwind cell."""
+    return q[2]
+
+
+_DR3 = (1 / 3, 2 / 3)
+_CR3 = ((-0.5, 1.5), (0.5, 0.5))
+
+
+def _weno3_parts(q):
+    """weno3_base.py:33-49 on (u_im, u_i, u_ip) = the upwind-biased cells i-1, i, i+1."""
+    u_im, u_i, u_ip = q[1], q[2], q[3]
+    beta_0 = np.square(u_i - u_im)
+    beta_1 = np.square(u_ip - u_i)
+    p_0 = _CR3[0][0] * u_im + _CR3[0][1] * u_i
+    p_1 = _CR3[1][0] * u_i + _CR3[1][1] * u_ip
+    return beta_0, beta_1, p_0, p_1
+
+
+def weno3js(q, j):
+    """weno/weno3_js.py:15-43."""
+    beta_0, beta_1, p_0, p_1 = _weno3_parts(q)
+    one_beta_0_sq = 1.0 / (beta_0 * beta_0 + STENCIL_EPS)
+    one_beta_1_sq = 1.0 / (beta_1 * beta_1 + STENCIL_EPS)
+    alpha_0 = _DR3[0] * one_beta_0_sq
+    alpha_1 = _DR3[1] * one_beta_1_sq
+    one_alpha = 1.0 / (alpha_0 + alpha_1)
+    return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1
+
+
+def weno3z(q, j):
+    """weno/weno3_z.py:23-43."""
+    beta_0, beta_1, p_0, p_1 = _weno3_parts(q)
+    tau_3 = np.abs(beta_0 - beta_1)
+    alpha_z_0 = _DR3[0] * (1.0 + tau_3 / (beta_0 + STENCIL_EPS))
+    alpha_z_1 = _DR3[1] * (1.0 + tau_3 / (beta_1 + STENCIL_EPS))
+    one_alpha_z = 1.0 / (alpha_z_0 + alpha_z_1)
+    return (alpha_z_0 * one_alpha_z) * p_0 + (alpha_z_1 * one_alpha_z) * p_1
+
+
+def weno3n(q, j):
+    """weno/weno3_n.py:22-41: WENO3-Z weights with tau_3 = |(beta_0 + beta_1)/2 - beta_3|."""
+    beta_0, beta_1, p_0, p_1 = _weno3_parts(q)
+    u_im, u_i, u_ip = q[1], q[2], q[3]
+    beta_3 = 13 / 12 * np.square(u_im - 2 * u_i + u_ip) + 1 / 4 * np.square(u_im - u_ip)
+    tau_3 = np.abs(0.5 * (beta_0 + beta_1) - beta_3)
+    alpha_z_0 = _DR3[0] * (1.0 + tau_3 / (beta_0 + STENCIL_EPS))
+    alpha_z_1 = _DR3[1] * (1.0 + tau_3 / (beta_1 + STENCIL_EPS))
+    one_alpha_z = 1.0 / (alpha_z_0 + alpha_z_1)
+    return (alpha_z_0 * one_alpha_z) * p_0 + (alpha_z_1 * one_alpha_z) * p_1
+
+
+def central2(q, j):
+    """reconstruction/central/central_2.py:38-47 (the one central stencil stencils/__init__.py:19 offers the convective
+    reconstruction): the mean of the two cells of the face, on both sides."""
+    return 0.5 * (q[2] + q[3])
+
+
+def _weno5_parts(a, b, c, d, e):
+    """weno5_base.py:34-51."""
+    beta_0 = 13.0 / 12.0 * np.square(a - 2 * b + c) + 1.0 / 4.0 * np.square(a - 4 * b + 3 * c)
+    beta_1 = 13.0 / 12.0 * np.square(b - 2 * c + d) + 1.0 / 4.0 * np.square(b - d)
+    beta_2 = 13.0 / 12.0 * np.square(c - 2 * d + e) + 1.0 / 4.0 * np.square(3 * c - 4 * d + e)
+    p_0 = _CR[0][0] * a + _CR[0][1] * b + _CR[0][2] * c
+    p_1 = _CR[1][0] * b + _CR[1][1] * c + _CR[1][2] * d
+    p_2 = _CR[2][0] * c + _CR[2][1] * d + _CR[2][2] * e
+    return beta_0, beta_1, beta_2, p_0, p_1, p_2
+
+
+_DR_TENO5 = (0.05, 0.55, 0.40)                  # teno/teno5.py:26 ("optimized spectral properties")
+
+
+def teno5(q, j):
+    """teno/teno5.py:32-71: C = 1, q = 6, C_T = 1e-5; sharp cut-off of the sub-stencils."""
+    beta_0, beta_1, beta_2, p_0, p_1, p_2 = _weno5_parts(q[0], q[1], q[2], q[3], q[4])
+    tau_5 = np.abs(beta_0 - beta_2)
+    gamma_0 = np.power(1.0 + tau_5 / (beta_0 + STENCIL_EPS), 6)
+    gamma_1 = np.power(1.0 + tau_5 / (beta_1 + STENCIL_EPS), 6)
+    gamma_2 = np.power(1.0 + tau_5 / (beta_2 + STENCIL_EPS), 6)
+    one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2)
+    w0 = _DR_TENO5[0] * np.where(gamma_0 * one_gamma_sum < 1e-5, 0, 1)
+    w1 = _DR_TENO5[1] * np.where(gamma_1 * one_gamma_sum < 1e-5, 0, 1)
+    w2 = _DR_TENO5[2] * np.where(gamma_2 * one_gamma_sum < 1e-5, 0, 1)
+    one_dk = 1.0 / (w0 + w1 + w2 + STENCIL_EPS)
+    return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2
+
+
+_DR6 = (1 / 20, 9 / 20, 9 / 20, 1 / 20)
+_CR6_3 = (11 / 6, -7 / 6, 1 / 3)
+
+
+def weno6cu(q, j):
+    """weno6_base.py:32-58 and weno/weno6_cu.py:36-63 (C = 20) on the six cells i-2..i+3 (mirrored for j=1)."""
+    u_imm, u_im, u_i, u_ip, u_ipp, u_ippp = q
+    beta_0, beta_1, beta_2, p_0, p_1, p_2 = _weno5_parts(u_imm, u_im, u_i, u_ip, u_ipp)
+    beta_3 = 1.0 / 10080 / 12 * (
+        271779 * u_imm * u_imm +
+        u_imm * (-2380800 * u_im + 4086352 * u_i - 3462252 * u_ip + 1458762 * u_ipp - 245620 * u_ippp) +
+        u_im * (5653317 * u_im - 20427884 * u_i + 17905032 * u_ip - 7727988 * u_ipp + 1325006 * u_ippp) +
+        u_i * (19510972 * u_i - 35817664 * u_ip + 15929912 * u_ipp - 2792660 * u_ippp) +
+        u_ip * (17195652 * u_ip - 15880404 * u_ipp + 2863984 * u_ippp) +
+        u_ipp * (3824847 * u_ipp - 1429976 * u_ippp) +
+        139633 * u_ippp * u_ippp)
+    p_3 = _CR6_3[0] * u_ip + _CR6_3[1] * u_ipp + _CR6_3[2] * u_ippp
+    tau_6 = beta_3 - 1 / 6 * (beta_0 + 4 * beta_1 + beta_2)
+    alpha_0 = _DR6[0] * (20 + tau_6 / (beta_0 + STENCIL_EPS))
+    alpha_1 = _DR6[1] * (20 + tau_6 / (beta_1 + STENCIL_EPS))
+    alpha_2 = _DR6[2] * (20 + tau_6 / (beta_2 + STENCIL_EPS))
+    alpha_3 = _DR6[3] * (20 + tau_6 / (beta_3 + STENCIL_EPS))
+    one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2 + alpha_3)
+    return ((alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2 +
+            (alpha_3 * one_alpha) * p_3)
+
+
+_DR_TENO6 = (0.050, 0.450, 0.300, 0.200)        # teno/teno6.py:23 (6th-order convergence)
+_CR_TENO6_3 = (3 / 12, 13 / 12, -5 / 12, 1 / 12)
+
+
+def teno6(q, j):
+    """teno6_base.py:32-62 and teno/teno6.py:42-73 (C = 1, q = 6, C_T = 1e-7) on the six cells i-2..i+3."""
+    u_imm, u_im, u_i, u_ip, u_ipp, u_ippp = q
+    beta_0, beta_1, beta_2, p_0, p_1, p_2 = _weno5_parts(u_imm, u_im, u_i, u_ip, u_ipp)
+    beta_3 = 1.0 / 240.0 * (
+        u_i * (2107 * u_i - 9402 * u_ip + 7042 * u_ipp - 1854 * u_ippp)
+        + u_ip * (11003 * u_ip - 17246 * u_ipp + 4642 * u_ippp)
+        + u_ipp * (7043 * u_ipp - 3882 * u_ippp)
+        + 547 * u_ippp * u_ippp)
+    beta_6 = 1.0 / 10080 / 12 * (
+        271779 * u_imm * u_imm +
+        u_imm * (-2380800 * u_im + 4086352 * u_i - 3462252 * u_ip + 1458762 * u_ipp - 245620 * u_ippp) +
+        u_im * (5653317 * u_im - 20427884 * u_i + 17905032 * u_ip - 7727988 * u_ipp + 1325006 * u_ippp) +
+        u_i * (19510972 * u_i - 35817664 * u_ip + 15929912 * u_ipp - 2792660 * u_ippp) +
+        u_ip * (17195652 * u_ip - 15880404 * u_ipp + 2863984 * u_ippp) +
+        u_ipp * (3824847 * u_ipp - 1429976 * u_ippp) +
+        139633 * u_ippp * u_ippp)
+    p_3 = _CR_TENO6_3[0] * u_i + _CR_TENO6_3[1] * u_ip + _CR_TENO6_3[2] * u_ipp + _CR_TENO6_3[3] * u_ippp
+    tau_6 = np.abs(beta_6 - 1 / 6 * (beta_0 + 4 * beta_1 + beta_2))
+    gamma_0 = (1.0 + tau_6 / (beta_0 + STENCIL_EPS)) ** 6
+    gamma_1 = (1.0 + tau_6 / (beta_1 + STENCIL_EPS)) ** 6
+    gamma_2 = (1.0 + tau_6 / (beta_2 + STENCIL_EPS)) ** 6
+    gamma_3 = (1.0 + tau_6 / (beta_3 + STENCIL_EPS)) ** 6
+    one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2 + gamma_3)
+    w0 = _DR_TENO6[0] * np.where(gamma_0 * one_gamma_sum < 1e-7, 0, 1)
+    w1 = _DR_TENO6[1] * np.where(gamma_1 * one_gamma_sum < 1e-7, 0, 1)
+    w2 = _DR_TENO6[2] * np.where(gamma_2 * one_gamma_sum < 1e-7, 0, 1)
+    w3 = _DR_TENO6[3] * np.where(gamma_3 * one_gamma_sum < 1e-7, 0, 1)
+    one_dk = 1.0 / (w0 + w1 + w2 + w3 + STENCIL_EPS)
+    return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3
+
+
+# stencils/limiter.py:6-22
+MUSCL_LIMITERS = {
+    "KOREN": lambda r: np.maximum(0, np.minimum(2 * r, np.minimum((1 + 2 * r) / 3, 2))),
+    "MC": lambda r: np.maximum(0, np.minimum(2 * r, np.minimum((1 + r) / 2, 2))),
+    "MINMOD": lambda r: np.maximum(0, np.minimum(1, r)),
+    "SUPERBEE": lambda r: np.maximum(0, np.maximum(np.minimum(1, 2 * r), np.minimum(2, r))),
+    "VANALBADA": lambda r: np.maximum(0, r) * (1 + r) / (1 + r * r),
+    "VANLEER": lambda r: np.maximum(0, 2 * r) / (1 + np.abs(r)),
+}
+
+
+def _muscl3(limiter):
+    def fn(q, j):
+        """muscl/muscl3.py:39-77: the two sides are NOT mirror images of one formula (sign of the differences)."""
+        s0, s1, s2 = q[1], q[2], q[3]
+        if j == 0:
+            delta_central = s2 - s1
+            delta_upwind = s1 - s0
+        else:
+            delta_central = s1 - s2
+            delta_upwind = s0 - s1
+        r = np.where(delta_upwind >= STENCIL_EPS, delta_central / (delta_upwind + 1e-10),
+                     (delta_central + STENCIL_EPS) / (delta_upwind + STENCIL_EPS))
+        lim = MUSCL_LIMITERS[limiter](r)
+        if j == 0:
+            return s1 + 0.5 * lim * delta_upwind
+        return s1 - 0.5 * lim * delta_upwind
+    return fn
+
+
+# name -> f(q, j): q = the six cells around the face in upwind-biased order (q[2] | q[3] is the face;
+# j = 0: cells i-2..i+3, j = 1: their mirror i+3..i-2), spatial_stencil.py:45-113
+STENCILS = {"WENO5-Z": lambda q, j: weno5z(*q[:5]), "WENO5-JS": lambda q, j: weno5js(*q[:5]),
+            "WENO1": weno1, "WENO3-JS": weno3js, "WENO3-Z": weno3z, "TENO5": teno5, "WENO6-CU": weno6cu,
+            **{name: _muscl3(name) for name in MUSCL_LIMITERS}, "WENO3-N": weno3n, "CENTRAL2": central2,
+            "TENO6": teno6}
+# halo cells the stencil itself needs (required_halos of the reference classes; the sm_100a kernels always stage
+# 3 cells on either side of a face)
+REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3, "WENO1": 1, "WENO3-JS": 2, "WENO3-Z": 2, "TENO5": 3, "WENO6-CU": 3,
+                  **{name: 2 for name in MUSCL_LIMITERS}, "WENO3-N": 2, "CENTRAL2": 1, "TENO6": 3}
 
 
 def _window(prims, axis, s: Setup):
@@ -343,10 +536,10 @@ def reconstruct(prims, axis, s: Setup):
     """high_order_godunov.py:233-419 (PRIMITIVE :267-280, CHAR-PRIMITIVE :298-316,:401-402).
     Returns (prims_L, prims_R, cons_L, cons_R), each (5, faces...)."""
     w = _window(prims, axis, s)
-    weno5z = STENCILS[s.stencil]                 # the stencil the JSON names (local name kept for brevity)
+    stencil = STENCILS[s.stencil]                # the stencil the JSON names
     if s.recon == "PRIMITIVE":
-        pl = weno5z(w[0], w[1], w[2], w[3], w[4])
-        pr = weno5z(w[5], w[4], w[3], w[2], w[1])
+        pl = stencil(w, 0)
+        pr = stencil(w[::-1], 1)
     elif s.recon == "CHAR-PRIMITIVE":
         g = s.gamma
         ua = 1 + axis
@@ -369,8 +562,8 @@ def reconstruct(prims, axis, s: Setup):
             o[e1] = x[m1]
             o[4] = 0.5 / c_ave * x[ua] + 0.5 / (cc_ave * rho_ave) * x[4]
             chars.append(np.stack(o, axis=0))
-        cl = weno5z(chars[0], chars[1], chars[2], chars[3], chars[4])
-        cr = weno5z(chars[5], chars[4], chars[3], chars[2], chars[1])
+        cl = stencil(chars, 0)
+        cr = stencil(chars[::-1], 1)
         # back to primitives (eigendecomposition.py:517-521)
         res = []
         for x in (cl, cr):
@@ -493,6 +686,64 @@ def hll(pl, pr, cl, cr, axis, gamma, signal_speed="EINFELDT"):
     fL = physical_flux(pl, cl, axis)
     fR = physical_flux(pr, cr, axis)
     return (wR * fL - wL * fR + wL * wR * (cr - cl)) / (wR - wL + EPS)
+
+
+def hllclm(pl, pr, cl, cr, axis, gamma, signal_speed="EINFELDT"):
+    """HLLCLM.py:30-135 (single phase): HLLC with the low-Mach wave-speed limiter of Fleischmann et al. 2020,
+    Ma_limit = 0.1 (:28)."""
+    ua = 1 + axis
+    m0, m1 = MINOR_AXES[axis]
+    aL = speed_of_sound(pl[4], pl[0], gamma)
+    aR = speed_of_sound(pr[4], pr[0], gamma)
+    S_L, S_R = signal_speeds(signal_speed, pl[ua], pr[ua], aL, aR, pl[0], pr[0], pl[4], pr[4], gamma)
+    S_s = sstar(pl[ua], pr[ua], pl[4], pr[4], pl[0], pr[0], S_L, S_R)
+
+    def ustar(p, c, S_K):                                                          # Toro 10.73, :96-109
+        pre = (S_K - p[ua]) / (S_K - S_s) * p[0]
+        us = [pre, pre, pre, pre,
+              pre * (c[4] / c[0] + (S_s - p[ua]) * (S_s + p[4] / p[0] / (S_K - p[ua])))]
+        us[ua] = us[ua] * S_s
+        us[m0] = us[m0] * p[m0]
+        us[m1] = us[m1] * p[m1]
+        return np.stack(us, axis=0)
+    usL, usR = ustar(pl, cl, S_L), ustar(pr, cr, S_R)
+    Ma_local = np.maximum(np.abs(pl[ua] / aL), np.abs(pr[ua] / aR))                # :52-56
+    phi = np.sin(np.minimum(1.0, Ma_local / 0.1) * np.pi * 0.5)
+    wL = phi * S_L
+    wR = phi * S_R
+    fL = physical_flux(pl, cl, axis)
+    fR = physical_flux(pr, cr, axis)
+    flux_star = 0.5 * (fL + fR) + 0.5 * (wL * (usL - cl) + np.abs(S_s) * (usL - usR) + wR * (usR - cr))   # Eq. 19
+    return (0.5 * (1 + np.sign(S_L)) * fL + 0.5 * (1 - np.sign(S_R)) * fR
+            + 0.25 * (1 - np.sign(S_L)) * (1 + np.sign(S_R)) * flux_star)          # Eq. 18
+
+
+def ausmp(pl, pr, cl, cr, axis, gamma):
+    """AUSMP.py:29-95 (AUSM+, interface speed of sound ARITHMETIC, alpha = 3/16, beta = 1/8)."""
+    ua = 1 + axis
+    alpha, beta = 3.0 / 16.0, 1.0 / 8.0
+    phi_L = np.stack([cl[0], cl[1], cl[2], cl[3], cl[4] + pl[4]], axis=0)          # get_phi :86-95
+    phi_R = np.stack([cr[0], cr[1], cr[2], cr[3], cr[4] + pr[4]], axis=0)
+    aL = speed_of_sound(pl[4], pl[0], gamma)
+    aR = speed_of_sound(pr[4], pr[0], gamma)
+    a = 0.5 * (aL + aR)
+    M_l = pl[ua] / a
+    M_r = pr[ua] / a
+    M_plus = np.where(np.abs(M_l) >= 1, 0.5 * (M_l + np.abs(M_l)),
+                      0.25 * np.square(M_l + 1.0) + beta * np.square(M_l * M_l - 1.0))
+    M_minus = np.where(np.abs(M_r) >= 1, 0.5 * (M_r - np.abs(M_r)),
+                       -0.25 * np.square(M_r - 1.0) - beta * np.square(M_r * M_r - 1.0))
+    M_ausm = M_plus + M_minus
+    M_ausm_plus = 0.5 * (M_ausm + np.abs(M_ausm))
+    M_ausm_minus = 0.5 * (M_ausm - np.abs(M_ausm))
+    P_plus = np.where(np.abs(M_l) >= 1.0, 0.5 * (1 + np.sign(M_l)),
+                      0.25 * np.square(M_l + 1.0) * (2.0 - M_l) + alpha * M_l * np.square(M_l * M_l - 1.0))
+    P_minus = np.where(np.abs(M_r) >= 1.0, 0.5 * (1 - np.sign(M_r)),
+                       0.25 * np.square(M_r - 1.0) * (2.0 + M_r) - alpha * M_r * np.square(M_r * M_r - 1.0))
+    pressure_ausm = P_plus * pl[4] + P_minus * pr[4]
+    F = a * (M_ausm_plus * phi_L + M_ausm_minus * phi_R)
+    F[ua] = F[ua] + pressure_ausm
+    return F
 
 
 def rusanov(pl, pr, cl, cr, axis, gamma):
@@ -682,9 +933,115 @@ def flux_limiter(F, prims, cons, dt, axis, s: Setup):
     return theta * F_pos + (1 - theta) * F
 
 
+def _matvec(M, x):
+    """jnp.einsum("ij...,j...->i...", M, x) (eigendecomposition.py:717-743) with the sum over j taken in order."""
+    out = []
+    for i in range(5):
+        acc = M[i][0] * x[0]
+        for j in range(1, 5):
+            acc = acc + M[i][j] * x[j]
+        out.append(acc)
+    return np.stack(out, axis=0)
+
+
+def conservative_eigensystem(pL, pR, axis, gamma, flux_splitting=None):
+    """eigendecomposition.py:576-715 with the ARITHMETIC frozen state of :146-231 (single phase, ideal gas): right and
+    left eigenvectors of the conservative flux Jacobian after Fedkiw et al. 1999 as 5x5 nested lists of face arrays,
+    and -- for the flux-splitting scheme -- the eigenvalue magnitudes (ROE :668-671, CLLF :674-681, LLF :684-689)."""
+    ua = 1 + axis
+    m0, m1 = MINOR_AXES[axis]
+    ave = 0.5 * (pL + pR)
+    G = (gamma - 1) * np.ones_like(ave[0])                                     # get_grueneisen, ideal_gas.py:65-67
+    E = ave[4] / (gamma - 1) + 0.5 * ave[0] * (np.square(ave[1]) + np.square(ave[2]) + np.square(ave[3]))
+    H = (E + ave[4]) / ave[0]                                                  # ideal_gas.py:90-110
+    c = np.sqrt(gamma * ave[4] / ave[0])
+    cc = c * c
+    q2 = np.sum(np.square(ave[1:4]), axis=0)
+    one_cc = 1.0 / cc
+    one_rho = 1.0 / ave[0]
+    Z = np.zeros_like(ave[0])
+    Rm = [[Z for _ in range(5)] for _ in range(5)]
+    Lm = [[Z for _ in range(5)] for _ in range(5)]
+    Rm[0][0] = np.ones_like(Z)
+    Rm[ua][0] = ave[ua] - c
+    Rm[m0][0] = ave[m0]
+    Rm[m1][0] = ave[m1]
+    Rm[4][0] = H - ave[ua] * c
+    Rm[0][ua] = G
+    Rm[1][ua] = G * ave[1]
+    Rm[2][ua] = G * ave[2]
+    Rm[3][ua] = G * ave[3]
+    Rm[4][ua] = G * H - cc
+    Rm[m0][m0] = -ave[0]
+    Rm[4][m0] = -ave[0] * ave[m0]
+    Rm[m1][m1] = ave[0]
+    Rm[4][m1] = ave[0] * ave[m1]
+    Rm[0][4] = np.ones_like(Z)
+    Rm[ua][4] = ave[ua] + c
+    Rm[m0][4] = ave[m0]
+    Rm[m1][4] = ave[m1]
+    Rm[4][4] = H + ave[ua] * c
+    Lm[0][0] = 0.5 * one_cc * (G * q2 - G * H + (ave[ua] + c) * c)
+    Lm[0][ua] = 0.5 * one_cc * (-ave[ua] * G - c)
+    Lm[0][m0] = 0.5 * one_cc * (-ave[m0] * G)
+    Lm[0][m1] = 0.5 * one_cc * (-ave[m1] * G)
+    Lm[0][4] = 0.5 * one_cc * G
+    Lm[ua][0] = one_cc * (H - q2)
+    Lm[ua][1] = ave[1] * one_cc
+    Lm[ua][2] = ave[2] * one_cc
+    Lm[ua][3] = ave[3] * one_cc
+    Lm[ua][4] = -one_cc
+    Lm[m0][0] = ave[m0] * one_rho
+    Lm[m0][m0] = -one_rho
+    Lm[m1][0] = -ave[m1] * one_rho
+    Lm[m1][m1] = one_rho
+    Lm[4][0] = 0.5 * one_cc * (G * q2 - G * H - (ave[ua] - c) * c)
+    Lm[4][ua] = 0.5 * one_cc * (-ave[ua] * G + c)
+    Lm[4][m0] = 0.5 * one_cc * (-ave[m0] * G)
+    Lm[4][m1] = 0.5 * one_cc * (-ave[m1] * G)
+    Lm[4][4] = 0.5 * one_cc * G
+    lam = None
+    if flux_splitting == "ROE":
+        lam = (np.abs(ave[ua] - c), np.abs(ave[ua]), np.abs(ave[ua] + c))
+    elif flux_splitting == "CLLF":
+        cL, cR = speed_of_sound(pL[4], pL[0], gamma), speed_of_sound(pR[4], pR[0], gamma)
+        lam = (np.maximum(np.abs(pL[ua] - cL), np.abs(pR[ua] - cR)), np.maximum(np.abs(pL[ua]), np.abs(pR[ua])),
+               np.maximum(np.abs(pL[ua] + cL), np.abs(pR[ua] + cR)))
+    elif flux_splitting == "LLF":
+        g = np.maximum(np.abs(pL[ua]) + speed_of_sound(pL[4], pL[0], gamma),
+                       np.abs(pR[ua]) + speed_of_sound(pR[4], pR[0], gamma))
+        lam = (g, g, g)
+    elif flux_splitting is not None:
+        raise NotImplementedError(flux_splitting)
+    return Rm, Lm, lam
+
+
+def flux_splitting_face_flux(prims, cons, axis, s: Setup):
+    """flux_splitting_scheme.py:62-111: conservatives and physical fluxes of the stencil cells in the characteristic space
+    of the face's frozen state, split by the eigenvalue magnitudes, F+ reconstructed from the left (j = 0), F- from
+    the right (j = 1), summed and transformed back."""
+    wp = _window(prims, axis, s)
+    wc = _window(cons, axis, s)
+    Rm, Lm, lam = conservative_eigensystem(wp[2], wp[3], axis, s.gamma, s.flux_splitting)
+    lam5 = (lam[0], lam[1], lam[1], lam[1], lam[2])
+    pos, neg = [], []
+    for p, c in zip(wp, wc):
+        char = _matvec(Lm, c)
+        char_flux = _matvec(Lm, physical_flux(p, c, axis))
+        lam_char = np.stack([lam5[i] * char[i] for i in range(5)], axis=0)
+        pos.append(0.5 * (char_flux + lam_char))
+        neg.append(0.5 * (char_flux - lam_char))
+    stencil = STENCILS[s.stencil]
+    char_flux_xi = stencil(pos, 0) + stencil(neg[::-1], 1)
+    return _matvec(Rm, char_flux_xi)
+
+
 def face_flux(prims, axis, s: Setup, cons=None, dt=None):
     """high_order_godunov.py:117-231: face fluxes (5, N_axis+1, transverse interior); with positivity/flux_limiter
     the positivity-preserving switch of space_solver.py:532-543 follows."""
+    if s.convective_solver == "FLUX-SPLITTING":
+        cons = cons_from_prims(prims, s.gamma) if cons is None else cons
+        return flux_splitting_face_flux(prims, cons, axis, s)
     pl, pr, cl, cr = reconstruct(prims, axis, s)
     if s.riemann == "HLLC":
         F = hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
@@ -692,6 +1049,10 @@ def face_flux(prims, axis, s: Setup, cons=None, dt=None):
         F = rusanov(pl, pr, cl, cr, axis, s.gamma)
     elif s.riemann == "HLL":
         F = hll(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
+    elif s.riemann == "HLLC-LM":
+        F = hllclm(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
+    elif s.riemann == "AUSMP":
+        F = ausmp(pl, pr, cl, cr, axis, s.gamma)
     else:
         raise NotImplementedError(s.riemann)
     if s.flux_limiter:

@@ -65,7 +65,48 @@ FIXTURES = {
     "rti_16x48_dirichlet_gravity_rk3": ("rti", dict(cells=(16, 48, None)), 5, (5,)),
     # the shipped 1-D heat equation example, shrunk: heat flux only (is_convective_flux false), DIRICHLET E/W, nh 4
     "heat1d_40_dirichlet_noconv_rk3": ("heat1d", dict(cells=(40, None, None)), 6, (6,)),
+    # RK2_LS4 (time_integration/RK2_LS4.py) and the generic reconstruction stencils (TENO5, WENO3-Z, WENO6-CU, MUSCL);
+    # kept in tests/golden/generic/ (tests/helpers.generic_golden_names)
+    "generic/sod100_teno5_char_hllc_rk2ls4": ("sod", dict(cells=(100, None, None), stencil="TENO5", integrator="RK2_LS4"), 20, (20,)),
+    "generic/riemann2d_20x24_weno3z_prim_hllc_rk3": ("riemann2d", dict(cells=(20, 24, None), stencil="WENO3-Z", recon="PRIMITIVE"), 3, (3,)),
+    "generic/riemann2d_16x20_weno6cu_char_hllc_rk3": ("riemann2d", dict(cells=(16, 20, None), stencil="WENO6-CU"), 3, (3,)),
+    "generic/sod100_vanleer_prim_rusanov_rk3": ("sod", dict(cells=(100, None, None), stencil="VANLEER", recon="PRIMITIVE",
+                                                     riemann="RUSANOV"), 10, (10,)),
+    "generic/tgv_10x8x12_per_minmod_char_hllc_rk2ls4": ("tgv", dict(cells=(10, 8, 12), bc="PERIODIC", stencil="MINMOD",
+                                                            integrator="RK2_LS4"), 2, (2,)),
+    "generic/riemann2d_16x20_teno6_char_hllc_rk3": ("riemann2d", dict(cells=(16, 20, None), stencil="TENO6"), 3, (3,)),
+    # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
+    "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
+    "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),
+    "generic/riemann2d_20x24_prim_ausmp_rk3": ("riemann2d", dict(cells=(20, 24, None), recon="PRIMITIVE", riemann="AUSMP"), 3, (3,)),
+    "generic/sod100_char_ausmp_weno3z_rk2": ("sod", dict(cells=(100, None, None), riemann="AUSMP", stencil="WENO3-Z",
+                                                          integrator="RK2"), 10, (10,)),
 }
+
+GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU", "KOREN", "MC",
+                    "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
+
+
+def make_stencil_fixture():
+    """rhs of one shocked, oscillatory 2-D state for every generic reconstruction stencil x {PRIMITIVE, CHAR-PRIMITIVE}:
+    jumps (the TENO cut-off and the slope limiters switch) next to smooth waves of both signs."""
+    d = {}
+    x, y = np.meshgrid(np.linspace(0, 1, 20), np.linspace(0, 1, 24), indexing="ij")
+    rho = np.where(x < 0.45, 1.0 + 0.3 * np.sin(9 * y), 0.25 + 0.1 * np.cos(7 * x + 5 * y)) + 0.5 * (y > 0.6)
+    p = np.where(x + y < 0.9, 1.0 + 0.2 * np.cos(5 * x), 0.15 + 0.05 * np.sin(11 * y))
+    user = np.stack([rho, 0.6 * np.sin(6 * x + 2 * y), -0.4 * np.cos(4 * y - 3 * x) + 0.3 * (x > 0.7), p])[..., None]
+    d["user"] = user
+    for st in GENERIC_STENCILS:
+        for rv, tag in (("PRIMITIVE", "prim"), ("CHAR-PRIMITIVE", "char")):
+            case, num = rr.customize(*rr.load_case("riemann2d"), cells=(20, 24, None), stencil=st, recon=rv)
+            run = rr.ReferenceRun(case, num, user_prime_init=user)
+            key = f"{st}_{tag}"
+            d[f"case_json_{key}"], d[f"num_json_{key}"] = np.array(json.dumps(case)), np.array(json.dumps(num))
+            d["prims_halo"] = run.primitives
+            d[f"rhs_{key}"] = run.compute_rhs()
+    path = os.path.join(OUT, "special", "stencils_riemann2d_20x24.npz")
+    np.savez_compressed(path, **d)
+    print(f"special/stencils_riemann2d_20x24: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
 def make_limiter_fixture():
@@ -152,6 +193,7 @@ def make(name, case_name, kw, nsteps, snaps):
     for k, v in seq.items():
         d[k] = np.array(v)
     path = os.path.join(OUT, name + ".npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, **d)
     print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB")
 
@@ -170,3 +212,6 @@ if __name__ == "__main__":
     if not only or "flux_limiter" in only:
         with np.errstate(all="ignore"):
             make_flux_limiter_fixture()
+    if not only or "stencils" in only:
+        with np.errstate(all="ignore"):
+            make_stencil_fixture()

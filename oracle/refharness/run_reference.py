@@ -64,7 +64,7 @@ def load_case(name: str):
 
 
 def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None,
-              signal_speed=None, positivity=None, initial_condition=None):
+              signal_speed=None, positivity=None, initial_condition=None, flux_splitting=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -74,7 +74,16 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         for face in ("east", "west", "north", "south", "top", "bottom"):
             if case["boundary_conditions"][face]["type"] not in ("INACTIVE", "DIRICHLET", "WALL"):
                 case["boundary_conditions"][face] = {"type": bc}
-    g = num["conservatives"]["convective_fluxes"]["godunov"]
+    cf = num["conservatives"]["convective_fluxes"]
+    if flux_splitting is not None:           # convective_solver FLUX-SPLITTING with this eigenvalue choice
+        cf["convective_solver"] = "FLUX-SPLITTING"
+        cf.setdefault("flux_splitting", {})
+        cf["flux_splitting"]["flux_splitting"] = flux_splitting
+        cf["flux_splitting"].setdefault("reconstruction_stencil",
+                                        cf.get("godunov", {}).get("reconstruction_stencil", "WENO5-Z"))
+        if stencil is not None:
+            cf["flux_splitting"]["reconstruction_stencil"] = stencil
+    g = cf.setdefault("godunov", {})
     if recon is not None:
         g["reconstruction_variable"] = recon
     if riemann is not None:

@@ -27,6 +27,15 @@ def golden_names(dissipative=None):
     return [n for n in names if ("visc" in n or "gravity" in n or "noconv" in n or "fluxlim" in n) == bool(dissipative)]
 
 
+def generic_golden_names():
+    """Fixtures of the generic reconstruction stencils / RK2_LS4 (tests/golden/generic/), as names load_golden takes."""
+    return sorted("generic/" + os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "generic", "*.npz")))
+
+
+GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU", "KOREN", "MC",
+                    "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
+
+
 def load_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     case = json.loads(str(g["case_json"]))
@@ -54,8 +63,13 @@ def dissipation_from_json(case, num) -> dict:
 def setup_from_json(case, num) -> port.Setup:
     d = case["domain"]
     c = num["conservatives"]
-    g = c["convective_fluxes"]["godunov"]
+    solver = c["convective_fluxes"].get("convective_solver", "GODUNOV")
+    fs = c["convective_fluxes"].get("flux_splitting", {}) or {}
+    g = c["convective_fluxes"].get("godunov", {}) or {}
+    if solver == "FLUX-SPLITTING":          # the stencil of the flux_splitting block; the godunov block is not read
+        g = dict(g, reconstruction_stencil=fs.get("reconstruction_stencil", "WENO5-Z"))
     return port.Setup(
+        convective_solver=solver, flux_splitting=fs.get("flux_splitting", "ROE"),
         cells=tuple(d[a]["cells"] for a in "xyz"),
         domain=tuple(tuple(d[a]["range"]) for a in "xyz"),
         bc={f: case["boundary_conditions"][f]["type"] for f in port.FACES},

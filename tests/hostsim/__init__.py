@@ -28,12 +28,30 @@ def load(fma=True, reference_order=False):
     return lib
 
 
+STENCIL_IDS = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z": 4, "TENO5": 5, "WENO6-CU": 6,
+               "KOREN": 7, "MC": 8, "MINMOD": 9, "SUPERBEE": 10, "VANALBADA": 11, "VANLEER": 12, "WENO3-N": 13,
+               "CENTRAL2": 14, "TENO6": 15}   # JXF_STENCIL_*
+
+
+def _recon_id(s):
+    """The kernels' RECON template parameter: variable + 2 * min(stencil, STENCIL_GENERIC) (dispatch_recon)."""
+    if s.convective_solver == "FLUX-SPLITTING":          # always the generic instantiation (dispatch_recon)
+        return 4
+    return {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * min(STENCIL_IDS[s.stencil], 2)
+
+
 def _opt(s):
-    """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4."""
+    """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4 | HLL << 8 | flux limiter << 9 |
+    generic stencil id << 11, as base_args (jxf_b200.cu) packs it."""
     lim = (2 if s.limit_velocity else 1) if s.is_interpolation_limiter else 0
     sig = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}[s.signal_speed]
     fl = {None: 0, "SIMPLE": 1, "NASA": 2}[s.flux_limiter]
-    return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9)
+    st = STENCIL_IDS[s.stencil]
+    alt = {"HLLC-LM": 1, "AUSMP": 2}.get(s.riemann, 0)              # RIEMANN_ALT_* (ride on the RUSANOV instantiations)
+    if s.convective_solver == "FLUX-SPLITTING":          # stencil id (all of them) + eigenvalue choice
+        return (st << 11) | ({"ROE": 1, "CLLF": 2, "LLF": 3}[s.flux_splitting] << 17)
+    return (lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9) | ((st if st >= 2 else 0) << 11) |
+            (alt << 15))
 
 
 def _flux_limiter_args(s, axis, dt):
@@ -60,7 +78,7 @@ def rhs_axis_march(prims, axis, s, fma=True, dt=None):
     shp = w.shape[:3]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_march_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
+    rc = lib.face_flux_march_host(axis, _recon_id(s), (1 if s.convective_solver == "FLUX-SPLITTING" else {"HLLC": 0}.get(s.riemann, 1)),
                                   w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s),
                                   *_flux_limiter_args(s, axis, dt))
     assert rc == 0
@@ -83,7 +101,7 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False, dt=None):
     shp = w.shape[:-2]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_host(axis, ({"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * {"WENO5-Z": 0, "WENO5-JS": 1}[s.stencil]), {"HLLC": 0, "RUSANOV": 1, "HLL": 1}[s.riemann],
+    rc = lib.face_flux_host(axis, _recon_id(s), (1 if s.convective_solver == "FLUX-SPLITTING" else {"HLLC": 0}.get(s.riemann, 1)),
                             w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s),
                             *_flux_limiter_args(s, axis, dt))
     assert rc == 0

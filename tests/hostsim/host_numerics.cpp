@@ -45,6 +45,8 @@ extern "C" int face_flux_march_host(int axis, int recon, int riemann, const doub
   MCASE(0,0,0) MCASE(0,0,1) MCASE(0,1,0) MCASE(0,1,1) MCASE(0,2,0) MCASE(0,2,1) MCASE(0,3,0) MCASE(0,3,1)
   MCASE(1,0,0) MCASE(1,0,1) MCASE(1,1,0) MCASE(1,1,1) MCASE(1,2,0) MCASE(1,2,1) MCASE(1,3,0) MCASE(1,3,1)
   MCASE(2,0,0) MCASE(2,0,1) MCASE(2,1,0) MCASE(2,1,1) MCASE(2,2,0) MCASE(2,2,1) MCASE(2,3,0) MCASE(2,3,1)
+  MCASE(0,4,0) MCASE(0,4,1) MCASE(0,5,0) MCASE(0,5,1) MCASE(1,4,0) MCASE(1,4,1) MCASE(1,5,0) MCASE(1,5,1)
+  MCASE(2,4,0) MCASE(2,4,1) MCASE(2,5,0) MCASE(2,5,1)
   return -1;
 }
 
@@ -56,5 +58,7 @@ extern "C" int face_flux_host(int axis, int recon, int riemann, const double* wi
   CASE(0,0,0) CASE(0,0,1) CASE(0,1,0) CASE(0,1,1) CASE(0,2,0) CASE(0,2,1) CASE(0,3,0) CASE(0,3,1)
   CASE(1,0,0) CASE(1,0,1) CASE(1,1,0) CASE(1,1,1) CASE(1,2,0) CASE(1,2,1) CASE(1,3,0) CASE(1,3,1)
   CASE(2,0,0) CASE(2,0,1) CASE(2,1,0) CASE(2,1,1) CASE(2,2,0) CASE(2,2,1) CASE(2,3,0) CASE(2,3,1)
+  CASE(0,4,0) CASE(0,4,1) CASE(0,5,0) CASE(0,5,1) CASE(1,4,0) CASE(1,4,1) CASE(1,5,0) CASE(1,5,1)
+  CASE(2,4,0) CASE(2,4,1) CASE(2,5,0) CASE(2,5,1)
   return -1;
 }

@@ -21,7 +21,7 @@ def total_rhs(prims, s, fma, reference_order=False):
     return tot
 
 
-@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False) + H.generic_golden_names())
 def test_device_functions_without_fma_are_bit_identical_to_reference(name):
     g, case, num = H.load_golden(name)
     s = H.setup_from_json(case, num)
@@ -31,7 +31,7 @@ def test_device_functions_without_fma_are_bit_identical_to_reference(name):
 
 
 @pytest.mark.parametrize("reference_order", [True, False])
-@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False) + H.generic_golden_names())
 def test_device_functions_with_fma_within_tolerance(name, reference_order):
     """Both evaluations (reference order / production re-association), FMA-contracted, every stage of
     the first step of every reference fixture."""
@@ -55,7 +55,7 @@ def test_cancelled_total_norm_measures_conditioning_not_implementation():
     assert H.rel_linf(a, b, scale=H.rhs_scales(g["prims0_halo"], s)) < 1e-12
 
 
-@pytest.mark.parametrize("name", H.golden_names(dissipative=False))
+@pytest.mark.parametrize("name", H.golden_names(dissipative=False) + H.generic_golden_names())
 def test_marching_variant_with_carried_weights(name):
     """sweep_strided's face_flux_carry (cell-centred weights of the as-is fields carried between
     consecutive faces) against the reference fixtures, every axis."""
@@ -144,3 +144,70 @@ def test_flux_limiter_host_simulated(tag):
             assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True, dt=dt), ref, scale=scales) <= H.TOL_RHS
             assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True, dt=dt), ref, scale=scales) <= H.TOL_RHS
     assert np.array_equal(ref_total, g[f"rhs_{tag}"])
+
+
+@pytest.mark.parametrize("variable", ["prim", "char"])
+@pytest.mark.parametrize("stencil", H.GENERIC_STENCILS)
+def test_generic_stencils_host_simulated(stencil, variable):
+    """stencil_generic / reconstruct_generic (numerics.cuh) on the reference's shocked fixture, where the TENO cut-off
+    and the slope limiters switch: without FMA bit-identical to the reference's rhs, with FMA (what nvcc emits) within
+    1e-12, through face_flux and through the marching form."""
+    import json
+    import os
+    g = np.load(os.path.join(H.GOLDEN, "special", "stencils_riemann2d_20x24.npz"))
+    key = f"{stencil}_{variable}"
+    s = H.setup_from_json(json.loads(str(g[f"case_json_{key}"])), json.loads(str(g[f"num_json_{key}"])))
+    prims = g["prims_halo"]
+    scales = H.rhs_scales(prims, s)
+    tot_exact, tot_fma, tot_march = 0.0, 0.0, 0.0
+    for a in s.active:
+        tot_exact = tot_exact + hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True)
+        tot_fma = tot_fma + hostsim.rhs_axis(prims, a, s, fma=True)
+        tot_march = tot_march + hostsim.rhs_axis_march(prims, a, s, fma=True)
+    assert np.array_equal(tot_exact, g[f"rhs_{key}"])
+    assert H.rel_linf(tot_fma, g[f"rhs_{key}"], scale=scales) <= H.TOL_RHS
+    assert H.rel_linf(tot_march, g[f"rhs_{key}"], scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("stencil", ["WENO3-Z", "TENO5", "WENO6-CU", "VANALBADA"])
+def test_generic_stencils_3d_all_axes_host_simulated(stencil):
+    """Every sweep axis (the axis only enters through the velocity roles) and both reconstruction variables."""
+    for cells, recon, bc in [((8, 10, 12), "CHAR-PRIMITIVE", "SYMMETRY"), ((9, 8, 10), "PRIMITIVE", "PERIODIC")]:
+        s = H.make_setup(cells, bc=bc, recon=recon, stencil=stencil)
+        prims, cons = port.initialize(H.smooth_ic(s, seed=11, amp=0.2), s)
+        scales = H.rhs_scales(prims, s)
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s)
+            assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)
+            assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+
+
+def _fast_ic(s, seed, factor):
+    """smooth_ic with the velocities scaled up: sub- and supersonic faces of both signs."""
+    ic = H.smooth_ic(s, seed=seed, amp=0.2)
+    ic[1:4] *= factor
+    return ic
+
+
+@pytest.mark.parametrize("riemann,sig", [("HLLC-LM", "EINFELDT"), ("HLLC-LM", "DAVIS"), ("HLLC-LM", "TORO"),
+                                         ("AUSMP", "EINFELDT")])
+def test_hllclm_and_ausmp_host_simulated(riemann, sig):
+    """riemann_solver = HLLC-LM (HLLCLM.py) / AUSMP (AUSMP.py): riemann_other (numerics.cuh) without FMA bit-identical
+    to the pinned oracle, with FMA within 1e-12 (face_flux and the marching form) -- on low-Mach states (the HLLC-LM
+    limiter phi < 1) and on states with supersonic faces of both signs (the |M| >= 1 branches of AUSM+, sign(S_K))."""
+    for cells, recon, bc, factor in [((48, 1, 1), "CHAR-PRIMITIVE", "ZEROGRADIENT", 4.0),
+                                     ((14, 18, 1), "PRIMITIVE", "PERIODIC", 4.0),
+                                     ((8, 10, 12), "CHAR-PRIMITIVE", "SYMMETRY", 0.05)]:
+        s = H.make_setup(cells, bc=bc, recon=recon, riemann=riemann)
+        s.signal_speed = sig
+        prims, cons = port.initialize(_fast_ic(s, 4, factor), s)
+        pi = prims[(slice(None),) + s.interior]
+        mach = pi[1] / port.speed_of_sound(pi[4], pi[0], s.gamma)
+        assert (mach.min() < -1.05 and mach.max() > 1.05) if factor > 1 else np.abs(mach).max() < 0.1
+        scales = H.rhs_scales(prims, s)
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s)
+            assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)
+            assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS

@@ -68,12 +68,13 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
 
 
 @pytest.mark.parametrize("path,value", [
-    (GOD + ("riemann_solver",), "HLLC-LM"),
+    (GOD + ("riemann_solver",), "LAX-FRIEDRICHS"),
+    (GOD + ("riemann_solver",), "CATUM"),
     (GOD + ("signal_speed",), "DAVIS2"),
-    (GOD + ("reconstruction_stencil",), "TENO5"),
+    (GOD + ("reconstruction_stencil",), "TENO6-A"),
+    (GOD + ("reconstruction_stencil",), "WENO7-JS"),
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
-    (("conservatives", "time_integration", "integrator"), "RK2_LS4"),
     (("active_physics", "is_geometric_source"), True),
     (("conservatives", "positivity", "flux_limiter"), "HAS"),
     (("conservatives", "positivity", "flux_partition"), "WAVESPEED"),
@@ -84,6 +85,24 @@ def test_valid_reference_options_outside_the_path_raise_not_implemented(path, va
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     with pytest.raises(NotImplementedError, match="B200 path"):
         InputManager(case, _mod(num, path, value))
+
+
+@pytest.mark.parametrize("stencil", ["WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU",
+                                     "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER"])
+def test_generic_stencil_names_and_rk2_ls4_select_the_path(stencil):
+    """The reference's stencil / integrator names select the B200 path unchanged; a halo count that is valid for the
+    stencil in the reference but below what the sweep kernels stage says so."""
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    num = _mod(_mod(num, GOD + ("reconstruction_stencil",), stencil), ("conservatives", "time_integration", "integrator"),
+               "RK2_LS4")
+    im = InputManager(case, num)
+    assert im.numerical_setup.conservatives.convective_fluxes.godunov.reconstruction_stencil == stencil
+    assert im.numerical_setup.conservatives.time_integration.integrator == "RK2_LS4"
+    from jaxfluids_b200 import _lib, registries as R
+    assert stencil in _lib.STENCIL and R.REQUIRED_HALOS[stencil] <= 3
+    if R.REQUIRED_HALOS[stencil] < 3:
+        with pytest.raises(NotImplementedError, match="halo_cells >= 3"):
+            InputManager(case, _mod(num, ("conservatives", "halo_cells"), R.REQUIRED_HALOS[stencil]))
 
 
 @pytest.mark.parametrize("path,value", [

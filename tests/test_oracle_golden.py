@@ -6,7 +6,7 @@ from oracle import port
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("name", H.golden_names())
+@pytest.mark.parametrize("name", H.golden_names() + H.generic_golden_names())
 def test_port_reproduces_reference_fixture(name):
     g, case, num = H.load_golden(name)
     s = H.setup_from_json(case, num)
@@ -97,3 +97,23 @@ def test_flux_limiter_fixture(tag):
         switched = sum(int((port.face_flux(prims, a, s, cons, dt) != port.face_flux(prims, a, s0)).any(axis=0).sum())
                        for a in s.active)
     assert switched > 80                                   # the limiter really acts on this state
+
+
+@pytest.mark.parametrize("variable", ["prim", "char"])
+@pytest.mark.parametrize("stencil", H.GENERIC_STENCILS)
+def test_generic_stencil_fixture(stencil, variable):
+    """Every generic reconstruction stencil (WENO1, WENO3-JS/-Z, TENO5, WENO6-CU, the six MUSCL limiters) x
+    {PRIMITIVE, CHAR-PRIMITIVE} on one shocked 2-D state: rhs bit-identical to what the reference produced
+    (oracle/refharness/make_goldens.py:make_stencil_fixture), and the stencil really differs from WENO5-Z there."""
+    import copy, json, os
+    g = np.load(os.path.join(H.GOLDEN, "special", "stencils_riemann2d_20x24.npz"))
+    key = f"{stencil}_{variable}"
+    s = H.setup_from_json(json.loads(str(g[f"case_json_{key}"])), json.loads(str(g[f"num_json_{key}"])))
+    assert s.stencil == stencil and s.recon == {"prim": "PRIMITIVE", "char": "CHAR-PRIMITIVE"}[variable]
+    prims, cons = port.initialize(g["user"], s, from_user_buffer=True)
+    assert np.array_equal(prims, g["prims_halo"])
+    rhs = port.compute_rhs(prims, s)
+    assert np.array_equal(rhs, g[f"rhs_{key}"])
+    s5 = copy.copy(s)
+    s5.stencil = "WENO5-Z"
+    assert H.rel_linf(port.compute_rhs(prims, s5), rhs) > 1e-3

@@ -42,6 +42,29 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("cavity", dict(cells=(16, 14, None)), 2),
     ("rti", dict(cells=(12, 32, None)), 2),
     ("heat1d", dict(cells=(32, None, None)), 2),
+    # RK2_LS4 and the generic reconstruction stencils
+    ("sod", dict(cells=(64, None, None), integrator="RK2_LS4"), 2),
+    ("tgv", dict(cells=(10, 8, 12), stencil="TENO5", integrator="RK2_LS4"), 1),
+    ("tgv", dict(cells=(8, 8, 10), stencil="WENO6-CU", bc="PERIODIC"), 1),
+    ("riemann2d", dict(cells=(16, 20, None), stencil="WENO3-JS", recon="PRIMITIVE"), 2),
+    ("riemann2d", dict(cells=(16, 20, None), stencil="WENO3-Z"), 2),
+    ("sod", dict(cells=(64, None, None), stencil="WENO1"), 2),
+    ("sod", dict(cells=(64, None, None), stencil="KOREN"), 2),
+    ("sod", dict(cells=(64, None, None), stencil="MC", recon="PRIMITIVE"), 2),
+    ("riemann2d", dict(cells=(16, 16, None), stencil="MINMOD"), 1),
+    ("riemann2d", dict(cells=(16, 16, None), stencil="SUPERBEE", recon="PRIMITIVE"), 1),
+    ("sod", dict(cells=(64, None, None), stencil="VANALBADA"), 2),
+    ("sod", dict(cells=(64, None, None), stencil="VANLEER", riemann="RUSANOV"), 2),
+    ("sod", dict(cells=(64, None, None), stencil="WENO3-N"), 2),
+    ("riemann2d", dict(cells=(16, 16, None), stencil="CENTRAL2", recon="PRIMITIVE"), 1),
+    ("tgv", dict(cells=(8, 8, 10), stencil="TENO6"), 1),
+    # HLLC-LM and AUSM+
+    ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
+    ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
+    ("riemann2d", dict(cells=(16, 20, None), riemann="HLLC-LM", signal_speed="DAVIS", recon="PRIMITIVE"), 2),
+    ("sod", dict(cells=(64, None, None), riemann="AUSMP"), 3),
+    ("riemann2d", dict(cells=(16, 20, None), riemann="AUSMP", recon="PRIMITIVE"), 2),
+    ("tgv", dict(cells=(8, 8, 10), riemann="AUSMP", bc="PERIODIC"), 1),
 ])
 def test_port_is_bit_identical_to_reference(name, kw, nsteps):
     from oracle.refharness import pin_check
