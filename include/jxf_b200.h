@@ -47,6 +47,9 @@ enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1, JXF_RIEMANN_HLL = 2 /* HLL
        JXF_RIEMANN_AUSMP = 4 /* AUSMP.py (AUSM+) */ };
 /* ref: solvers/riemann_solvers/signal_speeds.py (DICT_SIGNAL_SPEEDS); DAVIS2 is marked not working upstream */
 enum { JXF_SIGNAL_EINFELDT = 0, JXF_SIGNAL_ARITHMETIC = 1, JXF_SIGNAL_RUSANOV = 2, JXF_SIGNAL_DAVIS = 3, JXF_SIGNAL_TORO = 4 };
+/* ref: solvers/convective_fluxes/__init__.py:7-12; solvers/__init__.py:1-3 (TUPLE_FLUX_SPLITTING) */
+enum { JXF_SOLVER_GODUNOV = 0, JXF_SOLVER_FLUX_SPLITTING = 1 };
+enum { JXF_FS_ROE = 1, JXF_FS_CLLF = 2, JXF_FS_LLF = 3 };
 /* ref: time_integration/__init__.py:6-11 */
 enum { JXF_INT_EULER = 0, JXF_INT_RK2 = 1, JXF_INT_RK3 = 2, JXF_INT_RK2_LS4 = 3 /* RK2_LS4.py: 4 stages */ };
 /* ref: halos/outer/__init__.py:1-7; NEIGHBOR = face owned by another rank (halos/inner/material.py:30-93) */
@@ -97,6 +100,12 @@ typedef struct jxf_config {
    * step from the device scalar of jxf_stage / jxf_step_fused; jxf_sweep / jxf_compute_rhs use jxf_bind_timestep. */
   int32_t flux_limiter;             /* JXF_FLUXLIM_*                                              */
   int32_t flux_partition;           /* JXF_PARTITION_*                                            */
+  /* ref: conservatives/convective_fluxes/convective_solver (solvers/convective_fluxes/__init__.py:7-12).  With
+   * JXF_SOLVER_FLUX_SPLITTING (flux_splitting_scheme.py:62-111) `stencil` is flux_splitting/reconstruction_stencil,
+   * `flux_splitting` the eigenvalue choice (eigendecomposition.py:664-689), the frozen state is ARITHMETIC; recon,
+   * riemann, signal_speed and the positivity limiters are not read. */
+  int32_t convective_solver;        /* JXF_SOLVER_*                                               */
+  int32_t flux_splitting;           /* JXF_FS_*                                                   */
 } jxf_config;
 
 enum { JXF_FLUXLIM_NONE = 0, JXF_FLUXLIM_SIMPLE = 1, JXF_FLUXLIM_NASA = 2 };

@@ -29,6 +29,8 @@ FLUX_LIMITER = {None: 0, False: 0, "SIMPLE": 1, "NASA": 2}
 FLUX_PARTITION = {"UNIFORM": 0, "CELLSIZE": 1}
 RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2, "HLLC-LM": 3, "AUSMP": 4}
 SIGNAL = {"EINFELDT": 0, "ARITHMETIC": 1, "RUSANOV": 2, "DAVIS": 3, "TORO": 4}
+CONVECTIVE_SOLVER = {"GODUNOV": 0, "FLUX-SPLITTING": 1}
+FLUX_SPLITTING = {"ROE": 1, "CLLF": 2, "LLF": 3}
 INTEGRATOR = {"EULER": 0, "RK2": 1, "RK3": 2, "RK2_LS4": 3}
 BC = {"INACTIVE": 0, "PERIODIC": 1, "SYMMETRY": 2, "ZEROGRADIENT": 3, "NEIGHBOR": 4, "WALL": 5, "DIRICHLET": 6}
 FACES = ("east", "west", "north", "south", "top", "bottom")
@@ -65,6 +67,8 @@ class JxfConfig(C.Structure):
         ("gravity", C.c_double * 3),
         ("flux_limiter", C.c_int32),
         ("flux_partition", C.c_int32),
+        ("convective_solver", C.c_int32),
+        ("flux_splitting", C.c_int32),
     ]
 
 

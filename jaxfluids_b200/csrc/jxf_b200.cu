@@ -1184,6 +1184,14 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
   if (cfg->signal_speed < JXF_SIGNAL_EINFELDT || cfg->signal_speed > JXF_SIGNAL_TORO)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
+  if (cfg->convective_solver != JXF_SOLVER_GODUNOV && cfg->convective_solver != JXF_SOLVER_FLUX_SPLITTING)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: convective_solver id %d not implemented on the B200 path", cfg->convective_solver);
+  if (cfg->convective_solver == JXF_SOLVER_FLUX_SPLITTING) {
+    if (cfg->flux_splitting < JXF_FS_ROE || cfg->flux_splitting > JXF_FS_LLF)
+      return fail(JXF_ERR_UNSUPPORTED, "jxf_create: flux_splitting id %d not implemented on the B200 path", cfg->flux_splitting);
+    if (cfg->flux_limiter != 0)
+      return fail(JXF_ERR_UNSUPPORTED, "jxf_create: the positivity flux limiter is not implemented with FLUX-SPLITTING");
+  }
   if (cfg->integrator < JXF_INT_EULER || cfg->integrator > JXF_INT_RK2_LS4)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: integrator id %d not implemented on the B200 path", cfg->integrator);
   if (!(cfg->gamma > 1.0)) return fail(JXF_ERR_BAD_ARG, "jxf_create: gamma=%g", cfg->gamma);
@@ -1535,6 +1543,8 @@ static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cuda
     return fail(JXF_ERR_UNSUPPORTED, "tuning build: WENO5-Z CHAR-PRIMITIVE only");
   return dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
 #else
+  // FLUX-SPLITTING: a run-time branch of the generic instantiations' face flux (numerics.cuh flux_splitting_flux)
+  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING) return dispatch_epi<A, 4, RIEMANN_RUSANOV>(s, a, epi, st);
   // every stencil other than the two tuned WENO5 forms runs in the STENCIL_GENERIC instantiations (RECON 4 / 5),
   // selected at run time by bits 11-14 of the option word (base_args)
   switch (s->cfg.recon + 2 * std::min(s->cfg.stencil, (int)STENCIL_GENERIC)) {
@@ -1570,6 +1580,8 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
                 : s->cfg.riemann == JXF_RIEMANN_AUSMP ? RIEMANN_ALT_AUSMP : 0) << 15) |
               (s->cfg.flux_limiter << 9) |
               ((s->cfg.stencil >= JXF_STENCIL_WENO1 ? s->cfg.stencil : 0) << 11);   // generic stencil id (numerics.cuh ALT_*)
+  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING)       // stencil id (all sixteen) | eigenvalue choice << 17
+    a.limiter = (s->cfg.stencil << 11) | (s->cfg.flux_splitting << 17);
   // positivity flux limiter: lambda = dt / dx * sigma (limiter_flux.py:202-205, compute_partition :681-720)
   a.fl.dt = s->dt_bound;
   a.fl.inv_dx = s->cfg.inv_dx[axis];

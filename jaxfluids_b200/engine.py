@@ -54,6 +54,8 @@ class BlockConfig:
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     is_convective_flux: bool = True
+    convective_solver: str = "GODUNOV"                 # or FLUX-SPLITTING (then `stencil` is the flux_splitting block's)
+    flux_splitting: str = "ROE"                        # flux_splitting/flux_splitting: ROE | CLLF | LLF
 
     @property
     def is_dissipative(self) -> bool:
@@ -91,6 +93,8 @@ class BlockConfig:
         c.riemann = lookup(_lib.RIEMANN, self.riemann, "riemann_solver")
         c.signal_speed = lookup(_lib.SIGNAL, self.signal_speed, "signal_speed")
         c.integrator = lookup(_lib.INTEGRATOR, self.integrator, "integrator")
+        c.convective_solver = lookup(_lib.CONVECTIVE_SOLVER, self.convective_solver, "convective_solver")
+        c.flux_splitting = lookup(_lib.FLUX_SPLITTING, self.flux_splitting, "flux_splitting")
         for k, f in enumerate(FACES):
             c.bc[k] = lookup(_lib.BC, self.bc[f], f"boundary condition type at {f}")
         c.viscous_flux = int(bool(self.is_viscous_flux))

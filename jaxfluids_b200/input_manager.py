@@ -82,9 +82,19 @@ class HighOrderGodunovSetup(NamedTuple):
     frozen_state: str
 
 
+class FluxSplittingSetup(NamedTuple):
+    """data_types/numerical_setup/conservatives.py:44-48."""
+    flux_splitting: str
+    reconstruction_stencil: str
+    split_reconstruction: Any = None
+    frozen_state: str = "ARITHMETIC"
+
+
 class ConvectiveFluxesSetup(NamedTuple):
+    """data_types/numerical_setup/conservatives.py:62-67 (the block of the selected solver is set, like the reference)."""
     convective_solver: str
-    godunov: HighOrderGodunovSetup
+    godunov: Optional[HighOrderGodunovSetup] = None
+    flux_splitting: Optional[FluxSplittingSetup] = None
 
 
 class DissipativeFluxesSetup(NamedTuple):
@@ -263,6 +273,8 @@ class InputManager:
                                  True, "GODUNOV")
         solver = R.select(solver, R.REFERENCE_CONVECTIVE_SOLVERS, R.DICT_CONVECTIVE_SOLVER,
                           "conservatives/convective_fluxes/convective_solver")
+        if solver == "FLUX-SPLITTING":
+            return InputManager._read_flux_splitting_setup(d, cons_d, cf_d, nh, integ, cfl, fixed)
         base = "conservatives/convective_fluxes/godunov"
         g_d = get_setup_value(cf_d, "godunov", base, dict, False)
         riemann = get_setup_value(g_d, "riemann_solver", base + "/riemann_solver", str, False)
@@ -277,6 +289,16 @@ class InputManager:
                            base + "/reconstruction_stencil")
         frozen = get_setup_value(g_d, "frozen_state", base + "/frozen_state", str, True, "ARITHMETIC")
         frozen = R.select(frozen, R.REFERENCE_FROZEN_STATES, R.TUPLE_FROZEN_STATE, base + "/frozen_state")
+        InputManager._check_halos(stencil, nh)
+        dissipative, positivity, active_physics, precision, logging_setup = InputManager._read_common_blocks(d, cons_d)
+        return NumericalSetup(
+            ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
+                               ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen)),
+                               dissipative, positivity),
+            active_physics, precision, OutputSetup(logging_setup))
+
+    @staticmethod
+    def _check_halos(stencil, nh):
         # read_conservatives.py:361-365
         req = R.REQUIRED_HALOS[stencil]
         _assert(nh >= req, f"Reconstruction stencil {stencil} requires at least {req} halo cells, "
@@ -285,6 +307,34 @@ class InputManager:
             raise NotImplementedError(f"conservatives/halo_cells = {nh} is valid for {stencil} in JAX-Fluids, but the "
                                       f"B200 sweep kernels stage {R.KERNEL_HALOS} cells on either side of a face: "
                                       f"halo_cells >= {R.KERNEL_HALOS} is required on the B200 path")
+
+    @staticmethod
+    def _read_flux_splitting_setup(d, cons_d, cf_d, nh, integ, cfl, fixed):
+        """read_conservatives.py:205-244 (read_flux_splitting): convective_solver = FLUX-SPLITTING."""
+        base = "conservatives/convective_fluxes/flux_splitting"
+        fs_d = get_setup_value(cf_d, "flux_splitting", base, dict, False)
+        fs = get_setup_value(fs_d, "flux_splitting", base + "/flux_splitting", str, False)
+        fs = R.select(fs, R.REFERENCE_FLUX_SPLITTING, R.TUPLE_FLUX_SPLITTING, base + "/flux_splitting")
+        stencil = get_setup_value(fs_d, "reconstruction_stencil", base + "/reconstruction_stencil", str, False)
+        stencil = R.select(stencil, R.REFERENCE_RECONSTRUCTION_STENCILS + ("SPLIT-RECONSTRUCTION",),
+                           R.DICT_SPATIAL_RECONSTRUCTION, base + "/reconstruction_stencil")
+        frozen = get_setup_value(fs_d, "frozen_state", base + "/frozen_state", str, True, "ARITHMETIC")
+        frozen = R.select(frozen, R.REFERENCE_FROZEN_STATES, R.TUPLE_FROZEN_STATE, base + "/frozen_state")
+        InputManager._check_halos(stencil, nh)
+        dissipative, positivity, active_physics, precision, logging_setup = InputManager._read_common_blocks(d, cons_d)
+        if positivity.flux_limiter:
+            raise NotImplementedError("conservatives/positivity/flux_limiter with convective_solver = FLUX-SPLITTING is "
+                                      "not implemented on the B200 path")
+        return NumericalSetup(
+            ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
+                               ConvectiveFluxesSetup("FLUX-SPLITTING", None, FluxSplittingSetup(fs, stencil, None, frozen)),
+                               dissipative, positivity),
+            active_physics, precision, OutputSetup(logging_setup))
+
+    @staticmethod
+    def _read_common_blocks(d, cons_d):
+        """positivity, active_physics, dissipative_fluxes, precision, output/logging -- the blocks every convective
+        solver shares."""
         pos_d = cons_d.get("positivity", {}) or {}
         for k, v in pos_d.items():
             if k.startswith("is_") and v and k != "is_interpolation_limiter":
@@ -362,11 +412,7 @@ class InputManager:
             is_positivity=bool(get_setup_value(log_d, "is_positivity", "output/logging/is_positivity", bool, True, True)),
             is_only_last_stage=bool(get_setup_value(log_d, "is_only_last_stage", "output/logging/is_only_last_stage",
                                                     bool, True, True)))
-        return NumericalSetup(
-            ConservativesSetup(nh, TimeIntegrationSetup(integ, cfl, fixed),
-                               ConvectiveFluxesSetup(solver, HighOrderGodunovSetup(riemann, sig, stencil, rv, frozen)),
-                               dissipative, positivity),
-            active_physics, precision, OutputSetup(logging_setup))
+        return dissipative, positivity, active_physics, precision, logging_setup
 
     # -- case setup ----------------------------------------------------------
     @staticmethod

@@ -36,7 +36,10 @@ REFERENCE_BOUNDARY_TYPES = (
     "ISOTHERMALOPPOSITIONCONTROLWALL")
 
 # what the sm_100a kernels implement
-DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov"}
+DICT_CONVECTIVE_SOLVER = {"GODUNOV": "HighOrderGodunov", "FLUX-SPLITTING": "FluxSplittingScheme"}
+REFERENCE_FLUX_SPLITTING = ("ROE", "CLLF", "LLF", "CLF")     # solvers/__init__.py:1-3
+# "CLF" passes the reference's input check but no branch of eigendecomposition.py:664-703 handles it (it raises there)
+TUPLE_FLUX_SPLITTING = ("ROE", "CLLF", "LLF")
 # HLLC is the tuned kernel; the others ride on the RUSANOV kernel instantiations (run-time variants).  Not
 # implemented: LAX-FRIEDRICHS (a global max over all faces before every sweep), CATUM, HLLC_SIMPLEALPHA (its
 # single-phase branch raises NotImplementedError in the reference itself)

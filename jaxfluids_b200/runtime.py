@@ -41,7 +41,8 @@ class BlockRuntime:
         di = input_manager.domain_information
         num = input_manager.numerical_setup
         case = input_manager.case_setup
-        god = num.conservatives.convective_fluxes.godunov
+        cf = num.conservatives.convective_fluxes
+        god, fs = cf.godunov, cf.flux_splitting
         ti = num.conservatives.time_integration
         self.parallel = parallel
         self.domain_information = di
@@ -55,10 +56,12 @@ class BlockRuntime:
             gamma=case.material_setup.specific_heat_ratio,
             bc=self.bc_block,
             nh=di.nh_conservatives,
-            recon=god.reconstruction_variable,
-            stencil=god.reconstruction_stencil,
-            riemann=god.riemann_solver,
-            signal_speed=god.signal_speed,
+            convective_solver=cf.convective_solver,
+            flux_splitting=fs.flux_splitting if fs is not None else "ROE",
+            recon=god.reconstruction_variable if god is not None else "CHAR-PRIMITIVE",
+            stencil=god.reconstruction_stencil if god is not None else fs.reconstruction_stencil,
+            riemann=god.riemann_solver if god is not None else "HLLC",
+            signal_speed=god.signal_speed if god is not None else "EINFELDT",
             integrator=ti.integrator,
             cfl=ti.CFL,
             fixed_dt=float(ti.fixed_timestep) if ti.fixed_timestep else 0.0,

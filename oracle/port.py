@@ -54,6 +54,7 @@ class Setup:
     riemann: str = "HLLC"                        # or RUSANOV
     signal_speed: str = "EINFELDT"               # HLLC wave-speed estimate: EINFELDT | ARITHMETIC | RUSANOV | DAVIS | TORO
     integrator: str = "RK3"
+    frozen_state: str = "ARITHMETIC"             # godunov/frozen_state or flux_splitting/frozen_state: ARITHMETIC | ROE
     convective_solver: str = "GODUNOV"           # or FLUX-SPLITTING (convective_fluxes/flux_splitting block)
     flux_splitting: str = "ROE"                  # flux_splitting/flux_splitting: ROE | CLLF | LLF (eigenvalue choice)
     cfl: float = 0.5
@@ -532,12 +533,26 @@ def _window(prims, axis, s: Setup):
 # --------------------------------------------------------------------------
 # reconstruction
 # --------------------------------------------------------------------------
-def reconstruct(prims, axis, s: Setup):
-    """high_order_godunov.py:233-419 (PRIMITIVE :267-280, CHAR-PRIMITIVE :298-316,:401-402).
-    Returns (prims_L, prims_R, cons_L, cons_R), each (5, faces...)."""
+def reconstruct(prims, axis, s: Setup, cons=None):
+    """high_order_godunov.py:233-419 (PRIMITIVE :267-280, CONSERVATIVE :282-296, CHAR-PRIMITIVE :298-316,:401-402,
+    CHAR-CONSERVATIVE :404-417).  Returns (prims_L, prims_R, cons_L, cons_R), each (5, faces...).  The two
+    conservative forms read the conservative buffer (`cons`; formed from the primitives when not given)."""
     w = _window(prims, axis, s)
     stencil = STENCILS[s.stencil]                # the stencil the JSON names
-    if s.recon == "PRIMITIVE":
+    cl = cr = None
+    if s.recon in ("CONSERVATIVE", "CHAR-CONSERVATIVE"):
+        wc = _window(cons_from_prims(prims, s.gamma) if cons is None else cons, axis, s)
+        if s.recon == "CONSERVATIVE":
+            cl = stencil(wc, 0)
+            cr = stencil(wc[::-1], 1)
+        else:
+            # eigendecomposition.py:576-715 at the frozen state of the face, transformtochar / transformtophysical :717-743
+            Rm, Lm, _ = conservative_eigensystem(w[2], w[3], axis, s.gamma, None, s.frozen_state)
+            chars = [_matvec(Lm, x) for x in wc]
+            cl = _matvec(Rm, stencil(chars, 0))
+            cr = _matvec(Rm, stencil(chars[::-1], 1))
+        pl, pr = prims_from_cons(cl, s.gamma), prims_from_cons(cr, s.gamma)
+    elif s.recon == "PRIMITIVE":
         pl = stencil(w, 0)
         pr = stencil(w[::-1], 1)
     elif s.recon == "CHAR-PRIMITIVE":
@@ -547,10 +562,8 @@ def reconstruct(prims, axis, s: Setup):
         # rows the tangential velocities occupy in characteristic space
         # (eigendecomposition.py:69-73): axis0 -> (2,3); axis1 -> (3,2); axis2 -> (2,3)
         e0, e1 = ((2, 3), (3, 2), (2, 3))[axis]
-        # frozen state, arithmetic mean of cells i and i+1 (eigendecomposition.py:139-148, 215-231)
-        ave = 0.5 * (w[2] + w[3])
-        c_ave = np.sqrt(g * ave[4] / ave[0])
-        cc_ave = c_ave * c_ave
+        # frozen state of the face from cells i and i+1 (eigendecomposition.py:139-148, 215-231; ROE :233-276)
+        ave, _, _, c_ave, cc_ave, _ = frozen_state(w[2], w[3], g, s.frozen_state)
         rho_ave = ave[0]
         # to characteristic variables (eigendecomposition.py:425-431)
         chars = []
@@ -562,11 +575,11 @@ def reconstruct(prims, axis, s: Setup):
             o[e1] = x[m1]
             o[4] = 0.5 / c_ave * x[ua] + 0.5 / (cc_ave * rho_ave) * x[4]
             chars.append(np.stack(o, axis=0))
-        cl = stencil(chars, 0)
-        cr = stencil(chars[::-1], 1)
+        char_l = stencil(chars, 0)
+        char_r = stencil(chars[::-1], 1)
         # back to primitives (eigendecomposition.py:517-521)
         res = []
-        for x in (cl, cr):
+        for x in (char_l, char_r):
             o = [None] * 5
             o[0] = rho_ave * (x[0] + x[4]) + x[1]
             o[ua] = c_ave * (-x[0] + x[4])
@@ -577,10 +590,13 @@ def reconstruct(prims, axis, s: Setup):
         pl, pr = res
     else:
         raise NotImplementedError(s.recon)
-    if s.is_interpolation_limiter:               # high_order_godunov.py:163-174
+    if s.is_interpolation_limiter:               # high_order_godunov.py:163-174 (returns the conservatives of the limited state)
         pl = _limit_interpolation(pl, w[2], s)   # WENO1 left state = cell i
         pr = _limit_interpolation(pr, w[3], s)   # WENO1 right state = cell i+1
-    return pl, pr, cons_from_prims(pl, s.gamma), cons_from_prims(pr, s.gamma)
+        cl = cr = None
+    if cl is None:
+        cl, cr = cons_from_prims(pl, s.gamma), cons_from_prims(pr, s.gamma)
+    return pl, pr, cl, cr
 
 
 INTERPOLATION_LIMITER_EPS = (1e-12, 1e-10)       # config/precision.py:54 (density, pressure), fp64
@@ -933,6 +949,37 @@ def flux_limiter(F, prims, cons, dt, axis, s: Setup):
     return theta * F_pos + (1 - theta) * F
 
 
+def frozen_state(pL, pR, gamma, kind="ARITHMETIC"):
+    """eigendecomposition.py:120-281 (single phase, ideal gas): (primes_ave, enthalpy_ave, grueneisen_ave, c_ave, cc_ave,
+    velocity_square) at the face between the cells with primitives pL, pR."""
+    def total_enthalpy(p):                                                     # ideal_gas.py:90-110
+        E = p[4] / (gamma - 1) + 0.5 * p[0] * (np.square(p[1]) + np.square(p[2]) + np.square(p[3]))
+        return (E + p[4]) / p[0]
+    if kind == "ARITHMETIC":                                                   # :146-231
+        ave = 0.5 * (pL + pR)
+        G = (gamma - 1) * np.ones_like(ave[0])                                 # get_grueneisen, ideal_gas.py:65-67
+        H = total_enthalpy(ave)
+        c = np.sqrt(gamma * ave[4] / ave[0])
+        cc = c * c
+        q2 = np.sum(np.square(ave[1:4]), axis=0)
+    elif kind == "ROE":                                                        # :233-276, compute_roe_cons :283-294
+        ave = (np.sqrt(pL[0]) * pL + np.sqrt(pR[0]) * pR) / (np.sqrt(pL[0]) + np.sqrt(pR[0]))
+        ave[0] = np.sqrt(pL[0] * pR[0])
+        sL, sR = np.sqrt(pL[0]), np.sqrt(pR[0])
+        rho_div = 1.0 / (sL + sR)
+        H = (sL * total_enthalpy(pL) + sR * total_enthalpy(pR)) * rho_div
+        psi = (sL * (pL[4] / pL[0]) + sR * (pR[4] / pR[0])) * rho_div          # get_psi, ideal_gas.py:61-63
+        G = (sL * (gamma - 1) + sR * (gamma - 1)) * rho_div
+        dq2 = np.sum(np.square(pR[1:4] - pL[1:4]), axis=0)
+        p_over_rho = (sL * pL[4] / pL[0] + sR * pR[4] / pR[0]) * rho_div + 0.5 * ave[0] * rho_div * rho_div * dq2
+        q2 = np.sum(np.square(ave[1:4]), axis=0)
+        cc = psi + G * p_over_rho
+        c = np.sqrt(cc)
+    else:
+        raise NotImplementedError(kind)
+    return ave, H, G, c, cc, q2
+
+
 def _matvec(M, x):
     """jnp.einsum("ij...,j...->i...", M, x) (eigendecomposition.py:717-743) with the sum over j taken in order."""
     out = []
@@ -944,19 +991,13 @@ def _matvec(M, x):
     return np.stack(out, axis=0)
 
 
-def conservative_eigensystem(pL, pR, axis, gamma, flux_splitting=None):
-    """eigendecomposition.py:576-715 with the ARITHMETIC frozen state of :146-231 (single phase, ideal gas): right and
+def conservative_eigensystem(pL, pR, axis, gamma, flux_splitting=None, frozen="ARITHMETIC"):
+    """eigendecomposition.py:576-715 at the frozen state of :120-281 (single phase, ideal gas): right and
     left eigenvectors of the conservative flux Jacobian after Fedkiw et al. 1999 as 5x5 nested lists of face arrays,
     and -- for the flux-splitting scheme -- the eigenvalue magnitudes (ROE :668-671, CLLF :674-681, LLF :684-689)."""
     ua = 1 + axis
     m0, m1 = MINOR_AXES[axis]
-    ave = 0.5 * (pL + pR)
-    G = (gamma - 1) * np.ones_like(ave[0])                                     # get_grueneisen, ideal_gas.py:65-67
-    E = ave[4] / (gamma - 1) + 0.5 * ave[0] * (np.square(ave[1]) + np.square(ave[2]) + np.square(ave[3]))
-    H = (E + ave[4]) / ave[0]                                                  # ideal_gas.py:90-110
-    c = np.sqrt(gamma * ave[4] / ave[0])
-    cc = c * c
-    q2 = np.sum(np.square(ave[1:4]), axis=0)
+    ave, H, G, c, cc, q2 = frozen_state(pL, pR, gamma, frozen)
     one_cc = 1.0 / cc
     one_rho = 1.0 / ave[0]
     Z = np.zeros_like(ave[0])
@@ -1022,7 +1063,7 @@ def flux_splitting_face_flux(prims, cons, axis, s: Setup):
     the right (j = 1), summed and transformed back."""
     wp = _window(prims, axis, s)
     wc = _window(cons, axis, s)
-    Rm, Lm, lam = conservative_eigensystem(wp[2], wp[3], axis, s.gamma, s.flux_splitting)
+    Rm, Lm, lam = conservative_eigensystem(wp[2], wp[3], axis, s.gamma, s.flux_splitting, s.frozen_state)
     lam5 = (lam[0], lam[1], lam[1], lam[1], lam[2])
     pos, neg = [], []
     for p, c in zip(wp, wc):
@@ -1042,7 +1083,7 @@ def face_flux(prims, axis, s: Setup, cons=None, dt=None):
     if s.convective_solver == "FLUX-SPLITTING":
         cons = cons_from_prims(prims, s.gamma) if cons is None else cons
         return flux_splitting_face_flux(prims, cons, axis, s)
-    pl, pr, cl, cr = reconstruct(prims, axis, s)
+    pl, pr, cl, cr = reconstruct(prims, axis, s, cons)
     if s.riemann == "HLLC":
         F = hllc(pl, pr, cl, cr, axis, s.gamma, s.signal_speed)
     elif s.riemann == "RUSANOV":

@@ -75,6 +75,13 @@ FIXTURES = {
     "generic/tgv_10x8x12_per_minmod_char_hllc_rk2ls4": ("tgv", dict(cells=(10, 8, 12), bc="PERIODIC", stencil="MINMOD",
                                                             integrator="RK2_LS4"), 2, (2,)),
     "generic/riemann2d_16x20_teno6_char_hllc_rk3": ("riemann2d", dict(cells=(16, 20, None), stencil="TENO6"), 3, (3,)),
+    # convective_solver = FLUX-SPLITTING (flux_splitting_scheme.py): the shipped Lax and Woodward-Colella examples,
+    # shrunk, and 2-D / 3-D variants with the other eigenvalue choices
+    "generic/lax100_fs_roe_weno6cu_rk3": ("lax", dict(cells=(100, None, None)), 20, (20,)),
+    "generic/woodward200_fs_roe_weno5z_rk3": ("woodward", dict(cells=(200, None, None)), 30, (30,)),
+    "generic/riemann2d_16x20_fs_cllf_teno5_rk3": ("riemann2d", dict(cells=(16, 20, None), flux_splitting="CLLF",
+                                                                    stencil="TENO5"), 3, (3,)),
+    "generic/tgv_10x8x12_fs_llf_weno5js_rk3": ("tgv", dict(cells=(10, 8, 12), flux_splitting="LLF", stencil="WENO5-JS"), 2, (2,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

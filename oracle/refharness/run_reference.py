@@ -50,6 +50,8 @@ CASES = {
     "rti": ("examples_2D/04_rayleigh_taylor_instability", "rti.json"),           # DIRICHLET N/S, gravity, limiter
     "heat1d": ("examples_1D/08_heat_equation", "heat_equation.json"),            # heat flux only (no convective flux)
     "rarefaction": ("examples_1D/04_double_rarefaction", "double_rarefaction.json"),  # flux limiter SIMPLE + interp. limiter
+    "lax": ("examples_1D/03_lax_shock_tube", "lax.json"),                             # FLUX-SPLITTING ROE + WENO6-CU
+    "woodward": ("examples_1D/06_woodward_shock_tube", "woodward_shock_tube.json"),   # FLUX-SPLITTING ROE + WENO5-Z, SYMMETRY
 }
 
 
@@ -64,7 +66,7 @@ def load_case(name: str):
 
 
 def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None,
-              signal_speed=None, positivity=None, initial_condition=None, flux_splitting=None):
+              signal_speed=None, positivity=None, initial_condition=None, flux_splitting=None, frozen_state=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -92,6 +94,8 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         g["reconstruction_stencil"] = stencil
     if signal_speed is not None:
         g["signal_speed"] = signal_speed
+    if frozen_state is not None:             # of the block the selected solver reads
+        (cf["flux_splitting"] if cf.get("convective_solver") == "FLUX-SPLITTING" else g)["frozen_state"] = frozen_state
     if integrator is not None:
         num["conservatives"]["time_integration"]["integrator"] = integrator
     if positivity is not None:

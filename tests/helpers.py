@@ -70,6 +70,7 @@ def setup_from_json(case, num) -> port.Setup:
         g = dict(g, reconstruction_stencil=fs.get("reconstruction_stencil", "WENO5-Z"))
     return port.Setup(
         convective_solver=solver, flux_splitting=fs.get("flux_splitting", "ROE"),
+        frozen_state=(fs if solver == "FLUX-SPLITTING" else g).get("frozen_state", "ARITHMETIC"),
         cells=tuple(d[a]["cells"] for a in "xyz"),
         domain=tuple(tuple(d[a]["range"]) for a in "xyz"),
         bc={f: case["boundary_conditions"][f]["type"] for f in port.FACES},

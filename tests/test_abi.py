@@ -70,7 +70,7 @@ def test_create_destroy_and_sizes(built_library):
     (dict(recon=3), -2, "reconstruction_variable"),
     (dict(riemann=5), -2, "riemann_solver"),
     (dict(sig=9), -2, "signal_speed"),
-    (dict(integ=3), -2, "integrator"),
+    (dict(integ=4), -2, "integrator"),
     (dict(bc=[7] * 6), -2, "boundary type"),
     (dict(gamma=0.9), -1, "gamma"),
     (dict(n=(16, 16, 16), bc=[1, 1, 1, 1, 0, 0]), -1, "INACTIVE"),

@@ -211,3 +211,22 @@ def test_hllclm_and_ausmp_host_simulated(riemann, sig):
             assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)
             assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
             assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+
+
+@pytest.mark.parametrize("fs,stencil", [("ROE", "WENO5-Z"), ("CLLF", "WENO6-CU"), ("LLF", "WENO5-JS"), ("ROE", "TENO5"),
+                                        ("CLLF", "WENO3-Z"), ("LLF", "VANLEER")])
+def test_flux_splitting_host_simulated(fs, stencil):
+    """convective_solver = FLUX-SPLITTING (flux_splitting_scheme.py): flux_splitting_flux (numerics.cuh) without FMA
+    bit-identical to the pinned oracle, with FMA within 1e-12 (face_flux and the marching form), every axis, sub- and
+    supersonic states; the stencil ids of the two tuned WENO5 forms included (reference-order forms in the generic
+    function)."""
+    for cells, bc, factor in [((48, 1, 1), "ZEROGRADIENT", 4.0), ((14, 18, 1), "PERIODIC", 1.0), ((8, 10, 12), "SYMMETRY", 1.0)]:
+        s = H.make_setup(cells, bc=bc, stencil=stencil)
+        s.convective_solver, s.flux_splitting = "FLUX-SPLITTING", fs
+        prims, cons = port.initialize(_fast_ic(s, 4, factor), s)
+        scales = H.rhs_scales(prims, s)
+        for a in s.active:
+            ref = port.rhs_axis(prims, a, s)
+            assert np.array_equal(hostsim.rhs_axis(prims, a, s, fma=False, reference_order=True), ref)
+            assert H.rel_linf(hostsim.rhs_axis(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS
+            assert H.rel_linf(hostsim.rhs_axis_march(prims, a, s, fma=True), ref, scale=scales) <= H.TOL_RHS

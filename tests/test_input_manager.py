@@ -74,7 +74,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (GOD + ("reconstruction_stencil",), "TENO6-A"),
     (GOD + ("reconstruction_stencil",), "WENO7-JS"),
     (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
-    (("conservatives", "convective_fluxes", "convective_solver"), "FLUX-SPLITTING"),
+    (("conservatives", "convective_fluxes", "convective_solver"), "ALDM"),
     (("active_physics", "is_geometric_source"), True),
     (("conservatives", "positivity", "flux_limiter"), "HAS"),
     (("conservatives", "positivity", "flux_partition"), "WAVESPEED"),
@@ -189,3 +189,57 @@ def test_decomposition_bookkeeping():
     assert di.block_slices(6) == (slice(32, 64), slice(16, 32), slice(0, 8))
     di1 = DomainInformation((64, 1, 1), ((0, 1),) * 3, (1, 1, 1), 5)
     assert di1.neighbor(0, "east", periodic=True) is None     # unsplit periodic axis is a local BC
+
+
+def test_flux_splitting_block_is_read_like_the_reference():
+    """convective_solver = FLUX-SPLITTING (read_conservatives.py:205-244): the flux_splitting block selects the path, the
+    godunov block is not needed; CLF (accepted by the reference's input check, unhandled by its eigendecomposition)
+    and the ROE frozen state say 'not implemented'."""
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    num = copy.deepcopy(num)
+    cf = num["conservatives"]["convective_fluxes"]
+    cf["convective_solver"] = "FLUX-SPLITTING"
+    cf.pop("godunov")
+    cf["flux_splitting"] = {"flux_splitting": "CLLF", "reconstruction_stencil": "WENO6-CU"}
+    im = InputManager(case, num)
+    c = im.numerical_setup.conservatives.convective_fluxes
+    assert c.convective_solver == "FLUX-SPLITTING" and c.godunov is None
+    assert (c.flux_splitting.flux_splitting, c.flux_splitting.reconstruction_stencil, c.flux_splitting.frozen_state) == \
+        ("CLLF", "WENO6-CU", "ARITHMETIC")
+    for key, value in (("flux_splitting", "CLF"), ("frozen_state", "ROE"), ("reconstruction_stencil", "WENO7-JS")):
+        with pytest.raises(NotImplementedError, match="B200 path"):
+            InputManager(case, _mod(num, ("conservatives", "convective_fluxes", "flux_splitting", key), value))
+    with pytest.raises(AssertionError, match="Consistency error in numerical setup file"):
+        InputManager(case, _mod(num, ("conservatives", "convective_fluxes", "flux_splitting", "flux_splitting"), "HLL"))
+    with pytest.raises(NotImplementedError, match="FLUX-SPLITTING"):
+        InputManager(case, _mod(num, ("conservatives", "positivity", "flux_limiter"), "SIMPLE"))
+
+
+@pytest.mark.parametrize("name,expect", [
+    ("generic/lax100_fs_roe_weno6cu_rk3", dict(convective_solver=1, flux_splitting=1, stencil=6, integrator=2)),
+    ("generic/riemann2d_16x20_fs_cllf_teno5_rk3", dict(convective_solver=1, flux_splitting=2, stencil=5)),
+    ("generic/sod100_teno5_char_hllc_rk2ls4", dict(convective_solver=0, stencil=5, recon=1, riemann=0, integrator=3)),
+    ("generic/riemann2d_20x24_prim_ausmp_rk3", dict(convective_solver=0, stencil=0, recon=0, riemann=4)),
+    ("generic/sod100_char_hllclm_rk3", dict(riemann=3, signal_speed=0)),
+    ("generic/sod100_vanleer_prim_rusanov_rk3", dict(stencil=12, recon=0, riemann=1)),
+    ("sod200_char_hllc_rk3", dict(convective_solver=0, stencil=0, recon=1, riemann=0, integrator=2)),
+])
+def test_json_options_reach_the_c_config(name, expect, monkeypatch):
+    """JSON -> InputManager -> BlockRuntime -> BlockConfig.to_c(): the ids the C ABI receives (include/jxf_b200.h),
+    checked without a GPU by stopping at the solver's construction."""
+    import jaxfluids_b200.runtime as RT
+    from jaxfluids_b200.parallel import ParallelContext
+
+    class Reached(Exception):
+        pass
+
+    def fake_solver(cfg, *a, **k):
+        raise Reached(cfg.to_c())
+    monkeypatch.setattr(RT, "BlockSolver", fake_solver)
+    g, case, num = H.load_golden(name)
+    im = InputManager(case, num)
+    with pytest.raises(Reached) as info:
+        RT.BlockRuntime(im, ParallelContext(im.domain_information))
+    c = info.value.args[0]
+    for key, value in expect.items():
+        assert getattr(c, key) == value, key

@@ -58,6 +58,13 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("sod", dict(cells=(64, None, None), stencil="WENO3-N"), 2),
     ("riemann2d", dict(cells=(16, 16, None), stencil="CENTRAL2", recon="PRIMITIVE"), 1),
     ("tgv", dict(cells=(8, 8, 10), stencil="TENO6"), 1),
+    # convective_solver = FLUX-SPLITTING: the shipped Lax / Woodward-Colella examples and the other eigenvalue choices
+    ("lax", dict(cells=(80, None, None)), 3),
+    ("woodward", dict(cells=(100, None, None)), 3),
+    ("sod", dict(cells=(64, None, None), flux_splitting="CLLF", stencil="WENO6-CU"), 2),
+    ("riemann2d", dict(cells=(16, 20, None), flux_splitting="LLF"), 2),
+    ("tgv", dict(cells=(10, 8, 12), flux_splitting="ROE"), 1),
+    ("tgv", dict(cells=(8, 8, 10), flux_splitting="CLLF", bc="PERIODIC", stencil="TENO5"), 1),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
