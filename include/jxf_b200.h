@@ -31,7 +31,12 @@ typedef enum jxf_status {
 } jxf_status;
 
 /* ref: stencils/__init__.py:15-19 + godunov.reconstruction_variable (read_conservatives.py:126-203) */
-enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1 };
+enum { JXF_RECON_PRIMITIVE = 0, JXF_RECON_CHAR_PRIMITIVE = 1,
+       /* high_order_godunov.py:282-296, :404-417: run in the generic (reference-order) kernel instantiations */
+       JXF_RECON_CONSERVATIVE = 2, JXF_RECON_CHAR_CONSERVATIVE = 3 };
+/* ref: godunov/frozen_state, flux_splitting/frozen_state (solvers/__init__.py:5-7; eigendecomposition.py:146-276);
+ * ROE runs in the generic kernel instantiations */
+enum { JXF_FROZEN_ARITHMETIC = 0, JXF_FROZEN_ROE = 1 };
 /* ref: stencils/reconstruction/shock_capturing/weno/weno5_z.py, weno5_js.py (DICT_SPATIAL_RECONSTRUCTION): the two
  * tuned forms.  Ids >= 2: the other stencils of the reference that fit the kernels' 6-cell window, evaluated in
  * the reference's operation order by one generic set of kernel instantiations (weno/weno1_js.py, weno3_js.py,
@@ -106,6 +111,7 @@ typedef struct jxf_config {
    * riemann, signal_speed and the positivity limiters are not read. */
   int32_t convective_solver;        /* JXF_SOLVER_*                                               */
   int32_t flux_splitting;           /* JXF_FS_*                                                   */
+  int32_t frozen_state;             /* JXF_FROZEN_*: state the characteristic decompositions are frozen at */
 } jxf_config;
 
 enum { JXF_FLUXLIM_NONE = 0, JXF_FLUXLIM_SIMPLE = 1, JXF_FLUXLIM_NASA = 2 };

@@ -20,7 +20,8 @@ EXPORTS = (
     "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature", "jxf_face_slab_elems_ext", "jxf_pack_face_ext", "jxf_unpack_face_ext", "jxf_bind_timestep",
 )
 
-RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}
+RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1, "CONSERVATIVE": 2, "CHAR-CONSERVATIVE": 3}
+FROZEN_STATE = {"ARITHMETIC": 0, "ROE": 1}
 # ids = include/jxf_b200.h JXF_STENCIL_*; >= 2: the generic (reference-order) kernel instantiations
 STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z": 4, "TENO5": 5, "WENO6-CU": 6,
            "KOREN": 7, "MC": 8, "MINMOD": 9, "SUPERBEE": 10, "VANALBADA": 11, "VANLEER": 12, "WENO3-N": 13,
@@ -69,6 +70,7 @@ class JxfConfig(C.Structure):
         ("flux_partition", C.c_int32),
         ("convective_solver", C.c_int32),
         ("flux_splitting", C.c_int32),
+        ("frozen_state", C.c_int32),
     ]
 
 

@@ -1176,7 +1176,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   if (cfg->nh < 3) return fail(JXF_ERR_BAD_ARG, "jxf_create: halo_cells=%d < 3 required by WENO5", cfg->nh);
   for (int i = 0; i < 3; ++i)
     if (cfg->n[i] < 1) return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d", i, cfg->n[i]);
-  if (cfg->recon != JXF_RECON_PRIMITIVE && cfg->recon != JXF_RECON_CHAR_PRIMITIVE)
+  if (cfg->recon < JXF_RECON_PRIMITIVE || cfg->recon > JXF_RECON_CHAR_CONSERVATIVE)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
   if (cfg->stencil < JXF_STENCIL_WENO5Z || cfg->stencil > JXF_STENCIL_TENO6)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
@@ -1184,6 +1184,8 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
   if (cfg->signal_speed < JXF_SIGNAL_EINFELDT || cfg->signal_speed > JXF_SIGNAL_TORO)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: signal_speed id %d not implemented on the B200 path", cfg->signal_speed);
+  if (cfg->frozen_state != JXF_FROZEN_ARITHMETIC && cfg->frozen_state != JXF_FROZEN_ROE)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_create: frozen_state id %d not implemented on the B200 path", cfg->frozen_state);
   if (cfg->convective_solver != JXF_SOLVER_GODUNOV && cfg->convective_solver != JXF_SOLVER_FLUX_SPLITTING)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: convective_solver id %d not implemented on the B200 path", cfg->convective_solver);
   if (cfg->convective_solver == JXF_SOLVER_FLUX_SPLITTING) {
@@ -1521,6 +1523,11 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   return check_launch("sweep");
 }
 
+// Godunov setups the tuned instantiations do not cover (numerics.cuh STENCIL_GENERIC)
+static bool generic_path(const jxf_solver* s) {
+  return s->cfg.stencil >= JXF_STENCIL_WENO1 || s->cfg.recon >= JXF_RECON_CONSERVATIVE || s->cfg.frozen_state == JXF_FROZEN_ROE;
+}
+
 template <int A, int RECON, int RIEMANN>
 static int dispatch_epi(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
   return epi ? launch_sweep<A, RECON, RIEMANN, 1>(s, a, st) : launch_sweep<A, RECON, RIEMANN, 0>(s, a, st);
@@ -1545,15 +1552,14 @@ static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cuda
 #else
   // FLUX-SPLITTING: a run-time branch of the generic instantiations' face flux (numerics.cuh flux_splitting_flux)
   if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING) return dispatch_epi<A, 4, RIEMANN_RUSANOV>(s, a, epi, st);
-  // every stencil other than the two tuned WENO5 forms runs in the STENCIL_GENERIC instantiations (RECON 4 / 5),
-  // selected at run time by bits 11-14 of the option word (base_args)
-  switch (s->cfg.recon + 2 * std::min(s->cfg.stencil, (int)STENCIL_GENERIC)) {
+  // every stencil other than the two tuned WENO5 forms, the conservative reconstruction variables and the ROE frozen
+  // state run in the STENCIL_GENERIC instantiations (RECON 4 / 5), selected at run time by the option word (base_args)
+  if (generic_path(s)) return (s->cfg.recon & 1) ? dispatch_riemann<A, 5>(s, a, epi, st) : dispatch_riemann<A, 4>(s, a, epi, st);
+  switch (s->cfg.recon + 2 * s->cfg.stencil) {
     case 0: return dispatch_riemann<A, 0>(s, a, epi, st);
     case 1: return dispatch_riemann<A, 1>(s, a, epi, st);
     case 2: return dispatch_riemann<A, 2>(s, a, epi, st);
-    case 3: return dispatch_riemann<A, 3>(s, a, epi, st);
-    case 4: return dispatch_riemann<A, 4>(s, a, epi, st);
-    default: return dispatch_riemann<A, 5>(s, a, epi, st);
+    default: return dispatch_riemann<A, 3>(s, a, epi, st);
   }
 #endif
 }
@@ -1579,9 +1585,10 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
               ((s->cfg.riemann == JXF_RIEMANN_HLLCLM ? RIEMANN_ALT_HLLCLM                 // ... and so do HLLC-LM, AUSM+
                 : s->cfg.riemann == JXF_RIEMANN_AUSMP ? RIEMANN_ALT_AUSMP : 0) << 15) |
               (s->cfg.flux_limiter << 9) |
-              ((s->cfg.stencil >= JXF_STENCIL_WENO1 ? s->cfg.stencil : 0) << 11);   // generic stencil id (numerics.cuh ALT_*)
-  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING)       // stencil id (all sixteen) | eigenvalue choice << 17
-    a.limiter = (s->cfg.stencil << 11) | (s->cfg.flux_splitting << 17);
+              // generic instantiations: stencil id (numerics.cuh ALT_*) | reconstruction variable << 19 | ROE << 21
+              (generic_path(s) ? (s->cfg.stencil << 11) | (s->cfg.recon << 19) | (s->cfg.frozen_state << 21) : 0);
+  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING)       // stencil id | eigenvalue choice << 17 | ROE << 21
+    a.limiter = (s->cfg.stencil << 11) | (s->cfg.flux_splitting << 17) | (s->cfg.frozen_state << 21);
   // positivity flux limiter: lambda = dt / dx * sigma (limiter_flux.py:202-205, compute_partition :681-720)
   a.fl.dt = s->dt_bound;
   a.fl.inv_dx = s->cfg.inv_dx[axis];
@@ -2026,7 +2033,7 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   // stencils other than the two WENO5 forms: the generic instantiations + the stencil id in the option word
   const int stencil = recon >> 1;
   if (recon < 0 || stencil > JXF_STENCIL_TENO6) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
-  const int opt = (stencil >= JXF_STENCIL_WENO1 ? stencil : 0) << 11;
+  const int opt = stencil >= JXF_STENCIL_WENO1 ? (stencil << 11) | ((recon & 1) << 19) : 0;
   recon = (recon & 1) + 2 * std::min(stencil, (int)STENCIL_GENERIC);
   (void)opt;
 #define JXF_DBG_CASE(A, R, S)                                                                     \

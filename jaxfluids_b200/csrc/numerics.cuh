@@ -54,7 +54,15 @@ struct Win6 {
   double w[5][6];
 };
 template <int A>
-__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs);             // defined below
+__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs, int roe);    // defined below
+// reconstruction_variable CONSERVATIVE / CHAR-CONSERVATIVE and frozen_state ROE: bits 19-21 of the option word
+// (`mode` = variable | roe << 2), generic instantiations only
+enum { VAR_PRIMITIVE = 0, VAR_CHAR_PRIMITIVE = 1, VAR_CONSERVATIVE = 2, VAR_CHAR_CONSERVATIVE = 3 };
+struct Vec10 {
+  double l[5], r[5];
+};
+template <int A>
+__device__ JXF_NOINLINE Vec10 reconstruct_conservative(Win6 W, double gamma, int id, int mode);      // defined below
 __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
                                                     double rhoR, double pL, double pR, double gamma) {
   double S_L, S_R;
@@ -244,20 +252,71 @@ __device__ __forceinline__ void stencil_generic_lr(int id, const double (&q)[6],
   right = stencil_generic(id, 1, q[5], q[4], q[3], q[2], q[1], q[0]);
 }
 
-// reconstruct() of the generic stencils: PRIMITIVE (high_order_godunov.py:267-280) or CHAR-PRIMITIVE (:298-316 with
-// eigendecomposition.py:139-148, 215-231, 425-431, 517-521), reference order.
+// Frozen state of a face from the primitives of its two cells (eigendecomposition.py:120-281, single phase, ideal
+// gas): ARITHMETIC :146-231 or ROE :233-276 (compute_roe_cons :283-294).  Reference order.
+struct Frozen {
+  double ave[5], H, G, c, cc, q2;
+};
+__device__ __forceinline__ double total_enthalpy_ref(const double (&p)[5], double gamma) {   // ideal_gas.py:90-110
+  const double E = p[4] / (gamma - 1.0) + 0.5 * p[0] * ((p[1] * p[1] + p[2] * p[2]) + p[3] * p[3]);
+  return (E + p[4]) / p[0];
+}
+__device__ __forceinline__ Frozen frozen_state(const double (&pL)[5], const double (&pR)[5], double gamma, int roe) {
+  Frozen f;
+  if (!roe) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) f.ave[v] = 0.5 * (pL[v] + pR[v]);
+    f.G = gamma - 1.0;
+    f.H = total_enthalpy_ref(f.ave, gamma);
+    f.c = sqrt(gamma * f.ave[4] / f.ave[0]);
+    f.cc = f.c * f.c;
+    f.q2 = (f.ave[1] * f.ave[1] + f.ave[2] * f.ave[2]) + f.ave[3] * f.ave[3];
+  } else {
+    const double sL = sqrt(pL[0]), sR = sqrt(pR[0]);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) f.ave[v] = (sL * pL[v] + sR * pR[v]) / (sL + sR);
+    f.ave[0] = sqrt(pL[0] * pR[0]);
+    const double rho_div = 1.0 / (sL + sR);
+    f.H = (sL * total_enthalpy_ref(pL, gamma) + sR * total_enthalpy_ref(pR, gamma)) * rho_div;
+    const double psi = (sL * (pL[4] / pL[0]) + sR * (pR[4] / pR[0])) * rho_div;
+    f.G = (sL * (gamma - 1.0) + sR * (gamma - 1.0)) * rho_div;
+    const double du = pR[1] - pL[1], dv = pR[2] - pL[2], dw = pR[3] - pL[3];
+    const double dq2 = (du * du + dv * dv) + dw * dw;
+    const double p_over_rho = (sL * pL[4] / pL[0] + sR * pR[4] / pR[0]) * rho_div + 0.5 * f.ave[0] * rho_div * rho_div * dq2;
+    f.q2 = (f.ave[1] * f.ave[1] + f.ave[2] * f.ave[2]) + f.ave[3] * f.ave[3];
+    f.cc = psi + f.G * p_over_rho;
+    f.c = sqrt(f.cc);
+  }
+  return f;
+}
+
+// reconstruct() of the generic stencils: PRIMITIVE (high_order_godunov.py:267-280), CHAR-PRIMITIVE (:298-316 with
+// eigendecomposition.py:120-281, 425-431, 517-521) -- or, out of line, the two conservative forms -- reference order.
+// `mode` = reconstruction variable | (frozen_state == ROE) << 2.
 template <int A, bool CHAR>
 __device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                    double (&pr)[5], int id) {
+                                                    double (&pr)[5], int id, int mode) {
   using Id = AxisIds<A>;
-  if (!CHAR) {
+  if ((mode & 3) >= VAR_CONSERVATIVE) {
+    Win6 W;
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) W.w[v][k] = w[v][k];
+    const Vec10 o = reconstruct_conservative<A>(W, gamma, id, mode);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) { pl[v] = o.l[v]; pr[v] = o.r[v]; }
+  } else if (!CHAR) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) stencil_generic_lr(id, w[v], pl[v], pr[v]);
   } else {
-    const double rho_ave = 0.5 * (w[0][2] + w[0][3]);
-    const double p_ave = 0.5 * (w[4][2] + w[4][3]);
-    const double c_ave = sqrt(gamma * p_ave / rho_ave);
-    const double cc_ave = c_ave * c_ave;
+    double cL[5], cR[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) { cL[v] = w[v][2]; cR[v] = w[v][3]; }
+    const Frozen fz = frozen_state(cL, cR, gamma, (mode >> 2) & 1);
+    const double rho_ave = fz.ave[0];
+    const double c_ave = fz.c;
+    const double cc_ave = fz.cc;
     const double k_u = 0.5 / c_ave;
     const double k_p = 0.5 / (cc_ave * rho_ave);
     const double k_cc = 1.0 / cc_ave;
@@ -387,10 +446,10 @@ __device__ __forceinline__ void physical_flux(const double (&p)[5], const double
 // ---------------------------------------------------------------------------
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
-                                            double (&pl)[5], double (&pr)[5], int alt = 0) {
+                                            double (&pl)[5], double (&pr)[5], int alt = 0, int mode = 0) {
   using Id = AxisIds<A>;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
-    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt);
+    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt, mode);
   } else if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) weno5z_lr<(RECON >> 1)>(w[v], pl[v], pr[v]);
@@ -706,10 +765,10 @@ __device__ __forceinline__ void prims_from_cons(const double (&c)[5], double gam
 // ---------------------------------------------------------------------------
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamma,
-                                            double (&pl)[5], double (&pr)[5], int alt = 0) {
+                                            double (&pl)[5], double (&pr)[5], int alt = 0, int mode = 0) {
   using Id = AxisIds<A>;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
-    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt);
+    reconstruct_generic<A, (RECON & 1) != RECON_PRIMITIVE>(w, gamma, pl, pr, alt, mode);
   } else if ((RECON & 1) == RECON_PRIMITIVE) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -797,10 +856,10 @@ __device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconC
 // of this face); on exit those of window cell 3 (right stencil of this face = left stencil of the next)
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                  double (&pr)[5], ReconCarry<RECON>& cy, int alt = 0) {
+                                                  double (&pr)[5], ReconCarry<RECON>& cy, int alt = 0, int mode = 0) {
   using Id = AxisIds<A>;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
-    reconstruct<A, RECON>(w, gamma, pl, pr, alt);
+    reconstruct<A, RECON>(w, gamma, pl, pr, alt, mode);
   } else {
 #pragma unroll
     for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
@@ -1159,26 +1218,15 @@ __device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR
 // of the window cells are formed from the primitives (equation_manager.py:93-101).  Reference order; the matrix
 // products run over all five entries in order, zeros included, like the reference's einsum.
 // ---------------------------------------------------------------------------
+// Right / left eigenvectors of the conservative flux Jacobian at a frozen state (Fedkiw et al. 1999;
+// eigendecomposition.py:590-660), as the reference fills them.
 template <int A>
-__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs) {
+__device__ __forceinline__ void conservative_eigenvectors(const Frozen& fz, double (&R)[5][5], double (&L)[5][5]) {
   using Id = AxisIds<A>;
-  const double (&w)[5][6] = W.w;
-  double ave[5], pL[5], pR[5];
-#pragma unroll
-  for (int v = 0; v < 5; ++v) {
-    pL[v] = w[v][2];
-    pR[v] = w[v][3];
-    ave[v] = 0.5 * (pL[v] + pR[v]);
-  }
-  const double G = gamma - 1.0;
-  const double q2 = (ave[1] * ave[1] + ave[2] * ave[2]) + ave[3] * ave[3];
-  const double E = ave[4] / (gamma - 1.0) + 0.5 * ave[0] * q2;
-  const double H = (E + ave[4]) / ave[0];
-  const double c = sqrt(gamma * ave[4] / ave[0]);
-  const double cc = c * c;
+  const double (&ave)[5] = fz.ave;
+  const double H = fz.H, G = fz.G, c = fz.c, cc = fz.cc, q2 = fz.q2;
   const double one_cc = 1.0 / cc, one_rho = 1.0 / ave[0];
   const int ua = Id::un, m0 = Id::t0, m1 = Id::t1;
-  double R[5][5], L[5][5];
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
@@ -1221,6 +1269,24 @@ __device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, i
   L[4][m0] = 0.5 * one_cc * (-ave[m0] * G);
   L[4][m1] = 0.5 * one_cc * (-ave[m1] * G);
   L[4][4] = 0.5 * one_cc * G;
+}
+
+template <int A>
+__device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, int fs, int roe) {
+  using Id = AxisIds<A>;
+  const double (&w)[5][6] = W.w;
+  double pL[5], pR[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    pL[v] = w[v][2];
+    pR[v] = w[v][3];
+  }
+  const Frozen fz = frozen_state(pL, pR, gamma, roe);
+  const double (&ave)[5] = fz.ave;
+  const double c = fz.c;
+  const int ua = Id::un;
+  double R[5][5], L[5][5];
+  conservative_eigenvectors<A>(fz, R, L);
   double lam[5];
   if (fs == FS_ROE) {
     lam[0] = fabs(ave[ua] - c);
@@ -1278,15 +1344,78 @@ __device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, i
 }
 
 template <int A>
-__device__ __forceinline__ void flux_splitting_face(const double (&w)[5][6], double gamma, double (&F)[5], int id, int fs) {
+__device__ __forceinline__ void flux_splitting_face(const double (&w)[5][6], double gamma, double (&F)[5], int id, int fs,
+                                                    int roe) {
   Win6 W;
 #pragma unroll
   for (int v = 0; v < 5; ++v)
 #pragma unroll
     for (int k = 0; k < 6; ++k) W.w[v][k] = w[v][k];
-  const Vec5 o = flux_splitting_flux<A>(W, gamma, id, fs);
+  const Vec5 o = flux_splitting_flux<A>(W, gamma, id, fs, roe);
 #pragma unroll
   for (int v = 0; v < 5; ++v) F[v] = o.v[v];
+}
+
+// reconstruction_variable CONSERVATIVE (high_order_godunov.py:282-296) and CHAR-CONSERVATIVE (:404-417 with
+// eigendecomposition.py:576-660, transformtochar / transformtophysical :717-743): the conservatives of the window cells
+// (formed from their primitives) are reconstructed as they are, or in the characteristic space of the face's frozen
+// state; the face primitives follow from the reconstructed conservatives (equation_manager.py:164-171).
+template <int A>
+__device__ JXF_NOINLINE Vec10 reconstruct_conservative(Win6 W, double gamma, int id, int mode) {
+  const double (&w)[5][6] = W.w;
+  double u[5][6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double p[5], c[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) p[v] = w[v][k];
+    cons_from_prims(p, gamma, c);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) u[v][k] = c[v];
+  }
+  double cl[5], cr[5];
+  if ((mode & 3) == VAR_CONSERVATIVE) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) stencil_generic_lr(id, u[v], cl[v], cr[v]);
+  } else {
+    double pL[5], pR[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      pL[v] = w[v][2];
+      pR[v] = w[v][3];
+    }
+    const Frozen fz = frozen_state(pL, pR, gamma, (mode >> 2) & 1);
+    double R[5][5], L[5][5];
+    conservative_eigenvectors<A>(fz, R, L);
+    double xl[5], xr[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double ch[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double acc = L[i][0] * u[0][k];
+#pragma unroll
+        for (int v = 1; v < 5; ++v) acc = acc + L[i][v] * u[v][k];
+        ch[k] = acc;
+      }
+      stencil_generic_lr(id, ch, xl[i], xr[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double al = R[i][0] * xl[0], ar = R[i][0] * xr[0];
+#pragma unroll
+      for (int v = 1; v < 5; ++v) {
+        al = al + R[i][v] * xl[v];
+        ar = ar + R[i][v] * xr[v];
+      }
+      cl[i] = al;
+      cr[i] = ar;
+    }
+  }
+  Vec10 o;
+  prims_from_cons(cl, gamma, o.l);
+  prims_from_cons(cr, gamma, o.r);
+  return o;
 }
 
 // Interpolation limiter (solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE; eps from
@@ -1380,12 +1509,12 @@ __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma,
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
-      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3);
+      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3, (opt >> 21) & 1);
       return;
     }
   }
   double pl[5], pr[5];
-  reconstruct<A, RECON>(w, gamma, pl, pr, (opt >> 11) & 15);
+  reconstruct<A, RECON>(w, gamma, pl, pr, (opt >> 11) & 15, (opt >> 19) & 7);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
@@ -1405,8 +1534,8 @@ template <int A, int RECON>
 __device__ __forceinline__ void recon_carry_init(const double (&)[5][6], ReconCarry<RECON>&) {}
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                  double (&pr)[5], ReconCarry<RECON>&, int alt = 0) {
-  reconstruct<A, RECON>(w, gamma, pl, pr, alt);
+                                                  double (&pr)[5], ReconCarry<RECON>&, int alt = 0, int mode = 0) {
+  reconstruct<A, RECON>(w, gamma, pl, pr, alt, mode);
 }
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5], ReconCarry<RECON>&,
@@ -1421,12 +1550,12 @@ __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double 
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
-      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3);
+      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3, (opt >> 21) & 1);
       return;
     }
   }
   double pl[5], pr[5];
-  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy, (opt >> 11) & 15);
+  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy, (opt >> 11) & 15, (opt >> 19) & 7);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
 #if JXF_RIEMANN_MAIN

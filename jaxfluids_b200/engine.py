@@ -56,6 +56,7 @@ class BlockConfig:
     is_convective_flux: bool = True
     convective_solver: str = "GODUNOV"                 # or FLUX-SPLITTING (then `stencil` is the flux_splitting block's)
     flux_splitting: str = "ROE"                        # flux_splitting/flux_splitting: ROE | CLLF | LLF
+    frozen_state: str = "ARITHMETIC"                   # godunov/frozen_state or flux_splitting/frozen_state: ARITHMETIC | ROE
 
     @property
     def is_dissipative(self) -> bool:
@@ -95,6 +96,7 @@ class BlockConfig:
         c.integrator = lookup(_lib.INTEGRATOR, self.integrator, "integrator")
         c.convective_solver = lookup(_lib.CONVECTIVE_SOLVER, self.convective_solver, "convective_solver")
         c.flux_splitting = lookup(_lib.FLUX_SPLITTING, self.flux_splitting, "flux_splitting")
+        c.frozen_state = lookup(_lib.FROZEN_STATE, self.frozen_state, "frozen_state")
         for k, f in enumerate(FACES):
             c.bc[k] = lookup(_lib.BC, self.bc[f], f"boundary condition type at {f}")
         c.viscous_flux = int(bool(self.is_viscous_flux))

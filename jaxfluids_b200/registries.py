@@ -52,8 +52,10 @@ DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS", "WENO
                                "MC": "MC", "MINMOD": "MINMOD", "SUPERBEE": "SUPERBEE", "VANALBADA": "VANALBADA",
                                "VANLEER": "VANLEER", "WENO3-N": "WENO3N",
                                "CENTRAL2": "CentralSecondOrderReconstruction", "TENO6": "TENO6"}
-TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CHAR-PRIMITIVE")
-TUPLE_FROZEN_STATE = ("ARITHMETIC",)
+# PRIMITIVE / CHAR-PRIMITIVE with the ARITHMETIC frozen state are the tuned kernels; the conservative forms and ROE run
+# in the generic (reference-order) instantiations
+TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE")
+TUPLE_FROZEN_STATE = ("ARITHMETIC", "ROE")
 TUPLE_POSITIVITY_FIXES = ("SIMPLE", "NASA")          # HAS is marked "TODO NEEDS UPDATE" upstream (limiter_flux.py:211)
 TUPLE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE")   # WAVESPEED needs a global max per axis before every sweep
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face

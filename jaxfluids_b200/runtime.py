@@ -58,6 +58,7 @@ class BlockRuntime:
             nh=di.nh_conservatives,
             convective_solver=cf.convective_solver,
             flux_splitting=fs.flux_splitting if fs is not None else "ROE",
+            frozen_state=(god if god is not None else fs).frozen_state,
             recon=god.reconstruction_variable if god is not None else "CHAR-PRIMITIVE",
             stencil=god.reconstruction_stencil if god is not None else fs.reconstruction_stencil,
             riemann=god.riemann_solver if god is not None else "HLLC",

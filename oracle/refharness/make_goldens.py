@@ -82,6 +82,13 @@ FIXTURES = {
     "generic/riemann2d_16x20_fs_cllf_teno5_rk3": ("riemann2d", dict(cells=(16, 20, None), flux_splitting="CLLF",
                                                                     stencil="TENO5"), 3, (3,)),
     "generic/tgv_10x8x12_fs_llf_weno5js_rk3": ("tgv", dict(cells=(10, 8, 12), flux_splitting="LLF", stencil="WENO5-JS"), 2, (2,)),
+    # reconstruction_variable CONSERVATIVE / CHAR-CONSERVATIVE and frozen_state ROE
+    "generic/sod100_charcons_roe_hllc_rk3": ("sod", dict(cells=(100, None, None), recon="CHAR-CONSERVATIVE", frozen_state="ROE"), 10, (10,)),
+    "generic/riemann2d_16x20_cons_teno5_hll_rk3": ("riemann2d", dict(cells=(16, 20, None), recon="CONSERVATIVE", stencil="TENO5",
+                                                                     riemann="HLL"), 3, (3,)),
+    "generic/tgv_10x8x12_char_roe_hllc_rk3": ("tgv", dict(cells=(10, 8, 12), frozen_state="ROE"), 2, (2,)),
+    "generic/tgv_8x10x12_per_charcons_hllc_rk3": ("tgv", dict(cells=(8, 10, 12), bc="PERIODIC", recon="CHAR-CONSERVATIVE"), 2, (2,)),
+    "generic/lax100_fs_roe_weno6cu_roefrozen_rk3": ("lax", dict(cells=(100, None, None), frozen_state="ROE"), 10, (10,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

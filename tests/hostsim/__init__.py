@@ -33,11 +33,23 @@ STENCIL_IDS = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z"
                "CENTRAL2": 14, "TENO6": 15}   # JXF_STENCIL_*
 
 
+VARIABLE_IDS = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1, "CONSERVATIVE": 2, "CHAR-CONSERVATIVE": 3}   # JXF_RECON_*
+
+
+def _generic(s):
+    """Whether base_args / dispatch_recon (jxf_b200.cu) route this setup to the generic kernel instantiations."""
+    return (s.convective_solver == "FLUX-SPLITTING" or STENCIL_IDS[s.stencil] >= 2 or VARIABLE_IDS[s.recon] >= 2 or
+            s.frozen_state == "ROE")
+
+
 def _recon_id(s):
     """The kernels' RECON template parameter: variable + 2 * min(stencil, STENCIL_GENERIC) (dispatch_recon)."""
     if s.convective_solver == "FLUX-SPLITTING":          # always the generic instantiation (dispatch_recon)
         return 4
-    return {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1}[s.recon] + 2 * min(STENCIL_IDS[s.stencil], 2)
+    var = VARIABLE_IDS[s.recon]
+    if var >= 2 or s.frozen_state == "ROE":               # the conservative forms / the ROE frozen state: generic too
+        return 4 + (var & 1)
+    return var + 2 * min(STENCIL_IDS[s.stencil], 2)
 
 
 def _opt(s):
@@ -48,10 +60,11 @@ def _opt(s):
     fl = {None: 0, "SIMPLE": 1, "NASA": 2}[s.flux_limiter]
     st = STENCIL_IDS[s.stencil]
     alt = {"HLLC-LM": 1, "AUSMP": 2}.get(s.riemann, 0)              # RIEMANN_ALT_* (ride on the RUSANOV instantiations)
-    if s.convective_solver == "FLUX-SPLITTING":          # stencil id (all of them) + eigenvalue choice
-        return (st << 11) | ({"ROE": 1, "CLLF": 2, "LLF": 3}[s.flux_splitting] << 17)
-    return (lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9) | ((st if st >= 2 else 0) << 11) |
-            (alt << 15))
+    roe = 1 if s.frozen_state == "ROE" else 0
+    if s.convective_solver == "FLUX-SPLITTING":          # stencil id (all of them) + eigenvalue choice + frozen state
+        return (st << 11) | ({"ROE": 1, "CLLF": 2, "LLF": 3}[s.flux_splitting] << 17) | (roe << 21)
+    gen = (st << 11) | (VARIABLE_IDS[s.recon] << 19) | (roe << 21) if _generic(s) else 0
+    return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9) | gen | (alt << 15)
 
 
 def _flux_limiter_args(s, axis, dt):

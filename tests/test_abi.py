@@ -67,7 +67,7 @@ def test_create_destroy_and_sizes(built_library):
 
 @pytest.mark.parametrize("kw,code,frag", [
     (dict(nh=2), -1, "halo_cells"),
-    (dict(recon=3), -2, "reconstruction_variable"),
+    (dict(recon=4), -2, "reconstruction_variable"),
     (dict(riemann=5), -2, "riemann_solver"),
     (dict(sig=9), -2, "signal_speed"),
     (dict(integ=4), -2, "integrator"),

@@ -21,6 +21,7 @@ def make_solver(s: port.Setup, bc=None):
     cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min),
                       gamma=s.gamma, bc=bc or s.bc, nh=s.nh, recon=s.recon, stencil=s.stencil, riemann=s.riemann,
                       signal_speed=s.signal_speed, convective_solver=s.convective_solver, flux_splitting=s.flux_splitting,
+                      frozen_state=s.frozen_state,
                       integrator=s.integrator, cfl=s.cfl,
                       is_viscous_flux=s.is_viscous_flux, is_heat_flux=s.is_heat_flux,
                       is_viscous_heat_production=s.is_viscous_heat_production, dynamic_viscosity=s.dynamic_viscosity,

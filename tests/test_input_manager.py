@@ -73,7 +73,6 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (GOD + ("signal_speed",), "DAVIS2"),
     (GOD + ("reconstruction_stencil",), "TENO6-A"),
     (GOD + ("reconstruction_stencil",), "WENO7-JS"),
-    (GOD + ("reconstruction_variable",), "CHAR-CONSERVATIVE"),
     (("conservatives", "convective_fluxes", "convective_solver"), "ALDM"),
     (("active_physics", "is_geometric_source"), True),
     (("conservatives", "positivity", "flux_limiter"), "HAS"),
@@ -194,7 +193,7 @@ def test_decomposition_bookkeeping():
 def test_flux_splitting_block_is_read_like_the_reference():
     """convective_solver = FLUX-SPLITTING (read_conservatives.py:205-244): the flux_splitting block selects the path, the
     godunov block is not needed; CLF (accepted by the reference's input check, unhandled by its eigendecomposition)
-    and the ROE frozen state say 'not implemented'."""
+    says 'not implemented'."""
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     num = copy.deepcopy(num)
     cf = num["conservatives"]["convective_fluxes"]
@@ -206,7 +205,9 @@ def test_flux_splitting_block_is_read_like_the_reference():
     assert c.convective_solver == "FLUX-SPLITTING" and c.godunov is None
     assert (c.flux_splitting.flux_splitting, c.flux_splitting.reconstruction_stencil, c.flux_splitting.frozen_state) == \
         ("CLLF", "WENO6-CU", "ARITHMETIC")
-    for key, value in (("flux_splitting", "CLF"), ("frozen_state", "ROE"), ("reconstruction_stencil", "WENO7-JS")):
+    roe = InputManager(case, _mod(num, ("conservatives", "convective_fluxes", "flux_splitting", "frozen_state"), "ROE"))
+    assert roe.numerical_setup.conservatives.convective_fluxes.flux_splitting.frozen_state == "ROE"
+    for key, value in (("flux_splitting", "CLF"), ("reconstruction_stencil", "WENO7-JS")):
         with pytest.raises(NotImplementedError, match="B200 path"):
             InputManager(case, _mod(num, ("conservatives", "convective_fluxes", "flux_splitting", key), value))
     with pytest.raises(AssertionError, match="Consistency error in numerical setup file"):
@@ -222,8 +223,12 @@ def test_flux_splitting_block_is_read_like_the_reference():
     ("generic/riemann2d_20x24_prim_ausmp_rk3", dict(convective_solver=0, stencil=0, recon=0, riemann=4)),
     ("generic/sod100_char_hllclm_rk3", dict(riemann=3, signal_speed=0)),
     ("generic/sod100_vanleer_prim_rusanov_rk3", dict(stencil=12, recon=0, riemann=1)),
-    ("sod200_char_hllc_rk3", dict(convective_solver=0, stencil=0, recon=1, riemann=0, integrator=2)),
+    ("sod200_char_hllc_rk3", dict(convective_solver=0, stencil=0, recon=1, riemann=0, integrator=2, frozen_state=0)),
+    ("generic/sod100_charcons_roe_hllc_rk3", dict(recon=3, frozen_state=1, stencil=0)),
+    ("generic/riemann2d_16x20_cons_teno5_hll_rk3", dict(recon=2, frozen_state=0, stencil=5, riemann=2)),
+    ("generic/lax100_fs_roe_weno6cu_roefrozen_rk3", dict(convective_solver=1, flux_splitting=1, stencil=6, frozen_state=1)),
 ])
+
 def test_json_options_reach_the_c_config(name, expect, monkeypatch):
     """JSON -> InputManager -> BlockRuntime -> BlockConfig.to_c(): the ids the C ABI receives (include/jxf_b200.h),
     checked without a GPU by stopping at the solver's construction."""
@@ -243,3 +248,12 @@ def test_json_options_reach_the_c_config(name, expect, monkeypatch):
     c = info.value.args[0]
     for key, value in expect.items():
         assert getattr(c, key) == value, key
+
+
+@pytest.mark.parametrize("variable", ["PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE"])
+@pytest.mark.parametrize("frozen", ["ARITHMETIC", "ROE"])
+def test_every_reconstruction_variable_and_frozen_state_selects_the_path(variable, frozen):
+    case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
+    num = _mod(_mod(num, GOD + ("reconstruction_variable",), variable), GOD + ("frozen_state",), frozen)
+    g = InputManager(case, num).numerical_setup.conservatives.convective_fluxes.godunov
+    assert (g.reconstruction_variable, g.frozen_state) == (variable, frozen)

@@ -65,6 +65,15 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("riemann2d", dict(cells=(16, 20, None), flux_splitting="LLF"), 2),
     ("tgv", dict(cells=(10, 8, 12), flux_splitting="ROE"), 1),
     ("tgv", dict(cells=(8, 8, 10), flux_splitting="CLLF", bc="PERIODIC", stencil="TENO5"), 1),
+    # reconstruction_variable CONSERVATIVE / CHAR-CONSERVATIVE, frozen_state ROE (godunov and flux_splitting blocks)
+    ("sod", dict(cells=(64, None, None), recon="CONSERVATIVE"), 2),
+    ("riemann2d", dict(cells=(16, 20, None), recon="CHAR-CONSERVATIVE", stencil="TENO5", riemann="HLL"), 2),
+    ("tgv", dict(cells=(10, 8, 12), recon="CHAR-CONSERVATIVE"), 1),
+    ("rarefaction", dict(cells=(80, None, None), recon="CHAR-CONSERVATIVE"), 6),
+    ("sod", dict(cells=(64, None, None), frozen_state="ROE"), 2),
+    ("tgv", dict(cells=(10, 8, 12), frozen_state="ROE", recon="CHAR-CONSERVATIVE"), 1),
+    ("riemann2d", dict(cells=(16, 20, None), frozen_state="ROE", flux_splitting="CLLF"), 2),
+    ("lax", dict(cells=(80, None, None), frozen_state="ROE"), 2),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
