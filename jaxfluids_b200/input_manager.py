@@ -193,13 +193,45 @@ class CaseSetup(NamedTuple):
     initial_condition_setup: Dict[str, Any]
     material_setup: MaterialSetup
     wall_velocity_setup: Dict[str, Tuple[float, float, float]] = {}      # WALL faces: constant (u, v, w)
-    dirichlet_setup: Dict[str, Tuple[float, float, float, float, float]] = {}   # DIRICHLET faces: constant prims
+    # DIRICHLET faces: (rho, u, v, w, p), each a float or a lambda string of (active transverse coordinates, t)
+    dirichlet_setup: Dict[str, Tuple[Any, Any, Any, Any, Any]] = {}
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)               # forcings/gravity
 
 
 def _np_namespace():
     """`jnp` as seen by the lambda strings of a case file (setup_reader.py:171): NumPy."""
     return np
+
+
+def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0):
+    """primitives_callable of one DIRICHLET face on this block (halos/outer/material.py:770-790 with
+    boundary_condition.py:105-126): floats stay floats; lambda strings are evaluated on the mesh grid (indexing "ij") of
+    the ACTIVE transverse cell centres and returned shaped like the face's halo slab with extent 1 along the normal and
+    the inactive axes.  Labels must be the active transverse axis names + "t" (read_boundary_conditions.py:156).
+    Time-dependent callables are not implemented on the B200 path (the halo data is set up once)."""
+    di = domain_information
+    ax = FACES.index(face) // 2
+    trans = [i for i in di.active_axes_indices if i != ax]
+    centers = di.get_device_cell_centers(rank)
+    mesh = np.meshgrid(*[np.asarray(centers[i], dtype=np.float64) for i in trans], indexing="ij") if trans else []
+    shape = [di.device_number_of_cells[i] if i in trans else 1 for i in range(3)]
+    labels = tuple(AXES[i] for i in trans) + ("t",)
+    out = []
+    for k, v in zip(("rho", "u", "v", "w", "p"), values):
+        if not isinstance(v, str):
+            out.append(float(v))
+            continue
+        path = f"boundary_conditions/{face}/primitives_callable/{k}"
+        fn = eval(v, {"jnp": _np_namespace(), "np": np})   # noqa: S307 -- same contract as the reference
+        names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
+        _assert(tuple(names) == labels, f"Input argument labels of lambda for {path} must be {labels}.", "case")
+        mshape = mesh[0].shape if mesh else ()
+        a = np.broadcast_to(np.asarray(fn(*mesh, 0.0), dtype=np.float64), mshape).reshape(shape)
+        b = np.broadcast_to(np.asarray(fn(*mesh, 0.7310585786300049), dtype=np.float64), mshape).reshape(shape)
+        if not np.array_equal(a, b, equal_nan=True):
+            raise NotImplementedError(f"{path}: a time-dependent DIRICHLET callable is not implemented on the B200 path")
+        out.append(np.ascontiguousarray(a))
+    return tuple(out)
 
 
 def make_ic_callable(value, labels: Tuple[str, ...], path: str) -> Callable:
@@ -498,10 +530,9 @@ class InputManager:
                 for k in ("rho", "u", "v", "w", "p"):
                     v = get_setup_value(pc_d, k, f"boundary_conditions/{f}/primitives_callable/{k}", (float, str),
                                         False, setup=S)
-                    if isinstance(v, str):
-                        raise NotImplementedError(f"boundary_conditions/{f}/primitives_callable/{k} given as a lambda "
-                                                  "string is not implemented on the B200 path (constant values only)")
-                    vals.append(float(v))
+                    # a lambda of the face's active transverse coordinates and the time (read_boundary_conditions.py:156);
+                    # evaluated on the block's transverse cell centres by evaluate_dirichlet_face (time-independent only)
+                    vals.append(v if isinstance(v, str) else float(v))
                 dirichlets[f] = tuple(vals)
         for ax, (hi, lo) in enumerate((("east", "west"), ("north", "south"), ("top", "bottom"))):
             _assert((bcs[hi] == "PERIODIC") == (bcs[lo] == "PERIODIC"),

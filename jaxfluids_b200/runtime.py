@@ -80,7 +80,7 @@ class BlockRuntime:
             flux_limiter=num.conservatives.positivity.flux_limiter,
             flux_partition=num.conservatives.positivity.flux_partition,
             wall_velocity=dict(case.wall_velocity_setup),
-            dirichlet=dict(case.dirichlet_setup),
+            dirichlet=self._dirichlet_constants(case, di, parallel),
             is_volume_force=num.active_physics.is_volume_force,
             is_convective_flux=num.active_physics.is_convective_flux,
             gravity=tuple(case.gravity),
@@ -89,6 +89,13 @@ class BlockRuntime:
         self.solver = BlockSolver(self.cfg)
         s = self.solver
         self.device = s.device
+        # space-dependent DIRICHLET data: (destination index, primitive slab, conservative slab) per face, written over
+        # the halo kernels' placeholder values after every halo fill (_apply_dirichlet_slabs)
+        self.dirichlet_slabs = {f: self._make_dirichlet_slab(f, v) for f, v in self._dirichlet_varying.items()}
+        self._host_halo = bool(self.dirichlet_slabs)
+        if self._host_halo and self.neighbors:
+            raise NotImplementedError("space-dependent DIRICHLET data (primitives_callable given as a lambda) is "
+                                      "implemented for single-block runs on the B200 path")
         self.stages = s.stages
         self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
         self.cons = [s.new_field(EPS), s.new_field(EPS)]        # cons[0] = U / U^n, cons[1] = stage scratch
@@ -119,6 +126,49 @@ class BlockRuntime:
         self._first_axis = first
         self._first_strided = len(s.active) > 1   # the contiguous (last active) axis takes no partial ranges
         self._first_split = any(f in self.neighbors for f in (FACES[2 * first], FACES[2 * first + 1]))
+
+    # -- space-dependent DIRICHLET boundaries ---------------------------------
+    def _dirichlet_constants(self, case, di, parallel) -> Dict[str, Tuple[float, ...]]:
+        """Evaluate every DIRICHLET face's primitives_callable on this block (halos/outer/material.py:770-790).  Faces
+        whose values are all constants go to the kernels (jxf_config.dirichlet); faces with a space-dependent entry are
+        kept in self._dirichlet_varying and get a finite placeholder in the kernels' table."""
+        from .input_manager import evaluate_dirichlet_face
+        consts, self._dirichlet_varying = {}, {}
+        for f, values in dict(case.dirichlet_setup).items():
+            if self.bc_block.get(f) != "DIRICHLET":          # a face this block shares with a neighbour
+                continue
+            vals = evaluate_dirichlet_face(values, f, di, parallel.rank)
+            if all(isinstance(v, float) for v in vals):
+                consts[f] = vals
+            else:
+                self._dirichlet_varying[f] = vals
+                consts[f] = tuple(v if isinstance(v, float) else float(np.ravel(v)[0]) for v in vals)
+        return consts
+
+    def _make_dirichlet_slab(self, face: str, vals):
+        """Halo slab of one face: the transverse field broadcast over the nh halo layers (the reference expands the
+        callable's values along the face normal), and its conservatives (equation_manager.py:93-101) in the reference's
+        operation order."""
+        nh, gamma = self.cfg.nh, float(self.cfg.gamma)
+        ax = FACE_ID[face] >> 1
+        hi = (FACE_ID[face] & 1) == 0                      # east / north / top
+        shape = [n if n > 1 else 1 for n in self.cfg.cells]
+        shape[ax] = nh
+        p = np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), shape) for v in vals], axis=0)
+        e = p[4] / (p[0] * (gamma - 1.0))
+        c = np.stack([p[0], p[0] * p[1], p[0] * p[2], p[0] * p[3],
+                      p[0] * (0.5 * (np.square(p[1]) + np.square(p[2]) + np.square(p[3])) + e)], axis=0)
+        idx = [slice(None)] + list(self.cfg.interior)
+        idx[1 + ax] = slice(-nh, None) if hi else slice(0, nh)
+        to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device)  # noqa: E731
+        return tuple(idx), to_dev(p), to_dev(c)
+
+    def _apply_dirichlet_slabs(self, prims: torch.Tensor, cons: torch.Tensor):
+        for idx, p, c in self.dirichlet_slabs.values():
+            prims[idx] = p
+            cons[idx] = c
+        if self.cfg.is_dissipative and len(self.solver.active) > 1:     # edges read the face halos (halo_manager.py:119-129)
+            self.solver.halo_fill_edges(prims, cons)
 
     # -- views ------------------------------------------------------------
     @property
@@ -214,6 +264,8 @@ class BlockRuntime:
                 s.unpack_face(FACE_ID[f], self.recv[f], prims, cons)
         if not local_done:
             s.halo_fill(prims, cons)
+            if self.dirichlet_slabs:
+                self._apply_dirichlet_slabs(prims, cons)
 
     def _allreduce_red(self):
         if self.parallel.is_parallel:
@@ -272,6 +324,10 @@ class BlockRuntime:
                 s.sweep_range(ax, 0, n, p_in, self.rhs, accumulate=False)
                 self.finish_pending()
             s.stage_tail(k, 1, *args, reduce=reduce, fill_halo=True)
+        elif self._host_halo:
+            # space-dependent DIRICHLET data: no fused halo images; halo kernel, slabs, edges after the stage
+            s.stage(k, *args, reduce=reduce, fill_halo=False)
+            self.halo_update(p_out, c_out)
         else:
             self.finish_pending()
             s.stage(k, *args, reduce=reduce, fill_halo=True)
@@ -326,7 +382,7 @@ class BlockRuntime:
 
     def step(self):
         """One full time step, enqueue-only (no host sync)."""
-        if not self.parallel.is_parallel:
+        if not self.parallel.is_parallel and not self._host_halo:
             if getattr(self, "_graphs", None) is not None:
                 return self._graph_step()
             return self._eager_step()

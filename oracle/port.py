@@ -76,7 +76,9 @@ class Setup:
     flux_limiter: str | None = None              # positivity/flux_limiter: SIMPLE | NASA (limiter_flux.py)
     flux_partition: str = "UNIFORM"              # positivity/flux_partition: UNIFORM | CELLSIZE
     wall_velocity: Dict[str, Tuple[float, float, float]] = field(default_factory=dict)   # face -> (u, v, w), constants
-    dirichlet: Dict[str, Tuple[float, float, float, float, float]] = field(default_factory=dict)  # face -> constant prims
+    # face -> (rho, u, v, w, p): constants, or arrays over the transverse interior cells of the face shaped like the
+    # halo slab with extent 1 along the face normal (a lambda of the transverse coordinates in the case file)
+    dirichlet: Dict[str, Tuple] = field(default_factory=dict)
     # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
@@ -195,8 +197,8 @@ def halo_fill(prims, cons, s: Setup):
         sl_src[1 + ax] = src
         sl_dst[1 + ax] = dst
         hp = prims[tuple(sl_src)]
-        if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: constant primitives_callable
-            vals = s.dirichlet[face]
+        if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: primitives_callable -- constants, or
+            vals = s.dirichlet[face]             # arrays over the face's transverse cells (extent 1 along its normal)
             hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(5)], axis=0)
         if kind == "SYMMETRY":
             sign = np.ones((5, 1, 1, 1))

@@ -89,6 +89,9 @@ FIXTURES = {
     "generic/tgv_10x8x12_char_roe_hllc_rk3": ("tgv", dict(cells=(10, 8, 12), frozen_state="ROE"), 2, (2,)),
     "generic/tgv_8x10x12_per_charcons_hllc_rk3": ("tgv", dict(cells=(8, 10, 12), bc="PERIODIC", recon="CHAR-CONSERVATIVE"), 2, (2,)),
     "generic/lax100_fs_roe_weno6cu_roefrozen_rk3": ("lax", dict(cells=(100, None, None), frozen_state="ROE"), 10, (10,)),
+    # the shipped 2-D heat equation example, shrunk: heat flux only, DIRICHLET on four faces with p(x) = 1 + sin(pi x) at
+    # the north face (a lambda in the case file).  tests/golden/api/: fixtures that run through the public API only
+    "api/heat2d_24x20_dirichlet_lambda_noconv_rk3": ("heat2d", dict(cells=(24, 20, None)), 6, (6,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

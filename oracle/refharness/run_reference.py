@@ -50,6 +50,7 @@ CASES = {
     "rti": ("examples_2D/04_rayleigh_taylor_instability", "rti.json"),           # DIRICHLET N/S, gravity, limiter
     "heat1d": ("examples_1D/08_heat_equation", "heat_equation.json"),            # heat flux only (no convective flux)
     "rarefaction": ("examples_1D/04_double_rarefaction", "double_rarefaction.json"),  # flux limiter SIMPLE + interp. limiter
+    "heat2d": ("examples_2D/06_heat_equation", "heat_equation.json"),                  # heat flux only, DIRICHLET x4, p(x) at north
     "lax": ("examples_1D/03_lax_shock_tube", "lax.json"),                             # FLUX-SPLITTING ROE + WENO6-CU
     "woodward": ("examples_1D/06_woodward_shock_tube", "woodward_shock_tube.json"),   # FLUX-SPLITTING ROE + WENO5-Z, SYMMETRY
 }

@@ -32,6 +32,11 @@ def generic_golden_names():
     return sorted("generic/" + os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "generic", "*.npz")))
 
 
+def api_golden_names():
+    """Fixtures that only the public API can run (tests/golden/api/): setups whose data lives in the host runtime."""
+    return sorted("api/" + os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "api", "*.npz")))
+
+
 GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU", "KOREN", "MC",
                     "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
 
@@ -58,6 +63,33 @@ def dissipation_from_json(case, num) -> dict:
                 thermal_conductivity=float(tc.get("value", 0.0) or 0.0),
                 prandtl_number=float(tc.get("prandtl_number", 1.0) or 1.0),
                 gas_constant=float(case["material_properties"]["equation_of_state"]["specific_gas_constant"]))
+
+
+def dirichlet_values(case, face):
+    """primitives_callable of a DIRICHLET face (halos/outer/material.py:770-790, boundary_condition.py:105-126): floats, or
+    lambdas of the ACTIVE transverse coordinates and the time, evaluated on the mesh grid of the face's transverse cell
+    centres (single block) and shaped like the halo slab with extent 1 along the normal and the inactive axes."""
+    d = case["domain"]
+    cells = [d[a]["cells"] for a in "xyz"]
+    ax = port.FACE_AXIS[face]
+    trans = [i for i in range(3) if i != ax and cells[i] > 1]
+    centers = []
+    for i in trans:
+        lo, hi = d["xyz"[i]]["range"]
+        dx = (hi - lo) / cells[i]
+        centers.append(np.linspace(lo + dx / 2, hi - dx / 2, cells[i]))
+    mesh = np.meshgrid(*centers, indexing="ij") if centers else []
+    shape = [cells[i] if i in trans else 1 for i in range(3)]
+    out = []
+    for k in ("rho", "u", "v", "w", "p"):
+        v = case["boundary_conditions"][face]["primitives_callable"][k]
+        if isinstance(v, str):
+            fn = eval(v, {"jnp": np, "np": np})                       # noqa: S307 -- the reference's own contract
+            v = np.asarray(fn(*mesh, 0.0), dtype=np.float64).reshape(shape)
+        else:
+            v = float(v)
+        out.append(v)
+    return tuple(out)
 
 
 def setup_from_json(case, num) -> port.Setup:
@@ -89,8 +121,7 @@ def setup_from_json(case, num) -> port.Setup:
         wall_velocity={f: tuple(float(case["boundary_conditions"][f].get("wall_velocity_callable", {}).get(k, 0.0))
                                 for k in "uvw")
                        for f in port.FACES if case["boundary_conditions"][f]["type"] == "WALL"},
-        dirichlet={f: tuple(float(case["boundary_conditions"][f]["primitives_callable"][k]) for k in ("rho", "u", "v", "w", "p"))
-                   for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
+        dirichlet={f: dirichlet_values(case, f) for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
         is_volume_force=bool(num.get("active_physics", {}).get("is_volume_force", False)),
         is_convective_flux=bool(num.get("active_physics", {}).get("is_convective_flux", True)),
         gravity=tuple(float(x) for x in (case.get("forcings", {}) or {}).get("gravity", (0.0, 0.0, 0.0))),

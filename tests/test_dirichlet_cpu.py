@@ -1,0 +1,110 @@
+"""CPU: space-dependent DIRICHLET data (primitives_callable given as lambdas of the transverse coordinates,
+halos/outer/material.py:770-790) -- the host-side pieces of the B200 path against the pinned oracle: the case-file
+evaluation on the block's transverse cells and the halo slabs BlockRuntime writes over the halo kernels' placeholder
+values (torch index assignment, so the logic is the same on CPU tensors)."""
+import copy
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests import helpers as H
+
+HEAT2D = {
+    "general": {"case_name": "heat2d", "end_time": 1.0, "save_path": "./results", "save_dt": 1.0},
+    "domain": {"x": {"cells": 20, "range": [0.0, 1.0]}, "y": {"cells": 16, "range": [0.0, 1.0]},
+               "z": {"cells": 1, "range": [0.0, 1.0]},
+               "decomposition": {"split_x": 1, "split_y": 1, "split_z": 1}},
+    "boundary_conditions": {
+        "east": {"type": "DIRICHLET", "primitives_callable": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 1.0}},
+        "west": {"type": "DIRICHLET", "primitives_callable": {"rho": "lambda y,t: 1.0 + 0.1 * jnp.cos(3 * y)", "u": 0.0,
+                                                              "v": "lambda y,t: 0.2 * y", "w": 0.0, "p": 1.0}},
+        "north": {"type": "DIRICHLET", "primitives_callable": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0,
+                                                               "p": "lambda x,t: 1.0 + jnp.sin(jnp.pi * x)"}},
+        "south": {"type": "DIRICHLET", "primitives_callable": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 1.0}},
+        "top": {"type": "INACTIVE"}, "bottom": {"type": "INACTIVE"}},
+    "initial_condition": {"rho": 1.0, "u": 0.0, "v": 0.0, "w": 0.0, "p": 1.0},
+    "material_properties": {"equation_of_state": {"model": "IdealGas", "specific_heat_ratio": 1.4,
+                                                  "specific_gas_constant": 1.0},
+                            "transport": {"dynamic_viscosity": {"model": "CUSTOM", "value": 0.1}, "bulk_viscosity": 0.0,
+                                          "thermal_conductivity": {"model": "CUSTOM", "value": 0.1}}},
+}
+NUM = {"conservatives": {"halo_cells": 4, "time_integration": {"integrator": "RK3", "CFL": 0.9},
+                         "convective_fluxes": {"convective_solver": "GODUNOV", "godunov": {
+                             "riemann_solver": "HLLC", "signal_speed": "EINFELDT", "reconstruction_stencil": "WENO5-JS",
+                             "reconstruction_variable": "PRIMITIVE"}},
+                         "dissipative_fluxes": {"reconstruction_stencil": "CENTRAL4", "derivative_stencil_center": "CENTRAL4",
+                                                "derivative_stencil_face": "CENTRAL4"}},
+       "active_physics": {"is_convective_flux": False, "is_viscous_flux": False, "is_heat_flux": True, "is_volume_force": False},
+       "output": {"logging": {"level": "NONE"}}}
+
+
+def test_dirichlet_lambdas_are_evaluated_like_the_oracle():
+    from jaxfluids_b200.input_manager import InputManager, evaluate_dirichlet_face
+    im = InputManager(HEAT2D, NUM)
+    s = H.setup_from_json(HEAT2D, NUM)
+    for face in ("east", "west", "north", "south"):
+        got = evaluate_dirichlet_face(im.case_setup.dirichlet_setup[face], face, im.domain_information)
+        for a, b in zip(got, s.dirichlet[face]):
+            assert type(a) is type(b) or (isinstance(a, np.ndarray) and isinstance(b, np.ndarray))
+            assert np.array_equal(a, b)
+    assert isinstance(s.dirichlet["north"][4], np.ndarray) and s.dirichlet["north"][4].shape == (20, 1, 1)
+    assert isinstance(s.dirichlet["west"][0], np.ndarray) and s.dirichlet["west"][0].shape == (1, 16, 1)
+
+
+def test_time_dependent_dirichlet_and_wrong_labels_are_refused():
+    from jaxfluids_b200.input_manager import InputManager, evaluate_dirichlet_face
+    case = copy.deepcopy(HEAT2D)
+    case["boundary_conditions"]["north"]["primitives_callable"]["p"] = "lambda x,t: 1.0 + t * x"
+    im = InputManager(case, NUM)
+    with pytest.raises(NotImplementedError, match="time-dependent"):
+        evaluate_dirichlet_face(im.case_setup.dirichlet_setup["north"], "north", im.domain_information)
+    case["boundary_conditions"]["north"]["primitives_callable"]["p"] = "lambda y,t: 1.0 + y"
+    im = InputManager(case, NUM)
+    with pytest.raises(AssertionError, match="Input argument labels"):
+        evaluate_dirichlet_face(im.case_setup.dirichlet_setup["north"], "north", im.domain_information)
+
+
+def test_halo_slabs_reproduce_the_oracle_halo_fill():
+    """BlockRuntime's slab construction and overwrite on CPU tensors: after the halo kernel's placeholder fill (here: the
+    oracle's fill with the placeholder constants the kernels get), the face halos of primitives AND conservatives are
+    bit-identical to the oracle's fill with the space-dependent data."""
+    from jaxfluids_b200.engine import BlockConfig
+    from jaxfluids_b200.input_manager import InputManager
+    from jaxfluids_b200.parallel import ParallelContext
+    from jaxfluids_b200.runtime import BlockRuntime
+    im = InputManager(HEAT2D, NUM)
+    s = H.setup_from_json(HEAT2D, NUM)
+    rt = BlockRuntime.__new__(BlockRuntime)
+    rt.bc_block = dict(im.case_setup.boundary_condition_setup)
+    consts = rt._dirichlet_constants(im.case_setup, im.domain_information, ParallelContext(im.domain_information))
+    assert set(rt._dirichlet_varying) == {"west", "north"} and set(consts) == {"east", "west", "north", "south"}
+    assert all(isinstance(v, float) for vals in consts.values() for v in vals)
+    rt.cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min), gamma=s.gamma,
+                         bc=rt.bc_block, nh=s.nh, is_heat_flux=True)
+    rt.device = torch.device("cpu")
+    edges = []
+    rt.solver = SimpleNamespace(active=s.active, halo_fill_edges=lambda p, c: edges.append(1))
+    rt.dirichlet_slabs = {f: rt._make_dirichlet_slab(f, v) for f, v in rt._dirichlet_varying.items()}
+    # the state a halo kernel leaves: placeholder constants on the varying faces
+    rng = np.random.default_rng(3)
+    interior = 1.0 + 0.1 * rng.random((5,) + s.cells)
+    prims, cons = port.initialize(interior, s)
+    s_placeholder = copy.copy(s)
+    s_placeholder.dirichlet = consts
+    s_placeholder.is_heat_flux = False                       # faces only (the edges follow the slabs on the device)
+    p0, c0 = port.halo_fill(prims, cons, s_placeholder)
+    s_faces = copy.copy(s)
+    s_faces.is_heat_flux = False
+    ref_p, ref_c = port.halo_fill(prims, cons, s_faces)
+    assert not np.array_equal(p0, ref_p)
+    tp, tc = torch.as_tensor(p0.copy()), torch.as_tensor(c0.copy())
+    rt._apply_dirichlet_slabs(tp, tc)
+    assert edges == [1]                                      # the edge fill is re-run after the slabs (dissipative, 2-D)
+    m = H.face_halo_mask(s)
+    assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
+    assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])

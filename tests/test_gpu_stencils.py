@@ -240,3 +240,32 @@ def test_reconstruction_variables_and_roe_frozen_state(recon, frozen, stencil, r
     m = H.defined_mask(s)
     assert H.rel_linf(P.host(st.primitives)[:, m], prims[:, m]) <= 1e-11
     assert abs(st.dt.item() - dt) <= 1e-11 * dt
+
+
+@pytest.mark.parametrize("name", H.api_golden_names())
+def test_public_api_runs_space_dependent_dirichlet_example(name):
+    """The reference's 2-D heat equation example (shrunk): DIRICHLET data given as a lambda of the transverse
+    coordinate -- halo slabs written by the host runtime after every halo fill (tests/test_dirichlet_cpu.py checks
+    that logic on CPU tensors) -- through InputManager / InitializationManager / SimulationManager.simulate."""
+    from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+    g, case, num = H.load_golden(name)
+    n = len(g["dt"])
+    case, num = json.loads(json.dumps(case)), json.loads(json.dumps(num))
+    case["general"]["end_step"] = n
+    case["general"]["end_time"] = 1e300
+    num.setdefault("output", {}).setdefault("logging", {})["level"] = "NONE"
+    im = InputManager(case, num)
+    buffers = InitializationManager(im).initialization()
+    s = H.setup_from_json(case, num)
+    m = H.defined_mask(s)
+    p0 = P.host(buffers.simulation_buffers.material_fields.primitives)
+    assert np.array_equal(p0[:, m], g["prims0_halo"][:, m])          # initial halos incl. the lambda's values, bit-exact
+    assert abs(buffers.time_control_variables.physical_timestep_size - float(g["dt0"])) <= 1e-14 * float(g["dt0"])
+    sim = SimulationManager(im)
+    assert sim.runtime.dirichlet_slabs
+    sim.simulate(buffers)
+    out = sim.final_buffers
+    pr = P.host(out.simulation_buffers.material_fields.primitives)
+    assert out.time_control_variables.simulation_step == n
+    assert H.rel_linf(pr[:, m], g[f"prims_n{n}"][:, m]) <= H.TOL_PRIMS_100
+    assert abs(out.time_control_variables.physical_timestep_size - g["dt"][n - 1]) <= 1e-10 * g["dt"][n - 1]

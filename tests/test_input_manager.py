@@ -227,6 +227,7 @@ def test_flux_splitting_block_is_read_like_the_reference():
     ("generic/sod100_charcons_roe_hllc_rk3", dict(recon=3, frozen_state=1, stencil=0)),
     ("generic/riemann2d_16x20_cons_teno5_hll_rk3", dict(recon=2, frozen_state=0, stencil=5, riemann=2)),
     ("generic/lax100_fs_roe_weno6cu_roefrozen_rk3", dict(convective_solver=1, flux_splitting=1, stencil=6, frozen_state=1)),
+    ("api/heat2d_24x20_dirichlet_lambda_noconv_rk3", dict(no_convective_flux=1, heat_flux=1, stencil=1)),
 ])
 
 def test_json_options_reach_the_c_config(name, expect, monkeypatch):

@@ -6,7 +6,7 @@ from oracle import port
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("name", H.golden_names() + H.generic_golden_names())
+@pytest.mark.parametrize("name", H.golden_names() + H.generic_golden_names() + H.api_golden_names())
 def test_port_reproduces_reference_fixture(name):
     g, case, num = H.load_golden(name)
     s = H.setup_from_json(case, num)

@@ -74,6 +74,8 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("tgv", dict(cells=(10, 8, 12), frozen_state="ROE", recon="CHAR-CONSERVATIVE"), 1),
     ("riemann2d", dict(cells=(16, 20, None), frozen_state="ROE", flux_splitting="CLLF"), 2),
     ("lax", dict(cells=(80, None, None), frozen_state="ROE"), 2),
+    # the shipped 2-D heat equation example: DIRICHLET data given as a lambda of the transverse coordinate
+    ("heat2d", dict(cells=(20, 16, None)), 3),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
