@@ -193,7 +193,8 @@ class CaseSetup(NamedTuple):
     initial_condition_setup: Dict[str, Any]
     material_setup: MaterialSetup
     wall_velocity_setup: Dict[str, Tuple[float, float, float]] = {}      # WALL faces: constant (u, v, w)
-    # DIRICHLET faces: (rho, u, v, w, p), each a float or a lambda string of (active transverse coordinates, t)
+    # DIRICHLET / NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces: (rho, u, v, w, p), each a float, a lambda string of
+    # (active transverse coordinates, t), or None where the type reads no such entry
     dirichlet_setup: Dict[str, Tuple[Any, Any, Any, Any, Any]] = {}
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)               # forcings/gravity
 
@@ -219,7 +220,7 @@ def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0
     out = []
     for k, v in zip(("rho", "u", "v", "w", "p"), values):
         if not isinstance(v, str):
-            out.append(float(v))
+            out.append(None if v is None else float(v))
             continue
         path = f"boundary_conditions/{face}/primitives_callable/{k}"
         fn = eval(v, {"jnp": _np_namespace(), "np": np})   # noqa: S307 -- same contract as the reference
@@ -522,12 +523,16 @@ class InputManager:
                                                   "string is not implemented on the B200 path (constant wall velocity only)")
                     uvw.append(float(v))
                 walls[f] = tuple(uvw)
-            if t == "DIRICHLET":
-                # read_boundary_conditions: primitives_callable {rho, u, v, w, p}, floats or lambdas of (coords, t)
+            if t in R.BOUNDARY_VALUE_KEYS:
+                # read_boundary_conditions: primitives_callable {rho, u, v, w, p} (SIMPLE_INFLOW: no p, SIMPLE_OUTFLOW:
+                # p only), floats or lambdas of (coords, t); None for the entries the type does not read
                 pc_d = get_setup_value(f_d, "primitives_callable", f"boundary_conditions/{f}/primitives_callable",
                                        dict, False, setup=S)
                 vals = []
                 for k in ("rho", "u", "v", "w", "p"):
+                    if k not in R.BOUNDARY_VALUE_KEYS[t]:
+                        vals.append(None)
+                        continue
                     v = get_setup_value(pc_d, k, f"boundary_conditions/{f}/primitives_callable/{k}", (float, str),
                                         False, setup=S)
                     # a lambda of the face's active transverse coordinates and the time (read_boundary_conditions.py:156);

@@ -61,7 +61,13 @@ TUPLE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE")   # WAVESPEED needs a glob
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
 DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3", "RK2_LS4": "RungeKutta2_LS4"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
-TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL", "DIRICHLET")
+# NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW: the halo kernels fill ZEROGRADIENT, the host runtime applies the prescribed
+# data on top (runtime.BlockRuntime._apply_host_boundaries)
+TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL", "DIRICHLET", "NEUMANN",
+                        "SIMPLE_INFLOW", "SIMPLE_OUTFLOW")
+# entries of primitives_callable each of these types reads (read_boundary_conditions.py:160-365)
+BOUNDARY_VALUE_KEYS = {"DIRICHLET": ("rho", "u", "v", "w", "p"), "NEUMANN": ("rho", "u", "v", "w", "p"),
+                       "SIMPLE_INFLOW": ("rho", "u", "v", "w"), "SIMPLE_OUTFLOW": ("p",)}
 
 # required_halos of the reference classes (weno5_base.py:18, weno3_base.py:18, weno6_base.py:17, muscl3.py:20,
 # weno1_js.py: 1, central_2.py:21, teno6_base.py:16)

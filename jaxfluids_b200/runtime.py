@@ -49,12 +49,13 @@ class BlockRuntime:
         self.bc_global = dict(case.boundary_condition_setup)
         self.bc_block = parallel.block_boundary_types(self.bc_global)
         self.neighbors = parallel.neighbors(self.bc_global)
+        self._cell_sizes = tuple(di.cell_sizes)           # as the reference forms them (domain_information.py:290)
         self.cfg = BlockConfig(
             cells=tuple(di.device_number_of_cells),
             inv_dx=tuple(float(x) for x in di.one_cell_sizes),
             dx_min=di.smallest_cell_size,
             gamma=case.material_setup.specific_heat_ratio,
-            bc=self.bc_block,
+            bc=self._kernel_boundary_types(),
             nh=di.nh_conservatives,
             convective_solver=cf.convective_solver,
             flux_splitting=fs.flux_splitting if fs is not None else "ROE",
@@ -89,13 +90,12 @@ class BlockRuntime:
         self.solver = BlockSolver(self.cfg)
         s = self.solver
         self.device = s.device
-        # space-dependent DIRICHLET data: (destination index, primitive slab, conservative slab) per face, written over
-        # the halo kernels' placeholder values after every halo fill (_apply_dirichlet_slabs)
-        self.dirichlet_slabs = {f: self._make_dirichlet_slab(f, v) for f, v in self._dirichlet_varying.items()}
-        self._host_halo = bool(self.dirichlet_slabs)
+        # boundary data the host writes over the halo kernels' values after every halo fill (_apply_host_boundaries)
+        self.host_boundaries = {f: self._make_host_boundary(f, t, v) for f, (t, v) in self._host_faces.items()}
+        self._host_halo = bool(self.host_boundaries)
         if self._host_halo and self.neighbors:
-            raise NotImplementedError("space-dependent DIRICHLET data (primitives_callable given as a lambda) is "
-                                      "implemented for single-block runs on the B200 path")
+            raise NotImplementedError("space-dependent DIRICHLET data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
+                                      "are implemented for single-block runs on the B200 path")
         self.stages = s.stages
         self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
         self.cons = [s.new_field(EPS), s.new_field(EPS)]        # cons[0] = U / U^n, cons[1] = stage scratch
@@ -127,46 +127,81 @@ class BlockRuntime:
         self._first_strided = len(s.active) > 1   # the contiguous (last active) axis takes no partial ranges
         self._first_split = any(f in self.neighbors for f in (FACES[2 * first], FACES[2 * first + 1]))
 
-    # -- space-dependent DIRICHLET boundaries ---------------------------------
+    # -- boundaries the host applies on top of the halo kernels -------------------
+    # DIRICHLET with space-dependent data, NEUMANN, SIMPLE_INFLOW, SIMPLE_OUTFLOW: the halo kernels fill these faces with
+    # what they implement (constants / ZEROGRADIENT), then torch index assignments write the prescribed data and the
+    # conservatives of those halo cells, and the edge fill is re-run.  No new kernel; single block only.
+    KERNEL_TYPE = {"NEUMANN": "ZEROGRADIENT", "SIMPLE_INFLOW": "ZEROGRADIENT", "SIMPLE_OUTFLOW": "ZEROGRADIENT"}
+
+    def _kernel_boundary_types(self) -> Dict[str, str]:
+        """The boundary types the kernels are configured with: NEUMANN / SIMPLE_* faces are ZEROGRADIENT there (the source
+        cell of all three is the last interior cell, boundary_condition.py:580-595)."""
+        return {f: self.KERNEL_TYPE.get(t, t) for f, t in self.bc_block.items()}
+
     def _dirichlet_constants(self, case, di, parallel) -> Dict[str, Tuple[float, ...]]:
-        """Evaluate every DIRICHLET face's primitives_callable on this block (halos/outer/material.py:770-790).  Faces
-        whose values are all constants go to the kernels (jxf_config.dirichlet); faces with a space-dependent entry are
-        kept in self._dirichlet_varying and get a finite placeholder in the kernels' table."""
+        """Evaluate every primitives_callable of this block's outer faces (halos/outer/material.py:770-790, :825-866,
+        :966-1050).  DIRICHLET faces whose values are all constants go to the kernels (jxf_config.dirichlet); everything
+        else is kept in self._host_faces = {face: (type, values)}, DIRICHLET faces among them with a finite placeholder
+        in the kernels' table."""
         from .input_manager import evaluate_dirichlet_face
-        consts, self._dirichlet_varying = {}, {}
+        consts, self._host_faces = {}, {}
         for f, values in dict(case.dirichlet_setup).items():
-            if self.bc_block.get(f) != "DIRICHLET":          # a face this block shares with a neighbour
+            t = self.bc_block.get(f)
+            if t not in ("DIRICHLET", "NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):   # a face shared with a neighbour
                 continue
             vals = evaluate_dirichlet_face(values, f, di, parallel.rank)
-            if all(isinstance(v, float) for v in vals):
+            if t != "DIRICHLET":
+                self._host_faces[f] = (t, vals)
+            elif all(isinstance(v, float) for v in vals):
                 consts[f] = vals
             else:
-                self._dirichlet_varying[f] = vals
+                self._host_faces[f] = (t, vals)
                 consts[f] = tuple(v if isinstance(v, float) else float(np.ravel(v)[0]) for v in vals)
         return consts
 
-    def _make_dirichlet_slab(self, face: str, vals):
-        """Halo slab of one face: the transverse field broadcast over the nh halo layers (the reference expands the
-        callable's values along the face normal), and its conservatives (equation_manager.py:93-101) in the reference's
-        operation order."""
-        nh, gamma = self.cfg.nh, float(self.cfg.gamma)
+    def _make_host_boundary(self, face: str, kind: str, vals):
+        """(halo index, type, per-variable device slabs) of one face: each prescribed field broadcast over the nh halo
+        layers (the reference expands the callable's values along the face normal); NEUMANN slabs hold the increment
+        (value * upwind sign) * dx of halos/outer/material.py:857-862."""
+        nh = self.cfg.nh
         ax = FACE_ID[face] >> 1
         hi = (FACE_ID[face] & 1) == 0                      # east / north / top
         shape = [n if n > 1 else 1 for n in self.cfg.cells]
         shape[ax] = nh
-        p = np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), shape) for v in vals], axis=0)
-        e = p[4] / (p[0] * (gamma - 1.0))
-        c = np.stack([p[0], p[0] * p[1], p[0] * p[2], p[0] * p[3],
-                      p[0] * (0.5 * (np.square(p[1]) + np.square(p[2]) + np.square(p[3])) + e)], axis=0)
         idx = [slice(None)] + list(self.cfg.interior)
         idx[1 + ax] = slice(-nh, None) if hi else slice(0, nh)
-        to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device)  # noqa: E731
-        return tuple(idx), to_dev(p), to_dev(c)
+        slabs = []
+        for v in vals:
+            if v is None:
+                slabs.append(None)
+                continue
+            a = np.broadcast_to(np.asarray(v, dtype=np.float64), shape)
+            if kind == "NEUMANN":
+                dx = np.float64(1.0) / np.float64(self.cfg.inv_dx[ax]) if self._cell_sizes is None else self._cell_sizes[ax]
+                a = a * (-1 if hi else 1) * dx
+            slabs.append(torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device))
+        return tuple(idx), kind, slabs
 
-    def _apply_dirichlet_slabs(self, prims: torch.Tensor, cons: torch.Tensor):
-        for idx, p, c in self.dirichlet_slabs.values():
-            prims[idx] = p
-            cons[idx] = c
+    def _apply_host_boundaries(self, prims: torch.Tensor, cons: torch.Tensor):
+        """Right after the halo kernel (which left constants / the ZEROGRADIENT copy in these halos)."""
+        g1 = float(self.cfg.gamma) - 1.0
+        for idx, kind, slabs in self.host_boundaries.values():
+            h = prims[idx]                                 # a view of the face's halo cells
+            for v, slab in enumerate(slabs):
+                if slab is None:
+                    continue                               # SIMPLE_INFLOW keeps the copied p, SIMPLE_OUTFLOW rho, u, v, w
+                if kind == "NEUMANN":
+                    h[v] = h[v] + slab                     # last interior cell (the kernel's copy) + increment
+                else:
+                    h[v] = slab
+            # conservatives of the halo cells (equation_manager.py:93-101), the reference's operation order
+            e = h[4] / (h[0] * g1)
+            c = cons[idx]
+            c[0] = h[0]
+            c[1] = h[0] * h[1]
+            c[2] = h[0] * h[2]
+            c[3] = h[0] * h[3]
+            c[4] = h[0] * (0.5 * (torch.square(h[1]) + torch.square(h[2]) + torch.square(h[3])) + e)
         if self.cfg.is_dissipative and len(self.solver.active) > 1:     # edges read the face halos (halo_manager.py:119-129)
             self.solver.halo_fill_edges(prims, cons)
 
@@ -264,8 +299,8 @@ class BlockRuntime:
                 s.unpack_face(FACE_ID[f], self.recv[f], prims, cons)
         if not local_done:
             s.halo_fill(prims, cons)
-            if self.dirichlet_slabs:
-                self._apply_dirichlet_slabs(prims, cons)
+            if self.host_boundaries:
+                self._apply_host_boundaries(prims, cons)
 
     def _allreduce_red(self):
         if self.parallel.is_parallel:
@@ -325,7 +360,7 @@ class BlockRuntime:
                 self.finish_pending()
             s.stage_tail(k, 1, *args, reduce=reduce, fill_halo=True)
         elif self._host_halo:
-            # space-dependent DIRICHLET data: no fused halo images; halo kernel, slabs, edges after the stage
+            # host-applied boundary data: no fused halo images; halo kernel, host data, edges after the stage
             s.stage(k, *args, reduce=reduce, fill_halo=False)
             self.halo_update(p_out, c_out)
         else:

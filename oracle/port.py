@@ -79,6 +79,9 @@ class Setup:
     # face -> (rho, u, v, w, p): constants, or arrays over the transverse interior cells of the face shaped like the
     # halo slab with extent 1 along the face normal (a lambda of the transverse coordinates in the case file)
     dirichlet: Dict[str, Tuple] = field(default_factory=dict)
+    # NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces -> (rho, u, v, w, p) of their primitives_callable, None where the
+    # type takes no entry (SIMPLE_INFLOW: no p; SIMPLE_OUTFLOW: p only); floats or arrays as for `dirichlet`
+    bc_values: Dict[str, Tuple] = field(default_factory=dict)
     # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
@@ -187,8 +190,8 @@ def halo_fill(prims, cons, s: Setup):
             src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
         elif kind in ("SYMMETRY", "WALL"):
             src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
-        elif kind in ("ZEROGRADIENT", "DIRICHLET"):
-            src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)
+        elif kind in ("ZEROGRADIENT", "DIRICHLET", "NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
+            src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)     # boundary_condition.py:580-595
         else:
             raise NotImplementedError(kind)
         dst = slice(-nh, None) if hi else slice(0, nh)
@@ -200,6 +203,16 @@ def halo_fill(prims, cons, s: Setup):
         if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: primitives_callable -- constants, or
             vals = s.dirichlet[face]             # arrays over the face's transverse cells (extent 1 along its normal)
             hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(5)], axis=0)
+        if kind == "NEUMANN":                    # :825-866: last interior cell + (value * upwind sign) * dx
+            vals = s.bc_values[face]
+            sgn = -1 if hi else 1                # material.py:41-44
+            hp = np.stack([hp[v] + (np.ones_like(hp[0]) * vals[v]) * sgn * s.dx[ax] for v in range(5)], axis=0)
+        if kind == "SIMPLE_INFLOW":              # :966-1022: density and velocity prescribed, pressure from inside
+            vals = s.bc_values[face]
+            hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(4)] + [hp[4]], axis=0)
+        if kind == "SIMPLE_OUTFLOW":             # :1024-1050: everything from inside, pressure prescribed
+            vals = s.bc_values[face]
+            hp = np.stack([hp[v] for v in range(4)] + [np.ones_like(hp[0]) * vals[4]], axis=0)
         if kind == "SYMMETRY":
             sign = np.ones((5, 1, 1, 1))
             sign[1 + ax] *= -1.0

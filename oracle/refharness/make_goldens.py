@@ -92,6 +92,22 @@ FIXTURES = {
     # the shipped 2-D heat equation example, shrunk: heat flux only, DIRICHLET on four faces with p(x) = 1 + sin(pi x) at
     # the north face (a lambda in the case file).  tests/golden/api/: fixtures that run through the public API only
     "api/heat2d_24x20_dirichlet_lambda_noconv_rk3": ("heat2d", dict(cells=(24, 20, None)), 6, (6,)),
+    # SIMPLE_INFLOW (west) / SIMPLE_OUTFLOW (east) / NEUMANN (north, south) with constants and lambdas, convective and
+    # with the viscous + heat flux (edge halos)
+    "api/riemann2d_16x20_inflow_outflow_neumann_rk3": ("riemann2d", dict(cells=(16, 20, None), boundary_conditions={
+        "west": {"type": "SIMPLE_INFLOW", "primitives_callable": {"rho": "lambda y,t: 0.5 + 0.2 * y", "u": 1.2,
+                                                                  "v": "lambda y,t: 0.1 * jnp.sin(6 * y)", "w": 0.0}},
+        "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": "lambda y,t: 1.0 + 0.5 * y"}},
+        "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0,
+                                                             "p": -0.3}},
+        "south": {"type": "NEUMANN", "primitives_callable": {"rho": "lambda x,t: 0.3 * jnp.cos(5 * x)", "u": 0.0, "v": 0.1,
+                                                             "w": 0.0, "p": 0.2}}}), 4, (4,)),
+    "api/riemann2d_16x20_inflow_outflow_visc_rk3": ("riemann2d", dict(cells=(16, 20, None), dissipation=dict(mu=1e-3, kappa=1e-3),
+                                                                      boundary_conditions={
+        "west": {"type": "SIMPLE_INFLOW", "primitives_callable": {"rho": 1.0, "u": 0.3, "v": 0.0, "w": 0.0}},
+        "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": 0.1}},
+        "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0,
+                                                             "p": -0.3}}}), 3, (3,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

@@ -67,7 +67,8 @@ def load_case(name: str):
 
 
 def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrator=None, stencil=None,
-              signal_speed=None, positivity=None, initial_condition=None, flux_splitting=None, frozen_state=None):
+              signal_speed=None, positivity=None, initial_condition=None, flux_splitting=None, frozen_state=None,
+              boundary_conditions=None):
     case, num = copy.deepcopy(case), copy.deepcopy(num)
     if cells is not None:
         for ax, n in zip("xyz", cells):
@@ -77,6 +78,9 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
         for face in ("east", "west", "north", "south", "top", "bottom"):
             if case["boundary_conditions"][face]["type"] not in ("INACTIVE", "DIRICHLET", "WALL"):
                 case["boundary_conditions"][face] = {"type": bc}
+    if boundary_conditions is not None:       # face -> the face's whole entry (type + callables)
+        for face, entry in boundary_conditions.items():
+            case["boundary_conditions"][face] = copy.deepcopy(entry)
     cf = num["conservatives"]["convective_fluxes"]
     if flux_splitting is not None:           # convective_solver FLUX-SPLITTING with this eigenvalue choice
         cf["convective_solver"] = "FLUX-SPLITTING"

@@ -65,7 +65,7 @@ def dissipation_from_json(case, num) -> dict:
                 gas_constant=float(case["material_properties"]["equation_of_state"]["specific_gas_constant"]))
 
 
-def dirichlet_values(case, face):
+def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p")):
     """primitives_callable of a DIRICHLET face (halos/outer/material.py:770-790, boundary_condition.py:105-126): floats, or
     lambdas of the ACTIVE transverse coordinates and the time, evaluated on the mesh grid of the face's transverse cell
     centres (single block) and shaped like the halo slab with extent 1 along the normal and the inactive axes."""
@@ -82,6 +82,9 @@ def dirichlet_values(case, face):
     shape = [cells[i] if i in trans else 1 for i in range(3)]
     out = []
     for k in ("rho", "u", "v", "w", "p"):
+        if k not in keys:                     # SIMPLE_INFLOW takes no p, SIMPLE_OUTFLOW only p
+            out.append(None)
+            continue
         v = case["boundary_conditions"][face]["primitives_callable"][k]
         if isinstance(v, str):
             fn = eval(v, {"jnp": np, "np": np})                       # noqa: S307 -- the reference's own contract
@@ -90,6 +93,10 @@ def dirichlet_values(case, face):
             v = float(v)
         out.append(v)
     return tuple(out)
+
+
+# entries of primitives_callable the type reads (read_boundary_conditions.py:160-365)
+BC_VALUE_KEYS = {"NEUMANN": ("rho", "u", "v", "w", "p"), "SIMPLE_INFLOW": ("rho", "u", "v", "w"), "SIMPLE_OUTFLOW": ("p",)}
 
 
 def setup_from_json(case, num) -> port.Setup:
@@ -122,6 +129,8 @@ def setup_from_json(case, num) -> port.Setup:
                                 for k in "uvw")
                        for f in port.FACES if case["boundary_conditions"][f]["type"] == "WALL"},
         dirichlet={f: dirichlet_values(case, f) for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
+        bc_values={f: dirichlet_values(case, f, BC_VALUE_KEYS[case["boundary_conditions"][f]["type"]]) for f in port.FACES
+                   if case["boundary_conditions"][f]["type"] in BC_VALUE_KEYS},
         is_volume_force=bool(num.get("active_physics", {}).get("is_volume_force", False)),
         is_convective_flux=bool(num.get("active_physics", {}).get("is_convective_flux", True)),
         gravity=tuple(float(x) for x in (case.get("forcings", {}) or {}).get("gravity", (0.0, 0.0, 0.0))),

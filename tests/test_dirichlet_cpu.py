@@ -43,6 +43,25 @@ NUM = {"conservatives": {"halo_cells": 4, "time_integration": {"integrator": "RK
        "output": {"logging": {"level": "NONE"}}}
 
 
+def _host_runtime(im, s, **cfg_kw):
+    """A BlockRuntime with everything but the CUDA solver: the host-side boundary logic on CPU tensors."""
+    from jaxfluids_b200.engine import BlockConfig
+    from jaxfluids_b200.parallel import ParallelContext
+    from jaxfluids_b200.runtime import BlockRuntime
+    rt = BlockRuntime.__new__(BlockRuntime)
+    rt.bc_block = dict(im.case_setup.boundary_condition_setup)
+    rt._cell_sizes = tuple(im.domain_information.cell_sizes)
+    consts = rt._dirichlet_constants(im.case_setup, im.domain_information, ParallelContext(im.domain_information))
+    rt.cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min), gamma=s.gamma,
+                         bc=rt._kernel_boundary_types(), nh=s.nh, dirichlet=consts, **cfg_kw)
+    rt.cfg.to_c()                                            # the kernels' configuration is constructible
+    rt.device = torch.device("cpu")
+    edges = []
+    rt.solver = SimpleNamespace(active=s.active, halo_fill_edges=lambda p, c: edges.append(1))
+    rt.host_boundaries = {f: rt._make_host_boundary(f, t, v) for f, (t, v) in rt._host_faces.items()}
+    return rt, consts, edges
+
+
 def test_dirichlet_lambdas_are_evaluated_like_the_oracle():
     from jaxfluids_b200.input_manager import InputManager, evaluate_dirichlet_face
     im = InputManager(HEAT2D, NUM)
@@ -79,17 +98,9 @@ def test_halo_slabs_reproduce_the_oracle_halo_fill():
     from jaxfluids_b200.runtime import BlockRuntime
     im = InputManager(HEAT2D, NUM)
     s = H.setup_from_json(HEAT2D, NUM)
-    rt = BlockRuntime.__new__(BlockRuntime)
-    rt.bc_block = dict(im.case_setup.boundary_condition_setup)
-    consts = rt._dirichlet_constants(im.case_setup, im.domain_information, ParallelContext(im.domain_information))
-    assert set(rt._dirichlet_varying) == {"west", "north"} and set(consts) == {"east", "west", "north", "south"}
+    rt, consts, edges = _host_runtime(im, s, is_heat_flux=True)
+    assert set(rt._host_faces) == {"west", "north"} and set(consts) == {"east", "west", "north", "south"}
     assert all(isinstance(v, float) for vals in consts.values() for v in vals)
-    rt.cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min), gamma=s.gamma,
-                         bc=rt.bc_block, nh=s.nh, is_heat_flux=True)
-    rt.device = torch.device("cpu")
-    edges = []
-    rt.solver = SimpleNamespace(active=s.active, halo_fill_edges=lambda p, c: edges.append(1))
-    rt.dirichlet_slabs = {f: rt._make_dirichlet_slab(f, v) for f, v in rt._dirichlet_varying.items()}
     # the state a halo kernel leaves: placeholder constants on the varying faces
     rng = np.random.default_rng(3)
     interior = 1.0 + 0.1 * rng.random((5,) + s.cells)
@@ -103,8 +114,45 @@ def test_halo_slabs_reproduce_the_oracle_halo_fill():
     ref_p, ref_c = port.halo_fill(prims, cons, s_faces)
     assert not np.array_equal(p0, ref_p)
     tp, tc = torch.as_tensor(p0.copy()), torch.as_tensor(c0.copy())
-    rt._apply_dirichlet_slabs(tp, tc)
+    rt._apply_host_boundaries(tp, tc)
     assert edges == [1]                                      # the edge fill is re-run after the slabs (dissipative, 2-D)
     m = H.face_halo_mask(s)
+    assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
+    assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])
+
+
+def test_neumann_and_simple_inflow_outflow_reproduce_the_oracle_halo_fill():
+    """NEUMANN (halos/outer/material.py:825-866), SIMPLE_INFLOW (:966-1022), SIMPLE_OUTFLOW (:1024-1050): the kernels are
+    configured with ZEROGRADIENT on these faces; the host's index assignments on top of that fill give the oracle's
+    halos bit for bit (primitives and conservatives)."""
+    from jaxfluids_b200.input_manager import InputManager
+    case = copy.deepcopy(HEAT2D)
+    case["boundary_conditions"].update({
+        "west": {"type": "SIMPLE_INFLOW", "primitives_callable": {"rho": "lambda y,t: 0.5 + 0.2 * y", "u": 1.2,
+                                                                  "v": "lambda y,t: 0.1 * jnp.sin(6 * y)", "w": 0.0}},
+        "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": "lambda y,t: 1.0 + 0.5 * y"}},
+        "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0,
+                                                             "p": -0.3}},
+        "south": {"type": "NEUMANN", "primitives_callable": {"rho": "lambda x,t: 0.3 * jnp.cos(5 * x)", "u": 0.0, "v": 0.1,
+                                                             "w": 0.0, "p": 0.2}}})
+    num = copy.deepcopy(NUM)
+    num["active_physics"] = {"is_convective_flux": True}
+    im = InputManager(case, num)
+    s = H.setup_from_json(case, num)
+    assert s.bc["west"] == "SIMPLE_INFLOW" and s.bc_values["east"][:4] == (None,) * 4
+    rt, consts, edges = _host_runtime(im, s)
+    assert consts == {} and set(rt._host_faces) == {"west", "east", "north", "south"}
+    assert set(rt.cfg.bc[f] for f in ("west", "east", "north", "south")) == {"ZEROGRADIENT"}
+    rng = np.random.default_rng(5)
+    prims, cons = port.initialize(1.0 + 0.1 * rng.random((5,) + s.cells), s)
+    s_kernel = copy.copy(s)
+    s_kernel.bc = dict(rt.cfg.bc)                            # what the halo kernel fills: ZEROGRADIENT
+    p0, c0 = port.halo_fill(prims, cons, s_kernel)
+    ref_p, ref_c = port.halo_fill(prims, cons, s)
+    tp, tc = torch.as_tensor(p0.copy()), torch.as_tensor(c0.copy())
+    rt._apply_host_boundaries(tp, tc)
+    assert edges == []                                       # convective only: no edge halos
+    m = H.face_halo_mask(s)
+    assert not np.array_equal(p0[:, m], ref_p[:, m])
     assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
     assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])

@@ -145,8 +145,8 @@ def test_dissipative_setup_is_read_like_the_reference():
 def test_case_errors():
     case, num = SETUPS["tgv16_sym_char_hllc_rk3"]
     with pytest.raises(NotImplementedError):
-        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "NEUMANN"), num)
-    # DIRICHLET: constant primitives_callable
+        InputManager(_mod(case, ("boundary_conditions", "east", "type"), "LINEAREXTRAPOLATION"), num)
+    # DIRICHLET: primitives_callable
     with pytest.raises(AssertionError, match="primitives_callable"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "DIRICHLET"), num)
     dirich = _mod(case, ("boundary_conditions", "east"),
@@ -228,6 +228,7 @@ def test_flux_splitting_block_is_read_like_the_reference():
     ("generic/riemann2d_16x20_cons_teno5_hll_rk3", dict(recon=2, frozen_state=0, stencil=5, riemann=2)),
     ("generic/lax100_fs_roe_weno6cu_roefrozen_rk3", dict(convective_solver=1, flux_splitting=1, stencil=6, frozen_state=1)),
     ("api/heat2d_24x20_dirichlet_lambda_noconv_rk3", dict(no_convective_flux=1, heat_flux=1, stencil=1)),
+    ("api/riemann2d_16x20_inflow_outflow_visc_rk3", dict(viscous_flux=1, heat_flux=1)),
 ])
 
 def test_json_options_reach_the_c_config(name, expect, monkeypatch):
@@ -249,6 +250,10 @@ def test_json_options_reach_the_c_config(name, expect, monkeypatch):
     c = info.value.args[0]
     for key, value in expect.items():
         assert getattr(c, key) == value, key
+    # NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces reach the kernels as ZEROGRADIENT (3); the host applies their data
+    for k, f in enumerate(("east", "west", "north", "south", "top", "bottom")):
+        if case["boundary_conditions"][f]["type"] in ("NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
+            assert c.bc[k] == 3
 
 
 @pytest.mark.parametrize("variable", ["PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE"])

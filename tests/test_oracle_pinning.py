@@ -76,6 +76,16 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("lax", dict(cells=(80, None, None), frozen_state="ROE"), 2),
     # the shipped 2-D heat equation example: DIRICHLET data given as a lambda of the transverse coordinate
     ("heat2d", dict(cells=(20, 16, None)), 3),
+    # SIMPLE_INFLOW / SIMPLE_OUTFLOW / NEUMANN boundaries
+    ("sod", dict(cells=(64, None, None), boundary_conditions={
+        "west": {"type": "SIMPLE_INFLOW", "primitives_callable": {"rho": 1.0, "u": 0.3, "v": 0.0, "w": 0.0}},
+        "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": 0.1}}}), 3),
+    ("riemann2d", dict(cells=(16, 20, None), dissipation=dict(mu=1e-3, kappa=1e-3), boundary_conditions={
+        "west": {"type": "SIMPLE_INFLOW", "primitives_callable": {"rho": "lambda y,t: 0.5 + 0.2 * y", "u": 1.2, "v": 0.0, "w": 0.0}},
+        "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": "lambda y,t: 1.0 + 0.5 * y"}},
+        "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0, "p": -0.3}},
+        "south": {"type": "NEUMANN", "primitives_callable": {"rho": "lambda x,t: 0.3 * jnp.cos(5 * x)", "u": 0.0, "v": 0.1, "w": 0.0,
+                                                             "p": 0.2}}}), 2),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
@@ -86,5 +96,6 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
 ])
 def test_port_is_bit_identical_to_reference(name, kw, nsteps):
     from oracle.refharness import pin_check
+    kw = dict(kw)
     with np.errstate(all="ignore"):
         pin_check.check(name, nsteps=nsteps, **kw)
