@@ -197,6 +197,10 @@ class CaseSetup(NamedTuple):
     # (active transverse coordinates, t), or None where the type reads no such entry
     dirichlet_setup: Dict[str, Tuple[Any, Any, Any, Any, Any]] = {}
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)               # forcings/gravity
+    # faces given as a LIST of types with bounding_domain lambdas (halos/outer/material.py:121-277): face -> the
+    # DIRICHLET entries [(values, bounding_domain string)] and the bounding_domain of the entry the kernels fill;
+    # boundary_condition_setup[face] names that entry's type (ZEROGRADIENT / SYMMETRY)
+    multi_type_setup: Dict[str, Dict[str, Any]] = {}
 
 
 def _np_namespace():
@@ -233,6 +237,25 @@ def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0
             raise NotImplementedError(f"{path}: a time-dependent DIRICHLET callable is not implemented on the B200 path")
         out.append(np.ascontiguousarray(a))
     return tuple(out)
+
+
+def evaluate_bounding_domain(expr: str, face: str, domain_information, rank: int = 0) -> np.ndarray:
+    """bounding_domain of one entry of a multi-type face (halos/outer/material.py:252-258): a lambda of the ACTIVE
+    transverse coordinates, evaluated on this block's transverse cell centres; bool, shaped like the face's halo slab
+    with extent 1 along the normal and the inactive axes."""
+    di = domain_information
+    ax = FACES.index(face) // 2
+    trans = [i for i in di.active_axes_indices if i != ax]
+    centers = di.get_device_cell_centers(rank)
+    mesh = np.meshgrid(*[np.asarray(centers[i], dtype=np.float64) for i in trans], indexing="ij") if trans else []
+    shape = [di.device_number_of_cells[i] if i in trans else 1 for i in range(3)]
+    fn = eval(expr, {"jnp": _np_namespace(), "np": np})   # noqa: S307 -- same contract as the reference
+    names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
+    labels = tuple(AXES[i] for i in trans)
+    _assert(tuple(names) == labels, f"Input argument labels of lambda for boundary_conditions/{face}/bounding_domain must "
+                                    f"be {labels}.", "case")
+    mshape = mesh[0].shape if mesh else ()
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(fn(*mesh)), mshape).astype(bool).reshape(shape))
 
 
 def make_ic_callable(value, labels: Tuple[str, ...], path: str) -> Callable:
@@ -499,11 +522,32 @@ class InputManager:
         bcs = {}
         walls = {}
         dirichlets = {}
+        multi = {}
         for f in FACES:
             f_d = get_setup_value(bc_d, f, f"boundary_conditions/{f}", (dict, list), False, setup=S)
             if isinstance(f_d, list):
-                raise NotImplementedError(f"boundary_conditions/{f}: multiple types per face are not implemented on "
-                                          "the B200 path")
+                # several types on one face, each with a bounding_domain lambda of the transverse coordinates: one entry
+                # of a type the halo kernels fill (ZEROGRADIENT / SYMMETRY) + DIRICHLET entries the host applies
+                natives = [e for e in f_d if e.get("type") in ("ZEROGRADIENT", "SYMMETRY")]
+                others = [e for e in f_d if e.get("type") not in ("ZEROGRADIENT", "SYMMETRY")]
+                for e in f_d:
+                    R.select(get_setup_value(e, "type", f"boundary_conditions/{f}/type", str, False, setup=S),
+                             R.REFERENCE_BOUNDARY_TYPES, R.TUPLE_BOUNDARY_TYPES, f"boundary_conditions/{f}/type", S)
+                    get_setup_value(e, "bounding_domain", f"boundary_conditions/{f}/bounding_domain", str, False, setup=S)
+                if len(natives) != 1 or any(e["type"] != "DIRICHLET" for e in others):
+                    raise NotImplementedError(
+                        f"boundary_conditions/{f}: several types per face are implemented on the B200 path for one "
+                        "ZEROGRADIENT or SYMMETRY entry combined with DIRICHLET entries")
+                entries = []
+                for e in others:
+                    pc_d = get_setup_value(e, "primitives_callable", f"boundary_conditions/{f}/primitives_callable", dict,
+                                           False, setup=S)
+                    vals = tuple(v if isinstance(v, str) else float(v) for v in (
+                        get_setup_value(pc_d, k, f"boundary_conditions/{f}/primitives_callable/{k}", (float, str), False,
+                                        setup=S) for k in ("rho", "u", "v", "w", "p")))
+                    entries.append((vals, e["bounding_domain"]))
+                multi[f] = {"dirichlet": entries, "kernel_bounding_domain": natives[0]["bounding_domain"]}
+                f_d = {"type": natives[0]["type"]}
             t = get_setup_value(f_d, "type", f"boundary_conditions/{f}/type", str, False, setup=S)
             t = R.select(t, R.REFERENCE_BOUNDARY_TYPES, R.TUPLE_BOUNDARY_TYPES, f"boundary_conditions/{f}/type", S)
             active = cells[FACE_AXIS[f]] > 1
@@ -574,7 +618,7 @@ class InputManager:
             gravity = tuple(float(x) for x in gv)
         transport = self._read_transport(mp_d)
         return CaseSetup(general, domain, bcs, ic, MaterialSetup(model, float(gamma), float(Rgas), transport), walls,
-                         dirichlets, gravity)
+                         dirichlets, gravity, multi)
 
     def _read_transport(self, mp_d: Dict) -> TransportSetup:
         """read_material_manager.py:200-330: required exactly when the flux that needs them is active."""

@@ -91,7 +91,10 @@ class BlockRuntime:
         s = self.solver
         self.device = s.device
         # boundary data the host writes over the halo kernels' values after every halo fill (_apply_host_boundaries)
-        self.host_boundaries = {f: self._make_host_boundary(f, t, v) for f, (t, v) in self._host_faces.items()}
+        self.host_boundaries = {f: self._make_host_boundary(f, t, v, m) for f, (t, v, m) in self._host_faces.items()}
+        if self.cfg.is_dissipative and any(isinstance(f, tuple) for f in self.host_boundaries):
+            raise NotImplementedError("several boundary types on one face together with the viscous / heat flux (edge "
+                                      "halos next to such a face) are not implemented on the B200 path")
         self._host_halo = bool(self.host_boundaries)
         if self._host_halo and self.neighbors:
             raise NotImplementedError("space-dependent DIRICHLET data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
@@ -151,19 +154,35 @@ class BlockRuntime:
                 continue
             vals = evaluate_dirichlet_face(values, f, di, parallel.rank)
             if t != "DIRICHLET":
-                self._host_faces[f] = (t, vals)
+                self._host_faces[f] = (t, vals, None)
             elif all(isinstance(v, float) for v in vals):
                 consts[f] = vals
             else:
-                self._host_faces[f] = (t, vals)
+                self._host_faces[f] = (t, vals, None)
                 consts[f] = tuple(v if isinstance(v, float) else float(np.ravel(v)[0]) for v in vals)
+        # faces with several types: the kernels fill the ZEROGRADIENT / SYMMETRY entry on the whole face, the DIRICHLET
+        # entries are written where their bounding_domain holds.  The masks must partition the face (then the order
+        # in which the reference applies the entries, material.py:121-277, does not matter).
+        from .input_manager import evaluate_bounding_domain
+        for f, m in dict(getattr(case, "multi_type_setup", {}) or {}).items():
+            if self.bc_block.get(f) not in ("ZEROGRADIENT", "SYMMETRY"):
+                continue
+            covered = evaluate_bounding_domain(m["kernel_bounding_domain"], f, di, parallel.rank).astype(int)
+            for i, (values, dom) in enumerate(m["dirichlet"]):
+                mask = evaluate_bounding_domain(dom, f, di, parallel.rank)
+                covered = covered + mask.astype(int)
+                self._host_faces[(f, i)] = ("DIRICHLET", evaluate_dirichlet_face(values, f, di, parallel.rank), mask)
+            if not np.all(covered == 1):
+                raise NotImplementedError(f"boundary_conditions/{f}: the bounding domains of the face's types must "
+                                          "partition the face on the B200 path")
         return consts
 
-    def _make_host_boundary(self, face: str, kind: str, vals):
+    def _make_host_boundary(self, face, kind: str, vals, mask=None):
         """(halo index, type, per-variable device slabs) of one face: each prescribed field broadcast over the nh halo
         layers (the reference expands the callable's values along the face normal); NEUMANN slabs hold the increment
         (value * upwind sign) * dx of halos/outer/material.py:857-862."""
         nh = self.cfg.nh
+        face = face[0] if isinstance(face, tuple) else face    # (face, i): the i-th DIRICHLET entry of a multi-type face
         ax = FACE_ID[face] >> 1
         hi = (FACE_ID[face] & 1) == 0                      # east / north / top
         shape = [n if n > 1 else 1 for n in self.cfg.cells]
@@ -180,18 +199,22 @@ class BlockRuntime:
                 dx = np.float64(1.0) / np.float64(self.cfg.inv_dx[ax]) if self._cell_sizes is None else self._cell_sizes[ax]
                 a = a * (-1 if hi else 1) * dx
             slabs.append(torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device))
-        return tuple(idx), kind, slabs
+        if mask is not None:
+            mask = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(mask, shape))).to(self.device)
+        return tuple(idx), kind, slabs, mask
 
     def _apply_host_boundaries(self, prims: torch.Tensor, cons: torch.Tensor):
         """Right after the halo kernel (which left constants / the ZEROGRADIENT copy in these halos)."""
         g1 = float(self.cfg.gamma) - 1.0
-        for idx, kind, slabs in self.host_boundaries.values():
+        for idx, kind, slabs, mask in self.host_boundaries.values():
             h = prims[idx]                                 # a view of the face's halo cells
             for v, slab in enumerate(slabs):
                 if slab is None:
                     continue                               # SIMPLE_INFLOW keeps the copied p, SIMPLE_OUTFLOW rho, u, v, w
                 if kind == "NEUMANN":
                     h[v] = h[v] + slab                     # last interior cell (the kernel's copy) + increment
+                elif mask is not None:
+                    h[v] = torch.where(mask, slab, h[v])   # one type of a multi-type face, inside its bounding domain
                 else:
                     h[v] = slab
             # conservatives of the halo cells (equation_manager.py:93-101), the reference's operation order

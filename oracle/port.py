@@ -82,6 +82,10 @@ class Setup:
     # NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces -> (rho, u, v, w, p) of their primitives_callable, None where the
     # type takes no entry (SIMPLE_INFLOW: no p; SIMPLE_OUTFLOW: p only); floats or arrays as for `dirichlet`
     bc_values: Dict[str, Tuple] = field(default_factory=dict)
+    # faces with several types (a list in the case file): face -> [dict(kind, mask, values)], mask = bounding_domain on the
+    # face's transverse cells (bool, shaped like the halo slab with extent 1 along the normal), values for DIRICHLET
+    # entries; bc[face] then names the entry the sm_100a kernels fill (the others are applied by the host runtime)
+    bc_multi: Dict[str, list] = field(default_factory=dict)
     # active_physics/is_volume_force + forcings/gravity (source_term_solver.py:163-186)
     is_volume_force: bool = False
     gravity: Tuple[float, float, float] = (0.0, 0.0, 0.0)
@@ -182,47 +186,51 @@ def halo_fill(prims, cons, s: Setup):
     inter = s.interior
     for face in FACES:
         ax = FACE_AXIS[face]
-        kind = s.bc[face]
-        if ax not in s.active or kind == "INACTIVE":
+        if ax not in s.active or s.bc[face] == "INACTIVE":
             continue
         hi = face in ("east", "north", "top")
-        if kind == "PERIODIC":
-            src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
-        elif kind in ("SYMMETRY", "WALL"):
-            src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
-        elif kind in ("ZEROGRADIENT", "DIRICHLET", "NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
-            src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)     # boundary_condition.py:580-595
-        else:
-            raise NotImplementedError(kind)
-        dst = slice(-nh, None) if hi else slice(0, nh)
-        sl_src = [slice(None)] + list(inter)
-        sl_dst = [slice(None)] + list(inter)
-        sl_src[1 + ax] = src
-        sl_dst[1 + ax] = dst
-        hp = prims[tuple(sl_src)]
-        if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: primitives_callable -- constants, or
-            vals = s.dirichlet[face]             # arrays over the face's transverse cells (extent 1 along its normal)
-            hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(5)], axis=0)
-        if kind == "NEUMANN":                    # :825-866: last interior cell + (value * upwind sign) * dx
-            vals = s.bc_values[face]
-            sgn = -1 if hi else 1                # material.py:41-44
-            hp = np.stack([hp[v] + (np.ones_like(hp[0]) * vals[v]) * sgn * s.dx[ax] for v in range(5)], axis=0)
-        if kind == "SIMPLE_INFLOW":              # :966-1022: density and velocity prescribed, pressure from inside
-            vals = s.bc_values[face]
-            hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(4)] + [hp[4]], axis=0)
-        if kind == "SIMPLE_OUTFLOW":             # :1024-1050: everything from inside, pressure prescribed
-            vals = s.bc_values[face]
-            hp = np.stack([hp[v] for v in range(4)] + [np.ones_like(hp[0]) * vals[4]], axis=0)
-        if kind == "SYMMETRY":
-            sign = np.ones((5, 1, 1, 1))
-            sign[1 + ax] *= -1.0
-            hp = hp * sign
-        if kind == "WALL":                       # halos/outer/material.py:473-520: u_halo = 2 u_wall - u_mirror
-            uw = s.wall_velocity.get(face, (0.0, 0.0, 0.0))
-            hp = np.stack([hp[0]] + [2 * (np.ones_like(hp[0]) * uw[k]) - hp[1 + k] for k in range(3)] + [hp[4]], axis=0)
-        hc = cons_from_prims(hp, s.gamma)
-        prims[tuple(sl_dst)] = prims[tuple(sl_dst)] * (1 - 1.0) + hp * 1.0
-        cons[tuple(sl_dst)] = cons[tuple(sl_dst)] * (1 - 1.0) + hc * 1.0
+        # several types on one face (case file: a list with bounding_domain lambdas, material.py:121-277): applied one
+        # after the other, each through its mask over the face's transverse cells
+        entries = s.bc_multi.get(face) or [dict(kind=s.bc[face], mask=1.0, values=None)]
+        for ent in entries:
+            kind, mask = ent["kind"], ent["mask"]
+            if kind == "PERIODIC":
+                src = slice(nh, 2 * nh) if hi else slice(-2 * nh, -nh)
+            elif kind in ("SYMMETRY", "WALL"):
+                src = slice(-nh - 1, -2 * nh - 1, -1) if hi else slice(2 * nh - 1, nh - 1, -1)
+            elif kind in ("ZEROGRADIENT", "DIRICHLET", "NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
+                src = slice(-nh - 1, -nh) if hi else slice(nh, nh + 1)     # boundary_condition.py:580-595
+            else:
+                raise NotImplementedError(kind)
+            dst = slice(-nh, None) if hi else slice(0, nh)
+            sl_src = [slice(None)] + list(inter)
+            sl_dst = [slice(None)] + list(inter)
+            sl_src[1 + ax] = src
+            sl_dst[1 + ax] = dst
+            hp = prims[tuple(sl_src)]
+            if kind == "DIRICHLET":                  # halos/outer/material.py:732-798: primitives_callable -- constants, or
+                vals = ent["values"] if ent["values"] is not None else s.dirichlet[face]   # arrays over the transverse cells
+                hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(5)], axis=0)
+            if kind == "NEUMANN":                    # :825-866: last interior cell + (value * upwind sign) * dx
+                vals = s.bc_values[face]
+                sgn = -1 if hi else 1                # material.py:41-44
+                hp = np.stack([hp[v] + (np.ones_like(hp[0]) * vals[v]) * sgn * s.dx[ax] for v in range(5)], axis=0)
+            if kind == "SIMPLE_INFLOW":              # :966-1022: density and velocity prescribed, pressure from inside
+                vals = s.bc_values[face]
+                hp = np.stack([np.ones_like(hp[0]) * vals[v] for v in range(4)] + [hp[4]], axis=0)
+            if kind == "SIMPLE_OUTFLOW":             # :1024-1050: everything from inside, pressure prescribed
+                vals = s.bc_values[face]
+                hp = np.stack([hp[v] for v in range(4)] + [np.ones_like(hp[0]) * vals[4]], axis=0)
+            if kind == "SYMMETRY":
+                sign = np.ones((5, 1, 1, 1))
+                sign[1 + ax] *= -1.0
+                hp = hp * sign
+            if kind == "WALL":                       # halos/outer/material.py:473-520: u_halo = 2 u_wall - u_mirror
+                uw = s.wall_velocity.get(face, (0.0, 0.0, 0.0))
+                hp = np.stack([hp[0]] + [2 * (np.ones_like(hp[0]) * uw[k]) - hp[1 + k] for k in range(3)] + [hp[4]], axis=0)
+            hc = cons_from_prims(hp, s.gamma)
+            prims[tuple(sl_dst)] = prims[tuple(sl_dst)] * (1 - mask) + hp * mask       # material.py:270-275
+            cons[tuple(sl_dst)] = cons[tuple(sl_dst)] * (1 - mask) + hc * mask
     if s.is_dissipative and len(s.active) > 1:       # halo_manager.py:119-129, :193-199
         prims, cons = edge_halo_fill(prims, cons, s)
     return prims, cons

@@ -108,6 +108,8 @@ FIXTURES = {
         "east": {"type": "SIMPLE_OUTFLOW", "primitives_callable": {"p": 0.1}},
         "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0,
                                                              "p": -0.3}}}), 3, (3,)),
+    # the shipped double Mach reflection example, shrunk: the south face is DIRICHLET for x < 1/6 and SYMMETRY beyond
+    "api/dmr_48x32_dirichlet_symmetry_south_rk3": ("dmr", dict(cells=(48, 32, None)), 8, (8,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

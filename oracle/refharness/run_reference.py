@@ -51,6 +51,7 @@ CASES = {
     "heat1d": ("examples_1D/08_heat_equation", "heat_equation.json"),            # heat flux only (no convective flux)
     "rarefaction": ("examples_1D/04_double_rarefaction", "double_rarefaction.json"),  # flux limiter SIMPLE + interp. limiter
     "heat2d": ("examples_2D/06_heat_equation", "heat_equation.json"),                  # heat flux only, DIRICHLET x4, p(x) at north
+    "dmr": ("examples_2D/08_double_mach_reflection", "double_mach_reflection.json"),   # south: DIRICHLET | SYMMETRY by x, limiter
     "lax": ("examples_1D/03_lax_shock_tube", "lax.json"),                             # FLUX-SPLITTING ROE + WENO6-CU
     "woodward": ("examples_1D/06_woodward_shock_tube", "woodward_shock_tube.json"),   # FLUX-SPLITTING ROE + WENO5-Z, SYMMETRY
 }
@@ -76,7 +77,8 @@ def customize(case, num, cells=None, bc=None, recon=None, riemann=None, integrat
                 case["domain"][ax]["cells"] = int(n)
     if bc is not None:
         for face in ("east", "west", "north", "south", "top", "bottom"):
-            if case["boundary_conditions"][face]["type"] not in ("INACTIVE", "DIRICHLET", "WALL"):
+            if isinstance(case["boundary_conditions"][face], dict) and \
+                    case["boundary_conditions"][face]["type"] not in ("INACTIVE", "DIRICHLET", "WALL"):
                 case["boundary_conditions"][face] = {"type": bc}
     if boundary_conditions is not None:       # face -> the face's whole entry (type + callables)
         for face, entry in boundary_conditions.items():

@@ -65,7 +65,39 @@ def dissipation_from_json(case, num) -> dict:
                 gas_constant=float(case["material_properties"]["equation_of_state"]["specific_gas_constant"]))
 
 
-def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p")):
+def _transverse_mesh(case, face):
+    d = case["domain"]
+    cells = [d[a]["cells"] for a in "xyz"]
+    ax = port.FACE_AXIS[face]
+    trans = [i for i in range(3) if i != ax and cells[i] > 1]
+    centers = []
+    for i in trans:
+        lo, hi = d["xyz"[i]]["range"]
+        dx = (hi - lo) / cells[i]
+        centers.append(np.linspace(lo + dx / 2, hi - dx / 2, cells[i]))
+    mesh = np.meshgrid(*centers, indexing="ij") if centers else []
+    return mesh, [cells[i] if i in trans else 1 for i in range(3)]
+
+
+def multi_type_entries(case, face):
+    """A face given as a list of types with bounding_domain lambdas (halos/outer/material.py:121-277)."""
+    mesh, shape = _transverse_mesh(case, face)
+    out = []
+    for ent in case["boundary_conditions"][face]:
+        mask = np.asarray(eval(ent["bounding_domain"], {"jnp": np, "np": np})(*mesh)).reshape(shape)   # noqa: S307
+        vals = dirichlet_values(case, face, entry=ent) if ent["type"] == "DIRICHLET" else None
+        out.append(dict(kind=ent["type"], mask=mask, values=vals))
+    return out
+
+
+def kernel_type_of(entry):
+    """bc[face] of a multi-type face: the entry the kernels fill (the first that is not DIRICHLET)."""
+    if isinstance(entry, list):
+        return next(e["type"] for e in entry if e["type"] != "DIRICHLET")
+    return entry["type"]
+
+
+def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p"), entry=None):
     """primitives_callable of a DIRICHLET face (halos/outer/material.py:770-790, boundary_condition.py:105-126): floats, or
     lambdas of the ACTIVE transverse coordinates and the time, evaluated on the mesh grid of the face's transverse cell
     centres (single block) and shaped like the halo slab with extent 1 along the normal and the inactive axes."""
@@ -85,7 +117,7 @@ def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p")):
         if k not in keys:                     # SIMPLE_INFLOW takes no p, SIMPLE_OUTFLOW only p
             out.append(None)
             continue
-        v = case["boundary_conditions"][face]["primitives_callable"][k]
+        v = (entry or case["boundary_conditions"][face])["primitives_callable"][k]
         if isinstance(v, str):
             fn = eval(v, {"jnp": np, "np": np})                       # noqa: S307 -- the reference's own contract
             v = np.asarray(fn(*mesh, 0.0), dtype=np.float64).reshape(shape)
@@ -93,6 +125,12 @@ def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p")):
             v = float(v)
         out.append(v)
     return tuple(out)
+
+
+def _type(case, face):
+    """Type of a single-type face (None for a face given as a list of types)."""
+    e = case["boundary_conditions"][face]
+    return None if isinstance(e, list) else e["type"]
 
 
 # entries of primitives_callable the type reads (read_boundary_conditions.py:160-365)
@@ -112,7 +150,8 @@ def setup_from_json(case, num) -> port.Setup:
         frozen_state=(fs if solver == "FLUX-SPLITTING" else g).get("frozen_state", "ARITHMETIC"),
         cells=tuple(d[a]["cells"] for a in "xyz"),
         domain=tuple(tuple(d[a]["range"]) for a in "xyz"),
-        bc={f: case["boundary_conditions"][f]["type"] for f in port.FACES},
+        bc={f: kernel_type_of(case["boundary_conditions"][f]) for f in port.FACES},
+        bc_multi={f: multi_type_entries(case, f) for f in port.FACES if isinstance(case["boundary_conditions"][f], list)},
         gamma=case["material_properties"]["equation_of_state"]["specific_heat_ratio"],
         nh=c["halo_cells"],
         recon=g.get("reconstruction_variable", "PRIMITIVE"),
@@ -127,10 +166,10 @@ def setup_from_json(case, num) -> port.Setup:
         flux_partition=(c.get("positivity", {}) or {}).get("flux_partition", "UNIFORM"),
         wall_velocity={f: tuple(float(case["boundary_conditions"][f].get("wall_velocity_callable", {}).get(k, 0.0))
                                 for k in "uvw")
-                       for f in port.FACES if case["boundary_conditions"][f]["type"] == "WALL"},
-        dirichlet={f: dirichlet_values(case, f) for f in port.FACES if case["boundary_conditions"][f]["type"] == "DIRICHLET"},
-        bc_values={f: dirichlet_values(case, f, BC_VALUE_KEYS[case["boundary_conditions"][f]["type"]]) for f in port.FACES
-                   if case["boundary_conditions"][f]["type"] in BC_VALUE_KEYS},
+                       for f in port.FACES if _type(case, f) == "WALL"},
+        dirichlet={f: dirichlet_values(case, f) for f in port.FACES if _type(case, f) == "DIRICHLET"},
+        bc_values={f: dirichlet_values(case, f, BC_VALUE_KEYS[_type(case, f)]) for f in port.FACES
+                   if _type(case, f) in BC_VALUE_KEYS},
         is_volume_force=bool(num.get("active_physics", {}).get("is_volume_force", False)),
         is_convective_flux=bool(num.get("active_physics", {}).get("is_convective_flux", True)),
         gravity=tuple(float(x) for x in (case.get("forcings", {}) or {}).get("gravity", (0.0, 0.0, 0.0))),

@@ -58,7 +58,7 @@ def _host_runtime(im, s, **cfg_kw):
     rt.device = torch.device("cpu")
     edges = []
     rt.solver = SimpleNamespace(active=s.active, halo_fill_edges=lambda p, c: edges.append(1))
-    rt.host_boundaries = {f: rt._make_host_boundary(f, t, v) for f, (t, v) in rt._host_faces.items()}
+    rt.host_boundaries = {f: rt._make_host_boundary(f, t, v, m) for f, (t, v, m) in rt._host_faces.items()}
     return rt, consts, edges
 
 
@@ -156,3 +156,34 @@ def test_neumann_and_simple_inflow_outflow_reproduce_the_oracle_halo_fill():
     assert not np.array_equal(p0[:, m], ref_p[:, m])
     assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
     assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])
+
+
+def test_several_types_on_one_face_reproduce_the_oracle_halo_fill():
+    """The shipped double Mach reflection example (shrunk): the south face is DIRICHLET for x < 1/6 and SYMMETRY beyond
+    (a list with bounding_domain lambdas, halos/outer/material.py:121-277).  The kernels fill SYMMETRY on the whole
+    face, the host writes the DIRICHLET state inside its bounding domain: halos bit-identical to the oracle's."""
+    from jaxfluids_b200.input_manager import InputManager
+    g, case, num = H.load_golden("api/dmr_48x32_dirichlet_symmetry_south_rk3")
+    im = InputManager(case, num)
+    assert im.case_setup.boundary_condition_setup["south"] == "SYMMETRY" and "south" in im.case_setup.multi_type_setup
+    s = H.setup_from_json(case, num)
+    assert s.bc["south"] == "SYMMETRY" and [e["kind"] for e in s.bc_multi["south"]] == ["DIRICHLET", "SYMMETRY"]
+    rt, consts, edges = _host_runtime(im, s)
+    assert set(rt._host_faces) == {("south", 0)} and set(consts) == {"west"}
+    prims, cons = g["prims0_halo"], g["cons0_halo"]
+    s_kernel = copy.copy(s)
+    s_kernel.bc_multi = {}                                   # what the halo kernel fills: SYMMETRY on the whole face
+    p0, c0 = port.halo_fill(prims, cons, s_kernel)
+    ref_p, ref_c = port.halo_fill(prims, cons, s)
+    m = H.face_halo_mask(s)
+    assert not np.array_equal(p0[:, m], ref_p[:, m])
+    tp, tc = torch.as_tensor(p0.copy()), torch.as_tensor(c0.copy())
+    rt._apply_host_boundaries(tp, tc)
+    assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
+    assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])
+    # bounding domains that do not partition the face are refused
+    bad = copy.deepcopy(case)
+    bad["boundary_conditions"]["south"][1]["bounding_domain"] = "lambda x: x >= 0.5"
+    im_bad = InputManager(bad, num)
+    with pytest.raises(NotImplementedError, match="partition"):
+        _host_runtime(im_bad, s)

@@ -229,6 +229,7 @@ def test_flux_splitting_block_is_read_like_the_reference():
     ("generic/lax100_fs_roe_weno6cu_roefrozen_rk3", dict(convective_solver=1, flux_splitting=1, stencil=6, frozen_state=1)),
     ("api/heat2d_24x20_dirichlet_lambda_noconv_rk3", dict(no_convective_flux=1, heat_flux=1, stencil=1)),
     ("api/riemann2d_16x20_inflow_outflow_visc_rk3", dict(viscous_flux=1, heat_flux=1)),
+    ("api/dmr_48x32_dirichlet_symmetry_south_rk3", dict(interpolation_limiter=1, recon=1)),
 ])
 
 def test_json_options_reach_the_c_config(name, expect, monkeypatch):
@@ -252,7 +253,10 @@ def test_json_options_reach_the_c_config(name, expect, monkeypatch):
         assert getattr(c, key) == value, key
     # NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces reach the kernels as ZEROGRADIENT (3); the host applies their data
     for k, f in enumerate(("east", "west", "north", "south", "top", "bottom")):
-        if case["boundary_conditions"][f]["type"] in ("NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
+        entry = case["boundary_conditions"][f]
+        if isinstance(entry, list):                          # several types: the kernels fill the SYMMETRY entry (2)
+            assert c.bc[k] == 2
+        elif entry["type"] in ("NEUMANN", "SIMPLE_INFLOW", "SIMPLE_OUTFLOW"):
             assert c.bc[k] == 3
 
 

@@ -86,6 +86,8 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
         "north": {"type": "NEUMANN", "primitives_callable": {"rho": 0.1, "u": "lambda x,t: 0.2 * x", "v": 0.0, "w": 0.0, "p": -0.3}},
         "south": {"type": "NEUMANN", "primitives_callable": {"rho": "lambda x,t: 0.3 * jnp.cos(5 * x)", "u": 0.0, "v": 0.1, "w": 0.0,
                                                              "p": 0.2}}}), 2),
+    # the shipped double Mach reflection example: two boundary types on the south face
+    ("dmr", dict(cells=(48, 32, None)), 3),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
