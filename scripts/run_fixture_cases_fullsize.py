@@ -11,7 +11,12 @@ from jaxfluids_b200 import InputManager, InitializationManager, SimulationManage
 
 FULL = {"cavity_24x20_wall_js_visc_rk3": (128, 128, 1), "rti_16x48_dirichlet_gravity_rk3": (64, 256, 1),
         "heat1d_40_dirichlet_noconv_rk3": (100, 1, 1), "sod200_char_hllc_rk3": (1000, 1, 1),
-        "riemann2d_32x32_char_hllc_rk3": (1024, 1024, 1), "tgv12_sym_visc_prandtl_rk3": (128, 128, 128)}
+        "riemann2d_32x32_char_hllc_rk3": (1024, 1024, 1), "tgv12_sym_visc_prandtl_rk3": (128, 128, 128),
+        # the examples added with the generic stencils / flux splitting / host-applied boundaries
+        "generic/lax100_fs_roe_weno6cu_rk3": (200, 1, 1), "generic/woodward200_fs_roe_weno5z_rk3": (400, 1, 1),
+        "api/heat2d_24x20_dirichlet_lambda_noconv_rk3": (100, 100, 1),
+        "api/dmr_48x32_dirichlet_symmetry_south_rk3": (256, 256, 1),
+        "generic/tgv_10x8x12_per_minmod_char_hllc_rk2ls4": (64, 64, 64), "generic/tgv_10x8x12_sym_char_hllclm_rk3": (64, 64, 64)}
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 for name, cells in FULL.items():
     _, case, num = H.load_golden(name)
