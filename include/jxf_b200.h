@@ -45,7 +45,8 @@ enum { JXF_FROZEN_ARITHMETIC = 0, JXF_FROZEN_ROE = 1 };
 enum { JXF_STENCIL_WENO5Z = 0, JXF_STENCIL_WENO5JS = 1, JXF_STENCIL_WENO1 = 2, JXF_STENCIL_WENO3JS = 3,
        JXF_STENCIL_WENO3Z = 4, JXF_STENCIL_TENO5 = 5, JXF_STENCIL_WENO6CU = 6, JXF_STENCIL_KOREN = 7, JXF_STENCIL_MC = 8,
        JXF_STENCIL_MINMOD = 9, JXF_STENCIL_SUPERBEE = 10, JXF_STENCIL_VANALBADA = 11, JXF_STENCIL_VANLEER = 12,
-       JXF_STENCIL_WENO3N = 13, JXF_STENCIL_CENTRAL2 = 14, JXF_STENCIL_TENO6 = 15 };
+       JXF_STENCIL_WENO3N = 13, JXF_STENCIL_CENTRAL2 = 14, JXF_STENCIL_TENO6 = 15,
+       JXF_STENCIL_TENO5A = 16 /* teno/teno5_a.py */, JXF_STENCIL_TENO6A = 17 /* teno/teno6_a.py */ };
 /* ref: solvers/riemann_solvers/__init__.py:16-34 */
 enum { JXF_RIEMANN_HLLC = 0, JXF_RIEMANN_RUSANOV = 1, JXF_RIEMANN_HLL = 2 /* HLL.py; uses jxf_config.signal_speed */,
        JXF_RIEMANN_HLLCLM = 3 /* HLLCLM.py (low-Mach HLLC, Fleischmann et al. 2020); uses jxf_config.signal_speed */,

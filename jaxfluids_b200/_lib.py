@@ -25,7 +25,7 @@ FROZEN_STATE = {"ARITHMETIC": 0, "ROE": 1}
 # ids = include/jxf_b200.h JXF_STENCIL_*; >= 2: the generic (reference-order) kernel instantiations
 STENCIL = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z": 4, "TENO5": 5, "WENO6-CU": 6,
            "KOREN": 7, "MC": 8, "MINMOD": 9, "SUPERBEE": 10, "VANALBADA": 11, "VANLEER": 12, "WENO3-N": 13,
-           "CENTRAL2": 14, "TENO6": 15}
+           "CENTRAL2": 14, "TENO6": 15, "TENO5-A": 16, "TENO6-A": 17}
 FLUX_LIMITER = {None: 0, False: 0, "SIMPLE": 1, "NASA": 2}
 FLUX_PARTITION = {"UNIFORM": 0, "CELLSIZE": 1}
 RIEMANN = {"HLLC": 0, "RUSANOV": 1, "HLL": 2, "HLLC-LM": 3, "AUSMP": 4}

@@ -1178,7 +1178,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     if (cfg->n[i] < 1) return fail(JXF_ERR_BAD_ARG, "jxf_create: n[%d]=%d", i, cfg->n[i]);
   if (cfg->recon < JXF_RECON_PRIMITIVE || cfg->recon > JXF_RECON_CHAR_CONSERVATIVE)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_variable id %d not implemented on the B200 path", cfg->recon);
-  if (cfg->stencil < JXF_STENCIL_WENO5Z || cfg->stencil > JXF_STENCIL_TENO6)
+  if (cfg->stencil < JXF_STENCIL_WENO5Z || cfg->stencil > JXF_STENCIL_TENO6A)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: reconstruction_stencil id %d not implemented on the B200 path", cfg->stencil);
   if (cfg->riemann < JXF_RIEMANN_HLLC || cfg->riemann > JXF_RIEMANN_AUSMP)
     return fail(JXF_ERR_UNSUPPORTED, "jxf_create: riemann_solver id %d not implemented on the B200 path", cfg->riemann);
@@ -1531,6 +1531,9 @@ static int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   return check_launch("sweep");
 }
 
+// stencil id in the option word: bits 11-14, the fifth id bit at bit 22 (numerics.cuh stencil_id)
+static int stencil_bits(int stencil) { return ((stencil & 15) << 11) | ((stencil >> 4) << 22); }
+
 // Godunov setups the tuned instantiations do not cover (numerics.cuh STENCIL_GENERIC)
 static bool generic_path(const jxf_solver* s) {
   return s->cfg.stencil >= JXF_STENCIL_WENO1 || s->cfg.recon >= JXF_RECON_CONSERVATIVE || s->cfg.frozen_state == JXF_FROZEN_ROE;
@@ -1594,9 +1597,9 @@ static SweepArgs base_args(const jxf_solver* s, int axis, const double* prims, d
                 : s->cfg.riemann == JXF_RIEMANN_AUSMP ? RIEMANN_ALT_AUSMP : 0) << 15) |
               (s->cfg.flux_limiter << 9) |
               // generic instantiations: stencil id (numerics.cuh ALT_*) | reconstruction variable << 19 | ROE << 21
-              (generic_path(s) ? (s->cfg.stencil << 11) | (s->cfg.recon << 19) | (s->cfg.frozen_state << 21) : 0);
+              (generic_path(s) ? stencil_bits(s->cfg.stencil) | (s->cfg.recon << 19) | (s->cfg.frozen_state << 21) : 0);
   if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING)       // stencil id | eigenvalue choice << 17 | ROE << 21
-    a.limiter = (s->cfg.stencil << 11) | (s->cfg.flux_splitting << 17) | (s->cfg.frozen_state << 21);
+    a.limiter = stencil_bits(s->cfg.stencil) | (s->cfg.flux_splitting << 17) | (s->cfg.frozen_state << 21);
   // positivity flux limiter: lambda = dt / dx * sigma (limiter_flux.py:202-205, compute_partition :681-720)
   a.fl.dt = s->dt_bound;
   a.fl.inv_dx = s->cfg.inv_dx[axis];
@@ -2040,8 +2043,8 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
   (void)bx; (void)st; (void)axis; (void)riemann; (void)gamma;
   // stencils other than the two WENO5 forms: the generic instantiations + the stencil id in the option word
   const int stencil = recon >> 1;
-  if (recon < 0 || stencil > JXF_STENCIL_TENO6) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
-  const int opt = stencil >= JXF_STENCIL_WENO1 ? (stencil << 11) | ((recon & 1) << 19) : 0;
+  if (recon < 0 || stencil > JXF_STENCIL_TENO6A) return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
+  const int opt = stencil >= JXF_STENCIL_WENO1 ? stencil_bits(stencil) | ((recon & 1) << 19) : 0;
   recon = (recon & 1) + 2 * std::min(stencil, (int)STENCIL_GENERIC);
   (void)opt;
 #define JXF_DBG_CASE(A, R, S)                                                                     \

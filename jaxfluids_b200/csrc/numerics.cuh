@@ -22,7 +22,7 @@ enum { STENCIL_WENO5Z = 0, STENCIL_WENO5JS = 1, STENCIL_GENERIC = 2 };   // reco
 enum { ALT_WENO5Z = 0, ALT_WENO5JS = 1,   // reference-order forms of the two tuned stencils (flux-splitting path only)
        ALT_WENO1 = 2, ALT_WENO3JS = 3, ALT_WENO3Z = 4, ALT_TENO5 = 5, ALT_WENO6CU = 6, ALT_KOREN = 7, ALT_MC = 8,
        ALT_MINMOD = 9, ALT_SUPERBEE = 10, ALT_VANALBADA = 11, ALT_VANLEER = 12, ALT_WENO3N = 13, ALT_CENTRAL2 = 14,
-       ALT_TENO6 = 15 };
+       ALT_TENO6 = 15, ALT_TENO5A = 16, ALT_TENO6A = 17 };   // ids >= 16: bit 22 of the option word is the fifth id bit
 enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
 // HLLC wave-speed estimate (signal_speeds.py): a run-time option `sig` of riemann_flux (uniform branch), packed
 // with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4) | (HLL << 8), HLL = the HLL
@@ -125,9 +125,21 @@ template <> struct AxisIds<2> { static constexpr int un = 3, t0 = 1, t1 = 2; };
 //   TENO5            teno/teno5.py:32-71 (C = 1, q = 6, C_T = 1e-5, d = (0.05, 0.55, 0.40)), weno5_base.py:34-51
 //   WENO6-CU         weno6_base.py:32-58, weno/weno6_cu.py:36-63 (C = 20)
 //   TENO6            teno6_base.py:32-62, teno/teno6.py:42-73 (C = 1, q = 6, C_T = 1e-7, d = (.05, .45, .3, .2))
+//   TENO5-A / TENO6-A teno/teno5_a.py:46-101, teno/teno6_a.py:42-140: the cut-off C_T adapts to the local smoothness
+//                    (TENO5-A reads the WENO5 weights of its base class -- its own are stored under another name)
 //   KOREN .. VANLEER muscl/muscl3.py:39-77 with stencils/limiter.py:6-22 (the two sides are not mirror images of
 //                    one formula, hence `j`)
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double teno_a_eta(double a, double b, double eps_d) {
+  return (fabs(2.0 * a * b) + eps_d) / (a * a + b * b + eps_d);
+}
+__device__ __forceinline__ double teno_a_ct(double eta, double Cr, double alpha_1, double alpha_2) {
+  const double m = 1.0 - fmin(1.0, eta / Cr);
+  const double x = 1.0 - m, x2 = x * x;
+  const double g = (x2 * x2) * (1.0 + 4.0 * m);              // jnp.power(1 - m, 4) * (1 + 4 m)
+  const double beta_bar = ceil(alpha_1 - alpha_2 * (1.0 - g)) - 1.0;
+  return pow(10.0, -beta_bar);
+}
 __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
                                                double q5) {
   const double eps = kStencilEps;
@@ -155,7 +167,8 @@ __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double 
     const double p_1 = 0.5 * q2 + 0.5 * q3;
     return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1;
   }
-  if (id == ALT_TENO5 || id == ALT_WENO6CU || id == ALT_TENO6 || id == ALT_WENO5Z || id == ALT_WENO5JS) {
+  if (id == ALT_TENO5 || id == ALT_WENO6CU || id == ALT_TENO6 || id == ALT_WENO5Z || id == ALT_WENO5JS || id == ALT_TENO5A ||
+      id == ALT_TENO6A) {
     const double s0 = q0 - 2.0 * q1 + q2, t0 = q0 - 4.0 * q1 + 3.0 * q2;
     const double s1 = q1 - 2.0 * q2 + q3, t1 = q1 - q3;
     const double s2 = q2 - 2.0 * q3 + q4, t2 = 3.0 * q2 - 4.0 * q3 + q4;
@@ -180,16 +193,24 @@ __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double 
       const double one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2);
       return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2;
     }
-    if (id == ALT_TENO5) {
+    if (id == ALT_TENO5 || id == ALT_TENO5A) {
       const double tau_5 = fabs(beta_0 - beta_2);
       // jnp.power(x, 6): the value only feeds the cut-off comparison below
       const double x0 = 1.0 + tau_5 / (beta_0 + eps), x1 = 1.0 + tau_5 / (beta_1 + eps), x2 = 1.0 + tau_5 / (beta_2 + eps);
       const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2;
       const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2;
       const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2);
-      const double w0 = 0.05 * ((gamma_0 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
-      const double w1 = 0.55 * ((gamma_1 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
-      const double w2 = 0.40 * ((gamma_2 * one_gamma_sum < 1e-5) ? 0.0 : 1.0);
+      double CT = 1e-5, d0 = 0.05, d1 = 0.55, d2 = 0.40;
+      if (id == ALT_TENO5A) {
+        const double eps_d = 2.842105263157895e-07;          // 0.9 Cr / (1 - Cr) xi^2, Cr = 0.24, xi = 1e-3
+        const double eta = fmin(teno_a_eta(q2 - q1, q1 - q0, eps_d),
+                                fmin(teno_a_eta(q3 - q2, q2 - q1, eps_d), teno_a_eta(q4 - q3, q3 - q2, eps_d)));
+        CT = teno_a_ct(eta, 0.24, 10.0, 5.0);
+        d0 = 0.1; d1 = 0.6; d2 = 0.3;
+      }
+      const double w0 = d0 * ((gamma_0 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double w1 = d1 * ((gamma_1 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double w2 = d2 * ((gamma_2 * one_gamma_sum < CT) ? 0.0 : 1.0);
       const double one_dk = 1.0 / (w0 + w1 + w2 + eps);
       return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2;
     }
@@ -201,24 +222,41 @@ __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double 
         q3 * (17195652 * q3 - 15880404 * q4 + 2863984 * q5) +
         q4 * (3824847 * q4 - 1429976 * q5) +
         139633 * q5 * q5);
-    if (id == ALT_TENO6) {
-      const double beta_3 = 1.0 / 240.0 * (
+    if (id == ALT_TENO6 || id == ALT_TENO6A) {
+      const bool adaptive = (id == ALT_TENO6A);
+      double beta_6a = beta_6;
+      double beta_3 = 1.0 / 240.0 * (
           q2 * (2107 * q2 - 9402 * q3 + 7042 * q4 - 1854 * q5)
           + q3 * (11003 * q3 - 17246 * q4 + 4642 * q5)
           + q4 * (7043 * q4 - 3882 * q5)
           + 547 * q5 * q5);
       const double p_3 = (3.0 / 12.0) * q2 + (13.0 / 12.0) * q3 + (-5.0 / 12.0) * q4 + (1.0 / 12.0) * q5;
-      const double tau_6 = fabs(beta_6 - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2));
+      if (adaptive) {                                        // is_positivity_limiter_smoothness
+        beta_3 = fabs(beta_3);
+        beta_6a = fabs(beta_6a);
+      }
+      const double tau_6 = fabs(beta_6a - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2));
       const double x0 = 1.0 + tau_6 / (beta_0 + eps), x1 = 1.0 + tau_6 / (beta_1 + eps);
       const double x2 = 1.0 + tau_6 / (beta_2 + eps), x3 = 1.0 + tau_6 / (beta_3 + eps);
       const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2, c3 = x3 * x3 * x3;
       const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2, gamma_3 = c3 * c3;
       const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2 + gamma_3);
-      const double w0 = 0.050 * ((gamma_0 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
-      const double w1 = 0.450 * ((gamma_1 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
-      const double w2 = 0.300 * ((gamma_2 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
-      const double w3 = 0.200 * ((gamma_3 * one_gamma_sum < 1e-7) ? 0.0 : 1.0);
-      const double one_dk = 1.0 / (w0 + w1 + w2 + w3 + eps);
+      double CT = 1e-7, d0 = 0.050, d1 = 0.450, d2 = 0.300, d3 = 0.200;
+      if (adaptive) {
+        const double eps_d = 1.8433734939759037e-07;         // 0.9 Cr / (1 - Cr) xi^2, Cr = 0.17, xi = 1e-3
+        const double f0 = q1 - q0, f1 = q2 - q1, f2 = q3 - q2, f3 = q4 - q3, f4 = q5 - q4;
+        double eta = teno_a_eta(f1, f0, eps_d);
+        eta = fmin(eta, teno_a_eta(f2, f1, eps_d));
+        eta = fmin(eta, teno_a_eta(f3, f2, eps_d));
+        eta = fmin(eta, teno_a_eta(f4, f3, eps_d));
+        CT = teno_a_ct(eta, 0.17, 10.5, 4.5);
+        d0 = 0.0855682281039113; d1 = 0.4294317718960898; d2 = 0.1727270875843552; d3 = 0.3122729124156450;
+      }
+      const double w0 = d0 * ((gamma_0 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double w1 = d1 * ((gamma_1 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double w2 = d2 * ((gamma_2 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double w3 = d3 * ((gamma_3 * one_gamma_sum < CT) ? 0.0 : 1.0);
+      const double one_dk = adaptive ? 1.0 / (w0 + w1 + w2 + w3) : 1.0 / (w0 + w1 + w2 + w3 + eps);
       return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3;
     }
     const double beta_3 = beta_6;       // weno6_base.py calls the six-point indicator beta_3
@@ -1418,6 +1456,9 @@ __device__ JXF_NOINLINE Vec10 reconstruct_conservative(Win6 W, double gamma, int
   return o;
 }
 
+// generic stencil id of the option word: bits 11-14, fifth bit at bit 22
+__device__ __forceinline__ int stencil_id(int opt) { return ((opt >> 11) & 15) | (((opt >> 22) & 1) << 4); }
+
 // Interpolation limiter (solvers/positivity/limiter_interpolation.py:77-209, SINGLE-PHASE; eps from
 // config/precision.py:54): a reconstructed state whose density is < 1e-12, or whose pressure then is < 1e-10,
 // falls back to the first-order state (the adjacent cell: window index 2 for the left, 3 for the right state) --
@@ -1509,12 +1550,12 @@ __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma,
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
-      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3, (opt >> 21) & 1);
+      flux_splitting_face<A>(w, gamma, F, stencil_id(opt), (opt >> 17) & 3, (opt >> 21) & 1);
       return;
     }
   }
   double pl[5], pr[5];
-  reconstruct<A, RECON>(w, gamma, pl, pr, (opt >> 11) & 15, (opt >> 19) & 7);
+  reconstruct<A, RECON>(w, gamma, pl, pr, stencil_id(opt), (opt >> 19) & 7);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
@@ -1550,12 +1591,12 @@ __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double 
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
-      flux_splitting_face<A>(w, gamma, F, (opt >> 11) & 15, (opt >> 17) & 3, (opt >> 21) & 1);
+      flux_splitting_face<A>(w, gamma, F, stencil_id(opt), (opt >> 17) & 3, (opt >> 21) & 1);
       return;
     }
   }
   double pl[5], pr[5];
-  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy, (opt >> 11) & 15, (opt >> 19) & 7);
+  reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy, stencil_id(opt), (opt >> 19) & 7);
   limit_interpolation(pl, w, 2, lim);
   limit_interpolation(pr, w, 3, lim);
 #if JXF_RIEMANN_MAIN

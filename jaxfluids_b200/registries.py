@@ -51,7 +51,8 @@ DICT_SPATIAL_RECONSTRUCTION = {"WENO5-Z": "WENO5Z", "WENO5-JS": "WENO5JS", "WENO
                                "WENO3-Z": "WENO3Z", "TENO5": "TENO5", "WENO6-CU": "WENO6CU", "KOREN": "KOREN",
                                "MC": "MC", "MINMOD": "MINMOD", "SUPERBEE": "SUPERBEE", "VANALBADA": "VANALBADA",
                                "VANLEER": "VANLEER", "WENO3-N": "WENO3N",
-                               "CENTRAL2": "CentralSecondOrderReconstruction", "TENO6": "TENO6"}
+                               "CENTRAL2": "CentralSecondOrderReconstruction", "TENO6": "TENO6", "TENO5-A": "TENO5A",
+                               "TENO6-A": "TENO6A"}
 # PRIMITIVE / CHAR-PRIMITIVE with the ARITHMETIC frozen state are the tuned kernels; the conservative forms and ROE run
 # in the generic (reference-order) instantiations
 TUPLE_RECONSTRUCTION_VARIABLES = ("PRIMITIVE", "CONSERVATIVE", "CHAR-PRIMITIVE", "CHAR-CONSERVATIVE")
@@ -73,7 +74,7 @@ BOUNDARY_VALUE_KEYS = {"DIRICHLET": ("rho", "u", "v", "w", "p"), "NEUMANN": ("rh
 # weno1_js.py: 1, central_2.py:21, teno6_base.py:16)
 REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3, "WENO1": 1, "WENO3-JS": 2, "WENO3-Z": 2, "TENO5": 3, "WENO6-CU": 3,
                   "KOREN": 2, "MC": 2, "MINMOD": 2, "SUPERBEE": 2, "VANALBADA": 2, "VANLEER": 2, "WENO3-N": 2,
-                  "CENTRAL2": 1, "TENO6": 3}
+                  "CENTRAL2": 1, "TENO6": 3, "TENO5-A": 3, "TENO6-A": 3}
 KERNEL_HALOS = 3          # the sweep kernels always stage 3 cells on either side of a face
 
 

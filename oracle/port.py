@@ -498,6 +498,84 @@ def teno6(q, j):
     return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3
 
 
+def teno5a(q, j):
+    """teno/teno5_a.py:46-101.  The class stores its optimised weights in `dr_` but reads `_dr`, i.e. the WENO5 weights
+    of its base class (weno5_base.py:21) -- restated as the reference computes."""
+    u_imm, u_im, u_i, u_ip, u_ipp = q[:5]
+    beta_0, beta_1, beta_2, p_0, p_1, p_2 = _weno5_parts(u_imm, u_im, u_i, u_ip, u_ipp)
+    tau_5 = np.abs(beta_0 - beta_2)
+    gamma_0 = np.power(1.0 + tau_5 / (beta_0 + STENCIL_EPS), 6)
+    gamma_1 = np.power(1.0 + tau_5 / (beta_1 + STENCIL_EPS), 6)
+    gamma_2 = np.power(1.0 + tau_5 / (beta_2 + STENCIL_EPS), 6)
+    one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2)
+    # eta_k pairs (u_i - u_im, u_im - u_imm), (u_ip - u_i, u_i - u_im), (u_ipp - u_ip, u_ip - u_i): :62-68, written there
+    # with the later difference first
+    CT = _teno_a_ct_pairs([(u_i - u_im, u_im - u_imm), (u_ip - u_i, u_i - u_im), (u_ipp - u_ip, u_ip - u_i)], 0.24, 10.0, 5.0,
+                          nested_min=True)
+    w0 = _DR[0] * np.where(gamma_0 * one_gamma_sum < CT, 0, 1)
+    w1 = _DR[1] * np.where(gamma_1 * one_gamma_sum < CT, 0, 1)
+    w2 = _DR[2] * np.where(gamma_2 * one_gamma_sum < CT, 0, 1)
+    one_dk = 1.0 / (w0 + w1 + w2 + STENCIL_EPS)
+    return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2
+
+
+def _teno_a_ct_pairs(pairs, Cr, alpha_1, alpha_2, nested_min=False):
+    """C_T from explicit (later, earlier) difference pairs; the arithmetic of both TENO-A classes:
+    (|2 a b| + eps) / (a^2 + b^2 + eps), the minimum over the pairs, m, g, beta_bar, 10^-beta_bar."""
+    eps_d = 0.9 * Cr / (1 - Cr) * 1e-3 ** 2
+    etas = [(np.abs(2 * a * b) + eps_d) / (a ** 2 + b ** 2 + eps_d) for a, b in pairs]
+    if nested_min:                                  # teno5_a.py:70: min(eta_0, min(eta_1, eta_2))
+        eta = np.minimum(etas[0], np.minimum(etas[1], etas[2]))
+    else:                                           # teno6_a.py:124-137: running minimum
+        eta = etas[0]
+        for e in etas[1:]:
+            eta = np.minimum(eta, e)
+    m = 1 - np.minimum(1.0, eta / Cr)
+    g = np.power((1 - m), 4) * (1 + 4 * m)
+    beta_bar = alpha_1 - alpha_2 * (1 - g)
+    beta_bar = np.ceil(beta_bar) - 1.0
+    return np.power(10, (-beta_bar))
+
+
+_DR_TENO6A = (0.0855682281039113, 0.4294317718960898, 0.1727270875843552, 0.3122729124156450)
+
+
+def teno6a(q, j):
+    """teno/teno6_a.py:42-102 (C = 1, q = 6, Cr = 0.17, alpha = (10.5, 4.5), |beta_3|, |beta_6|, no eps in 1/sum w)."""
+    u_imm, u_im, u_i, u_ip, u_ipp, u_ippp = q
+    beta_0, beta_1, beta_2, p_0, p_1, p_2 = _weno5_parts(u_imm, u_im, u_i, u_ip, u_ipp)
+    beta_3 = 1.0 / 240.0 * (
+        u_i * (2107 * u_i - 9402 * u_ip + 7042 * u_ipp - 1854 * u_ippp)
+        + u_ip * (11003 * u_ip - 17246 * u_ipp + 4642 * u_ippp)
+        + u_ipp * (7043 * u_ipp - 3882 * u_ippp)
+        + 547 * u_ippp * u_ippp)
+    beta_6 = 1.0 / 10080 / 12 * (
+        271779 * u_imm * u_imm +
+        u_imm * (-2380800 * u_im + 4086352 * u_i - 3462252 * u_ip + 1458762 * u_ipp - 245620 * u_ippp) +
+        u_im * (5653317 * u_im - 20427884 * u_i + 17905032 * u_ip - 7727988 * u_ipp + 1325006 * u_ippp) +
+        u_i * (19510972 * u_i - 35817664 * u_ip + 15929912 * u_ipp - 2792660 * u_ippp) +
+        u_ip * (17195652 * u_ip - 15880404 * u_ipp + 2863984 * u_ippp) +
+        u_ipp * (3824847 * u_ipp - 1429976 * u_ippp) +
+        139633 * u_ippp * u_ippp)
+    p_3 = _CR_TENO6_3[0] * u_i + _CR_TENO6_3[1] * u_ip + _CR_TENO6_3[2] * u_ipp + _CR_TENO6_3[3] * u_ippp
+    beta_3 = np.abs(beta_3)
+    beta_6 = np.abs(beta_6)
+    tau_6 = np.abs(beta_6 - 1 / 6 * (beta_0 + 4 * beta_1 + beta_2))
+    gamma_0 = (1.0 + tau_6 / (beta_0 + STENCIL_EPS)) ** 6
+    gamma_1 = (1.0 + tau_6 / (beta_1 + STENCIL_EPS)) ** 6
+    gamma_2 = (1.0 + tau_6 / (beta_2 + STENCIL_EPS)) ** 6
+    gamma_3 = (1.0 + tau_6 / (beta_3 + STENCIL_EPS)) ** 6
+    one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2 + gamma_3)
+    d = [u_im - u_imm, u_i - u_im, u_ip - u_i, u_ipp - u_ip, u_ippp - u_ipp]
+    CT = _teno_a_ct_pairs([(d[1], d[0]), (d[2], d[1]), (d[3], d[2]), (d[4], d[3])], 0.17, 10.5, 4.5)
+    w0 = _DR_TENO6A[0] * np.where(gamma_0 * one_gamma_sum < CT, 0, 1)
+    w1 = _DR_TENO6A[1] * np.where(gamma_1 * one_gamma_sum < CT, 0, 1)
+    w2 = _DR_TENO6A[2] * np.where(gamma_2 * one_gamma_sum < CT, 0, 1)
+    w3 = _DR_TENO6A[3] * np.where(gamma_3 * one_gamma_sum < CT, 0, 1)
+    one_dk = 1.0 / (w0 + w1 + w2 + w3)
+    return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3
+
+
 # stencils/limiter.py:6-22
 MUSCL_LIMITERS = {
     "KOREN": lambda r: np.maximum(0, np.minimum(2 * r, np.minimum((1 + 2 * r) / 3, 2))),
@@ -533,11 +611,11 @@ def _muscl3(limiter):
 STENCILS = {"WENO5-Z": lambda q, j: weno5z(*q[:5]), "WENO5-JS": lambda q, j: weno5js(*q[:5]),
             "WENO1": weno1, "WENO3-JS": weno3js, "WENO3-Z": weno3z, "TENO5": teno5, "WENO6-CU": weno6cu,
             **{name: _muscl3(name) for name in MUSCL_LIMITERS}, "WENO3-N": weno3n, "CENTRAL2": central2,
-            "TENO6": teno6}
+            "TENO6": teno6, "TENO5-A": teno5a, "TENO6-A": teno6a}
 # halo cells the stencil itself needs (required_halos of the reference classes; the sm_100a kernels always stage
 # 3 cells on either side of a face)
 REQUIRED_HALOS = {"WENO5-Z": 3, "WENO5-JS": 3, "WENO1": 1, "WENO3-JS": 2, "WENO3-Z": 2, "TENO5": 3, "WENO6-CU": 3,
-                  **{name: 2 for name in MUSCL_LIMITERS}, "WENO3-N": 2, "CENTRAL2": 1, "TENO6": 3}
+                  **{name: 2 for name in MUSCL_LIMITERS}, "WENO3-N": 2, "CENTRAL2": 1, "TENO6": 3, "TENO5-A": 3, "TENO6-A": 3}
 
 
 def _window(prims, axis, s: Setup):

@@ -110,6 +110,8 @@ FIXTURES = {
                                                              "p": -0.3}}}), 3, (3,)),
     # the shipped double Mach reflection example, shrunk: the south face is DIRICHLET for x < 1/6 and SYMMETRY beyond
     "api/dmr_48x32_dirichlet_symmetry_south_rk3": ("dmr", dict(cells=(48, 32, None)), 8, (8,)),
+    "generic/sod100_teno6a_char_hllc_rk3": ("sod", dict(cells=(100, None, None), stencil="TENO6-A"), 10, (10,)),
+    "generic/riemann2d_16x20_teno5a_prim_hllc_rk3": ("riemann2d", dict(cells=(16, 20, None), stencil="TENO5-A", recon="PRIMITIVE"), 3, (3,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),
@@ -118,8 +120,8 @@ FIXTURES = {
                                                           integrator="RK2"), 10, (10,)),
 }
 
-GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU", "KOREN", "MC",
-                    "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
+GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO5-A", "TENO6", "TENO6-A", "WENO6-CU",
+                    "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
 
 
 def make_stencil_fixture():

@@ -37,8 +37,8 @@ def api_golden_names():
     return sorted("api/" + os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "api", "*.npz")))
 
 
-GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU", "KOREN", "MC",
-                    "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
+GENERIC_STENCILS = ("WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO5-A", "TENO6", "TENO6-A", "WENO6-CU",
+                    "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER")
 
 
 def load_golden(name):

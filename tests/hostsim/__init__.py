@@ -30,7 +30,12 @@ def load(fma=True, reference_order=False):
 
 STENCIL_IDS = {"WENO5-Z": 0, "WENO5-JS": 1, "WENO1": 2, "WENO3-JS": 3, "WENO3-Z": 4, "TENO5": 5, "WENO6-CU": 6,
                "KOREN": 7, "MC": 8, "MINMOD": 9, "SUPERBEE": 10, "VANALBADA": 11, "VANLEER": 12, "WENO3-N": 13,
-               "CENTRAL2": 14, "TENO6": 15}   # JXF_STENCIL_*
+               "CENTRAL2": 14, "TENO6": 15, "TENO5-A": 16, "TENO6-A": 17}   # JXF_STENCIL_*
+
+
+def _stencil_bits(st):
+    """stencil id in the option word: bits 11-14 + the fifth id bit at bit 22 (jxf_b200.cu stencil_bits)."""
+    return ((st & 15) << 11) | ((st >> 4) << 22)
 
 
 VARIABLE_IDS = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1, "CONSERVATIVE": 2, "CHAR-CONSERVATIVE": 3}   # JXF_RECON_*
@@ -62,8 +67,8 @@ def _opt(s):
     alt = {"HLLC-LM": 1, "AUSMP": 2}.get(s.riemann, 0)              # RIEMANN_ALT_* (ride on the RUSANOV instantiations)
     roe = 1 if s.frozen_state == "ROE" else 0
     if s.convective_solver == "FLUX-SPLITTING":          # stencil id (all of them) + eigenvalue choice + frozen state
-        return (st << 11) | ({"ROE": 1, "CLLF": 2, "LLF": 3}[s.flux_splitting] << 17) | (roe << 21)
-    gen = (st << 11) | (VARIABLE_IDS[s.recon] << 19) | (roe << 21) if _generic(s) else 0
+        return _stencil_bits(st) | ({"ROE": 1, "CLLF": 2, "LLF": 3}[s.flux_splitting] << 17) | (roe << 21)
+    gen = _stencil_bits(st) | (VARIABLE_IDS[s.recon] << 19) | (roe << 21) if _generic(s) else 0
     return lim | (sig << 4) | ((1 if s.riemann == "HLL" else 0) << 8) | (fl << 9) | gen | (alt << 15)
 
 

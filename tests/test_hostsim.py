@@ -175,7 +175,7 @@ def test_generic_stencils_host_simulated(stencil, variable):
     assert H.rel_linf(tot_march, g[f"rhs_{key}"], scale=scales) <= H.TOL_RHS
 
 
-@pytest.mark.parametrize("stencil", ["WENO3-Z", "TENO5", "WENO6-CU", "VANALBADA"])
+@pytest.mark.parametrize("stencil", ["WENO3-Z", "TENO5", "WENO6-CU", "VANALBADA", "TENO5-A", "TENO6-A"])
 def test_generic_stencils_3d_all_axes_host_simulated(stencil):
     """Every sweep axis (the axis only enters through the velocity roles) and both reconstruction variables."""
     for cells, recon, bc in [((8, 10, 12), "CHAR-PRIMITIVE", "SYMMETRY"), ((9, 8, 10), "PRIMITIVE", "PERIODIC")]:

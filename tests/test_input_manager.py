@@ -71,7 +71,7 @@ GOD = ("conservatives", "convective_fluxes", "godunov")
     (GOD + ("riemann_solver",), "LAX-FRIEDRICHS"),
     (GOD + ("riemann_solver",), "CATUM"),
     (GOD + ("signal_speed",), "DAVIS2"),
-    (GOD + ("reconstruction_stencil",), "TENO6-A"),
+    (GOD + ("reconstruction_stencil",), "TENO8"),
     (GOD + ("reconstruction_stencil",), "WENO7-JS"),
     (("conservatives", "convective_fluxes", "convective_solver"), "ALDM"),
     (("active_physics", "is_geometric_source"), True),
@@ -86,7 +86,7 @@ def test_valid_reference_options_outside_the_path_raise_not_implemented(path, va
         InputManager(case, _mod(num, path, value))
 
 
-@pytest.mark.parametrize("stencil", ["WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO6", "WENO6-CU",
+@pytest.mark.parametrize("stencil", ["WENO1", "WENO3-JS", "WENO3-Z", "WENO3-N", "CENTRAL2", "TENO5", "TENO5-A", "TENO6", "TENO6-A", "WENO6-CU",
                                      "KOREN", "MC", "MINMOD", "SUPERBEE", "VANALBADA", "VANLEER"])
 def test_generic_stencil_names_and_rk2_ls4_select_the_path(stencil):
     """The reference's stencil / integrator names select the B200 path unchanged; a halo count that is valid for the

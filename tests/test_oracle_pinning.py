@@ -88,6 +88,8 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
                                                              "p": 0.2}}}), 2),
     # the shipped double Mach reflection example: two boundary types on the south face
     ("dmr", dict(cells=(48, 32, None)), 3),
+    ("sod", dict(cells=(64, None, None), stencil="TENO5-A"), 2),
+    ("tgv", dict(cells=(8, 8, 10), stencil="TENO6-A"), 1),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
