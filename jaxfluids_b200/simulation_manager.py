@@ -23,6 +23,7 @@ from .data_types import (ControlFlowParameters, DiscretizationCounter, EulerInte
                          PositivityCounter, PositivityStateInformation, SimulationBuffers, SolidFieldBuffers,
                          StepInformation, TimeControlVariables, WallClockTimes)
 from .input_manager import InputManager
+from .logger import Logger
 from .parallel import ParallelContext
 from .runtime import BlockRuntime
 
@@ -168,31 +169,27 @@ class SimulationManager:
         self.space_solver = SpaceSolver(rt)
         self.time_integrator = TimeIntegrator(rt, self.numerical_setup.conservatives.time_integration.integrator)
         self.halo_manager = HaloManager(rt)
-        level = self.numerical_setup.output.logging.level
-        self.logger = _NullLogger()
-        if level != "NONE" and self.parallel.rank == 0:
-            self.logger = logging.getLogger("jaxfluids_b200")
-            if not self.logger.handlers:
-                h = logging.StreamHandler()
-                h.setFormatter(logging.Formatter("%(message)s"))
-                self.logger.addHandler(h)
-            self.logger.setLevel(logging.DEBUG if "DEBUG" in level else logging.INFO)
+        log = self.numerical_setup.output.logging
+        # the reference's block layout (io_utils/logger.py); rank 0 only, like the reference's is_multihost guard
+        self.logger = Logger(level=log.level, frequency=log.frequency, is_positivity=log.is_positivity,
+                             is_active=self.parallel.rank == 0)
         self.wall_clock_times = WallClockTimes()
 
     # ------------------------------------------------------------------
     def simulate(self, jxf_buffers: JaxFluidsBuffers, ml_parameters=None, ml_callables=None) -> int:
         """simulation_manager.py:186-295 (no h5 output on this path)."""
-        self.logger.info(f"jaxfluids_b200: case {self.case_setup.general_setup.case_name}, "
-                         f"{self.domain_information.global_number_of_cells} cells, "
-                         f"{self.parallel.world_size} block(s)")
+        self.logger.log_sim_start(self.case_setup.general_setup.case_name,
+                                  self.domain_information.global_number_of_cells, self.parallel.world_size)
+        self.logger.log_initial_time_step(jxf_buffers.time_control_variables, jxf_buffers.step_information)
+        t0 = _time.time()
         self.final_buffers = self.advance(jxf_buffers, ml_parameters, ml_callables)
+        self.logger.log_sim_finish(_time.time() - t0)
         return 0
 
     def advance(self, jxf_buffers: JaxFluidsBuffers, ml_parameters=None, ml_callables=None) -> JaxFluidsBuffers:
         """simulation_manager.py:297-426: host while-loop over steps."""
         tcv = jxf_buffers.time_control_variables
         t, step = tcv.physical_simulation_time, tcv.simulation_step
-        freq = self.numerical_setup.output.logging.frequency
         cells = self.domain_information.cells_per_device
         n_timed, mean = 0, 0.0
         while t < tcv.end_time and step < tcv.end_step:
@@ -207,12 +204,7 @@ class SimulationManager:
                 n_timed += 1
                 mean += (wall - mean) / n_timed
             self.wall_clock_times = WallClockTimes(wall, wall / cells, mean, mean / cells)
-            if step % freq == 0:
-                pos = jxf_buffers.step_information.positivity[-1]
-                self.logger.info(
-                    f"CURRENT TIME = {t:4.4e} | TIME STEP = {tcv.physical_timestep_size:4.4e} | STEP = {step:6d} | "
-                    f"WALL CLOCK TIMESTEP = {wall:4.4e} | WALL CLOCK TIMESTEP CELL = {wall / cells:4.4e} | "
-                    f"MIN DENSITY = {pos.min_density:4.4e} | MIN PRESSURE = {pos.min_pressure:4.4e}")
+            self.logger.log_end_time_step(tcv, jxf_buffers.step_information, self.wall_clock_times)
         return jxf_buffers
 
     def compute_control_flow_params(self, time_control_variables, step_information) -> ControlFlowParameters:
