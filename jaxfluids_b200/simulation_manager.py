@@ -11,7 +11,6 @@ log line, as the reference's host loop does (simulation_manager.py:325-397).
 from __future__ import annotations
 
 import contextlib
-import logging
 import time as _time
 from typing import Dict, List, Optional, Tuple
 
@@ -146,11 +145,6 @@ def compute_time_step_size(primitives, runtime: BlockRuntime) -> float:
     """time_integration/time_step_size.py:15-157 on the device; returns the host float."""
     dt, _, _ = runtime.initial_time_step_and_positivity(primitives)
     return dt
-
-
-class _NullLogger:
-    def __getattr__(self, _):
-        return lambda *a, **k: None
 
 
 class SimulationManager:
