@@ -192,7 +192,7 @@ class CaseSetup(NamedTuple):
     boundary_condition_setup: Dict[str, str]
     initial_condition_setup: Dict[str, Any]
     material_setup: MaterialSetup
-    wall_velocity_setup: Dict[str, Tuple[float, float, float]] = {}      # WALL faces: constant (u, v, w)
+    wall_velocity_setup: Dict[str, Tuple[Any, Any, Any]] = {}            # WALL faces: (u, v, w), floats or lambda strings
     # DIRICHLET / NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces: (rho, u, v, w, p), each a float, a lambda string of
     # (active transverse coordinates, t), or None where the type reads no such entry
     dirichlet_setup: Dict[str, Tuple[Any, Any, Any, Any, Any]] = {}
@@ -208,7 +208,8 @@ def _np_namespace():
     return np
 
 
-def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0):
+def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0,
+                            callable_name: str = "primitives_callable"):
     """primitives_callable of one DIRICHLET face on this block (halos/outer/material.py:770-790 with
     boundary_condition.py:105-126): floats stay floats; lambda strings are evaluated on the mesh grid (indexing "ij") of
     the ACTIVE transverse cell centres and returned shaped like the face's halo slab with extent 1 along the normal and
@@ -226,7 +227,7 @@ def evaluate_dirichlet_face(values, face: str, domain_information, rank: int = 0
         if not isinstance(v, str):
             out.append(None if v is None else float(v))
             continue
-        path = f"boundary_conditions/{face}/primitives_callable/{k}"
+        path = f"boundary_conditions/{face}/{callable_name}/{k}"
         fn = eval(v, {"jnp": _np_namespace(), "np": np})   # noqa: S307 -- same contract as the reference
         names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
         _assert(tuple(names) == labels, f"Input argument labels of lambda for {path} must be {labels}.", "case")
@@ -562,10 +563,9 @@ class InputManager:
                 for k in ("u", "v", "w"):
                     v = get_setup_value(wv_d, k, f"boundary_conditions/{f}/wall_velocity_callable/{k}", (float, str),
                                         False, setup=S)
-                    if isinstance(v, str):
-                        raise NotImplementedError(f"boundary_conditions/{f}/wall_velocity_callable/{k} given as a lambda "
-                                                  "string is not implemented on the B200 path (constant wall velocity only)")
-                    uvw.append(float(v))
+                    # a lambda of the face's active transverse coordinates and the time, like primitives_callable;
+                    # evaluated on the block's transverse cell centres by the runtime (time-independent only)
+                    uvw.append(v if isinstance(v, str) else float(v))
                 walls[f] = tuple(uvw)
             if t in R.BOUNDARY_VALUE_KEYS:
                 # read_boundary_conditions: primitives_callable {rho, u, v, w, p} (SIMPLE_INFLOW: no p, SIMPLE_OUTFLOW:

@@ -80,8 +80,8 @@ class BlockRuntime:
             limit_velocity=num.conservatives.positivity.limit_velocity,
             flux_limiter=num.conservatives.positivity.flux_limiter,
             flux_partition=num.conservatives.positivity.flux_partition,
-            wall_velocity=dict(case.wall_velocity_setup),
             dirichlet=self._dirichlet_constants(case, di, parallel),
+            wall_velocity=self._wall_constants(case, di, parallel),
             is_volume_force=num.active_physics.is_volume_force,
             is_convective_flux=num.active_physics.is_convective_flux,
             gravity=tuple(case.gravity),
@@ -97,7 +97,7 @@ class BlockRuntime:
                                       "halos next to such a face) are not implemented on the B200 path")
         self._host_halo = bool(self.host_boundaries)
         if self._host_halo and self.neighbors:
-            raise NotImplementedError("space-dependent DIRICHLET data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
+            raise NotImplementedError("space-dependent DIRICHLET / WALL data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
                                       "are implemented for single-block runs on the B200 path")
         self.stages = s.stages
         self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
@@ -177,6 +177,23 @@ class BlockRuntime:
                                           "partition the face on the B200 path")
         return consts
 
+    def _wall_constants(self, case, di, parallel) -> Dict[str, Tuple[float, float, float]]:
+        """wall_velocity_callable of the WALL faces (halos/outer/material.py:473-520).  Constant velocities go to the
+        kernels; a face with a space-dependent component gets velocity 0 there (halo = -u_mirror) and the host adds
+        2 u_wall on top (_apply_host_boundaries).  Called after _dirichlet_constants (which creates self._host_faces)."""
+        from .input_manager import evaluate_dirichlet_face
+        consts = {}
+        for f, uvw in dict(case.wall_velocity_setup).items():
+            if self.bc_block.get(f) != "WALL":
+                continue
+            vals = evaluate_dirichlet_face((None,) + tuple(uvw) + (None,), f, di, parallel.rank, "wall_velocity_callable")
+            if all(isinstance(v, float) for v in vals[1:4]):
+                consts[f] = tuple(vals[1:4])
+            else:
+                self._host_faces[f] = ("WALL", vals, None)
+                consts[f] = (0.0, 0.0, 0.0)
+        return consts
+
     def _make_host_boundary(self, face, kind: str, vals, mask=None):
         """(halo index, type, per-variable device slabs) of one face: each prescribed field broadcast over the nh halo
         layers (the reference expands the callable's values along the face normal); NEUMANN slabs hold the increment
@@ -198,6 +215,8 @@ class BlockRuntime:
             if kind == "NEUMANN":
                 dx = np.float64(1.0) / np.float64(self.cfg.inv_dx[ax]) if self._cell_sizes is None else self._cell_sizes[ax]
                 a = a * (-1 if hi else 1) * dx
+            if kind == "WALL":
+                a = 2 * a                                  # u_halo = 2 u_wall - u_mirror (material.py:494-496)
             slabs.append(torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device))
         if mask is not None:
             mask = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(mask, shape))).to(self.device)
@@ -211,7 +230,9 @@ class BlockRuntime:
             for v, slab in enumerate(slabs):
                 if slab is None:
                     continue                               # SIMPLE_INFLOW keeps the copied p, SIMPLE_OUTFLOW rho, u, v, w
-                if kind == "NEUMANN":
+                if kind == "WALL":
+                    h[v] = slab + h[v]                     # 2 u_wall + (-u_mirror): the kernel ran with u_wall = 0
+                elif kind == "NEUMANN":
                     h[v] = h[v] + slab                     # last interior cell (the kernel's copy) + increment
                 elif mask is not None:
                     h[v] = torch.where(mask, slab, h[v])   # one type of a multi-type face, inside its bounding domain

@@ -112,6 +112,10 @@ FIXTURES = {
     "api/dmr_48x32_dirichlet_symmetry_south_rk3": ("dmr", dict(cells=(48, 32, None)), 8, (8,)),
     "generic/sod100_teno6a_char_hllc_rk3": ("sod", dict(cells=(100, None, None), stencil="TENO6-A"), 10, (10,)),
     "generic/riemann2d_16x20_teno5a_prim_hllc_rk3": ("riemann2d", dict(cells=(16, 20, None), stencil="TENO5-A", recon="PRIMITIVE"), 3, (3,)),
+    # the shipped lid-driven cavity with a regularised lid u(x) = 16 x^2 (1 - x)^2: WALL with a space-dependent velocity
+    "api/cavity_24x20_wall_lambda_lid_visc_rk3": ("cavity", dict(cells=(24, 20, None), boundary_conditions={
+        "north": {"type": "WALL", "wall_velocity_callable": {"u": "lambda x,t: 16.0 * x**2 * (1.0 - x)**2", "v": 0.0,
+                                                             "w": 0.0}}}), 4, (4,)),
     # HLLC-LM (HLLCLM.py; the TGV at Mach 0.1 is where its low-Mach limiter acts) and AUSM+ (AUSMP.py)
     "generic/sod100_char_hllclm_rk3": ("sod", dict(cells=(100, None, None), riemann="HLLC-LM"), 10, (10,)),
     "generic/tgv_10x8x12_sym_char_hllclm_rk3": ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 2, (2,)),

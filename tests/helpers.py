@@ -97,7 +97,7 @@ def kernel_type_of(entry):
     return entry["type"]
 
 
-def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p"), entry=None):
+def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p"), entry=None, name="primitives_callable"):
     """primitives_callable of a DIRICHLET face (halos/outer/material.py:770-790, boundary_condition.py:105-126): floats, or
     lambdas of the ACTIVE transverse coordinates and the time, evaluated on the mesh grid of the face's transverse cell
     centres (single block) and shaped like the halo slab with extent 1 along the normal and the inactive axes."""
@@ -117,7 +117,7 @@ def dirichlet_values(case, face, keys=("rho", "u", "v", "w", "p"), entry=None):
         if k not in keys:                     # SIMPLE_INFLOW takes no p, SIMPLE_OUTFLOW only p
             out.append(None)
             continue
-        v = (entry or case["boundary_conditions"][face])["primitives_callable"][k]
+        v = (entry or case["boundary_conditions"][face])[name][k]
         if isinstance(v, str):
             fn = eval(v, {"jnp": np, "np": np})                       # noqa: S307 -- the reference's own contract
             v = np.asarray(fn(*mesh, 0.0), dtype=np.float64).reshape(shape)
@@ -164,8 +164,7 @@ def setup_from_json(case, num) -> port.Setup:
         limit_velocity=bool((c.get("positivity", {}) or {}).get("limit_velocity", False)),
         flux_limiter=(c.get("positivity", {}) or {}).get("flux_limiter", None) or None,
         flux_partition=(c.get("positivity", {}) or {}).get("flux_partition", "UNIFORM"),
-        wall_velocity={f: tuple(float(case["boundary_conditions"][f].get("wall_velocity_callable", {}).get(k, 0.0))
-                                for k in "uvw")
+        wall_velocity={f: dirichlet_values(case, f, ("u", "v", "w"), name="wall_velocity_callable")[1:4]
                        for f in port.FACES if _type(case, f) == "WALL"},
         dirichlet={f: dirichlet_values(case, f) for f in port.FACES if _type(case, f) == "DIRICHLET"},
         bc_values={f: dirichlet_values(case, f, BC_VALUE_KEYS[_type(case, f)]) for f in port.FACES

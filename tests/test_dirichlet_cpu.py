@@ -52,8 +52,10 @@ def _host_runtime(im, s, **cfg_kw):
     rt.bc_block = dict(im.case_setup.boundary_condition_setup)
     rt._cell_sizes = tuple(im.domain_information.cell_sizes)
     consts = rt._dirichlet_constants(im.case_setup, im.domain_information, ParallelContext(im.domain_information))
+    rt.wall_constants = rt._wall_constants(im.case_setup, im.domain_information, ParallelContext(im.domain_information))
     rt.cfg = BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min), gamma=s.gamma,
-                         bc=rt._kernel_boundary_types(), nh=s.nh, dirichlet=consts, **cfg_kw)
+                         bc=rt._kernel_boundary_types(), nh=s.nh, dirichlet=consts, wall_velocity=rt.wall_constants,
+                         **cfg_kw)
     rt.cfg.to_c()                                            # the kernels' configuration is constructible
     rt.device = torch.device("cpu")
     edges = []
@@ -187,3 +189,38 @@ def test_several_types_on_one_face_reproduce_the_oracle_halo_fill():
     im_bad = InputManager(bad, num)
     with pytest.raises(NotImplementedError, match="partition"):
         _host_runtime(im_bad, s)
+
+
+def test_space_dependent_wall_velocity_reproduces_the_oracle_halo_fill():
+    """WALL with wall_velocity_callable lambdas (halos/outer/material.py:473-520; a regularised lid): the kernels run with
+    wall velocity 0 on such a face (halo = -u_mirror), the host adds 2 u_wall: bit-identical to the oracle's halos."""
+    from jaxfluids_b200.input_manager import InputManager
+    g, case, num = H.load_golden("cavity_24x20_wall_js_visc_rk3")
+    case = copy.deepcopy(case)
+    case["boundary_conditions"]["north"]["wall_velocity_callable"] = {"u": "lambda x,t: 16.0 * x**2 * (1.0 - x)**2",
+                                                                      "v": 0.0, "w": 0.0}
+    case["boundary_conditions"]["east"]["wall_velocity_callable"] = {"u": 0.0, "v": "lambda y,t: 0.1 * jnp.sin(3 * y)",
+                                                                     "w": 0.0}
+    im = InputManager(case, num)
+    s = H.setup_from_json(case, num)
+    assert isinstance(s.wall_velocity["north"][0], np.ndarray) and s.wall_velocity["south"] == (0.0, 0.0, 0.0)
+    rt, consts, edges = _host_runtime(im, s, is_viscous_flux=True)
+    assert set(rt._host_faces) == {"north", "east"} and rt.wall_constants["north"] == (0.0, 0.0, 0.0)
+    assert rt.cfg.bc["north"] == "WALL"
+    rng = np.random.default_rng(7)
+    interior = 1.0 + 0.1 * rng.random((5,) + s.cells)
+    interior[1:4] -= 1.05
+    s_faces = copy.copy(s)
+    s_faces.is_viscous_flux = False                          # faces only (the edges follow on the device)
+    prims, cons = port.initialize(interior, s_faces)
+    s_kernel = copy.copy(s_faces)
+    s_kernel.wall_velocity = dict(rt.wall_constants)         # what the halo kernel fills: u_wall = 0 on north / east
+    p0, c0 = port.halo_fill(prims, cons, s_kernel)
+    ref_p, ref_c = port.halo_fill(prims, cons, s_faces)
+    m = H.face_halo_mask(s)
+    assert not np.array_equal(p0[:, m], ref_p[:, m])
+    tp, tc = torch.as_tensor(p0.copy()), torch.as_tensor(c0.copy())
+    rt._apply_host_boundaries(tp, tc)
+    assert edges == [1]
+    assert np.array_equal(tp.numpy()[:, m], ref_p[:, m])
+    assert np.array_equal(tc.numpy()[:, m], ref_c[:, m])

@@ -157,14 +157,13 @@ def test_case_errors():
         InputManager(case, _mod(num, ("active_physics", "is_volume_force"), True))
     grav = _mod(case, ("forcings",), {"gravity": [0.0, 1.0, 0.0]})
     assert InputManager(grav, _mod(num, ("active_physics", "is_volume_force"), True)).case_setup.gravity == (0.0, 1.0, 0.0)
-    # WALL: constant wall_velocity_callable is read; a missing one is the reference's consistency error; a lambda
-    # string is a valid option this path does not implement
+    # WALL: wall_velocity_callable is read (floats or lambda strings); a missing one is the reference's consistency error
     with pytest.raises(AssertionError, match="wall_velocity_callable"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "WALL"), num)
     wall = _mod(case, ("boundary_conditions", "east"), {"type": "WALL", "wall_velocity_callable": {"u": 0.0, "v": 0.5, "w": 0.0}})
     assert InputManager(wall, num).case_setup.wall_velocity_setup == {"east": (0.0, 0.5, 0.0)}
-    with pytest.raises(NotImplementedError, match="B200 path"):
-        InputManager(_mod(wall, ("boundary_conditions", "east", "wall_velocity_callable", "v"), "lambda y, z, t: 0.5"), num)
+    lam = InputManager(_mod(wall, ("boundary_conditions", "east", "wall_velocity_callable", "v"), "lambda y, z, t: 0.5"), num)
+    assert lam.case_setup.wall_velocity_setup["east"] == (0.0, "lambda y, z, t: 0.5", 0.0)   # evaluated by the runtime
     with pytest.raises(AssertionError, match="case setup"):
         InputManager(_mod(case, ("boundary_conditions", "east", "type"), "PERIODIC"), num)   # west is SYMMETRY
     with pytest.raises(AssertionError, match="argument labels"):
@@ -230,6 +229,7 @@ def test_flux_splitting_block_is_read_like_the_reference():
     ("api/heat2d_24x20_dirichlet_lambda_noconv_rk3", dict(no_convective_flux=1, heat_flux=1, stencil=1)),
     ("api/riemann2d_16x20_inflow_outflow_visc_rk3", dict(viscous_flux=1, heat_flux=1)),
     ("api/dmr_48x32_dirichlet_symmetry_south_rk3", dict(interpolation_limiter=1, recon=1)),
+    ("api/cavity_24x20_wall_lambda_lid_visc_rk3", dict(viscous_flux=1, stencil=1)),
 ])
 
 def test_json_options_reach_the_c_config(name, expect, monkeypatch):

@@ -90,6 +90,9 @@ pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="reference 
     ("dmr", dict(cells=(48, 32, None)), 3),
     ("sod", dict(cells=(64, None, None), stencil="TENO5-A"), 2),
     ("tgv", dict(cells=(8, 8, 10), stencil="TENO6-A"), 1),
+    # WALL with a space-dependent wall velocity (a regularised lid on the shipped cavity)
+    ("cavity", dict(cells=(16, 14, None), boundary_conditions={"north": {"type": "WALL", "wall_velocity_callable": {
+        "u": "lambda x,t: 16.0 * x**2 * (1.0 - x)**2", "v": 0.0, "w": 0.0}}}), 2),
     # HLLC-LM and AUSM+
     ("sod", dict(cells=(64, None, None), riemann="HLLC-LM"), 3),
     ("tgv", dict(cells=(10, 8, 12), riemann="HLLC-LM"), 1),
