@@ -277,6 +277,11 @@ int jxf_unpack_face_ext(jxf_handle h, int face, int ext_mask, const double* slab
 int jxf_profile_enable(jxf_handle h, int enable);
 int jxf_profile_read(jxf_handle h, double* ms_sum, int64_t* timed, int64_t* launches, int reset);
 
+/* Test hook (no device work; callable without a GPU): the kernel instantiation and the face-flux option word the
+ * handle's configuration selects -- RECON / RIEMANN template parameters of the sweep kernels and the packed options of
+ * numerics.cuh face_flux -- so that the host simulation of the device functions can be checked to use the same ones. */
+int jxf_debug_dispatch(jxf_handle h, int axis, int* recon_template, int* riemann_template, int* option_word);
+
 /* Test hook: the per-face device function (reconstruction + Riemann flux,
  * ref: HighOrderGodunov.compute_flux_xi, high_order_godunov.py:117-231) on caller-supplied
  * 6-cell windows.  windows: (n, 5, 6) doubles, flux: (n, 5) doubles, both on the device.

@@ -1543,14 +1543,29 @@ template <int A, int RECON, int RIEMANN>
 static int dispatch_epi(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
   return epi ? launch_sweep<A, RECON, RIEMANN, 1>(s, a, st) : launch_sweep<A, RECON, RIEMANN, 0>(s, a, st);
 }
+// The kernel instantiation a configuration runs in (also reported by jxf_debug_dispatch, so that the host simulation
+// of the device functions, tests/hostsim, can be checked to use the same template parameters and option word):
+//   RECON   0..3 = reconstruction variable + 2 * stencil for the tuned WENO5-Z / WENO5-JS forms; 4 / 5 = the generic
+//           instantiations (every other stencil, the conservative variables, the ROE frozen state, FLUX-SPLITTING);
+//   RIEMANN HLLC, or RUSANOV for everything else (Rusanov, HLL, HLLC-LM, AUSM+ as run-time variants; FLUX-SPLITTING).
+static int recon_template_of(const jxf_solver* s) {
+  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING) return 4;
+  if (generic_path(s)) return 4 + (s->cfg.recon & 1);
+  return s->cfg.recon + 2 * s->cfg.stencil;
+}
+static int riemann_template_of(const jxf_solver* s) {
+  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING) return RIEMANN_RUSANOV;
+  return s->cfg.riemann == JXF_RIEMANN_HLLC ? RIEMANN_HLLC : RIEMANN_RUSANOV;
+}
+
 template <int A, int RECON>
 static int dispatch_riemann(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
 #ifdef JXF_TUNE_ONLY   // tuning builds instantiate the bench variant only (CHAR-PRIMITIVE + HLLC)
   if (s->cfg.riemann != JXF_RIEMANN_HLLC) return fail(JXF_ERR_UNSUPPORTED, "tuning build: HLLC only");
   return dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st);
 #else
-  return s->cfg.riemann == JXF_RIEMANN_HLLC ? dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st)
-                                            : dispatch_epi<A, RECON, RIEMANN_RUSANOV>(s, a, epi, st);
+  return riemann_template_of(s) == RIEMANN_HLLC ? dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st)
+                                                : dispatch_epi<A, RECON, RIEMANN_RUSANOV>(s, a, epi, st);
 #endif
 }
 template <int A>
@@ -1561,16 +1576,16 @@ static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cuda
     return fail(JXF_ERR_UNSUPPORTED, "tuning build: WENO5-Z CHAR-PRIMITIVE only");
   return dispatch_riemann<A, RECON_CHAR_PRIMITIVE>(s, a, epi, st);
 #else
-  // FLUX-SPLITTING: a run-time branch of the generic instantiations' face flux (numerics.cuh flux_splitting_flux)
-  if (s->cfg.convective_solver == JXF_SOLVER_FLUX_SPLITTING) return dispatch_epi<A, 4, RIEMANN_RUSANOV>(s, a, epi, st);
+  // FLUX-SPLITTING is a run-time branch of the generic instantiations' face flux (numerics.cuh flux_splitting_flux);
   // every stencil other than the two tuned WENO5 forms, the conservative reconstruction variables and the ROE frozen
   // state run in the STENCIL_GENERIC instantiations (RECON 4 / 5), selected at run time by the option word (base_args)
-  if (generic_path(s)) return (s->cfg.recon & 1) ? dispatch_riemann<A, 5>(s, a, epi, st) : dispatch_riemann<A, 4>(s, a, epi, st);
-  switch (s->cfg.recon + 2 * s->cfg.stencil) {
+  switch (recon_template_of(s)) {
     case 0: return dispatch_riemann<A, 0>(s, a, epi, st);
     case 1: return dispatch_riemann<A, 1>(s, a, epi, st);
     case 2: return dispatch_riemann<A, 2>(s, a, epi, st);
-    default: return dispatch_riemann<A, 3>(s, a, epi, st);
+    case 3: return dispatch_riemann<A, 3>(s, a, epi, st);
+    case 4: return dispatch_riemann<A, 4>(s, a, epi, st);
+    default: return dispatch_riemann<A, 5>(s, a, epi, st);
   }
 #endif
 }
@@ -2063,6 +2078,15 @@ extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const doubl
 #endif
 #undef JXF_DBG_CASE
   return fail(JXF_ERR_BAD_ARG, "jxf_debug_face_flux: unknown variant");
+}
+
+extern "C" int jxf_debug_dispatch(jxf_handle h, int axis, int* recon_template, int* riemann_template, int* option_word) {
+  if (!h || axis < 0 || axis > 2 || !recon_template || !riemann_template || !option_word)
+    return fail(JXF_ERR_BAD_ARG, "jxf_debug_dispatch: bad argument");
+  *recon_template = recon_template_of(h);
+  *riemann_template = riemann_template_of(h);
+  *option_word = base_args(h, axis, nullptr, nullptr).limiter;
+  return JXF_OK;
 }
 
 extern "C" int jxf_debug_math(const double* x, int64_t n, double* out, void* stream) {

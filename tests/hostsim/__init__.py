@@ -57,6 +57,12 @@ def _recon_id(s):
     return var + 2 * min(STENCIL_IDS[s.stencil], 2)
 
 
+def _riemann_id(s):
+    """The kernels' RIEMANN template parameter: HLLC (0), or the RUSANOV instantiation (1) for everything else
+    (dispatch_riemann / riemann_template_of, jxf_b200.cu)."""
+    return 1 if s.convective_solver == "FLUX-SPLITTING" else {"HLLC": 0}.get(s.riemann, 1)
+
+
 def _opt(s):
     """face_flux `opt` (numerics.cuh): limiter mode | signal speed << 4 | HLL << 8 | flux limiter << 9 |
     generic stencil id << 11, as base_args (jxf_b200.cu) packs it."""
@@ -96,7 +102,7 @@ def rhs_axis_march(prims, axis, s, fma=True, dt=None):
     shp = w.shape[:3]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_march_host(axis, _recon_id(s), (1 if s.convective_solver == "FLUX-SPLITTING" else {"HLLC": 0}.get(s.riemann, 1)),
+    rc = lib.face_flux_march_host(axis, _recon_id(s), _riemann_id(s),
                                   w.ctypes.data, shp[0] * shp[1], shp[2], s.gamma, out.ctypes.data, _opt(s),
                                   *_flux_limiter_args(s, axis, dt))
     assert rc == 0
@@ -119,7 +125,7 @@ def rhs_axis(prims, axis, s, fma=True, reference_order=False, dt=None):
     shp = w.shape[:-2]
     w = np.ascontiguousarray(w.reshape(-1, 5, 6))
     out = np.empty((w.shape[0], 5))
-    rc = lib.face_flux_host(axis, _recon_id(s), (1 if s.convective_solver == "FLUX-SPLITTING" else {"HLLC": 0}.get(s.riemann, 1)),
+    rc = lib.face_flux_host(axis, _recon_id(s), _riemann_id(s),
                             w.ctypes.data, w.shape[0], s.gamma, out.ctypes.data, _opt(s),
                             *_flux_limiter_args(s, axis, dt))
     assert rc == 0

@@ -94,3 +94,45 @@ def test_null_arguments_are_rejected(built_library):
     assert lib.jxf_stage(h, 0, None, None, None, None, None, None, None, None, 0, 1, None) == -1
     assert lib.jxf_halo_fill(h, None, None, None) == -1
     lib.jxf_destroy(h)
+
+
+def _block_config(s):
+    from jaxfluids_b200.engine import BlockConfig
+    return BlockConfig(cells=s.cells, inv_dx=tuple(float(x) for x in s.inv_dx), dx_min=float(s.dx_min), gamma=s.gamma,
+                       bc=s.bc, nh=s.nh, recon=s.recon, stencil=s.stencil, riemann=s.riemann, signal_speed=s.signal_speed,
+                       convective_solver=s.convective_solver, flux_splitting=s.flux_splitting, frozen_state=s.frozen_state,
+                       integrator=s.integrator, is_interpolation_limiter=s.is_interpolation_limiter,
+                       limit_velocity=s.limit_velocity, flux_limiter=s.flux_limiter, flux_partition=s.flux_partition)
+
+
+def test_host_simulation_uses_the_kernels_template_parameters_and_option_word(built_library):
+    """tests/hostsim validates the device functions for a (RECON, RIEMANN, option word) it derives from the setup; the
+    kernels get theirs from dispatch_recon / dispatch_riemann / base_args (jxf_b200.cu).  jxf_debug_dispatch reports the
+    latter -- no GPU needed -- and the two must agree for every option combination, or the host simulation would be
+    validating something the GPU does not run."""
+    import itertools
+    from tests import helpers as H
+    from tests import hostsim
+    lib = _lib.load()
+    stencils = list(_lib.STENCIL)
+    n = 0
+    combos = itertools.chain(
+        itertools.product(["GODUNOV"], stencils, list(_lib.RECON), ["ARITHMETIC", "ROE"], list(_lib.RIEMANN),
+                          ["EINFELDT", "TORO"], [(False, False, None), (True, True, "NASA")]),
+        itertools.product(["FLUX-SPLITTING"], stencils, ["CHAR-PRIMITIVE"], ["ARITHMETIC", "ROE"], ["HLLC"], ["EINFELDT"],
+                          [(False, False, None)]))
+    for solver, stencil, recon, frozen, riemann, sig, (lim, limv, fluxlim) in combos:
+        for fs in (["ROE", "CLLF", "LLF"] if solver == "FLUX-SPLITTING" else ["ROE"]):
+            s = H.make_setup((12, 10, 8), bc="PERIODIC", recon=recon, riemann=riemann, stencil=stencil)
+            s.convective_solver, s.flux_splitting, s.frozen_state, s.signal_speed = solver, fs, frozen, sig
+            s.is_interpolation_limiter, s.limit_velocity, s.flux_limiter = lim, limv, fluxlim
+            h = C.c_void_p()
+            assert lib.jxf_create(C.byref(_block_config(s).to_c()), C.byref(h)) == 0, lib.jxf_last_error()
+            r, m, o = C.c_int32(), C.c_int32(), C.c_int32()
+            for axis in range(3):
+                assert lib.jxf_debug_dispatch(h, axis, C.byref(r), C.byref(m), C.byref(o)) == 0
+                assert (r.value, m.value, o.value) == (hostsim._recon_id(s), hostsim._riemann_id(s), hostsim._opt(s)), \
+                    (solver, stencil, recon, frozen, riemann, sig, lim, fluxlim, fs)
+            lib.jxf_destroy(h)
+            n += 1
+    assert n > 2000
