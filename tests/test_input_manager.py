@@ -267,3 +267,48 @@ def test_every_reconstruction_variable_and_frozen_state_selects_the_path(variabl
     num = _mod(_mod(num, GOD + ("reconstruction_variable",), variable), GOD + ("frozen_state",), frozen)
     g = InputManager(case, num).numerical_setup.conservatives.convective_fluxes.godunov
     assert (g.reconstruction_variable, g.frozen_state) == (variable, frozen)
+
+
+@pytest.mark.parametrize("name", H.golden_names() + H.generic_golden_names() + H.api_golden_names())
+def test_block_config_of_every_fixture_matches_the_oracle_setup(name, monkeypatch):
+    """JSON -> InputManager -> BlockRuntime -> BlockConfig, field by field against the oracle's reading of the same JSON
+    (tests/helpers.setup_from_json), for every fixture: what the kernels are configured with is what the oracle runs."""
+    import jaxfluids_b200.runtime as RT
+    from jaxfluids_b200.parallel import ParallelContext
+
+    class Reached(Exception):
+        pass
+
+    def fake_solver(cfg, *a, **k):
+        raise Reached(cfg)
+    monkeypatch.setattr(RT, "BlockSolver", fake_solver)
+    g, case, num = H.load_golden(name)
+    im = InputManager(case, num)
+    with pytest.raises(Reached) as info:
+        RT.BlockRuntime(im, ParallelContext(im.domain_information))
+    cfg, s = info.value.args[0], H.setup_from_json(case, num)
+    assert tuple(cfg.cells) == tuple(s.cells) and cfg.nh == s.nh and cfg.gamma == s.gamma
+    assert tuple(np.float64(x) for x in cfg.inv_dx) == tuple(s.inv_dx) and np.float64(cfg.dx_min) == s.dx_min
+    assert (cfg.convective_solver, cfg.stencil, cfg.integrator, cfg.cfl) == (s.convective_solver, s.stencil, s.integrator, s.cfl)
+    assert cfg.frozen_state == s.frozen_state
+    if s.convective_solver == "FLUX-SPLITTING":
+        assert cfg.flux_splitting == s.flux_splitting
+    else:
+        assert (cfg.recon, cfg.riemann, cfg.signal_speed) == (s.recon, s.riemann, s.signal_speed)
+    assert (cfg.is_interpolation_limiter, cfg.limit_velocity, cfg.flux_limiter, cfg.flux_partition) == \
+        (s.is_interpolation_limiter, s.limit_velocity, s.flux_limiter, s.flux_partition)
+    assert (cfg.is_viscous_flux, cfg.is_heat_flux, cfg.is_convective_flux, cfg.is_volume_force) == \
+        (s.is_viscous_flux, s.is_heat_flux, s.is_convective_flux, s.is_volume_force)
+    if s.is_viscous_flux:                                     # (the viscosity is not read with the heat flux alone)
+        assert (cfg.dynamic_viscosity, cfg.bulk_viscosity) == (s.dynamic_viscosity, s.bulk_viscosity)
+    if s.is_dissipative:
+        assert cfg.gas_constant == s.gas_constant
+    assert tuple(cfg.gravity) == tuple(s.gravity)
+    kernel_type = {"NEUMANN": "ZEROGRADIENT", "SIMPLE_INFLOW": "ZEROGRADIENT", "SIMPLE_OUTFLOW": "ZEROGRADIENT"}
+    assert {f: cfg.bc[f] for f in H.port.FACES} == {f: kernel_type.get(s.bc[f], s.bc[f]) for f in H.port.FACES}
+    for f, vals in s.dirichlet.items():                      # constants reach the kernels; arrays are host-applied
+        if all(isinstance(v, float) for v in vals):
+            assert tuple(cfg.dirichlet[f]) == tuple(vals)
+    for f, vals in s.wall_velocity.items():
+        if all(isinstance(v, float) for v in vals):
+            assert tuple(cfg.wall_velocity[f]) == tuple(vals)
