@@ -1283,14 +1283,9 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) s->num_sms = sms;
   }
-  // The generic (reference-order) instantiations pass 6-cell windows by value to out-of-line functions: ~1.2 KB of stack
-  // in the kernel plus the callees' frames.  The driver grows the per-thread stack per launch as needed; asking for it
-  // here makes that explicit (and happens once, outside the step).  No effect on the tuned path.
-  if (cfg->stencil >= JXF_STENCIL_WENO1 || cfg->recon >= JXF_RECON_CONSERVATIVE || cfg->frozen_state == JXF_FROZEN_ROE ||
-      cfg->convective_solver == JXF_SOLVER_FLUX_SPLITTING || cfg->riemann >= JXF_RIEMANN_HLLCLM) {
-    size_t cur = 0;
-    if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < 8192) (void)cudaDeviceSetLimit(cudaLimitStackSize, 8192);
-  }
+  // (The generic instantiations' stack frames are static -- no recursion -- and the driver sizes local memory per launch
+  // from them, so the device-wide cudaLimitStackSize is left alone: raising it would reserve local memory for every
+  // kernel of the process, torch's included.)
   (void)cudaGetLastError();
   *out = s;
   return JXF_OK;

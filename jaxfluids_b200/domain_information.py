@@ -26,6 +26,9 @@ class DomainInformation:
         self.nh_conservatives = int(nh)
         self.no_subdomains = int(np.prod(self.split_factors))
         self.is_parallel = self.no_subdomains > 1
+        for ax, n, sp in zip(AXES, self.global_number_of_cells, self.split_factors):
+            assert sp >= 1 and n % sp == 0, (
+                f"domain/decomposition/split_{ax}={sp} does not divide domain/{ax}/cells={n}")
         self.device_number_of_cells = tuple(n // s for n, s in zip(self.global_number_of_cells, self.split_factors))
         self.active_axes_indices = tuple(i for i in range(3) if self.global_number_of_cells[i] > 1)
         self.inactive_axes_indices = tuple(i for i in range(3) if self.global_number_of_cells[i] == 1)

@@ -305,6 +305,8 @@ class InputManager:
         self.numerical_setup = self._read_numerical(self.numerical_setup_dict)
         self.case_setup = self._read_case(self.case_setup_dict)
         self.equation_information = EquationInformation()
+        ap = self.numerical_setup.active_physics          # equation_information.py: temperature buffer with these on
+        self.equation_information.is_compute_temperature = bool(ap.is_viscous_flux or ap.is_heat_flux)
         self.domain_information = DomainInformation(
             cells=self.case_setup.domain_setup.cells,
             domain_range=self.case_setup.domain_setup.range,

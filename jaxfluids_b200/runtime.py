@@ -35,6 +35,10 @@ class BlockRuntime:
                 parallel = ParallelContext.from_environment(input_manager.domain_information)
             rt = cls(input_manager, parallel)
             cls._cache[input_manager] = rt
+        elif parallel is not None and parallel is not rt.parallel and (
+                parallel.rank, parallel.world_size) != (rt.parallel.rank, rt.parallel.world_size):
+            raise ValueError("BlockRuntime.get: a runtime for this InputManager already exists with a different "
+                             "ParallelContext (rank / world size)")
         return rt
 
     def __init__(self, input_manager, parallel: ParallelContext):
@@ -348,6 +352,9 @@ class BlockRuntime:
 
     def _allreduce_red(self):
         if self.parallel.is_parallel:
+            # order the collective after an in-flight P2P halo exchange (they may use different NCCL communicators on
+            # different streams; concurrent communicators with rank-dependent launch order can deadlock)
+            self.finish_pending()
             buf = self.red * self._sign
             self.parallel.allreduce_max(buf)
             self.red.copy_(buf * self._sign)

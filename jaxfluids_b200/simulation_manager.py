@@ -21,6 +21,7 @@ from .data_types import (ControlFlowParameters, DiscretizationCounter, EulerInte
                          IntegrationBuffers, JaxFluidsBuffers, LevelsetFieldBuffers, MaterialFieldBuffers,
                          PositivityCounter, PositivityStateInformation, SimulationBuffers, SolidFieldBuffers,
                          StepInformation, TimeControlVariables, WallClockTimes)
+from . import callbacks as _cb
 from .input_manager import InputManager
 from .logger import Logger
 from .parallel import ParallelContext
@@ -149,8 +150,16 @@ def compute_time_step_size(primitives, runtime: BlockRuntime) -> float:
 
 class SimulationManager:
     def __init__(self, input_manager: InputManager, callbacks=None, parallel: Optional[ParallelContext] = None) -> None:
-        if callbacks:
-            raise NotImplementedError("callbacks are not implemented on the B200 path")
+        # simulation_manager.py:179-184: one callback or a list; every hook of the reference's Callback is honoured
+        # except after_compute_rhs (the fused stage kernel never materialises the rhs between sweep and update)
+        if callbacks is not None and not isinstance(callbacks, (list, tuple)):
+            callbacks = [callbacks]
+        self.callbacks = list(callbacks or [])
+        for cb in self.callbacks:
+            if _cb.overrides(cb, "after_compute_rhs"):
+                raise NotImplementedError("callback hook 'after_compute_rhs' is not available on the B200 path: the stage "
+                                          "kernel fuses the last sweep with the stage update")
+        self._stage_hooks = any(_cb.overrides(cb, h) for cb in self.callbacks for h in ("on_stage_start", "on_stage_end"))
         self.input_manager = input_manager
         self.case_setup = input_manager.case_setup
         self.numerical_setup = input_manager.numerical_setup
@@ -168,6 +177,24 @@ class SimulationManager:
         self.logger = Logger(level=log.level, frequency=log.frequency, is_positivity=log.is_positivity,
                              is_active=self.parallel.rank == 0)
         self.wall_clock_times = WallClockTimes()
+        for cb in self.callbacks:
+            if hasattr(cb, "init_callback"):
+                cb.init_callback(sim_manager=self)
+
+    def _callback(self, hook_name: str, jxf_buffers=None, callback_dict=None, conservatives=None, primitives=None,
+                  **kwargs):
+        """simulation_manager.py:1079-1160: run `hook_name` of every callback (missing hooks are the identity)."""
+        if hook_name in ("on_stage_start", "on_stage_end"):
+            for cb in self.callbacks:
+                fn = getattr(cb, hook_name, None)
+                if fn is not None:
+                    conservatives, primitives = fn(conservatives=conservatives, primitives=primitives, **kwargs)
+            return conservatives, primitives
+        for cb in self.callbacks:
+            fn = getattr(cb, hook_name, None)
+            if fn is not None:
+                jxf_buffers, callback_dict = fn(jxf_buffers=jxf_buffers, callback_dict=callback_dict, **kwargs)
+        return jxf_buffers, callback_dict
 
     # ------------------------------------------------------------------
     def simulate(self, jxf_buffers: JaxFluidsBuffers, ml_parameters=None, ml_callables=None) -> int:
@@ -186,11 +213,16 @@ class SimulationManager:
         t, step = tcv.physical_simulation_time, tcv.simulation_step
         cells = self.domain_information.cells_per_device
         n_timed, mean = 0, 0.0
+        callback_dict: Dict = {}
+        jxf_buffers, callback_dict = self._callback("on_simulation_start", jxf_buffers, callback_dict)
         while t < tcv.end_time and step < tcv.end_step:
             torch.cuda.synchronize()
             t0 = _time.time()
             cfp = self.compute_control_flow_params(tcv, jxf_buffers.step_information)
-            jxf_buffers, _ = self.do_integration_step(jxf_buffers, cfp, ml_parameters, ml_callables)
+            jxf_buffers, callback_dict = self._callback("before_step_start", jxf_buffers, callback_dict)
+            jxf_buffers, callback_dict_step = self.do_integration_step(jxf_buffers, cfp, ml_parameters, ml_callables)
+            jxf_buffers, callback_dict = self._callback("after_step_end", jxf_buffers, callback_dict,
+                                                        callback_dict_step=callback_dict_step)
             tcv = jxf_buffers.time_control_variables
             t, step = tcv.physical_simulation_time, tcv.simulation_step
             wall = _time.time() - t0
@@ -199,6 +231,7 @@ class SimulationManager:
                 mean += (wall - mean) / n_timed
             self.wall_clock_times = WallClockTimes(wall, wall / cells, mean, mean / cells)
             self.logger.log_end_time_step(tcv, jxf_buffers.step_information, self.wall_clock_times)
+        jxf_buffers, callback_dict = self._callback("on_simulation_end", jxf_buffers, callback_dict)
         return jxf_buffers
 
     def compute_control_flow_params(self, time_control_variables, step_information) -> ControlFlowParameters:
@@ -212,11 +245,16 @@ class SimulationManager:
 
     def _do_integration_step(self, jxf_buffers, control_flow_params=None, ml_parameters=None, ml_callables=None):
         rt = self.runtime
+        callback_dict: Dict = {}
+        jxf_buffers, callback_dict = self._callback("on_step_start", jxf_buffers, callback_dict)
         mf = jxf_buffers.simulation_buffers.material_fields
         tcv = jxf_buffers.time_control_variables
         rt.adopt(mf.primitives, mf.conservatives)
         rt.set_time_control(tcv.physical_simulation_time, tcv.physical_timestep_size)
-        rt.step()
+        if self._stage_hooks:
+            self._step_with_stage_hooks(tcv)
+        else:
+            rt.step()
         t, dt_next, _, min_rho, min_p = rt.read_step_scalars()
         tcv = tcv._replace(physical_simulation_time=t, simulation_step=tcv.simulation_step + 1,
                            physical_timestep_size=dt_next)
@@ -224,7 +262,29 @@ class SimulationManager:
         sim = SimulationBuffers(material_fields, jxf_buffers.simulation_buffers.levelset_fields,
                                 jxf_buffers.simulation_buffers.solid_fields)
         info = StepInformation(positivity=(PositivityStateInformation(min_pressure=min_p, min_density=min_rho),))
-        return JaxFluidsBuffers(sim, tcv, jxf_buffers.forcing_parameters, info), {}
+        out = JaxFluidsBuffers(sim, tcv, jxf_buffers.forcing_parameters, info)
+        return self._callback("on_step_end", out, callback_dict)
+
+    def _step_with_stage_hooks(self, tcv):
+        """The step stage by stage with on_stage_start / on_stage_end around every stage (simulation_manager.py:778,
+        :1018).  The hooks see the stage's conservatives / primitives; what they return becomes the state."""
+        rt = self.runtime
+        kw = dict(physical_timestep_size=tcv.physical_timestep_size, physical_simulation_time=tcv.physical_simulation_time)
+        def hook(name, cons, prims):
+            c, p = self._callback(name, conservatives=cons, primitives=prims, **kw)
+            if c is not cons:
+                cons.copy_(c)
+            if p is not prims:
+                prims.copy_(p)
+        for k in range(rt.stages):
+            last = k == rt.stages - 1
+            rt.finish_pending()
+            hook("on_stage_start", rt.cons[0] if k == 0 else rt.cons[1], rt.primitives)
+            rt.stage(k, reduce=last)
+            rt.finish_pending()
+            hook("on_stage_end", rt.cons[0] if last else rt.cons[1], rt.primitives)
+        rt._allreduce_red()
+        rt.solver.finish_step(rt.red, rt.dt, rt.time, rt.info)
 
     def do_runge_kutta_stages(self, material_fields: MaterialFieldBuffers, time_control_variables: TimeControlVariables,
                               levelset_fields=None, solid_fields=None, forcing_buffers=None,
