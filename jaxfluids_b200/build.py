@@ -8,16 +8,25 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "jxf_b200.cu")]
-DEPS = [os.path.join(HERE, "csrc", "numerics.cuh"), os.path.join(HERE, "csrc", "dissipative.cuh"), os.path.join(os.path.dirname(HERE), "include", "jxf_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+MAIN = os.path.join(CSRC, "jxf_b200.cu")
+INST = os.path.join(CSRC, "sweep_inst.cu")        # compiled once per (axis, RECON) pair: the sweep kernel instantiations
+SRC = [MAIN, INST]
+DEPS = [os.path.join(CSRC, n) for n in ("numerics.cuh", "dissipative.cuh", "sweep_kernels.cuh", "plan.cuh")] + \
+       [os.path.join(os.path.dirname(HERE), "include", "jxf_b200.h")]
 OUT = os.path.join(HERE, "lib", "libjxf_b200.so")
+OBJ = os.path.join(HERE, "lib", "obj")            # object files (git-ignored, gpurun-ignored: only the .so travels)
 STAMP = OUT + ".srchash"          # written after a successful build; travels with the .so
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
+    "-Xfatbin", "-compress-all",      # 19 cubins with line info: 117 MB uncompressed
 ]
+# (axis, RECON) pairs of the production library; tuning builds (-DJXF_TUNE_ONLY) keep the bench variant only
+PAIRS = [(a, r) for a in range(3) for r in range(6)]
+TUNE_PAIRS = [(a, 1) for a in range(3)]
 
 
 def find_nvcc() -> str:
@@ -48,30 +57,67 @@ def up_to_date() -> bool:
         return fh.read().strip() == source_hash()
 
 
+def _compile_all(out: str, defines, verbose: bool, tag: str) -> None:
+    """One nvcc -c per translation unit, in parallel over the host cores, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    tune = any(d.split("=")[0] == "JXF_TUNE_ONLY" for d in defines)
+    objdir = os.path.join(OBJ, tag)
+    os.makedirs(objdir, exist_ok=True)
+    base = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c"]
+    jobs = [(base + ["-o", os.path.join(objdir, "main.o"), MAIN], os.path.join(objdir, "main.o"))]
+    # the generic instantiations (RECON 4 / 5) take longest: start them first
+    for a, r in sorted(TUNE_PAIRS if tune else PAIRS, key=lambda p: -p[1]):
+        o = os.path.join(objdir, f"sweep_a{a}_r{r}.o")
+        jobs.append((base + [f"-DJXF_INST_A={a}", f"-DJXF_INST_RECON={r}", "-o", o, INST], o))
+
+    def run(job):
+        cmd, _ = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stdout.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    workers = int(os.environ.get("JXF_BUILD_JOBS", str(max(1, min(len(jobs), os.cpu_count() or 1)))))
+    print(f"[jaxfluids_b200.build] {len(jobs)} translation units, {workers} parallel nvcc jobs -> {out}", flush=True)
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(run, jobs))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [o for _, o in jobs]
+    subprocess.run(link, check=True)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    print("[jaxfluids_b200.build]", " ".join(cmd), flush=True)
     digest = source_hash()             # before the compile: an edit during the build must not be stamped as built
     if os.path.exists(STAMP):
         os.remove(STAMP)
-    subprocess.run(cmd, check=True)
+    _compile_all(OUT, [], verbose, "prod")
     with open(STAMP, "w") as fh:
         fh.write(digest + "\n")
     return OUT
 
 
-def build_variant(name: str, defines) -> str:
-    """Tuning builds (e.g. JXF_MIN_BLOCKS=4) next to the production library; selected at run time with
-    JXF_LIB_VARIANT=<name>.  Not used by tests or the default bench."""
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """Tuning / checking builds (e.g. JXF_TUNE_ONLY, JXF_REFERENCE_ORDER) next to the production library; selected at run
+    time with JXF_LIB_VARIANT=<name>.  `defines` may hold nvcc flags too (entries starting with '-')."""
     out = OUT.replace(".so", f"_{name}.so")
-    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SRC
-    print("[jaxfluids_b200.build]", " ".join(cmd), flush=True)
-    subprocess.run(cmd, check=True)
+    flags = [d for d in defines if d.startswith("-")]
+    defs = [d for d in defines if not d.startswith("-")]
+    global NVCC_FLAGS
+    saved = NVCC_FLAGS
+    NVCC_FLAGS = NVCC_FLAGS + flags
+    try:
+        _compile_all(out, defs, verbose, name)
+    finally:
+        NVCC_FLAGS = saved
     return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose="-v" in sys.argv)
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -63,7 +63,7 @@ struct Vec10 {
 };
 template <int A>
 __device__ JXF_NOINLINE Vec10 reconstruct_conservative(Win6 W, double gamma, int id, int mode);      // defined below
-__device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
+static __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double uR, double aL, double aR, double rhoL,
                                                     double rhoR, double pL, double pR, double gamma) {
   double S_L, S_R;
   if (sig == SIG_ARITHMETIC) {
@@ -95,7 +95,7 @@ __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, double 
 
 // signal_speeds.py:109-133 in the reference's order (IEEE sqrt / division) -- for the HLL solver, which is not a
 // tuned path (the HLLC kernels carry their own fast evaluation of the same formula)
-__device__ JXF_NOINLINE double2 einfeldt_signal_speeds(double uL, double uR, double aL, double aR, double rhoL,
+static __device__ JXF_NOINLINE double2 einfeldt_signal_speeds(double uL, double uR, double aL, double aR, double rhoL,
                                                       double rhoR) {
   const double sL = sqrt(rhoL), sR = sqrt(rhoR);
   const double one_dens = 1.0 / (sL + sR);
@@ -140,7 +140,7 @@ __device__ __forceinline__ double teno_a_ct(double eta, double Cr, double alpha_
   const double beta_bar = ceil(alpha_1 - alpha_2 * (1.0 - g)) - 1.0;
   return pow(10.0, -beta_bar);
 }
-__device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
+static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
                                                double q5) {
   const double eps = kStencilEps;
   if (id == ALT_WENO1) return q2;

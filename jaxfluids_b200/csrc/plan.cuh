@@ -1,0 +1,191 @@
+// plan.cuh -- host side shared by the translation units: the solver handle, launch accounting and the launch plan of
+// one sweep (launch_sweep<A, RECON, RIEMANN, EPI>, explicitly instantiated in sweep_inst.cu).
+#pragma once
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "sweep_kernels.cuh"
+
+using namespace jxf;
+
+int jxf_fail(int code, const char* fmt, ...);      // sets jxf_last_error(); defined in jxf_b200.cu
+#define fail jxf_fail
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JXF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return JXF_OK;
+}
+
+struct jxf_solver {
+  jxf_config cfg;
+  Geom g;
+  int active[3];
+  int n_active;
+  int active_mask;
+  int lane_axis;      // contiguous active axis
+  int order[3];       // order[k] = axis of the k-th sweep of a stage; the LAST one carries the fused epilogue
+  const double* dt_bound;   // jxf_bind_timestep: time step for the flux limiter outside jxf_stage
+  int num_sms;
+  int stages;
+  double dt_mult[4];
+  double blend[4][2];
+  // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
+  bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
+  bool tma_ok;
+  bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
+  int n_maps;
+  const void* map_ptr[8];
+  CUtensorMap map[8];
+  // launch accounting / optional per-kernel event timing (jxf_profile_*)
+  long long launches[JXF_PROFILE_KINDS];
+  int prof_on;
+  int prof_n;
+  int prof_cap;
+  cudaEvent_t* prof_start;
+  cudaEvent_t* prof_stop;
+  unsigned char* prof_kind;
+};
+
+struct ProfScope {
+  jxf_solver* s;
+  cudaStream_t st;
+  int slot;
+  ProfScope(const jxf_solver* cs, int kind, cudaStream_t stream) : s(const_cast<jxf_solver*>(cs)), st(stream), slot(-1) {
+    s->launches[kind]++;
+    if (s->prof_on && s->prof_n < s->prof_cap) {
+      slot = s->prof_n++;
+      s->prof_kind[slot] = (unsigned char)kind;
+      cudaEventRecord(s->prof_start[slot], st);
+    }
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(s->prof_stop[slot], st);
+  }
+};
+
+// TMA descriptor of a halo'd field buffer for the rows kernel (nullptr: use the cp.async loader); jxf_b200.cu
+const CUtensorMap* get_rows_map(jxf_solver* s, const double* base);
+
+inline void set_role_bcs(SweepGeom& sg, const SweepArgs& a) {
+  sg.bcA_hi = a.bc[2 * sg.axA]; sg.bcA_lo = a.bc[2 * sg.axA + 1];
+  sg.bc1_hi = a.bc[2 * sg.ax1]; sg.bc1_lo = a.bc[2 * sg.ax1 + 1];
+  sg.bc2_hi = a.bc[2 * sg.ax2]; sg.bc2_lo = a.bc[2 * sg.ax2 + 1];
+}
+
+template <int A, int RECON, int RIEMANN, int EPI>
+int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
+  const Geom& g = s->g;
+  const int resident = s->num_sms * JXF_MIN_BLOCKS;   // CTAs of 128 threads resident on the device
+  // fold the interior origin into the base pointers
+  const long long h0 = g.off[0] * g.st[0] + g.off[1] * g.st[1] + g.off[2] * g.st[2];
+  a.prims += h0;
+  if (a.cons_in) a.cons_in += h0;
+  if (a.cons_n) a.cons_n += h0;
+  if (a.cons_out) a.cons_out += h0;
+  if (a.prims_out) a.prims_out += h0;
+  SweepGeom sg;
+  sg.axA = A;
+  sg.nA = g.n[A];
+  sg.sA = g.st[A];
+  sg.rA = g.rst[A];
+  sg.vst = g.vst;
+  sg.rvst = g.rvst;
+  const int T1 = (A == 0) ? 1 : 0;       // slower transverse axis
+  const int T2 = (A == 2) ? 1 : 2;       // faster transverse axis
+  if (A != s->lane_axis) {
+    // lanes along the contiguous axis C; the other transverse axis O is the slow one
+    const int C = s->lane_axis;
+    const int O = 3 - A - C;
+    sg.ax1 = O; sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
+    sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
+    const long long plane = (long long)sg.n1 * sg.n2;
+    const int bx = (int)((plane + 127) / 128);
+    const int resident = s->num_sms * (s->no_march ? JXF_MIN_BLOCKS : JXF_MARCH_BLOCKS);
+    // chunks along A: every chunk costs one redundant face (+ a 5-plane prologue), while few CTAs per
+    // resident slot leave a partial last wave; pick the chunk count that minimises
+    // (1 + 1.5/chunk_len) * ceil(waves)/waves over chunk lengths >= 16 cells
+    if (a.range_hi <= a.range_lo) { a.range_lo = 0; a.range_hi = g.n[A]; }
+    const int nr = a.range_hi - a.range_lo;
+    int chunks = 1;
+    double best = 1e30;
+    const int max_chunks = std::max(1, std::min(nr / 16, 65535));
+    for (int c = 1; c <= max_chunks; ++c) {
+      const int len = (nr + c - 1) / c;
+      const int cc = (nr + len - 1) / len;
+      const double waves = (double)bx * cc / resident;
+      const double cost = (1.0 + 1.5 / len) * (waves <= 1.0 ? 1.0 / waves : std::ceil(waves) / waves);
+      if (cost < best - 1e-12) { best = cost; chunks = cc; }
+    }
+    a.chunk_len = (nr + chunks - 1) / chunks;
+    chunks = (nr + a.chunk_len - 1) / a.chunk_len;
+    dim3 grid(bx, chunks);
+    set_role_bcs(sg, a);
+    ProfScope prof(s, A + 3 * EPI, st);
+#ifdef JXF_WITH_STRIDED
+    if (s->no_march) {
+      sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
+      return check_launch("sweep_strided");
+    }
+#endif
+    sweep_march<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
+  } else {
+    sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
+    sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    set_role_bcs(sg, a);
+    const long long rows = (long long)sg.n1 * sg.n2;
+    const int nf = g.n[A] + 1;
+    const long long total = rows * nf;
+#if JXF_ROWS_KERNEL
+    // production form whenever groups of >= 4 rows give every resident warp several work items
+    const long long warps_resident = 4LL * resident;
+    if ((s->force_rows || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
+      RowsArgs ra;
+      ra.iters_per_row = (g.n[A] + 31) / 32;
+      // one group per warp, 4 warps per CTA, many more CTAs than resident slots: the hardware block
+      // scheduler balances the tail (a static groups-per-warp split left ~8 % of the warps idle at the end)
+      int G = 8;
+      while (G > 4 && rows / G < warps_resident * 16) G >>= 1;
+      ra.group_rows = G;
+      ra.shift = ((g.off[A] - 2) & 1) ? 3 : 2;
+      ra.cA_off = g.off[A];
+      ra.c1_off = g.off[T1];
+      ra.c2_off = g.off[T2];
+      ra.tma_dim1_is_role = 2;
+      const long long groups = (rows + G - 1) / G;
+      const long long blocks = std::min<long long>((groups + 3) / 4, 1LL << 30);
+      const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0);
+      ProfScope prof(s, A + 3 * EPI, st);
+      if (map) {
+        sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map);
+      } else {
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy);
+      }
+      return check_launch("sweep_rows");
+    }
+#endif
+    const long long target_warps = 4LL * resident * 4;   // ~4 waves of warps
+    long long span;
+    if (rows >= target_warps) {
+      span = (rows / target_warps) * nf;                 // whole rows per range, no carry-in face
+      span = std::min<long long>(span, 64LL * nf);
+    } else {
+      span = std::max<long long>(31, ((total / target_warps) / 32) * 32 - 1);
+      span = std::min<long long>(span, 32LL * 256 - 1);
+    }
+    if (span > 0x7fffffff) span = 0x7fffffff;
+    a.span = (int)span;
+    const long long nranges = (total + span - 1) / span;
+    const long long blocks = std::min<long long>((nranges + 3) / 4, (long long)resident * 4);
+    ProfScope prof(s, A + 3 * EPI, st);
+    sweep_contig<A, RECON, RIEMANN, EPI><<<(unsigned)std::max<long long>(1, blocks), 128, 0, st>>>(sg, a, total);
+  }
+  return check_launch("sweep");
+}
