@@ -62,12 +62,13 @@ def _compile_all(out: str, defines, verbose: bool, tag: str) -> None:
     from concurrent.futures import ThreadPoolExecutor
     nvcc = find_nvcc()
     tune = any(d.split("=")[0] == "JXF_TUNE_ONLY" for d in defines)
+    limit = next((int(d.split("=")[1]) for d in defines if d.split("=")[0] == "JXF_RECON_LIMIT"), 6)
     objdir = os.path.join(OBJ, tag)
     os.makedirs(objdir, exist_ok=True)
     base = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c"]
     jobs = [(base + ["-o", os.path.join(objdir, "main.o"), MAIN], os.path.join(objdir, "main.o"))]
     # the generic instantiations (RECON 4 / 5) take longest: start them first
-    for a, r in sorted(TUNE_PAIRS if tune else PAIRS, key=lambda p: -p[1]):
+    for a, r in sorted(TUNE_PAIRS if tune else [p for p in PAIRS if p[1] < limit], key=lambda p: -p[1]):
         o = os.path.join(objdir, f"sweep_a{a}_r{r}.o")
         jobs.append((base + [f"-DJXF_INST_A={a}", f"-DJXF_INST_RECON={r}", "-o", o, INST], o))
 
@@ -115,9 +116,25 @@ def build_variant(name: str, defines, verbose: bool = False) -> str:
     return out
 
 
+def build_reforder(force: bool = False) -> str:
+    """The checking build of tests/test_gpu_production.py: the reference's operations in the reference's order, no FMA
+    contraction (-DJXF_REFERENCE_ORDER -fmad=false); the WENO5-Z instantiations (PRIMITIVE / CHAR-PRIMITIVE, every Riemann
+    solver) are enough for the fixtures it is run on.  Selected with JXF_LIB_VARIANT=reforder."""
+    out = OUT.replace(".so", "_reforder.so")
+    stamp = out + ".srchash"
+    digest = source_hash()
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return out
+    build_variant("reforder", ["JXF_REFERENCE_ORDER", "JXF_RECON_LIMIT=2", "-fmad=false"])
+    with open(stamp, "w") as fh:
+        fh.write(digest + "\n")
+    return out
+
+
 if __name__ == "__main__":
     if "--variant" in sys.argv:
         i = sys.argv.index("--variant")
-        build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose="-v" in sys.argv)
+        rest = [x for x in sys.argv[i + 2:] if x != "--ptxas-v"]
+        build_variant(sys.argv[i + 1], rest, verbose="--ptxas-v" in sys.argv)
     else:
         build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -491,6 +491,8 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
 #ifdef JXF_WITH_STRIDED
   s->no_march = getenv("JXF_NO_MARCH") && atoi(getenv("JXF_NO_MARCH")) != 0;
 #endif
+  s->rows_group = getenv("JXF_ROWS_G") ? std::max(0, std::min(32, atoi(getenv("JXF_ROWS_G")))) : 0;
+  s->no_plain = getenv("JXF_NO_PLAIN") && atoi(getenv("JXF_NO_PLAIN")) != 0;   // A/B: option-carrying instantiations
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
   s->n_maps = 0;
   s->num_sms = 148;
@@ -625,87 +627,28 @@ const CUtensorMap* get_rows_map(jxf_solver* s, const double* base) {
 // sweep dispatch
 // ---------------------------------------------------------------------------
 // launch_sweep<A, RECON, RIEMANN, EPI> is instantiated in sweep_inst.cu, one translation unit per (A, RECON)
-#ifdef JXF_TUNE_ONLY
-extern template int launch_sweep<0, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-#else
-extern template int launch_sweep<0, 0, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 0, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 0, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 0, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 1, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 1, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 2, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 2, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 2, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 2, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 3, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 3, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 3, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 3, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 4, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 4, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 4, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 4, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 5, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 5, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 5, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<0, 5, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 0, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 0, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 0, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 0, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 1, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 2, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 2, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 2, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 2, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 3, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 3, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 3, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 3, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 4, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 4, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 4, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 4, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 5, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 5, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 5, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<1, 5, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 0, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 0, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 0, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 0, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 1, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 2, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 2, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 2, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 2, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 3, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 3, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 3, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 3, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 4, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 4, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 4, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 4, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 5, 0, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 5, 0, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 5, 1, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-extern template int launch_sweep<2, 5, 1, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
+#ifndef JXF_RECON_LIMIT
+#define JXF_RECON_LIMIT 6     // RECON templates 0 .. JXF_RECON_LIMIT - 1 are in this build
 #endif
+#define JXF_EXTERN_SWEEP(A, R, S, E) extern template int launch_sweep<A, R, S, E>(const jxf_solver*, SweepArgs, cudaStream_t);
+#ifdef JXF_TUNE_ONLY
+JXF_SWEEPS_TUNE(JXF_EXTERN_SWEEP, 0) JXF_SWEEPS_TUNE(JXF_EXTERN_SWEEP, 1) JXF_SWEEPS_TUNE(JXF_EXTERN_SWEEP, 2)
+#else
+#if JXF_RECON_LIMIT < 6     // checking builds with the WENO5-Z instantiations only (build.py build_reforder)
+#define JXF_EXTERN_AXIS(A)                                                                                   \
+  JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 0) JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 1)                                 \
+  JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 0) JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 1)
+#else
+#define JXF_EXTERN_AXIS(A)                                                                                   \
+  JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 0) JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 1) JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 2) \
+  JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 3) JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 4) JXF_SWEEPS_OF(JXF_EXTERN_SWEEP, A, 5) \
+  JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 0) JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 1)                     \
+  JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 2) JXF_SWEEPS_PLAIN_OF(JXF_EXTERN_SWEEP, A, 3)
+#endif
+JXF_EXTERN_AXIS(0) JXF_EXTERN_AXIS(1) JXF_EXTERN_AXIS(2)
+#undef JXF_EXTERN_AXIS
+#endif
+#undef JXF_EXTERN_SWEEP
 
 // stencil id in the option word: bits 11-14, the fifth id bit at bit 22 (numerics.cuh stencil_id)
 static int stencil_bits(int stencil) { return ((stencil & 15) << 11) | ((stencil >> 4) << 22); }
@@ -718,6 +661,20 @@ static bool generic_path(const jxf_solver* s) {
 template <int A, int RECON, int RIEMANN>
 static int dispatch_epi(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
   return epi ? launch_sweep<A, RECON, RIEMANN, 1>(s, a, st) : launch_sweep<A, RECON, RIEMANN, 0>(s, a, st);
+}
+// HLLC + EINFELDT with option word 0 (no limiter, no alternative signal speed) on a tuned stencil: the RIEMANN_HLLC_PLAIN
+// instantiations (numerics.cuh), and for the usual epilogue (earlier axes' sum present, no volume force) the
+// instantiations with compile-time blend / reduce flags (sweep_kernels.cuh EpiFlags).  Same arithmetic.
+template <int A, int RECON>
+static int dispatch_plain(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  if (!epi) return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 0>(s, a, st);
+  if (!a.has_prev || a.volume_force) return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 1>(s, a, st);
+  switch ((a.blend ? 1 : 0) | (a.reduce ? 2 : 0)) {
+    case 0: return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 2>(s, a, st);
+    case 1: return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 3>(s, a, st);
+    case 2: return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 4>(s, a, st);
+    default: return launch_sweep<A, RECON, RIEMANN_HLLC_PLAIN, 5>(s, a, st);
+  }
 }
 // The kernel instantiation a configuration runs in (also reported by jxf_debug_dispatch, so that the host simulation
 // of the device functions, tests/hostsim, can be checked to use the same template parameters and option word):
@@ -736,6 +693,9 @@ static int riemann_template_of(const jxf_solver* s) {
 
 template <int A, int RECON>
 static int dispatch_riemann(const jxf_solver* s, const SweepArgs& a, int epi, cudaStream_t st) {
+  if constexpr (RECON < 4) {
+    if (riemann_template_of(s) == RIEMANN_HLLC && a.limiter == 0 && !s->no_plain) return dispatch_plain<A, RECON>(s, a, epi, st);
+  }
 #ifdef JXF_TUNE_ONLY   // tuning builds instantiate the bench variant only (CHAR-PRIMITIVE + HLLC)
   if (s->cfg.riemann != JXF_RIEMANN_HLLC) return fail(JXF_ERR_UNSUPPORTED, "tuning build: HLLC only");
   return dispatch_epi<A, RECON, RIEMANN_HLLC>(s, a, epi, st);
@@ -755,13 +715,19 @@ static int dispatch_recon(const jxf_solver* s, const SweepArgs& a, int epi, cuda
   // FLUX-SPLITTING is a run-time branch of the generic instantiations' face flux (numerics.cuh flux_splitting_flux);
   // every stencil other than the two tuned WENO5 forms, the conservative reconstruction variables and the ROE frozen
   // state run in the STENCIL_GENERIC instantiations (RECON 4 / 5), selected at run time by the option word (base_args)
+  if (recon_template_of(s) >= JXF_RECON_LIMIT)
+    return fail(JXF_ERR_UNSUPPORTED, "this (checking) build holds the RECON < %d kernel instantiations only", JXF_RECON_LIMIT);
   switch (recon_template_of(s)) {
     case 0: return dispatch_riemann<A, 0>(s, a, epi, st);
     case 1: return dispatch_riemann<A, 1>(s, a, epi, st);
+#if JXF_RECON_LIMIT >= 6
     case 2: return dispatch_riemann<A, 2>(s, a, epi, st);
     case 3: return dispatch_riemann<A, 3>(s, a, epi, st);
     case 4: return dispatch_riemann<A, 4>(s, a, epi, st);
     default: return dispatch_riemann<A, 5>(s, a, epi, st);
+#else
+    default: return JXF_ERR_UNSUPPORTED;
+#endif
   }
 #endif
 }

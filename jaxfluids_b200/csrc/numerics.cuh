@@ -23,7 +23,11 @@ enum { ALT_WENO5Z = 0, ALT_WENO5JS = 1,   // reference-order forms of the two tu
        ALT_WENO1 = 2, ALT_WENO3JS = 3, ALT_WENO3Z = 4, ALT_TENO5 = 5, ALT_WENO6CU = 6, ALT_KOREN = 7, ALT_MC = 8,
        ALT_MINMOD = 9, ALT_SUPERBEE = 10, ALT_VANALBADA = 11, ALT_VANLEER = 12, ALT_WENO3N = 13, ALT_CENTRAL2 = 14,
        ALT_TENO6 = 15, ALT_TENO5A = 16, ALT_TENO6A = 17 };   // ids >= 16: bit 22 of the option word is the fifth id bit
-enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1 };
+enum { RIEMANN_HLLC = 0, RIEMANN_RUSANOV = 1,
+       // HLLC + EINFELDT with every run-time option of the face flux off (option word 0: no interpolation / flux limiter,
+       // no alternative signal speed): the same arithmetic as RIEMANN_HLLC with the option branches -- and the
+       // out-of-line call sites behind them -- compiled out of the sweep loops.  Tuned stencils only (RECON 0..3).
+       RIEMANN_HLLC_PLAIN = 2 };
 // HLLC wave-speed estimate (signal_speeds.py): a run-time option `sig` of riemann_flux (uniform branch), packed
 // with the limiter mode into the `opt` argument of face_flux: opt = lim | (sig << 4) | (HLL << 8), HLL = the HLL
 // Riemann solver (HLL.py) riding on the RIEMANN_RUSANOV kernel instantiations
@@ -1547,6 +1551,12 @@ __device__ __forceinline__ void apply_flux_limiter(const double (&w)[5][6], doub
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma, double (&F)[5], int opt,
                                           const FluxLimArgs& fl) {
+  if constexpr (RIEMANN == RIEMANN_HLLC_PLAIN) {
+    double pl[5], pr[5];
+    reconstruct<A, RECON>(w, gamma, pl, pr);
+    riemann_flux<A, RIEMANN_HLLC>(pl, pr, gamma, F, SIG_EINFELDT);
+    return;
+  }
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
@@ -1588,6 +1598,12 @@ __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double 
 template <int A, int RECON, int RIEMANN>
 __device__ __forceinline__ void face_flux_carry(const double (&w)[5][6], double gamma, double (&F)[5],
                                                 ReconCarry<RECON>& cy, int opt, const FluxLimArgs& fl) {
+  if constexpr (RIEMANN == RIEMANN_HLLC_PLAIN) {
+    double pl[5], pr[5];
+    reconstruct_carry<A, RECON>(w, gamma, pl, pr, cy);
+    riemann_flux<A, RIEMANN_HLLC>(pl, pr, gamma, F, SIG_EINFELDT);
+    return;
+  }
   const int lim = opt & 15, sig = opt >> 4;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     if ((opt >> 17) & 3) {       // convective_solver = FLUX-SPLITTING
@@ -1632,6 +1648,21 @@ struct Red {
     min_rho = fmin(min_rho, p[0]);
     min_p = fmin(min_p, p[4]);
   }
+#ifndef JXF_REFERENCE_ORDER
+  // the same with the MUFU + Newton reciprocal / rsqrt (<= 3 ulp on c; dt = CFL dx / (max + eps) moves by as much) and
+  // plain compare-selects (finite data); used by the tuned epilogue instantiations
+  __device__ __forceinline__ void add_cell_fast(const double (&p)[5], double gamma, int active_mask) {
+    const double x = gamma * p[4] * rcp_fast(p[0]);
+    const double c = x * rsqrt_fast(x);
+    double s = 0.0;
+    if (active_mask & 1) s += fabs(p[1]) + c;
+    if (active_mask & 2) s += fabs(p[2]) + c;
+    if (active_mask & 4) s += fabs(p[3]) + c;
+    max_s = (s > max_s) ? s : max_s;
+    min_rho = (p[0] < min_rho) ? p[0] : min_rho;
+    min_p = (p[4] < min_p) ? p[4] : min_p;
+  }
+#endif
 };
 
 __device__ __forceinline__ void atomic_max_f64(double* addr, double v) {

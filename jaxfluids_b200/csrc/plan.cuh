@@ -38,6 +38,8 @@ struct jxf_solver {
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
+  int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
+  bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
   int n_maps;
   const void* map_ptr[8];
@@ -126,7 +128,7 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     chunks = (nr + a.chunk_len - 1) / a.chunk_len;
     dim3 grid(bx, chunks);
     set_role_bcs(sg, a);
-    ProfScope prof(s, A + 3 * EPI, st);
+    ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
 #ifdef JXF_WITH_STRIDED
     if (s->no_march) {
       sweep_strided<A, RECON, RIEMANN, EPI><<<grid, 128, 0, st>>>(sg, a);
@@ -151,6 +153,7 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       // scheduler balances the tail (a static groups-per-warp split left ~8 % of the warps idle at the end)
       int G = 8;
       while (G > 4 && rows / G < warps_resident * 16) G >>= 1;
+      if (s->rows_group > 0) G = s->rows_group;            // JXF_ROWS_G (tuning)
       ra.group_rows = G;
       ra.shift = ((g.off[A] - 2) & 1) ? 3 : 2;
       ra.cA_off = g.off[A];
@@ -160,7 +163,7 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       const long long groups = (rows + G - 1) / G;
       const long long blocks = std::min<long long>((groups + 3) / 4, 1LL << 30);
       const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0);
-      ProfScope prof(s, A + 3 * EPI, st);
+      ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
       if (map) {
         sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map);
       } else {
@@ -184,8 +187,15 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     a.span = (int)span;
     const long long nranges = (total + span - 1) / span;
     const long long blocks = std::min<long long>((nranges + 3) / 4, (long long)resident * 4);
-    ProfScope prof(s, A + 3 * EPI, st);
+    ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
     sweep_contig<A, RECON, RIEMANN, EPI><<<(unsigned)std::max<long long>(1, blocks), 128, 0, st>>>(sg, a, total);
   }
   return check_launch("sweep");
 }
+
+// The instantiations of launch_sweep: X(A, RECON, RIEMANN, EPI).  Every (A, RECON) pair has the four (RIEMANN, EPI)
+// combinations with run-time options; the tuned stencils (RECON 0..3) add the option-free HLLC + EINFELDT set with the
+// run-time-flag epilogue (1) and the four compile-time-flag epilogues (2..5).
+#define JXF_SWEEPS_OF(X, A, R) X(A, R, 0, 0) X(A, R, 0, 1) X(A, R, 1, 0) X(A, R, 1, 1)
+#define JXF_SWEEPS_PLAIN_OF(X, A, R) X(A, R, 2, 0) X(A, R, 2, 1) X(A, R, 2, 2) X(A, R, 2, 3) X(A, R, 2, 4) X(A, R, 2, 5)
+#define JXF_SWEEPS_TUNE(X, A) X(A, 1, 0, 0) X(A, 1, 0, 1) JXF_SWEEPS_PLAIN_OF(X, A, 1)

@@ -6,9 +6,12 @@
 #error "compile with -DJXF_INST_A=<axis> -DJXF_INST_RECON=<recon>"
 #endif
 
-template int launch_sweep<JXF_INST_A, JXF_INST_RECON, RIEMANN_HLLC, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-template int launch_sweep<JXF_INST_A, JXF_INST_RECON, RIEMANN_HLLC, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
-#ifndef JXF_TUNE_ONLY
-template int launch_sweep<JXF_INST_A, JXF_INST_RECON, RIEMANN_RUSANOV, 0>(const jxf_solver*, SweepArgs, cudaStream_t);
-template int launch_sweep<JXF_INST_A, JXF_INST_RECON, RIEMANN_RUSANOV, 1>(const jxf_solver*, SweepArgs, cudaStream_t);
+#define JXF_INST_SWEEP(A, R, S, E) template int launch_sweep<A, R, S, E>(const jxf_solver*, SweepArgs, cudaStream_t);
+#ifdef JXF_TUNE_ONLY
+JXF_SWEEPS_TUNE(JXF_INST_SWEEP, JXF_INST_A)
+#else
+JXF_SWEEPS_OF(JXF_INST_SWEEP, JXF_INST_A, JXF_INST_RECON)
+#if JXF_INST_RECON < 4
+JXF_SWEEPS_PLAIN_OF(JXF_INST_SWEEP, JXF_INST_A, JXF_INST_RECON)
+#endif
 #endif

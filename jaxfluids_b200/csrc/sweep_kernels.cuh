@@ -88,18 +88,45 @@ __device__ __forceinline__ void prefetch_l2(const double* p) {
 #endif
 }
 
+// a * b + c of the cell update: one fused multiply-add in the production evaluation; separate multiply and add -- the
+// reference's operations -- in JXF_REFERENCE_ORDER builds (compiled with -fmad=false for the strict-norm parity test)
+#ifdef JXF_REFERENCE_ORDER
+#define JXF_MADD(a, b, c) ((a) * (b) + (c))
+#else
+#define JXF_MADD(a, b, c) fma((a), (b), (c))
+#endif
+
+// EPI template parameter of the sweep kernels:
+//   0      no epilogue: the axis contribution goes to the rhs accumulator;
+//   1      epilogue with RUN-TIME flags (has_prev, blend, reduce, volume_force, fuse_halo of SweepArgs);
+//   2..5   "fast" epilogue: has_prev = 1, volume_force = 0 and the flags (EPI - 2) = blend | reduce << 1 are COMPILE-TIME,
+//          so the hot loop carries no flag loads / branches for them (launch_sweep picks the instantiation from the
+//          run-time flags; same arithmetic).  fuse_halo stays a run-time flag (its call sits in a cold branch).
+template <int EPI>
+struct EpiFlags {
+  static constexpr bool kStatic = EPI >= 2;
+  static constexpr bool kBlend = ((EPI - 2) & 1) != 0;
+  static constexpr bool kReduce = ((EPI - 2) & 2) != 0;
+  __device__ static __forceinline__ bool has_prev(const SweepArgs& a) { return kStatic ? true : a.has_prev != 0; }
+  __device__ static __forceinline__ bool blend(const SweepArgs& a) { return kStatic ? kBlend : a.blend != 0; }
+  __device__ static __forceinline__ bool reduce(const SweepArgs& a) { return kStatic ? kReduce : a.reduce != 0; }
+  __device__ static __forceinline__ bool halo(const SweepArgs& a) { return a.fuse_halo != 0; }
+  __device__ static __forceinline__ bool force(const SweepArgs& a) { return kStatic ? false : a.volume_force != 0; }
+};
+
 // operands of the cell update that come from memory; loaded EARLY (before the flux arithmetic of
 // the iteration) so their latency hides behind ~700 FP64 instructions
 template <int EPI>
 struct CellIn {
-  double rhs[5];   // EPI=0: accumulate target (if accumulate); EPI=1: earlier axes' sum (if has_prev)
-  double U[5];     // EPI=1
-  double Un[5];    // EPI=1, blend
+  double rhs[5];   // EPI=0: accumulate target (if accumulate); EPI>=1: earlier axes' sum (if has_prev)
+  double U[5];     // EPI>=1
+  double Un[5];    // EPI>=1, blend
 };
 
 template <int EPI>
 __device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
                                              CellIn<EPI>& in) {
+  using E = EpiFlags<EPI>;
   if (EPI == 0) {
     if (a.accumulate) {
 #pragma unroll
@@ -108,11 +135,11 @@ __device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs
   } else {
 #pragma unroll
     for (int v = 0; v < 5; ++v) in.U[v] = a.cons_in[hidx + v * g.vst];
-    if (a.has_prev) {
+    if (E::has_prev(a)) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) in.rhs[v] = a.rhs[ridx + v * g.rvst];
     }
-    if (a.blend) {
+    if (E::blend(a)) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) in.Un[v] = a.cons_n[hidx + v * g.vst];
     }
@@ -200,22 +227,23 @@ template <int EPI>
 __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArgs& a, long long hidx, long long ridx,
                                               const CellIn<EPI>& in, const double (&r)[5], double step, Red& red,
                                               int iA, int i1, int i2) {
+  using E = EpiFlags<EPI>;
   // r = F_{i-1/2} - F_{i+1/2}; the axis contribution (1/dx) r (space_solver.py:597-599) is added to the
   // earlier axes' sum with one fused multiply-add
   if (EPI == 0) {
 #pragma unroll
-    for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = a.accumulate ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
+    for (int v = 0; v < 5; ++v) a.rhs[ridx + v * g.rvst] = a.accumulate ? JXF_MADD(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
   } else {
     double U[5];
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
-      double tot = a.has_prev ? fma(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
-      if (a.volume_force) {     // space_solver.py:378-384 with the einsums of source_term_solver.py:180-182
+      double tot = E::has_prev(a) ? JXF_MADD(a.inv_dx, r[v], in.rhs[v]) : a.inv_dx * r[v];
+      if (E::force(a)) {     // space_solver.py:378-384 with the einsums of source_term_solver.py:180-182
         if (v >= 1 && v <= 3) tot += a.gravity[v - 1] * in.U[0];
         if (v == 4) tot += (a.gravity[0] * in.U[1] + a.gravity[1] * in.U[2]) + a.gravity[2] * in.U[3];
       }
       double u = in.U[v];
-      if (a.blend) u = a.ca * u + a.cb * in.Un[v];
+      if (E::blend(a)) u = a.ca * u + a.cb * in.Un[v];
       U[v] = u + step * tot;
     }
     double p[5];
@@ -225,8 +253,13 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
       a.cons_out[hidx + v * g.vst] = U[v];
       a.prims_out[hidx + v * g.vst] = p[v];
     }
-    if (a.reduce) red.add_cell(p, a.gamma, a.active_mask);
-    if (a.fuse_halo) {
+    if (E::reduce(a)) {
+#ifndef JXF_REFERENCE_ORDER
+      if (E::kStatic) red.add_cell_fast(p, a.gamma, a.active_mask); else
+#endif
+      red.add_cell(p, a.gamma, a.active_mask);
+    }
+    if (E::halo(a)) {
       // boundary-adjacent cells only (a thin shell); warp-divergent by construction
       const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (i1 < a.nh) | (i1 >= g.n1 - a.nh) | (i2 < a.nh) |
                         (i2 >= g.n2 - a.nh);
@@ -307,7 +340,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_strided(const __gri
     }
   }
   if (EPI) {
-    if (a.reduce) red_commit(red, a.red);
+    if (EpiFlags<EPI>::reduce(a)) red_commit(red, a.red);
   }
 }
 
@@ -411,7 +444,7 @@ sweep_march(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepAr
     ring_wait<0>();
   }
   if (EPI) {
-    if (a.reduce) red_commit(red, a.red);
+    if (EpiFlags<EPI>::reduce(a)) red_commit(red, a.red);
   }
 }
 
@@ -509,7 +542,7 @@ __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS) sweep_contig(const __grid
     }
   }
   if (EPI) {
-    if (a.reduce) red_commit(red, a.red);
+    if (EpiFlags<EPI>::reduce(a)) red_commit(red, a.red);
   }
 }
 
@@ -587,6 +620,155 @@ struct RowsArgs {
   int tma_dim1_is_role;   // which role (1 or 2) is TMA dimension 1 (the faster transverse axis): always role 2
 };
 
+#ifndef JXF_ROWS_V1      // -DJXF_ROWS_V1: the round-1 form of the loop (A/B builds)
+// Loop structure (round 2): rows and iterations are nested loops, so that the iteration body is ONE straight-line
+// block -- no `it == 0` / `act` / `j + 1 < total` branches around the flux arithmetic, the TMA issue is predicated
+// instead of branched, every lane evaluates its face (lanes past the end of the row work on the zero-filled tail of
+// the window; only their loads / stores are predicated), and the left flux comes from ONE rotate-shuffle per
+// variable (lane l <- lane l-1, lane 0 <- lane 31 = the carry of the next iteration).
+template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
+__global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
+sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
+  __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
+  __shared__ alignas(8) uint64_t bars[4 * 2];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long ngwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nrows = (long long)g.n1 * g.n2;
+  const int G = ra.group_rows;
+  const long long ngroups = (nrows + G - 1) / G;
+  const int ipr = ra.iters_per_row;
+  const int nA = g.nA;
+  const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
+  unsigned char* const win0 = win_raw + wid * 2 * kWinStride;      // this warp's two window buffers
+  uint64_t* const bar0 = &bars[wid * 2];
+  const uint32_t bar_s = smem_u32(bar0), win_s = smem_u32(win0);
+  uint32_t phase_bits = 0u;                                        // bit b = parity to wait for on buffer b
+  if (USE_TMA) {
+    if (lane == 0) {
+      mbar_init(bar0, 1);
+      mbar_init(bar0 + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  Red red;
+  red.init();
+  const int prev_lane = (lane + 31) & 31;
+
+  // stage the window of (row (i1n, i2n), iteration itn) into buffer b; `on` = false posts nothing (past the end)
+  auto issue = [&](int b, int itn, int i1n, int i2n, bool on) {
+    if (USE_TMA) {
+      // TMA dims: (contiguous sweep axis, faster transverse (role 2), slower transverse (role 1), variable);
+      // cells past the end of the row are zero-filled by the TMA unit.  One elected lane, predicated (no branch).
+      const int c0 = ra.cA_off + 32 * itn - ra.shift, c1 = ra.c2_off + i2n, c2 = ra.c1_off + i1n;
+      const uint32_t bar = bar_s + 8u * b, dst = win_s + (uint32_t)kWinStride * b;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.ne.s32 p, %7, 0;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %8;\n"
+          "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%3, %4, %5, %6}], [%1];\n"
+          "}\n" ::"r"(dst), "r"(bar), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(0),
+          "r"((int)(on && lane == 0)), "r"(kWinBytes)
+          : "memory");
+    } else {
+      if (on) {
+        double* const wb = reinterpret_cast<double*>(win0 + b * kWinStride);
+        const double* src = a.prims + i1n * g.s1 + i2n * g.s2 + (long long)(32 * itn - ra.shift) * g.sA;
+        const int cmax = nA + 2 - (32 * itn - ra.shift);  // slots holding cells <= nA+2 are valid
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          if (lane <= cmax) cp_async8(wb + v * kWinSlots + lane, src + v * g.vst + lane);
+          if (lane < 6 && 32 + lane <= cmax) cp_async8(wb + v * kWinSlots + 32 + lane, src + v * g.vst + 32 + lane);
+        }
+      }
+      cp_async_commit();
+    }
+  };
+
+  for (long long group = gwarp; group < ngroups; group += ngwarps) {
+    const long long row0 = group * G;
+    const int nr = (int)min((long long)G, nrows - row0);
+    const int i1_0 = (int)(row0 / g.n2);
+    const int i2_0 = (int)(row0 - (long long)i1_0 * g.n2);
+    int b = 0;
+    issue(0, 0, i1_0, i2_0, true);
+    // ---- the row-opening faces f = 0 of this group, one row per lane (direct strided loads; the flux
+    // code is called out of line here so the hot loop below holds the only inlined copy) -----------
+    double F0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane < nr) {
+      const long long row = row0 + lane;
+      const int k1 = (int)(row / g.n2);
+      const int k2 = (int)(row - (long long)k1 * g.n2);
+      face_flux_from_global<A, RECON, RIEMANN>(a.prims + k1 * g.s1 + k2 * g.s2 - 3 * g.sA, g.vst, g.sA, a.gamma, F0, a.limiter, a.fl);
+    }
+    int i1 = i1_0, i2 = i2_0;
+    for (int r = 0; r < nr; ++r) {
+      // next row (for the staging of its first window during this row's last iteration)
+      int i1x = i1, i2x = i2 + 1;
+      if (i2x == g.n2) {
+        i2x = 0;
+        ++i1x;
+      }
+      const bool more_rows = r + 1 < nr;
+      const long long col_h = i1 * g.s1 + i2 * g.s2;
+      const long long col_r = i1 * g.r1 + i2 * g.r2;
+      double carry[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) carry[v] = __shfl_sync(0xffffffffu, F0[v], r);
+      for (int it = 0; it < ipr; ++it) {
+        // stage the next iteration's window into the other buffer
+        const bool last_it = it + 1 == ipr;
+        issue(b ^ 1, last_it ? 0 : it + 1, last_it ? i1x : i1, last_it ? i2x : i2, !last_it || more_rows);
+        const int f = 1 + 32 * it + lane;
+        const bool act = f <= nA;
+        const long long hidx = col_h + (long long)(f - 1) * g.sA;
+        const long long ridx = col_r + (long long)(f - 1) * g.rA;
+        CellIn<EPI> in;
+        if (act) load_cell_in<EPI>(g, a, hidx, ridx, in);
+        // wait for this iteration's window
+        const double* const wb = reinterpret_cast<const double*>(win0 + b * kWinStride);
+        if (USE_TMA) {
+          mbar_wait(bar0 + b, (phase_bits >> b) & 1u);
+          phase_bits ^= (1u << b);
+        } else {
+          cp_async_wait<1>();
+          __syncwarp();
+        }
+        double F[5];
+        {
+          double w[5][6];
+          const double* wl = wb + (ra.shift - 2) + lane;
+#pragma unroll
+          for (int v = 0; v < 5; ++v)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) w[v][k] = wl[v * kWinSlots + k];
+          // (idle tail lanes see the zero-filled end of the window: their NaN result is never used or stored)
+          face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter, a.fl);
+        }
+        double rr[5];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          const double rot = __shfl_sync(0xffffffffu, F[v], prev_lane);   // lane 0 receives lane 31's flux
+          rr[v] = ((lane == 0) ? carry[v] : rot) - F[v];
+          carry[v] = rot;                                                // meaningful on lane 0: the next carry
+        }
+        if (act) finalize_cell<EPI>(g, a, hidx, ridx, in, rr, step, red, f - 1, i1, i2);
+        __syncwarp();          // all lanes are done with win[b] before it is refilled two iterations later
+        b ^= 1;
+      }
+      i1 = i1x;
+      i2 = i2x;
+    }
+    if (!USE_TMA) cp_async_wait<0>();
+  }
+  if (EPI) {
+    if (EpiFlags<EPI>::reduce(a)) red_commit(red, a.red);
+  }
+}
+#else
 template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
 __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
 sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
@@ -727,8 +909,10 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
     }
   }
   if (EPI) {
-    if (a.reduce) red_commit(red, a.red);
+    if (EpiFlags<EPI>::reduce(a)) red_commit(red, a.red);
   }
 }
+
+#endif  // JXF_ROWS_V1
 
 }  // namespace jxf

@@ -41,11 +41,25 @@ class InitializationManager:
         di = self.domain_information
         mesh = di.compute_device_mesh_grid(self.parallel.rank, sparse=True)
         ic = self.case_setup.initial_condition_setup
+        if "turbulent" in ic:
+            return self._host_primitives_turbulent(ic["turbulent"])
         out = np.empty((5,) + tuple(di.device_number_of_cells), dtype=np.float64)
         shape = tuple(di.device_number_of_cells)
         for v, name in enumerate(("rho", "u", "v", "w", "p")):
             out[v] = np.broadcast_to(ic[name](*mesh), shape)
         return out
+
+    def _host_primitives_turbulent(self, tb) -> np.ndarray:
+        """initial_condition/turbulent/case = HIT (turbulence/initialization/turb_init_manager.py:44-82, hit.py:20-110):
+        the generator works on the global grid (global FFTs); every rank evaluates it with the case file's seed and
+        keeps its block."""
+        from . import turbulence
+        di = self.domain_information
+        mat = self.case_setup.material_setup
+        par = {k: v for k, v in tb.items() if k != "case"}
+        glob = turbulence.initialize_hit(di.global_number_of_cells[0], mat.specific_heat_ratio,
+                                         mat.specific_gas_constant, **par)
+        return np.ascontiguousarray(glob[(slice(None),) + di.block_slices(self.parallel.rank)])
 
     def _host_primitives_from_user(self, user_prime_init) -> np.ndarray:
         """user_prime_init is the GLOBAL (5-3+dim, Nx, Ny, Nz) array (material_fields_initializer.py

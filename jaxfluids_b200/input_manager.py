@@ -594,9 +594,37 @@ class InputManager:
             ic_d = ic_d["primitives"]
         labels = tuple(ax for i, ax in enumerate(AXES) if cells[i] > 1)
         ic = {}
-        for name in ("rho", "u", "v", "w", "p"):
-            _assert(name in ic_d, f"Key {name} is not optional, but missing initial_condition/{name}.", S)
-            ic[name] = make_ic_callable(ic_d[name], labels, f"initial_condition/{name}")
+        if "turbulent" in ic_d:
+            # initial_condition/turbulent (read_initial_conditions.py:95-170): a generated turbulent field instead of
+            # lambdas; the HIT generator (turbulence/initialization/hit.py) is what this path implements
+            tb = get_setup_value(ic_d, "turbulent", "initial_condition/turbulent", dict, False, setup=S)
+            tcase = get_setup_value(tb, "case", "initial_condition/turbulent/case", str, False, setup=S)
+            if tcase != "HIT":
+                raise NotImplementedError(f"initial_condition/turbulent/case '{tcase}' is not implemented on the B200 "
+                                          "path (implemented: HIT)")
+            seed = get_setup_value(tb, "random_seed", "initial_condition/turbulent/random_seed", int, True, 0,
+                                   numerical_value_condition=(">=", 0), setup=S)
+            pp = "initial_condition/turbulent/parameters"
+            par = get_setup_value(tb, "parameters", pp, dict, False, setup=S)
+            ic["turbulent"] = dict(
+                case=tcase, random_seed=seed,
+                T_ref=get_setup_value(par, "T_ref", f"{pp}/T_ref", float, False, numerical_value_condition=(">", 0.0), setup=S),
+                rho_ref=get_setup_value(par, "rho_ref", f"{pp}/rho_ref", float, False, numerical_value_condition=(">", 0.0), setup=S),
+                ma_target=get_setup_value(par, "ma_target", f"{pp}/ma_target", float, False, numerical_value_condition=(">", 0.0), setup=S),
+                energy_spectrum=get_setup_value(par, "energy_spectrum", f"{pp}/energy_spectrum", str, False,
+                                                possible_string_values=("KOLMOGOROV", "EXPONENTIAL", "BOX"), setup=S),
+                ic_type=get_setup_value(par, "ic_type", f"{pp}/ic_type", str, False,
+                                        possible_string_values=("IC1", "IC2", "IC3", "IC4"), setup=S),
+                xi_0=get_setup_value(par, "xi_0", f"{pp}/xi_0", int, False, numerical_value_condition=(">=", 0), setup=S),
+                xi_1=get_setup_value(par, "xi_1", f"{pp}/xi_1", int, True, 16, numerical_value_condition=(">=", 0), setup=S),
+                is_velocity_spectral=get_setup_value(par, "is_velocity_spectral", f"{pp}/is_velocity_spectral", bool, True,
+                                                     False, setup=S))
+            _assert(cells[0] == cells[1] == cells[2] and cells[0] > 1,
+                    "initial_condition/turbulent/case HIT needs a cubic 3-D grid.", S)
+        else:
+            for name in ("rho", "u", "v", "w", "p"):
+                _assert(name in ic_d, f"Key {name} is not optional, but missing initial_condition/{name}.", S)
+                ic[name] = make_ic_callable(ic_d[name], labels, f"initial_condition/{name}")
 
         mp_d = get_setup_value(d, "material_properties", "material_properties", dict, False, setup=S)
         eos_d = get_setup_value(mp_d, "equation_of_state", "material_properties/equation_of_state", dict, False, setup=S)

@@ -23,7 +23,7 @@ class _AtIndexer:
         return self._apply(f)
 
     def add(self, v, **k):
-        def f(o): o[self.idx] = o[self.idx] + v
+        def f(o): _np.add.at(o, self.idx, v)      # scatter-add: duplicate indices accumulate, like jax
         return self._apply(f)
 
     def subtract(self, v, **k):
@@ -142,6 +142,17 @@ amax = max
 sum = _red(_np.sum)
 all = _red(_np.all)
 any = _red(_np.any)
+
+
+class _FFT:
+    """jnp.fft: numpy.fft returning the immutable-flavoured subclass (`buffer_hat /= N**3` inside a callee must not
+    alias the caller's array: turbulence/statistics/utilities/energy_spectrum.py:86)."""
+
+    def __getattr__(self, name):
+        return _wrapping(getattr(_np.fft, name))
+
+
+fft = _FFT()
 
 
 def array(x, dtype=None, **k):

@@ -16,12 +16,23 @@ def main(path, pat):
         if m:
             ins.append((int(m.group(1), 16), m.group(2)))
     best = None
+    loops = []
     for addr, txt in ins:
         m = re.search(r"\bBRA\S*\s+(?:\S+,\s*)?`?\(?(0x[0-9a-f]+)\)?", txt)
         if m:
             tgt = int(m.group(1), 16)
-            if tgt < addr and (best is None or addr - tgt > best[1] - best[0]):
-                best = (tgt, addr)
+            if tgt < addr:
+                loops.append((tgt, addr))
+                if best is None or addr - tgt > best[1] - best[0]:
+                    best = (tgt, addr)
+    # --inner: the SMALLEST loop that still holds at least half of the FP64 instructions of the largest one
+    if "--inner" in sys.argv and best is not None:
+        def nfp(lo, hi):
+            return sum(1 for a, t in ins if lo <= a <= hi and re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0]
+                       in ("DFMA", "DMUL", "DADD"))
+        ref = nfp(*best)
+        cands = [l for l in loops if nfp(*l) * 2 >= ref]
+        best = min(cands, key=lambda l: l[1] - l[0])
     print(lines[start].strip(), "total instr", len(ins))
     if best is None:
         print("no loop")

@@ -1,0 +1,144 @@
+"""GPU parity of the PRODUCTION code paths at real sizes, and the strict-norm proof.
+
+* test_reference_order_build_meets_strict_norm: the kernels compiled with -DJXF_REFERENCE_ORDER -fmad=false (the
+  reference's operations in the reference's order, no FMA contraction) meet the north-star bound 1e-12 in the STRICT
+  norm of SURVEY 8(c), max|a - b| / max|b| per field, on the TGV / Riemann / Sod fixtures generated from the reference.
+  The production build differs from that build by rounding only (re-association, FMA, MUFU + Newton reciprocals).
+* test_production_build_reports_both_norms: what the production build reaches in both norms (printed), with the bound
+  each norm supports.
+* test_tgv128_three_steps / test_riemann2d_1024_two_steps: the kernels that run at bench sizes -- sweep_rows with TMA
+  windows, sweep_march with chunking, the fused epilogue with halo images -- against the oracle (port_mt, bit-identical
+  to port) after whole steps, not on forced tiny grids.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port, port_mt
+from tests import helpers as H
+from tests.test_gpu_parity import make_solver, dev, host
+
+pytestmark = pytest.mark.gpu
+ROOT = H.ROOT
+
+
+def _strict_norm_subprocess(variant):
+    env = dict(os.environ)
+    if variant:
+        env["JXF_LIB_VARIANT"] = variant
+    else:
+        env.pop("JXF_LIB_VARIANT", None)
+    r = subprocess.run([sys.executable, "-m", "tests.tools.strict_norm_check"], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = next(l for l in r.stdout.splitlines() if l.startswith("STRICT_NORM "))
+    return json.loads(line[len("STRICT_NORM "):])
+
+
+def test_reference_order_build_meets_strict_norm():
+    from jaxfluids_b200 import build
+    path = build.OUT.replace(".so", "_reforder.so")
+    if not os.path.exists(path):            # normally prebuilt by __graft_entry__.build() and shipped with the tree
+        build.build_reforder()
+    res = _strict_norm_subprocess("reforder")
+    print("\nreference-order, -fmad=false build (strict = SURVEY 8(c) norm):")
+    for name, e in res.items():
+        print(f"  {name:36s} stage rhs strict {e['strict']:.2e}  terms {e['terms']:.2e}  axis {e['axis_strict']:.2e}  "
+              f"step prims {e['step_prims']:.2e}  dt {e['dt']:.1e}")
+        assert e["strict"] <= H.TOL_RHS, (name, e)
+        assert e["axis_strict"] <= H.TOL_RHS, (name, e)
+        assert e["step_prims"] <= 1e-12 and e["dt"] <= 1e-14, (name, e)
+
+
+def test_production_build_reports_both_norms():
+    res = _strict_norm_subprocess(os.environ.get("JXF_LIB_VARIANT"))
+    print("\nproduction build:")
+    for name, e in res.items():
+        print(f"  {name:36s} stage rhs strict {e['strict']:.2e}  terms {e['terms']:.2e}  axis {e['axis_strict']:.2e}  "
+              f"step prims {e['step_prims']:.2e}  dt {e['dt']:.1e}")
+        # the terms norm carries the 1e-12 bound (DESIGN.md "parity norm"); in the strict norm the production build sits
+        # at the conditioning of the reference's own formula under FMA contraction (7.5e-11 on TGV at Mach 0.1)
+        assert e["terms"] <= H.TOL_RHS, (name, e)
+        assert e["strict"] <= 1e-9, (name, e)
+        assert e["step_prims"] <= 1e-12, (name, e)
+
+
+def _tgv_prims(n, two_pi=6.283185307179586):
+    s = port.Setup(cells=(n, n, n), domain=((0.0, two_pi),) * 3, bc={f: "SYMMETRY" for f in port.FACES},
+                   gamma=1.6666666666666667)
+    x, y, z = np.meshgrid(*s.cell_centers(), indexing="ij", sparse=True)
+    pr = np.empty((5, n, n, n))
+    pr[0] = 1.0
+    pr[1] = np.sin(x) * np.cos(y) * np.cos(z)
+    pr[2] = -np.cos(x) * np.sin(y) * np.cos(z)
+    pr[3] = 0.0
+    pr[4] = 1 / 1.4 / 0.1 ** 2 + 1 / 16.0 * ((np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2))
+    return s, pr
+
+
+def _run_and_compare(s, pr, steps, tol_prims, tol_dt=1e-12):
+    from jaxfluids_b200.engine import BlockState
+    with np.errstate(all="ignore"):
+        prims, cons = port.initialize(pr, s)
+    sol = make_solver(s)
+    st = BlockState(sol, prims, cons)
+    stepper = port_mt.ThreadedStepper(s, os.cpu_count() or 1) if s.cells[0] >= 16 else None
+    dt = port.time_step_size(prims, s)
+    assert abs(st.dt.item() - dt) <= 1e-14 * dt
+    mask = H.defined_mask(s)
+    worst = 0.0
+    for i in range(steps):
+        st.step()
+        if stepper is not None:
+            prims, cons, dt = stepper.step(prims, cons, dt)
+        else:
+            prims, cons, dt = port.step(prims, cons, dt, s)
+        assert abs(st.dt.item() - dt) <= tol_dt * dt, f"dt after step {i + 1}"
+        e_p = H.rel_linf(host(st.primitives)[:, mask], prims[:, mask])
+        e_c = H.rel_linf(host(st.conservatives)[:, mask], cons[:, mask])
+        worst = max(worst, e_p, e_c)
+        assert e_p <= tol_prims and e_c <= tol_prims, f"step {i + 1}: prims {e_p:.2e} cons {e_c:.2e}"
+    info = host(st.info)
+    it = (slice(None),) + s.interior
+    assert abs(info[1] - prims[it][0].min()) <= 1e-12 * abs(prims[it][0].min())
+    assert abs(info[2] - prims[it][4].min()) <= 1e-12 * abs(prims[it][4].min())
+    return worst
+
+
+def test_tgv128_three_steps_production_kernels():
+    """TGV 128^3 SYMMETRY, CHAR-PRIMITIVE WENO5-Z + HLLC + RK3: 3 full steps through jxf_step_fused -- sweep_march
+    (x, y; chunked), sweep_rows + TMA (z) with the fused epilogue and halo images -- vs the oracle."""
+    s, pr = _tgv_prims(128)
+    worst = _run_and_compare(s, pr, steps=3, tol_prims=1e-12)
+    print(f"\nTGV 128^3, 3 steps: worst rel Linf (prims, cons incl. face halos) {worst:.2e}")
+
+
+def test_tgv128_periodic_rusanov_two_steps():
+    s, pr = _tgv_prims(128)
+    s.bc = {f: "PERIODIC" for f in port.FACES}
+    s.riemann = "RUSANOV"
+    worst = _run_and_compare(s, pr, steps=2, tol_prims=1e-12)
+    print(f"\nTGV 128^3 PERIODIC Rusanov, 2 steps: worst rel Linf {worst:.2e}")
+
+
+def test_riemann2d_1024_two_steps_production_kernels():
+    """BASELINE config 2: 2-D Riemann problem (Lax-Liu configuration 3) at 1024^2, ZEROGRADIENT, gamma 1.4,
+    CHAR-PRIMITIVE WENO5-Z + HLLC + RK3: 2 steps (2-D rows kernel with the cp.async loader, marching x sweep)."""
+    n = 1024
+    s = port.Setup(cells=(n, n, 1), domain=((0.0, 1.0), (0.0, 1.0), (0.0, 1.0)),
+                   bc={f: ("ZEROGRADIENT" if f in ("east", "west", "north", "south") else "INACTIVE") for f in port.FACES},
+                   gamma=1.4)
+    x, y, _ = np.meshgrid(*s.cell_centers(), indexing="ij", sparse=True)
+    ne, nw, sw, se = (x >= 0.5) & (y >= 0.5), (x < 0.5) & (y >= 0.5), (x < 0.5) & (y < 0.5), (x >= 0.5) & (y < 0.5)
+    pr = np.zeros((5, n, n, 1))
+    for m, (rho, u, v, p) in ((ne, (1.5, 0.0, 0.0, 1.5)), (nw, (0.5323, 1.206, 0.0, 0.3)), (sw, (0.138, 1.206, 1.206, 0.029)),
+                              (se, (0.5323, 0.0, 1.206, 0.3))):
+        m = np.broadcast_to(m, (n, n, 1))
+        pr[0][m], pr[1][m], pr[2][m], pr[4][m] = rho, u, v, p
+    worst = _run_and_compare(s, pr, steps=2, tol_prims=1e-12)
+    print(f"\n2-D Riemann 1024^2, 2 steps: worst rel Linf {worst:.2e}")
