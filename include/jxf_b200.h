@@ -262,6 +262,26 @@ int jxf_pack_face_ext(jxf_handle h, int face, int ext_mask, const double* prims,
 int jxf_unpack_face_ext(jxf_handle h, int face, int ext_mask, const double* slab, double* prims, double* cons,
                         void* stream);
 
+/* The same for the `layers` (1 .. nh) cell layers next to the face only.  The convective stencils read 3 cells
+ * beyond a face (ref: spatial_reconstruction.py:21-41 with the WENO5 6-cell window), the reference ships all nh
+ * (halos/inner/material.py:74-88): exchanging 3 between RK stages moves 40 % less data; the layers farther out keep
+ * their previous values until an nh-layer exchange completes them (BlockRuntime.complete_halos). */
+int64_t jxf_face_slab_elems_n(jxf_handle h, int face, int ext_mask, int layers);
+int jxf_pack_face_n(jxf_handle h, int face, int ext_mask, int layers, const double* prims, double* slab, void* stream);
+int jxf_unpack_face_n(jxf_handle h, int face, int ext_mask, int layers, const double* slab, double* prims, double* cons,
+                      void* stream);
+
+/* One RK stage on THREE full-size buffers: `prims` is updated IN PLACE (no ping-pong buffer) and the rhs accumulator is
+ * two slabs of `slab_planes` x planes (jxf_rhs_slab_elems doubles each, stored back to back in `rhs_slabs`).  The block
+ * is processed slab by slab with the x sweep running one slab ahead (see the definition).  3-D blocks, convective flux
+ * only.  Same results as jxf_stage (same kernels and arithmetic; the launch plan differs).  cons_out may alias cons_in.
+ * Footprint at 1024^3: 3 x 44.2 GB + 2 x 2.7 GB against 221 GB for jxf_stage's plan.
+ * ref: time_integration/RK3.py:27-62, solvers/space_solver.py:266-314. */
+int64_t jxf_rhs_slab_elems(jxf_handle h, int slab_planes);
+int jxf_stage_inplace(jxf_handle h, int stage, double* prims, const double* cons_in, const double* cons_n,
+                      double* cons_out, double* rhs_slabs, int slab_planes, const double* dt_dev, double* red_dev,
+                      int reduce, int fill_halo, void* stream);
+
 /* Launch accounting and optional per-kernel timing (bench / roofline evidence).
  * Kinds: 0..2 = sweep along axis 0..2 writing rhs; 3..5 = sweep along axis 0..2 with the fused
  * RK-stage epilogue; 6 = halo fill; 7 = other (transforms, reductions, pack/unpack); 8 = dissipative

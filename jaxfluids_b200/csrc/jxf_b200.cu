@@ -268,6 +268,7 @@ struct FaceArgs {
   double gamma;
   int face;
   int unpack;
+  int layers;             // layers exchanged (<= nh): the ones next to the face
   int lo1, n1, lo2, n2;   // transverse ranges in BUFFER coordinates: [lo, lo + n) along the two transverse axes
 };
 
@@ -279,7 +280,8 @@ __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const Face
   const int t1 = (ax == 0) ? 1 : 0;
   const int t2 = (ax == 2) ? 1 : 2;
   const int n1 = a.n1, n2 = a.n2;
-  const long long total = (long long)g.nh * n1 * n2;
+  const int nl = a.layers;
+  const long long total = (long long)nl * n1 * n2;
   const int nh = g.nh, ext = g.ext[ax];
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
        q += (long long)gridDim.x * blockDim.x) {
@@ -288,8 +290,8 @@ __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const Face
     // exchange run this kernel, so the order is private to it)
     int i1, i2, l;
     if (g.st[ax] == 1) {
-      l = (int)(q % nh);
-      const long long q1 = q / nh;
+      l = (int)(q % nl);
+      const long long q1 = q / nl;
       i2 = (int)(q1 % n2);
       i1 = (int)(q1 / n2);
     } else {
@@ -300,12 +302,12 @@ __global__ void __launch_bounds__(128) face_slab_kernel(const Geom g, const Face
     }
     const long long tr = (long long)(i1 + a.lo1) * g.st[t1] + (long long)(i2 + a.lo2) * g.st[t2];
     if (!a.unpack) {
-      const int src = hi ? (ext - 2 * nh + l) : (nh + l);   // interior layers adjacent to the face
+      const int src = hi ? (ext - nh - nl + l) : (nh + l);  // the nl interior layers adjacent to the face
       const long long is = tr + (long long)src * g.st[ax];
 #pragma unroll
       for (int v = 0; v < 5; ++v) a.slab[q + v * total] = a.prims[is + v * g.vst];
     } else {
-      const int dst = hi ? (ext - nh + l) : l;
+      const int dst = hi ? (ext - nh + l) : (nh - nl + l);  // the nl halo layers adjacent to the face
       const long long id = tr + (long long)dst * g.st[ax];
       double p[5], c[5];
 #pragma unroll
@@ -1052,6 +1054,108 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
   return JXF_OK;
 }
 
+// ---------------------------------------------------------------------------
+// In-place stage on THREE full-size buffers (prims, U, U^n) + two slab-sized rhs accumulators: the memory plan for
+// blocks whose five-buffer plan does not fit the device (1024^3 on one B200: 3 x 44.2 GB + 2 x 2.7 GB).
+//
+// The block is cut into slabs of `slab_planes` x planes.  The only reader of a slab's OLD primitives from outside
+// the slab is the x sweep of its two neighbours, so the x sweep runs ONE SLAB AHEAD of the y sweep / z sweep +
+// epilogue, which then update the slab's primitives and conservatives in place:
+//     X(0), X(1), [Y(0), Z+epi(0)], X(2), [Y(1), Z+epi(1)], ...        (stream order)
+// Inside the z sweep the rows kernel waits for the next staged window before it stores (sweep_rows, a.inplace).
+// Fused halo images are written into the same buffers; the two whose OLD halo values are still needed later in the
+// stage -- PERIODIC east (read by the x sweep of the last slab) and PERIODIC top (read by the last window of the
+// same row) -- are deferred to one halo_fill launch after the last slab.  Same arithmetic as jxf_stage.
+// Reference semantics kept: RK3.py:27-62, space_solver.py:266-314 (rhs = ((0 + x) + y) + z per cell).
+// ---------------------------------------------------------------------------
+extern "C" int64_t jxf_rhs_slab_elems(jxf_handle h, int slab_planes) {
+  if (!h || slab_planes < 1) return -1;
+  return 5LL * std::min(slab_planes, h->g.n[0]) * h->g.n[1] * h->g.n[2];
+}
+
+extern "C" int jxf_stage_inplace(jxf_handle h, int stage, double* prims, const double* cons_in, const double* cons_n,
+                                 double* cons_out, double* rhs_slabs, int slab_planes, const double* dt_dev,
+                                 double* red_dev, int reduce, int fill_halo, void* stream) {
+  if (!h || !prims || !cons_in || !cons_out || !rhs_slabs || !dt_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage_inplace: null argument");
+  if (stage < 0 || stage >= h->stages) return fail(JXF_ERR_BAD_ARG, "jxf_stage_inplace: stage %d out of range", stage);
+  if (stage > 0 && !cons_n) return fail(JXF_ERR_BAD_ARG, "jxf_stage_inplace: cons_n required for stage > 0");
+  if (reduce && !red_dev) return fail(JXF_ERR_BAD_ARG, "jxf_stage_inplace: red_dev required when reduce != 0");
+  if (h->n_active != 3 || h->order[2] != 2)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_stage_inplace: 3-D blocks with the reference sweep order only");
+  if (dissipative(h) || h->cfg.no_convective_flux)
+    return fail(JXF_ERR_UNSUPPORTED, "jxf_stage_inplace: convective flux only");
+  const Geom& g = h->g;
+  const int nx = g.n[0];
+  const int P = std::min(slab_planes, nx);
+  if (P < 2 * 3 && P < nx) return fail(JXF_ERR_BAD_ARG, "jxf_stage_inplace: slab_planes=%d too thin", slab_planes);
+  const int nslabs = (nx + P - 1) / P;
+  const long long slab_rvst = (long long)P * g.n[1] * g.n[2];
+  double* slab_buf[2] = {rhs_slabs, rhs_slabs + 5 * slab_rvst};
+  cudaStream_t st = (cudaStream_t)stream;
+
+  auto sweep_x = [&](int sidx) -> int {
+    const int x0 = sidx * P, x1 = std::min(nx, x0 + P);
+    // the kernel indexes the rhs with the GLOBAL x index: shift the slab accumulator's base accordingly
+    SweepArgs a = base_args(h, 0, prims, slab_buf[sidx & 1] - (long long)x0 * g.rst[0]);
+    a.fl.dt = dt_dev;
+    a.accumulate = 0;
+    a.range_lo = x0;
+    a.range_hi = x1;
+    a.rvst_slab = slab_rvst;
+    return dispatch_axis(h, 0, a, 0, st);
+  };
+  int rc = sweep_x(0);
+  if (rc) return rc;
+  bool defer[6] = {false, false, false, false, false, false};
+  for (int sidx = 0; sidx < nslabs; ++sidx) {
+    if (sidx + 1 < nslabs && (rc = sweep_x(sidx + 1))) return rc;
+    const int x0 = sidx * P, x1 = std::min(nx, x0 + P);
+    {   // y sweep of the slab
+      SweepArgs a = base_args(h, 1, prims, slab_buf[sidx & 1]);
+      a.fl.dt = dt_dev;
+      a.accumulate = 1;
+      a.sub_lo = x0; a.sub_n = x1 - x0; a.rvst_slab = slab_rvst;
+      if ((rc = dispatch_axis(h, 1, a, 0, st))) return rc;
+    }
+    {   // z sweep + epilogue of the slab, in place
+      SweepArgs a = base_args(h, 2, prims, slab_buf[sidx & 1]);
+      a.fl.dt = dt_dev;
+      a.sub_lo = x0; a.sub_n = x1 - x0; a.rvst_slab = slab_rvst;
+      a.cons_in = cons_in; a.cons_n = cons_n; a.cons_out = cons_out; a.prims_out = prims;
+      a.dt = dt_dev; a.red = red_dev;
+      a.blend = stage > 0; a.ca = h->blend[stage][0]; a.cb = h->blend[stage][1]; a.dt_mult = h->dt_mult[stage];
+      a.has_prev = 1; a.reduce = reduce ? 1 : 0; a.fuse_halo = fill_halo ? 1 : 0; a.nh = h->cfg.nh; a.inplace = 1;
+      for (int f = 0; f < 6; ++f) {
+        a.bc[f] = h->cfg.bc[f];
+        for (int q = 0; q < 3; ++q) a.wall[f][q] = h->cfg.wall_velocity[f][q];
+        for (int q = 0; q < 5; ++q) a.dirichlet[f][q] = h->cfg.dirichlet[f][q];
+      }
+      // east (face 0) / top (face 4) PERIODIC images overwrite halos the stage still reads: deferred
+      for (int f : {0, 4})
+        if (a.bc[f] == JXF_BC_PERIODIC) { a.bc[f] = JXF_BC_NEIGHBOR; defer[f] = true; }
+      a.volume_force = h->cfg.volume_force;
+      for (int q = 0; q < 3; ++q) a.gravity[q] = h->cfg.gravity[q];
+      if ((rc = dispatch_axis(h, 2, a, 1, st))) return rc;
+    }
+  }
+  if (fill_halo && (defer[0] || defer[4])) {
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prims = prims; a.cons = cons_out; a.gamma = h->cfg.gamma;
+    long long maxcells = 0;
+    for (int f = 0; f < 6; ++f) {
+      a.bc[f] = defer[f] ? JXF_BC_PERIODIC : JXF_BC_INACTIVE;
+      const int ax = f >> 1, t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
+      if (defer[f]) maxcells = std::max(maxcells, (long long)g.nh * g.n[t1] * g.n[t2]);
+    }
+    const int bx = (int)std::min<long long>((maxcells + 127) / 128, 148 * 16);
+    ProfScope prof(h, JXF_PROFILE_HALO, st);
+    halo_fill_kernel<<<dim3(bx, 6), 128, 0, st>>>(h->g, a);
+    if ((rc = check_launch("halo_fill (deferred)"))) return rc;
+  }
+  return JXF_OK;
+}
+
 extern "C" int jxf_step_fused(jxf_handle h, double* prims_a, double* prims_b, double* cons_a, double* cons_b,
                               double* rhs_scratch, double* dt_dev, double* time_dev, double* red_dev,
                               double* info_dev, int fill_halo, void* stream) {
@@ -1150,17 +1254,24 @@ static void slab_ranges(const jxf_solver* h, int face, int ext_mask, int& lo1, i
   }
 }
 
-extern "C" int64_t jxf_face_slab_elems_ext(jxf_handle h, int face, int ext_mask) {
-  if (!h || face < 0 || face > 5) return -1;
+extern "C" int64_t jxf_face_slab_elems_n(jxf_handle h, int face, int ext_mask, int layers) {
+  if (!h || face < 0 || face > 5 || layers < 1 || layers > h->g.nh) return -1;
   int lo1, n1, lo2, n2;
   slab_ranges(h, face, ext_mask, lo1, n1, lo2, n2);
-  return 5LL * h->g.nh * n1 * n2;
+  return 5LL * layers * n1 * n2;
+}
+
+extern "C" int64_t jxf_face_slab_elems_ext(jxf_handle h, int face, int ext_mask) {
+  return h ? jxf_face_slab_elems_n(h, face, ext_mask, h->g.nh) : -1;
 }
 
 extern "C" int64_t jxf_face_slab_elems(jxf_handle h, int face) { return jxf_face_slab_elems_ext(h, face, 0); }
 
-static int face_slab(jxf_handle h, int face, int ext_mask, double* prims, double* cons, double* slab, int unpack, void* stream) {
+static int face_slab(jxf_handle h, int face, int ext_mask, double* prims, double* cons, double* slab, int unpack, void* stream,
+                     int layers = 0) {
   if (!h || !prims || !slab || (unpack && !cons)) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: null argument");
+  if (layers == 0) layers = h->g.nh;
+  if (layers < 1 || layers > h->g.nh) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: layers=%d outside [1, halo_cells]", layers);
   if (face < 0 || face > 5 || h->g.n[face >> 1] <= 1) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: face %d not active", face);
   if (ext_mask < 0 || ext_mask > 15) return fail(JXF_ERR_BAD_ARG, "jxf_(un)pack_face: ext_mask %d", ext_mask);
   FaceArgs a;
@@ -1170,8 +1281,9 @@ static int face_slab(jxf_handle h, int face, int ext_mask, double* prims, double
   a.gamma = h->cfg.gamma;
   a.face = face;
   a.unpack = unpack;
+  a.layers = layers;
   slab_ranges(h, face, ext_mask, a.lo1, a.n1, a.lo2, a.n2);
-  const long long total = (long long)h->g.nh * a.n1 * a.n2;
+  const long long total = (long long)layers * a.n1 * a.n2;
   const int bx = (int)std::min<long long>((total + 127) / 128, 148 * 16);
   ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
   face_slab_kernel<<<bx, 128, 0, (cudaStream_t)stream>>>(h->g, a);
@@ -1190,6 +1302,14 @@ extern "C" int jxf_pack_face_ext(jxf_handle h, int face, int ext_mask, const dou
 extern "C" int jxf_unpack_face_ext(jxf_handle h, int face, int ext_mask, const double* slab, double* prims, double* cons,
                                    void* stream) {
   return face_slab(h, face, ext_mask, prims, cons, const_cast<double*>(slab), 1, stream);
+}
+
+extern "C" int jxf_pack_face_n(jxf_handle h, int face, int ext_mask, int layers, const double* prims, double* slab, void* stream) {
+  return face_slab(h, face, ext_mask, const_cast<double*>(prims), nullptr, slab, 0, stream, layers);
+}
+extern "C" int jxf_unpack_face_n(jxf_handle h, int face, int ext_mask, int layers, const double* slab, double* prims,
+                                 double* cons, void* stream) {
+  return face_slab(h, face, ext_mask, prims, cons, const_cast<double*>(slab), 1, stream, layers);
 }
 
 extern "C" int jxf_debug_face_flux(int axis, int recon, int riemann, const double* windows, int64_t n, double gamma,

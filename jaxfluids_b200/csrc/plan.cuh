@@ -97,7 +97,20 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   sg.sA = g.st[A];
   sg.rA = g.rst[A];
   sg.vst = g.vst;
-  sg.rvst = g.rvst;
+  sg.rvst = a.rvst_slab > 0 ? a.rvst_slab : g.rvst;
+  sg.i1_base = 0;
+  // slab launches: a y / z sweep over the x planes [sub_lo, sub_lo + sub_n) only (x is role 1 of both in 3-D); the
+  // field pointers move to the slab's first plane, the rhs pointer is the slab-sized accumulator as passed
+  const bool slab = (A != 0) && a.sub_n > 0;
+  if (slab) {
+    const long long off = (long long)a.sub_lo * g.st[0];
+    a.prims += off;
+    if (a.cons_in) a.cons_in += off;
+    if (a.cons_n) a.cons_n += off;
+    if (a.cons_out) a.cons_out += off;
+    if (a.prims_out) a.prims_out += off;
+    sg.i1_base = a.sub_lo;
+  }
   const int T1 = (A == 0) ? 1 : 0;       // slower transverse axis
   const int T2 = (A == 2) ? 1 : 2;       // faster transverse axis
   if (A != s->lane_axis) {
@@ -106,6 +119,11 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     const int O = 3 - A - C;
     sg.ax1 = O; sg.n1 = g.n[O]; sg.s1 = g.st[O]; sg.r1 = g.rst[O];
     sg.ax2 = C; sg.n2 = g.n[C]; sg.s2 = g.st[C]; sg.r2 = g.rst[C];
+    sg.n1_full = sg.n1;
+    if (slab) {
+      if (O != 0) return fail(JXF_ERR_UNSUPPORTED, "slab launch: x is not the slow transverse axis of this sweep");
+      sg.n1 = a.sub_n;
+    }
     const long long plane = (long long)sg.n1 * sg.n2;
     const int bx = (int)((plane + 127) / 128);
     const int resident = s->num_sms * (s->no_march ? JXF_MIN_BLOCKS : JXF_MARCH_BLOCKS);
@@ -139,6 +157,11 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   } else {
     sg.ax1 = T1; sg.n1 = g.n[T1]; sg.s1 = g.st[T1]; sg.r1 = g.rst[T1];
     sg.ax2 = T2; sg.n2 = g.n[T2]; sg.s2 = g.st[T2]; sg.r2 = g.rst[T2];
+    sg.n1_full = sg.n1;
+    if (slab) {
+      if (T1 != 0) return fail(JXF_ERR_UNSUPPORTED, "slab launch: x is not the slow transverse axis of this sweep");
+      sg.n1 = a.sub_n;
+    }
     set_role_bcs(sg, a);
     const long long rows = (long long)sg.n1 * sg.n2;
     const int nf = g.n[A] + 1;
@@ -157,12 +180,12 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       ra.group_rows = G;
       ra.shift = ((g.off[A] - 2) & 1) ? 3 : 2;
       ra.cA_off = g.off[A];
-      ra.c1_off = g.off[T1];
+      ra.c1_off = g.off[T1] + (slab ? a.sub_lo : 0);
       ra.c2_off = g.off[T2];
       ra.tma_dim1_is_role = 2;
       const long long groups = (rows + G - 1) / G;
       const long long blocks = std::min<long long>((groups + 3) / 4, 1LL << 30);
-      const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0);
+      const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0 - (slab ? (long long)a.sub_lo * g.st[0] : 0));
       ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
       if (map) {
         sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map);
@@ -174,6 +197,8 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       return check_launch("sweep_rows");
     }
 #endif
+    if (EPI && a.inplace)
+      return fail(JXF_ERR_UNSUPPORTED, "in-place stage: the last sweep must run in the rows kernel (grid too small)");
     const long long target_warps = 4LL * resident * 4;   // ~4 waves of warps
     long long span;
     if (rows >= target_warps) {

@@ -53,6 +53,11 @@ struct SweepArgs {
   double gravity[3];
   double wall[6][3];       // wall velocity (u, v, w) per JXF_BC_WALL face
   double dirichlet[6][5];  // prescribed primitives per JXF_BC_DIRICHLET face
+  // slab launches (jxf_stage_inplace): a sweep along y or z restricted to the x planes [sub_lo, sub_lo + sub_n);
+  // rvst_slab: variable stride of the slab-sized rhs accumulator (0: the full-size one)
+  int sub_lo, sub_n;
+  long long rvst_slab;
+  int inplace;             // EPI: prims_out aliases prims (rows kernel: the next window must have landed before a store)
 };
 
 // ---------------------------------------------------------------------------
@@ -68,6 +73,7 @@ struct SweepGeom {
   long long sA, s1, s2;      // strides in the halo'd buffers
   long long rA, r1, r2;      // strides in the interior-only rhs buffer
   long long vst, rvst;       // variable strides
+  int i1_base, n1_full;      // slab launches (jxf_stage_inplace): role 1 covers cells [i1_base, i1_base + n1) of n1_full
 };
 
 #ifndef JXF_MIN_BLOCKS
@@ -261,9 +267,10 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
     }
     if (E::halo(a)) {
       // boundary-adjacent cells only (a thin shell); warp-divergent by construction
-      const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (i1 < a.nh) | (i1 >= g.n1 - a.nh) | (i2 < a.nh) |
+      const int j1 = i1 + g.i1_base;      // global index along role 1 (slab launches)
+      const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (j1 < a.nh) | (j1 >= g.n1_full - a.nh) | (i2 < a.nh) |
                         (i2 >= g.n2 - a.nh);
-      if (near) halo_images_cell(g, a, hidx, p[0], p[1], p[2], p[3], p[4], iA, i1, i2);
+      if (near) halo_images_cell(g, a, hidx, p[0], p[1], p[2], p[3], p[4], iA, j1, i2);
     }
   }
 }
@@ -274,7 +281,7 @@ static __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const S
   const double p[5] = {p0, p1, p2, p3, p4};
   halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1],
                    a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1]);
-  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
+  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1_full, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
                    a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1]);
   halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1],
                    a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1]);
@@ -694,6 +701,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
     const int i1_0 = (int)(row0 / g.n2);
     const int i2_0 = (int)(row0 - (long long)i1_0 * g.n2);
     int b = 0;
+    bool next_landed = false;
     issue(0, 0, i1_0, i2_0, true);
     // ---- the row-opening faces f = 0 of this group, one row per lane (direct strided loads; the flux
     // code is called out of line here so the hot loop below holds the only inlined copy) -----------
@@ -728,14 +736,16 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
         const long long ridx = col_r + (long long)(f - 1) * g.rA;
         CellIn<EPI> in;
         if (act) load_cell_in<EPI>(g, a, hidx, ridx, in);
-        // wait for this iteration's window
+        // wait for this iteration's window (in-place stages already waited for it before the previous stores)
         const double* const wb = reinterpret_cast<const double*>(win0 + b * kWinStride);
-        if (USE_TMA) {
-          mbar_wait(bar0 + b, (phase_bits >> b) & 1u);
-          phase_bits ^= (1u << b);
-        } else {
-          cp_async_wait<1>();
-          __syncwarp();
+        if (!next_landed) {
+          if (USE_TMA) {
+            mbar_wait(bar0 + b, (phase_bits >> b) & 1u);
+            phase_bits ^= (1u << b);
+          } else {
+            cp_async_wait<1>();
+            __syncwarp();
+          }
         }
         double F[5];
         {
@@ -755,6 +765,20 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
           rr[v] = ((lane == 0) ? carry[v] : rot) - F[v];
           carry[v] = rot;                                                // meaningful on lane 0: the next carry
         }
+        if (EPI && a.inplace) {
+          // prims_out aliases prims: the window staged for the next iteration overlaps the cells stored below (and
+          // the next row's is read from global while this one stores) -- it must have landed first
+          if (USE_TMA) {
+            if (!last_it || more_rows) {
+              mbar_wait(bar0 + (b ^ 1), (phase_bits >> (b ^ 1)) & 1u);
+              phase_bits ^= (1u << (b ^ 1));
+            }
+          } else {
+            cp_async_wait<0>();
+            __syncwarp();
+          }
+          next_landed = true;
+        }
         if (act) finalize_cell<EPI>(g, a, hidx, ridx, in, rr, step, red, f - 1, i1, i2);
         __syncwarp();          // all lanes are done with win[b] before it is refilled two iterations later
         b ^= 1;
@@ -762,6 +786,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
       i1 = i1x;
       i2 = i2x;
     }
+    next_landed = false;
     if (!USE_TMA) cp_async_wait<0>();
   }
   if (EPI) {

@@ -211,6 +211,19 @@ class BlockSolver:
                                       _ptr(cons_n), _ptr(cons_out), _ptr(rhs), _ptr(dt_dev), _ptr(red_dev),
                                       int(bool(reduce)), int(bool(fill_halo)), _stream()))
 
+    def rhs_slab_elems(self, slab_planes: int) -> int:
+        return int(self.lib.jxf_rhs_slab_elems(self._h, int(slab_planes)))
+
+    def new_rhs_slabs(self, slab_planes: int) -> torch.Tensor:
+        """Two slab-sized rhs accumulators, back to back (jxf_stage_inplace)."""
+        return torch.empty(2 * self.rhs_slab_elems(slab_planes), dtype=torch.float64, device=self.device)
+
+    def stage_inplace(self, stage, prims, cons_in, cons_n, cons_out, rhs_slabs, slab_planes, dt_dev, red_dev=None,
+                      reduce=False, fill_halo=True):
+        _lib.check(self.lib.jxf_stage_inplace(self._h, int(stage), _ptr(prims), _ptr(cons_in), _ptr(cons_n), _ptr(cons_out),
+                                              _ptr(rhs_slabs), int(slab_planes), _ptr(dt_dev), _ptr(red_dev),
+                                              int(bool(reduce)), int(bool(fill_halo)), _stream()))
+
     def sweep_range(self, axis: int, lo: int, hi: int, prims, rhs, accumulate: bool):
         _lib.check(self.lib.jxf_sweep_range(self._h, int(axis), int(lo), int(hi), _ptr(prims), _ptr(rhs),
                                             int(bool(accumulate)), _stream()))
@@ -283,15 +296,16 @@ class BlockSolver:
         _lib.check(self.lib.jxf_profile_read(self._h, ms, timed, launches, int(bool(reset))))
         return {k: (ms[i], timed[i], launches[i]) for i, k in enumerate(self.PROFILE_KINDS)}
 
-    def face_slab_elems(self, face: int, ext_mask: int = 0) -> int:
-        return int(self.lib.jxf_face_slab_elems_ext(self._h, int(face), int(ext_mask)))
+    def face_slab_elems(self, face: int, ext_mask: int = 0, layers: Optional[int] = None) -> int:
+        return int(self.lib.jxf_face_slab_elems_n(self._h, int(face), int(ext_mask), int(layers or self.cfg.nh)))
 
-    def pack_face(self, face: int, prims, slab, ext_mask: int = 0):
-        _lib.check(self.lib.jxf_pack_face_ext(self._h, int(face), int(ext_mask), _ptr(prims), _ptr(slab), _stream()))
+    def pack_face(self, face: int, prims, slab, ext_mask: int = 0, layers: Optional[int] = None):
+        _lib.check(self.lib.jxf_pack_face_n(self._h, int(face), int(ext_mask), int(layers or self.cfg.nh), _ptr(prims),
+                                            _ptr(slab), _stream()))
 
-    def unpack_face(self, face: int, slab, prims, cons, ext_mask: int = 0):
-        _lib.check(self.lib.jxf_unpack_face_ext(self._h, int(face), int(ext_mask), _ptr(slab), _ptr(prims), _ptr(cons),
-                                                _stream()))
+    def unpack_face(self, face: int, slab, prims, cons, ext_mask: int = 0, layers: Optional[int] = None):
+        _lib.check(self.lib.jxf_unpack_face_n(self._h, int(face), int(ext_mask), int(layers or self.cfg.nh), _ptr(slab),
+                                              _ptr(prims), _ptr(cons), _stream()))
 
 
 class BlockState:

@@ -85,7 +85,13 @@ class InitializationManager:
                         ("user_restart_file_path", user_restart_file_path)):
             if v is not None:
                 raise NotImplementedError(f"{name} is not implemented on the B200 path")
-        if user_prime_init is not None:
+        if callable(user_prime_init):
+            # extension of the reference's array argument (material_fields_initializer.py:425-497) for grids whose
+            # GLOBAL array does not fit a host: fn(block_slices, out) fills `out`, the (5, bx, by, bz) interior VIEW of
+            # this rank's device state buffer, with the block's primitives (all five rows; inactive velocities as given)
+            sl = self.domain_information.block_slices(self.parallel.rank)
+            host = lambda out: user_prime_init(sl, out)      # noqa: E731
+        elif user_prime_init is not None:
             host = self._host_primitives_from_user(user_prime_init)
         else:
             host = self._host_primitives_from_ic()

@@ -104,10 +104,22 @@ class BlockRuntime:
             raise NotImplementedError("space-dependent DIRICHLET / WALL data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
                                       "are implemented for single-block runs on the B200 path")
         self.stages = s.stages
-        self.prims = [s.new_field(EPS), s.new_field(EPS)]       # helper_functions.py:21-60: eps fill
+        # Memory plan.  "pingpong" (default): 2 primitive + 2 conservative buffers + a full-size rhs accumulator.
+        # "inplace": ONE primitive buffer updated in place + 2 conservative buffers + two slab-sized rhs accumulators
+        # (jxf_stage_inplace) -- 3 full-size buffers instead of 5, for blocks the default plan cannot hold (1024^3 on one
+        # GPU).  JXF_MEMORY_PLAN=pingpong|inplace|auto; auto picks in place when the default plan exceeds the free memory.
+        self.memory_plan = self._pick_memory_plan()
+        self.slab_planes = int(os.environ.get("JXF_SLAB_PLANES", "64"))
+        if self.memory_plan == "inplace":
+            p = s.new_field(EPS)
+            self.prims = [p, p]                                 # one buffer: the stage updates it in place
+            self.rhs = None
+            self.rhs_slabs = s.new_rhs_slabs(self.slab_planes)
+        else:
+            self.prims = [s.new_field(EPS), s.new_field(EPS)]   # helper_functions.py:21-60: eps fill
+            self.rhs = s.new_rhs() if (len(s.active) > 1 or self.cfg.is_dissipative) else None
         self.cons = [s.new_field(EPS), s.new_field(EPS)]        # cons[0] = U / U^n, cons[1] = stage scratch
         self.cur = 0
-        self.rhs = s.new_rhs() if (len(s.active) > 1 or self.cfg.is_dissipative) else None
         self.red = s.new_red()
         self.info = s.new_scalars(3)
         self.time = s.new_scalars(1, 0.0)
@@ -121,6 +133,15 @@ class BlockRuntime:
         self.send = {f: torch.empty(s.face_slab_elems(FACE_ID[f], self.ext_mask[f]), dtype=torch.float64,
                                     device=self.device) for f in self.neighbors}
         self.recv = {f: torch.empty_like(self.send[f]) for f in self.neighbors}
+        # Layers shipped per shared face between RK stages.  The convective stencils read REACH = 3 cells beyond a face,
+        # the reference ships all nh (halos/inner/material.py:74-88).  stage_layers < nh leaves the outer halo layers
+        # stale until complete_halos() -- which every API call that hands buffers to the user runs -- so what the user
+        # sees is bit-identical to a full exchange.  The dissipative stencils reach 2 + 2 cells: full exchange there.
+        self.stage_layers = self.cfg.nh
+        if not self.cfg.is_dissipative and os.environ.get("JXF_EXCHANGE_LAYERS", "") != "full":
+            self.stage_layers = min(self.cfg.nh, int(os.environ.get("JXF_EXCHANGE_LAYERS", self.REACH)))
+        self._halos_partial = False
+        self._comm_prof = None                    # comm_profile(True): lists of (name, start event, stop event)
         # inter-block exchange runs on its own stream and overlaps the first sweep of the next stage
         self.overlap = (bool(self.neighbors) and os.environ.get("JXF_OVERLAP", "1") != "0"
                         and not self.cfg.is_dissipative)
@@ -133,6 +154,21 @@ class BlockRuntime:
         self._first_axis = first
         self._first_strided = len(s.active) > 1   # the contiguous (last active) axis takes no partial ranges
         self._first_split = any(f in self.neighbors for f in (FACES[2 * first], FACES[2 * first + 1]))
+
+    def _pick_memory_plan(self) -> str:
+        want = os.environ.get("JXF_MEMORY_PLAN", "auto").lower()
+        can = (len(self.solver.active) == 3 and not self.cfg.is_dissipative and self.cfg.is_convective_flux
+               and not self._host_halo)
+        if want == "inplace":
+            if not can:
+                raise NotImplementedError("JXF_MEMORY_PLAN=inplace: 3-D convective-only blocks without host-applied boundaries")
+            return "inplace"
+        if want == "pingpong" or not can:
+            return "pingpong"
+        field = int(np.prod(self.cfg.shape)) * 8
+        need = 4 * field + int(np.prod(self.cfg.rhs_shape)) * 8
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return "inplace" if need > 0.92 * free else "pingpong"
 
     # -- boundaries the host applies on top of the halo kernels -------------------
     # DIRICHLET with space-dependent data, NEUMANN, SIMPLE_INFLOW, SIMPLE_OUTFLOW: the halo kernels fill these faces with
@@ -284,7 +320,12 @@ class BlockRuntime:
         p = self.prims[self.cur]
         p.fill_(EPS)
         sl = (slice(None),) + self.cfg.interior
-        p[sl] = torch.as_tensor(np.ascontiguousarray(host_interior), dtype=torch.float64).to(self.device)
+        if callable(host_interior):          # a filler of the interior view (InitializationManager: callable user_prime_init)
+            host_interior(p[sl])
+        elif torch.is_tensor(host_interior):
+            p[sl] = host_interior.to(device=self.device, dtype=torch.float64)
+        else:
+            p[sl] = torch.as_tensor(np.ascontiguousarray(host_interior), dtype=torch.float64).to(self.device)
         self.solver.cons_from_prims(p, self.cons[0])
         self.halo_update(p, self.cons[0])
         return p, self.cons[0]
@@ -332,19 +373,63 @@ class BlockRuntime:
             for f in faces:
                 s.unpack_face(FACE_ID[f], self.recv[f], prims, cons, self.ext_mask[f])
 
-    def halo_update(self, prims: torch.Tensor, cons: torch.Tensor, local_done: bool = False):
-        """halo_manager.py:146-234: inter-block faces (inner/material.py:30-93) then outer BCs."""
+    # -- communication timing (bench `comm` object) ------------------------------
+    def comm_profile(self, on: bool = True):
+        """Record CUDA events around pack / NCCL / unpack (communication stream) and around the compute stream's wait
+        for the exchange; read with comm_profile_read()."""
+        self._comm_prof = [] if on else None
+
+    def _tick(self, name):
+        """Context manager timing a span on the CURRENT stream when profiling is on."""
+        import contextlib
+        if self._comm_prof is None:
+            return contextlib.nullcontext()
+        rt = self
+
+        class Span:
+            def __enter__(self_):
+                self_.a = torch.cuda.Event(enable_timing=True)
+                self_.b = torch.cuda.Event(enable_timing=True)
+                self_.a.record()
+
+            def __exit__(self_, *exc):
+                self_.b.record()
+                rt._comm_prof.append((name, self_.a, self_.b))
+        return Span()
+
+    def comm_profile_read(self, reset: bool = True):
+        """-> {name: total ms} over the spans recorded so far (synchronises)."""
+        out = {}
+        if self._comm_prof:
+            torch.cuda.synchronize()
+            for name, a, b in self._comm_prof:
+                out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+            if reset:
+                self._comm_prof = []
+        return out
+
+    def halo_update(self, prims: torch.Tensor, cons: torch.Tensor, local_done: bool = False, layers: Optional[int] = None):
+        """halo_manager.py:146-234: inter-block faces (inner/material.py:30-93) then outer BCs.  `layers`: cell layers
+        shipped per shared face (default: all nh)."""
         s = self.solver
         if self.neighbors and self.cfg.is_dissipative:
             return self._halo_update_with_edges(prims, cons, local_done)
         if self.neighbors:
-            for f in self.neighbors:
-                s.pack_face(FACE_ID[f], prims, self.send[f])
-            reqs = self.parallel.exchange(self.neighbors, self.send, self.recv)
-            for r in reqs:
-                r.wait()
-            for f in self.neighbors:
-                s.unpack_face(FACE_ID[f], self.recv[f], prims, cons)
+            nl = int(layers or self.cfg.nh)
+            full = nl == self.cfg.nh
+            cut = {f: (self.send[f] if full else self.send[f][:s.face_slab_elems(FACE_ID[f], 0, nl)]) for f in self.neighbors}
+            got = {f: (self.recv[f] if full else self.recv[f][:cut[f].numel()]) for f in self.neighbors}
+            with self._tick("pack"):
+                for f in self.neighbors:
+                    s.pack_face(FACE_ID[f], prims, cut[f], 0, nl)
+            with self._tick("nccl"):
+                reqs = self.parallel.exchange(self.neighbors, cut, got)
+                for r in reqs:
+                    r.wait()
+            with self._tick("unpack"):
+                for f in self.neighbors:
+                    s.unpack_face(FACE_ID[f], got[f], prims, cons, 0, nl)
+            self._halos_partial = not full
         if not local_done:
             s.halo_fill(prims, cons)
             if self.host_boundaries:
@@ -375,7 +460,7 @@ class BlockRuntime:
         ready.record(compute)
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            self.halo_update(prims, cons, local_done=True)
+            self.halo_update(prims, cons, local_done=True, layers=self.stage_layers)
             done = torch.cuda.Event()
             done.record(self.comm_stream)
         self._pending = done
@@ -383,8 +468,17 @@ class BlockRuntime:
     def finish_pending(self):
         """Make the current stream wait for an in-flight halo exchange (before anyone reads halos)."""
         if self._pending is not None:
-            torch.cuda.current_stream().wait_event(self._pending)
+            with self._tick("wait"):
+                torch.cuda.current_stream().wait_event(self._pending)
             self._pending = None
+
+    def complete_halos(self):
+        """Bring every halo layer of the current state up to date (after stages that shipped stage_layers < nh): one
+        full exchange.  Run by the API before buffers are handed to the user; the step loop itself never needs it."""
+        self.finish_pending()
+        if self._halos_partial and self.neighbors:
+            self.halo_update(self.prims[self.cur], self.cons[0], local_done=True)
+        self._halos_partial = False
 
     def stage(self, k: int, reduce: bool):
         """One RK stage on the current state (simulation_manager.py:770-1047).  With several blocks the
@@ -396,6 +490,14 @@ class BlockRuntime:
         p_in, p_out = self.prims[self.cur], self.prims[self.cur ^ 1]
         c_in = self.cons[0] if k == 0 else self.cons[1]
         c_out = self.cons[0] if last else self.cons[1]
+        if self.memory_plan == "inplace":
+            self.finish_pending()
+            s.stage_inplace(k, p_in, c_in, self.cons[0], c_out, self.rhs_slabs, self.slab_planes, self.dt, self.red,
+                            reduce=reduce, fill_halo=True)
+            if self.neighbors:          # the in-place stage overwrites what an overlapped sweep would read: no overlap
+                self.halo_update(p_out, c_out, local_done=True, layers=self.stage_layers)
+            self.cur ^= 1
+            return
         args = (p_in, p_out, c_in, self.cons[0], c_out, self.rhs, self.dt, self.red)
         if self._pending is not None and self.overlap and self._first_strided:
             ax, n, w = self._first_axis, self.cfg.cells[self._first_axis], self.REACH
@@ -421,7 +523,7 @@ class BlockRuntime:
             if self.overlap:
                 self._start_exchange(p_out, c_out)
             else:
-                self.halo_update(p_out, c_out, local_done=True)
+                self.halo_update(p_out, c_out, local_done=True, layers=self.stage_layers)
         self.cur ^= 1
 
     # -- CUDA graphs ------------------------------------------------------------
@@ -468,7 +570,7 @@ class BlockRuntime:
 
     def step(self):
         """One full time step, enqueue-only (no host sync)."""
-        if not self.parallel.is_parallel and not self._host_halo:
+        if not self.parallel.is_parallel and not self._host_halo and self.memory_plan != "inplace":
             if getattr(self, "_graphs", None) is not None:
                 return self._graph_step()
             return self._eager_step()
@@ -477,8 +579,10 @@ class BlockRuntime:
         self._allreduce_red()
         self.solver.finish_step(self.red, self.dt, self.time, self.info)
 
-    def read_step_scalars(self):
+    def read_step_scalars(self, complete_halos: bool = False):
         """(time, dt_next, max_speed_sum, min_rho, min_p) -- ONE device->host sync."""
+        if complete_halos:
+            self.complete_halos()
         self.finish_pending()
         v = torch.cat([self.time, self.dt, self.info]).cpu().numpy()
         return float(v[0]), float(v[1]), float(v[2]), float(v[3]), float(v[4])

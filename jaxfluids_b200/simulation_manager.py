@@ -220,7 +220,8 @@ class SimulationManager:
             t0 = _time.time()
             cfp = self.compute_control_flow_params(tcv, jxf_buffers.step_information)
             jxf_buffers, callback_dict = self._callback("before_step_start", jxf_buffers, callback_dict)
-            jxf_buffers, callback_dict_step = self.do_integration_step(jxf_buffers, cfp, ml_parameters, ml_callables)
+            jxf_buffers, callback_dict_step = self._do_integration_step(jxf_buffers, cfp, ml_parameters, ml_callables,
+                                                                        complete_halos=bool(self.callbacks))
             jxf_buffers, callback_dict = self._callback("after_step_end", jxf_buffers, callback_dict,
                                                         callback_dict_step=callback_dict_step)
             tcv = jxf_buffers.time_control_variables
@@ -231,6 +232,7 @@ class SimulationManager:
                 mean += (wall - mean) / n_timed
             self.wall_clock_times = WallClockTimes(wall, wall / cells, mean, mean / cells)
             self.logger.log_end_time_step(tcv, jxf_buffers.step_information, self.wall_clock_times)
+        self.runtime.complete_halos()
         jxf_buffers, callback_dict = self._callback("on_simulation_end", jxf_buffers, callback_dict)
         return jxf_buffers
 
@@ -240,10 +242,14 @@ class SimulationManager:
     # ------------------------------------------------------------------
     def do_integration_step(self, jxf_buffers: JaxFluidsBuffers, control_flow_params=None, ml_parameters=None,
                             ml_callables=None) -> Tuple[JaxFluidsBuffers, Dict]:
-        """simulation_manager.py:1178-1246 -> _do_integration_step :536-668."""
+        """simulation_manager.py:1178-1246 -> _do_integration_step :536-668.
+
+        The returned JaxFluidsBuffers hold VIEWS of the runtime's device buffers (no copy): the next step overwrites
+        them, where the reference returns fresh immutable arrays.  Clone what must outlive the next call."""
         return self._do_integration_step(jxf_buffers, control_flow_params, ml_parameters, ml_callables)
 
-    def _do_integration_step(self, jxf_buffers, control_flow_params=None, ml_parameters=None, ml_callables=None):
+    def _do_integration_step(self, jxf_buffers, control_flow_params=None, ml_parameters=None, ml_callables=None,
+                             complete_halos: bool = True):
         rt = self.runtime
         callback_dict: Dict = {}
         jxf_buffers, callback_dict = self._callback("on_step_start", jxf_buffers, callback_dict)
@@ -255,7 +261,9 @@ class SimulationManager:
             self._step_with_stage_hooks(tcv)
         else:
             rt.step()
-        t, dt_next, _, min_rho, min_p = rt.read_step_scalars()
+        # multi-block runs ship only the layers the stencils read between stages; complete the rest before the
+        # buffers go back to the caller (advance() defers this to the end of its loop when no callback looks)
+        t, dt_next, _, min_rho, min_p = rt.read_step_scalars(complete_halos=complete_halos)
         tcv = tcv._replace(physical_simulation_time=t, simulation_step=tcv.simulation_step + 1,
                            physical_timestep_size=dt_next)
         material_fields = MaterialFieldBuffers(rt.conservatives, rt.primitives, rt.temperature(rt.primitives))
@@ -298,7 +306,7 @@ class SimulationManager:
         for k in range(rt.stages):
             rt.stage(k, reduce=(k == rt.stages - 1))
         rt._allreduce_red()
-        rt.finish_pending()
+        rt.complete_halos()
         red = rt.red.cpu().numpy()
         tcv = time_control_variables._replace(
             physical_simulation_time=time_control_variables.physical_simulation_time +

@@ -9,7 +9,7 @@ for r in $(seq $reps); do for spec in $specs; do
   envs=()
   for e in "${parts[@]:1}"; do envs+=("$e"); done
   if [ "$v" = base ]; then lv=; else lv=$v; fi
-  env JXF_LIB_VARIANT=$lv "${envs[@]}" python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+  env JXF_LIB_VARIANT=$lv "${envs[@]}" python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline --no-parity 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['roofline']['kernel_ms']

@@ -142,3 +142,96 @@ def test_riemann2d_1024_two_steps_production_kernels():
         pr[0][m], pr[1][m], pr[2][m], pr[4][m] = rho, u, v, p
     worst = _run_and_compare(s, pr, steps=2, tol_prims=1e-12)
     print(f"\n2-D Riemann 1024^2, 2 steps: worst rel Linf {worst:.2e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the three-buffer memory plan: jxf_stage_inplace (prims updated in place, slab-sized rhs accumulators)
+# ---------------------------------------------------------------------------------------------------------------
+def _inplace_steps(sol, prims, cons, steps, slab_planes):
+    """`steps` RK steps through jxf_stage_inplace on ONE primitive buffer; returns (prims, cons, dt, info) tensors."""
+    p = dev(np.nan_to_num(prims, nan=1.0))
+    ca, cb = dev(np.nan_to_num(cons, nan=1.0)), sol.new_field(1.0)
+    slabs = sol.new_rhs_slabs(slab_planes)
+    red, info, time, dt = sol.new_red(), sol.new_scalars(3), sol.new_scalars(1, 0.0), sol.new_scalars(1, 0.0)
+    sol.reduce_reset(red)
+    sol.reduce(p, red)
+    sol.finish_step(red, dt, None, info)
+    for _ in range(steps):
+        for k in range(sol.stages):
+            last = k == sol.stages - 1
+            sol.stage_inplace(k, p, ca if k == 0 else cb, ca, ca if last else cb, slabs, slab_planes, dt, red,
+                              reduce=last, fill_halo=True)
+        sol.finish_step(red, dt, time, info)
+    return p, ca, dt, info
+
+
+@pytest.mark.parametrize("no_tma", [0, 1])
+@pytest.mark.parametrize("cells,bc,planes", [((24, 16, 40), "PERIODIC", 8), ((20, 12, 64), "SYMMETRY", 7),
+                                             ((17, 10, 33), "PERIODIC", 6), ((16, 12, 96), "ZEROGRADIENT", 16),
+                                             ((12, 8, 40), "PERIODIC", 64)])
+def test_inplace_stage_equals_pingpong_stage(cells, bc, planes, no_tma, monkeypatch):
+    """jxf_stage_inplace (3 full-size buffers: the x sweep one slab ahead, y / z + epilogue updating the slab in place,
+    deferred PERIODIC east / top halo images) against jxf_step_fused (5 buffers) BIT FOR BIT, and against the oracle."""
+    from jaxfluids_b200.engine import BlockState
+    monkeypatch.setenv("JXF_FORCE_ROWS", "1")
+    monkeypatch.setenv("JXF_NO_TMA", str(no_tma))
+    s = H.make_setup(cells, bc=bc)
+    prims, cons = port.initialize(H.smooth_ic(s, seed=5, amp=0.1), s)
+    sol = make_solver(s)
+    st = BlockState(sol, np.nan_to_num(prims, nan=1.0), np.nan_to_num(cons, nan=1.0))
+    steps = 3
+    for _ in range(steps):
+        st.step()
+    p, c, dt, info = _inplace_steps(sol, prims, cons, steps, planes)
+    mask = H.face_halo_mask(s)
+    assert np.array_equal(host(p)[:, mask], host(st.primitives)[:, mask])
+    assert np.array_equal(host(c)[:, mask], host(st.conservatives)[:, mask])
+    assert dt.item() == st.dt.item() and np.array_equal(host(info), host(st.info))
+    dto = port.time_step_size(prims, s)
+    for _ in range(steps):
+        prims, cons, dto = port.step(prims, cons, dto, s)
+    assert H.rel_linf(host(p)[:, mask], prims[:, mask]) <= 1e-12
+    assert abs(dt.item() - dto) <= 1e-12 * dto
+
+
+def test_inplace_stage_tgv128_vs_oracle():
+    """The three-buffer plan at a production-kernel size (rows + TMA at real pitch, marching chunks, 4 slabs of 32
+    planes): TGV 128^3 SYMMETRY, 2 steps vs the oracle."""
+    s, pr = _tgv_prims(128)
+    with np.errstate(all="ignore"):
+        prims, cons = port.initialize(pr, s)
+    sol = make_solver(s)
+    p, c, dt, info = _inplace_steps(sol, prims, cons, 2, 32)
+    stepper = port_mt.ThreadedStepper(s, os.cpu_count() or 1)
+    dto = port.time_step_size(prims, s)
+    for _ in range(2):
+        prims, cons, dto = stepper.step(prims, cons, dto)
+    mask = H.face_halo_mask(s)
+    e = H.rel_linf(host(p)[:, mask], prims[:, mask])
+    print(f"\nin-place TGV 128^3, 2 steps: rel Linf {e:.2e}")
+    assert e <= 1e-12 and abs(dt.item() - dto) <= 1e-12 * dto
+
+
+def test_inplace_memory_plan_through_public_api(monkeypatch):
+    """JXF_MEMORY_PLAN=inplace selects the plan in BlockRuntime: the public API on the TGV case, 3 steps, equals the
+    default plan bit for bit."""
+    import bench
+    from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+    out = {}
+    monkeypatch.setenv("JXF_FORCE_ROWS", "1")      # 48^3 is below the size at which the rows kernel is picked by itself
+    for plan in ("pingpong", "inplace"):
+        monkeypatch.setenv("JXF_MEMORY_PLAN", plan)
+        monkeypatch.setenv("JXF_SLAB_PLANES", "16")
+        case, num = bench.tgv_case(48, (1, 1, 1), end_step=3, bc="PERIODIC")
+        im = InputManager(case, num)
+        buf = InitializationManager(im).initialization()
+        sim = SimulationManager(im)
+        assert sim.runtime.memory_plan == plan
+        sim.simulate(buf)
+        fb = sim.final_buffers
+        out[plan] = (host(fb.simulation_buffers.material_fields.primitives).copy(),
+                     fb.time_control_variables.physical_timestep_size, fb.time_control_variables.physical_simulation_time)
+    s = H.make_setup((48, 48, 48))
+    mask = H.face_halo_mask(s)
+    assert np.array_equal(out["pingpong"][0][:, mask], out["inplace"][0][:, mask])
+    assert out["pingpong"][1:] == out["inplace"][1:]
