@@ -800,13 +800,17 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     sweeps = {k: v for k, v in prof.items() if k.startswith("sweep") and v[1] > 0}
     dom = max(sweeps, key=lambda k: sweeps[k][0])
-    dom_ms = sweeps[dom][0] / sweeps[dom][1]
+    # time of the kernel kind PER RK STAGE: one launch in the default plan; the sum of a stage's launches when the sweep
+    # is issued in pieces (slabs of the in-place plan, interior + strips of the overlapped exchange)
+    n_stage_launches = max(1, (args.steps if not small else min(args.steps, 50)) * rt.stages)
+    dom_ms = sweeps[dom][0] / n_stage_launches
     cells_local = int(np.prod(im.domain_information.device_number_of_cells))
     n_axes = len(rt.solver.active)
     flops_launch = ALG_FLOPS_PER_RHS_AXIS + (ALG_FLOPS_EPILOGUE if dom.endswith("epilogue") else 0.0)
     ach_tf = cells_local * flops_launch / (dom_ms * 1e-3) / 1e12
     ach_gbs = cells_local * KERNEL_BYTES[dom] / (dom_ms * 1e-3) / 1e9
-    kernel_ms = {k: (round(v[0] / v[1], 4) if v[1] else None) for k, v in prof.items()}
+    kernel_ms = {k: (round(v[0] / n_stage_launches, 4) if v[1] else None) for k, v in prof.items()}
+    launches_per_stage = {k: round(v[2] / n_stage_launches, 2) for k, v in prof.items() if v[2]}
     tot_prof = sum(x[0] for x in prof.values())
     share = {k: round(v[0] / (ms_total if (world == 1 and not small) else max(tot_prof, 1e-30)), 4) for k, v in prof.items()}
     alg_flops_step = 3.0 * (n_axes * ALG_FLOPS_PER_RHS_AXIS + ALG_FLOPS_EPILOGUE)     # 9.7e3 in 3-D
@@ -827,7 +831,8 @@ def main():
                            f"launch at 512^3; a constant from that capture, not measured in this run)" if traffic else None),
         "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "bytes_per_cell_launch": KERNEL_BYTES[dom], "peak_source": peak_src},
-        "kernel_ms": kernel_ms, "kernel_share_of_step": share,
+        "kernel_ms": kernel_ms, "kernel_ms_is": "per RK stage (sum over the launches of the kind in one stage)",
+        "launches_per_stage": launches_per_stage, "kernel_share_of_step": share,
         "step_roofline": {
             "alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP, "alg_flops_per_cell_step": alg_flops_step,
             "fp64_peak_tflops_measured": fp64_tflops, "hbm_bound_mcups": 1e-6 / t_hbm, "fp64_bound_mcups": 1e-6 / t_fp64,

@@ -271,6 +271,16 @@ int jxf_pack_face_n(jxf_handle h, int face, int ext_mask, int layers, const doub
 int jxf_unpack_face_n(jxf_handle h, int face, int ext_mask, int layers, const double* slab, double* prims, double* cons,
                       void* stream);
 
+/* Boundary DATA of one outer face, applied on top of the face's base rule (bc[face]) by jxf_halo_fill and by the fused
+ * halo images of jxf_stage: what the reference's NEUMANN, SIMPLE_INFLOW, SIMPLE_OUTFLOW boundaries, DIRICHLET boundaries
+ * with space-dependent primitives_callable, WALL boundaries with a space-dependent wall_velocity_callable and faces with
+ * several types prescribe (ref: halos/outer/material.py:473-520, :732-798, :825-866, :966-1050, :121-277).
+ * data_dev: (5, n1, n2) doubles over the face's transverse INTERIOR cells (the two other axes in increasing order, the
+ * later one fastest), the same for all nh halo layers; ops: 2 bits per variable v at bits 2v: 0 keep the base rule's
+ * value, 1 replace it by data_v, 2 add data_v to it; mask_dev: (n1, n2) bytes or NULL -- apply only where != 0.
+ * The caller owns both arrays and keeps them alive; ops = 0 clears the face. */
+int jxf_set_face_data(jxf_handle h, int face, int ops, const double* data_dev, const unsigned char* mask_dev);
+
 /* One RK stage on THREE full-size buffers: `prims` is updated IN PLACE (no ping-pong buffer) and the rhs accumulator is
  * two slabs of `slab_planes` x planes (jxf_rhs_slab_elems doubles each, stored back to back in `rhs_slabs`).  The block
  * is processed slab by slab with the x sweep running one slab ahead (see the definition).  3-D blocks, convective flux

@@ -18,7 +18,7 @@ EXPORTS = (
     "jxf_num_stages", "jxf_compute_rhs", "jxf_sweep", "jxf_stage", "jxf_halo_fill", "jxf_prims_from_cons",
     "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
     "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_dispatch", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature", "jxf_face_slab_elems_ext", "jxf_pack_face_ext", "jxf_unpack_face_ext", "jxf_bind_timestep",
-    "jxf_face_slab_elems_n", "jxf_pack_face_n", "jxf_unpack_face_n", "jxf_rhs_slab_elems", "jxf_stage_inplace",
+    "jxf_face_slab_elems_n", "jxf_pack_face_n", "jxf_unpack_face_n", "jxf_rhs_slab_elems", "jxf_stage_inplace", "jxf_set_face_data",
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1, "CONSERVATIVE": 2, "CHAR-CONSERVATIVE": 3}
@@ -171,6 +171,8 @@ def load():
     lib.jxf_rhs_slab_elems.argtypes = [vp, i32]
     lib.jxf_stage_inplace.restype = i32
     lib.jxf_stage_inplace.argtypes = [vp, i32, dp, dp, dp, dp, dp, i32, dp, dp, i32, i32, vp]
+    lib.jxf_set_face_data.restype = i32
+    lib.jxf_set_face_data.argtypes = [vp, i32, i32, dp, vp]
     lib.jxf_debug_math.restype = i32
     lib.jxf_debug_math.argtypes = [dp, i64, dp, vp]
     lib.jxf_debug_face_flux.restype = i32

@@ -27,6 +27,8 @@ struct HaloArgs {
   int bc[6];
   double wall[6][3];
   double dirichlet[6][5];
+  FaceData fd;             // per-face boundary data on top of the base rule (sweep_kernels.cuh), when has_fd
+  int has_fd;
 };
 
 __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const HaloArgs a) {
@@ -44,10 +46,20 @@ __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const Halo
   const int nh = g.nh, ext = g.ext[ax];
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
        q += (long long)gridDim.x * blockDim.x) {
-    const int i2 = (int)(q % n2);
-    const long long q1 = q / n2;
-    const int i1 = (int)(q1 % n1);
-    const int l = (int)(q1 / n1);   // halo layer in increasing buffer index
+    // halo layer l in increasing buffer index.  Faces of the CONTIGUOUS axis: the nh layers of a row are adjacent in
+    // memory, so l runs fastest there (one 8 nh-byte segment per row instead of nh accesses a row pitch apart)
+    int i1, i2, l;
+    if (g.st[ax] == 1) {
+      l = (int)(q % nh);
+      const long long q1 = q / nh;
+      i2 = (int)(q1 % n2);
+      i1 = (int)(q1 / n2);
+    } else {
+      i2 = (int)(q % n2);
+      const long long q1 = q / n2;
+      i1 = (int)(q1 % n1);
+      l = (int)(q1 / n1);
+    }
     const int dst = hi ? (ext - nh + l) : l;
     int src;
     if (kind == JXF_BC_PERIODIC) src = hi ? (nh + l) : (ext - 2 * nh + l);
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(128) halo_fill_kernel(const Geom g, const Halo
 #pragma unroll
       for (int v = 0; v < 5; ++v) p[v] = a.dirichlet[face][v];
     }
+    if (a.has_fd) apply_face_data(a.fd, face, (long long)i1 * n2 + i2, (long long)n1 * n2, p);
     cons_from_prims(p, a.gamma, c);
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -941,12 +954,33 @@ extern "C" int jxf_compute_rhs(jxf_handle h, const double* prims, double* rhs, v
   return JXF_OK;
 }
 
+// Per-face boundary data (sweep_kernels.cuh FaceData): the caller owns the device arrays and keeps them alive while the
+// handle uses them.  ops = 0 (or data = null) clears the face.
+extern "C" int jxf_set_face_data(jxf_handle h, int face, int ops, const double* data_dev, const unsigned char* mask_dev) {
+  if (!h || face < 0 || face > 5) return fail(JXF_ERR_BAD_ARG, "jxf_set_face_data: bad argument");
+  if (ops < 0 || ops >= (1 << 10)) return fail(JXF_ERR_BAD_ARG, "jxf_set_face_data: ops=%d", ops);
+  for (int v = 0; v < 5; ++v)
+    if (((ops >> (2 * v)) & 3) == 3) return fail(JXF_ERR_BAD_ARG, "jxf_set_face_data: op 3 of variable %d is undefined", v);
+  if (ops && !data_dev) return fail(JXF_ERR_BAD_ARG, "jxf_set_face_data: ops without data");
+  const int b = h->cfg.bc[face];
+  if (ops && (b == JXF_BC_PERIODIC || b == JXF_BC_NEIGHBOR || b == JXF_BC_INACTIVE))
+    return fail(JXF_ERR_BAD_ARG, "jxf_set_face_data: face %d carries no physical boundary rule to build on", face);
+  h->face_data.ops[face] = data_dev ? ops : 0;
+  h->face_data.data[face] = ops ? data_dev : nullptr;
+  h->face_data.mask[face] = ops ? mask_dev : nullptr;
+  h->has_face_data = 0;
+  for (int f = 0; f < 6; ++f) h->has_face_data |= (h->face_data.ops[f] != 0);
+  return JXF_OK;
+}
+
 extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream) {
   if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill: null argument");
   HaloArgs a;
   a.prims = prims;
   a.cons = cons;
   a.gamma = h->cfg.gamma;
+  a.fd = h->face_data;
+  a.has_fd = h->has_face_data;
   long long maxcells = 0;
   for (int f = 0; f < 6; ++f) {
     a.bc[f] = h->cfg.bc[f];
@@ -1045,6 +1079,9 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       }
       a.volume_force = h->cfg.volume_force;
       for (int q = 0; q < 3; ++q) a.gravity[q] = h->cfg.gravity[q];
+      a.face_data = h->face_data;
+      a.has_face_data = h->has_face_data;
+      for (int q = 0; q < 3; ++q) a.n_phys[q] = h->g.n[q];
       rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
     }
     if (rc) return rc;
@@ -1135,6 +1172,9 @@ extern "C" int jxf_stage_inplace(jxf_handle h, int stage, double* prims, const d
         if (a.bc[f] == JXF_BC_PERIODIC) { a.bc[f] = JXF_BC_NEIGHBOR; defer[f] = true; }
       a.volume_force = h->cfg.volume_force;
       for (int q = 0; q < 3; ++q) a.gravity[q] = h->cfg.gravity[q];
+      a.face_data = h->face_data;
+      a.has_face_data = h->has_face_data;
+      for (int q = 0; q < 3; ++q) a.n_phys[q] = h->g.n[q];
       if ((rc = dispatch_axis(h, 2, a, 1, st))) return rc;
     }
   }

@@ -38,6 +38,8 @@ struct jxf_solver {
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
+  FaceData face_data;  // jxf_set_face_data: device pointers owned by the caller
+  int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
   bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
@@ -169,7 +171,8 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
 #if JXF_ROWS_KERNEL
     // production form whenever groups of >= 4 rows give every resident warp several work items
     const long long warps_resident = 4LL * resident;
-    if ((s->force_rows || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
+    // (an in-place epilogue needs the staged windows of this kernel: forced whatever the slab's row count)
+    if ((s->force_rows || (EPI && a.inplace) || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
       RowsArgs ra;
       ra.iters_per_row = (g.n[A] + 31) / 32;
       // one group per warp, 4 warps per CTA, many more CTAs than resident slots: the hardware block

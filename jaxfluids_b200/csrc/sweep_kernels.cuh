@@ -22,6 +22,33 @@ struct Geom {
   long long rvst;
 };
 
+// Per-face boundary DATA on the device (jxf_set_face_data): what NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW faces,
+// DIRICHLET faces with space-dependent primitives_callable, WALL faces with a space-dependent velocity and faces
+// with several types prescribe on top of the face's base rule (halos/outer/material.py:473-520, :732-866, :966-1050).
+// The base rule (bc[face]: ZEROGRADIENT copy of the last interior cell, the WALL / SYMMETRY mirror, ...) produces the
+// halo primitives; then, per variable v with op = (ops >> 2 v) & 3:  1: p_v = data_v,  2: p_v = p_v + data_v
+// (NEUMANN increment (value * sign) * dx; WALL 2 u_wall on top of -u_mirror), 0: keep.  data: (5, n1, n2) over the
+// face's transverse interior cells, the same for every halo layer (the reference expands the callable's values along
+// the face normal); mask (n1, n2) or null: apply only where mask != 0 (one type of a multi-type face).
+struct FaceData {
+  const double* data[6];
+  const unsigned char* mask[6];
+  int ops[6];
+};
+
+__device__ __forceinline__ void apply_face_data(const FaceData& fd, int face, long long tidx, long long tcount, double (&p)[5]) {
+  const int ops = fd.ops[face];
+  if (ops == 0) return;
+  if (fd.mask[face] && fd.mask[face][tidx] == 0) return;
+  const double* d = fd.data[face] + tidx;
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    const int op = (ops >> (2 * v)) & 3;
+    if (op == 1) p[v] = d[v * tcount];
+    else if (op == 2) p[v] = p[v] + d[v * tcount];
+  }
+}
+
 struct SweepArgs {
   const double* prims;     // stage-entry primitives (halo'd)
   double* rhs;             // interior-only accumulator
@@ -58,6 +85,9 @@ struct SweepArgs {
   int sub_lo, sub_n;
   long long rvst_slab;
   int inplace;             // EPI: prims_out aliases prims (rows kernel: the next window must have landed before a store)
+  FaceData face_data;      // EPI + fuse_halo: per-face boundary data (device pointers), used when has_face_data
+  int has_face_data;
+  int n_phys[3];           // interior cells per PHYSICAL axis (transverse indexing of face_data)
 };
 
 // ---------------------------------------------------------------------------
@@ -166,9 +196,11 @@ struct HaloOut {
 };
 
 // wall = nullptr: copy, negating velocity component flip_var (1..3; -1 = none).  wall != nullptr: no-slip wall
-// moving with (u, v, w) = wall[0..2]: every velocity component becomes 2 u_wall - u (halos/outer/material.py:510-512)
+// moving with (u, v, w) = wall[0..2]: every velocity component becomes 2 u_wall - u (halos/outer/material.py:510-512).
+// fd / face / tidx / tcount: the face's device-resident boundary data, applied on top (apply_face_data)
 __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, double p0, double p1, double p2, double p3,
-                                           double p4, int flip_var, const double* wall = nullptr) {
+                                           double p4, int flip_var, const double* wall, const FaceData* fd, int face,
+                                           long long tidx, long long tcount) {
   double q[5] = {p0, p1, p2, p3, p4};
   if (wall) {
 #pragma unroll
@@ -177,6 +209,7 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
 #pragma unroll
     for (int v = 1; v < 4; ++v) q[v] = (v == flip_var) ? q[v] * -1.0 : q[v];
   }
+  if (fd) apply_face_data(*fd, face, tidx, tcount, q);
   double c[5];
   cons_from_prims(q, h.gamma, c);
 #pragma unroll
@@ -186,41 +219,44 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
   }
 }
 
-// one role axis of the images of a cell; wall_hi / wall_lo: wall velocities of the two faces of this axis
+// one role axis of the images of a cell; wall_hi / wall_lo: wall velocities of the two faces of this axis;
+// tidx / tcount: the cell's index / the cell count in the transverse plane of this axis (face data)
 __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
                                                  int ax, int n, int i, long long stride, const double* wall_hi,
-                                                 const double* wall_lo, const double* dir_hi, const double* dir_lo) {
+                                                 const double* wall_lo, const double* dir_hi, const double* dir_lo,
+                                                 const FaceData* fd, long long tidx, long long tcount) {
   if (n <= 1) return;
   const int nh = h.nh;
+  const int fhi = 2 * ax, flo = 2 * ax + 1;
   // low side (west / south / bottom)
   if (blo == JXF_BC_SYMMETRY) {
-    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
+    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax, nullptr, fd, flo, tidx, tcount);
   } else if (blo == JXF_BC_WALL) {
-    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_lo);
+    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_lo, fd, flo, tidx, tcount);
   } else if (blo == JXF_BC_PERIODIC) {
-    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
+    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, flo, 0, 0);
   } else if (blo == JXF_BC_ZEROGRADIENT) {
     if (i == 0)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, fd, flo, tidx, tcount);
   } else if (blo == JXF_BC_DIRICHLET) {       // constants: written by the thread of the boundary-adjacent cell
     if (i == 0)
       for (int l = 1; l <= nh; ++l)
-        halo_image(h, hidx - (long long)l * stride, dir_lo[0], dir_lo[1], dir_lo[2], dir_lo[3], dir_lo[4], -1);
+        halo_image(h, hidx - (long long)l * stride, dir_lo[0], dir_lo[1], dir_lo[2], dir_lo[3], dir_lo[4], -1, nullptr, fd, flo, tidx, tcount);
   }
   // high side (east / north / top)
   if (bhi == JXF_BC_SYMMETRY) {
-    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax);
+    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax, nullptr, fd, fhi, tidx, tcount);
   } else if (bhi == JXF_BC_WALL) {
-    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_hi);
+    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_hi, fd, fhi, tidx, tcount);
   } else if (bhi == JXF_BC_PERIODIC) {
-    if (i < nh) halo_image(h, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1);
+    if (i < nh) halo_image(h, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, fhi, 0, 0);
   } else if (bhi == JXF_BC_ZEROGRADIENT) {
     if (i == n - 1)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1);
+      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, fd, fhi, tidx, tcount);
   } else if (bhi == JXF_BC_DIRICHLET) {
     if (i == n - 1)
       for (int l = 1; l <= nh; ++l)
-        halo_image(h, hidx + (long long)l * stride, dir_hi[0], dir_hi[1], dir_hi[2], dir_hi[3], dir_hi[4], -1);
+        halo_image(h, hidx + (long long)l * stride, dir_hi[0], dir_hi[1], dir_hi[2], dir_hi[3], dir_hi[4], -1, nullptr, fd, fhi, tidx, tcount);
   }
 }
 
@@ -279,12 +315,24 @@ static __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const S
                                               double p2, double p3, double p4, int iA, int i1, int i2) {
   const HaloOut h{a.prims_out, a.cons_out, g.vst, a.gamma, a.nh};
   const double p[5] = {p0, p1, p2, p3, p4};
+  const FaceData* fd = a.has_face_data ? &a.face_data : nullptr;
+  // transverse index / count per PHYSICAL face axis (face data is laid out over (t1, t2) = the two other physical axes
+  // in increasing order, t2 fastest): only when the stage carries face data
+  long long tidx[3] = {0, 0, 0}, tcnt[3] = {0, 0, 0};
+  if (fd) {
+    int idx[3];
+    idx[g.axA] = iA; idx[g.ax1] = i1; idx[g.ax2] = i2;
+    const int* n = a.n_phys;
+    tidx[0] = (long long)idx[1] * n[2] + idx[2]; tcnt[0] = (long long)n[1] * n[2];
+    tidx[1] = (long long)idx[0] * n[2] + idx[2]; tcnt[1] = (long long)n[0] * n[2];
+    tidx[2] = (long long)idx[0] * n[1] + idx[1]; tcnt[2] = (long long)n[0] * n[1];
+  }
   halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1],
-                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1]);
+                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1], fd, tidx[g.axA], tcnt[g.axA]);
   halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1_full, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
-                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1]);
+                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1], fd, tidx[g.ax1], tcnt[g.ax1]);
   halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1],
-                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1]);
+                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1], fd, tidx[g.ax2], tcnt[g.ax2]);
 }
 
 #ifdef JXF_WITH_STRIDED   // the register-window predecessor of sweep_march: A/B builds only (-DJXF_WITH_STRIDED)

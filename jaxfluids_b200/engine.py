@@ -262,6 +262,17 @@ class BlockSolver:
         _lib.check(self.lib.jxf_temperature(self._h, _ptr(prims), _ptr(out), _stream()))
         return out
 
+    def set_face_data(self, face: int, ops: int, data: Optional[torch.Tensor], mask: Optional[torch.Tensor] = None):
+        """Per-face boundary data applied on top of the face's base rule (include/jxf_b200.h jxf_set_face_data);
+        the caller keeps `data` (5, n1, n2) fp64 and `mask` (n1, n2) uint8 alive."""
+        if data is not None:
+            assert data.is_cuda and data.dtype == torch.float64 and data.is_contiguous()
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+        _lib.check(self.lib.jxf_set_face_data(self._h, int(face), int(ops),
+                                              None if data is None else C.c_void_p(data.data_ptr()),
+                                              None if mask is None else C.c_void_p(mask.data_ptr())))
+
     def halo_fill(self, prims, cons):
         _lib.check(self.lib.jxf_halo_fill(self._h, _ptr(prims), _ptr(cons), _stream()))
 

@@ -62,8 +62,8 @@ TUPLE_POSITIVITY_PARTITIONS = ("UNIFORM", "CELLSIZE")   # WAVESPEED needs a glob
 TUPLE_DISSIPATIVE_STENCILS = ("CENTRAL4",)     # reconstruction / derivative_center / derivative_face
 DICT_TIME_INTEGRATION = {"EULER": "Euler", "RK2": "RungeKutta2", "RK3": "RungeKutta3", "RK2_LS4": "RungeKutta2_LS4"}
 DICT_MATERIAL = {"IdealGas": "IdealGas"}
-# NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW: the halo kernels fill ZEROGRADIENT, the host runtime applies the prescribed
-# data on top (runtime.BlockRuntime._apply_host_boundaries)
+# NEUMANN / SIMPLE_INFLOW / SIMPLE_OUTFLOW: the kernels' base rule on these faces is ZEROGRADIENT; the prescribed data is
+# applied on top of it in the kernels from per-face device arrays (runtime.BlockRuntime._make_face_data)
 TUPLE_BOUNDARY_TYPES = ("ZEROGRADIENT", "SYMMETRY", "PERIODIC", "INACTIVE", "WALL", "DIRICHLET", "NEUMANN",
                         "SIMPLE_INFLOW", "SIMPLE_OUTFLOW")
 # entries of primitives_callable each of these types reads (read_boundary_conditions.py:160-365)

@@ -94,15 +94,17 @@ class BlockRuntime:
         self.solver = BlockSolver(self.cfg)
         s = self.solver
         self.device = s.device
-        # boundary data the host writes over the halo kernels' values after every halo fill (_apply_host_boundaries)
-        self.host_boundaries = {f: self._make_host_boundary(f, t, v, m) for f, (t, v, m) in self._host_faces.items()}
-        if self.cfg.is_dissipative and any(isinstance(f, tuple) for f in self.host_boundaries):
+        # boundary DATA of this block's outer faces (space-dependent DIRICHLET / WALL values, NEUMANN increments,
+        # SIMPLE_INFLOW / SIMPLE_OUTFLOW values, the DIRICHLET parts of multi-type faces): device arrays over the face's
+        # transverse cells that the halo kernel and the fused halo images apply on top of the face's base rule
+        # (jxf_set_face_data); the tensors are owned here
+        self.face_data = self._make_face_data()
+        if self.cfg.is_dissipative and any(isinstance(f, tuple) for f in self._host_faces):
             raise NotImplementedError("several boundary types on one face together with the viscous / heat flux (edge "
                                       "halos next to such a face) are not implemented on the B200 path")
-        self._host_halo = bool(self.host_boundaries)
-        if self._host_halo and self.neighbors:
-            raise NotImplementedError("space-dependent DIRICHLET / WALL data, NEUMANN, SIMPLE_INFLOW and SIMPLE_OUTFLOW boundaries "
-                                      "are implemented for single-block runs on the B200 path")
+        for f, (ops, data, mask) in self.face_data.items():
+            s.set_face_data(FACE_ID[f], ops, data, mask)
+        self._host_halo = False                # (kept for the memory-plan / graph conditions: nothing is host-applied)
         self.stages = s.stages
         # Memory plan.  "pingpong" (default): 2 primitive + 2 conservative buffers + a full-size rhs accumulator.
         # "inplace": ONE primitive buffer updated in place + 2 conservative buffers + two slab-sized rhs accumulators
@@ -167,13 +169,17 @@ class BlockRuntime:
             return "pingpong"
         field = int(np.prod(self.cfg.shape)) * 8
         need = 4 * field + int(np.prod(self.cfg.rhs_shape)) * 8
-        free, _ = torch.cuda.mem_get_info(self.device)
+        try:
+            free, _ = torch.cuda.mem_get_info(self.device)
+        except Exception:
+            return "pingpong"
         return "inplace" if need > 0.92 * free else "pingpong"
 
-    # -- boundaries the host applies on top of the halo kernels -------------------
-    # DIRICHLET with space-dependent data, NEUMANN, SIMPLE_INFLOW, SIMPLE_OUTFLOW: the halo kernels fill these faces with
-    # what they implement (constants / ZEROGRADIENT), then torch index assignments write the prescribed data and the
-    # conservatives of those halo cells, and the edge fill is re-run.  No new kernel; single block only.
+    # -- boundaries with data beyond the kernels' constants -----------------------
+    # DIRICHLET with space-dependent data, NEUMANN, SIMPLE_INFLOW, SIMPLE_OUTFLOW, space-dependent WALL velocities,
+    # multi-type faces: the kernels are configured with the base rule of the face (constants / ZEROGRADIENT / WALL at
+    # rest) and apply the prescribed data -- device arrays over the face's transverse cells -- on top of it, in the halo
+    # kernel and in the fused halo images alike (jxf_set_face_data).  Multi-block runs included.
     KERNEL_TYPE = {"NEUMANN": "ZEROGRADIENT", "SIMPLE_INFLOW": "ZEROGRADIENT", "SIMPLE_OUTFLOW": "ZEROGRADIENT"}
 
     def _kernel_boundary_types(self) -> Dict[str, str]:
@@ -234,60 +240,50 @@ class BlockRuntime:
                 consts[f] = (0.0, 0.0, 0.0)
         return consts
 
-    def _make_host_boundary(self, face, kind: str, vals, mask=None):
-        """(halo index, type, per-variable device slabs) of one face: each prescribed field broadcast over the nh halo
-        layers (the reference expands the callable's values along the face normal); NEUMANN slabs hold the increment
-        (value * upwind sign) * dx of halos/outer/material.py:857-862."""
-        nh = self.cfg.nh
-        face = face[0] if isinstance(face, tuple) else face    # (face, i): the i-th DIRICHLET entry of a multi-type face
-        ax = FACE_ID[face] >> 1
-        hi = (FACE_ID[face] & 1) == 0                      # east / north / top
-        shape = [n if n > 1 else 1 for n in self.cfg.cells]
-        shape[ax] = nh
-        idx = [slice(None)] + list(self.cfg.interior)
-        idx[1 + ax] = slice(-nh, None) if hi else slice(0, nh)
-        slabs = []
-        for v in vals:
-            if v is None:
-                slabs.append(None)
-                continue
-            a = np.broadcast_to(np.asarray(v, dtype=np.float64), shape)
-            if kind == "NEUMANN":
-                dx = np.float64(1.0) / np.float64(self.cfg.inv_dx[ax]) if self._cell_sizes is None else self._cell_sizes[ax]
-                a = a * (-1 if hi else 1) * dx
-            if kind == "WALL":
-                a = 2 * a                                  # u_halo = 2 u_wall - u_mirror (material.py:494-496)
-            slabs.append(torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.device))
-        if mask is not None:
-            mask = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(mask, shape))).to(self.device)
-        return tuple(idx), kind, slabs, mask
-
-    def _apply_host_boundaries(self, prims: torch.Tensor, cons: torch.Tensor):
-        """Right after the halo kernel (which left constants / the ZEROGRADIENT copy in these halos)."""
-        g1 = float(self.cfg.gamma) - 1.0
-        for idx, kind, slabs, mask in self.host_boundaries.values():
-            h = prims[idx]                                 # a view of the face's halo cells
-            for v, slab in enumerate(slabs):
-                if slab is None:
+    # ops of jxf_set_face_data per variable: 1 = replace by the data, 2 = add the data to the base rule's value
+    def _make_face_data(self):
+        """{face: (ops, data (5, n1, n2) device tensor, mask (n1, n2) uint8 device tensor or None)} from self._host_faces.
+        NEUMANN: the increment (value * upwind sign) * dx of halos/outer/material.py:857-862 added to the ZEROGRADIENT
+        copy; SIMPLE_INFLOW: rho, u, v, w replaced, p kept (:966-1022); SIMPLE_OUTFLOW: p replaced (:1024-1050); DIRICHLET:
+        all five replaced (:770-790); WALL: 2 u_wall added to -u_mirror (:494-496, the kernels run with u_wall = 0
+        there); entries of a multi-type face: replaced inside the union of their bounding domains (:121-277)."""
+        out = {}
+        for key, (kind, vals, mask) in self._host_faces.items():
+            face = key[0] if isinstance(key, tuple) else key
+            ax = FACE_ID[face] >> 1
+            hi = (FACE_ID[face] & 1) == 0                      # east / north / top
+            shape3 = [n if n > 1 else 1 for n in self.cfg.cells]
+            shape3[ax] = 1
+            tshape = tuple(n for i, n in enumerate(self.cfg.cells) if i != ax)       # (n1, n2), physical order
+            data = np.zeros((5,) + tshape)
+            ops = 0
+            for v, val in enumerate(vals):
+                if val is None:
                     continue                               # SIMPLE_INFLOW keeps the copied p, SIMPLE_OUTFLOW rho, u, v, w
-                if kind == "WALL":
-                    h[v] = slab + h[v]                     # 2 u_wall + (-u_mirror): the kernel ran with u_wall = 0
-                elif kind == "NEUMANN":
-                    h[v] = h[v] + slab                     # last interior cell (the kernel's copy) + increment
-                elif mask is not None:
-                    h[v] = torch.where(mask, slab, h[v])   # one type of a multi-type face, inside its bounding domain
-                else:
-                    h[v] = slab
-            # conservatives of the halo cells (equation_manager.py:93-101), the reference's operation order
-            e = h[4] / (h[0] * g1)
-            c = cons[idx]
-            c[0] = h[0]
-            c[1] = h[0] * h[1]
-            c[2] = h[0] * h[2]
-            c[3] = h[0] * h[3]
-            c[4] = h[0] * (0.5 * (torch.square(h[1]) + torch.square(h[2]) + torch.square(h[3])) + e)
-        if self.cfg.is_dissipative and len(self.solver.active) > 1:     # edges read the face halos (halo_manager.py:119-129)
-            self.solver.halo_fill_edges(prims, cons)
+                a = np.broadcast_to(np.asarray(val, dtype=np.float64), shape3).reshape(tshape)
+                op = 1
+                if kind == "NEUMANN":
+                    a = a * (-1 if hi else 1) * self._cell_sizes[ax]
+                    op = 2
+                elif kind == "WALL":
+                    if v not in (1, 2, 3):
+                        continue
+                    a = 2 * a                              # u_halo = 2 u_wall - u_mirror
+                    op = 2
+                data[v] = a
+                ops |= op << (2 * v)
+            m = None if mask is None else np.broadcast_to(np.asarray(mask, dtype=bool), shape3).reshape(tshape)
+            if face in out:                                # a further DIRICHLET entry of the same multi-type face
+                ops0, data0, m0 = out[face]
+                assert ops0 == ops and m0 is not None and m is not None
+                data = np.where(m[None], data, data0)
+                m = m | m0
+            out[face] = (ops, data, m)
+        dev = {}
+        for face, (ops, data, m) in out.items():
+            dev[face] = (ops, torch.as_tensor(np.ascontiguousarray(data), dtype=torch.float64).to(self.device),
+                         None if m is None else torch.as_tensor(np.ascontiguousarray(m.astype(np.uint8))).to(self.device))
+        return dev
 
     # -- views ------------------------------------------------------------
     @property
@@ -432,8 +428,6 @@ class BlockRuntime:
             self._halos_partial = not full
         if not local_done:
             s.halo_fill(prims, cons)
-            if self.host_boundaries:
-                self._apply_host_boundaries(prims, cons)
 
     def _allreduce_red(self):
         if self.parallel.is_parallel:
@@ -512,10 +506,6 @@ class BlockRuntime:
                 s.sweep_range(ax, 0, n, p_in, self.rhs, accumulate=False)
                 self.finish_pending()
             s.stage_tail(k, 1, *args, reduce=reduce, fill_halo=True)
-        elif self._host_halo:
-            # host-applied boundary data: no fused halo images; halo kernel, host data, edges after the stage
-            s.stage(k, *args, reduce=reduce, fill_halo=False)
-            self.halo_update(p_out, c_out)
         else:
             self.finish_pending()
             s.stage(k, *args, reduce=reduce, fill_halo=True)

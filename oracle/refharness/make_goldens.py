@@ -198,6 +198,36 @@ def make_flux_limiter_fixture():
     print(f"special/flux_limiter_riemann2d_20x24: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def make_hit_fixture():
+    """SURVEY 8(c) / BASELINE config 5 at 32^3: periodic [0, 2 pi]^3, gamma 1.4, the benchmark's synthetic solenoidal
+    field (jaxfluids_b200/turbulence.synthetic_solenoidal_ic: E(k) ~ k^4 exp(-2 k^2 / k0^2), k0 = 4, Ma_t = 0.4,
+    seed 0) injected through initialization(user_prime_init=...), TGV numerical setup (CHAR-PRIMITIVE WENO5-Z + HLLC +
+    RK3).  Compact: interior arrays only (the IC is stored, not regenerated: its BLAS contractions are not
+    bit-reproducible across hosts)."""
+    from jaxfluids_b200 import turbulence
+    case, num = rr.customize(*rr.load_case("tgv"), cells=(32, 32, 32), bc="PERIODIC")
+    case["material_properties"]["equation_of_state"]["specific_heat_ratio"] = 1.4
+    user = turbulence.synthetic_solenoidal_ic(32, gamma=1.4, k0=4.0, ma_t=0.4, seed=0)
+    run = rr.ReferenceRun(case, num, user_prime_init=user)
+    d = {"case_json": np.array(json.dumps(case)), "num_json": np.array(json.dumps(num)), "user": user,
+         "dt0": np.float64(run.dt)}
+    nsteps = 3
+    seq = {"dt": [], "time": [], "totals": [], "min_density": [], "min_pressure": []}
+    for n in range(1, nsteps + 1):
+        rec = run.step(record_stages=(n == 1))
+        if n == 1:
+            d["rhs_s0"] = rec["rhs"][0]
+        for k, key in (("dt", "dt_next"), ("time", "time"), ("totals", "totals"), ("min_density", "min_density"),
+                       ("min_pressure", "min_pressure")):
+            seq[k].append(rec[key])
+    d[f"prims_n{nsteps}"] = run.interior(run.primitives).copy()
+    for k, v in seq.items():
+        d[k] = np.array(v)
+    path = os.path.join(OUT, "special", "hit32_per_char_hllc_rk3.npz")
+    np.savez_compressed(path, **d)
+    print(f"special/hit32_per_char_hllc_rk3: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def make(name, case_name, kw, nsteps, snaps):
     kw = dict(kw)
     dissipation = kw.pop("dissipation", None)
@@ -253,6 +283,9 @@ if __name__ == "__main__":
     if not only or "flux_limiter" in only:
         with np.errstate(all="ignore"):
             make_flux_limiter_fixture()
+    if not only or "hit" in only:
+        with np.errstate(all="ignore"):
+            make_hit_fixture()
     if not only or "stencils" in only:
         with np.errstate(all="ignore"):
             make_stencil_fixture()

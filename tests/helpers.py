@@ -289,3 +289,39 @@ def defined_mask(s: port.Setup):
     ix, iy, iz = np.meshgrid(*inter, indexing="ij")
     n_out = (~ix).astype(int) + (~iy).astype(int) + (~iz).astype(int)
     return n_out <= (2 if s.is_dissipative else 1)
+
+
+def apply_face_data_numpy(face_data, prims, cons, cells, nh, gamma):
+    """What the halo kernel / the fused halo images do with jxf_set_face_data's arrays (sweep_kernels.cuh
+    apply_face_data), on NumPy arrays that hold the faces' BASE-rule halos: per variable op 1 = replace by the data,
+    op 2 = add it, inside the optional mask, the same for every halo layer; then the conservatives of those halo
+    cells (equation_manager.py:93-101).  face_data: {face: (ops, data (5, n1, n2), mask (n1, n2) or None)} (tensors or
+    arrays).  Used by the CPU tests of BlockRuntime's boundary-data construction."""
+    prims, cons = prims.copy(), cons.copy()
+    g1 = gamma - 1.0
+    for face, (ops, data, mask) in face_data.items():
+        data = np.asarray(data)
+        mask = None if mask is None else np.asarray(mask).astype(bool)
+        ax = port.FACE_AXIS[face]
+        hi = face in ("east", "north", "top")
+        idx = [slice(None)] + [slice(nh, -nh) if n > 1 else slice(None) for n in cells]
+        idx[1 + ax] = slice(-nh, None) if hi else slice(0, nh)
+        h = prims[tuple(idx)]                               # view (5, ..nh along ax..)
+        shape = [n if n > 1 else 1 for n in cells]
+        shape[ax] = 1
+        for v in range(5):
+            op = (ops >> (2 * v)) & 3
+            if op == 0:
+                continue
+            d = data[v].reshape(shape)
+            new = np.broadcast_to(d, h[v].shape) if op == 1 else h[v] + d
+            h[v] = new if mask is None else np.where(mask.reshape(shape), new, h[v])
+        with np.errstate(all="ignore"):
+            e = h[4] / (h[0] * g1)
+            c = cons[tuple(idx)]
+            c[0] = h[0]
+            c[1] = h[0] * h[1]
+            c[2] = h[0] * h[2]
+            c[3] = h[0] * h[3]
+            c[4] = h[0] * (0.5 * (np.square(h[1]) + np.square(h[2]) + np.square(h[3])) + e)
+    return prims, cons

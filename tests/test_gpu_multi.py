@@ -135,3 +135,73 @@ def test_pencil_and_block_decompositions(split, cells, bc, nproc, visc, tmp_path
     env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="3",
                JXF_CELLS=",".join(map(str, cells)), JXF_VISC=str(visc))
     _run_worker(worker, env, nproc)
+
+
+API_WORKER = r'''
+import json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["JXF_ROOT"])
+from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+from tests import helpers as H
+
+name = os.environ["JXF_FIXTURE"]
+split = tuple(int(v) for v in os.environ["JXF_SPLIT"].split(","))
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+g, case, num = H.load_golden(name)
+n = len(g["dt"])
+case, num = json.loads(json.dumps(case)), json.loads(json.dumps(num))
+case["general"]["end_step"] = n
+case["general"]["end_time"] = 1e300
+case["domain"]["decomposition"] = {"split_x": split[0], "split_y": split[1], "split_z": split[2]}
+num.setdefault("output", {}).setdefault("logging", {})["level"] = "NONE"
+im = InputManager(case, num)
+buf = InitializationManager(im).initialization()
+assert dist.is_initialized()
+rank = dist.get_rank()
+sim = SimulationManager(im)
+assert sim.runtime.face_data, "this rank's block carries boundary data (jxf_set_face_data)"
+sim.simulate(buf)
+out = sim.final_buffers
+s = H.setup_from_json(case, num)
+di = im.domain_information
+it = (slice(None),) + s.interior
+mine = out.simulation_buffers.material_fields.primitives[it].cpu().numpy()
+gathered = [None] * dist.get_world_size()
+dist.all_gather_object(gathered, (di.block_slices(rank), mine, out.time_control_variables.physical_timestep_size))
+if rank == 0:
+    ref = g[f"prims_n{n}"][it]
+    glob = np.empty_like(ref)
+    for sl, arr, _ in gathered:
+        glob[(slice(None),) + sl] = arr
+    err = H.rel_linf(glob, ref)
+    print("RESULT " + json.dumps({"err": err, "dt_err": max(abs(d - g["dt"][n - 1]) / g["dt"][n - 1] for _, _, d in gathered),
+                                  "t_err": 0.0}))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("name,split", [("api/riemann2d_16x20_inflow_outflow_neumann_rk3", (2, 1, 1)),
+                                        ("api/riemann2d_16x20_inflow_outflow_neumann_rk3", (1, 2, 1)),
+                                        ("api/dmr_48x32_dirichlet_symmetry_south_rk3", (2, 1, 1)),
+                                        ("api/heat2d_24x20_dirichlet_lambda_noconv_rk3", (2, 1, 1)),
+                                        ("api/riemann2d_16x20_inflow_outflow_visc_rk3", (1, 2, 1)),
+                                        ("api/cavity_24x20_wall_lambda_lid_visc_rk3", (2, 1, 1))])
+def test_boundary_data_fixtures_on_two_blocks(name, split, tmp_path):
+    """The reference's fixtures with boundary DATA (NEUMANN, SIMPLE_INFLOW / SIMPLE_OUTFLOW, space-dependent DIRICHLET and
+    WALL velocities, a multi-type face) through the public API on TWO blocks: every block applies the data of its own
+    outer faces in its kernels (per-block transverse cells), the shared face is exchanged; result = the reference's
+    single-block fixture."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = tmp_path / "worker.py"
+    worker.write_text(API_WORKER)
+    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_FIXTURE=name)
+    port_no = 29500 + (os.getpid() % 200)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port_no), str(worker)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, out.stdout[-2000:] + out.stderr[-4000:]
+    res = json.loads(lines[-1][7:])
+    assert res["err"] <= H.TOL_PRIMS_100 and res["dt_err"] <= 1e-10, res

@@ -262,7 +262,7 @@ def test_public_api_runs_space_dependent_dirichlet_example(name):
     assert np.array_equal(p0[:, m], g["prims0_halo"][:, m])          # initial halos incl. the lambda's values, bit-exact
     assert abs(buffers.time_control_variables.physical_timestep_size - float(g["dt0"])) <= 1e-14 * float(g["dt0"])
     sim = SimulationManager(im)
-    assert sim.runtime.host_boundaries
+    assert sim.runtime.face_data            # boundary data applied in the kernels (jxf_set_face_data)
     sim.simulate(buffers)
     out = sim.final_buffers
     pr = P.host(out.simulation_buffers.material_fields.primitives)

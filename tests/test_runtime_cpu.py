@@ -1,4 +1,4 @@
-"""CPU: the WHOLE host side of the host-applied-boundary path -- InputManager -> InitializationManager ->
+"""CPU: the WHOLE host side of the boundary-data path -- InputManager -> InitializationManager ->
 SimulationManager.simulate -> BlockRuntime (stage by stage, halo kernel, host boundary data, edge fill, buffer rotation,
 time step) -- with the CUDA solver replaced by an oracle-backed stand-in on CPU tensors.  What the stand-in does per call
 is what the kernels are tested to do on the GPU (tests/test_gpu_parity.py); this test checks that the runtime calls them
@@ -49,6 +49,11 @@ class OracleSolver:
     def bind_timestep(self, dt):
         pass
 
+    def set_face_data(self, face, ops, data, mask=None):
+        """jxf_set_face_data: kept per face, applied after the base rule by halo_fill (helpers.apply_face_data_numpy)"""
+        self.face_data = getattr(self, "face_data", {})
+        self.face_data[port.FACES[face]] = (ops, data, mask)
+
     # "kernels"
     def cons_from_prims(self, prims, cons):
         with np.errstate(all="ignore"):
@@ -60,8 +65,12 @@ class OracleSolver:
         return s
 
     def halo_fill(self, prims, cons):
+        s = self.setup
         with np.errstate(all="ignore"):
-            p, c = port.halo_fill(prims.numpy(), cons.numpy(), self.setup)       # faces, then edges when dissipative
+            p, c = port.halo_fill(prims.numpy(), cons.numpy(), self._faces_only())     # the faces' base rules
+            p, c = H.apply_face_data_numpy(getattr(self, "face_data", {}), p, c, s.cells, s.nh, s.gamma)
+            if s.is_dissipative and len(s.active) > 1:                               # then the edges
+                p, c = port.edge_halo_fill(p, c, s)
         prims.copy_(torch.as_tensor(p))
         cons.copy_(torch.as_tensor(c))
 
@@ -81,7 +90,7 @@ class OracleSolver:
         self._last = prims.numpy().copy()
 
     def stage(self, k, p_in, p_out, c_in, c_n, c_out, rhs, dt, red, reduce=False, fill_halo=True):
-        assert not fill_halo, "the host-applied-boundary path must not ask for fused halo images"
+        assert fill_halo, "the stage carries the halo images (fused in the kernels; here: halo_fill after the update)"
         s, rk = self.setup, port.RK[self.setup.integrator]
         with np.errstate(all="ignore"):
             r = port.compute_rhs(p_in.numpy(), s, c_in.numpy(), float(dt.item()))
@@ -95,8 +104,20 @@ class OracleSolver:
             prims = port.prims_from_cons(cons, s.gamma)
         c_out.copy_(torch.as_tensor(cons))
         p_out.copy_(torch.as_tensor(prims))
+        self.halo_fill(p_out, c_out)
         if reduce:
-            self._last = prims.copy()
+            self._last = p_out.numpy().copy()
+
+    def step_fused(self, pa, pb, ca, cb, rhs, dt, time, red, info, fill_halo=True):
+        """jxf_step_fused: all stages on the ping-pong buffers, then the step scalars; returns the buffer parity"""
+        pr, cur = [pa, pb], 0
+        for k in range(self.stages):
+            last = k == self.stages - 1
+            self.stage(k, pr[cur], pr[cur ^ 1], ca if k == 0 else cb, ca, ca if last else cb, rhs, dt, red, reduce=last,
+                       fill_halo=fill_halo)
+            cur ^= 1
+        self.finish_step(red, dt, time, info)
+        return cur
 
     def finish_step(self, red, dt, time, info):
         s = self.setup
@@ -129,7 +150,7 @@ def test_public_api_on_cpu_with_oracle_backed_solver(name, monkeypatch):
     assert np.array_equal(mf.conservatives.numpy()[:, m], g["cons0_halo"][:, m])
     assert buffers.time_control_variables.physical_timestep_size == float(g["dt0"])
     sim = SimulationManager(im)
-    assert sim.runtime.host_boundaries and sim.runtime._host_halo
+    assert sim.runtime.face_data and not sim.runtime._host_halo
     sim.simulate(buffers)
     out = sim.final_buffers
     tcv = out.time_control_variables
