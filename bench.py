@@ -471,7 +471,7 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
             stagebuf[i % 2].copy_(host_state, non_blocking=True)
             up[i % 2].record(copy_stream)
 
-    def pipelined(state_back, host_out):
+    def pipelined(state_back, host_out, outbuf=None):
         nonlocal jb
         cur = torch.cuda.current_stream()
         for ev in free:
@@ -482,18 +482,20 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
             if k + 1 < k_pipe:
                 upload(k + 1)
             cur.wait_event(up[k % 2])
-            if back_done is not None:
-                cur.wait_event(back_done)              # the copy-back of the previous result reads a buffer this
-                back_done = None                       # step's device copy / stages are about to overwrite
             rt.primitives.copy_(stagebuf[k % 2], non_blocking=True)
             free[k % 2].record(cur)
             jb = one_step(jb)
             if state_back:
+                # result -> device staging buffer (fast), then D2H on the copy-back stream while the next step and the
+                # next upload run; the staging buffer is reused once its copy-back has finished
+                if back_done is not None:
+                    cur.wait_event(back_done)
+                outbuf.copy_(rt.primitives, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(cur)
                 with torch.cuda.stream(back_stream):
                     back_stream.wait_event(done)
-                    host_out.copy_(rt.primitives, non_blocking=True)
+                    host_out.copy_(outbuf, non_blocking=True)
                     back_done = torch.cuda.Event()
                     back_done.record(back_stream)
         if back_done is not None:
@@ -512,13 +514,14 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
                       "ms_per_step": ms_serial / k_e2e, "what": "same without any overlap (upload, then step)"}}
     try:
         host_out = torch.empty(tuple(rt.primitives.shape), dtype=torch.float64, pin_memory=True)
-        ms_back = timed(lambda: pipelined(True, host_out))
+        outbuf = torch.empty_like(rt.primitives)
+        ms_back = timed(lambda: pipelined(True, host_out, outbuf))
         e2e["state_back"] = {"value": cells_global * k_pipe / (ms_back * 1e-3) / 1e6, "unit": "MCUPS", "steps": k_pipe,
                              "ms_per_step": ms_back / k_pipe, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 40,
                              "what": "the pipelined leg with the step's halo'd primitive state ALSO copied back to pinned "
-                                     "host memory every step (copy-back stream, overlapping the next step; PCIe is full "
-                                     "duplex)"}
-        del host_out
+                                     "host memory every step (device staging copy, then D2H on a copy-back stream that "
+                                     "overlaps the next step and the next upload; PCIe is full duplex)"}
+        del host_out, outbuf
     except Exception as exc:
         e2e["state_back"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
     del stagebuf
