@@ -36,6 +36,59 @@ enum { SIG_EINFELDT = 0, SIG_ARITHMETIC = 1, SIG_RUSANOV = 2, SIG_DAVIS = 3, SIG
 // the RIEMANN_RUSANOV kernel instantiations like HLL: plain reference-order arithmetic in an out-of-line function.
 enum { RIEMANN_ALT_NONE = 0, RIEMANN_ALT_HLLCLM = 1 /* HLLCLM.py */, RIEMANN_ALT_AUSMP = 2 /* AUSMP.py */ };
 
+// ---------------------------------------------------------------------------
+// fast reciprocal / rsqrt / sqrt: MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 bits) + Newton.
+// Valid for normal, finite, positive-or-negative (rcp) / positive (rsqrt) arguments -- all
+// call sites divide by densities, sound speeds, wave-speed differences and WENO weight sums.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double rcp_fast(double a) {
+  // seed error e0 <= 2^-20 (measured 9.8e-7, tests/test_gpu_parity.py); one cubic step: x (1 + e + e^2),
+  // remaining error e0^3 ~ 1e-18
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  const double e = fma(-a, x, 1.0);
+  return fma(x, fma(e, e, e), x);
+}
+__device__ __forceinline__ double rsqrt_fast(double a) {
+  // seed error <= 2^-20; one cubic step y (1 + e/2 + 3 e^2/8), e = 1 - a y^2, remaining error ~ e^3
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-a * y, y, 1.0);
+  return fma(y, e * fma(0.375, e, 0.5), y);
+}
+#else
+__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
+__device__ __forceinline__ double rsqrt_fast(double a) { return 1.0 / sqrt(a); }
+#endif
+// sqrt(a) = a * rsqrt(a): y carries <= 2 ulp, the product <= 3 ulp -- these roots only feed wave-speed
+// estimates (a_K, d_bar), whose relative error enters the flux multiplied by the (small) jump
+__device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a) */) { return a * y; }
+
+// Division / reciprocal / square root / 10^-n of the GENERIC (reference-order) device functions -- the other stencils,
+// HLLC-LM / AUSM+ / HLL, the flux splitting, the conservative reconstruction variables.  On the device, in production
+// builds: MUFU seed + Newton (<= 1.5 ulp) instead of the IEEE division / sqrt sequences (~4x fewer instructions, no slow
+// path), and a table for the TENO-A cut-off 10^-n (n is a small integer by construction: ceil(.) - 1).  On the host
+// (tests/hostsim) and in JXF_REFERENCE_ORDER builds: the IEEE operations, i.e. bit-identical to the reference without
+// FMA contraction.  Denominators here are beta + 1e-30, sums of positive weights, densities, sound speeds, wave-speed
+// differences: normal, finite, non-zero.  (The MUSCL limiters keep IEEE division: their denominators can vanish.)
+#if defined(__CUDACC__) && !defined(JXF_REFERENCE_ORDER) && !defined(JXF_GENERIC_IEEE)
+__device__ __forceinline__ double gdiv(double a, double b) { return a * rcp_fast(b); }
+__device__ __forceinline__ double grcp(double b) { return rcp_fast(b); }
+__device__ __forceinline__ double gsqrt(double a) { return a * rsqrt_fast(a); }
+__device__ __forceinline__ double gpow10_neg(double n) {
+  // 10^-n, n integer-valued in [0, 15] (TENO5-A: 4..9, TENO6-A: 5..10): the correctly rounded decimal literals
+  const double t[16] = {1e0, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10, 1e-11, 1e-12, 1e-13, 1e-14, 1e-15};
+  const int i = (int)n;
+  return (i >= 0 && i < 16 && (double)i == n) ? t[i] : pow(10.0, -n);
+}
+#else
+__device__ __forceinline__ double gdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ double grcp(double b) { return 1.0 / b; }
+__device__ __forceinline__ double gsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double gpow10_neg(double n) { return pow(10.0, -n); }
+#endif
+
 // signal_speeds.py:10-69, :135-157 with estimate_pressure :201-214 -- the simple estimates, reference order.
 // OUT OF LINE: the tuned path is EINFELDT; keeping these (IEEE sqrt / divisions) out of the sweep loops keeps the
 // hot loops' size and register allocation what they are without them.
@@ -101,12 +154,12 @@ static __device__ JXF_NOINLINE double2 simple_signal_speeds(int sig, double uL, 
 // tuned path (the HLLC kernels carry their own fast evaluation of the same formula)
 static __device__ JXF_NOINLINE double2 einfeldt_signal_speeds(double uL, double uR, double aL, double aR, double rhoL,
                                                       double rhoR) {
-  const double sL = sqrt(rhoL), sR = sqrt(rhoR);
-  const double one_dens = 1.0 / (sL + sR);
+  const double sL = gsqrt(rhoL), sR = gsqrt(rhoR);
+  const double one_dens = grcp(sL + sR);
   const double eta2 = 0.5 * sL * sR * one_dens * one_dens;
   const double u_bar = (sL * uL + sR * uR) * one_dens;
   const double du = uR - uL;
-  const double d_bar = sqrt((sL * aL * aL + sR * aR * aR) * one_dens + eta2 * (du * du));
+  const double d_bar = gsqrt((sL * aL * aL + sR * aR * aR) * one_dens + eta2 * (du * du));
   double2 r;
   r.x = fmin(u_bar - d_bar, uL - aL);
   r.y = fmax(u_bar + d_bar, uR + aR);
@@ -135,14 +188,14 @@ template <> struct AxisIds<2> { static constexpr int un = 3, t0 = 1, t1 = 2; };
 //                    one formula, hence `j`)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double teno_a_eta(double a, double b, double eps_d) {
-  return (fabs(2.0 * a * b) + eps_d) / (a * a + b * b + eps_d);
+  return gdiv(fabs(2.0 * a * b) + eps_d, a * a + b * b + eps_d);
 }
 __device__ __forceinline__ double teno_a_ct(double eta, double Cr, double alpha_1, double alpha_2) {
-  const double m = 1.0 - fmin(1.0, eta / Cr);
+  const double m = 1.0 - fmin(1.0, gdiv(eta, Cr));
   const double x = 1.0 - m, x2 = x * x;
   const double g = (x2 * x2) * (1.0 + 4.0 * m);              // jnp.power(1 - m, 4) * (1 + 4 m)
   const double beta_bar = ceil(alpha_1 - alpha_2 * (1.0 - g)) - 1.0;
-  return pow(10.0, -beta_bar);
+  return gpow10_neg(beta_bar);
 }
 static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
                                                double q5) {
@@ -154,8 +207,8 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
     const double beta_0 = d0 * d0, beta_1 = d1 * d1;
     double alpha_0, alpha_1;
     if (id == ALT_WENO3JS) {
-      alpha_0 = (1.0 / 3.0) * (1.0 / (beta_0 * beta_0 + eps));
-      alpha_1 = (2.0 / 3.0) * (1.0 / (beta_1 * beta_1 + eps));
+      alpha_0 = (1.0 / 3.0) * grcp(beta_0 * beta_0 + eps);
+      alpha_1 = (2.0 / 3.0) * grcp(beta_1 * beta_1 + eps);
     } else {
       double tau_3 = fabs(beta_0 - beta_1);
       if (id == ALT_WENO3N) {
@@ -163,10 +216,10 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
         const double beta_3 = (13.0 / 12.0) * (s * s) + 0.25 * (t * t);
         tau_3 = fabs(0.5 * (beta_0 + beta_1) - beta_3);
       }
-      alpha_0 = (1.0 / 3.0) * (1.0 + tau_3 / (beta_0 + eps));
-      alpha_1 = (2.0 / 3.0) * (1.0 + tau_3 / (beta_1 + eps));
+      alpha_0 = (1.0 / 3.0) * (1.0 + gdiv(tau_3, beta_0 + eps));
+      alpha_1 = (2.0 / 3.0) * (1.0 + gdiv(tau_3, beta_1 + eps));
     }
-    const double one_alpha = 1.0 / (alpha_0 + alpha_1);
+    const double one_alpha = grcp(alpha_0 + alpha_1);
     const double p_0 = -0.5 * q1 + 1.5 * q2;
     const double p_1 = 0.5 * q2 + 0.5 * q3;
     return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1;
@@ -186,24 +239,24 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
       double alpha_0, alpha_1, alpha_2;
       if (id == ALT_WENO5Z) {
         const double tau_5 = fabs(beta_0 - beta_2);
-        alpha_0 = 0.1 * (1.0 + tau_5 / (beta_0 + eps));
-        alpha_1 = 0.6 * (1.0 + tau_5 / (beta_1 + eps));
-        alpha_2 = 0.3 * (1.0 + tau_5 / (beta_2 + eps));
+        alpha_0 = 0.1 * (1.0 + gdiv(tau_5, beta_0 + eps));
+        alpha_1 = 0.6 * (1.0 + gdiv(tau_5, beta_1 + eps));
+        alpha_2 = 0.3 * (1.0 + gdiv(tau_5, beta_2 + eps));
       } else {
-        alpha_0 = 0.1 * (1.0 / (beta_0 * beta_0 + eps));
-        alpha_1 = 0.6 * (1.0 / (beta_1 * beta_1 + eps));
-        alpha_2 = 0.3 * (1.0 / (beta_2 * beta_2 + eps));
+        alpha_0 = 0.1 * grcp(beta_0 * beta_0 + eps);
+        alpha_1 = 0.6 * grcp(beta_1 * beta_1 + eps);
+        alpha_2 = 0.3 * grcp(beta_2 * beta_2 + eps);
       }
-      const double one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2);
+      const double one_alpha = grcp(alpha_0 + alpha_1 + alpha_2);
       return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2;
     }
     if (id == ALT_TENO5 || id == ALT_TENO5A) {
       const double tau_5 = fabs(beta_0 - beta_2);
       // jnp.power(x, 6): the value only feeds the cut-off comparison below
-      const double x0 = 1.0 + tau_5 / (beta_0 + eps), x1 = 1.0 + tau_5 / (beta_1 + eps), x2 = 1.0 + tau_5 / (beta_2 + eps);
+      const double x0 = 1.0 + gdiv(tau_5, beta_0 + eps), x1 = 1.0 + gdiv(tau_5, beta_1 + eps), x2 = 1.0 + gdiv(tau_5, beta_2 + eps);
       const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2;
       const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2;
-      const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2);
+      const double one_gamma_sum = grcp(gamma_0 + gamma_1 + gamma_2);
       double CT = 1e-5, d0 = 0.05, d1 = 0.55, d2 = 0.40;
       if (id == ALT_TENO5A) {
         const double eps_d = 2.842105263157895e-07;          // 0.9 Cr / (1 - Cr) xi^2, Cr = 0.24, xi = 1e-3
@@ -215,7 +268,7 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
       const double w0 = d0 * ((gamma_0 * one_gamma_sum < CT) ? 0.0 : 1.0);
       const double w1 = d1 * ((gamma_1 * one_gamma_sum < CT) ? 0.0 : 1.0);
       const double w2 = d2 * ((gamma_2 * one_gamma_sum < CT) ? 0.0 : 1.0);
-      const double one_dk = 1.0 / (w0 + w1 + w2 + eps);
+      const double one_dk = grcp(w0 + w1 + w2 + eps);
       return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2;
     }
     const double beta_6 = 1.0 / 10080 / 12 * (
@@ -240,11 +293,11 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
         beta_6a = fabs(beta_6a);
       }
       const double tau_6 = fabs(beta_6a - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2));
-      const double x0 = 1.0 + tau_6 / (beta_0 + eps), x1 = 1.0 + tau_6 / (beta_1 + eps);
-      const double x2 = 1.0 + tau_6 / (beta_2 + eps), x3 = 1.0 + tau_6 / (beta_3 + eps);
+      const double x0 = 1.0 + gdiv(tau_6, beta_0 + eps), x1 = 1.0 + gdiv(tau_6, beta_1 + eps);
+      const double x2 = 1.0 + gdiv(tau_6, beta_2 + eps), x3 = 1.0 + gdiv(tau_6, beta_3 + eps);
       const double c0 = x0 * x0 * x0, c1 = x1 * x1 * x1, c2 = x2 * x2 * x2, c3 = x3 * x3 * x3;
       const double gamma_0 = c0 * c0, gamma_1 = c1 * c1, gamma_2 = c2 * c2, gamma_3 = c3 * c3;
-      const double one_gamma_sum = 1.0 / (gamma_0 + gamma_1 + gamma_2 + gamma_3);
+      const double one_gamma_sum = grcp(gamma_0 + gamma_1 + gamma_2 + gamma_3);
       double CT = 1e-7, d0 = 0.050, d1 = 0.450, d2 = 0.300, d3 = 0.200;
       if (adaptive) {
         const double eps_d = 1.8433734939759037e-07;         // 0.9 Cr / (1 - Cr) xi^2, Cr = 0.17, xi = 1e-3
@@ -260,17 +313,17 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
       const double w1 = d1 * ((gamma_1 * one_gamma_sum < CT) ? 0.0 : 1.0);
       const double w2 = d2 * ((gamma_2 * one_gamma_sum < CT) ? 0.0 : 1.0);
       const double w3 = d3 * ((gamma_3 * one_gamma_sum < CT) ? 0.0 : 1.0);
-      const double one_dk = adaptive ? 1.0 / (w0 + w1 + w2 + w3) : 1.0 / (w0 + w1 + w2 + w3 + eps);
+      const double one_dk = adaptive ? grcp(w0 + w1 + w2 + w3) : grcp(w0 + w1 + w2 + w3 + eps);
       return (w0 * one_dk) * p_0 + (w1 * one_dk) * p_1 + (w2 * one_dk) * p_2 + (w3 * one_dk) * p_3;
     }
     const double beta_3 = beta_6;       // weno6_base.py calls the six-point indicator beta_3
     const double p_3 = (11.0 / 6.0) * q3 + (-7.0 / 6.0) * q4 + (1.0 / 3.0) * q5;
     const double tau_6 = beta_3 - (1.0 / 6.0) * (beta_0 + 4.0 * beta_1 + beta_2);
-    const double alpha_0 = (1.0 / 20.0) * (20.0 + tau_6 / (beta_0 + eps));
-    const double alpha_1 = (9.0 / 20.0) * (20.0 + tau_6 / (beta_1 + eps));
-    const double alpha_2 = (9.0 / 20.0) * (20.0 + tau_6 / (beta_2 + eps));
-    const double alpha_3 = (1.0 / 20.0) * (20.0 + tau_6 / (beta_3 + eps));
-    const double one_alpha = 1.0 / (alpha_0 + alpha_1 + alpha_2 + alpha_3);
+    const double alpha_0 = (1.0 / 20.0) * (20.0 + gdiv(tau_6, beta_0 + eps));
+    const double alpha_1 = (9.0 / 20.0) * (20.0 + gdiv(tau_6, beta_1 + eps));
+    const double alpha_2 = (9.0 / 20.0) * (20.0 + gdiv(tau_6, beta_2 + eps));
+    const double alpha_3 = (1.0 / 20.0) * (20.0 + gdiv(tau_6, beta_3 + eps));
+    const double one_alpha = grcp(alpha_0 + alpha_1 + alpha_2 + alpha_3);
     return (alpha_0 * one_alpha) * p_0 + (alpha_1 * one_alpha) * p_1 + (alpha_2 * one_alpha) * p_2 +
            (alpha_3 * one_alpha) * p_3;
   }
@@ -301,7 +354,7 @@ struct Frozen {
 };
 __device__ __forceinline__ double total_enthalpy_ref(const double (&p)[5], double gamma) {   // ideal_gas.py:90-110
   const double E = p[4] / (gamma - 1.0) + 0.5 * p[0] * ((p[1] * p[1] + p[2] * p[2]) + p[3] * p[3]);
-  return (E + p[4]) / p[0];
+  return gdiv(E + p[4], p[0]);
 }
 __device__ __forceinline__ Frozen frozen_state(const double (&pL)[5], const double (&pR)[5], double gamma, int roe) {
   Frozen f;
@@ -310,24 +363,24 @@ __device__ __forceinline__ Frozen frozen_state(const double (&pL)[5], const doub
     for (int v = 0; v < 5; ++v) f.ave[v] = 0.5 * (pL[v] + pR[v]);
     f.G = gamma - 1.0;
     f.H = total_enthalpy_ref(f.ave, gamma);
-    f.c = sqrt(gamma * f.ave[4] / f.ave[0]);
+    f.c = gsqrt(gdiv(gamma * f.ave[4], f.ave[0]));
     f.cc = f.c * f.c;
     f.q2 = (f.ave[1] * f.ave[1] + f.ave[2] * f.ave[2]) + f.ave[3] * f.ave[3];
   } else {
-    const double sL = sqrt(pL[0]), sR = sqrt(pR[0]);
+    const double sL = gsqrt(pL[0]), sR = gsqrt(pR[0]);
 #pragma unroll
-    for (int v = 0; v < 5; ++v) f.ave[v] = (sL * pL[v] + sR * pR[v]) / (sL + sR);
-    f.ave[0] = sqrt(pL[0] * pR[0]);
-    const double rho_div = 1.0 / (sL + sR);
+    for (int v = 0; v < 5; ++v) f.ave[v] = gdiv(sL * pL[v] + sR * pR[v], sL + sR);
+    f.ave[0] = gsqrt(pL[0] * pR[0]);
+    const double rho_div = grcp(sL + sR);
     f.H = (sL * total_enthalpy_ref(pL, gamma) + sR * total_enthalpy_ref(pR, gamma)) * rho_div;
-    const double psi = (sL * (pL[4] / pL[0]) + sR * (pR[4] / pR[0])) * rho_div;
+    const double psi = (sL * gdiv(pL[4], pL[0]) + sR * gdiv(pR[4], pR[0])) * rho_div;
     f.G = (sL * (gamma - 1.0) + sR * (gamma - 1.0)) * rho_div;
     const double du = pR[1] - pL[1], dv = pR[2] - pL[2], dw = pR[3] - pL[3];
     const double dq2 = (du * du + dv * dv) + dw * dw;
-    const double p_over_rho = (sL * pL[4] / pL[0] + sR * pR[4] / pR[0]) * rho_div + 0.5 * f.ave[0] * rho_div * rho_div * dq2;
+    const double p_over_rho = (gdiv(sL * pL[4], pL[0]) + gdiv(sR * pR[4], pR[0])) * rho_div + 0.5 * f.ave[0] * rho_div * rho_div * dq2;
     f.q2 = (f.ave[1] * f.ave[1] + f.ave[2] * f.ave[2]) + f.ave[3] * f.ave[3];
     f.cc = psi + f.G * p_over_rho;
-    f.c = sqrt(f.cc);
+    f.c = gsqrt(f.cc);
   }
   return f;
 }
@@ -359,9 +412,9 @@ __device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], dou
     const double rho_ave = fz.ave[0];
     const double c_ave = fz.c;
     const double cc_ave = fz.cc;
-    const double k_u = 0.5 / c_ave;
-    const double k_p = 0.5 / (cc_ave * rho_ave);
-    const double k_cc = 1.0 / cc_ave;
+    const double k_u = gdiv(0.5, c_ave);
+    const double k_p = gdiv(0.5, cc_ave * rho_ave);
+    const double k_cc = grcp(cc_ave);
     double q[6], l0, r0, l1, r1, l4, r4;
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = -k_u * w[Id::un][k] + k_p * w[4][k];
@@ -500,9 +553,9 @@ __device__ __forceinline__ void reconstruct(const double (&w)[5][6], double gamm
     const double p_ave = 0.5 * (w[4][2] + w[4][3]);
     const double c_ave = sqrt(gamma * p_ave / rho_ave);
     const double cc_ave = c_ave * c_ave;
-    const double k_u = 0.5 / c_ave;
-    const double k_p = 0.5 / (cc_ave * rho_ave);
-    const double k_cc = 1.0 / cc_ave;
+    const double k_u = gdiv(0.5, c_ave);
+    const double k_p = gdiv(0.5, cc_ave * rho_ave);
+    const double k_cc = grcp(cc_ave);
     double q[6], l0, r0, l1, r1, l4, r4;
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = -k_u * w[Id::un][k] + k_p * w[4][k];
@@ -623,35 +676,6 @@ __device__ __forceinline__ void riemann_flux(const double (&pl)[5], const double
 #ifndef JXF_RIEMANN_MAIN       // marching sweeps: 1 = branch-free short-chain Riemann solve + rare S* = 0 fix-up
 #define JXF_RIEMANN_MAIN 0
 #endif
-
-// ---------------------------------------------------------------------------
-// fast reciprocal / rsqrt / sqrt: MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 bits) + Newton.
-// Valid for normal, finite, positive-or-negative (rcp) / positive (rsqrt) arguments -- all
-// call sites divide by densities, sound speeds, wave-speed differences and WENO weight sums.
-// ---------------------------------------------------------------------------
-#ifdef __CUDACC__
-__device__ __forceinline__ double rcp_fast(double a) {
-  // seed error e0 <= 2^-20 (measured 9.8e-7, tests/test_gpu_parity.py); one cubic step: x (1 + e + e^2),
-  // remaining error e0^3 ~ 1e-18
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  const double e = fma(-a, x, 1.0);
-  return fma(x, fma(e, e, e), x);
-}
-__device__ __forceinline__ double rsqrt_fast(double a) {
-  // seed error <= 2^-20; one cubic step y (1 + e/2 + 3 e^2/8), e = 1 - a y^2, remaining error ~ e^3
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double e = fma(-a * y, y, 1.0);
-  return fma(y, e * fma(0.375, e, 0.5), y);
-}
-#else
-__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
-__device__ __forceinline__ double rsqrt_fast(double a) { return 1.0 / sqrt(a); }
-#endif
-// sqrt(a) = a * rsqrt(a): y carries <= 2 ulp, the product <= 3 ulp -- these roots only feed wave-speed
-// estimates (a_K, d_bar), whose relative error enters the flux multiplied by the (small) jump
-__device__ __forceinline__ double sqrt_fast(double a, double y /* = rsqrt_fast(a) */) { return a * y; }
 
 // ---------------------------------------------------------------------------
 // WENO5-Z on the five first differences d_i = q_{i+1} - q_i of the 6-cell window
@@ -1179,8 +1203,8 @@ __device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR
   double cl[5], cr[5];
   cons_from_prims(pl, gamma, cl);
   cons_from_prims(pr, gamma, cr);
-  const double aL = sqrt(gamma * pl[4] / pl[0]);
-  const double aR = sqrt(gamma * pr[4] / pr[0]);
+  const double aL = gsqrt(gdiv(gamma * pl[4], pl[0]));
+  const double aR = gsqrt(gdiv(gamma * pr[4], pr[0]));
   const double uL = pl[Id::un], uR = pr[Id::un];
   Vec5 out;
   if (variant == RIEMANN_ALT_HLLCLM) {
@@ -1189,25 +1213,25 @@ __device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR
     const double S_L = ss.x, S_R = ss.y;
     const double dL = pl[0] * (S_L - uL);
     const double dR = pr[0] * (S_R - uR);
-    const double S_s = ((pr[4] - pl[4]) + (uL * dL - uR * dR)) / (dL - dR);
+    const double S_s = gdiv((pr[4] - pl[4]) + (uL * dL - uR * dR), dL - dR);
     double usL[5], usR[5];
     {
-      const double pre = (S_L - uL) / (S_L - S_s) * pl[0];
+      const double pre = gdiv(S_L - uL, S_L - S_s) * pl[0];
       usL[0] = pre;
       usL[Id::un] = pre * S_s;
       usL[Id::t0] = pre * pl[Id::t0];
       usL[Id::t1] = pre * pl[Id::t1];
-      usL[4] = pre * (cl[4] / cl[0] + (S_s - uL) * (S_s + pl[4] / pl[0] / (S_L - uL)));
+      usL[4] = pre * (gdiv(cl[4], cl[0]) + (S_s - uL) * (S_s + gdiv(gdiv(pl[4], pl[0]), S_L - uL)));
     }
     {
-      const double pre = (S_R - uR) / (S_R - S_s) * pr[0];
+      const double pre = gdiv(S_R - uR, S_R - S_s) * pr[0];
       usR[0] = pre;
       usR[Id::un] = pre * S_s;
       usR[Id::t0] = pre * pr[Id::t0];
       usR[Id::t1] = pre * pr[Id::t1];
-      usR[4] = pre * (cr[4] / cr[0] + (S_s - uR) * (S_s + pr[4] / pr[0] / (S_R - uR)));
+      usR[4] = pre * (gdiv(cr[4], cr[0]) + (S_s - uR) * (S_s + gdiv(gdiv(pr[4], pr[0]), S_R - uR)));
     }
-    const double Ma_local = fmax(fabs(uL / aL), fabs(uR / aR));
+    const double Ma_local = fmax(fabs(gdiv(uL, aL)), fabs(gdiv(uR, aR)));
     const double phi = sin(fmin(1.0, Ma_local / 0.1) * 3.141592653589793 * 0.5);
     const double wL = phi * S_L, wR = phi * S_R;
     double fL[5], fR[5];
@@ -1225,7 +1249,7 @@ __device__ JXF_NOINLINE Vec5 riemann_other(int variant, int sp, Vec5 PL, Vec5 PR
   } else {   // RIEMANN_ALT_AUSMP
     const double alpha = 3.0 / 16.0, beta = 1.0 / 8.0;
     const double a = 0.5 * (aL + aR);
-    const double M_l = uL / a, M_r = uR / a;
+    const double M_l = gdiv(uL, a), M_r = gdiv(uR, a);
     const double ql = M_l * M_l - 1.0, qr = M_r * M_r - 1.0;
     const double M_plus = (fabs(M_l) >= 1.0) ? 0.5 * (M_l + fabs(M_l))
                                              : 0.25 * ((M_l + 1.0) * (M_l + 1.0)) + beta * (ql * ql);
@@ -1267,7 +1291,7 @@ __device__ __forceinline__ void conservative_eigenvectors(const Frozen& fz, doub
   using Id = AxisIds<A>;
   const double (&ave)[5] = fz.ave;
   const double H = fz.H, G = fz.G, c = fz.c, cc = fz.cc, q2 = fz.q2;
-  const double one_cc = 1.0 / cc, one_rho = 1.0 / ave[0];
+  const double one_cc = grcp(cc), one_rho = grcp(ave[0]);
   const int ua = Id::un, m0 = Id::t0, m1 = Id::t1;
 #pragma unroll
   for (int i = 0; i < 5; ++i)
@@ -1335,7 +1359,7 @@ __device__ JXF_NOINLINE Vec5 flux_splitting_flux(Win6 W, double gamma, int id, i
     lam[1] = fabs(ave[ua]);
     lam[4] = fabs(ave[ua] + c);
   } else {
-    const double cL = sqrt(gamma * pL[4] / pL[0]), cR = sqrt(gamma * pR[4] / pR[0]);
+    const double cL = gsqrt(gdiv(gamma * pL[4], pL[0])), cR = gsqrt(gdiv(gamma * pR[4], pR[0]));
     if (fs == FS_CLLF) {
       lam[0] = fmax(fabs(pL[ua] - cL), fabs(pR[ua] - cR));
       lam[1] = fmax(fabs(pL[ua]), fabs(pR[ua]));

@@ -235,3 +235,72 @@ def test_inplace_memory_plan_through_public_api(monkeypatch):
     mask = H.face_halo_mask(s)
     assert np.array_equal(out["pingpong"][0][:, mask], out["inplace"][0][:, mask])
     assert out["pingpong"][1:] == out["inplace"][1:]
+
+
+def test_callbacks_are_called_with_the_reference_hook_names(monkeypatch):
+    """SimulationManager(callbacks=[...]) (simulation_manager.py:179-184, callbacks/base_callback.py): every hook fires the
+    reference's number of times, identity hooks leave the result bit-identical to a run without callbacks, a hook that
+    edits the buffers is honoured, after_compute_rhs is refused."""
+    import bench
+    from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
+    from jaxfluids_b200.callbacks import Callback
+
+    class Count(Callback):
+        def __init__(self):
+            self.n = {}
+
+        def _hit(self, k):
+            self.n[k] = self.n.get(k, 0) + 1
+
+        def on_simulation_start(self, jxf_buffers, callback_dict, **kw):
+            self._hit("sim_start"); return jxf_buffers, callback_dict
+
+        def on_simulation_end(self, jxf_buffers, callback_dict, **kw):
+            self._hit("sim_end"); return jxf_buffers, callback_dict
+
+        def before_step_start(self, jxf_buffers, callback_dict, **kw):
+            self._hit("before"); return jxf_buffers, callback_dict
+
+        def after_step_end(self, jxf_buffers, callback_dict, **kw):
+            self._hit("after"); return jxf_buffers, callback_dict
+
+        def on_step_start(self, jxf_buffers, callback_dict, **kw):
+            self._hit("step_start"); return jxf_buffers, callback_dict
+
+        def on_step_end(self, jxf_buffers, callback_dict, **kw):
+            self._hit("step_end"); return jxf_buffers, callback_dict
+
+        def on_stage_start(self, conservatives, primitives, **kw):
+            self._hit("stage_start"); return conservatives, primitives
+
+        def on_stage_end(self, conservatives, primitives, **kw):
+            self._hit("stage_end"); return conservatives, primitives
+
+    def run(cbs):
+        case, num = bench.tgv_case(24, (1, 1, 1), end_step=3, bc="PERIODIC")
+        im = InputManager(case, num)
+        buf = InitializationManager(im).initialization()
+        sim = SimulationManager(im, callbacks=cbs)
+        sim.simulate(buf)
+        fb = sim.final_buffers
+        return host(fb.simulation_buffers.material_fields.primitives).copy(), fb.time_control_variables
+
+    base, tcv0 = run(None)
+    cb = Count()
+    got, tcv1 = run([cb])
+    assert cb.n == {"sim_start": 1, "sim_end": 1, "before": 3, "after": 3, "step_start": 3, "step_end": 3,
+                    "stage_start": 9, "stage_end": 9}
+    mask = H.face_halo_mask(H.make_setup((24, 24, 24)))
+    assert np.array_equal(base[:, mask], got[:, mask]) and tcv0 == tcv1
+
+    class Damp(Callback):                       # a hook that edits the state: returns NEW tensors, like a JAX callback would
+        def on_stage_end(self, conservatives, primitives, **kw):
+            return conservatives * 1.0, primitives * 1.0
+    got2, _ = run(Damp())
+    assert np.array_equal(base[:, mask], got2[:, mask])
+
+    class Rhs(Callback):
+        def after_compute_rhs(self, rhs_buffers, **kw):
+            return rhs_buffers
+    with pytest.raises(NotImplementedError, match="after_compute_rhs"):
+        run([Rhs()])

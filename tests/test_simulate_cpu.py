@@ -40,8 +40,11 @@ class StubRuntime:
         self.dt *= 0.5
         self.steps += 1
 
-    def read_step_scalars(self):
+    def read_step_scalars(self, complete_halos=False):
         return self.t, self.dt, 3.0, 0.125, 0.1
+
+    def complete_halos(self):
+        pass
 
     def temperature(self, prims):
         return None
