@@ -918,64 +918,88 @@ __device__ __forceinline__ void recon_carry_init(const double (&w)[5][6], ReconC
   }
 }
 
+// weights of the face's RIGHT cell (window cell 3) for the as-is fields
+template <int A, int RECON>
+__device__ __forceinline__ void recon_g_right(const double (&w)[5][6], ReconCarry<RECON>& gr) {
+  using Id = AxisIds<A>;
+  if constexpr ((RECON >> 1) != STENCIL_GENERIC) {
+#pragma unroll
+    for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+      const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+      gr.g[j] = weno5z_g<(RECON >> 1)>(w[v][2] - w[v][1], w[v][3] - w[v][2], w[v][4] - w[v][3], w[v][5] - w[v][4]);
+    }
+  }
+}
+
+// reconstruct() with the cell-centred weights of the as-is fields GIVEN: gl = those of window cell 2 (left stencil of
+// this face), gr = those of window cell 3 (right stencil).  Marching sweeps carry gr of one face to gl of the next in
+// registers (reconstruct_carry); sweeps whose lanes are consecutive faces (sweep_rows) get gl from the lane before by
+// warp shuffle -- either way every cell's weights are evaluated once.  Tuned stencils only.
+template <int A, int RECON>
+__device__ __forceinline__ void reconstruct_given(const double (&w)[5][6], double gamma, double (&pl)[5], double (&pr)[5],
+                                                  const ReconCarry<RECON>& gl, const ReconCarry<RECON>& gr) {
+  using Id = AxisIds<A>;
+#pragma unroll
+  for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
+    const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
+    const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
+                 d4 = w[v][5] - w[v][4];
+    pl[v] = w[v][2] + weno5z_left_corr(gl.g[j], d0, d1, d2, d3);
+    pr[v] = w[v][3] + weno5z_right_corr(gr.g[j], d1, d2, d3, d4);
+  }
+  if ((RECON & 1) != RECON_PRIMITIVE) {
+    double dr[5], du[5], dp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      dr[k] = w[0][k + 1] - w[0][k];
+      du[k] = w[Id::un][k + 1] - w[Id::un][k];
+      dp[k] = w[4][k + 1] - w[4][k];
+    }
+    const double rho_ave = fma(0.5, dr[2], w[0][2]);
+    const double p_ave = fma(0.5, dp[2], w[4][2]);
+    const double gp = gamma * p_ave;
+    const double z = rsqrt_fast(gp * rho_ave);
+    const double ic = rho_ave * z;
+    const double c_ave = gp * z;
+    const double k_u = 0.5 * ic;
+    const double k_cc = ic * ic;
+    const double k_p = k_u * z;
+    double l0, r0, l1, r1, l4, r4;
+    {
+      double a[5], b[5], c[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double t = k_p * dp[k];
+        a[k] = fma(-k_u, du[k], t);
+        c[k] = fma(k_u, du[k], t);
+        b[k] = fma(-k_cc, dp[k], dr[k]);
+      }
+      weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
+      weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
+      weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
+    }
+    const double sl = l0 + l4, sr = r0 + r4;
+    pl[0] = w[0][2] + fma(rho_ave, sl, l1);
+    pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
+    pl[4] = fma(gp, sl, w[4][2]);
+    pr[0] = w[0][3] + fma(rho_ave, sr, r1);
+    pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
+    pr[4] = fma(gp, sr, w[4][3]);
+  }
+}
+
 // reconstruct() for marching sweeps: `cy` holds, on entry, the weights of window cell 2 (left stencil
 // of this face); on exit those of window cell 3 (right stencil of this face = left stencil of the next)
 template <int A, int RECON>
 __device__ __forceinline__ void reconstruct_carry(const double (&w)[5][6], double gamma, double (&pl)[5],
                                                   double (&pr)[5], ReconCarry<RECON>& cy, int alt = 0, int mode = 0) {
-  using Id = AxisIds<A>;
   if constexpr ((RECON >> 1) == STENCIL_GENERIC) {
     reconstruct<A, RECON>(w, gamma, pl, pr, alt, mode);
   } else {
-#pragma unroll
-    for (int j = 0; j < ReconCarry<RECON>::N; ++j) {
-      const int v = ((RECON & 1) == RECON_PRIMITIVE) ? j : (j == 0 ? Id::t0 : Id::t1);
-      const double d0 = w[v][1] - w[v][0], d1 = w[v][2] - w[v][1], d2 = w[v][3] - w[v][2], d3 = w[v][4] - w[v][3],
-                   d4 = w[v][5] - w[v][4];
-      pl[v] = w[v][2] + weno5z_left_corr(cy.g[j], d0, d1, d2, d3);
-      const WenoG gn = weno5z_g<(RECON >> 1)>(d1, d2, d3, d4);
-      pr[v] = w[v][3] + weno5z_right_corr(gn, d1, d2, d3, d4);
-      cy.g[j] = gn;
-    }
-    if ((RECON & 1) != RECON_PRIMITIVE) {
-      double dr[5], du[5], dp[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        dr[k] = w[0][k + 1] - w[0][k];
-        du[k] = w[Id::un][k + 1] - w[Id::un][k];
-        dp[k] = w[4][k + 1] - w[4][k];
-      }
-      const double rho_ave = fma(0.5, dr[2], w[0][2]);
-      const double p_ave = fma(0.5, dp[2], w[4][2]);
-      const double gp = gamma * p_ave;
-      const double z = rsqrt_fast(gp * rho_ave);
-      const double ic = rho_ave * z;
-      const double c_ave = gp * z;
-      const double k_u = 0.5 * ic;
-      const double k_cc = ic * ic;
-      const double k_p = k_u * z;
-      double l0, r0, l1, r1, l4, r4;
-      {
-        double a[5], b[5], c[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const double t = k_p * dp[k];
-          a[k] = fma(-k_u, du[k], t);
-          c[k] = fma(k_u, du[k], t);
-          b[k] = fma(-k_cc, dp[k], dr[k]);
-        }
-        weno5_corr<(RECON >> 1)>(a[0], a[1], a[2], a[3], a[4], l0, r0);
-        weno5_corr<(RECON >> 1)>(b[0], b[1], b[2], b[3], b[4], l1, r1);
-        weno5_corr<(RECON >> 1)>(c[0], c[1], c[2], c[3], c[4], l4, r4);
-      }
-      const double sl = l0 + l4, sr = r0 + r4;
-      pl[0] = w[0][2] + fma(rho_ave, sl, l1);
-      pl[Id::un] = fma(c_ave, l4 - l0, w[Id::un][2]);
-      pl[4] = fma(gp, sl, w[4][2]);
-      pr[0] = w[0][3] + fma(rho_ave, sr, r1);
-      pr[Id::un] = fma(c_ave, r4 - r0, w[Id::un][3]);
-      pr[4] = fma(gp, sr, w[4][3]);
-    }
+    ReconCarry<RECON> gn;
+    recon_g_right<A, RECON>(w, gn);
+    reconstruct_given<A, RECON>(w, gamma, pl, pr, cy, gn);
+    cy = gn;
   }
 }
 
@@ -1595,6 +1619,17 @@ __device__ __forceinline__ void face_flux(const double (&w)[5][6], double gamma,
   riemann_flux<A, RIEMANN>(pl, pr, gamma, F, sig);
   apply_flux_limiter<A>(w, gamma, F, opt, fl);
 }
+
+#ifndef JXF_REFERENCE_ORDER
+// the option-free face flux with the as-is fields' weights given (sweep_rows' lane carry); tuned stencils, HLLC_PLAIN
+template <int A, int RECON>
+__device__ __forceinline__ void face_flux_given(const double (&w)[5][6], double gamma, double (&F)[5],
+                                                const ReconCarry<RECON>& gl, const ReconCarry<RECON>& gr) {
+  double pl[5], pr[5];
+  reconstruct_given<A, RECON>(w, gamma, pl, pr, gl, gr);
+  riemann_flux<A, RIEMANN_HLLC>(pl, pr, gamma, F, SIG_EINFELDT);
+}
+#endif
 
 #ifdef JXF_REFERENCE_ORDER
 template <int A, int RIEMANN>

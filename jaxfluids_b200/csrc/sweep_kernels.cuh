@@ -675,6 +675,9 @@ struct RowsArgs {
   int tma_dim1_is_role;   // which role (1 or 2) is TMA dimension 1 (the faster transverse axis): always role 2
 };
 
+#ifndef JXF_ROWS_LANE_CARRY
+#define JXF_ROWS_LANE_CARRY 0
+#endif
 #ifndef JXF_ROWS_V1      // -DJXF_ROWS_V1: the round-1 form of the loop (A/B builds)
 // Loop structure (round 2): rows and iterations are nested loops, so that the iteration body is ONE straight-line
 // block -- no `it == 0` / `act` / `j + 1 < total` branches around the flux arithmetic, the TMA issue is predicated
@@ -711,6 +714,13 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
   Red red;
   red.init();
   const int prev_lane = (lane + 31) & 31;
+#if !defined(JXF_REFERENCE_ORDER) && JXF_ROWS_LANE_CARRY
+  // lane carry of the cell-centred WENO weights: the option-free tuned instantiations only
+  constexpr bool kLaneCarry = (RIEMANN == RIEMANN_HLLC_PLAIN) && ((RECON >> 1) != STENCIL_GENERIC);
+  // lane 0's carries (the previous iteration's lane-31 weights) live in shared memory, not in registers of all lanes
+  __shared__ double gcarry_s[4][16];
+  double* const gcs = gcarry_s[wid];
+#endif
 
   // stage the window of (row (i1n, i2n), iteration itn) into buffer b; `on` = false posts nothing (past the end)
   auto issue = [&](int b, int itn, int i1n, int i2n, bool on) {
@@ -804,6 +814,28 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
 #pragma unroll
             for (int k = 0; k < 6; ++k) w[v][k] = wl[v * kWinSlots + k];
           // (idle tail lanes see the zero-filled end of the window: their NaN result is never used or stored)
+#if !defined(JXF_REFERENCE_ORDER) && JXF_ROWS_LANE_CARRY
+          if constexpr (kLaneCarry) {
+            // cell-centred WENO weights of the as-is fields: this lane evaluates those of its face's RIGHT cell; the LEFT
+            // cell's are the right-cell weights of the lane before (rotate-shuffle; lane 0: lane 31's of the previous
+            // iteration, or -- first iteration of a row -- its own evaluation)
+            ReconCarry<RECON> gr, gl;
+            recon_g_right<A, RECON>(w, gr);
+#pragma unroll
+            for (int q = 0; q < ReconCarry<RECON>::N; ++q) {
+              const double r0 = __shfl_sync(0xffffffffu, gr.g[q].g0, prev_lane);
+              const double r1 = __shfl_sync(0xffffffffu, gr.g[q].g1, prev_lane);
+              const double r2 = __shfl_sync(0xffffffffu, gr.g[q].g2, prev_lane);
+              gl.g[q].g0 = r0; gl.g[q].g1 = r1; gl.g[q].g2 = r2;
+              if (lane == 0) {           // take the carry, leave lane 31's weights of this iteration as the next one
+                gl.g[q].g0 = gcs[3 * q]; gl.g[q].g1 = gcs[3 * q + 1]; gl.g[q].g2 = gcs[3 * q + 2];
+                gcs[3 * q] = r0; gcs[3 * q + 1] = r1; gcs[3 * q + 2] = r2;
+              }
+            }
+            if (it == 0 && lane == 0) recon_carry_init<A, RECON>(w, gl);      // the row's first cell: nobody's right cell
+            face_flux_given<A, RECON>(w, a.gamma, F, gl, gr);
+          } else
+#endif
           face_flux<A, RECON, RIEMANN>(w, a.gamma, F, a.limiter, a.fl);
         }
         double rr[5];
