@@ -512,6 +512,10 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
                    "min p: 40 B) -- the state stays on the device; PCIe-bound (the upload)",
            "serial": {"value": cells_global * k_e2e / (ms_serial * 1e-3) / 1e6, "steps": k_e2e,
                       "ms_per_step": ms_serial / k_e2e, "what": "same without any overlap (upload, then step)"}}
+    if world > 1:      # one more pinned buffer per rank: kept to single-GPU runs (8 ranks would pin 2 x 46 GB of host memory)
+        e2e["state_back"] = {"value": None, "skipped": "measured at N = 1 only"}
+        del stagebuf
+        return e2e
     try:
         host_out = torch.empty(tuple(rt.primitives.shape), dtype=torch.float64, pin_memory=True)
         outbuf = torch.empty_like(rt.primitives)

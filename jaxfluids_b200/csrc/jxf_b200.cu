@@ -507,6 +507,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   s->no_march = getenv("JXF_NO_MARCH") && atoi(getenv("JXF_NO_MARCH")) != 0;
 #endif
   s->rows_group = getenv("JXF_ROWS_G") ? std::max(0, std::min(32, atoi(getenv("JXF_ROWS_G")))) : 0;
+  s->no_tma_in = getenv("JXF_NO_TMA_IN") && atoi(getenv("JXF_NO_TMA_IN")) != 0;   // A/B: per-lane loads of the cell inputs
   s->no_plain = getenv("JXF_NO_PLAIN") && atoi(getenv("JXF_NO_PLAIN")) != 0;   // A/B: option-carrying instantiations
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
   s->n_maps = 0;
@@ -636,6 +637,32 @@ const CUtensorMap* get_rows_map(jxf_solver* s, const double* base) {
   s->map_ptr[slot] = base;
   if (s->n_maps < 8) s->n_maps++;
   return &s->map[slot];
+}
+
+// Tensor maps of the CELL INPUTS of the rows kernel's epilogue (sweep_kernels.cuh, RowsArgs::tma_in): a halo'd
+// conservative buffer with a box of kInCells cells x 5 variables, or the interior-only (or slab-sized) rhs accumulator
+// with a box of 32 cells x 5 variables.  Encoded per launch into the caller's storage (a few microseconds of host
+// time); false when TMA cannot describe the buffer (odd extents: the per-lane loads are used instead).
+bool encode_rows_input_map(const jxf_solver* s, CUtensorMap* out, const double* base, bool is_rhs, int rhs_planes,
+                           long long rhs_vst) {
+  PFN_encodeTiled enc = get_encode_fn();
+  const Geom& g = s->g;
+  if (!enc || !s->tma_ok || s->lane_axis != 2 || ((uintptr_t)base % 16) != 0) return false;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4] = {(cuuint32_t)(is_rhs ? 32 : kInCells), 1, 1, 5};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (is_rhs) {
+    if ((g.n[2] % 2) != 0 || (rhs_vst % 2) != 0) return false;
+    dims[0] = g.n[2]; dims[1] = g.n[1]; dims[2] = rhs_planes; dims[3] = 5;
+    strides[0] = (cuuint64_t)g.n[2] * 8; strides[1] = (cuuint64_t)g.n[1] * g.n[2] * 8; strides[2] = (cuuint64_t)rhs_vst * 8;
+  } else {
+    if ((g.ext[2] % 2) != 0 || (g.vst % 2) != 0) return false;
+    dims[0] = g.ext[2]; dims[1] = g.ext[1]; dims[2] = g.ext[0]; dims[3] = 5;
+    strides[0] = (cuuint64_t)g.ext[2] * 8; strides[1] = (cuuint64_t)g.ext[1] * g.ext[2] * 8; strides[2] = (cuuint64_t)g.vst * 8;
+  }
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------

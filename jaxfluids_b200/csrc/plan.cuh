@@ -41,6 +41,7 @@ struct jxf_solver {
   FaceData face_data;  // jxf_set_face_data: device pointers owned by the caller
   int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
+  bool no_tma_in;      // JXF_NO_TMA_IN=1: the rows kernel's epilogue loads its cell inputs per lane (A/B only)
   bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
   int n_maps;
@@ -75,6 +76,8 @@ struct ProfScope {
 
 // TMA descriptor of a halo'd field buffer for the rows kernel (nullptr: use the cp.async loader); jxf_b200.cu
 const CUtensorMap* get_rows_map(jxf_solver* s, const double* base);
+bool encode_rows_input_map(const jxf_solver* s, CUtensorMap* out, const double* base, bool is_rhs, int rhs_planes,
+                           long long rhs_vst);
 
 inline void set_role_bcs(SweepGeom& sg, const SweepArgs& a) {
   sg.bcA_hi = a.bc[2 * sg.axA]; sg.bcA_lo = a.bc[2 * sg.axA + 1];
@@ -189,13 +192,25 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       const long long groups = (rows + G - 1) / G;
       const long long blocks = std::min<long long>((groups + 3) / 4, 1LL << 30);
       const CUtensorMap* map = get_rows_map(const_cast<jxf_solver*>(s), a.prims - h0 - (slab ? (long long)a.sub_lo * g.st[0] : 0));
+      // the epilogue's cell inputs (U, U^n, the earlier axes' rhs sum) staged by TMA next to the windows
+      RowsInMaps im;
+      memset(&im, 0, sizeof(im));
+      ra.tma_in = 0;
+      ra.lead = g.off[A] & 1;             // the U / U^n boxes start `lead` cells before the iteration's first cell (16 B)
+      if (EPI && map && !s->no_tma_in && a.has_prev && a.rhs && a.cons_in) {
+        const long long slab_off = slab ? (long long)a.sub_lo * g.st[0] : 0;
+        bool ok = encode_rows_input_map(s, &im.u, a.cons_in - h0 - slab_off, false, 0, 0) &&
+                  encode_rows_input_map(s, &im.rhs, a.rhs, true, slab ? a.sub_n : g.n[0], sg.rvst);
+        if (ok && a.blend) ok = a.cons_n && encode_rows_input_map(s, &im.un, a.cons_n - h0 - slab_off, false, 0, 0);
+        ra.tma_in = ok ? 1 : 0;
+      }
       ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
       if (map) {
-        sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map);
+        sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map, im);
       } else {
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
-        sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy);
+        sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy, im);
       }
       return check_launch("sweep_rows");
     }

@@ -673,6 +673,19 @@ struct RowsArgs {
   int c1_off, c2_off;     // halo offsets of the two transverse roles in TMA coordinates
   int cA_off;             // halo offset of the sweep axis
   int tma_dim1_is_role;   // which role (1 or 2) is TMA dimension 1 (the faster transverse axis): always role 2
+  int tma_in;             // EPI: the cell inputs (U, U^n, rhs sum) are staged by TMA too (RowsInMaps), not loaded per lane
+  int lead;               // ... their U / U^n boxes start `lead` (0 / 1) cells before the iteration's first cell
+};
+
+// Tensor maps of the epilogue's cell inputs (plan.cuh encode_rows_input_map): boxes of kInCells (U, U^n; halo'd
+// conservative buffers) / 32 (rhs accumulator) cells x 5 variables, landing in the per-warp input buffers
+constexpr int kInCells = 34;                    // 32 cells + lead, rounded to a 16-byte multiple
+constexpr int kInUBytes = 5 * kInCells * 8;     // 1360
+constexpr int kInRBytes = 5 * 32 * 8;           // 1280
+constexpr int kInUStride = 1408;                // 128-byte multiples (TMA destination alignment)
+constexpr int kInStride = 2 * kInUStride + kInRBytes;   // 4096: U | U^n | rhs
+struct RowsInMaps {
+  CUtensorMap u, un, rhs;
 };
 
 #ifndef JXF_ROWS_LANE_CARRY
@@ -686,9 +699,13 @@ struct RowsArgs {
 // variable (lane l <- lane l-1, lane 0 <- lane 31 = the carry of the next iteration).
 template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
 __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
-sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
+sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap,
+           const __grid_constant__ RowsInMaps im) {
   __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
   __shared__ alignas(8) uint64_t bars[4 * 2];
+  // cell inputs of the epilogue (U, U^n, rhs sum), staged by TMA with the windows: 2 x 4 KB per warp
+  constexpr bool kTmaIn = (EPI != 0) && (USE_TMA != 0);
+  __shared__ alignas(128) unsigned char in_raw[kTmaIn ? 4 * 2 * kInStride : 16];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -698,6 +715,8 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
   const long long ngroups = (nrows + G - 1) / G;
   const int ipr = ra.iters_per_row;
   const int nA = g.nA;
+  const bool tma_in = kTmaIn && ra.tma_in;
+  const uint32_t in_s = smem_u32(in_raw) + (kTmaIn ? wid * 2 * kInStride : 0);
   const double step = (EPI ? (*a.dt) * a.dt_mult : 0.0);
   unsigned char* const win0 = win_raw + wid * 2 * kWinStride;      // this warp's two window buffers
   uint64_t* const bar0 = &bars[wid * 2];
@@ -729,6 +748,8 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
       // cells past the end of the row are zero-filled by the TMA unit.  One elected lane, predicated (no branch).
       const int c0 = ra.cA_off + 32 * itn - ra.shift, c1 = ra.c2_off + i2n, c2 = ra.c1_off + i1n;
       const uint32_t bar = bar_s + 8u * b, dst = win_s + (uint32_t)kWinStride * b;
+      const int pred = (int)(on && lane == 0);
+      const int tx = kWinBytes + (tma_in ? kInUBytes + kInRBytes + (EpiFlags<EPI>::blend(a) ? kInUBytes : 0) : 0);
       asm volatile(
           "{\n"
           ".reg .pred p;\n"
@@ -736,8 +757,34 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
           "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %8;\n"
           "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%3, %4, %5, %6}], [%1];\n"
           "}\n" ::"r"(dst), "r"(bar), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(0),
-          "r"((int)(on && lane == 0)), "r"(kWinBytes)
+          "r"(pred), "r"(tx)
           : "memory");
+      if (kTmaIn) {
+        if (tma_in) {      // uniform
+          const uint32_t ib = in_s + (uint32_t)kInStride * b;
+          const int cu = ra.cA_off + 32 * itn - ra.lead;
+          const int pun = pred && EpiFlags<EPI>::blend(a);
+          asm volatile(
+              "{\n"
+              ".reg .pred p, q;\n"
+              "setp.ne.s32 p, %9, 0;\n"
+              "setp.ne.s32 q, %10, 0;\n"
+              "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%3, {%6, %7, %8, %11}], [%2];\n"
+              "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%1], [%4, {%6, %7, %8, %11}], [%2];\n"
+              "}\n" ::"r"(ib), "r"(ib + (uint32_t)kInUStride), "r"(bar), "l"(reinterpret_cast<uint64_t>(&im.u)),
+              "l"(reinterpret_cast<uint64_t>(&im.un)), "r"(0), "r"(cu), "r"(c1), "r"(c2), "r"(pred), "r"(pun), "r"(0)
+              : "memory");
+          // rhs accumulator: interior-only (or slab-local) coordinates
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ne.s32 p, %6, 0;\n"
+              "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%3, %4, %5, %7}], [%1];\n"
+              "}\n" ::"r"(ib + 2u * (uint32_t)kInUStride), "r"(bar), "l"(reinterpret_cast<uint64_t>(&im.rhs)), "r"(32 * itn),
+              "r"(i2n), "r"(i1n), "r"(pred), "r"(0)
+              : "memory");
+        }
+      }
     } else {
       if (on) {
         double* const wb = reinterpret_cast<double*>(win0 + b * kWinStride);
@@ -793,7 +840,7 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
         const long long hidx = col_h + (long long)(f - 1) * g.sA;
         const long long ridx = col_r + (long long)(f - 1) * g.rA;
         CellIn<EPI> in;
-        if (act) load_cell_in<EPI>(g, a, hidx, ridx, in);
+        if (act && !tma_in) load_cell_in<EPI>(g, a, hidx, ridx, in);
         // wait for this iteration's window (in-place stages already waited for it before the previous stores)
         const double* const wb = reinterpret_cast<const double*>(win0 + b * kWinStride);
         if (!next_landed) {
@@ -845,6 +892,20 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
           rr[v] = ((lane == 0) ? carry[v] : rot) - F[v];
           carry[v] = rot;                                                // meaningful on lane 0: the next carry
         }
+        if (kTmaIn) {
+          if (tma_in) {      // the cell's inputs from this iteration's staged boxes (landed with the window)
+            const double* ib = reinterpret_cast<const double*>(in_raw + (wid * 2 + b) * kInStride);
+#pragma unroll
+            for (int v = 0; v < 5; ++v) {
+              in.U[v] = ib[v * kInCells + ra.lead + lane];
+              in.rhs[v] = ib[2 * (kInUStride / 8) + v * 32 + lane];
+            }
+            if (EpiFlags<EPI>::blend(a)) {
+#pragma unroll
+              for (int v = 0; v < 5; ++v) in.Un[v] = ib[kInUStride / 8 + v * kInCells + ra.lead + lane];
+            }
+          }
+        }
         if (EPI && a.inplace) {
           // prims_out aliases prims: the window staged for the next iteration overlaps the cells stored below (and
           // the next row's is read from global while this one stores) -- it must have landed first
@@ -876,7 +937,8 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
 #else
 template <int A, int RECON, int RIEMANN, int EPI, int USE_TMA>
 __global__ void __launch_bounds__(128, JXF_MIN_BLOCKS)
-sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap) {
+sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArgs a, const RowsArgs ra, const __grid_constant__ CUtensorMap tmap,
+           const __grid_constant__ RowsInMaps) {
   __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
   __shared__ alignas(8) uint64_t bars[4 * 2];
   const int lane = threadIdx.x & 31;
