@@ -172,7 +172,10 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
     const int nf = g.n[A] + 1;
     const long long total = rows * nf;
 #if JXF_ROWS_KERNEL
-    // production form whenever groups of >= 4 rows give every resident warp several work items
+    // production form whenever groups of >= 4 rows give every resident warp several work items.  (Measured, round 2:
+    // widening this rule -- groups down to 1 row, e.g. the rows kernel for the 1024 rows of 2-D 1024^2 -- is SLOWER than
+    // the contiguous kernel below there: 0.126 vs 0.096 ms per sweep with one partial wave of warps, and G = 2 instead
+    // of 4 at 256^3 costs 12 %: profiles/r02j_*.json against r02b_*.json.)
     const long long warps_resident = 4LL * resident;
     // (an in-place epilogue needs the staged windows of this kernel: forced whatever the slab's row count)
     if ((s->force_rows || (EPI && a.inplace) || rows / 4 >= warps_resident * 2) && g.n[A] >= 32) {
