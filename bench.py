@@ -537,6 +537,10 @@ def time_small_config(rt, steps, warmup, flush_bytes=512 << 20):
     an L2 flush (a 512 MB fill) between steps, outside the timed spans."""
     import torch
     flush = torch.empty(flush_bytes // 8, dtype=torch.float64, device="cuda")
+    # launch-bound steps (Sod-1000: 4 launches around ~10 us of work): replay the step from a captured CUDA graph
+    # (bit-identical to the launched step, tests/test_gpu_parity.py); JXF_BENCH_NO_GRAPH=1 launches kernel by kernel
+    if os.environ.get("JXF_BENCH_NO_GRAPH", "0") != "1" and not rt.parallel.is_parallel:
+        rt.use_cuda_graph(True)
     for _ in range(warmup):
         rt.step()
     torch.cuda.synchronize()
@@ -721,11 +725,12 @@ def main():
     small = workload in ("sod", "riemann2d")
     if small:
         config["l2"] = (f"working set {5 * field_gb * 1e3:.0f} MB: every step timed separately (CUDA events) with a "
-                        f"512 MB L2 flush between steps, outside the timed spans")
+                        f"512 MB L2 flush between steps, outside the timed spans; the step is replayed from a CUDA graph")
         rt.solver.profile_enable(False)
         sampler.mark()
         ms_total = time_small_config(rt, args.steps, args.warmup)
-        # per-kernel times from a second, unflushed pass (shares only)
+        # per-kernel times from a second, unflushed, kernel-by-kernel pass (shares only)
+        rt.use_cuda_graph(False)
         rt.solver.profile_read(reset=True)
         rt.solver.profile_enable(True)
         for _ in range(min(args.steps, 50)):

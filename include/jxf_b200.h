@@ -281,6 +281,19 @@ int jxf_unpack_face_n(jxf_handle h, int face, int ext_mask, int layers, const do
  * The caller owns both arrays and keeps them alive; ops = 0 clears the face. */
 int jxf_set_face_data(jxf_handle h, int face, int ops, const double* data_dev, const unsigned char* mask_dev);
 
+/* Peer-memory halo exchange (multi-GPU; replaces the ppermute of the face slabs, ref: halos/inner/material.py:30-93,
+ * halos/inner/halo_communication.py:35-77).  The caller maps the neighbours' field buffers into this process (CUDA IPC)
+ * and, before a stage, names per NEIGHBOR face the neighbour's OUTPUT buffers of that stage (jxf_set_peer_halo; NULL,
+ * NULL clears): jxf_stage's fused epilogue then stores the images of the cells within nh of the face -- the neighbour's
+ * halo cells, primitives and recomputed conservatives, all nh layers -- straight into the neighbour's memory.
+ * jxf_peer_signal (after the stage, same stream) publishes `epoch` in each neighbour's flag word
+ * (neighbour_flag_slots[face]: peer-mapped pointer to the word the neighbour polls for its opposite face, or NULL);
+ * jxf_peer_wait (before the first kernel that reads those halos) spins on this block's own flag words `flags[6]` until
+ * every face in `face_mask` shows >= epoch.  Enqueue-only; every rank must signal an epoch before it waits for it. */
+int jxf_set_peer_halo(jxf_handle h, int face, double* peer_prims_out, double* peer_cons_out);
+int jxf_peer_signal(jxf_handle h, int64_t* const* neighbour_flag_slots, int64_t epoch, void* stream);
+int jxf_peer_wait(jxf_handle h, const int64_t* flags, int face_mask, int64_t epoch, void* stream);
+
 /* One RK stage on THREE full-size buffers: `prims` is updated IN PLACE (no ping-pong buffer) and the rhs accumulator is
  * two slabs of `slab_planes` x planes (jxf_rhs_slab_elems doubles each, stored back to back in `rhs_slabs`).  The block
  * is processed slab by slab with the x sweep running one slab ahead (see the definition).  3-D blocks, convective flux

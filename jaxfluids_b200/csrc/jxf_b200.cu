@@ -1000,6 +1000,63 @@ extern "C" int jxf_set_face_data(jxf_handle h, int face, int ops, const double* 
   return JXF_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Peer-memory halo exchange (multi-GPU, one process per GPU, neighbours' buffers mapped with CUDA IPC): the fused
+// epilogue stores the halo images of NEIGHBOR faces straight into the neighbour's output buffers over NVLink
+// (halo_images_axis); what remains of the "exchange" is a pair of flags per shared face.
+//   jxf_peer_signal: after a stage's kernels (stream order), publish `epoch` in every neighbour's flag slot.
+//   jxf_peer_wait:   before the first kernel that reads the halos, spin until every neighbour has published `epoch`.
+// Every rank signals stage k before it waits for stage k, so the waits cannot form a cycle.
+// Replaces halos/inner/material.py:30-93 (ppermute of the face slabs) without staging buffers or a collective.
+// ---------------------------------------------------------------------------
+struct PeerFlags {
+  long long* slot[6];      // the neighbour's flag word this block writes, per face (null: none)
+};
+
+__global__ void peer_signal_kernel(PeerFlags pf, long long epoch) {
+  const int f = threadIdx.x;
+  if (f < 6 && pf.slot[f]) {
+    __threadfence_system();                     // this GPU's earlier stores (incl. the remote halo images) first
+    *reinterpret_cast<volatile long long*>(pf.slot[f]) = epoch;
+  }
+}
+
+__global__ void peer_wait_kernel(const long long* flags, int face_mask, long long epoch) {
+  const int f = threadIdx.x;
+  if (f < 6 && ((face_mask >> f) & 1)) {
+    const volatile long long* w = flags + f;
+    while (*w < epoch) __nanosleep(100);
+  }
+  __threadfence_system();
+}
+
+extern "C" int jxf_set_peer_halo(jxf_handle h, int face, double* peer_prims_out, double* peer_cons_out) {
+  if (!h || face < 0 || face > 5) return fail(JXF_ERR_BAD_ARG, "jxf_set_peer_halo: bad argument");
+  if ((peer_prims_out == nullptr) != (peer_cons_out == nullptr))
+    return fail(JXF_ERR_BAD_ARG, "jxf_set_peer_halo: both buffers or none");
+  if (peer_prims_out && h->cfg.bc[face] != JXF_BC_NEIGHBOR)
+    return fail(JXF_ERR_BAD_ARG, "jxf_set_peer_halo: face %d is not shared with another block", face);
+  h->peer_prims[face] = peer_prims_out;
+  h->peer_cons[face] = peer_cons_out;
+  return JXF_OK;
+}
+
+extern "C" int jxf_peer_signal(jxf_handle h, int64_t* const* neighbour_flag_slots, int64_t epoch, void* stream) {
+  if (!h || !neighbour_flag_slots) return fail(JXF_ERR_BAD_ARG, "jxf_peer_signal: null argument");
+  PeerFlags pf;
+  for (int f = 0; f < 6; ++f) pf.slot[f] = reinterpret_cast<long long*>(neighbour_flag_slots[f]);
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, (long long)epoch);
+  return check_launch("peer_signal");
+}
+
+extern "C" int jxf_peer_wait(jxf_handle h, const int64_t* flags, int face_mask, int64_t epoch, void* stream) {
+  if (!h || !flags) return fail(JXF_ERR_BAD_ARG, "jxf_peer_wait: null argument");
+  ProfScope prof(h, JXF_PROFILE_OTHER, (cudaStream_t)stream);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(flags), face_mask, (long long)epoch);
+  return check_launch("peer_wait");
+}
+
 extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream) {
   if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill: null argument");
   HaloArgs a;
@@ -1109,6 +1166,11 @@ extern "C" int jxf_stage_tail(jxf_handle h, int stage, int first_axis_index, con
       a.face_data = h->face_data;
       a.has_face_data = h->has_face_data;
       for (int q = 0; q < 3; ++q) a.n_phys[q] = h->g.n[q];
+      for (int f = 0; f < 6; ++f) {      // direct halo stores into the neighbours' buffers (jxf_set_peer_halo)
+        const bool on = fill_halo && a.bc[f] == JXF_BC_NEIGHBOR && h->peer_prims[f] && h->peer_cons[f];
+        a.peer_prims[f] = on ? h->peer_prims[f] : nullptr;
+        a.peer_cons[f] = on ? h->peer_cons[f] : nullptr;
+      }
       rc = dispatch_axis(h, axis, a, 1, (cudaStream_t)stream);
     }
     if (rc) return rc;

@@ -38,6 +38,8 @@ struct jxf_solver {
   // TMA descriptors of the primitive buffers seen so far (keyed by base pointer)
   bool force_rows;     // JXF_FORCE_ROWS=1: use the rows kernel on small grids too (tests)
   bool tma_ok;
+  double* peer_prims[6];   // jxf_set_peer_halo: the neighbours' output buffers of the NEXT stage call (peer-mapped), or null
+  double* peer_cons[6];
   FaceData face_data;  // jxf_set_face_data: device pointers owned by the caller
   int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
@@ -96,6 +98,10 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   if (a.cons_n) a.cons_n += h0;
   if (a.cons_out) a.cons_out += h0;
   if (a.prims_out) a.prims_out += h0;
+  for (int f = 0; f < 6; ++f) {
+    if (a.peer_prims[f]) a.peer_prims[f] += h0;
+    if (a.peer_cons[f]) a.peer_cons[f] += h0;
+  }
   SweepGeom sg;
   sg.axA = A;
   sg.nA = g.n[A];

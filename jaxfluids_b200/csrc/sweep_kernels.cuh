@@ -85,6 +85,12 @@ struct SweepArgs {
   int sub_lo, sub_n;
   long long rvst_slab;
   int inplace;             // EPI: prims_out aliases prims (rows kernel: the next window must have landed before a store)
+  // EPI + fuse_halo, multi-GPU: output buffers of the block across each NEIGHBOR face, mapped into this process (CUDA
+  // IPC over NVLink), or null.  The thread that produces a cell within nh of such a face stores the cell's image -- the
+  // neighbour's halo cell -- straight into the neighbour's memory (halo_images_axis), instead of a pack / send / unpack
+  // round through staging slabs.  Pointers carry the same interior-origin offset as prims_out / cons_out.
+  double* peer_prims[6];
+  double* peer_cons[6];
   FaceData face_data;      // EPI + fuse_halo: per-face boundary data (device pointers), used when has_face_data
   int has_face_data;
   int n_phys[3];           // interior cells per PHYSICAL axis (transverse indexing of face_data)
@@ -224,10 +230,21 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
 __device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
                                                  int ax, int n, int i, long long stride, const double* wall_hi,
                                                  const double* wall_lo, const double* dir_hi, const double* dir_lo,
-                                                 const FaceData* fd, long long tidx, long long tcount) {
+                                                 const FaceData* fd, long long tidx, long long tcount,
+                                                 double* const* peer_prims, double* const* peer_cons) {
   if (n <= 1) return;
   const int nh = h.nh;
   const int fhi = 2 * ax, flo = 2 * ax + 1;
+  // faces shared with another block: the nh cells next to the face are the neighbour's halo cells beyond ITS opposite
+  // face -- the same index arithmetic as a periodic image, into the neighbour's buffers
+  if (blo == JXF_BC_NEIGHBOR && peer_prims[flo]) {
+    const HaloOut hp{peer_prims[flo], peer_cons[flo], h.vst, h.gamma, h.nh};
+    if (i < nh) halo_image(hp, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, flo, 0, 0);
+  }
+  if (bhi == JXF_BC_NEIGHBOR && peer_prims[fhi]) {
+    const HaloOut hp{peer_prims[fhi], peer_cons[fhi], h.vst, h.gamma, h.nh};
+    if (i >= n - nh) halo_image(hp, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, fhi, 0, 0);
+  }
   // low side (west / south / bottom)
   if (blo == JXF_BC_SYMMETRY) {
     if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax, nullptr, fd, flo, tidx, tcount);
@@ -328,11 +345,11 @@ static __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const S
     tidx[2] = (long long)idx[0] * n[1] + idx[1]; tcnt[2] = (long long)n[0] * n[1];
   }
   halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1],
-                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1], fd, tidx[g.axA], tcnt[g.axA]);
+                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1], fd, tidx[g.axA], tcnt[g.axA], a.peer_prims, a.peer_cons);
   halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1_full, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
-                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1], fd, tidx[g.ax1], tcnt[g.ax1]);
+                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1], fd, tidx[g.ax1], tcnt[g.ax1], a.peer_prims, a.peer_cons);
   halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1],
-                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1], fd, tidx[g.ax2], tcnt[g.ax2]);
+                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1], fd, tidx[g.ax2], tcnt[g.ax2], a.peer_prims, a.peer_cons);
 }
 
 #ifdef JXF_WITH_STRIDED   // the register-window predecessor of sweep_march: A/B builds only (-DJXF_WITH_STRIDED)

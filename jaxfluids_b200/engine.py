@@ -273,6 +273,20 @@ class BlockSolver:
                                               None if data is None else C.c_void_p(data.data_ptr()),
                                               None if mask is None else C.c_void_p(mask.data_ptr())))
 
+    # -- peer-memory halo exchange (include/jxf_b200.h) ------------------------
+    def set_peer_halo(self, face: int, peer_prims_out: Optional[torch.Tensor], peer_cons_out: Optional[torch.Tensor]):
+        _lib.check(self.lib.jxf_set_peer_halo(self._h, int(face),
+                                              None if peer_prims_out is None else C.c_void_p(peer_prims_out.data_ptr()),
+                                              None if peer_cons_out is None else C.c_void_p(peer_cons_out.data_ptr())))
+
+    def peer_signal(self, slots, epoch: int):
+        """slots: 6 device pointers (int) or None -- the neighbours' flag words this block writes"""
+        arr = (C.c_void_p * 6)(*[C.c_void_p(p) if p else None for p in slots])
+        _lib.check(self.lib.jxf_peer_signal(self._h, arr, int(epoch), _stream()))
+
+    def peer_wait(self, flags: torch.Tensor, face_mask: int, epoch: int):
+        _lib.check(self.lib.jxf_peer_wait(self._h, C.c_void_p(flags.data_ptr()), int(face_mask), int(epoch), _stream()))
+
     def halo_fill(self, prims, cons):
         _lib.check(self.lib.jxf_halo_fill(self._h, _ptr(prims), _ptr(cons), _stream()))
 

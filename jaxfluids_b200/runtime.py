@@ -152,6 +152,13 @@ class BlockRuntime:
         prio = -1 if os.environ.get("JXF_COMM_PRIORITY", "1") != "0" else 0
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=prio) if self.neighbors else None
         self._pending = None                      # event: halos of the current primitives are complete
+        # Peer-memory halo exchange (JXF_PEER_HALO=1): the neighbours' field buffers are mapped into this process (CUDA
+        # IPC over NVLink) and the fused epilogue stores the halo images of shared faces straight into them; the
+        # exchange between stages shrinks to one flag word per shared face (jxf_peer_signal / jxf_peer_wait).
+        self.peer = None
+        if (self.neighbors and os.environ.get("JXF_PEER_HALO", "0") == "1" and not self.cfg.is_dissipative
+                and self.memory_plan == "pingpong"):
+            self._setup_peer()
         first = s.active[0]
         self._first_axis = first
         self._first_strided = len(s.active) > 1   # the contiguous (last active) axis takes no partial ranges
@@ -447,8 +454,43 @@ class BlockRuntime:
     # on either side, so only cells within 3 of a shared face read exchanged halos
     REACH = 3
 
+    def _setup_peer(self):
+        """Exchange CUDA-IPC handles of the four field buffers and of a flag array with every rank (torch's own
+        tensor-sharing plumbing), map the neighbours' and keep, per shared face, the pointer of the flag word to write."""
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.peer_flags = torch.zeros(8, dtype=torch.int64, device=self.device)
+        mine = [reduce_tensor(t) for t in (self.prims[0], self.prims[1], self.cons[0], self.cons[1], self.peer_flags)]
+        gathered = [None] * self.parallel.world_size
+        dist.all_gather_object(gathered, mine, group=self.parallel.group)
+        from .parallel import OPPOSITE
+        self._peer_tensors = {}
+        for nb in set(self.neighbors.values()):
+            assert nb != self.parallel.rank
+            self._peer_tensors[nb] = [fn(*args) for fn, args in gathered[nb]]
+        self.peer = {f: self._peer_tensors[nb] for f, nb in self.neighbors.items()}
+        # the word the neighbour across face f polls for ITS face opposite(f)
+        self.peer_slots = [None] * 6
+        self.peer_mask = 0
+        for f, t in self.peer.items():
+            self.peer_slots[FACE_ID[f]] = t[4].data_ptr() + 8 * FACE_ID[OPPOSITE[f]]
+            self.peer_mask |= 1 << FACE_ID[f]
+        self._epoch = 0
+        self.parallel.barrier()
+
+    def _set_peer_outputs(self, last: bool):
+        """Before a stage: the neighbours' OUTPUT buffers of this stage (every rank runs the same ping-pong sequence)."""
+        for f, t in self.peer.items():
+            self.solver.set_peer_halo(FACE_ID[f], t[self.cur ^ 1], t[2] if last else t[3])
+
     def _start_exchange(self, prims: torch.Tensor, cons: torch.Tensor):
         """Post the inter-block halo exchange of (prims, cons) on the communication stream."""
+        if self.peer is not None:      # the stage's epilogue already stored the halos remotely: publish the epoch
+            self._epoch += 1
+            with self._tick("signal"):
+                self.solver.peer_signal(self.peer_slots, self._epoch)
+            self._pending = ("peer", self._epoch)
+            return
         compute = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(compute)
@@ -463,7 +505,10 @@ class BlockRuntime:
         """Make the current stream wait for an in-flight halo exchange (before anyone reads halos)."""
         if self._pending is not None:
             with self._tick("wait"):
-                torch.cuda.current_stream().wait_event(self._pending)
+                if isinstance(self._pending, tuple):       # peer exchange: spin on this block's flag words
+                    self.solver.peer_wait(self.peer_flags, self.peer_mask, self._pending[1])
+                else:
+                    torch.cuda.current_stream().wait_event(self._pending)
             self._pending = None
 
     def complete_halos(self):
@@ -493,6 +538,8 @@ class BlockRuntime:
             self.cur ^= 1
             return
         args = (p_in, p_out, c_in, self.cons[0], c_out, self.rhs, self.dt, self.red)
+        if self.peer is not None:
+            self._set_peer_outputs(last)
         if self._pending is not None and self.overlap and self._first_strided:
             ax, n, w = self._first_axis, self.cfg.cells[self._first_axis], self.REACH
             if self._first_split and n > 2 * w:
@@ -510,7 +557,7 @@ class BlockRuntime:
             self.finish_pending()
             s.stage(k, *args, reduce=reduce, fill_halo=True)
         if self.neighbors:
-            if self.overlap:
+            if self.overlap or self.peer is not None:
                 self._start_exchange(p_out, c_out)
             else:
                 self.halo_update(p_out, c_out, local_done=True, layers=self.stage_layers)

@@ -21,7 +21,8 @@ def _ngpus():
 
 
 WORKER = r'''
-import json, os, sys
+import json, os, sys, signal
+signal.alarm(300)          # watchdog: a rank stuck in an exchange dies by itself instead of holding the GPU
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["JXF_ROOT"])
 from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
@@ -138,7 +139,8 @@ def test_pencil_and_block_decompositions(split, cells, bc, nproc, visc, tmp_path
 
 
 API_WORKER = r'''
-import json, os, sys
+import json, os, sys, signal
+signal.alarm(300)
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["JXF_ROOT"])
 from jaxfluids_b200 import InputManager, InitializationManager, SimulationManager
@@ -205,3 +207,18 @@ def test_boundary_data_fixtures_on_two_blocks(name, split, tmp_path):
     assert lines, out.stdout[-2000:] + out.stderr[-4000:]
     res = json.loads(lines[-1][7:])
     assert res["err"] <= H.TOL_PRIMS_100 and res["dt_err"] <= 1e-10, res
+
+
+@pytest.mark.parametrize("split,cells,bc,nproc", [((2, 1, 1), (32, 20, 36), "PERIODIC", 2), ((1, 2, 1), (20, 32, 36), "SYMMETRY", 2),
+                                                  ((1, 1, 2), (12, 16, 80), "PERIODIC", 2), ((2, 1, 1), (64, 24, 1), "ZEROGRADIENT", 2),
+                                                  ((2, 2, 1), (24, 32, 16), "PERIODIC", 4), ((2, 2, 2), (24, 20, 28), "SYMMETRY", 8)])
+def test_peer_memory_halo_exchange(split, cells, bc, nproc, tmp_path):
+    """JXF_PEER_HALO=1: the fused epilogue stores the halo images of shared faces straight into the neighbour's buffers
+    (CUDA IPC over NVLink), flags instead of pack / NCCL / unpack -- same result as the single-block oracle."""
+    if _ngpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    worker = tmp_path / "worker.py"
+    worker.write_text(WORKER)
+    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="4",
+               JXF_CELLS=",".join(map(str, cells)), JXF_VISC="0", JXF_PEER_HALO="1")
+    _run_worker(worker, env, nproc)
