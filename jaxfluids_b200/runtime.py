@@ -468,6 +468,31 @@ class BlockRuntime:
         for nb in set(self.neighbors.values()):
             assert nb != self.parallel.rank
             self._peer_tensors[nb] = [fn(*args) for fn, args in gathered[nb]]
+        # torch maps a shared block in the context of the OWNER's device; kernels on this rank's device reach it once
+        # peer access to that device is enabled (NVLink / NVSwitch: every pair of GPUs of the box)
+        import ctypes
+        rt_lib = None
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                rt_lib = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        mine_dev = torch.device(self.device).index
+        for nb, ts in self._peer_tensors.items():
+            d = ts[0].device.index
+            if d == mine_dev:
+                continue
+            if not torch.cuda.can_device_access_peer(mine_dev, d):
+                raise RuntimeError(f"JXF_PEER_HALO=1: device {mine_dev} cannot access device {d} as a peer")
+            with torch.cuda.device(mine_dev):
+                if rt_lib is not None:
+                    rt_lib.cudaSetDevice(ctypes.c_int(mine_dev))
+                rc = rt_lib.cudaDeviceEnablePeerAccess(ctypes.c_int(d), ctypes.c_uint(0)) if rt_lib is not None else 0
+                if rc not in (0, 704):          # 704 = cudaErrorPeerAccessAlreadyEnabled
+                    raise RuntimeError(f"cudaDeviceEnablePeerAccess({d}) failed with CUDA error {rc}")
+                if rt_lib is not None:
+                    rt_lib.cudaGetLastError()
         self.peer = {f: self._peer_tensors[nb] for f, nb in self.neighbors.items()}
         # the word the neighbour across face f polls for ITS face opposite(f)
         self.peer_slots = [None] * 6
