@@ -290,6 +290,14 @@ int jxf_set_face_data(jxf_handle h, int face, int ops, const double* data_dev, c
  * (neighbour_flag_slots[face]: peer-mapped pointer to the word the neighbour polls for its opposite face, or NULL);
  * jxf_peer_wait (before the first kernel that reads those halos) spins on this block's own flag words `flags[6]` until
  * every face in `face_mask` shows >= epoch.  Enqueue-only; every rank must signal an epoch before it waits for it. */
+/* Mapping a neighbour's buffer (one process per GPU): jxf_peer_export names the device allocation that holds `ptr` --
+ * a 64-byte CUDA IPC handle and ptr's byte offset inside that allocation -- for the caller to send to the other process
+ * (any transport); jxf_peer_import opens such a handle in the context of the CURRENT device (peer access to the owner's
+ * device is enabled by the driver, NVLink / NVSwitch) and returns the mapped address of the same byte.  An allocation is
+ * opened once per process and device (cached); jxf_peer_release unmaps everything this process imported. */
+int jxf_peer_export(const void* ptr, unsigned char* handle_out /* [64] */, int64_t* offset_out);
+int jxf_peer_import(const unsigned char* handle /* [64] */, int64_t offset, void** ptr_out);
+int jxf_peer_release(void);
 int jxf_set_peer_halo(jxf_handle h, int face, double* peer_prims_out, double* peer_cons_out);
 int jxf_peer_signal(jxf_handle h, int64_t* const* neighbour_flag_slots, int64_t epoch, void* stream);
 int jxf_peer_wait(jxf_handle h, const int64_t* flags, int face_mask, int64_t epoch, void* stream);

@@ -19,7 +19,7 @@ EXPORTS = (
     "jxf_cons_from_prims", "jxf_reduce", "jxf_reduce_reset", "jxf_finish_step", "jxf_face_slab_elems",
     "jxf_pack_face", "jxf_unpack_face", "jxf_fp64_probe", "jxf_step_fused", "jxf_profile_enable", "jxf_profile_read", "jxf_debug_face_flux", "jxf_debug_dispatch", "jxf_debug_math", "jxf_stage_tail", "jxf_sweep_range", "jxf_integrate_stage", "jxf_halo_fill_edges", "jxf_dissipative_sweep", "jxf_temperature", "jxf_face_slab_elems_ext", "jxf_pack_face_ext", "jxf_unpack_face_ext", "jxf_bind_timestep",
     "jxf_face_slab_elems_n", "jxf_pack_face_n", "jxf_unpack_face_n", "jxf_rhs_slab_elems", "jxf_stage_inplace", "jxf_set_face_data",
-    "jxf_set_peer_halo", "jxf_peer_signal", "jxf_peer_wait",
+    "jxf_set_peer_halo", "jxf_peer_signal", "jxf_peer_wait", "jxf_peer_export", "jxf_peer_import", "jxf_peer_release",
 )
 
 RECON = {"PRIMITIVE": 0, "CHAR-PRIMITIVE": 1, "CONSERVATIVE": 2, "CHAR-CONSERVATIVE": 3}
@@ -178,6 +178,12 @@ def load():
     lib.jxf_set_peer_halo.argtypes = [vp, i32, dp, dp]
     lib.jxf_peer_signal.restype = i32
     lib.jxf_peer_signal.argtypes = [vp, C.POINTER(C.c_void_p), i64, vp]
+    lib.jxf_peer_export.restype = i32
+    lib.jxf_peer_export.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    lib.jxf_peer_import.restype = i32
+    lib.jxf_peer_import.argtypes = [vp, i64, C.POINTER(C.c_void_p)]
+    lib.jxf_peer_release.restype = i32
+    lib.jxf_peer_release.argtypes = []
     lib.jxf_peer_wait.restype = i32
     lib.jxf_peer_wait.argtypes = [vp, dp, i32, i64, vp]
     lib.jxf_debug_math.restype = i32

@@ -13,6 +13,8 @@
 // (equation_manager.py:164-171) and the CFL / min-rho / min-p reductions
 // (time_step_size.py:103-109, positivity_handler.py:246-247).
 #include "plan.cuh"
+#include <mutex>
+#include <vector>
 
 namespace jxf {
 
@@ -1028,6 +1030,86 @@ __global__ void peer_wait_kernel(const long long* flags, int face_mask, long lon
     while (*w < epoch) __nanosleep(100);
   }
   __threadfence_system();
+}
+
+// Mapping the neighbours' buffers: jxf_peer_export names the device allocation that holds `ptr` (a 64-byte CUDA IPC
+// handle + the byte offset of ptr inside it); jxf_peer_import opens such a handle IN THE CONTEXT OF THE CURRENT DEVICE
+// (cudaIpcMemLazyEnablePeerAccess: the driver enables NVLink peer access to the owner's device) and returns the mapped
+// address of the same byte.  One allocation is opened once per process (handles are cached), jxf_peer_release unmaps all.
+namespace {
+struct PeerMapping { unsigned char handle[64]; void* base; int device; };
+std::mutex g_peer_mu;
+std::vector<PeerMapping> g_peer_maps;
+typedef CUresult (*PFN_getAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+}
+
+extern "C" int jxf_peer_export(const void* ptr, unsigned char* handle_out, int64_t* offset_out) {
+  if (!ptr || !handle_out || !offset_out) return fail(JXF_ERR_BAD_ARG, "jxf_peer_export: null argument");
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !fp) {
+    (void)cudaGetLastError();
+    return fail(JXF_ERR_CUDA, "jxf_peer_export: cuMemGetAddressRange is not available");
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = ((PFN_getAddressRange)fp)(&base, &size, (CUdeviceptr)(uintptr_t)ptr);
+  if (r != CUDA_SUCCESS) return fail(JXF_ERR_CUDA, "jxf_peer_export: cuMemGetAddressRange failed (%d)", (int)r);
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, (void*)(uintptr_t)base);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(JXF_ERR_CUDA, "jxf_peer_export: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  static_assert(sizeof(hd) == 64, "CUDA IPC handles are 64 bytes");
+  memcpy(handle_out, &hd, 64);
+  *offset_out = (int64_t)((uintptr_t)ptr - (uintptr_t)base);
+  return JXF_OK;
+}
+
+extern "C" int jxf_peer_import(const unsigned char* handle, int64_t offset, void** ptr_out) {
+  if (!handle || !ptr_out || offset < 0) return fail(JXF_ERR_BAD_ARG, "jxf_peer_import: bad argument");
+  int dev = -1;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_peer_mu);
+  for (const PeerMapping& m : g_peer_maps)
+    if (m.device == dev && memcmp(m.handle, handle, 64) == 0) {
+      *ptr_out = (char*)m.base + offset;
+      return JXF_OK;
+    }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  void* base = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(JXF_ERR_CUDA, "jxf_peer_import: cudaIpcOpenMemHandle on device %d: %s", dev, cudaGetErrorString(e));
+  }
+  PeerMapping m;
+  memcpy(m.handle, handle, 64);
+  m.base = base;
+  m.device = dev;
+  g_peer_maps.push_back(m);
+  *ptr_out = (char*)base + offset;
+  return JXF_OK;
+}
+
+extern "C" int jxf_peer_release(void) {
+  std::lock_guard<std::mutex> lock(g_peer_mu);
+  int rc = JXF_OK;
+  for (const PeerMapping& m : g_peer_maps) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != m.device) cudaSetDevice(m.device);
+    if (cudaIpcCloseMemHandle(m.base) != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(JXF_ERR_CUDA, "jxf_peer_release: cudaIpcCloseMemHandle failed");
+    }
+    if (cur != m.device) cudaSetDevice(cur);
+  }
+  g_peer_maps.clear();
+  return rc;
 }
 
 extern "C" int jxf_set_peer_halo(jxf_handle h, int face, double* peer_prims_out, double* peer_cons_out) {

@@ -274,10 +274,29 @@ class BlockSolver:
                                               None if mask is None else C.c_void_p(mask.data_ptr())))
 
     # -- peer-memory halo exchange (include/jxf_b200.h) ------------------------
-    def set_peer_halo(self, face: int, peer_prims_out: Optional[torch.Tensor], peer_cons_out: Optional[torch.Tensor]):
+    def set_peer_halo(self, face: int, peer_prims_out: Optional[int], peer_cons_out: Optional[int]):
+        """peer_*_out: peer-mapped device ADDRESSES (peer_import) of the neighbour's output buffers, or None"""
         _lib.check(self.lib.jxf_set_peer_halo(self._h, int(face),
-                                              None if peer_prims_out is None else C.c_void_p(peer_prims_out.data_ptr()),
-                                              None if peer_cons_out is None else C.c_void_p(peer_cons_out.data_ptr())))
+                                              C.c_void_p(peer_prims_out) if peer_prims_out else None,
+                                              C.c_void_p(peer_cons_out) if peer_cons_out else None))
+
+    def peer_export(self, t: torch.Tensor):
+        """-> (handle: 64 bytes, offset): names the device allocation holding t's first element for another process"""
+        buf = C.create_string_buffer(64)
+        off = C.c_int64(0)
+        _lib.check(self.lib.jxf_peer_export(C.c_void_p(t.data_ptr()), buf, C.byref(off)))
+        return bytes(buf.raw), int(off.value)
+
+    def peer_import(self, handle: bytes, offset: int) -> int:
+        """Map another process' allocation under the current device; -> the address of the exported element."""
+        assert len(handle) == 64
+        buf = C.create_string_buffer(handle, 64)
+        out = C.c_void_p(0)
+        _lib.check(self.lib.jxf_peer_import(buf, int(offset), C.byref(out)))
+        return int(out.value)
+
+    def peer_release(self):
+        _lib.check(self.lib.jxf_peer_release())
 
     def peer_signal(self, slots, epoch: int):
         """slots: 6 device pointers (int) or None -- the neighbours' flag words this block writes"""

@@ -455,52 +455,34 @@ class BlockRuntime:
     REACH = 3
 
     def _setup_peer(self):
-        """Exchange CUDA-IPC handles of the four field buffers and of a flag array with every rank (torch's own
-        tensor-sharing plumbing), map the neighbours' and keep, per shared face, the pointer of the flag word to write."""
+        """Map the neighbours' four field buffers and flag words into this process: every rank exports the CUDA-IPC
+        handle of each buffer's allocation (jxf_peer_export), the handles travel through the process group, and each
+        rank opens its neighbours' under ITS OWN device (jxf_peer_import), which enables NVLink peer access."""
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
+        from .parallel import OPPOSITE
+        s = self.solver
         self.peer_flags = torch.zeros(8, dtype=torch.int64, device=self.device)
-        mine = [reduce_tensor(t) for t in (self.prims[0], self.prims[1], self.cons[0], self.cons[1], self.peer_flags)]
+        torch.cuda.synchronize(self.device)
+        mine = [s.peer_export(t) for t in (self.prims[0], self.prims[1], self.cons[0], self.cons[1], self.peer_flags)]
         gathered = [None] * self.parallel.world_size
         dist.all_gather_object(gathered, mine, group=self.parallel.group)
-        from .parallel import OPPOSITE
-        self._peer_tensors = {}
-        for nb in set(self.neighbors.values()):
-            assert nb != self.parallel.rank
-            self._peer_tensors[nb] = [fn(*args) for fn, args in gathered[nb]]
-        # torch maps a shared block in the context of the OWNER's device; kernels on this rank's device reach it once
-        # peer access to that device is enabled (NVLink / NVSwitch: every pair of GPUs of the box)
-        import ctypes
-        rt_lib = None
-        for name in ("libcudart.so.12", "libcudart.so"):
-            try:
-                rt_lib = ctypes.CDLL(name)
-                break
-            except OSError:
-                continue
-        mine_dev = torch.device(self.device).index
-        for nb, ts in self._peer_tensors.items():
-            d = ts[0].device.index
-            if d == mine_dev:
-                continue
-            if not torch.cuda.can_device_access_peer(mine_dev, d):
-                raise RuntimeError(f"JXF_PEER_HALO=1: device {mine_dev} cannot access device {d} as a peer")
-            with torch.cuda.device(mine_dev):
-                if rt_lib is not None:
-                    rt_lib.cudaSetDevice(ctypes.c_int(mine_dev))
-                rc = rt_lib.cudaDeviceEnablePeerAccess(ctypes.c_int(d), ctypes.c_uint(0)) if rt_lib is not None else 0
-                if rc not in (0, 704):          # 704 = cudaErrorPeerAccessAlreadyEnabled
-                    raise RuntimeError(f"cudaDeviceEnablePeerAccess({d}) failed with CUDA error {rc}")
-                if rt_lib is not None:
-                    rt_lib.cudaGetLastError()
-        self.peer = {f: self._peer_tensors[nb] for f, nb in self.neighbors.items()}
+        with torch.cuda.device(self.device):
+            self._peer_ptrs = {}
+            for nb in set(self.neighbors.values()):
+                assert nb != self.parallel.rank
+                self._peer_ptrs[nb] = [s.peer_import(h, off) for h, off in gathered[nb]]
+        self.peer = {f: self._peer_ptrs[nb] for f, nb in self.neighbors.items()}
         # the word the neighbour across face f polls for ITS face opposite(f)
         self.peer_slots = [None] * 6
         self.peer_mask = 0
         for f, t in self.peer.items():
-            self.peer_slots[FACE_ID[f]] = t[4].data_ptr() + 8 * FACE_ID[OPPOSITE[f]]
+            self.peer_slots[FACE_ID[f]] = t[4] + 8 * FACE_ID[OPPOSITE[f]]
             self.peer_mask |= 1 << FACE_ID[f]
         self._epoch = 0
+        # prove the mappings before the first stage depends on them: epoch 0 into every neighbour's flag word (a no-op
+        # for the protocol), then a synchronise that surfaces an unmapped address HERE rather than inside a sweep
+        s.peer_signal(self.peer_slots, 0)
+        torch.cuda.synchronize(self.device)
         self.parallel.barrier()
 
     def _set_peer_outputs(self, last: bool):
