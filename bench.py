@@ -773,18 +773,24 @@ def main():
     # ---- per-rank exchange times (max over ranks), per RK stage -------------------------------------------
     comm = None
     if rt.neighbors:
-        keys = ("pack", "nccl", "unpack", "wait")
+        keys = ("pack", "nccl", "unpack", "wait", "signal")
         v = torch.tensor([comm_ms.get(k, 0.0) for k in keys], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
         nst = args.steps * rt.stages
         comm = {f"{k}_ms_per_stage": float(x) / nst for k, x in zip(keys, v.tolist())}
-        slab_mb = sum(rt.send[f][:rt.solver.face_slab_elems(0, 0, rt.stage_layers) if False else None].numel()
-                      for f in rt.neighbors) * 8 / 1e6 * rt.stage_layers / rt.cfg.nh
-        comm.update(faces=len(rt.neighbors), layers=rt.stage_layers, sent_mb_per_stage=slab_mb, overlap=bool(rt.overlap),
-                    what="CUDA-event spans, summed over the timed region / stages, max over ranks: pack / nccl / unpack "
-                         "on the communication stream (nccl = the grouped send/recv batch incl. waiting for the peer), "
-                         "wait = time the COMPUTE stream stalled on the exchange event")
+        peer = rt.peer is not None
+        layers = rt.cfg.nh if peer else rt.stage_layers
+        slab_mb = sum(rt.send[f].numel() for f in rt.neighbors) * 8 / 1e6 * layers / rt.cfg.nh
+        comm.update(mode="peer" if peer else "nccl", faces=len(rt.neighbors), layers=layers, sent_mb_per_stage=slab_mb,
+                    overlap=bool(rt.overlap),
+                    what=("peer mode: the stage epilogue stores the shared faces' halo images straight into the "
+                          "neighbours' buffers (CUDA IPC over NVLink, inside the sweep kernel's time); signal = the flag "
+                          "kernel after each stage, wait = the flag spin before the first kernel that reads halos; "
+                          "CUDA-event spans / stages, max over ranks") if peer else
+                         ("CUDA-event spans, summed over the timed region / stages, max over ranks: pack / nccl / unpack "
+                          "on the communication stream (nccl = the grouped send/recv batch incl. waiting for the peer), "
+                          "wait = time the COMPUTE stream stalled on the exchange event"))
 
     # ---- FP64 pipe peak (measured here, same clocks) ------------------------------------
     import ctypes as C
