@@ -47,7 +47,7 @@ KERNEL_BYTES = {"sweep_x": 80.0, "sweep_y": 120.0, "sweep_z": 120.0,
                 "dissipative": 106.7}
 # DRAM traffic per launch at 512^3: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture
 # (a CONSTANT from the named file, not measured in this run: ncu cannot run inside the bench)
-NCU_TRAFFIC_512 = {"file": "profiles/r02a_ncu_full_summary.txt",
+NCU_TRAFFIC_512 = {"file": "profiles/ncu_full_r02a_summary.txt",
                    "sweep_x": None, "sweep_y": None, "sweep_z_epilogue": None, "dissipative": None}
 try:
     with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as _fh:
@@ -421,13 +421,17 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
     import torch
     import torch.distributed as dist
     k_e2e = args.e2e_steps or max(2, min(args.steps, 5))
-    host_state = torch.empty(tuple(rt.primitives.shape), dtype=torch.float64, pin_memory=True)
-    host_state.copy_(rt.primitives)
+    # the step's host input is what the reference's user hands over: the INTERIOR cells of the block's primitives
+    # (material_fields_initializer.py:148-210); halos are filled on the device (outer rules + inter-block exchange)
+    sl = (slice(None),) + tuple(rt.cfg.interior)
+    host_state = torch.empty(tuple(rt.primitives[sl].shape), dtype=torch.float64, pin_memory=True)
+    host_state.copy_(rt.primitives[sl])
     jb = buffers._replace(time_control_variables=tcv._replace(physical_simulation_time=time_now,
                                                               physical_timestep_size=dt_now))
 
     def one_step(jb_):
         rt.solver.cons_from_prims(rt.primitives, rt.conservatives)
+        rt.halo_update(rt.primitives, rt.conservatives)
         mf = jb_.simulation_buffers.material_fields._replace(primitives=rt.primitives, conservatives=rt.conservatives)
         jb_ = jb_._replace(simulation_buffers=jb_.simulation_buffers._replace(material_fields=mf))
         return sim.do_integration_step(jb_)[0]          # public API; reads (t, dt, min rho, min p) back = D2H
@@ -450,8 +454,10 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
         for _ in range(k_e2e):
             # H2D: the step's input state (the block's halo'd primitive buffer) from pinned host memory;
             # the conservatives are rebuilt from it on the device
-            rt.primitives.copy_(host_state, non_blocking=True)
+            stagebuf[0].copy_(host_state, non_blocking=True)
+            rt.primitives[sl].copy_(stagebuf[0], non_blocking=True)
             jb = one_step(jb)
+    stagebuf = [torch.empty(tuple(host_state.shape), dtype=torch.float64, device=rt.primitives.device) for _ in range(2)]
     ms_serial = timed(serial)
 
     # (2) pipelined: the upload of step k+1's host input (copy stream, device staging buffer) overlaps step k;
@@ -459,7 +465,6 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
     # timed region, and the first upload is not overlapped with anything.  `state_back`: the step's primitive
     # state also returns to pinned host memory (copy-back stream, overlapping the next step).
     k_pipe = max(k_e2e, args.steps)
-    stagebuf = [torch.empty_like(rt.primitives) for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     back_stream = torch.cuda.Stream()
     up = [torch.cuda.Event() for _ in range(2)]
@@ -482,7 +487,7 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
             if k + 1 < k_pipe:
                 upload(k + 1)
             cur.wait_event(up[k % 2])
-            rt.primitives.copy_(stagebuf[k % 2], non_blocking=True)
+            rt.primitives[sl].copy_(stagebuf[k % 2], non_blocking=True)
             free[k % 2].record(cur)
             jb = one_step(jb)
             if state_back:
@@ -505,9 +510,10 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
     e2e = {"value": cells_global * k_pipe / (ms_pipe * 1e-3) / 1e6, "unit": "MCUPS",
            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 40,
            "steps": k_pipe, "ms_per_step": ms_pipe / k_pipe,
-           "what": "per step: H2D of the block's halo'd primitive buffer from pinned host memory (copy stream, "
-                   "device staging buffer; the upload of step k+1 overlaps step k, the first upload overlaps "
-                   "nothing), device copy into the state, prim->cons on the device, "
+           "what": "per step: H2D of the block's primitive state (interior cells, as the reference's user supplies them) "
+                   "from pinned host memory (copy stream, device staging buffer; the upload of step k+1 overlaps step k, "
+                   "the first upload overlaps nothing), device copy into the halo'd state, prim->cons and the halo "
+                   "update on the device, "
                    "SimulationManager.do_integration_step, D2H of the step's SCALARS ONLY (t, dt, max speed, min rho, "
                    "min p: 40 B) -- the state stays on the device; PCIe-bound (the upload)",
            "serial": {"value": cells_global * k_e2e / (ms_serial * 1e-3) / 1e6, "steps": k_e2e,
@@ -521,7 +527,7 @@ def measure_e2e(args, rt, sim, buffers, tcv, time_now, dt_now, cells_global, wor
         outbuf = torch.empty_like(rt.primitives)
         ms_back = timed(lambda: pipelined(True, host_out, outbuf))
         e2e["state_back"] = {"value": cells_global * k_pipe / (ms_back * 1e-3) / 1e6, "unit": "MCUPS", "steps": k_pipe,
-                             "ms_per_step": ms_back / k_pipe, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 40,
+                             "ms_per_step": ms_back / k_pipe, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(host_out.numel() * 8) + 40,
                              "what": "the pipelined leg with the step's halo'd primitive state ALSO copied back to pinned "
                                      "host memory every step (device staging copy, then D2H on a copy-back stream that "
                                      "overlaps the next step and the next upload; PCIe is full duplex)"}
@@ -722,7 +728,8 @@ def main():
     rt.set_time_control(tcv.physical_simulation_time, tcv.physical_timestep_size)
     sampler = ClockSampler(dev)
     sampler.start()                       # runs through warm-up + timed region (same workload throughout)
-    small = workload in ("sod", "riemann2d")
+    # working set (five field-sized buffers) within a few L2 sizes: time step by step with a flush in between
+    small = workload in ("sod", "riemann2d") or 5 * field_gb < 0.5
     if small:
         config["l2"] = (f"working set {5 * field_gb * 1e3:.0f} MB: every step timed separately (CUDA events) with a "
                         f"512 MB L2 flush between steps, outside the timed spans; the step is replayed from a CUDA graph")
@@ -846,7 +853,9 @@ def main():
                             "1063 per axis, + 43 per stage update; div and sqrt count 1 each), NOT executed instructions",
         "traffic": traffic,
         "traffic_source": (f"{NCU_TRAFFIC_512['file']} (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                           f"launch at 512^3; a constant from that capture, not measured in this run)" if traffic else None),
+                           f"launch at 512^3 -- for the z + epilogue kernel the STAGE-0 instantiation, which reads no U^n: 200 B/cell "
+                           f"algorithmic against 240 in stages 1 and 2; a constant from that capture, not measured in this run)"
+                           if traffic else None),
         "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "bytes_per_cell_launch": KERNEL_BYTES[dom], "peak_source": peak_src},
         "kernel_ms": kernel_ms, "kernel_ms_is": "per RK stage (sum over the launches of the kind in one stage)",

@@ -330,15 +330,16 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
   // MUSCL3 with a slope limiter
   const double delta_central = (j == 0) ? (q3 - q2) : (q2 - q3);
   const double delta_upwind = (j == 0) ? (q2 - q1) : (q1 - q2);
-  const double r = (delta_upwind >= eps) ? delta_central / (delta_upwind + 1e-10)
-                                         : (delta_central + eps) / (delta_upwind + eps);
+  // one reciprocal: the two forms of the ratio differ in numerator / denominator only (select first, divide once)
+  const bool big = delta_upwind >= eps;
+  const double r = gdiv(big ? delta_central : delta_central + eps, big ? delta_upwind + 1e-10 : delta_upwind + eps);
   double lim;
-  if (id == ALT_KOREN) lim = fmax(0.0, fmin(2.0 * r, fmin((1.0 + 2.0 * r) / 3.0, 2.0)));
+  if (id == ALT_KOREN) lim = fmax(0.0, fmin(2.0 * r, fmin(gdiv(1.0 + 2.0 * r, 3.0), 2.0)));
   else if (id == ALT_MC) lim = fmax(0.0, fmin(2.0 * r, fmin((1.0 + r) / 2.0, 2.0)));
   else if (id == ALT_MINMOD) lim = fmax(0.0, fmin(1.0, r));
   else if (id == ALT_SUPERBEE) lim = fmax(0.0, fmax(fmin(1.0, 2.0 * r), fmin(2.0, r)));
-  else if (id == ALT_VANALBADA) lim = fmax(0.0, r) * (1.0 + r) / (1.0 + r * r);
-  else lim = fmax(0.0, 2.0 * r) / (1.0 + fabs(r));   // ALT_VANLEER
+  else if (id == ALT_VANALBADA) lim = gdiv(fmax(0.0, r) * (1.0 + r), 1.0 + r * r);
+  else lim = gdiv(fmax(0.0, 2.0 * r), 1.0 + fabs(r));   // ALT_VANLEER
   return (j == 0) ? q2 + 0.5 * lim * delta_upwind : q2 - 0.5 * lim * delta_upwind;
 }
 

@@ -304,3 +304,28 @@ def test_callbacks_are_called_with_the_reference_hook_names(monkeypatch):
             return rhs_buffers
     with pytest.raises(NotImplementedError, match="after_compute_rhs"):
         run([Rhs()])
+
+
+def test_bench_line_contract_on_a_small_grid():
+    """`python bench.py --cells 64` as the driver launches it (one process, N = 1): the JSON line carries every key of the
+    bench contract, the e2e leg (host interior upload -> halo update -> public API step) moved the bytes it declares and
+    left a finite state, and the kernels counted as launched are this library's."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cells", "64", "--steps", "3", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["unit"] == "MCUPS" and line["dtype"] == "f64" and line["n_gpus"] == 1 and line["steps"] == 3
+    assert line["value"] > 0 and line["gpu_launches"] >= 3 * 3 * 3          # >= 3 sweeps x 3 stages x 3 steps
+    assert line["roofline"]["bound"] == "fp64" and 0 < line["roofline"]["frac"] < 1
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 5 * 64 ** 3 * 8 and e2e["d2h_bytes_per_step"] >= 40
+    assert 0 < e2e["value"] <= line["value"] * 1.05
+    assert e2e["state_back"]["value"] > 0 and e2e["state_back"]["d2h_bytes_per_step"] > e2e["h2d_bytes_per_step"]
+    st = line["state"]
+    assert np.isfinite([st["time"], st["dt"], st["min_density"], st["min_pressure"]]).all() and st["min_density"] > 0
