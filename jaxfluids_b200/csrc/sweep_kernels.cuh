@@ -193,6 +193,12 @@ __device__ __forceinline__ void load_cell_in(const SweepGeom& g, const SweepArgs
 // PERIODIC / SYMMETRY / ZEROGRADIENT faces is the image of exactly one interior cell within nh of
 // that face, so the thread that produced the cell also writes its images (prims, and cons
 // recomputed from the image prims, :248-250).  i = interior index along the role axis.
+//
+// Cost matters here: in the rows kernel every row end is such a cell, so one warp iteration in six takes this path.
+// The images of ONE face are one value written `count` times (count = 1, or nh for ZEROGRADIENT / DIRICHLET), so a
+// face reduces to a small descriptor and ONE out-of-line writer (write_images) holds the only copy of the image
+// arithmetic (velocity flip / wall reflection, boundary data, conservatives with the IEEE division of the
+// halo-fill kernel, ten stores).
 struct HaloOut {
   double* prims;
   double* cons;
@@ -203,11 +209,17 @@ struct HaloOut {
 
 // wall = nullptr: copy, negating velocity component flip_var (1..3; -1 = none).  wall != nullptr: no-slip wall
 // moving with (u, v, w) = wall[0..2]: every velocity component becomes 2 u_wall - u (halos/outer/material.py:510-512).
-// fd / face / tidx / tcount: the face's device-resident boundary data, applied on top (apply_face_data)
-__device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, double p0, double p1, double p2, double p3,
-                                           double p4, int flip_var, const double* wall, const FaceData* fd, int face,
-                                           long long tidx, long long tcount) {
+// fixed != nullptr: the face's DIRICHLET constants replace the cell's primitives.  fd / face / tidx / tcount: the
+// face's device-resident boundary data, applied on top (apply_face_data).  The image goes to dst, dst + dinc, ...
+static __device__ __noinline__ void write_images(double* prims, double* cons, long long dst, long long dinc, int count,
+                                                 long long vst, double gamma, double p0, double p1, double p2, double p3,
+                                                 double p4, int flip_var, const double* wall, const double* fixed,
+                                                 const FaceData* fd, int face, long long tidx, long long tcount) {
   double q[5] = {p0, p1, p2, p3, p4};
+  if (fixed) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) q[v] = fixed[v];
+  }
   if (wall) {
 #pragma unroll
     for (int v = 1; v < 4; ++v) q[v] = 2 * wall[v - 1] - q[v];
@@ -217,64 +229,57 @@ __device__ __forceinline__ void halo_image(const HaloOut& h, long long dst, doub
   }
   if (fd) apply_face_data(*fd, face, tidx, tcount, q);
   double c[5];
-  cons_from_prims(q, h.gamma, c);
+  cons_from_prims(q, gamma, c);
+#pragma unroll 1
+  for (int l = 0; l < count; ++l, dst += dinc) {
 #pragma unroll
-  for (int v = 0; v < 5; ++v) {
-    h.prims[dst + v * h.vst] = q[v];
-    h.cons[dst + v * h.vst] = c[v];
+    for (int v = 0; v < 5; ++v) {
+      prims[dst + v * vst] = q[v];
+      cons[dst + v * vst] = c[v];
+    }
   }
 }
 
-// one role axis of the images of a cell; wall_hi / wall_lo: wall velocities of the two faces of this axis;
-// tidx / tcount: the cell's index / the cell count in the transverse plane of this axis (face data)
-__device__ __forceinline__ void halo_images_axis(const HaloOut& h, int bhi, int blo, long long hidx, const double (&p)[5],
-                                                 int ax, int n, int i, long long stride, const double* wall_hi,
-                                                 const double* wall_lo, const double* dir_hi, const double* dir_lo,
-                                                 const FaceData* fd, long long tidx, long long tcount,
-                                                 double* const* peer_prims, double* const* peer_cons) {
-  if (n <= 1) return;
-  const int nh = h.nh;
-  const int fhi = 2 * ax, flo = 2 * ax + 1;
-  // faces shared with another block: the nh cells next to the face are the neighbour's halo cells beyond ITS opposite
-  // face -- the same index arithmetic as a periodic image, into the neighbour's buffers
-  if (blo == JXF_BC_NEIGHBOR && peer_prims[flo]) {
-    const HaloOut hp{peer_prims[flo], peer_cons[flo], h.vst, h.gamma, h.nh};
-    if (i < nh) halo_image(hp, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, flo, 0, 0);
+// the images one cell owes to ONE face of a role axis (high: east / north / top).  bc: the face's rule; i / n / stride:
+// the cell's index, the cell count and the element stride along the axis; tidx / tcount: face-data indexing.
+__device__ __forceinline__ void face_images(const HaloOut& own, const SweepArgs& a, const FaceData* fd, int bc, bool high,
+                                            int ax, int n, int i, long long stride, long long hidx, const double (&p)[5],
+                                            long long tidx, long long tcount) {
+  const int nh = own.nh;
+  const int face = 2 * ax + (high ? 0 : 1);
+  const bool at_face = high ? (i >= n - nh) : (i < nh);       // within nh of THIS face
+  const bool at_opposite = high ? (i < nh) : (i >= n - nh);   // ... of the other face of the axis
+  const long long out = high ? stride : -stride;              // one cell outwards through this face
+  double* bp = own.prims;
+  double* bq = own.cons;
+  long long dst = 0, dinc = 0;
+  int count = 0, flip = -1;
+  const double* wall = nullptr;
+  const double* fixed = nullptr;
+  bool with_fd = true;
+  if (bc == JXF_BC_SYMMETRY || bc == JXF_BC_WALL) {           // mirror image across the face
+    if (at_face) {
+      count = 1;
+      dst = hidx + (long long)(high ? 2 * (n - i) - 1 : -1 - 2 * i) * stride;
+      if (bc == JXF_BC_SYMMETRY) flip = 1 + ax; else wall = a.wall[face];
+    }
+  } else if (bc == JXF_BC_PERIODIC) {                         // this face's halo = the cells next to the OTHER face
+    if (at_opposite) { count = 1; dst = hidx + (long long)n * out; with_fd = false; }
+  } else if (bc == JXF_BC_ZEROGRADIENT || bc == JXF_BC_DIRICHLET) {   // the boundary-adjacent cell writes all nh layers
+    if (high ? (i == n - 1) : (i == 0)) {
+      count = nh; dst = hidx + out; dinc = out;
+      if (bc == JXF_BC_DIRICHLET) fixed = a.dirichlet[face];
+    }
+  } else if (bc == JXF_BC_NEIGHBOR) {
+    // shared with another block: the nh cells next to the face are the neighbour's halo cells beyond ITS opposite face --
+    // the index arithmetic of a periodic image, into the neighbour's (peer-mapped) buffers
+    if (at_face && a.peer_prims[face]) {
+      count = 1; bp = a.peer_prims[face]; bq = a.peer_cons[face]; dst = hidx - (long long)n * out; with_fd = false;
+    }
   }
-  if (bhi == JXF_BC_NEIGHBOR && peer_prims[fhi]) {
-    const HaloOut hp{peer_prims[fhi], peer_cons[fhi], h.vst, h.gamma, h.nh};
-    if (i >= n - nh) halo_image(hp, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, fhi, 0, 0);
-  }
-  // low side (west / south / bottom)
-  if (blo == JXF_BC_SYMMETRY) {
-    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax, nullptr, fd, flo, tidx, tcount);
-  } else if (blo == JXF_BC_WALL) {
-    if (i < nh) halo_image(h, hidx + (long long)(-1 - 2 * i) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_lo, fd, flo, tidx, tcount);
-  } else if (blo == JXF_BC_PERIODIC) {
-    if (i >= n - nh) halo_image(h, hidx - (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, flo, 0, 0);
-  } else if (blo == JXF_BC_ZEROGRADIENT) {
-    if (i == 0)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx - (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, fd, flo, tidx, tcount);
-  } else if (blo == JXF_BC_DIRICHLET) {       // constants: written by the thread of the boundary-adjacent cell
-    if (i == 0)
-      for (int l = 1; l <= nh; ++l)
-        halo_image(h, hidx - (long long)l * stride, dir_lo[0], dir_lo[1], dir_lo[2], dir_lo[3], dir_lo[4], -1, nullptr, fd, flo, tidx, tcount);
-  }
-  // high side (east / north / top)
-  if (bhi == JXF_BC_SYMMETRY) {
-    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], 1 + ax, nullptr, fd, fhi, tidx, tcount);
-  } else if (bhi == JXF_BC_WALL) {
-    if (i >= n - nh) halo_image(h, hidx + (long long)(2 * (n - i) - 1) * stride, p[0], p[1], p[2], p[3], p[4], -1, wall_hi, fd, fhi, tidx, tcount);
-  } else if (bhi == JXF_BC_PERIODIC) {
-    if (i < nh) halo_image(h, hidx + (long long)n * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, nullptr, fhi, 0, 0);
-  } else if (bhi == JXF_BC_ZEROGRADIENT) {
-    if (i == n - 1)
-      for (int l = 1; l <= nh; ++l) halo_image(h, hidx + (long long)l * stride, p[0], p[1], p[2], p[3], p[4], -1, nullptr, fd, fhi, tidx, tcount);
-  } else if (bhi == JXF_BC_DIRICHLET) {
-    if (i == n - 1)
-      for (int l = 1; l <= nh; ++l)
-        halo_image(h, hidx + (long long)l * stride, dir_hi[0], dir_hi[1], dir_hi[2], dir_hi[3], dir_hi[4], -1, nullptr, fd, fhi, tidx, tcount);
-  }
+  if (count)
+    write_images(bp, bq, dst, dinc, count, own.vst, own.gamma, p[0], p[1], p[2], p[3], p[4], flip, wall, fixed,
+                 with_fd ? fd : nullptr, face, tidx, tcount);
 }
 
 // OUT OF LINE on purpose: executed only by the thin shell of boundary-adjacent cells; keeping it out of
@@ -333,23 +338,28 @@ static __device__ __noinline__ void halo_images_cell(const SweepGeom& g, const S
   const HaloOut h{a.prims_out, a.cons_out, g.vst, a.gamma, a.nh};
   const double p[5] = {p0, p1, p2, p3, p4};
   const FaceData* fd = a.has_face_data ? &a.face_data : nullptr;
-  // transverse index / count per PHYSICAL face axis (face data is laid out over (t1, t2) = the two other physical axes
-  // in increasing order, t2 fastest): only when the stage carries face data
-  long long tidx[3] = {0, 0, 0}, tcnt[3] = {0, 0, 0};
-  if (fd) {
-    int idx[3];
-    idx[g.axA] = iA; idx[g.ax1] = i1; idx[g.ax2] = i2;
-    const int* n = a.n_phys;
-    tidx[0] = (long long)idx[1] * n[2] + idx[2]; tcnt[0] = (long long)n[1] * n[2];
-    tidx[1] = (long long)idx[0] * n[2] + idx[2]; tcnt[1] = (long long)n[0] * n[2];
-    tidx[2] = (long long)idx[0] * n[1] + idx[1]; tcnt[2] = (long long)n[0] * n[1];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int n = (r == 0) ? g.nA : (r == 1) ? g.n1_full : g.n2;
+    const int i = (r == 0) ? iA : (r == 1) ? i1 : i2;
+    // every rule takes its images from cells within nh of one of the axis' two faces
+    if (n <= 1 || (i >= a.nh && i < n - a.nh)) continue;
+    const int ax = (r == 0) ? g.axA : (r == 1) ? g.ax1 : g.ax2;
+    const long long stride = (r == 0) ? g.sA : (r == 1) ? g.s1 : g.s2;
+    const int bhi = (r == 0) ? g.bcA_hi : (r == 1) ? g.bc1_hi : g.bc2_hi;
+    const int blo = (r == 0) ? g.bcA_lo : (r == 1) ? g.bc1_lo : g.bc2_lo;
+    // face data is laid out over (t1, t2) = the two other PHYSICAL axes in increasing order, t2 fastest
+    long long tidx = 0, tcnt = 0;
+    if (fd) {
+      const int t1 = (ax == 0) ? 1 : 0, t2 = (ax == 2) ? 1 : 2;
+      const int j1 = (t1 == g.axA) ? iA : (t1 == g.ax1) ? i1 : i2;
+      const int j2 = (t2 == g.axA) ? iA : (t2 == g.ax1) ? i1 : i2;
+      tidx = (long long)j1 * a.n_phys[t2] + j2;
+      tcnt = (long long)a.n_phys[t1] * a.n_phys[t2];
+    }
+    face_images(h, a, fd, blo, false, ax, n, i, stride, hidx, p, tidx, tcnt);
+    face_images(h, a, fd, bhi, true, ax, n, i, stride, hidx, p, tidx, tcnt);
   }
-  halo_images_axis(h, g.bcA_hi, g.bcA_lo, hidx, p, g.axA, g.nA, iA, g.sA, a.wall[2 * g.axA], a.wall[2 * g.axA + 1],
-                   a.dirichlet[2 * g.axA], a.dirichlet[2 * g.axA + 1], fd, tidx[g.axA], tcnt[g.axA], a.peer_prims, a.peer_cons);
-  halo_images_axis(h, g.bc1_hi, g.bc1_lo, hidx, p, g.ax1, g.n1_full, i1, g.s1, a.wall[2 * g.ax1], a.wall[2 * g.ax1 + 1],
-                   a.dirichlet[2 * g.ax1], a.dirichlet[2 * g.ax1 + 1], fd, tidx[g.ax1], tcnt[g.ax1], a.peer_prims, a.peer_cons);
-  halo_images_axis(h, g.bc2_hi, g.bc2_lo, hidx, p, g.ax2, g.n2, i2, g.s2, a.wall[2 * g.ax2], a.wall[2 * g.ax2 + 1],
-                   a.dirichlet[2 * g.ax2], a.dirichlet[2 * g.ax2 + 1], fd, tidx[g.ax2], tcnt[g.ax2], a.peer_prims, a.peer_cons);
 }
 
 #ifdef JXF_WITH_STRIDED   // the register-window predecessor of sweep_march: A/B builds only (-DJXF_WITH_STRIDED)
