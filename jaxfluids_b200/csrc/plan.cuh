@@ -206,7 +206,7 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       memset(&im, 0, sizeof(im));
       ra.tma_in = 0;
       ra.lead = g.off[A] & 1;             // the U / U^n boxes start `lead` cells before the iteration's first cell (16 B)
-      if (EPI && map && !s->no_tma_in && a.has_prev && a.rhs && a.cons_in) {
+      if (JXF_ROWS_TMA_IN && EPI && map && !s->no_tma_in && a.has_prev && a.rhs && a.cons_in) {
         const long long slab_off = slab ? (long long)a.sub_lo * g.st[0] : 0;
         bool ok = encode_rows_input_map(s, &im.u, a.cons_in - h0 - slab_off, false, 0, 0) &&
                   encode_rows_input_map(s, &im.rhs, a.rhs, true, slab ? a.sub_n : g.n[0], sg.rvst);

@@ -706,6 +706,9 @@ struct RowsArgs {
 
 // Tensor maps of the epilogue's cell inputs (plan.cuh encode_rows_input_map): boxes of kInCells (U, U^n; halo'd
 // conservative buffers) / 32 (rhs accumulator) cells x 5 variables, landing in the per-warp input buffers
+#ifndef JXF_ROWS_TMA_IN
+#define JXF_ROWS_TMA_IN 0
+#endif
 constexpr int kInCells = 34;                    // 32 cells + lead, rounded to a 16-byte multiple
 constexpr int kInUBytes = 5 * kInCells * 8;     // 1360
 constexpr int kInRBytes = 5 * 32 * 8;           // 1280
@@ -731,7 +734,10 @@ sweep_rows(const __grid_constant__ SweepGeom g, const __grid_constant__ SweepArg
   __shared__ alignas(128) unsigned char win_raw[4 * 2 * kWinStride];
   __shared__ alignas(8) uint64_t bars[4 * 2];
   // cell inputs of the epilogue (U, U^n, rhs sum), staged by TMA with the windows: 2 x 4 KB per warp
-  constexpr bool kTmaIn = (EPI != 0) && (USE_TMA != 0);
+  // Compiled in only with -DJXF_ROWS_TMA_IN=1: measured twice on the same box against per-lane loads issued at the top of
+  // the iteration -- 7.55 vs 7.57 ms (profiles/r02i) and, with the lean halo path, 7.58 vs 7.47 ms (profiles/r02p): the
+  // three extra TMA issues and their waits cost ~60 executed instructions per face-warp against the 15 LDG they replace
+  constexpr bool kTmaIn = (EPI != 0) && (USE_TMA != 0) && (JXF_ROWS_TMA_IN != 0);
   __shared__ alignas(128) unsigned char in_raw[kTmaIn ? 4 * 2 * kInStride : 16];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;

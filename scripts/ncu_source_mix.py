@@ -14,6 +14,8 @@ hdr = rows[hdr_i]
 ix = {h: i for i, h in enumerate(hdr)}
 ex = collections.Counter()
 st = collections.Counter()
+by_count = collections.Counter()       # executed count of an instruction -> (how many instructions, total executed)
+by_count_n = collections.Counter()
 tot_ex = tot_s = 0
 for r in rows[hdr_i + 1:]:
     if len(r) < len(hdr) or not r[ix["Instructions Executed"]].isdigit():
@@ -24,6 +26,8 @@ for r in rows[hdr_i + 1:]:
     s = int(r[ix["# Samples"]] or 0)
     ex[op] += n
     st[op] += s
+    by_count[n] += n
+    by_count_n[n] += 1
     tot_ex += n
     tot_s += s
 print(f"total warp instr {tot_ex}  per unit {tot_ex/units:.1f}; samples {tot_s}")
@@ -31,3 +35,8 @@ fp64 = sum(v for k, v in ex.items() if k in ("DFMA", "DMUL", "DADD", "DSETP", "D
 print(f"FP64-pipe per unit {fp64/units:.1f}")
 for k, v in ex.most_common(28):
     print(f"  {k:8s} {v/units:8.1f} /unit   samples {100.0*st[k]/max(tot_s,1):5.1f}%")
+# where the instructions are executed: static instructions grouped by how often each one ran (hot loop = the units'
+# count; rarer groups are prologue, row set-up, the boundary-cell path)
+print("executed-count groups (count per instruction: static instructions, share of all executed):")
+for n, tot in sorted(by_count.items(), key=lambda kv: -kv[1])[:14]:
+    print(f"  {n:12d} x {by_count_n[n]:5d} instr  = {tot/units:8.1f} /unit  {100.0*tot/max(tot_ex,1):5.1f}%")
