@@ -509,6 +509,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
   s->no_march = getenv("JXF_NO_MARCH") && atoi(getenv("JXF_NO_MARCH")) != 0;
 #endif
   s->rows_group = getenv("JXF_ROWS_G") ? std::max(0, std::min(32, atoi(getenv("JXF_ROWS_G")))) : 0;
+  s->no_lane_defer = getenv("JXF_NO_LANE_DEFER") && atoi(getenv("JXF_NO_LANE_DEFER")) != 0;
   s->no_tma_in = getenv("JXF_NO_TMA_IN") && atoi(getenv("JXF_NO_TMA_IN")) != 0;   // A/B: per-lane loads of the cell inputs
   s->no_plain = getenv("JXF_NO_PLAIN") && atoi(getenv("JXF_NO_PLAIN")) != 0;   // A/B: option-carrying instantiations
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;
@@ -1139,8 +1140,7 @@ extern "C" int jxf_peer_wait(jxf_handle h, const int64_t* flags, int face_mask, 
   return check_launch("peer_wait");
 }
 
-extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream) {
-  if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill: null argument");
+int launch_halo_faces(const jxf_solver* h, double* prims, double* cons, int face_mask, cudaStream_t st) {
   HaloArgs a;
   a.prims = prims;
   a.cons = cons;
@@ -1149,7 +1149,7 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
   a.has_fd = h->has_face_data;
   long long maxcells = 0;
   for (int f = 0; f < 6; ++f) {
-    a.bc[f] = h->cfg.bc[f];
+    a.bc[f] = ((face_mask >> f) & 1) ? h->cfg.bc[f] : JXF_BC_INACTIVE;
     for (int k = 0; k < 3; ++k) a.wall[f][k] = h->cfg.wall_velocity[f][k];
     for (int k = 0; k < 5; ++k) a.dirichlet[f][k] = h->cfg.dirichlet[f][k];
     const int ax = f >> 1;
@@ -1160,11 +1160,16 @@ extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* st
   }
   if (maxcells > 0) {
     const int bx = (int)std::min<long long>((maxcells + 127) / 128, 148 * 16);
-    ProfScope prof(h, JXF_PROFILE_HALO, (cudaStream_t)stream);
-    halo_fill_kernel<<<dim3(bx, 6), 128, 0, (cudaStream_t)stream>>>(h->g, a);
-    int rc = check_launch("halo_fill");
-    if (rc) return rc;
+    ProfScope prof(h, JXF_PROFILE_HALO, st);
+    halo_fill_kernel<<<dim3(bx, 6), 128, 0, st>>>(h->g, a);
+    return check_launch("halo_fill");
   }
+  return JXF_OK;
+}
+
+extern "C" int jxf_halo_fill(jxf_handle h, double* prims, double* cons, void* stream) {
+  if (!h || !prims || !cons) return fail(JXF_ERR_BAD_ARG, "jxf_halo_fill: null argument");
+  if (int rc = launch_halo_faces(h, prims, cons, 0x3f, (cudaStream_t)stream)) return rc;
   if (dissipative(h)) return jxf_halo_fill_edges(h, prims, cons, stream);
   return JXF_OK;
 }

@@ -43,6 +43,7 @@ struct jxf_solver {
   FaceData face_data;  // jxf_set_face_data: device pointers owned by the caller
   int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
+  bool no_lane_defer;  // JXF_NO_LANE_DEFER=1: the rows kernel writes the halo images of its own axis' faces itself (A/B)
   bool no_tma_in;      // JXF_NO_TMA_IN=1: the rows kernel's epilogue loads its cell inputs per lane (A/B only)
   bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
@@ -78,6 +79,8 @@ struct ProfScope {
 
 // TMA descriptor of a halo'd field buffer for the rows kernel (nullptr: use the cp.async loader); jxf_b200.cu
 const CUtensorMap* get_rows_map(jxf_solver* s, const double* base);
+// halo_fill_kernel on the faces in face_mask only (jxf_b200.cu); prims / cons: buffer bases
+int launch_halo_faces(const jxf_solver* s, double* prims, double* cons, int face_mask, cudaStream_t st);
 bool encode_rows_input_map(const jxf_solver* s, CUtensorMap* out, const double* base, bool is_rhs, int rhs_planes,
                            long long rhs_vst);
 
@@ -110,6 +113,8 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   sg.vst = g.vst;
   sg.rvst = a.rvst_slab > 0 ? a.rvst_slab : g.rvst;
   sg.i1_base = 0;
+  sg.nearA_lo = s->cfg.nh;
+  sg.nearA_hi = g.n[A] - s->cfg.nh;
   // slab launches: a y / z sweep over the x planes [sub_lo, sub_lo + sub_n) only (x is role 1 of both in 3-D); the
   // field pointers move to the slab's first plane, the rhs pointer is the slab-sized accumulator as passed
   const bool slab = (A != 0) && a.sub_n > 0;
@@ -213,15 +218,34 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
         if (ok && a.blend) ok = a.cons_n && encode_rows_input_map(s, &im.un, a.cons_n - h0 - slab_off, false, 0, 0);
         ra.tma_in = ok ? 1 : 0;
       }
-      ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
-      if (map) {
-        sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map, im);
-      } else {
-        CUtensorMap dummy;
-        memset(&dummy, 0, sizeof(dummy));
-        sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy, im);
+      // The halo images of the two faces of THIS axis come from the row ends: one warp iteration in eight would take the
+      // out-of-line boundary-cell path with 5 active lanes.  Leave them to one halo_fill launch on those two faces after
+      // the sweep (0.3 GB of traffic at 512^3) and keep the fused images for the faces whose cells fill whole warps.
+      // Not with peer-mapped stores on these faces (they exist only inside the sweep), not for slab launches (the
+      // in-place stage defers on its own).
+      int defer_mask = 0;
+      if (EPI && a.fuse_halo && !slab && !s->no_lane_defer && !a.peer_prims[2 * A] && !a.peer_prims[2 * A + 1]) {
+        for (int f = 2 * A; f < 2 * A + 2; ++f)
+          if (a.bc[f] != JXF_BC_INACTIVE && a.bc[f] != JXF_BC_NEIGHBOR) defer_mask |= 1 << f;
+        if (defer_mask) {
+          sg.bcA_hi = sg.bcA_lo = JXF_BC_INACTIVE;
+          sg.nearA_lo = 0;
+          sg.nearA_hi = g.n[A];
+        }
       }
-      return check_launch("sweep_rows");
+      {
+        ProfScope prof(s, A + 3 * (EPI ? 1 : 0), st);
+        if (map) {
+          sweep_rows<A, RECON, RIEMANN, EPI, 1><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, *map, im);
+        } else {
+          CUtensorMap dummy;
+          memset(&dummy, 0, sizeof(dummy));
+          sweep_rows<A, RECON, RIEMANN, EPI, 0><<<(unsigned)blocks, 128, 0, st>>>(sg, a, ra, dummy, im);
+        }
+      }
+      if (int rc = check_launch("sweep_rows")) return rc;
+      if (defer_mask) return launch_halo_faces(s, a.prims_out - h0, a.cons_out - h0, defer_mask, st);
+      return JXF_OK;
     }
 #endif
     if (EPI && a.inplace)

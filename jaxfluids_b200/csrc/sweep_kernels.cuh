@@ -110,6 +110,9 @@ struct SweepGeom {
   long long rA, r1, r2;      // strides in the interior-only rhs buffer
   long long vst, rvst;       // variable strides
   int i1_base, n1_full;      // slab launches (jxf_stage_inplace): role 1 covers cells [i1_base, i1_base + n1) of n1_full
+  // cells with iA < nearA_lo or iA >= nearA_hi owe halo images to the faces of role A: nh / nA - nh, or 0 / nA when
+  // those faces are filled by a separate launch after the sweep (plan.cuh: rows kernel, every row END is such a cell)
+  int nearA_lo, nearA_hi;
 };
 
 #ifndef JXF_MIN_BLOCKS
@@ -326,7 +329,7 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
     if (E::halo(a)) {
       // boundary-adjacent cells only (a thin shell); warp-divergent by construction
       const int j1 = i1 + g.i1_base;      // global index along role 1 (slab launches)
-      const bool near = (iA < a.nh) | (iA >= g.nA - a.nh) | (j1 < a.nh) | (j1 >= g.n1_full - a.nh) | (i2 < a.nh) |
+      const bool near = (iA < g.nearA_lo) | (iA >= g.nearA_hi) | (j1 < a.nh) | (j1 >= g.n1_full - a.nh) | (i2 < a.nh) |
                         (i2 >= g.n2 - a.nh);
       if (near) halo_images_cell(g, a, hidx, p[0], p[1], p[2], p[3], p[4], iA, j1, i2);
     }
