@@ -43,7 +43,7 @@ struct jxf_solver {
   FaceData face_data;  // jxf_set_face_data: device pointers owned by the caller
   int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
-  bool no_lane_defer;  // JXF_NO_LANE_DEFER=1: the rows kernel writes the halo images of its own axis' faces itself (A/B)
+  bool no_lane_defer;  // default true; JXF_LANE_DEFER=1: the faces of the rows kernel's own axis are filled by a separate launch (A/B)
   bool no_tma_in;      // JXF_NO_TMA_IN=1: the rows kernel's epilogue loads its cell inputs per lane (A/B only)
   bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
@@ -218,11 +218,12 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
         if (ok && a.blend) ok = a.cons_n && encode_rows_input_map(s, &im.un, a.cons_n - h0 - slab_off, false, 0, 0);
         ra.tma_in = ok ? 1 : 0;
       }
-      // The halo images of the two faces of THIS axis come from the row ends: one warp iteration in eight would take the
-      // out-of-line boundary-cell path with 5 active lanes.  Leave them to one halo_fill launch on those two faces after
-      // the sweep (0.3 GB of traffic at 512^3) and keep the fused images for the faces whose cells fill whole warps.
-      // Not with peer-mapped stores on these faces (they exist only inside the sweep), not for slab launches (the
-      // in-place stage defers on its own).
+      // The halo images of the two faces of THIS axis come from the row ends: one warp iteration in eight takes the
+      // out-of-line boundary-cell path with 5 active lanes (0.31 ms of the 7.27 ms launch at 512^3).  JXF_LANE_DEFER=1
+      // leaves them to one halo_fill launch on those two faces after the sweep -- measured SLOWER in total (the separate
+      // launch takes 0.40 ms: 2.6 M row ends x 15 fields, every access a 40-byte segment in its own DRAM page, where the
+      // fused stores land in the lines the row's last cells are being written to; profiles/r02u_ab_lane_defer.txt), so it
+      // is off by default.  Never with peer-mapped stores on these faces, never for slab launches.
       int defer_mask = 0;
       if (EPI && a.fuse_halo && !slab && !s->no_lane_defer && !a.peer_prims[2 * A] && !a.peer_prims[2 * A + 1]) {
         for (int f = 2 * A; f < 2 * A + 2; ++f)
