@@ -510,6 +510,7 @@ extern "C" int jxf_create(const jxf_config* cfg, jxf_handle* out) {
 #endif
   s->rows_group = getenv("JXF_ROWS_G") ? std::max(0, std::min(32, atoi(getenv("JXF_ROWS_G")))) : 0;
   s->no_lane_defer = !(getenv("JXF_LANE_DEFER") && atoi(getenv("JXF_LANE_DEFER")) != 0);   // opt-in: measured slower
+  s->lean_images = getenv("JXF_LEAN_IMAGES") && atoi(getenv("JXF_LEAN_IMAGES")) != 0;
   s->no_tma_in = getenv("JXF_NO_TMA_IN") && atoi(getenv("JXF_NO_TMA_IN")) != 0;   // A/B: per-lane loads of the cell inputs
   s->no_plain = getenv("JXF_NO_PLAIN") && atoi(getenv("JXF_NO_PLAIN")) != 0;   // A/B: option-carrying instantiations
   s->force_rows = getenv("JXF_FORCE_ROWS") && atoi(getenv("JXF_FORCE_ROWS")) != 0;

@@ -44,6 +44,7 @@ struct jxf_solver {
   int has_face_data;
   int rows_group;      // JXF_ROWS_G=<1..32>: rows per warp work item of the rows kernel (tuning; 0 = automatic)
   bool no_lane_defer;  // default true; JXF_LANE_DEFER=1: the faces of the rows kernel's own axis are filled by a separate launch (A/B)
+  bool lean_images;    // JXF_LEAN_IMAGES=1: mirror / periodic images of the rows kernel's own axis written inline (A/B)
   bool no_tma_in;      // JXF_NO_TMA_IN=1: the rows kernel's epilogue loads its cell inputs per lane (A/B only)
   bool no_plain;       // JXF_NO_PLAIN=1: never use the RIEMANN_HLLC_PLAIN / compile-time-flag instantiations (A/B only)
   bool no_march;       // -DJXF_WITH_STRIDED builds, JXF_NO_MARCH=1: register-window strided kernel (A/B only)
@@ -115,6 +116,7 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
   sg.i1_base = 0;
   sg.nearA_lo = s->cfg.nh;
   sg.nearA_hi = g.n[A] - s->cfg.nh;
+  sg.leanA_lo = sg.leanA_hi = 0;
   // slab launches: a y / z sweep over the x planes [sub_lo, sub_lo + sub_n) only (x is role 1 of both in 3-D); the
   // field pointers move to the slab's first plane, the rhs pointer is the slab-sized accumulator as passed
   const bool slab = (A != 0) && a.sub_n > 0;
@@ -224,6 +226,14 @@ int launch_sweep(const jxf_solver* s, SweepArgs a, cudaStream_t st) {
       // launch takes 0.40 ms: 2.6 M row ends x 15 fields, every access a 40-byte segment in its own DRAM page, where the
       // fused stores land in the lines the row's last cells are being written to; profiles/r02u_ab_lane_defer.txt), so it
       // is off by default.  Never with peer-mapped stores on these faces, never for slab launches.
+      // SYMMETRY / PERIODIC faces of this axis without boundary data or peer stores: images written inline by
+      // finalize_cell (SweepGeom::leanA_*), the out-of-line path skips them
+      if (EPI && a.fuse_halo && s->lean_images && !a.has_face_data) {
+        const int khi = a.bc[2 * A], klo = a.bc[2 * A + 1];
+        const bool per = khi == JXF_BC_PERIODIC && klo == JXF_BC_PERIODIC;
+        if (per || khi == JXF_BC_SYMMETRY) { sg.leanA_hi = per ? 2 : 1; sg.bcA_hi = JXF_BC_INACTIVE; sg.nearA_hi = g.n[A]; }
+        if (per || klo == JXF_BC_SYMMETRY) { sg.leanA_lo = per ? 2 : 1; sg.bcA_lo = JXF_BC_INACTIVE; sg.nearA_lo = 0; }
+      }
       int defer_mask = 0;
       if (EPI && a.fuse_halo && !slab && !s->no_lane_defer && !a.peer_prims[2 * A] && !a.peer_prims[2 * A + 1]) {
         for (int f = 2 * A; f < 2 * A + 2; ++f)

@@ -113,6 +113,9 @@ struct SweepGeom {
   // cells with iA < nearA_lo or iA >= nearA_hi owe halo images to the faces of role A: nh / nA - nh, or 0 / nA when
   // those faces are filled by a separate launch after the sweep (plan.cuh: rows kernel, every row END is such a cell)
   int nearA_lo, nearA_hi;
+  // faces of role A whose images finalize_cell writes INLINE (no call): 0 = no, 1 = SYMMETRY, 2 = PERIODIC -- faces without
+  // boundary data / peer stores only; the generic path then sees these faces as INACTIVE (plan.cuh)
+  int leanA_lo, leanA_hi;
 };
 
 #ifndef JXF_MIN_BLOCKS
@@ -327,6 +330,23 @@ __device__ __forceinline__ void finalize_cell(const SweepGeom& g, const SweepArg
       red.add_cell(p, a.gamma, a.active_mask);
     }
     if (E::halo(a)) {
+      // mirror / periodic images across the faces of the sweep's own axis: in the rows kernel these are the row ends (one
+      // warp iteration in eight, 5 active lanes).  The image is the cell with one velocity negated, or the cell itself:
+      // destination and flip are formed here from kernel constants and handed to the one image writer, without the
+      // descriptor logic of halo_images_cell (which reads the launch's geometry through generic loads)
+      if ((g.leanA_lo | g.leanA_hi) && ((iA < a.nh) | (iA >= g.nA - a.nh))) {
+#pragma unroll 1
+        for (int end = 0; end < 2; ++end) {
+          const bool here = end ? (iA >= g.nA - a.nh) : (iA < a.nh);
+          // the cells at this end feed THIS end's face when it mirrors, the OTHER end's face when the axis is periodic
+          const int mine = end ? g.leanA_hi : g.leanA_lo, other = end ? g.leanA_lo : g.leanA_hi;
+          if (here & ((mine == 1) | (other == 2))) {
+            const long long off = (mine == 1) ? (end ? 2 * (g.nA - iA) - 1 : -1 - 2 * iA) : (end ? -g.nA : g.nA);
+            write_images(a.prims_out, a.cons_out, hidx + off * g.sA, 0, 1, g.vst, a.gamma, p[0], p[1], p[2], p[3], p[4],
+                         (mine == 1) ? 1 + g.axA : -1, nullptr, nullptr, nullptr, 0, 0, 0);
+          }
+        }
+      }
       // boundary-adjacent cells only (a thin shell); warp-divergent by construction
       const int j1 = i1 + g.i1_base;      // global index along role 1 (slab launches)
       const bool near = (iA < g.nearA_lo) | (iA >= g.nearA_hi) | (j1 < a.nh) | (j1 >= g.n1_full - a.nh) | (i2 < a.nh) |
