@@ -197,8 +197,9 @@ __device__ __forceinline__ double teno_a_ct(double eta, double Cr, double alpha_
   const double beta_bar = ceil(alpha_1 - alpha_2 * (1.0 - g)) - 1.0;
   return gpow10_neg(beta_bar);
 }
-static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
-                                               double q5) {
+// `id` known at compile time after inlining (reconstruct_generic_id below): only that stencil's branch survives.
+__device__ __forceinline__ double stencil_generic_inl(const int id, const int j, double q0, double q1, double q2, double q3,
+                                                      double q4, double q5) {
   const double eps = kStencilEps;
   if (id == ALT_WENO1) return q2;
   if (id == ALT_CENTRAL2) return 0.5 * ((j == 0) ? (q2 + q3) : (q3 + q2));    // buffer[i] + buffer[i+1] on both sides
@@ -343,9 +344,19 @@ static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, 
   return (j == 0) ? q2 + 0.5 * lim * delta_upwind : q2 - 0.5 * lim * delta_upwind;
 }
 
+// run-time id, out of line: the conservative-variable and flux-splitting paths
+static __device__ JXF_NOINLINE double stencil_generic(int id, int j, double q0, double q1, double q2, double q3, double q4,
+                                               double q5) {
+  return stencil_generic_inl(id, j, q0, q1, q2, q3, q4, q5);
+}
 __device__ __forceinline__ void stencil_generic_lr(int id, const double (&q)[6], double& left, double& right) {
   left = stencil_generic(id, 0, q[0], q[1], q[2], q[3], q[4], q[5]);
   right = stencil_generic(id, 1, q[5], q[4], q[3], q[2], q[1], q[0]);
+}
+template <int ID>
+__device__ __forceinline__ void stencil_const_lr(const double (&q)[6], double& left, double& right) {
+  left = stencil_generic_inl(ID, 0, q[0], q[1], q[2], q[3], q[4], q[5]);
+  right = stencil_generic_inl(ID, 1, q[5], q[4], q[3], q[2], q[1], q[0]);
 }
 
 // Frozen state of a face from the primitives of its two cells (eigendecomposition.py:120-281, single phase, ideal
@@ -389,22 +400,17 @@ __device__ __forceinline__ Frozen frozen_state(const double (&pL)[5], const doub
 // reconstruct() of the generic stencils: PRIMITIVE (high_order_godunov.py:267-280), CHAR-PRIMITIVE (:298-316 with
 // eigendecomposition.py:120-281, 425-431, 517-521) -- or, out of line, the two conservative forms -- reference order.
 // `mode` = reconstruction variable | (frozen_state == ROE) << 2.
-template <int A, bool CHAR>
-__device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], double gamma, double (&pl)[5],
-                                                    double (&pr)[5], int id, int mode) {
+// One face, one stencil: the window comes by reference, the ten stencil evaluations (5 variables x 2 sides) are inlined
+// with the stencil id a compile-time constant -- ONE out-of-line call per face instead of ten calls that each walk the
+// id chain and spill / reload around the call (the rows kernel spent 55 % of its stall samples there,
+// profiles/stalls_r02t_teno6a_rows.txt).  Same operations in the same order as before.
+template <int A, bool CHAR, int ID>
+static __device__ JXF_NOINLINE void reconstruct_generic_id(const double (&w)[5][6], double gamma, double (&pl)[5],
+                                                           double (&pr)[5], int mode) {
   using Id = AxisIds<A>;
-  if ((mode & 3) >= VAR_CONSERVATIVE) {
-    Win6 W;
+  if (!CHAR) {
 #pragma unroll
-    for (int v = 0; v < 5; ++v)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) W.w[v][k] = w[v][k];
-    const Vec10 o = reconstruct_conservative<A>(W, gamma, id, mode);
-#pragma unroll
-    for (int v = 0; v < 5; ++v) { pl[v] = o.l[v]; pr[v] = o.r[v]; }
-  } else if (!CHAR) {
-#pragma unroll
-    for (int v = 0; v < 5; ++v) stencil_generic_lr(id, w[v], pl[v], pr[v]);
+    for (int v = 0; v < 5; ++v) stencil_const_lr<ID>(w[v], pl[v], pr[v]);
   } else {
     double cL[5], cR[5];
 #pragma unroll
@@ -419,15 +425,15 @@ __device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], dou
     double q[6], l0, r0, l1, r1, l4, r4;
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = -k_u * w[Id::un][k] + k_p * w[4][k];
-    stencil_generic_lr(id, q, l0, r0);
+    stencil_const_lr<ID>(q, l0, r0);
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = w[0][k] - k_cc * w[4][k];
-    stencil_generic_lr(id, q, l1, r1);
+    stencil_const_lr<ID>(q, l1, r1);
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = k_u * w[Id::un][k] + k_p * w[4][k];
-    stencil_generic_lr(id, q, l4, r4);
-    stencil_generic_lr(id, w[Id::t0], pl[Id::t0], pr[Id::t0]);
-    stencil_generic_lr(id, w[Id::t1], pl[Id::t1], pr[Id::t1]);
+    stencil_const_lr<ID>(q, l4, r4);
+    stencil_const_lr<ID>(w[Id::t0], pl[Id::t0], pr[Id::t0]);
+    stencil_const_lr<ID>(w[Id::t1], pl[Id::t1], pr[Id::t1]);
     const double ccr = cc_ave * rho_ave;
     pl[0] = rho_ave * (l0 + l4) + l1;
     pl[Id::un] = c_ave * (-l0 + l4);
@@ -436,6 +442,32 @@ __device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], dou
     pr[Id::un] = c_ave * (-r0 + r4);
     pr[4] = ccr * (r0 + r4);
   }
+}
+
+template <int A, bool CHAR>
+__device__ __forceinline__ void reconstruct_generic(const double (&w)[5][6], double gamma, double (&pl)[5],
+                                                    double (&pr)[5], int id, int mode) {
+  if ((mode & 3) >= VAR_CONSERVATIVE) {
+    Win6 W;
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) W.w[v][k] = w[v][k];
+    const Vec10 o = reconstruct_conservative<A>(W, gamma, id, mode);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) { pl[v] = o.l[v]; pr[v] = o.r[v]; }
+    return;
+  }
+#define JXF_STENCIL_CASE(ID) case ID: reconstruct_generic_id<A, CHAR, ID>(w, gamma, pl, pr, mode); break;
+  switch (id) {
+    JXF_STENCIL_CASE(ALT_WENO5Z) JXF_STENCIL_CASE(ALT_WENO5JS) JXF_STENCIL_CASE(ALT_WENO1) JXF_STENCIL_CASE(ALT_WENO3JS)
+    JXF_STENCIL_CASE(ALT_WENO3Z) JXF_STENCIL_CASE(ALT_TENO5) JXF_STENCIL_CASE(ALT_WENO6CU) JXF_STENCIL_CASE(ALT_KOREN)
+    JXF_STENCIL_CASE(ALT_MC) JXF_STENCIL_CASE(ALT_MINMOD) JXF_STENCIL_CASE(ALT_SUPERBEE) JXF_STENCIL_CASE(ALT_VANALBADA)
+    JXF_STENCIL_CASE(ALT_VANLEER) JXF_STENCIL_CASE(ALT_WENO3N) JXF_STENCIL_CASE(ALT_CENTRAL2) JXF_STENCIL_CASE(ALT_TENO6)
+    JXF_STENCIL_CASE(ALT_TENO5A) JXF_STENCIL_CASE(ALT_TENO6A)
+    default: break;
+  }
+#undef JXF_STENCIL_CASE
 }
 
 // ===========================================================================
