@@ -408,10 +408,10 @@ template <int A, bool CHAR, int ID>
 static __device__ JXF_NOINLINE void reconstruct_generic_id(const double (&w)[5][6], double gamma, double (&pl)[5],
                                                            double (&pr)[5], int mode) {
   using Id = AxisIds<A>;
-  // the six-point and adaptive stencils are 400-700 instructions per evaluation: ten inlined copies would not fit the
-  // instruction cache (measured: TENO6-A x / y sweeps 4.03 -> 4.7-4.9 ms fully unrolled), so their five rows are a rolled
-  // loop over a staged copy of the rows -- two evaluations per iteration
-  constexpr bool kRolled = (ID == ALT_TENO6 || ID == ALT_TENO6A || ID == ALT_WENO6CU || ID == ALT_TENO5A);
+  // the TENO6 / adaptive stencils are 500-700 instructions per evaluation: their five rows are a rolled loop over a staged
+  // copy of the rows, two evaluations per iteration (measured at 256^3, profiles/r02x_ / r02y_generic_timing.txt: TENO6-A
+  // z + epilogue 7.09 ms with ten inlined copies, 5.80 ms rolled; WENO6-CU the other way round, 786 vs 667 MCUPS)
+  constexpr bool kRolled = (ID == ALT_TENO6 || ID == ALT_TENO6A || ID == ALT_TENO5A);
   if (!CHAR) {
     if constexpr (kRolled) {
 #pragma unroll 1
