@@ -68,16 +68,47 @@ class OracleBlockSolver(OracleSolver):
     def _faces_only(self):
         return self._outer(super()._faces_only())
 
+    def _physical_edges(self, p, c):
+        """jxf_halo_fill_edges on a block: the reference's edge rule for edges between two PHYSICAL faces only; edges next
+        to a shared face arrive with the widened slabs of the exchange (runtime._halo_update_with_edges)"""
+        s = self.setup
+        p2, c2 = port.edge_halo_fill(p, c, self._outer())
+        nh = s.nh
+        for edge in port.EDGES:
+            fa, fb = edge.split("_")
+            axa, axb = port.FACE_AXIS[fa], port.FACE_AXIS[fb]
+            if axa not in s.active or axb not in s.active or "NEIGHBOR" in (s.bc[fa], s.bc[fb]):
+                continue
+            sl = [slice(None)] + list(s.interior)
+            sl[1 + axa] = port._edge_range(fa, None, nh)
+            sl[1 + axb] = port._edge_range(fb, None, nh)
+            p[tuple(sl)] = p2[tuple(sl)]
+            c[tuple(sl)] = c2[tuple(sl)]
+        return p, c
+
     def halo_fill(self, prims, cons):
-        keep = self.setup
-        self.setup = self._outer()
-        try:
-            super().halo_fill(prims, cons)
-        finally:
-            self.setup = keep
+        s = self.setup
+        with np.errstate(all="ignore"):
+            p, c = port.halo_fill(prims.numpy(), cons.numpy(), self._faces_only())     # physical faces
+            if s.is_dissipative and len(s.active) > 1:
+                p, c = self._physical_edges(p, c)
+        prims.copy_(torch.as_tensor(p))
+        cons.copy_(torch.as_tensor(c))
+
+    def halo_fill_edges(self, prims, cons):
+        with np.errstate(all="ignore"):
+            p, c = self._physical_edges(prims.numpy().copy(), cons.numpy().copy())
+        prims.copy_(torch.as_tensor(p))
+        cons.copy_(torch.as_tensor(c))
+
+    def temperature(self, prims):
+        with np.errstate(all="ignore"):
+            return torch.as_tensor(port.temperature(prims.numpy(), self.setup))
 
     # -- face slabs ------------------------------------------------------------------------------------------------
-    def _slab(self, face, layers, halo):
+    def _slab(self, face, layers, halo, ext=0):
+        """ext (jxf_pack_face_ext): transverse widening over the nh halo cells -- bit 0 / 1: low / high side of the slower
+        transverse axis, bit 2 / 3: of the faster one"""
         s = self.setup
         nh, ax = s.nh, FACE_AX[face]
         n = s.cells[ax]
@@ -88,25 +119,30 @@ class OracleBlockSolver(OracleSolver):
             rng = slice(nh + n - layers, nh + n) if hi else slice(nh, nh + layers)
         sl = [slice(None)] + list(s.interior)
         sl[1 + ax] = rng
+        t1, t2 = (1 if ax == 0 else 0), (1 if ax == 2 else 2)
+        for bit, t in ((0, t1), (2, t2)):
+            if s.cells[t] > 1:
+                lo = nh - (nh if ext & (1 << bit) else 0)
+                up = nh + s.cells[t] + (nh if ext & (2 << bit) else 0)
+                sl[1 + t] = slice(lo, up)
         return tuple(sl)
 
     def face_slab_elems(self, face, ext=0, layers=None):
-        assert ext == 0
         s = self.setup
         layers = s.nh if layers is None else layers
-        t = [s.cells[i] for i in range(3) if i != FACE_AX[face]]
-        return 5 * layers * t[0] * t[1]
+        shape = np.empty(s.shape, dtype=np.int8)[self._slab(face, layers, False, ext)].shape
+        return int(np.prod(shape))
 
     def pack_face(self, face, prims, buf, ext=0, layers=None):
         layers = self.setup.nh if layers is None else layers
         CALLS["pack"].append(layers)
-        src = prims.numpy()[self._slab(face, layers, halo=False)]
+        src = prims.numpy()[self._slab(face, layers, False, ext)]
         buf[:src.size].copy_(torch.as_tensor(np.ascontiguousarray(src).ravel()))
 
     def unpack_face(self, face, buf, prims, cons, ext=0, layers=None):
         layers = self.setup.nh if layers is None else layers
         CALLS["unpack"].append(layers)
-        sl = self._slab(face, layers, halo=True)
+        sl = self._slab(face, layers, True, ext)
         shape = prims.numpy()[sl].shape
         got = buf.numpy()[:int(np.prod(shape))].reshape(shape)
         prims.numpy()[sl] = got
@@ -170,6 +206,14 @@ class OracleBlockSolver(OracleSolver):
         if info is not None:
             info.copy_(red)
         d = s.dx_min / (np.float64(red[0].item()) + port.EPS)          # time_step_size.py:15-157, global maximum
+        if s.is_dissipative:           # :111-135 with constant mu / lambda: max(mu / rho) = mu / min(rho) (finish_step_kernel)
+            one = np.ones(1)
+            dx2 = s.dx_min * s.dx_min
+            rho_min = np.float64(red[1].item())
+            if s.is_viscous_flux:
+                d = np.minimum(d, 3.0 / 14.0 * dx2 / (port._dynamic_viscosity(one, s)[0] / rho_min + port.EPS))
+            if s.is_heat_flux:
+                d = np.minimum(d, 0.1 * dx2 / (port._thermal_conductivity(one, s)[0] / (rho_min * s.cp) + port.EPS))
         dt.fill_(float(d * s.cfl))
         self.reduce_reset(red)
 
@@ -179,6 +223,11 @@ bc = os.environ["JXF_BC"]
 nsteps = int(os.environ["JXF_STEPS"])
 cells = tuple(int(v) for v in os.environ["JXF_CELLS"].split(","))
 s = H.make_setup(cells, bc=bc, gamma=1.4, length=1.0)
+visc = os.environ.get("JXF_VISC", "0") == "1"
+if visc:
+    s.is_viscous_flux = s.is_heat_flux = True
+    s.dynamic_viscosity, s.bulk_viscosity = 0.02, 0.003
+    s.thermal_conductivity_model, s.prandtl_number, s.gas_constant = "PRANDTL", 0.71, 1.0
 prims0 = H.smooth_ic(s, seed=21, amp=0.1)
 case = {
   "general": {"case_name": "mg", "end_step": nsteps, "save_path": "./results"},
@@ -192,6 +241,12 @@ num = {"conservatives": {"halo_cells": 5, "time_integration": {"integrator": "RK
        "convective_fluxes": {"convective_solver": "GODUNOV", "godunov": {"riemann_solver": "HLLC", "signal_speed": "EINFELDT",
        "reconstruction_stencil": "WENO5-Z", "reconstruction_variable": "CHAR-PRIMITIVE"}}},
        "active_physics": {"is_convective_flux": True}, "output": {"logging": {"level": "NONE"}}}
+if visc:
+    num["active_physics"].update(is_viscous_flux=True, is_heat_flux=True)
+    num["conservatives"]["dissipative_fluxes"] = {"reconstruction_stencil": "CENTRAL4", "derivative_stencil_center": "CENTRAL4",
+                                                  "derivative_stencil_face": "CENTRAL4"}
+    case["material_properties"]["transport"] = {"dynamic_viscosity": {"model": "CUSTOM", "value": 0.02}, "bulk_viscosity": 0.003,
+                                                "thermal_conductivity": {"model": "PRANDTL", "prandtl_number": 0.71}}
 OracleSolver.reference_setup = s
 RT.BlockSolver = OracleBlockSolver
 im = InputManager(case, num)
@@ -203,7 +258,7 @@ user = prims0[[0] + [1 + i for i in active] + [4]]
 buf = init.initialization(user_prime_init=user)
 sim = SimulationManager(im)
 rt = sim.runtime
-assert rt.neighbors and rt.stage_layers == int(os.environ.get("JXF_EXCHANGE_LAYERS", "3").replace("full", "5"))
+assert rt.neighbors and rt.stage_layers == (5 if visc else int(os.environ.get("JXF_EXCHANGE_LAYERS", "3").replace("full", "5")))
 sim.simulate(buf)
 out = sim.final_buffers
 di = im.domain_information
@@ -248,12 +303,16 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("split,cells,bc,layers", [((2, 1, 1), (32, 16, 8), "PERIODIC", "3"), ((1, 2, 1), (8, 32, 16), "SYMMETRY", "3"),
-                                                   ((1, 1, 2), (8, 16, 32), "PERIODIC", "3"), ((2, 1, 1), (32, 16, 1), "ZEROGRADIENT", "full")])
-def test_two_blocks_through_the_host_runtime_equal_the_single_block_oracle(split, cells, bc, layers, tmp_path):
+@pytest.mark.parametrize("split,cells,bc,layers,visc", [
+    ((2, 1, 1), (32, 16, 8), "PERIODIC", "3", 0), ((1, 2, 1), (8, 32, 16), "SYMMETRY", "3", 0),
+    ((1, 1, 2), (8, 16, 32), "PERIODIC", "3", 0), ((2, 1, 1), (32, 16, 1), "ZEROGRADIENT", "full", 0),
+    # viscous + heat flux: the exchange also carries the EDGE halos next to the shared faces (widened slabs, axis by axis)
+    ((2, 1, 1), (32, 16, 8), "PERIODIC", "3", 1), ((1, 2, 1), (16, 32, 1), "SYMMETRY", "3", 1),
+    ((1, 1, 2), (8, 16, 32), "ZEROGRADIENT", "3", 1)])
+def test_two_blocks_through_the_host_runtime_equal_the_single_block_oracle(split, cells, bc, layers, visc, tmp_path):
     worker = tmp_path / "worker.py"
     worker.write_text(WORKER)
-    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="2",
+    env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="2", JXF_VISC=str(visc),
                JXF_CELLS=",".join(map(str, cells)), JXF_EXCHANGE_LAYERS=layers, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
     port_no = 29700 + (os.getpid() + sum(cells) + len(bc)) % 200
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
@@ -264,9 +323,13 @@ def test_two_blocks_through_the_host_runtime_equal_the_single_block_oracle(split
     res = json.loads(lines[-1][7:])
     assert res["equal"] and res["dt_equal"] and res["t_equal"], res
     assert res["halo_equal"], "halos of the returned buffers are not complete"
-    nl = 5 if layers == "full" else int(layers)
+    nl = 5 if (layers == "full" or visc) else int(layers)
     for calls, nbrs, overlap in zip(res["calls"], res["neighbors"], res["overlap"]):
-        assert overlap and len(nbrs) >= 1
+        assert len(nbrs) >= 1
+        if visc:                         # full slabs every stage, no overlap on this path
+            assert not overlap and set(calls["pack"]) == {5} and calls["stage_tail"] == 0
+            continue
+        assert overlap
         # between stages only `nl` layers travel; the hand-over to the user ships all five
         assert set(calls["pack"]) <= {nl, 5} and nl in calls["pack"] and 5 in calls["pack"]
         assert calls["pack"] == calls["unpack"] or sorted(calls["pack"]) == sorted(calls["unpack"])
