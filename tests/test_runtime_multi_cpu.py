@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the WHOLE host side of the multi-block path -- InputManager -> InitializationManager ->
+"""CPU, world_size 2 and 4 over gloo: the WHOLE host side of the multi-block path -- InputManager -> InitializationManager ->
 SimulationManager.simulate -> BlockRuntime with two blocks: NEIGHBOR faces, the 3-layer stage exchange with lazy halo
 completion, the split first sweep of the overlap branch (interior range, then the strips next to the shared faces), the
 MAX all-reduce of the step scalars ordered after the exchange -- with the CUDA solver replaced by an oracle-backed stand-in
@@ -308,14 +308,18 @@ dist.destroy_process_group()
     ((1, 1, 2), (8, 16, 32), "PERIODIC", "3", 0), ((2, 1, 1), (32, 16, 1), "ZEROGRADIENT", "full", 0),
     # viscous + heat flux: the exchange also carries the EDGE halos next to the shared faces (widened slabs, axis by axis)
     ((2, 1, 1), (32, 16, 8), "PERIODIC", "3", 1), ((1, 2, 1), (16, 32, 1), "SYMMETRY", "3", 1),
-    ((1, 1, 2), (8, 16, 32), "ZEROGRADIENT", "3", 1)])
+    ((1, 1, 2), (8, 16, 32), "ZEROGRADIENT", "3", 1),
+    # four blocks (pencils): two split axes -- with the dissipative fluxes the edge halos at the line where four blocks meet
+    # come from the DIAGONAL neighbour in two hops (x exchange, then y exchange over the halos x just filled)
+    ((2, 2, 1), (16, 16, 8), "PERIODIC", "3", 0), ((2, 2, 1), (16, 16, 8), "PERIODIC", "3", 1),
+    ((2, 2, 1), (32, 16, 1), "SYMMETRY", "3", 1)])
 def test_two_blocks_through_the_host_runtime_equal_the_single_block_oracle(split, cells, bc, layers, visc, tmp_path):
     worker = tmp_path / "worker.py"
     worker.write_text(WORKER)
     env = dict(os.environ, JXF_ROOT=ROOT, JXF_SPLIT=",".join(map(str, split)), JXF_BC=bc, JXF_STEPS="2", JXF_VISC=str(visc),
                JXF_CELLS=",".join(map(str, cells)), JXF_EXCHANGE_LAYERS=layers, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
     port_no = 29700 + (os.getpid() + sum(cells) + len(bc)) % 200
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={split[0] * split[1] * split[2]}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port_no), str(worker)],
                          env=env, capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
