@@ -50,3 +50,38 @@ def test_global_names_resolve(modname):
                     and not ins.argval.startswith("__"):
                 missing.append((code.co_name, ins.argval, ins.positions.lineno if ins.positions else None))
     assert not missing, f"unresolved names in {modname}: {missing}"
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under jaxfluids_b200/ (Python or CUDA sources) imports, names or opens
+    anything under oracle/; bench.py may -- in its CPU legs only (cpu_reference_run)."""
+    import ast
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "jaxfluids_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+            assert not re.search(r"\b(import|from)\s+oracle\b", text), f
+            assert "oracle/" not in text and "port_mt" not in text and "refharness" not in text, f
+    # bench.py: every use of the oracle sits inside cpu_reference_run (the cpu_baseline / --impl reference legs) or the
+    # parity leg, which runs BEFORE the timed region as the checker
+    tree = ast.parse(open(os.path.join(root, "bench.py"), encoding="utf-8").read())
+    allowed = {"cpu_reference_run", "parity_leg", "_oracle_tgv", "_oracle_hit"}     # the helpers of those two legs
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            names = [a.name for a in node.names] + [getattr(node, "module", "") or ""]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                owner = next((fn.name for fn in ast.walk(tree) if isinstance(fn, ast.FunctionDef)
+                              and any(child is node for child in ast.walk(fn))), None)
+                assert owner in allowed, f"bench.py imports the oracle in {owner}"
+    # ... and those helpers are reached from the two legs only
+    src = open(os.path.join(root, "bench.py"), encoding="utf-8").read()
+    for helper in ("_oracle_tgv", "_oracle_hit"):
+        for fn in ast.walk(tree):
+            if isinstance(fn, ast.FunctionDef) and fn.name not in allowed:
+                body = ast.get_source_segment(src, fn) or ""
+                assert helper + "(" not in body and ("= " + helper) not in body, (fn.name, helper)
