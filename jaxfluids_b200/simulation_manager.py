@@ -57,6 +57,10 @@ class SpaceSolver:
                     interface_velocity=None, interface_pressure=None, solid_velocity=None, solid_temperature=None,
                     interface_cells=None, forcing_buffers=None, ml_setup=None, is_feed_forward=False
                     ) -> Tuple[IntegrationBuffers, PositivityCounter, DiscretizationCounter]:
+        """space_solver.py:151-453.  `conservatives` is not read: on this path the reference uses it for the volume forces
+        and the positivity flux limiter only (:378-384, :532-543), where it is U(primitives) -- the kernels form those
+        values from `primitives` themselves (same arithmetic as equation_manager.get_conservatives_from_primitives).  A
+        caller that passes conservatives inconsistent with its primitives gets the primitives' answer."""
         with self._timestep(physical_timestep_size):
             rhs = self._rt.solver.compute_rhs(primitives)
         return (IntegrationBuffers(EulerIntegrationBuffers(rhs, None, None, None)), PositivityCounter(),
