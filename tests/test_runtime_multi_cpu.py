@@ -1,4 +1,4 @@
-"""CPU, world_size 2 and 4 over gloo: the WHOLE host side of the multi-block path -- InputManager -> InitializationManager ->
+"""CPU, world_size 2, 4 and 8 over gloo: the WHOLE host side of the multi-block path -- InputManager -> InitializationManager ->
 SimulationManager.simulate -> BlockRuntime with two blocks: NEIGHBOR faces, the 3-layer stage exchange with lazy halo
 completion, the split first sweep of the overlap branch (interior range, then the strips next to the shared faces), the
 MAX all-reduce of the step scalars ordered after the exchange -- with the CUDA solver replaced by an oracle-backed stand-in
@@ -312,7 +312,9 @@ dist.destroy_process_group()
     # four blocks (pencils): two split axes -- with the dissipative fluxes the edge halos at the line where four blocks meet
     # come from the DIAGONAL neighbour in two hops (x exchange, then y exchange over the halos x just filled)
     ((2, 2, 1), (16, 16, 8), "PERIODIC", "3", 0), ((2, 2, 1), (16, 16, 8), "PERIODIC", "3", 1),
-    ((2, 2, 1), (32, 16, 1), "SYMMETRY", "3", 1)])
+    ((2, 2, 1), (32, 16, 1), "SYMMETRY", "3", 1),
+    # eight blocks: every block has three neighbours, the edge halos of the dissipative stencils cross all three axes
+    ((2, 2, 2), (16, 16, 16), "PERIODIC", "3", 0), ((2, 2, 2), (16, 16, 16), "SYMMETRY", "3", 1)])
 def test_two_blocks_through_the_host_runtime_equal_the_single_block_oracle(split, cells, bc, layers, visc, tmp_path):
     worker = tmp_path / "worker.py"
     worker.write_text(WORKER)
